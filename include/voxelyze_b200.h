@@ -1,0 +1,281 @@
+/*
+ * voxelyze_b200.h -- C-ABI of the B200-native explicit dynamics step.
+ *
+ * This is the drop-in boundary for ONE hot path of jonhiller/Voxelyze:
+ *     CVoxelyze::doTimeStep            (reference src/Voxelyze.cpp:251-284)
+ * and the calls that feed it / read from it.  The reference has no FFI layer of
+ * its own: its contract is the public C++ class API.  The C++
+ * facade in voxelyze_b200/facade/ re-creates that class API (CVoxelyze,
+ * CVX_Material, CVX_Voxel, CVX_Link, CVX_External, CVX_Collision) on top of the
+ * entry points declared here; nothing else crosses the host/device boundary.
+ *
+ * Rules of the boundary
+ *   - extern "C", plain pointers and sizes only.  No C++/torch types.
+ *   - every function returns an int status (VX_OK == 0) unless noted.
+ *   - the caller owns all host buffers; the library owns all device memory.
+ *   - one caller thread per vx_sim handle (the reference is not thread safe either,
+ *     include/Voxelyze.h:134).
+ *   - there is NO CPU fallback: the CUDA build of this library fails with
+ *     VX_ERR_NO_DEVICE when no sm_100 device is usable.
+ *
+ * Three shared objects implement exactly this header:
+ *   voxelyze_b200/lib/libvoxelyze_b200.so   the product (hand written sm_100a CUDA)
+ *   oracle/liboracle_port.so                CPU restatement, test infrastructure only
+ *   oracle/_ref/libvxref.so                 the unmodified reference behind a shim,
+ *                                           test infrastructure only
+ * so a parity test is "same calls, two libraries, compare downloads".
+ *
+ * Index conventions
+ *   voxel index  = position in the array handed to vx_set_voxels (the reference's
+ *                  voxelsList order, i.e. setVoxel call order; Voxelyze.cpp:446).
+ *   link index   = the order in which the reference would have created the links for
+ *                  that setVoxel sequence (Voxelyze.cpp:453-455,508-539): for every
+ *                  voxel in order, for dir = X+,X-,Y+,Y-,Z+,Z-, a link to an already
+ *                  existing neighbour.  Query it with vx_get_links.
+ *   link direction / slot numbering follows CVX_Voxel::linkDirection
+ *                  (include/VX_Voxel.h:39-46): 0 X+, 1 X-, 2 Y+, 3 Y-, 4 Z+, 5 Z-.
+ *   quaternions are stored (w, x, y, z) like Quat3D (include/Quat3D.h:44-49).
+ */
+#ifndef VOXELYZE_B200_H
+#define VOXELYZE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VX_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define VX_OK              0
+#define VX_DIVERGED        1  /* vx_step: a link strain exceeded 100 (Voxelyze.cpp:265-269) */
+#define VX_ERR_ARG        -1
+#define VX_ERR_NO_DEVICE  -2
+#define VX_ERR_CUDA       -3
+#define VX_ERR_MATERIAL   -4  /* material model rejected (VX_Material.cpp:283-434) */
+#define VX_ERR_TOPOLOGY   -5
+#define VX_ERR_UNSUPPORTED -6
+#define VX_ERR_ALLOC      -7
+
+typedef struct vx_sim vx_sim;
+
+/* ---- materials ---------------------------------------------------------- */
+/* Raw, user level description of one voxel material == what a caller sets through
+ * CVX_Material (include/VX_Material.h:33-103).  The library derives the cached
+ * constants of CVX_MaterialVoxel::updateDerived (src/VX_MaterialVoxel.cpp:57-79)
+ * and builds one combined link material per adjacent pair exactly like
+ * CVoxelyze::combinedMaterial / CVX_MaterialLink::updateAll
+ * (src/Voxelyze.cpp:626-640, src/VX_MaterialLink.cpp:45-141).                     */
+#define VX_MODEL_LINEAR   0   /* setModelLinear(E, fail_stress)                    */
+#define VX_MODEL_BILINEAR 1   /* setModelBilinear(E, plastic_modulus, yield, fail) */
+#define VX_MODEL_DATA     2   /* setModel(n_points, strain, stress)                */
+
+typedef struct vx_material_desc {
+    int32_t model;            /* VX_MODEL_*                                            */
+    float   youngs_modulus;   /* Pa; LINEAR / BILINEAR                                  */
+    float   plastic_modulus;  /* Pa; BILINEAR                                           */
+    float   yield_stress;     /* Pa; BILINEAR                                           */
+    float   fail_stress;      /* Pa; LINEAR / BILINEAR; -1 = no failure                 */
+    int32_t n_points;         /* DATA: number of (strain, stress) points               */
+    const float* strain;      /* DATA                                                   */
+    const float* stress;      /* DATA                                                   */
+    float   density;          /* kg/m^3                                                 */
+    float   poissons_ratio;
+    float   cte;              /* coefficient of thermal expansion, 1/degC               */
+    float   mu_static;
+    float   mu_kinetic;
+    float   zeta_internal;    /* default 1 (VX_Material.cpp:65)                         */
+    float   zeta_global;
+    float   zeta_collision;
+    double  ext_scale[3];     /* setExternalScaleFactor, default (1,1,1)                */
+} vx_material_desc;
+
+/* Derived voxel-material constants, for accessors and tests (all float like the
+ * reference, except the two sizes).                                                */
+typedef struct vx_voxmat_row {
+    double nom_size;
+    double size[3];           /* nom_size * ext_scale                                   */
+    float  E, nu, rho, cte, mu_static, mu_kinetic;
+    float  zeta_internal, zeta_global, zeta_collision;
+    float  e_hat;
+    float  mass, mass_inv, sqrt_mass, first_moment;
+    float  moment_inertia, moment_inertia_inv;
+    float  two_sq_m_e_s;      /* _2xSqMxExS                                              */
+    float  two_sq_i_e_s3;     /* _2xSqIxExSxSxS                                          */
+    float  eps_yield, eps_fail, sigma_yield, sigma_fail;
+    int32_t linear;
+    int32_t n_curve;          /* number of model data points incl. the (0,0) point     */
+} vx_voxmat_row;
+
+/* Derived link-material constants (CVX_MaterialLink, include/VX_MaterialLink.h:34-43). */
+typedef struct vx_linkmat_row {
+    int32_t mat_a, mat_b;     /* constituent voxel materials (a <= b)                   */
+    int32_t linear;
+    int32_t n_curve;
+    float  E, nu, e_hat;
+    float  eps_yield, eps_fail, sigma_yield, sigma_fail;
+    float  a1, a2, b1, b2, b3;
+    float  sq_a1, sq_a2_ip, sq_b1, sq_b2_fmp, sq_b3_ip;
+} vx_linkmat_row;
+
+/* ---- state fields for upload / download --------------------------------- */
+/* Voxel fields are indexed by voxel index, link fields by link index.             */
+enum vx_field {
+    /* voxel, double */
+    VX_F_POS = 0,            /* 3 doubles / voxel  CVX_Voxel::pos     VX_Voxel.h:163  */
+    VX_F_ORIENT = 1,         /* 4 doubles (w,x,y,z)          orient   VX_Voxel.h:165  */
+    VX_F_LINMOM = 2,         /* 3 doubles                    linMom   VX_Voxel.h:164  */
+    VX_F_ANGMOM = 3,         /* 3 doubles                    angMom   VX_Voxel.h:166  */
+    /* voxel, 32 bit */
+    VX_F_TEMP = 4,           /* 1 float                      temp     VX_Voxel.h:171  */
+    VX_F_VOXFLAGS = 5,       /* 1 uint32, VX_VF_* bits                                 */
+    VX_F_PSTRAIN = 6,        /* 3 floats, cached poissons strain      VX_Voxel.h:179  */
+    /* link, double */
+    VX_F_FORCE_NEG = 16,     /* 3 doubles / link             forceNeg VX_Link.h:71    */
+    VX_F_FORCE_POS = 17,
+    VX_F_MOMENT_NEG = 18,
+    VX_F_MOMENT_POS = 19,
+    VX_F_POS2 = 20,          /* 3 doubles                    pos2     VX_Link.h:101   */
+    VX_F_ANGLE1V = 21,
+    VX_F_ANGLE2V = 22,
+    /* link, 32 bit */
+    VX_F_STRAIN = 24,        /* float                        strain   VX_Link.h:74    */
+    VX_F_MAXSTRAIN = 25,
+    VX_F_STRAINOFFSET = 26,
+    VX_F_STRESS = 27,        /* float                        _stress  VX_Link.h:107   */
+    VX_F_LINKFLAGS = 28      /* uint32, VX_LF_* bits                                   */
+};
+
+/* voxel flag bits (download) */
+#define VX_VF_STATIC_FRICTION 0x1u  /* FLOOR_STATIC_FRICTION, VX_Voxel.h:146          */
+#define VX_VF_SURFACE         0x2u  /* fewer than 6 links, VX_Voxel.cpp:376-381       */
+#define VX_VF_GHOST           0x4u  /* z-slab halo copy: pose is imported, never integrated */
+/* link flag bits (download) */
+#define VX_LF_SMALL_ANGLE     0x1u  /* CVX_Link::smallAngle, VX_Link.h:103            */
+#define VX_LF_LOCAL_VEL_VALID 0x2u  /* LOCAL_VELOCITY_VALID, VX_Link.h:80             */
+#define VX_LF_YIELDED         0x4u  /* CVX_Link::isYielded, VX_Link.cpp:127-130       */
+#define VX_LF_FAILED          0x8u  /* CVX_Link::isFailed,  VX_Link.cpp:132-135       */
+
+/* degrees of freedom, identical to dofComponent (include/VX_External.h:18-26) */
+#define VX_DOF_TX 0x01
+#define VX_DOF_TY 0x02
+#define VX_DOF_TZ 0x04
+#define VX_DOF_RX 0x08
+#define VX_DOF_RY 0x10
+#define VX_DOF_RZ 0x20
+#define VX_DOF_ALL 0x3F
+
+/* ---- life cycle ---------------------------------------------------------- */
+/* replaces CVoxelyze::CVoxelyze(double voxelSize)      include/Voxelyze.h:69.
+ * device = CUDA ordinal (ignored by the CPU oracles).                               */
+int  vx_create(double voxel_size, int device, vx_sim** out);
+/* replaces CVoxelyze::~CVoxelyze / clear()             src/Voxelyze.cpp:323-355     */
+void vx_destroy(vx_sim* s);
+/* human readable text of the last failure on this handle (never NULL)              */
+const char* vx_last_error(const vx_sim* s);
+/* "cuda-sm100a", "oracle-port" or "reference" */
+const char* vx_backend(void);
+int  vx_abi_version(void);
+
+/* ---- model definition ---------------------------------------------------- */
+/* replaces CVoxelyze::addMaterial + CVX_Material setters (src/Voxelyze.cpp:357-382,
+ * src/VX_Material.cpp:283-523).  May be called again between steps with the same
+ * count to change properties mid-run (test/tVoxelyze.h:356); dynamic state is kept. */
+int  vx_set_materials(vx_sim* s, int n, const vx_material_desc* descs);
+int  vx_get_voxmat(const vx_sim* s, int mat, vx_voxmat_row* out);
+/* link material for the unordered pair (mat_a, mat_b); derived on demand.           */
+int  vx_get_linkmat(vx_sim* s, int mat_a, int mat_b, vx_linkmat_row* out);
+/* model data points of the link material (strain/stress incl. the zero point)       */
+int  vx_get_linkmat_curve(vx_sim* s, int mat_a, int mat_b, float* strain, float* stress, int cap);
+
+/* replaces the setVoxel() sequence                     src/Voxelyze.cpp:422-461.
+ * ijk: 3*n lattice indices (each must fit a short like the reference,
+ * include/VX_Voxel.h:151); mat: material index per voxel; sim_id: NULL, or an
+ * ensemble member id per voxel -- voxels of different members never link and each
+ * member lives in its own lattice frame (SURVEY.md section 8e "ensemble"); flags: NULL or
+ * VX_VF_GHOST per voxel.  Resets all dynamic state like a fresh CVoxelyze.          */
+int  vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat,
+                   const int32_t* sim_id, const uint32_t* flags);
+int  vx_voxel_count(const vx_sim* s);
+int  vx_link_count(const vx_sim* s);
+/* link list in link-index order: negative-end voxel, positive-end voxel, axis 0..2
+ * (CVX_Link::pVNeg/pVPos/axis, include/VX_Link.h:70,88).  Any pointer may be NULL.  */
+int  vx_get_links(const vx_sim* s, int32_t* v_neg, int32_t* v_pos, uint8_t* axis);
+
+/* replaces CVX_External (include/VX_External.h:45-88) for the listed voxels; voxels
+ * not listed have no external.  dof: VX_DOF_* bits; force/moment: 3 floats each;
+ * translation/rotation: 3 doubles each (rotation is a rotation vector; the library
+ * caches the quaternion like CVX_External::rotationChanged, VX_External.cpp:100-109).
+ * Any of force/moment/translation/rotation may be NULL (= zeros).                    */
+int  vx_set_externals(vx_sim* s, int n, const int32_t* voxel, const uint8_t* dof,
+                      const float* force, const float* moment,
+                      const double* translation, const double* rotation);
+
+/* replaces setGravity / enableFloor / enableCollisions (src/Voxelyze.cpp:596-622)   */
+int  vx_set_gravity(vx_sim* s, float g);
+int  vx_enable_floor(vx_sim* s, int enabled);
+int  vx_enable_collisions(vx_sim* s, int enabled);
+/* CVX_Collision::envelopeRadius (static, src/VX_Collision.cpp:15)                   */
+int  vx_set_collision_envelope(vx_sim* s, float envelope_radius);
+
+/* replaces CVoxelyze::setAmbientTemperature(t, true) (src/Voxelyze.cpp:585-594):
+ * every voxel takes temperature t.                                                   */
+int  vx_set_temperature_all(vx_sim* s, float t);
+/* per ensemble member: member m takes t[m] (n_members values).                       */
+int  vx_set_temperature_members(vx_sim* s, int n_members, const float* t);
+/* replaces CVX_Voxel::setTemperature per voxel (src/VX_Voxel.cpp:108-114)            */
+int  vx_set_temperature(vx_sim* s, int n, const float* t);
+
+/* ---- the hot path --------------------------------------------------------- */
+/* replaces CVoxelyze::doTimeStep(dt) called n_steps times (src/Voxelyze.cpp:251-284).
+ * dt < 0: use vx_recommended_dt() each step (reference default argument).
+ * Returns VX_OK, or VX_DIVERGED with *diverged_step (may be NULL) = number of steps
+ * completed before the diverging one; like the reference, on the diverging step the
+ * links are updated but the voxels are not advanced, and no later step is run.       */
+int  vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step);
+/* replaces CVoxelyze::recommendedTimeStep()           src/Voxelyze.cpp:286-311      */
+int  vx_recommended_dt(vx_sim* s, float* dt);
+/* replaces CVoxelyze::resetTime()                     src/Voxelyze.cpp:313-321      */
+int  vx_reset(vx_sim* s);
+/* simulated time (float accumulation like currentTime, Voxelyze.cpp:282)            */
+float vx_time(const vx_sim* s);
+
+/* ---- state access ---------------------------------------------------------- */
+/* Copies elements [first, first+count) of a field to/from host memory.  Element
+ * sizes are given at enum vx_field.  Download waits for all queued steps.            */
+int  vx_download(vx_sim* s, int field, int first, int count, void* dst);
+int  vx_upload(vx_sim* s, int field, int first, int count, const void* src);
+
+/* replaces CVoxelyze::collisionList() (include/Voxelyze.h:115): watched pairs as
+ * (voxel1, voxel2) voxel indices with voxel1 < voxel2, in creation order
+ * (src/Voxelyze.cpp:730-747).  pairs may be NULL to query the count.                 */
+int  vx_collision_pairs(vx_sim* s, int32_t* pairs, int cap, int* n_pairs);
+
+/* replaces CVoxelyze::stateInfo (src/Voxelyze.cpp:752-800); info/type use the
+ * reference's enum values (include/Voxelyze.h:48-67).                                */
+int  vx_state_info(vx_sim* s, int info, int type, float* out);
+
+/* ---- device side hooks (CUDA build only; oracles return VX_ERR_UNSUPPORTED) -- */
+/* run all work of this handle on the given cudaStream_t (as an integer); 0 = the
+ * library's own stream.  Lets a caller order NCCL halo traffic with the step.        */
+int  vx_set_stream(vx_sim* s, uint64_t cuda_stream);
+/* z-slab halo exchange support: device address and element
+ * range of the packed pose records of all voxels with lattice z == iz, so that one
+ * plane can be sent/received as one contiguous message.  rec_bytes is the record
+ * size (64).                                                                          */
+int  vx_pose_plane(vx_sim* s, int iz, uint64_t* dev_ptr0, uint64_t* dev_ptr1,
+                   int* count, int* rec_bytes);
+/* number of kernels this handle has launched so far (bench.py "gpu_launches").       */
+int64_t vx_launch_count(const vx_sim* s);
+/* block until all queued work of this handle is done.                                */
+int  vx_sync(vx_sim* s);
+/* select kernel variant: 0 = auto, 1 = general two-kernel path, 2 = fused lattice
+ * path (dense boxes).  For tests and ablations.                                       */
+int  vx_set_path(vx_sim* s, int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXELYZE_B200_H */
