@@ -262,15 +262,26 @@ int  vx_state_info(vx_sim* s, int info, int type, float* out);
  * library's own stream.  Lets a caller order NCCL halo traffic with the step.        */
 int  vx_set_stream(vx_sim* s, uint64_t cuda_stream);
 /* z-slab halo exchange support: device address and element
- * range of the packed pose records of all voxels with lattice z == iz, so that one
- * plane can be sent/received as one contiguous message.  rec_bytes is the record
- * size (64).                                                                          */
+ * range of the two packed pose record arrays (pose0: pos.xyz+orient.w, pose1:
+ * orient.xyz+meta) of all voxels with lattice z == iz, so that one plane can be
+ * sent/received as two contiguous messages.  rec_bytes is the record size (32).                                                                         */
 int  vx_pose_plane(vx_sim* s, int iz, uint64_t* dev_ptr0, uint64_t* dev_ptr1,
                    int* count, int* rec_bytes);
+/* stores `count` received pose records (two arrays in the vx_pose_plane layout, device
+ * addresses) into the ghost voxels of layer iz: position and orientation are replaced,
+ * the receiving voxel keeps its own flag word (it stays a ghost) and takes the sender's
+ * temperature.                                                                        */
+int  vx_halo_import(vx_sim* s, int iz, uint64_t src_ptr0, uint64_t src_ptr1, int count);
 /* number of kernels this handle has launched so far (bench.py "gpu_launches").       */
 int64_t vx_launch_count(const vx_sim* s);
 /* block until all queued work of this handle is done.                                */
 int  vx_sync(vx_sim* s);
+/* measurement hook for bench.py: runs n_steps steps one launch at a time with CUDA events
+ * around each kernel group on the launching stream and returns accumulated device
+ * milliseconds: ms[0] link-force kernels, ms[1] voxel-integrate kernel, ms[2] everything
+ * else (Poisson pre-pass, collisions), ms[3] whole steps; launches[0..2] = kernel launches
+ * per group.  Same arithmetic as vx_step.                                                 */
+int  vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches);
 /* select kernel variant: 0 = auto, 1 = general two-kernel path, 2 = fused lattice
  * path (dense boxes).  For tests and ablations.                                       */
 int  vx_set_path(vx_sim* s, int path);

@@ -402,8 +402,10 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
 
 int vx_set_stream(vx_sim*, uint64_t) { return VX_ERR_UNSUPPORTED; }
 int vx_pose_plane(vx_sim*, int, uint64_t*, uint64_t*, int*, int*) { return VX_ERR_UNSUPPORTED; }
+int vx_halo_import(vx_sim*, int, uint64_t, uint64_t, int) { return VX_ERR_UNSUPPORTED; }
 int64_t vx_launch_count(const vx_sim*) { return 0; }
 int vx_sync(vx_sim*) { return VX_OK; }
 int vx_set_path(vx_sim*, int) { return VX_OK; }
+int vx_step_profile(vx_sim*, float, int, float*, int*) { return VX_ERR_UNSUPPORTED; }
 
 } // extern "C"

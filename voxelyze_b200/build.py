@@ -1,0 +1,71 @@
+"""In-tree builds: the CUDA product library and (separately) the oracle checkers.
+
+    python -m voxelyze_b200.build            # product + oracles
+    python -m voxelyze_b200.build product    # libvoxelyze_b200.so only
+
+nvcc cross-compiles for sm_100a without a GPU; the resulting .so files are git-ignored but
+travel to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "voxelyze_b200", "csrc")
+LIBDIR = os.path.join(ROOT, "voxelyze_b200", "lib")
+PRODUCT_SO = os.path.join(LIBDIR, "libvoxelyze_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    # the reference is built without FMA contraction (x86-64 baseline); parity needs the same
+    "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-diag-suppress", "177",
+]
+
+
+def _host_cxx() -> str:
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+
+
+def _newer(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources if os.path.exists(s))
+
+
+def product_sources():
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    srcs.append(os.path.join(ROOT, "include", "voxelyze_b200.h"))
+    return srcs
+
+
+def build_product(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    if not force and _newer(PRODUCT_SO, product_sources()):
+        return PRODUCT_SO
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, *NVCC_FLAGS, "-ccbin", _host_cxx(), "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+           "-o", PRODUCT_SO, os.path.join(CSRC, "vx_capi.cu")]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    subprocess.run(cmd, check=True)
+    return PRODUCT_SO
+
+
+def build_oracles() -> None:
+    """Builds the checkers (oracle port always; oracle/_ref only where /root/reference exists)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port", "ref"], check=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "product"):
+        print(build_product(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if what in ("all", "oracle"):
+        build_oracles()

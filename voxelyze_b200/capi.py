@@ -155,9 +155,11 @@ class VxLib:
             "vx_state_info": (i32, [vp, i32, i32, P(f32)]),
             "vx_set_stream": (i32, [vp, u64]),
             "vx_pose_plane": (i32, [vp, i32, P(u64), P(u64), P(i32), P(i32)]),
+            "vx_halo_import": (i32, [vp, i32, u64, u64, i32]),
             "vx_launch_count": (C.c_int64, [vp]),
             "vx_sync": (i32, [vp]),
             "vx_set_path": (i32, [vp, i32]),
+            "vx_step_profile": (i32, [vp, f32, i32, P(f32), P(i32)]),
         }
         self.symbols = list(sig)
         for name, (res, args) in sig.items():
@@ -350,11 +352,21 @@ class Sim:
         self._chk(self.L.lib.vx_pose_plane(self.h, iz, C.byref(p0), C.byref(p1), C.byref(n), C.byref(rb)))
         return p0.value, p1.value, n.value, rb.value
 
+    def halo_import(self, iz: int, ptr0: int, ptr1: int, count: int):
+        self._chk(self.L.lib.vx_halo_import(self.h, iz, ptr0, ptr1, count))
+
     def launch_count(self) -> int:
         return self.L.lib.vx_launch_count(self.h)
 
     def sync(self):
         self._chk(self.L.lib.vx_sync(self.h))
+
+    def step_profile(self, dt: float, n: int):
+        """Event-timed steps: returns ({'link','voxel','other','step'} ms totals, launches per group)."""
+        ms = (C.c_float * 4)()
+        ln = (C.c_int * 3)()
+        self._chk(self.L.lib.vx_step_profile(self.h, dt, n, ms, ln), ok=(VX_OK, VX_DIVERGED))
+        return dict(link=ms[0], voxel=ms[1], other=ms[2], step=ms[3]), list(ln)
 
     def set_path(self, path: int):
         self._chk(self.L.lib.vx_set_path(self.h, path))

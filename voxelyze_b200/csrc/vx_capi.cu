@@ -1,0 +1,846 @@
+// vx_capi.cu -- implementation of include/voxelyze_b200.h for sm_100a (the product).
+//
+// Host side of the drop-in boundary: owns the device-resident structure-of-arrays state of
+// one simulation, translates the flat model description into it, and drives the kernels of
+// vx_kernels.cuh (general path) / vx_lattice.cuh (fused dense-lattice path).
+// There is deliberately no CPU code path for stepping: without a usable CUDA device
+// vx_create fails with VX_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "voxelyze_b200.h"
+#include "vx_material.hpp"
+#include "vx_kernels.cuh"
+
+using namespace vxd;
+
+namespace {
+
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct LinkMatEntry { int a, b; vxm::Material mat; };
+
+constexpr int GRAPH_STEPS = 16;     // steps per captured CUDA graph
+constexpr int TPB = 128;
+
+inline int blocks_for(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+
+} // namespace
+
+struct vx_sim {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    double vox_size = 0.001;
+    std::string err;
+
+    // ---- model (host)
+    std::vector<vx_material_desc> descs; std::vector<std::vector<float>> d_eps, d_sig;
+    std::vector<vxm::Material> mats;
+    std::vector<LinkMatEntry> lmats; std::map<std::pair<int, int>, int> lmat_of;
+    bool any_poisson = false;
+
+    int N = 0, L = 0, n_members = 1;
+    std::vector<int32_t> ijk; std::vector<uint16_t> vmat_id; std::vector<int32_t> member; std::vector<uint32_t> vflags;
+    std::vector<int32_t> lk_vn, lk_vp; std::vector<uint8_t> lk_axis;   // caller (creation) order, caller voxel indices
+    std::vector<int32_t> v_e2i, v_i2e, l_e2i, l_i2e;
+    std::vector<uint8_t> linkmask;                                     // by caller voxel index
+    std::vector<uint16_t> lk_mat;                                      // by internal link index
+    int axis_first[4] = {0, 0, 0, 0};
+    std::vector<int64_t> sort_key;                                     // by internal voxel index: (member,z) key for plane lookup
+
+    // externals (host copy, caller voxel indices)
+    std::vector<int32_t> ext_vox; std::vector<DevExt> ext_rows;
+
+    float grav = 0.f, ambient = 0.f, envelope = 0.625f;
+    bool floor_on = false, collisions = false;
+    float time_host = 0.f;
+    int path = 0;
+
+    // ---- device
+    DevBuf<double4> pose0, pose1, mom0; DevBuf<double2> mom1;
+    DevBuf<int> ext_idx, ext_vox_dev, vox_e2i_dev, link_e2i_dev, member_dev;
+    DevBuf<float4> pstrain; DevBuf<double> slots; DevBuf<float> slot_strain;
+    DevBuf<int2> lends; DevBuf<uint32_t> lmeta; DevBuf<double4> lstA, lstB; DevBuf<double> lstC; DevBuf<float4> lstrain;
+    DevBuf<DevVoxMat> vmat_dev; DevBuf<DevLinkMat> lmat_dev; DevBuf<float> curve_e, curve_s;
+    DevBuf<DevExt> ext_dev;
+    DevBuf<DevParams> params; DevBuf<unsigned int> freq2; DevBuf<float> member_t;
+    DevBuf<unsigned char> staging;
+    DevParams* params_host = nullptr;     // pinned mirror
+    unsigned int* freq_host = nullptr;    // pinned
+
+    cudaGraphExec_t graph = nullptr; int graph_kernels = 0;
+    int64_t launches = 0;
+
+    Frame frame() const
+    {
+        Frame f{};
+        f.n_vox = N; f.n_link = L;
+        f.pose0 = pose0.p; f.pose1 = pose1.p; f.mom0 = mom0.p; f.mom1 = mom1.p;
+        f.ext_idx = ext_idx.p; f.pstrain = pstrain.p; f.slots = slots.p; f.slot_strain = slot_strain.p;
+        f.lends = lends.p; f.lmeta = lmeta.p; f.lstA = lstA.p; f.lstB = lstB.p; f.lstC = lstC.p; f.lstrain = lstrain.p;
+        f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
+        f.ext = ext_dev.p; f.params = params.p;
+        f.col_start = nullptr; f.col_ref = nullptr; f.col_force = nullptr;
+        return f;
+    }
+    void drop_graph() { if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; } }
+};
+
+static int fail(vx_sim* s, int code, const std::string& msg) { if (s) s->err = msg; return code; }
+static int cuda_fail(vx_sim* s, cudaError_t e, const char* what)
+{
+    if (s) s->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return VX_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(s, e_, #call); } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// material tables
+static int link_material(vx_sim* s, int a, int b)
+{
+    std::pair<int, int> key(std::min(a, b), std::max(a, b));
+    auto it = s->lmat_of.find(key);
+    if (it != s->lmat_of.end()) return it->second;
+    LinkMatEntry e; e.a = key.first; e.b = key.second;
+    e.mat = vxm::combine(s->mats[key.first], s->mats[key.second]);
+    s->lmats.push_back(e);
+    int id = (int)s->lmats.size() - 1;
+    s->lmat_of[key] = id;
+    return id;
+}
+
+static int upload_tables(vx_sim* s)
+{
+    CK(cudaSetDevice(s->device));
+    std::vector<DevVoxMat> vm(s->mats.size());
+    s->any_poisson = false;
+    for (size_t i = 0; i < vm.size(); i++) {
+        const vxm::Material& m = s->mats[i];
+        vxm::MassProps p = vxm::mass_props(m, s->vox_size);
+        DevVoxMat& d = vm[i];
+        for (int a = 0; a < 3; a++) d.size[a] = s->vox_size * m.ext_scale[a];
+        d.nom = s->vox_size;
+        d.cte = m.cte; d.mass = p.mass; d.mass_inv = p.mass_inv; d.inertia_inv = p.inertia_inv;
+        d.E = m.E; d.nu = m.nu;
+        d.two_sqrtm_zeta = 2 * p.sqrt_mass * m.zeta_int;
+        d.glob_damp_t = m.zeta_glob * p.two_sq_mes;
+        d.glob_damp_r = m.zeta_glob * p.two_sq_ies3;
+        d.coll_damp_t = m.zeta_coll * p.two_sq_mes;
+        d.pen_stiff = (float)(2 * m.E * s->vox_size);
+        d.mu_s = m.mu_s; d.mu_k = m.mu_k;
+        d.gravity_force = -p.mass * 9.80665f * s->grav;
+        d.nom_f = (float)s->vox_size;
+        d.pad = 0;
+        if (m.nu != 0.0f) s->any_poisson = true;
+    }
+    std::vector<DevLinkMat> lm(s->lmats.size());
+    std::vector<float> ce, cs;
+    for (size_t i = 0; i < lm.size(); i++) {
+        LinkMatEntry& e = s->lmats[i];
+        e.mat = vxm::combine(s->mats[e.a], s->mats[e.b]);
+        const vxm::Material& m = e.mat;
+        vxm::BeamConsts k = vxm::beam_consts(m, s->vox_size);
+        DevLinkMat& d = lm[i];
+        d.linear = m.linear ? 1 : 0;
+        d.curve_off = (int)ce.size(); d.curve_n = (int)m.eps.size();
+        ce.insert(ce.end(), m.eps.begin(), m.eps.end());
+        cs.insert(cs.end(), m.sig.begin(), m.sig.end());
+        d.E = m.E; d.nu = m.nu; d.e_hat = m.e_hat; d.eps_yield = m.eps_yield; d.eps_fail = m.eps_fail;
+        d.a1 = k.a1; d.a2 = k.a2; d.b1 = k.b1; d.b2 = k.b2; d.b3 = k.b3;
+        d.sq_a1 = k.sq_a1; d.sq_a2_ip = k.sq_a2_ip; d.sq_b1 = k.sq_b1; d.sq_b2_fmp = k.sq_b2_fmp; d.sq_b3_ip = k.sq_b3_ip;
+        if (m.nu != 0.0f) s->any_poisson = true;
+    }
+    CK(s->vmat_dev.alloc(std::max<size_t>(vm.size(), 1)));
+    CK(s->lmat_dev.alloc(std::max<size_t>(lm.size(), 1)));
+    CK(s->curve_e.alloc(std::max<size_t>(ce.size(), 2)));
+    CK(s->curve_s.alloc(std::max<size_t>(cs.size(), 2)));
+    CK(cudaStreamSynchronize(s->stream));
+    if (!vm.empty()) CK(cudaMemcpy(s->vmat_dev.p, vm.data(), vm.size() * sizeof(DevVoxMat), cudaMemcpyHostToDevice));
+    if (!lm.empty()) CK(cudaMemcpy(s->lmat_dev.p, lm.data(), lm.size() * sizeof(DevLinkMat), cudaMemcpyHostToDevice));
+    if (!ce.empty()) {
+        CK(cudaMemcpy(s->curve_e.p, ce.data(), ce.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->curve_s.p, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    s->drop_graph();
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// initial dynamic state (fresh CVoxelyze / resetTime)
+static uint32_t initial_bits(const vx_sim* s, int ext_caller)      // ext_caller: caller voxel index
+{
+    uint32_t b = s->vmat_id[ext_caller] & VM_MAT_MASK;
+    b |= (uint32_t)s->linkmask[ext_caller] << VM_LINK_SHIFT;
+    b |= VM_STATIC_FRIC | VM_PSTRAIN_STALE;                         // CVX_Voxel::reset, src/VX_Voxel.cpp:47-56
+    if (!s->vflags.empty() && (s->vflags[ext_caller] & VX_VF_GHOST)) b |= VM_GHOST;
+    return b;
+}
+
+static int upload_initial_state(vx_sim* s, float temp)
+{
+    const int N = s->N, L = s->L;
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    {
+        std::vector<double4> p0(N), p1(N);
+        std::vector<char> has_ext(N, 0);
+        for (int v : s->ext_vox) has_ext[v] = 1;
+        for (int i = 0; i < N; i++) {
+            int e = s->v_i2e[i];
+            double sz = s->vox_size;
+            p0[i] = make_double4(s->ijk[3 * e] * sz, s->ijk[3 * e + 1] * sz, s->ijk[3 * e + 2] * sz, 1.0);
+            uint32_t bits = initial_bits(s, e) | (has_ext[e] ? VM_HAS_EXT : 0u);
+            unsigned long long w = ((unsigned long long)bits << 32);
+            uint32_t tb; memcpy(&tb, &temp, 4); w |= tb;
+            double wd; memcpy(&wd, &w, 8);
+            p1[i] = make_double4(0.0, 0.0, 0.0, wd);
+        }
+        if (N) {
+            CK(cudaMemcpy(s->pose0.p, p0.data(), (size_t)N * sizeof(double4), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(s->pose1.p, p1.data(), (size_t)N * sizeof(double4), cudaMemcpyHostToDevice));
+            CK(cudaMemset(s->mom0.p, 0, (size_t)N * sizeof(double4)));
+            CK(cudaMemset(s->mom1.p, 0, (size_t)N * sizeof(double2)));
+            CK(cudaMemset(s->slots.p, 0, (size_t)N * 36 * sizeof(double)));
+            if (s->pstrain.p) CK(cudaMemset(s->pstrain.p, 0, (size_t)N * sizeof(float4)));
+            if (s->slot_strain.p) CK(cudaMemset(s->slot_strain.p, 0, (size_t)N * 6 * sizeof(float)));
+        }
+    }
+    if (L) {
+        CK(cudaMemset(s->lstA.p, 0, (size_t)L * sizeof(double4)));
+        CK(cudaMemset(s->lstB.p, 0, (size_t)L * sizeof(double4)));
+        CK(cudaMemset(s->lstC.p, 0, (size_t)L * sizeof(double)));
+        CK(cudaMemset(s->lstrain.p, 0, (size_t)L * sizeof(float4)));
+        std::vector<uint32_t> lm(L);
+        for (int i = 0; i < L; i++) lm[i] = s->lk_mat[i] | LM_SMALL_ANGLE;    // CVX_Link::reset, src/VX_Link.cpp:61-75
+        CK(cudaMemcpy(s->lmeta.p, lm.data(), (size_t)L * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    DevParams p{}; p.dt = 0; p.prev_dt = 0; p.time = 0; p.col_stale = 1;
+    CK(cudaMemcpy(s->params.p, &p, sizeof(p), cudaMemcpyHostToDevice));
+    s->time_host = 0.f;
+    return VX_OK;
+}
+
+static int upload_externals(vx_sim* s)
+{
+    if (s->N == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    Frame f = s->frame();
+    k_clear_ext_bits<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++;
+    int n = (int)s->ext_vox.size();
+    if (n) {
+        std::vector<int> internal(n);
+        for (int k = 0; k < n; k++) internal[k] = s->v_e2i[s->ext_vox[k]];
+        CK(s->ext_dev.alloc(n)); CK(s->ext_vox_dev.alloc(n));
+        CK(cudaStreamSynchronize(s->stream));
+        CK(cudaMemcpy(s->ext_dev.p, s->ext_rows.data(), (size_t)n * sizeof(DevExt), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->ext_vox_dev.p, internal.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        f = s->frame();
+        k_set_ext_bits<<<blocks_for(n), TPB, 0, s->stream>>>(f, n, s->ext_vox_dev.p, s->ext_idx.p); s->launches++;
+    }
+    CK(cudaGetLastError());
+    s->drop_graph();      // the ext table pointer may have moved
+    return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stepping
+static void launch_links(vx_sim* s, const Frame& f)
+{
+    const int* af = s->axis_first;
+    const bool P = s->any_poisson;
+    for (int a = 0; a < 3; a++) {
+        int cnt = af[a + 1] - af[a];
+        if (cnt <= 0) continue;
+        int g = blocks_for(cnt);
+        if (a == 0) { if (P) k_link<0, true><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); else k_link<0, false><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); }
+        if (a == 1) { if (P) k_link<1, true><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); else k_link<1, false><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); }
+        if (a == 2) { if (P) k_link<2, true><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); else k_link<2, false><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); }
+        s->launches++;
+    }
+}
+
+static void launch_recommended_dt(vx_sim* s, const Frame& f)
+{
+    cudaMemsetAsync(s->freq2.p, 0, sizeof(unsigned int), s->stream);
+    if (s->L > 0) {
+        int g = std::min(blocks_for(s->L, 256), 148 * 8);
+        k_max_freq<<<g, 256, 0, s->stream>>>(f, s->axis_first[1], s->axis_first[2], s->freq2.p);
+    } else {
+        int g = std::min(blocks_for(s->N, 256), 148 * 8);
+        k_max_freq_voxels<<<g, 256, 0, s->stream>>>(f, s->freq2.p);
+    }
+    s->launches++;
+}
+
+// one doTimeStep (src/Voxelyze.cpp:251-284); per_step_dt: dt < 0 with Poisson materials
+static void launch_step(vx_sim* s, const Frame& f, bool per_step_dt)
+{
+    if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
+    if (per_step_dt) { launch_recommended_dt(s, f); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+    launch_links(s, f);
+    k_voxel<<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0);
+    s->launches++;
+}
+
+__global__ void k_begin(DevParams* p, float dt, int set_dt)
+{
+    p->div_now = 0; p->div_latched = 0; p->steps_done = 0;
+    if (set_dt) p->dt = dt;
+}
+
+static int kernels_per_step(const vx_sim* s)
+{
+    int k = 1;
+    for (int a = 0; a < 3; a++) if (s->axis_first[a + 1] > s->axis_first[a]) k++;
+    if (s->any_poisson) k++;
+    return k;
+}
+
+static int ensure_graph(vx_sim* s)
+{
+    if (s->graph) return VX_OK;
+    Frame f = s->frame();
+    cudaGraph_t g = nullptr;
+    int64_t before = s->launches;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < GRAPH_STEPS; k++) launch_step(s, f, false);
+    cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    s->graph_kernels = (int)(s->launches - before);
+    s->launches = before;
+    if (e != cudaSuccess) return cuda_fail(s, e, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(&s->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { s->graph = nullptr; return cuda_fail(s, e, "cudaGraphInstantiate"); }
+    return VX_OK;
+}
+
+extern "C" {
+
+int vx_abi_version(void) { return VX_ABI_VERSION; }
+const char* vx_backend(void) { return "cuda-sm100a"; }
+
+int vx_create(double voxel_size, int device, vx_sim** out)
+{
+    if (!out) return VX_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return VX_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return VX_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return VX_ERR_NO_DEVICE;   // sm_100a code only
+    vx_sim* s = new vx_sim;
+    s->device = device; s->vox_size = voxel_size;
+    if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return VX_ERR_CUDA; }
+    s->stream = s->own_stream;
+    if (s->params.alloc(1) != cudaSuccess || s->freq2.alloc(1) != cudaSuccess ||
+        cudaMallocHost((void**)&s->params_host, sizeof(DevParams)) != cudaSuccess ||
+        cudaMallocHost((void**)&s->freq_host, sizeof(unsigned int)) != cudaSuccess) { vx_destroy(s); return VX_ERR_ALLOC; }
+    DevParams p{}; cudaMemcpy(s->params.p, &p, sizeof(p), cudaMemcpyHostToDevice);
+    *out = s;
+    return VX_OK;
+}
+
+void vx_destroy(vx_sim* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    s->drop_graph();
+    s->pose0.release(); s->pose1.release(); s->mom0.release(); s->mom1.release();
+    s->ext_idx.release(); s->ext_vox_dev.release(); s->vox_e2i_dev.release(); s->link_e2i_dev.release(); s->member_dev.release();
+    s->pstrain.release(); s->slots.release(); s->slot_strain.release();
+    s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release(); s->lstrain.release();
+    s->vmat_dev.release(); s->lmat_dev.release(); s->curve_e.release(); s->curve_s.release(); s->ext_dev.release();
+    s->params.release(); s->freq2.release(); s->member_t.release(); s->staging.release();
+    if (s->params_host) cudaFreeHost(s->params_host);
+    if (s->freq_host) cudaFreeHost(s->freq_host);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+const char* vx_last_error(const vx_sim* s) { return s ? s->err.c_str() : "null handle"; }
+
+int vx_set_materials(vx_sim* s, int n, const vx_material_desc* d)
+{
+    if (!s || n < 0 || (n && !d)) return VX_ERR_ARG;
+    if (n > VX_MAX_VOXMATS) return fail(s, VX_ERR_ARG, "too many materials");
+    if (s->N > 0 && n != (int)s->mats.size()) return fail(s, VX_ERR_ARG, "material count changed after voxels were set");
+    std::vector<vxm::Material> nm(n);
+    std::vector<std::vector<float>> ne(n), ns(n);
+    for (int i = 0; i < n; i++) {
+        if (d[i].model == VX_MODEL_DATA) {
+            if (d[i].n_points < 0 || !d[i].strain || !d[i].stress) return fail(s, VX_ERR_ARG, "data model without points");
+            ne[i].assign(d[i].strain, d[i].strain + d[i].n_points);
+            ns[i].assign(d[i].stress, d[i].stress + d[i].n_points);
+        }
+        if (!vxm::from_desc(nm[i], d[i], ne[i].data(), ns[i].data())) return fail(s, VX_ERR_MATERIAL, nm[i].error);
+    }
+    s->descs.assign(d, d + n);
+    for (auto& x : s->descs) x.strain = x.stress = nullptr;
+    s->d_eps.swap(ne); s->d_sig.swap(ns); s->mats.swap(nm);
+    return upload_tables(s);
+}
+
+int vx_get_voxmat(const vx_sim* s, int i, vx_voxmat_row* o)
+{
+    if (!s || !o || i < 0 || i >= (int)s->mats.size()) return VX_ERR_ARG;
+    vxm::fill_row(*o, s->mats[i], s->vox_size);
+    return VX_OK;
+}
+int vx_get_linkmat(vx_sim* s, int a, int b, vx_linkmat_row* o)
+{
+    if (!s || !o || a < 0 || b < 0 || a >= (int)s->mats.size() || b >= (int)s->mats.size()) return VX_ERR_ARG;
+    vxm::Material m = vxm::combine(s->mats[a], s->mats[b]);
+    vxm::fill_row(*o, m, s->vox_size, a, b);
+    return VX_OK;
+}
+int vx_get_linkmat_curve(vx_sim* s, int a, int b, float* eps, float* sig, int cap)
+{
+    if (!s || a < 0 || b < 0 || a >= (int)s->mats.size() || b >= (int)s->mats.size()) return VX_ERR_ARG;
+    vxm::Material m = vxm::combine(s->mats[a], s->mats[b]);
+    int n = (int)m.eps.size();
+    if (eps && sig) for (int i = 0; i < n && i < cap; i++) { eps[i] = m.eps[i]; sig[i] = m.sig[i]; }
+    return n;
+}
+
+int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags)
+{
+    if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    // ---- validate + bounding boxes per member
+    int max_member = 0;
+    int lo[3] = {32767, 32767, 32767}, hi[3] = {-32768, -32768, -32768};
+    for (int i = 0; i < n; i++) {
+        if (mat[i] >= s->mats.size()) return fail(s, VX_ERR_ARG, "material index out of range");
+        for (int a = 0; a < 3; a++) {
+            int c = ijk[3 * i + a];
+            if (c < -32768 || c > 32767) return fail(s, VX_ERR_ARG, "lattice index does not fit a short");
+            lo[a] = std::min(lo[a], c); hi[a] = std::max(hi[a], c);
+        }
+        int m = sim_id ? sim_id[i] : 0;
+        if (m < 0 || m > 65535) return fail(s, VX_ERR_ARG, "bad member id");
+        max_member = std::max(max_member, m);
+    }
+    s->N = n; s->n_members = max_member + 1;
+    s->ijk.assign(ijk, ijk + 3 * (size_t)n);
+    s->vmat_id.assign(mat, mat + n);
+    s->member.assign(n, 0); if (sim_id) s->member.assign(sim_id, sim_id + n);
+    s->vflags.clear(); if (flags) s->vflags.assign(flags, flags + n);
+    s->ext_vox.clear(); s->ext_rows.clear();
+    s->lmats.clear(); s->lmat_of.clear();
+    s->drop_graph();
+
+    // ---- occupancy lookup: dense grid over the common bounding box when affordable, else hash
+    long long ext3[3] = {n ? hi[0] - lo[0] + 1 : 0, n ? hi[1] - lo[1] + 1 : 0, n ? hi[2] - lo[2] + 1 : 0};
+    long long cells = ext3[0] * ext3[1] * ext3[2] * (long long)s->n_members;
+    bool dense = n > 0 && cells <= std::max<long long>(8LL * n, 1 << 20);
+    std::vector<int32_t> grid;
+    std::unordered_map<uint64_t, int32_t> hash;
+    auto cell_of = [&](int m, int x, int y, int z) -> long long {
+        if (x < lo[0] || x > hi[0] || y < lo[1] || y > hi[1] || z < lo[2] || z > hi[2]) return -1;
+        return (((long long)m * ext3[2] + (z - lo[2])) * ext3[1] + (y - lo[1])) * ext3[0] + (x - lo[0]);
+    };
+    auto key_of = [](int m, int x, int y, int z) -> uint64_t {
+        return ((uint64_t)(uint32_t)m << 48) | ((uint64_t)(uint16_t)(int16_t)x << 32) | ((uint64_t)(uint16_t)(int16_t)y << 16) | (uint64_t)(uint16_t)(int16_t)z;
+    };
+    if (dense) grid.assign((size_t)cells, -1); else hash.reserve((size_t)n * 2);
+    auto lookup = [&](int m, int x, int y, int z) -> int {
+        if (dense) { long long c = cell_of(m, x, y, z); return c < 0 ? -1 : grid[(size_t)c]; }
+        auto it = hash.find(key_of(m, x, y, z)); return it == hash.end() ? -1 : it->second;
+    };
+
+    // ---- links in the reference's creation order (src/Voxelyze.cpp:453-455, 508-539)
+    s->lk_vn.clear(); s->lk_vp.clear(); s->lk_axis.clear();
+    s->linkmask.assign(n, 0);
+    std::vector<int32_t> plus_link((size_t)n * 3, -1);        // caller link index of the +axis link of each voxel
+    static const int dx[6] = {1, -1, 0, 0, 0, 0}, dy[6] = {0, 0, 1, -1, 0, 0}, dz[6] = {0, 0, 0, 0, 1, -1};
+    for (int i = 0; i < n; i++) {
+        int m = s->member[i], x = ijk[3 * i], y = ijk[3 * i + 1], z = ijk[3 * i + 2];
+        if (lookup(m, x, y, z) >= 0) return fail(s, VX_ERR_TOPOLOGY, "duplicate voxel");
+        if (dense) grid[(size_t)cell_of(m, x, y, z)] = i; else hash[key_of(m, x, y, z)] = i;
+        bool gi = flags && (flags[i] & VX_VF_GHOST);
+        for (int d = 0; d < 6; d++) {
+            int o = lookup(m, x + dx[d], y + dy[d], z + dz[d]);
+            if (o < 0) continue;
+            if (gi && (flags[o] & VX_VF_GHOST)) continue;      // halo-halo links are never needed
+            bool this_neg = (d % 2) == 0;                      // src/VX_Link.cpp:31-53
+            int vn = this_neg ? i : o, vp = this_neg ? o : i;
+            int li = (int)s->lk_vn.size();
+            s->lk_vn.push_back(vn); s->lk_vp.push_back(vp); s->lk_axis.push_back((uint8_t)(d / 2));
+            s->linkmask[i] |= (uint8_t)(1u << d); s->linkmask[o] |= (uint8_t)(1u << (d ^ 1));
+            plus_link[(size_t)vn * 3 + d / 2] = li;
+        }
+    }
+    const int L = s->L = (int)s->lk_vn.size();
+
+    // ---- internal voxel order: (member, z, y, x)
+    s->v_i2e.resize(n);
+    for (int i = 0; i < n; i++) s->v_i2e[i] = i;
+    auto vkey = [&](int e) -> int64_t {
+        return ((int64_t)s->member[e] << 48) | ((int64_t)(ijk[3 * e + 2] + 32768) << 32) | ((int64_t)(ijk[3 * e + 1] + 32768) << 16) | (int64_t)(ijk[3 * e] + 32768);
+    };
+    {
+        bool sorted = true;
+        for (int i = 1; i < n && sorted; i++) if (vkey(i - 1) > vkey(i)) sorted = false;
+        if (!sorted) std::sort(s->v_i2e.begin(), s->v_i2e.end(), [&](int a, int b) { return vkey(a) < vkey(b); });
+    }
+    s->v_e2i.resize(n); s->sort_key.resize(n);
+    for (int i = 0; i < n; i++) { s->v_e2i[s->v_i2e[i]] = i; s->sort_key[i] = vkey(s->v_i2e[i]) >> 32; }
+
+    // ---- internal link order: by axis, then by internal index of the negative-end voxel
+    s->l_i2e.clear(); s->l_i2e.reserve(L);
+    for (int a = 0; a < 3; a++) {
+        s->axis_first[a] = (int)s->l_i2e.size();
+        for (int i = 0; i < n; i++) { int li = plus_link[(size_t)s->v_i2e[i] * 3 + a]; if (li >= 0) s->l_i2e.push_back(li); }
+    }
+    s->axis_first[3] = (int)s->l_i2e.size();
+    s->l_e2i.resize(L);
+    for (int i = 0; i < L; i++) s->l_e2i[s->l_i2e[i]] = i;
+    s->lk_mat.resize(L);
+    std::vector<int2> ends(L);
+    for (int i = 0; i < L; i++) {
+        int e = s->l_i2e[i];
+        int id = link_material(s, s->vmat_id[s->lk_vn[e]], s->vmat_id[s->lk_vp[e]]);
+        if (id > 0xFFFF) return fail(s, VX_ERR_ARG, "too many link materials");
+        s->lk_mat[i] = (uint16_t)id;
+        ends[i] = make_int2(s->v_e2i[s->lk_vn[e]], s->v_e2i[s->lk_vp[e]]);
+    }
+
+    // ---- device memory
+    size_t n1 = std::max(n, 1), l1 = std::max(L, 1);
+    CK(s->pose0.alloc(n1)); CK(s->pose1.alloc(n1)); CK(s->mom0.alloc(n1)); CK(s->mom1.alloc(n1));
+    CK(s->ext_idx.alloc(n1)); CK(s->slots.alloc(n1 * 36));
+    CK(s->vox_e2i_dev.alloc(n1)); CK(s->link_e2i_dev.alloc(l1)); CK(s->member_dev.alloc(n1));
+    CK(s->lends.alloc(l1)); CK(s->lmeta.alloc(l1)); CK(s->lstA.alloc(l1)); CK(s->lstB.alloc(l1)); CK(s->lstC.alloc(l1)); CK(s->lstrain.alloc(l1));
+    CK(s->pstrain.alloc(n1)); CK(s->slot_strain.alloc(n1 * 6));
+    CK(cudaStreamSynchronize(s->stream));
+    if (n) {
+        CK(cudaMemcpy(s->vox_e2i_dev.p, s->v_e2i.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<int> mem_internal(n);
+        for (int i = 0; i < n; i++) mem_internal[i] = s->member[s->v_i2e[i]];
+        CK(cudaMemcpy(s->member_dev.p, mem_internal.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (L) {
+        CK(cudaMemcpy(s->link_e2i_dev.p, s->l_e2i.data(), (size_t)L * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->lends.p, ends.data(), (size_t)L * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    int rc = upload_tables(s);                     // new link materials may have appeared
+    if (rc != VX_OK) return rc;
+    return upload_initial_state(s, s->ambient);    // new voxels start at ambient temperature, src/Voxelyze.cpp:449
+}
+
+int vx_voxel_count(const vx_sim* s) { return s ? s->N : 0; }
+int vx_link_count(const vx_sim* s) { return s ? s->L : 0; }
+int vx_get_links(const vx_sim* s, int32_t* vn, int32_t* vp, uint8_t* ax)
+{
+    if (!s) return VX_ERR_ARG;
+    if (vn) memcpy(vn, s->lk_vn.data(), (size_t)s->L * sizeof(int32_t));
+    if (vp) memcpy(vp, s->lk_vp.data(), (size_t)s->L * sizeof(int32_t));
+    if (ax) memcpy(ax, s->lk_axis.data(), (size_t)s->L);
+    return VX_OK;
+}
+
+int vx_set_externals(vx_sim* s, int n, const int32_t* voxel, const uint8_t* dof, const float* force, const float* moment,
+                     const double* tr, const double* rot)
+{
+    if (!s || n < 0 || (n && (!voxel || !dof))) return VX_ERR_ARG;
+    for (int k = 0; k < n; k++) if (voxel[k] < 0 || voxel[k] >= s->N) return fail(s, VX_ERR_ARG, "external voxel index out of range");
+    s->ext_vox.assign(voxel, voxel + n);
+    s->ext_rows.assign(n, DevExt{});
+    for (int k = 0; k < n; k++) {
+        DevExt& e = s->ext_rows[k];
+        int v = voxel[k];
+        for (int a = 0; a < 3; a++) {
+            e.nominal[a] = s->ijk[3 * v + a] * s->vox_size;
+            e.translation[a] = tr ? tr[3 * k + a] : 0.0;
+            e.force[a] = force ? force[3 * k + a] : 0.0f;
+            e.moment[a] = moment ? moment[3 * k + a] : 0.0f;
+        }
+        e.rot_q[0] = 1.0; e.rot_q[1] = e.rot_q[2] = e.rot_q[3] = 0.0;
+        if (rot && (rot[3 * k] != 0 || rot[3 * k + 1] != 0 || rot[3 * k + 2] != 0)) {
+            // Quat3D::FromRotationVector on the host (include/Quat3D.h:124-139, src/VX_External.cpp:100-109)
+            double hx = 0.5 * rot[3 * k], hy = 0.5 * rot[3 * k + 1], hz = 0.5 * rot[3 * k + 2];
+            double m2 = hx * hx + hy * hy + hz * hz, w, sc;
+            if (m2 * m2 < 5.328e-15) { w = 1.0 - 0.5 * m2; sc = 1.0 - m2 / 6.0; }
+            else { double m = std::sqrt(m2); w = std::cos(m); sc = std::sin(m) / m; }
+            e.rot_q[0] = w; e.rot_q[1] = hx * sc; e.rot_q[2] = hy * sc; e.rot_q[3] = hz * sc;
+        }
+        e.dof = dof[k] & 0x3F;
+    }
+    return upload_externals(s);
+}
+
+int vx_set_gravity(vx_sim* s, float g) { if (!s) return VX_ERR_ARG; s->grav = g; return s->mats.empty() ? VX_OK : upload_tables(s); }
+int vx_enable_floor(vx_sim* s, int e) { if (!s) return VX_ERR_ARG; s->floor_on = e != 0; s->drop_graph(); return VX_OK; }
+int vx_enable_collisions(vx_sim* s, int e)
+{
+    if (!s) return VX_ERR_ARG;
+    if (e) return fail(s, VX_ERR_UNSUPPORTED, "collisions are not built yet");
+    s->collisions = false; s->drop_graph(); return VX_OK;
+}
+int vx_set_collision_envelope(vx_sim* s, float r) { if (!s) return VX_ERR_ARG; s->envelope = r; return VX_OK; }
+
+int vx_set_temperature_all(vx_sim* s, float t)
+{
+    if (!s) return VX_ERR_ARG;
+    s->ambient = t;
+    if (s->N == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    k_fill_temp<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->frame(), t, nullptr, nullptr); s->launches++;
+    CK(cudaGetLastError());
+    return VX_OK;
+}
+int vx_set_temperature_members(vx_sim* s, int n, const float* t)
+{
+    if (!s || !t || n != s->n_members) return VX_ERR_ARG;
+    if (s->N == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    CK(s->member_t.alloc(n));
+    CK(cudaMemcpyAsync(s->member_t.p, t, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    k_fill_temp<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->frame(), 0.f, s->member_t.p, s->member_dev.p); s->launches++;
+    CK(cudaGetLastError());
+    return VX_OK;
+}
+int vx_set_temperature(vx_sim* s, int n, const float* t)
+{
+    if (!s || !t || n != s->N) return VX_ERR_ARG;
+    return vx_upload(s, VX_F_TEMP, 0, n, t);
+}
+
+int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
+{
+    if (!s || n_steps < 0) return VX_ERR_ARG;
+    if (n_steps == 0 || dt == 0 || s->N == 0) return VX_OK;       // dt == 0: src/Voxelyze.cpp:253
+    CK(cudaSetDevice(s->device));
+    Frame f = s->frame();
+    const bool per_step_dt = dt < 0 && s->any_poisson;
+    k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, dt > 0 ? 1 : 0); s->launches++;
+    if (dt < 0 && !per_step_dt) {                                  // constant recommended dt
+        launch_recommended_dt(s, f);
+        k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++;
+    }
+    int left = n_steps;
+    if (!per_step_dt && left >= GRAPH_STEPS) {
+        int rc = ensure_graph(s);
+        if (rc != VX_OK) return rc;
+        while (left >= GRAPH_STEPS) { CK(cudaGraphLaunch(s->graph, s->stream)); s->launches += s->graph_kernels; left -= GRAPH_STEPS; }
+    }
+    for (; left > 0; left--) launch_step(s, f, per_step_dt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->time_host = s->params_host->time;
+    if (s->params_host->div_latched) {
+        if (diverged_step) *diverged_step = s->params_host->steps_done;
+        return VX_DIVERGED;
+    }
+    return VX_OK;
+}
+
+int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
+{
+    if (!s || n_steps < 0 || !ms) return VX_ERR_ARG;
+    ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
+    if (launches) launches[0] = launches[1] = launches[2] = 0;
+    if (n_steps == 0 || dt == 0 || s->N == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    Frame f = s->frame();
+    const bool per_step_dt = dt < 0 && s->any_poisson;
+    k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, dt > 0 ? 1 : 0); s->launches++;
+    if (dt < 0 && !per_step_dt) { launch_recommended_dt(s, f); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+    std::vector<cudaEvent_t> ev((size_t)n_steps * 4);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (int k = 0; k < n_steps; k++) {
+        int64_t l0 = s->launches;
+        CK(cudaEventRecord(ev[4 * k + 0], s->stream));
+        if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
+        if (per_step_dt) { launch_recommended_dt(s, f); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+        int64_t l1 = s->launches;
+        CK(cudaEventRecord(ev[4 * k + 1], s->stream));
+        launch_links(s, f);
+        int64_t l2 = s->launches;
+        CK(cudaEventRecord(ev[4 * k + 2], s->stream));
+        k_voxel<<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0); s->launches++;
+        CK(cudaEventRecord(ev[4 * k + 3], s->stream));
+        if (launches) { launches[2] += (int)(l1 - l0); launches[0] += (int)(l2 - l1); launches[1] += 1; }
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < n_steps; k++) {
+        float a = 0, b = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, ev[4 * k + 0], ev[4 * k + 1]);
+        cudaEventElapsedTime(&b, ev[4 * k + 1], ev[4 * k + 2]);
+        cudaEventElapsedTime(&c, ev[4 * k + 2], ev[4 * k + 3]);
+        cudaEventElapsedTime(&d, ev[4 * k + 0], ev[4 * k + 3]);
+        ms[2] += a; ms[0] += b; ms[1] += c; ms[3] += d;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    s->time_host = s->params_host->time;
+    return s->params_host->div_latched ? VX_DIVERGED : VX_OK;
+}
+
+int vx_recommended_dt(vx_sim* s, float* dt)
+{
+    if (!s || !dt) return VX_ERR_ARG;
+    *dt = 0.f;
+    if (s->N == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    Frame f = s->frame();
+    if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
+    launch_recommended_dt(s, f);
+    CK(cudaMemcpyAsync(s->freq_host, s->freq2.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    float m; memcpy(&m, s->freq_host, 4);
+    *dt = (m <= 0.0f) ? 0.0f : 1.0f / (6.283185f * std::sqrt(m));
+    return VX_OK;
+}
+
+int vx_reset(vx_sim* s)
+{
+    if (!s) return VX_ERR_ARG;
+    return upload_initial_state(s, 0.0f);          // CVX_Voxel::reset zeroes the temperature, src/VX_Voxel.cpp:53
+}
+float vx_time(const vx_sim* s) { return s ? s->time_host : 0.f; }
+
+static bool field_info(int field, int& what, int& comps, int& esize, bool& is_link)
+{
+    switch (field) {
+    case VX_F_POS: what = G_POS; comps = 3; esize = 8; is_link = false; return true;
+    case VX_F_ORIENT: what = G_ORIENT; comps = 4; esize = 8; is_link = false; return true;
+    case VX_F_LINMOM: what = G_LINMOM; comps = 3; esize = 8; is_link = false; return true;
+    case VX_F_ANGMOM: what = G_ANGMOM; comps = 3; esize = 8; is_link = false; return true;
+    case VX_F_TEMP: what = G_TEMP; comps = 1; esize = 4; is_link = false; return true;
+    case VX_F_VOXFLAGS: what = G_VOXFLAGS; comps = 1; esize = 4; is_link = false; return true;
+    case VX_F_PSTRAIN: what = G_PSTRAIN; comps = 3; esize = 4; is_link = false; return true;
+    case VX_F_FORCE_NEG: what = G_FORCE_NEG; comps = 3; esize = 8; is_link = true; return true;
+    case VX_F_FORCE_POS: what = G_FORCE_POS; comps = 3; esize = 8; is_link = true; return true;
+    case VX_F_MOMENT_NEG: what = G_MOMENT_NEG; comps = 3; esize = 8; is_link = true; return true;
+    case VX_F_MOMENT_POS: what = G_MOMENT_POS; comps = 3; esize = 8; is_link = true; return true;
+    case VX_F_POS2: what = G_POS2; comps = 3; esize = 8; is_link = true; return true;
+    case VX_F_ANGLE1V: what = G_ANGLE1V; comps = 3; esize = 8; is_link = true; return true;
+    case VX_F_ANGLE2V: what = G_ANGLE2V; comps = 3; esize = 8; is_link = true; return true;
+    case VX_F_STRAIN: what = G_STRAIN; comps = 1; esize = 4; is_link = true; return true;
+    case VX_F_MAXSTRAIN: what = G_MAXSTRAIN; comps = 1; esize = 4; is_link = true; return true;
+    case VX_F_STRAINOFFSET: what = G_STRAINOFFSET; comps = 1; esize = 4; is_link = true; return true;
+    case VX_F_STRESS: what = G_STRESS; comps = 1; esize = 4; is_link = true; return true;
+    case VX_F_LINKFLAGS: what = G_LINKFLAGS; comps = 1; esize = 4; is_link = true; return true;
+    }
+    return false;
+}
+
+int vx_download(vx_sim* s, int field, int first, int count, void* dst)
+{
+    int what, comps, esize; bool is_link;
+    if (!s || !dst || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
+    if (first + count > (is_link ? s->L : s->N)) return VX_ERR_ARG;
+    if (count == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    size_t bytes = (size_t)count * comps * esize;
+    CK(cudaStreamSynchronize(s->stream));
+    CK(s->staging.alloc(bytes));
+    k_gather<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), what, is_link ? s->link_e2i_dev.p : s->vox_e2i_dev.p, first, count,
+                                                       s->staging.p, s->axis_first[1], s->axis_first[2]);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, s->staging.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return VX_OK;
+}
+
+int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
+{
+    int what, comps, esize; bool is_link;
+    if (!s || !src || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
+    if (is_link || what == G_PSTRAIN) return fail(s, VX_ERR_UNSUPPORTED, "only voxel state can be uploaded");
+    if (first + count > s->N) return VX_ERR_ARG;
+    if (count == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    size_t bytes = (size_t)count * comps * esize;
+    CK(cudaStreamSynchronize(s->stream));
+    CK(s->staging.alloc(bytes));
+    CK(cudaMemcpyAsync(s->staging.p, src, bytes, cudaMemcpyHostToDevice, s->stream));
+    k_scatter<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), what, s->vox_e2i_dev.p, first, count, s->staging.p);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s->stream));
+    return VX_OK;
+}
+
+int vx_collision_pairs(vx_sim* s, int32_t*, int, int* n_pairs) { if (!s) return VX_ERR_ARG; if (n_pairs) *n_pairs = 0; return VX_OK; }
+int vx_state_info(vx_sim* s, int, int, float*) { return fail(s, VX_ERR_UNSUPPORTED, "stateInfo is not built yet"); }
+
+int vx_set_stream(vx_sim* s, uint64_t stream)
+{
+    if (!s) return VX_ERR_ARG;
+    cudaStreamSynchronize(s->stream);
+    s->stream = stream ? (cudaStream_t)(uintptr_t)stream : s->own_stream;
+    s->drop_graph();
+    return VX_OK;
+}
+
+int vx_pose_plane(vx_sim* s, int iz, uint64_t* p0, uint64_t* p1, int* count, int* rec_bytes)
+{
+    if (!s || s->n_members != 1) return VX_ERR_ARG;
+    int64_t key = (int64_t)(iz + 32768);
+    auto lo = std::lower_bound(s->sort_key.begin(), s->sort_key.end(), key);
+    auto hi = std::upper_bound(s->sort_key.begin(), s->sort_key.end(), key);
+    size_t first = lo - s->sort_key.begin();
+    if (p0) *p0 = (uint64_t)(uintptr_t)(s->pose0.p + first);
+    if (p1) *p1 = (uint64_t)(uintptr_t)(s->pose1.p + first);
+    if (count) *count = (int)(hi - lo);
+    if (rec_bytes) *rec_bytes = (int)sizeof(double4);
+    return VX_OK;
+}
+
+__global__ void k_halo_import(double4* pose0, double4* pose1, const double4* src0, const double4* src1, int count)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    double4 a = src0[k], b = src1[k];
+    double keep = pose1[k].w;
+    pose0[k] = a;
+    pose1[k] = make_double4(b.x, b.y, b.z, meta_pack(meta_temp(b.w), meta_hi(keep)));
+}
+
+int vx_halo_import(vx_sim* s, int iz, uint64_t src0, uint64_t src1, int count)
+{
+    if (!s || !src0 || !src1) return VX_ERR_ARG;
+    uint64_t p0, p1; int n, rb;
+    int rc = vx_pose_plane(s, iz, &p0, &p1, &n, &rb);
+    if (rc != VX_OK) return rc;
+    if (n != count) return fail(s, VX_ERR_ARG, "halo layer size mismatch");
+    if (n == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    k_halo_import<<<blocks_for(n), TPB, 0, s->stream>>>((double4*)(uintptr_t)p0, (double4*)(uintptr_t)p1,
+                                                       (const double4*)(uintptr_t)src0, (const double4*)(uintptr_t)src1, n);
+    s->launches++;
+    CK(cudaGetLastError());
+    return VX_OK;
+}
+
+int64_t vx_launch_count(const vx_sim* s) { return s ? s->launches : 0; }
+int vx_sync(vx_sim* s) { if (!s) return VX_ERR_ARG; CK(cudaSetDevice(s->device)); CK(cudaStreamSynchronize(s->stream)); return VX_OK; }
+int vx_set_path(vx_sim* s, int path) { if (!s) return VX_ERR_ARG; s->path = path; s->drop_graph(); return VX_OK; }
+
+} // extern "C"

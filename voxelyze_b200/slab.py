@@ -1,0 +1,214 @@
+"""z-slab domain decomposition of one large lattice (BASELINE config C5b).
+
+One process per GPU.  Rank r owns the z-layers [z0, z1) plus one ghost layer on each cut.
+A voxel update needs only the *old* poses of its face neighbours, so the only exchange step
+is: after every step each rank sends the pose (position + orientation, 56 B) of its two
+boundary layers to its z-neighbours, which store them into their ghost layers.  Links that
+cross a cut are evaluated redundantly on both sides from identical inputs (identical bits),
+so no force ever travels.  Transport: NCCL send/recv over NVLink via torch.distributed on
+views of the library's own device arrays (no staging copy on the send side).
+
+The same class runs on CPU tensors over gloo with any C-ABI implementation (host exchange
+through vx_download / vx_upload); tests use that to check the partition logic bit for bit
+against an unsplit run.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+from . import scenarios
+from .capi import DOF_ALL, Material, Sim, VxLib, VF_GHOST
+
+
+def slab_range(nz: int, rank: int, world: int) -> Tuple[int, int]:
+    """Owned z-layers [z0, z1) of `rank`; layers are dealt as evenly as possible."""
+    base, rem = divmod(nz, world)
+    z0 = rank * base + min(rank, rem)
+    return z0, z0 + base + (1 if rank < rem else 0)
+
+
+class _DevMem:
+    """Exposes a raw device allocation to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class SingleRunner:
+    """Whole lattice on one GPU; same interface as SlabRunner."""
+
+    def __init__(self, sim: Sim):
+        self.sim = sim
+
+    def recommended_dt(self) -> float:
+        return self.sim.recommended_dt()
+
+    def step(self, dt: float, n: int):
+        return self.sim.step(dt, n)
+
+    def step_profile(self, dt: float, n: int):
+        return self.sim.step_profile(dt, n)
+
+    def global_counts(self):
+        return self.sim.n_voxels, self.sim.n_links
+
+    def local_counts(self):
+        return self.sim.n_voxels, self.sim.n_links
+
+    def read_probe(self):
+        return self.sim.download("pos", self.sim.n_voxels - 1, 1)
+
+    def dominant_kernel(self) -> str:
+        return "k_link<AXIS> (3 launches per step, one per link axis)"
+
+    def path_name(self) -> str:
+        return "general two-kernel path"
+
+
+class SlabRunner:
+    """Cantilever pattern of C5 (x=0 face fixed, -z load on the x=nx-1 face) split along z."""
+
+    def __init__(self, lib: VxLib, nx: int, ny: int, nz: int, rank: int, world: int, device: int = 0,
+                 voxel_size: float = 0.005, tip_load: float = 1.0, material: Material = None, host_exchange: bool = False):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = rank, world
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.z0, self.z1 = slab_range(nz, rank, world)
+        self.lo = self.z0 - 1 if rank > 0 else self.z0             # first stored layer (ghost below)
+        self.hi = self.z1 + 1 if rank < world - 1 else self.z1     # one past the last stored layer
+        self.plane = nx * ny
+        ijk = scenarios.box_ijk(nx, ny, self.hi - self.lo, origin=(0, 0, self.lo))
+        flags = np.zeros(len(ijk), np.uint32)
+        flags[(ijk[:, 2] < self.z0) | (ijk[:, 2] >= self.z1)] = VF_GHOST
+        sim = lib.create(voxel_size, device)
+        sim.set_materials([material or Material(E=1e6, rho=1e3)])
+        sim.set_voxels(ijk, np.zeros(len(ijk), np.uint16), flags=flags)
+        owned = flags == 0
+        fixed = np.nonzero((ijk[:, 0] == 0) & owned)[0]
+        load = np.nonzero((ijk[:, 0] == nx - 1) & owned)[0]
+        ev = np.concatenate([fixed, load]).astype(np.int32)
+        dof = np.concatenate([np.full(len(fixed), DOF_ALL), np.zeros(len(load))]).astype(np.uint8)
+        f = np.zeros((len(ev), 3), np.float32)
+        f[len(fixed):, 2] = np.float32(-tip_load / (ny * nz))
+        sim.set_externals(ev, dof, f)
+        self.sim, self.ijk = sim, ijk
+        self.host_exchange = host_exchange
+        self._bufs = None
+
+    # ---- bookkeeping -------------------------------------------------------------------
+    def global_counts(self):
+        nx, ny, nz = self.nx, self.ny, self.nz
+        return nx * ny * nz, (nx - 1) * ny * nz + nx * (ny - 1) * nz + nx * ny * (nz - 1)
+
+    def local_counts(self):
+        return self.plane * (self.z1 - self.z0), self.sim.n_links
+
+    def layer_index_range(self, z: int) -> Tuple[int, int]:
+        """Voxel index range (caller order) of stored layer z."""
+        first = (z - self.lo) * self.plane
+        return first, self.plane
+
+    def recommended_dt(self) -> float:
+        dt = self.sim.recommended_dt()
+        if self.world > 1:
+            import torch
+            dev = "cpu" if self.host_exchange else "cuda"
+            t = torch.tensor([dt], dtype=torch.float32, device=dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+            dt = float(t.item())
+        return dt
+
+    # ---- halo exchange -----------------------------------------------------------------
+    def _neighbours(self):
+        """(peer rank, layer I send, ghost layer I receive into)"""
+        out = []
+        if self.rank > 0:
+            out.append((self.rank - 1, self.z0, self.z0 - 1))
+        if self.rank < self.world - 1:
+            out.append((self.rank + 1, self.z1 - 1, self.z1))
+        return out
+
+    def _exchange_device(self):
+        import torch
+        dist = self.dist
+        if self._bufs is None:
+            self._bufs = {}
+            for peer, send_z, recv_z in self._neighbours():
+                p0, p1, n, rb = self.sim.pose_plane(send_z)
+                assert n == self.plane
+                s0 = torch.as_tensor(_DevMem(p0, n * rb), device="cuda")
+                s1 = torch.as_tensor(_DevMem(p1, n * rb), device="cuda")
+                r0 = torch.empty(n * rb, dtype=torch.uint8, device="cuda")
+                r1 = torch.empty(n * rb, dtype=torch.uint8, device="cuda")
+                self._bufs[peer] = (s0, s1, r0, r1, recv_z)
+        ops = []
+        for peer, (s0, s1, r0, r1, _) in self._bufs.items():
+            ops += [dist.P2POp(dist.isend, s0, peer), dist.P2POp(dist.isend, s1, peer),
+                    dist.P2POp(dist.irecv, r0, peer), dist.P2POp(dist.irecv, r1, peer)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for peer, (_, _, r0, r1, recv_z) in self._bufs.items():
+            self.sim.halo_import(recv_z, r0.data_ptr(), r1.data_ptr(), self.plane)
+
+    def _exchange_host(self):
+        import torch
+        dist = self.dist
+        reqs, recvs = [], []
+        for peer, send_z, recv_z in self._neighbours():
+            first, n = self.layer_index_range(send_z)
+            payload = np.concatenate([self.sim.download("pos", first, n).ravel(), self.sim.download("orient", first, n).ravel()])
+            reqs.append(dist.isend(torch.from_numpy(payload), peer))
+            buf = torch.empty(7 * self.plane, dtype=torch.float64)
+            reqs.append(dist.irecv(buf, peer))
+            recvs.append((buf, recv_z))
+        for r in reqs:
+            r.wait()
+        for buf, recv_z in recvs:
+            first, n = self.layer_index_range(recv_z)
+            a = buf.numpy()
+            self.sim.upload("pos", a[:3 * n].reshape(n, 3), first)
+            self.sim.upload("orient", a[3 * n:].reshape(n, 4), first)
+
+    def exchange(self):
+        if self.world == 1:
+            return
+        if self.host_exchange:
+            self._exchange_host()
+        else:
+            self._exchange_device()
+
+    # ---- stepping ------------------------------------------------------------------------
+    def step(self, dt: float, n: int):
+        div = None
+        for _ in range(n):
+            d = self.sim.step(dt, 1)
+            if d is not None:
+                div = d
+            self.exchange()
+        return div
+
+    def step_profile(self, dt: float, n: int):
+        tot, launches = None, None
+        for _ in range(n):
+            ms, ln = self.sim.step_profile(dt, 1)
+            self.exchange()
+            tot = ms if tot is None else {k: tot[k] + ms[k] for k in ms}
+            launches = ln if launches is None else [a + b for a, b in zip(launches, ln)]
+        return tot, launches
+
+    def read_probe(self):
+        first, n = self.layer_index_range(self.z1 - 1)
+        return self.sim.download("pos", first + n - 1, 1)
+
+    def owned_state(self, field: str) -> np.ndarray:
+        first, _ = self.layer_index_range(self.z0)
+        return self.sim.download(field, first, self.plane * (self.z1 - self.z0))
+
+    def dominant_kernel(self) -> str:
+        return "k_link<AXIS> (3 launches per step, one per link axis)"
+
+    def path_name(self) -> str:
+        return f"general two-kernel path, z-slab {self.rank}/{self.world} layers [{self.z0},{self.z1})"
