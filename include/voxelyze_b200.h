@@ -285,6 +285,8 @@ int  vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
 /* select kernel variant: 0 = auto, 1 = general two-kernel path, 2 = fused lattice
  * path (dense boxes).  For tests and ablations.                                       */
 int  vx_set_path(vx_sim* s, int path);
+/* which variant the handle runs: 1 general, 2 fused lattice (decided by vx_set_voxels)  */
+int  vx_active_path(const vx_sim* s);
 
 #ifdef __cplusplus
 }

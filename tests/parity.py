@@ -15,10 +15,10 @@ def snapshot(sim: capi.Sim, fields=None) -> dict:
     return {f: sim.download(f) for f in fields}
 
 
-def run(lib: capi.VxLib, sc: scenarios.Scenario, steps: int, dt=None, program=None, chunk=None, device=0):
+def run(lib: capi.VxLib, sc: scenarios.Scenario, steps: int, dt=None, program=None, chunk=None, device=0, path=0):
     """Builds `sc`, steps it, returns (sim, dt, diverged_at).  `program(sim, k, t)` is called
     before step k (for per-step temperature / force changes); with a program steps run one by one."""
-    sim = scenarios.build(lib, sc, device)
+    sim = scenarios.build(lib, sc, device, path)
     if dt is None:
         dt = sc.dt if sc.dt is not None else sim.recommended_dt()
     div = None

@@ -22,12 +22,15 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NOT_BUILT = {"collide_two", "plates_16x4x2"}     # cases needing features that are not on the GPU yet
 
 
+@pytest.mark.parametrize("path", [0, 1], ids=["auto", "general"])
 @pytest.mark.parametrize("case", cases.CASES, ids=lambda c: c.name)
-def test_cuda_matches_oracle(product, oracle, case):
+def test_cuda_matches_oracle(product, oracle, case, path):
+    """path auto = fused lattice kernel wherever the lattice is a full box, else the general
+    kernels; path general forces the two-kernel path on every case."""
     if case.name in NOT_BUILT:
         pytest.skip("feature not on the GPU yet")
     sc = case.make()
-    g, dtg, dg = parity.run(product, sc, case.steps, program=case.program)
+    g, dtg, dg = parity.run(product, sc, case.steps, program=case.program, path=path)
     o, dto, do = parity.run(oracle, sc, case.steps, program=case.program)
     assert g.launch_count() > 0
     assert dtg == dto, "recommended time step"
@@ -77,10 +80,45 @@ def test_material_tables_bitwise(product, oracle):
             assert _same(pl[key][k], ol[key][k]), (key, k)
 
 
-def test_determinism_two_runs_bit_equal(product):
+def test_lattice_path_is_selected_for_full_boxes(product):
+    assert scenarios.build(product, scenarios.cantilever(6, 3, 3)).active_path() == 2
+    assert scenarios.build(product, scenarios.cantilever(6, 3, 3), path=1).active_path() == 1
+    assert scenarios.build(product, scenarios.robot_ensemble(2, 3)).active_path() == 2
+    assert scenarios.build(product, cases.BY_NAME["temperature_bimorph"].make()).active_path() == 2
+    assert scenarios.build(product, cases.BY_NAME["mixed_six"].make()).active_path() == 1      # not a full box
+    assert scenarios.build(product, cases.BY_NAME["poisson_block"].make()).active_path() == 1  # nu != 0
+
+
+def test_fused_and_general_paths_agree_bitwise(product):
+    """Same physics functions, same summation order: the two device layouts give identical bits."""
+    sc = scenarios.cantilever(12, 5, 4, tip_load=30.0)
+    a, dt, _ = parity.run(product, sc, 700, path=0)
+    b, _, _ = parity.run(product, sc, 700, path=1)
+    sa, sb = parity.snapshot(a), parity.snapshot(b)
+    for f in sa:
+        assert parity.bit_equal(sa[f], sb[f]), f
+
+
+def test_diverging_step_semantics(product, oracle):
+    """A step whose links exceed strain 100 returns VX_DIVERGED, advances links but not voxels
+    (src/Voxelyze.cpp:263-269), on both device layouts."""
+    c = cases.BY_NAME["data_curve_fail"]
+    sc = c.make()
+    for path in (0, 1):
+        g, dt, dg = parity.run(product, sc, 2900, path=path)
+        o, _, do = parity.run(oracle, sc, 2900)
+        assert dg == do and dg is not None
+        sg, so = parity.snapshot(g), parity.snapshot(o)
+        err = parity.rel_errors(sg, so, sc)
+        assert err["pos"] <= 1e-7 and err["strain"] <= 1e-6, (path, err)
+        assert abs(g.time() - o.time()) <= 1e-9
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["auto", "general"])
+def test_determinism_two_runs_bit_equal(product, path):
     sc = scenarios.cantilever(16, 6, 5)
-    a, _, _ = parity.run(product, sc, 500)
-    b, _, _ = parity.run(product, sc, 500)
+    a, _, _ = parity.run(product, sc, 500, path=path)
+    b, _, _ = parity.run(product, sc, 500, path=path)
     sa, sb = parity.snapshot(a), parity.snapshot(b)
     for f in sa:
         assert np.array_equal(sa[f], sb[f]), f

@@ -159,6 +159,7 @@ class VxLib:
             "vx_launch_count": (C.c_int64, [vp]),
             "vx_sync": (i32, [vp]),
             "vx_set_path": (i32, [vp, i32]),
+            "vx_active_path": (i32, [vp]),
             "vx_step_profile": (i32, [vp, f32, i32, P(f32), P(i32)]),
         }
         self.symbols = list(sig)
@@ -367,6 +368,9 @@ class Sim:
         ln = (C.c_int * 3)()
         self._chk(self.L.lib.vx_step_profile(self.h, dt, n, ms, ln), ok=(VX_OK, VX_DIVERGED))
         return dict(link=ms[0], voxel=ms[1], other=ms[2], step=ms[3]), list(ln)
+
+    def active_path(self) -> int:
+        return self.L.lib.vx_active_path(self.h)
 
     def set_path(self, path: int):
         self._chk(self.L.lib.vx_set_path(self.h, path))

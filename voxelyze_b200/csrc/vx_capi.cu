@@ -1,8 +1,11 @@
 // vx_capi.cu -- implementation of include/voxelyze_b200.h for sm_100a (the product).
 //
 // Host side of the drop-in boundary: owns the device-resident structure-of-arrays state of
-// one simulation, translates the flat model description into it, and drives the kernels of
-// vx_kernels.cuh (general path) / vx_lattice.cuh (fused dense-lattice path).
+// one simulation, translates the flat model description into it, and drives the kernels.
+// Two device layouts exist behind the same ABI:
+//   lattice mode  dense box lattices (every cell of the bounding box filled, nu = 0): fused
+//                 single-pass kernel on ping-pong generations, vx_lattice.cuh  (headline path)
+//   general mode  any voxel set, Poisson materials: link kernels + voxel kernel, vx_kernels.cuh
 // There is deliberately no CPU code path for stepping: without a usable CUDA device
 // vx_create fails with VX_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
@@ -17,7 +20,7 @@
 
 #include "voxelyze_b200.h"
 #include "vx_material.hpp"
-#include "vx_kernels.cuh"
+#include "vx_lattice.cuh"
 
 using namespace vxd;
 
@@ -39,7 +42,7 @@ template <typename T> struct DevBuf {
 
 struct LinkMatEntry { int a, b; vxm::Material mat; };
 
-constexpr int GRAPH_STEPS = 16;     // steps per captured CUDA graph
+constexpr int GRAPH_STEPS = 16;     // steps per captured CUDA graph (even: generations re-align)
 constexpr int TPB = 128;
 
 inline int blocks_for(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
@@ -63,20 +66,29 @@ struct vx_sim {
     std::vector<int32_t> lk_vn, lk_vp; std::vector<uint8_t> lk_axis;   // caller (creation) order, caller voxel indices
     std::vector<int32_t> v_e2i, v_i2e, l_e2i, l_i2e;
     std::vector<uint8_t> linkmask;                                     // by caller voxel index
-    std::vector<uint16_t> lk_mat;                                      // by internal link index
+    std::vector<uint16_t> lk_mat;                                      // by internal link index (general mode)
     int axis_first[4] = {0, 0, 0, 0};
-    std::vector<int64_t> sort_key;                                     // by internal voxel index: (member,z) key for plane lookup
+    std::vector<int64_t> sort_key;                                     // by internal voxel index: (member,z)
 
-    // externals (host copy, caller voxel indices)
-    std::vector<int32_t> ext_vox; std::vector<DevExt> ext_rows;
+    std::vector<int32_t> ext_vox; std::vector<DevExt> ext_rows;        // externals, caller voxel indices
 
     float grav = 0.f, ambient = 0.f, envelope = 0.625f;
     bool floor_on = false, collisions = false;
     float time_host = 0.f;
-    int path = 0;
+    int path = 0;                       // vx_set_path: 0 auto, 1 general, 2 lattice
+
+    // ---- lattice mode
+    bool lattice = false;
+    int nx = 0, ny = 0, nz = 0;
+    int gen = 0;                        // generation that holds the current state
+    bool have_prev = false;             // gen^1 holds the inputs of the last executed step
+    float last_prev_dt = 0.f;           // previousDt that step used
+    float prev_dt_host = 0.f;           // mirror of DevParams::prev_dt
 
     // ---- device
-    DevBuf<double4> pose0, pose1, mom0; DevBuf<double2> mom1;
+    DevBuf<double4> pose0[2], pose1[2], mom0[2]; DevBuf<double2> mom1[2];   // general mode uses [0] only
+    DevBuf<double2> rec[2]; DevBuf<float4> recf[2];                         // lattice link records
+    DevBuf<uint16_t> pair_lmat; DevBuf<int> link_owner; DevBuf<unsigned char> link_axis_dev;
     DevBuf<int> ext_idx, ext_vox_dev, vox_e2i_dev, link_e2i_dev, member_dev;
     DevBuf<float4> pstrain; DevBuf<double> slots; DevBuf<float> slot_strain;
     DevBuf<int2> lends; DevBuf<uint32_t> lmeta; DevBuf<double4> lstA, lstB; DevBuf<double> lstC; DevBuf<float4> lstrain;
@@ -87,22 +99,47 @@ struct vx_sim {
     DevParams* params_host = nullptr;     // pinned mirror
     unsigned int* freq_host = nullptr;    // pinned
 
-    cudaGraphExec_t graph = nullptr; int graph_kernels = 0;
+    cudaGraphExec_t graph = nullptr; int graph_kernels = 0;      // general mode
+    cudaGraphExec_t lgraph[2] = {nullptr, nullptr};              // lattice mode, keyed by starting generation
     int64_t launches = 0;
 
     Frame frame() const
     {
         Frame f{};
+        const int g = lattice ? gen : 0;
         f.n_vox = N; f.n_link = L;
-        f.pose0 = pose0.p; f.pose1 = pose1.p; f.mom0 = mom0.p; f.mom1 = mom1.p;
-        f.ext_idx = ext_idx.p; f.pstrain = pstrain.p; f.slots = slots.p; f.slot_strain = slot_strain.p;
+        f.pose0 = pose0[g].p; f.pose1 = pose1[g].p; f.mom0 = mom0[g].p; f.mom1 = mom1[g].p;
+        f.ext_idx = ext_idx.p; f.pstrain = lattice ? nullptr : pstrain.p; f.slots = slots.p; f.slot_strain = slot_strain.p;
         f.lends = lends.p; f.lmeta = lmeta.p; f.lstA = lstA.p; f.lstB = lstB.p; f.lstC = lstC.p; f.lstrain = lstrain.p;
         f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
         f.ext = ext_dev.p; f.params = params.p;
         f.col_start = nullptr; f.col_ref = nullptr; f.col_force = nullptr;
         return f;
     }
-    void drop_graph() { if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; } }
+    // lattice frame reading generation g and writing generation g^1
+    LatFrame lat_frame(int g) const
+    {
+        LatFrame f{};
+        f.nx = nx; f.ny = ny; f.nz = nz; f.nxy = nx * ny; f.n_vox = N; f.n_mat = (int)mats.size();
+        f.c_pose0 = pose0[g].p; f.c_pose1 = pose1[g].p; f.c_mom0 = mom0[g].p; f.c_mom1 = mom1[g].p;
+        f.n_pose0 = pose0[g ^ 1].p; f.n_pose1 = pose1[g ^ 1].p; f.n_mom0 = mom0[g ^ 1].p; f.n_mom1 = mom1[g ^ 1].p;
+        for (int a = 0; a < 3; a++) {
+            for (int k = 0; k < 3; k++) {
+                f.c_rec[a][k] = rec[g].p + (size_t)(a * 3 + k) * N;
+                f.n_rec[a][k] = rec[g ^ 1].p + (size_t)(a * 3 + k) * N;
+            }
+            f.c_recf[a] = recf[g].p + (size_t)a * N;
+            f.n_recf[a] = recf[g ^ 1].p + (size_t)a * N;
+        }
+        f.ext_idx = ext_idx.p; f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
+        f.pair_lmat = pair_lmat.p; f.ext = ext_dev.p; f.params = params.p;
+        return f;
+    }
+    void drop_graph()
+    {
+        if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
+        for (int g = 0; g < 2; g++) if (lgraph[g]) { cudaGraphExecDestroy(lgraph[g]); lgraph[g] = nullptr; }
+    }
 };
 
 static int fail(vx_sim* s, int code, const std::string& msg) { if (s) s->err = msg; return code; }
@@ -154,6 +191,8 @@ static int upload_tables(vx_sim* s)
     }
     std::vector<DevLinkMat> lm(s->lmats.size());
     std::vector<float> ce, cs;
+    const int nm = (int)s->mats.size();
+    std::vector<uint16_t> pair((size_t)std::max(nm * nm, 1), 0);
     for (size_t i = 0; i < lm.size(); i++) {
         LinkMatEntry& e = s->lmats[i];
         e.mat = vxm::combine(s->mats[e.a], s->mats[e.b]);
@@ -168,11 +207,14 @@ static int upload_tables(vx_sim* s)
         d.a1 = k.a1; d.a2 = k.a2; d.b1 = k.b1; d.b2 = k.b2; d.b3 = k.b3;
         d.sq_a1 = k.sq_a1; d.sq_a2_ip = k.sq_a2_ip; d.sq_b1 = k.sq_b1; d.sq_b2_fmp = k.sq_b2_fmp; d.sq_b3_ip = k.sq_b3_ip;
         if (m.nu != 0.0f) s->any_poisson = true;
+        pair[(size_t)e.a * nm + e.b] = pair[(size_t)e.b * nm + e.a] = (uint16_t)i;
     }
+    if (s->lattice && s->any_poisson) return fail(s, VX_ERR_UNSUPPORTED, "Poisson's ratio on a lattice-mode handle: set materials before the voxels");
     CK(s->vmat_dev.alloc(std::max<size_t>(vm.size(), 1)));
     CK(s->lmat_dev.alloc(std::max<size_t>(lm.size(), 1)));
     CK(s->curve_e.alloc(std::max<size_t>(ce.size(), 2)));
     CK(s->curve_s.alloc(std::max<size_t>(cs.size(), 2)));
+    CK(s->pair_lmat.alloc(pair.size()));
     CK(cudaStreamSynchronize(s->stream));
     if (!vm.empty()) CK(cudaMemcpy(s->vmat_dev.p, vm.data(), vm.size() * sizeof(DevVoxMat), cudaMemcpyHostToDevice));
     if (!lm.empty()) CK(cudaMemcpy(s->lmat_dev.p, lm.data(), lm.size() * sizeof(DevLinkMat), cudaMemcpyHostToDevice));
@@ -180,18 +222,20 @@ static int upload_tables(vx_sim* s)
         CK(cudaMemcpy(s->curve_e.p, ce.data(), ce.size() * sizeof(float), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(s->curve_s.p, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
+    CK(cudaMemcpy(s->pair_lmat.p, pair.data(), pair.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     s->drop_graph();
     return VX_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // initial dynamic state (fresh CVoxelyze / resetTime)
-static uint32_t initial_bits(const vx_sim* s, int ext_caller)      // ext_caller: caller voxel index
+static uint32_t initial_bits(const vx_sim* s, int caller_voxel)
 {
-    uint32_t b = s->vmat_id[ext_caller] & VM_MAT_MASK;
-    b |= (uint32_t)s->linkmask[ext_caller] << VM_LINK_SHIFT;
+    uint32_t b = s->vmat_id[caller_voxel] & VM_MAT_MASK;
+    b |= (uint32_t)s->linkmask[caller_voxel] << VM_LINK_SHIFT;
     b |= VM_STATIC_FRIC | VM_PSTRAIN_STALE;                         // CVX_Voxel::reset, src/VX_Voxel.cpp:47-56
-    if (!s->vflags.empty() && (s->vflags[ext_caller] & VX_VF_GHOST)) b |= VM_GHOST;
+    if (!s->vflags.empty() && (s->vflags[caller_voxel] & VX_VF_GHOST)) b |= VM_GHOST;
+    if (s->lattice) b |= 0x15u << VM_LFLAG_SHIFT;                   // three owned links start in small-angle mode
     return b;
 }
 
@@ -200,7 +244,8 @@ static int upload_initial_state(vx_sim* s, float temp)
     const int N = s->N, L = s->L;
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
-    {
+    s->gen = 0; s->have_prev = false; s->prev_dt_host = 0.f;
+    if (N) {
         std::vector<double4> p0(N), p1(N);
         std::vector<char> has_ext(N, 0);
         for (int v : s->ext_vox) has_ext[v] = 1;
@@ -214,17 +259,24 @@ static int upload_initial_state(vx_sim* s, float temp)
             double wd; memcpy(&wd, &w, 8);
             p1[i] = make_double4(0.0, 0.0, 0.0, wd);
         }
-        if (N) {
-            CK(cudaMemcpy(s->pose0.p, p0.data(), (size_t)N * sizeof(double4), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(s->pose1.p, p1.data(), (size_t)N * sizeof(double4), cudaMemcpyHostToDevice));
-            CK(cudaMemset(s->mom0.p, 0, (size_t)N * sizeof(double4)));
-            CK(cudaMemset(s->mom1.p, 0, (size_t)N * sizeof(double2)));
+        const int gens = s->lattice ? 2 : 1;
+        for (int g = 0; g < gens; g++) {
+            CK(cudaMemcpy(s->pose0[g].p, p0.data(), (size_t)N * sizeof(double4), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(s->pose1[g].p, p1.data(), (size_t)N * sizeof(double4), cudaMemcpyHostToDevice));
+            CK(cudaMemset(s->mom0[g].p, 0, (size_t)N * sizeof(double4)));
+            CK(cudaMemset(s->mom1[g].p, 0, (size_t)N * sizeof(double2)));
+            if (s->lattice) {
+                CK(cudaMemset(s->rec[g].p, 0, (size_t)N * 9 * sizeof(double2)));
+                CK(cudaMemset(s->recf[g].p, 0, (size_t)N * 3 * sizeof(float4)));
+            }
+        }
+        if (!s->lattice) {
             CK(cudaMemset(s->slots.p, 0, (size_t)N * 36 * sizeof(double)));
-            if (s->pstrain.p) CK(cudaMemset(s->pstrain.p, 0, (size_t)N * sizeof(float4)));
-            if (s->slot_strain.p) CK(cudaMemset(s->slot_strain.p, 0, (size_t)N * 6 * sizeof(float)));
+            CK(cudaMemset(s->pstrain.p, 0, (size_t)N * sizeof(float4)));
+            CK(cudaMemset(s->slot_strain.p, 0, (size_t)N * 6 * sizeof(float)));
         }
     }
-    if (L) {
+    if (L && !s->lattice) {
         CK(cudaMemset(s->lstA.p, 0, (size_t)L * sizeof(double4)));
         CK(cudaMemset(s->lstB.p, 0, (size_t)L * sizeof(double4)));
         CK(cudaMemset(s->lstC.p, 0, (size_t)L * sizeof(double)));
@@ -233,9 +285,10 @@ static int upload_initial_state(vx_sim* s, float temp)
         for (int i = 0; i < L; i++) lm[i] = s->lk_mat[i] | LM_SMALL_ANGLE;    // CVX_Link::reset, src/VX_Link.cpp:61-75
         CK(cudaMemcpy(s->lmeta.p, lm.data(), (size_t)L * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
-    DevParams p{}; p.dt = 0; p.prev_dt = 0; p.time = 0; p.col_stale = 1;
+    DevParams p{}; p.col_stale = 1;
     CK(cudaMemcpy(s->params.p, &p, sizeof(p), cudaMemcpyHostToDevice));
     s->time_host = 0.f;
+    s->drop_graph();
     return VX_OK;
 }
 
@@ -262,7 +315,7 @@ static int upload_externals(vx_sim* s)
 }
 
 // ------------------------------------------------------------------------------------------------
-// stepping
+// stepping, general mode
 static void launch_links(vx_sim* s, const Frame& f)
 {
     const int* af = s->axis_first;
@@ -278,15 +331,19 @@ static void launch_links(vx_sim* s, const Frame& f)
     }
 }
 
-static void launch_recommended_dt(vx_sim* s, const Frame& f)
+static void launch_recommended_dt(vx_sim* s)
 {
     cudaMemsetAsync(s->freq2.p, 0, sizeof(unsigned int), s->stream);
-    if (s->L > 0) {
+    if (s->lattice) {
+        int g = std::min(blocks_for(s->N, 256), 148 * 8);
+        if (s->L > 0) k_lattice_max_freq<<<g, 256, 0, s->stream>>>(s->lat_frame(s->gen), s->freq2.p);
+        else k_max_freq_voxels<<<g, 256, 0, s->stream>>>(s->frame(), s->freq2.p);
+    } else if (s->L > 0) {
         int g = std::min(blocks_for(s->L, 256), 148 * 8);
-        k_max_freq<<<g, 256, 0, s->stream>>>(f, s->axis_first[1], s->axis_first[2], s->freq2.p);
+        k_max_freq<<<g, 256, 0, s->stream>>>(s->frame(), s->axis_first[1], s->axis_first[2], s->freq2.p);
     } else {
         int g = std::min(blocks_for(s->N, 256), 148 * 8);
-        k_max_freq_voxels<<<g, 256, 0, s->stream>>>(f, s->freq2.p);
+        k_max_freq_voxels<<<g, 256, 0, s->stream>>>(s->frame(), s->freq2.p);
     }
     s->launches++;
 }
@@ -295,7 +352,7 @@ static void launch_recommended_dt(vx_sim* s, const Frame& f)
 static void launch_step(vx_sim* s, const Frame& f, bool per_step_dt)
 {
     if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
-    if (per_step_dt) { launch_recommended_dt(s, f); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+    if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
     launch_links(s, f);
     k_voxel<<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0);
     s->launches++;
@@ -304,15 +361,8 @@ static void launch_step(vx_sim* s, const Frame& f, bool per_step_dt)
 __global__ void k_begin(DevParams* p, float dt, int set_dt)
 {
     p->div_now = 0; p->div_latched = 0; p->steps_done = 0;
+    p->pending = 0; p->div_flag[0] = 0; p->div_flag[1] = 0;
     if (set_dt) p->dt = dt;
-}
-
-static int kernels_per_step(const vx_sim* s)
-{
-    int k = 1;
-    for (int a = 0; a < 3; a++) if (s->axis_first[a + 1] > s->axis_first[a]) k++;
-    if (s->any_poisson) k++;
-    return k;
 }
 
 static int ensure_graph(vx_sim* s)
@@ -331,6 +381,83 @@ static int ensure_graph(vx_sim* s)
     cudaGraphDestroy(g);
     if (e != cudaSuccess) { s->graph = nullptr; return cuda_fail(s, e, "cudaGraphInstantiate"); }
     return VX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stepping, lattice mode
+static void launch_lattice(vx_sim* s, int g, int first_of_call)
+{
+    k_lattice_step<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
+    s->launches++;
+}
+
+static int ensure_lattice_graph(vx_sim* s, int g0)
+{
+    if (s->lgraph[g0]) return VX_OK;
+    cudaGraph_t g = nullptr;
+    int64_t before = s->launches;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < GRAPH_STEPS; k++) launch_lattice(s, (g0 + k) & 1, 0);
+    cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    s->launches = before;
+    if (e != cudaSuccess) return cuda_fail(s, e, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(&s->lgraph[g0], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { s->lgraph[g0] = nullptr; return cuda_fail(s, e, "cudaGraphInstantiate"); }
+    return VX_OK;
+}
+
+// after the queued steps: read back the step parameters and re-align generations
+static int finish_lattice_call(vx_sim* s, int g_start, int launched, int* diverged_step)
+{
+    k_lattice_finish<<<1, 1, 0, s->stream>>>(s->params.p, (g_start + launched - 1) & 1); s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    const DevParams& p = *s->params_host;
+    s->time_host = p.time;
+    if (!p.div_latched) {
+        s->gen = (g_start + launched) & 1;
+        s->have_prev = true;
+        s->last_prev_dt = launched > 1 ? p.dt : s->prev_dt_host;
+        s->prev_dt_host = p.prev_dt;
+        return VX_OK;
+    }
+    // step number steps_done (0-based) diverged: it read generation g, wrote g^1.  Links keep the
+    // advanced state, voxels are not advanced (src/Voxelyze.cpp:263-269): copy them over.
+    const int g = (g_start + p.steps_done) & 1;
+    k_lattice_copy_voxels<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->N, s->pose0[g].p, s->pose1[g].p, s->mom0[g].p, s->mom1[g].p,
+                                                                  s->pose0[g ^ 1].p, s->pose1[g ^ 1].p, s->mom0[g ^ 1].p, s->mom1[g ^ 1].p, 1);
+    s->launches++;
+    CK(cudaStreamSynchronize(s->stream));
+    s->gen = g ^ 1;
+    s->have_prev = true;
+    s->last_prev_dt = p.steps_done > 0 ? p.dt : s->prev_dt_host;
+    s->prev_dt_host = p.prev_dt;
+    if (diverged_step) *diverged_step = p.steps_done;
+    return VX_DIVERGED;
+}
+
+static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
+{
+    if (dt < 0) {                                   // nu = 0: the recommended step is a constant of the model
+        int rc = vx_recommended_dt(s, &dt);
+        if (rc != VX_OK) return rc;
+        if (dt <= 0) return VX_OK;
+    }
+    k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
+    const int g0 = s->gen;
+    int done = 0;
+    launch_lattice(s, g0, 1); done++;
+    while (n_steps - done >= GRAPH_STEPS) {
+        const int g = (g0 + done) & 1;
+        int rc = ensure_lattice_graph(s, g);
+        if (rc != VX_OK) return rc;
+        CK(cudaGraphLaunch(s->lgraph[g], s->stream));
+        s->launches += GRAPH_STEPS; done += GRAPH_STEPS;
+    }
+    for (; done < n_steps; done++) launch_lattice(s, (g0 + done) & 1, 0);
+    return finish_lattice_call(s, g0, n_steps, diverged_step);
 }
 
 extern "C" {
@@ -365,7 +492,8 @@ void vx_destroy(vx_sim* s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->drop_graph();
-    s->pose0.release(); s->pose1.release(); s->mom0.release(); s->mom1.release();
+    for (int g = 0; g < 2; g++) { s->pose0[g].release(); s->pose1[g].release(); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); s->recf[g].release(); }
+    s->pair_lmat.release(); s->link_owner.release(); s->link_axis_dev.release();
     s->ext_idx.release(); s->ext_vox_dev.release(); s->vox_e2i_dev.release(); s->link_e2i_dev.release(); s->member_dev.release();
     s->pstrain.release(); s->slots.release(); s->slot_strain.release();
     s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release(); s->lstrain.release();
@@ -426,7 +554,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
 {
     if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
     CK(cudaSetDevice(s->device));
-    // ---- validate + bounding boxes per member
+    // ---- validate + bounding box
     int max_member = 0;
     int lo[3] = {32767, 32767, 32767}, hi[3] = {-32768, -32768, -32768};
     for (int i = 0; i < n; i++) {
@@ -515,23 +643,47 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     s->axis_first[3] = (int)s->l_i2e.size();
     s->l_e2i.resize(L);
     for (int i = 0; i < L; i++) s->l_e2i[s->l_i2e[i]] = i;
-    s->lk_mat.resize(L);
-    std::vector<int2> ends(L);
+
+    // ---- layout: a completely filled box (per member) without Poisson materials runs fused
+    bool poisson = false;
+    for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
+    s->lattice = n > 0 && cells == (long long)n && !poisson && !s->collisions && s->path != 1;
+    s->nx = (int)ext3[0]; s->ny = (int)ext3[1]; s->nz = (int)ext3[2];
+    s->link_owner.release(); s->link_axis_dev.release();
+
     for (int i = 0; i < L; i++) {
-        int e = s->l_i2e[i];
-        int id = link_material(s, s->vmat_id[s->lk_vn[e]], s->vmat_id[s->lk_vp[e]]);
+        int id = link_material(s, s->vmat_id[s->lk_vn[i]], s->vmat_id[s->lk_vp[i]]);
         if (id > 0xFFFF) return fail(s, VX_ERR_ARG, "too many link materials");
-        s->lk_mat[i] = (uint16_t)id;
-        ends[i] = make_int2(s->v_e2i[s->lk_vn[e]], s->v_e2i[s->lk_vp[e]]);
     }
 
     // ---- device memory
     size_t n1 = std::max(n, 1), l1 = std::max(L, 1);
-    CK(s->pose0.alloc(n1)); CK(s->pose1.alloc(n1)); CK(s->mom0.alloc(n1)); CK(s->mom1.alloc(n1));
-    CK(s->ext_idx.alloc(n1)); CK(s->slots.alloc(n1 * 36));
-    CK(s->vox_e2i_dev.alloc(n1)); CK(s->link_e2i_dev.alloc(l1)); CK(s->member_dev.alloc(n1));
-    CK(s->lends.alloc(l1)); CK(s->lmeta.alloc(l1)); CK(s->lstA.alloc(l1)); CK(s->lstB.alloc(l1)); CK(s->lstC.alloc(l1)); CK(s->lstrain.alloc(l1));
-    CK(s->pstrain.alloc(n1)); CK(s->slot_strain.alloc(n1 * 6));
+    CK(s->ext_idx.alloc(n1)); CK(s->vox_e2i_dev.alloc(n1)); CK(s->link_e2i_dev.alloc(l1)); CK(s->member_dev.alloc(n1));
+    if (s->lattice) {
+        for (int g = 0; g < 2; g++) {
+            CK(s->pose0[g].alloc(n1)); CK(s->pose1[g].alloc(n1)); CK(s->mom0[g].alloc(n1)); CK(s->mom1[g].alloc(n1));
+            CK(s->rec[g].alloc(n1 * 9)); CK(s->recf[g].alloc(n1 * 3));
+        }
+        s->slots.release(); s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release();
+        s->lstrain.release(); s->pstrain.release(); s->slot_strain.release();
+        s->lk_mat.clear();
+    } else {
+        CK(s->pose0[0].alloc(n1)); CK(s->pose1[0].alloc(n1)); CK(s->mom0[0].alloc(n1)); CK(s->mom1[0].alloc(n1));
+        for (int g = 0; g < 2; g++) { s->rec[g].release(); s->recf[g].release(); }
+        s->pose0[1].release(); s->pose1[1].release(); s->mom0[1].release(); s->mom1[1].release();
+        CK(s->slots.alloc(n1 * 36));
+        CK(s->lends.alloc(l1)); CK(s->lmeta.alloc(l1)); CK(s->lstA.alloc(l1)); CK(s->lstB.alloc(l1)); CK(s->lstC.alloc(l1)); CK(s->lstrain.alloc(l1));
+        CK(s->pstrain.alloc(n1)); CK(s->slot_strain.alloc(n1 * 6));
+        s->lk_mat.resize(L);
+        std::vector<int2> ends(L);
+        for (int i = 0; i < L; i++) {
+            int e = s->l_i2e[i];
+            s->lk_mat[i] = (uint16_t)link_material(s, s->vmat_id[s->lk_vn[e]], s->vmat_id[s->lk_vp[e]]);
+            ends[i] = make_int2(s->v_e2i[s->lk_vn[e]], s->v_e2i[s->lk_vp[e]]);
+        }
+        CK(cudaStreamSynchronize(s->stream));
+        if (L) CK(cudaMemcpy(s->lends.p, ends.data(), (size_t)L * sizeof(int2), cudaMemcpyHostToDevice));
+    }
     CK(cudaStreamSynchronize(s->stream));
     if (n) {
         CK(cudaMemcpy(s->vox_e2i_dev.p, s->v_e2i.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
@@ -539,10 +691,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
         for (int i = 0; i < n; i++) mem_internal[i] = s->member[s->v_i2e[i]];
         CK(cudaMemcpy(s->member_dev.p, mem_internal.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     }
-    if (L) {
-        CK(cudaMemcpy(s->link_e2i_dev.p, s->l_e2i.data(), (size_t)L * sizeof(int), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(s->lends.p, ends.data(), (size_t)L * sizeof(int2), cudaMemcpyHostToDevice));
-    }
+    if (L) CK(cudaMemcpy(s->link_e2i_dev.p, s->l_e2i.data(), (size_t)L * sizeof(int), cudaMemcpyHostToDevice));
     int rc = upload_tables(s);                     // new link materials may have appeared
     if (rc != VX_OK) return rc;
     return upload_initial_state(s, s->ambient);    // new voxels start at ambient temperature, src/Voxelyze.cpp:449
@@ -632,11 +781,12 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     if (!s || n_steps < 0) return VX_ERR_ARG;
     if (n_steps == 0 || dt == 0 || s->N == 0) return VX_OK;       // dt == 0: src/Voxelyze.cpp:253
     CK(cudaSetDevice(s->device));
+    if (s->lattice) return lattice_step(s, dt, n_steps, diverged_step);
     Frame f = s->frame();
     const bool per_step_dt = dt < 0 && s->any_poisson;
     k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, dt > 0 ? 1 : 0); s->launches++;
     if (dt < 0 && !per_step_dt) {                                  // constant recommended dt
-        launch_recommended_dt(s, f);
+        launch_recommended_dt(s);
         k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++;
     }
     int left = n_steps;
@@ -650,6 +800,7 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->time_host = s->params_host->time;
+    s->prev_dt_host = s->params_host->prev_dt;
     if (s->params_host->div_latched) {
         if (diverged_step) *diverged_step = s->params_host->steps_done;
         return VX_DIVERGED;
@@ -664,40 +815,58 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
     if (launches) launches[0] = launches[1] = launches[2] = 0;
     if (n_steps == 0 || dt == 0 || s->N == 0) return VX_OK;
     CK(cudaSetDevice(s->device));
-    Frame f = s->frame();
-    const bool per_step_dt = dt < 0 && s->any_poisson;
-    k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, dt > 0 ? 1 : 0); s->launches++;
-    if (dt < 0 && !per_step_dt) { launch_recommended_dt(s, f); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
     std::vector<cudaEvent_t> ev((size_t)n_steps * 4);
     for (auto& e : ev) CK(cudaEventCreate(&e));
-    for (int k = 0; k < n_steps; k++) {
-        int64_t l0 = s->launches;
-        CK(cudaEventRecord(ev[4 * k + 0], s->stream));
-        if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
-        if (per_step_dt) { launch_recommended_dt(s, f); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
-        int64_t l1 = s->launches;
-        CK(cudaEventRecord(ev[4 * k + 1], s->stream));
-        launch_links(s, f);
-        int64_t l2 = s->launches;
-        CK(cudaEventRecord(ev[4 * k + 2], s->stream));
-        k_voxel<<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0); s->launches++;
-        CK(cudaEventRecord(ev[4 * k + 3], s->stream));
-        if (launches) { launches[2] += (int)(l1 - l0); launches[0] += (int)(l2 - l1); launches[1] += 1; }
-    }
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    for (int k = 0; k < n_steps; k++) {
-        float a = 0, b = 0, c = 0, d = 0;
-        cudaEventElapsedTime(&a, ev[4 * k + 0], ev[4 * k + 1]);
-        cudaEventElapsedTime(&b, ev[4 * k + 1], ev[4 * k + 2]);
-        cudaEventElapsedTime(&c, ev[4 * k + 2], ev[4 * k + 3]);
-        cudaEventElapsedTime(&d, ev[4 * k + 0], ev[4 * k + 3]);
-        ms[2] += a; ms[0] += b; ms[1] += c; ms[3] += d;
+    int rc = VX_OK;
+    if (s->lattice) {
+        // one fused kernel per step: reported as the "link" group (it is the dominant kernel)
+        if (dt < 0) { rc = vx_recommended_dt(s, &dt); if (rc != VX_OK || dt <= 0) return rc; }
+        k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
+        const int g0 = s->gen;
+        for (int k = 0; k < n_steps; k++) {
+            CK(cudaEventRecord(ev[4 * k + 0], s->stream));
+            launch_lattice(s, (g0 + k) & 1, k == 0 ? 1 : 0);
+            CK(cudaEventRecord(ev[4 * k + 3], s->stream));
+            if (launches) launches[0] += 1;
+        }
+        rc = finish_lattice_call(s, g0, n_steps, nullptr);
+        for (int k = 0; k < n_steps; k++) { float d = 0; cudaEventElapsedTime(&d, ev[4 * k + 0], ev[4 * k + 3]); ms[0] += d; ms[3] += d; }
+    } else {
+        Frame f = s->frame();
+        const bool per_step_dt = dt < 0 && s->any_poisson;
+        k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, dt > 0 ? 1 : 0); s->launches++;
+        if (dt < 0 && !per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+        for (int k = 0; k < n_steps; k++) {
+            int64_t l0 = s->launches;
+            CK(cudaEventRecord(ev[4 * k + 0], s->stream));
+            if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
+            if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+            int64_t l1 = s->launches;
+            CK(cudaEventRecord(ev[4 * k + 1], s->stream));
+            launch_links(s, f);
+            int64_t l2 = s->launches;
+            CK(cudaEventRecord(ev[4 * k + 2], s->stream));
+            k_voxel<<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0); s->launches++;
+            CK(cudaEventRecord(ev[4 * k + 3], s->stream));
+            if (launches) { launches[2] += (int)(l1 - l0); launches[0] += (int)(l2 - l1); launches[1] += 1; }
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        for (int k = 0; k < n_steps; k++) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, ev[4 * k + 0], ev[4 * k + 1]);
+            cudaEventElapsedTime(&b, ev[4 * k + 1], ev[4 * k + 2]);
+            cudaEventElapsedTime(&c, ev[4 * k + 2], ev[4 * k + 3]);
+            cudaEventElapsedTime(&d, ev[4 * k + 0], ev[4 * k + 3]);
+            ms[2] += a; ms[0] += b; ms[1] += c; ms[3] += d;
+        }
+        s->time_host = s->params_host->time;
+        s->prev_dt_host = s->params_host->prev_dt;
+        rc = s->params_host->div_latched ? VX_DIVERGED : VX_OK;
     }
     for (auto& e : ev) cudaEventDestroy(e);
-    s->time_host = s->params_host->time;
-    return s->params_host->div_latched ? VX_DIVERGED : VX_OK;
+    return rc;
 }
 
 int vx_recommended_dt(vx_sim* s, float* dt)
@@ -706,9 +875,8 @@ int vx_recommended_dt(vx_sim* s, float* dt)
     *dt = 0.f;
     if (s->N == 0) return VX_OK;
     CK(cudaSetDevice(s->device));
-    Frame f = s->frame();
-    if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
-    launch_recommended_dt(s, f);
+    if (s->any_poisson && !s->lattice) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->frame()); s->launches++; }
+    launch_recommended_dt(s);
     CK(cudaMemcpyAsync(s->freq_host, s->freq2.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     float m; memcpy(&m, s->freq_host, 4);
@@ -749,6 +917,18 @@ static bool field_info(int field, int& what, int& comps, int& esize, bool& is_li
     return false;
 }
 
+// lattice mode: link index -> (owner voxel, axis), built on the first link download
+static int ensure_link_refs(vx_sim* s)
+{
+    if (s->link_owner.p || s->L == 0) return VX_OK;
+    std::vector<int> owner(s->L); std::vector<unsigned char> axis(s->L);
+    for (int i = 0; i < s->L; i++) { int e = s->l_i2e[i]; owner[i] = s->v_e2i[s->lk_vn[e]]; axis[i] = s->lk_axis[e]; }
+    CK(s->link_owner.alloc(s->L)); CK(s->link_axis_dev.alloc(s->L));
+    CK(cudaMemcpy(s->link_owner.p, owner.data(), (size_t)s->L * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->link_axis_dev.p, axis.data(), (size_t)s->L, cudaMemcpyHostToDevice));
+    return VX_OK;
+}
+
 int vx_download(vx_sim* s, int field, int first, int count, void* dst)
 {
     int what, comps, esize; bool is_link;
@@ -759,8 +939,16 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
     size_t bytes = (size_t)count * comps * esize;
     CK(cudaStreamSynchronize(s->stream));
     CK(s->staging.alloc(bytes));
-    k_gather<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), what, is_link ? s->link_e2i_dev.p : s->vox_e2i_dev.p, first, count,
-                                                       s->staging.p, s->axis_first[1], s->axis_first[2]);
+    if (s->lattice && is_link) {
+        int rc = ensure_link_refs(s);
+        if (rc != VX_OK) return rc;
+        LatLinkRef ref{s->link_owner.p, s->link_axis_dev.p};
+        k_lattice_gather_links<<<blocks_for(count), TPB, 0, s->stream>>>(s->lat_frame(s->gen), s->lat_frame(s->gen ^ 1), s->have_prev ? 1 : 0,
+                                                                         s->last_prev_dt, what, s->link_e2i_dev.p, ref, first, count, s->staging.p);
+    } else {
+        k_gather<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), what, is_link ? s->link_e2i_dev.p : s->vox_e2i_dev.p, first, count,
+                                                           s->staging.p, s->axis_first[1], s->axis_first[2]);
+    }
     s->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, s->staging.p, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -806,8 +994,9 @@ int vx_pose_plane(vx_sim* s, int iz, uint64_t* p0, uint64_t* p1, int* count, int
     auto lo = std::lower_bound(s->sort_key.begin(), s->sort_key.end(), key);
     auto hi = std::upper_bound(s->sort_key.begin(), s->sort_key.end(), key);
     size_t first = lo - s->sort_key.begin();
-    if (p0) *p0 = (uint64_t)(uintptr_t)(s->pose0.p + first);
-    if (p1) *p1 = (uint64_t)(uintptr_t)(s->pose1.p + first);
+    Frame f = s->frame();                          // current generation in lattice mode
+    if (p0) *p0 = (uint64_t)(uintptr_t)(f.pose0 + first);
+    if (p1) *p1 = (uint64_t)(uintptr_t)(f.pose1 + first);
     if (count) *count = (int)(hi - lo);
     if (rec_bytes) *rec_bytes = (int)sizeof(double4);
     return VX_OK;
@@ -841,6 +1030,8 @@ int vx_halo_import(vx_sim* s, int iz, uint64_t src0, uint64_t src1, int count)
 
 int64_t vx_launch_count(const vx_sim* s) { return s ? s->launches : 0; }
 int vx_sync(vx_sim* s) { if (!s) return VX_ERR_ARG; CK(cudaSetDevice(s->device)); CK(cudaStreamSynchronize(s->stream)); return VX_OK; }
-int vx_set_path(vx_sim* s, int path) { if (!s) return VX_ERR_ARG; s->path = path; s->drop_graph(); return VX_OK; }
+/* takes effect at the next vx_set_voxels */
+int vx_set_path(vx_sim* s, int path) { if (!s) return VX_ERR_ARG; s->path = path; return VX_OK; }
+int vx_active_path(const vx_sim* s) { return s && s->lattice ? 2 : 1; }
 
 } // extern "C"

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) k_link(int first, int count, Frame f)
     on.w = n0.w; on.x = n1.x; on.y = n1.y; on.z = n1.z;
     op.w = p0.w; op.x = p1.x; op.y = p1.y; op.z = p1.z;
     d3 fN, mN, fP, mP;
-    link_forces<AXIS>(mk3(n0.x, n0.y, n0.z), on, mk3(p0.x, p0.y, p0.z), op, rest, t_area, t_sum,
+    link_forces(AXIS, mk3(n0.x, n0.y, n0.z), on, mk3(p0.x, p0.y, p0.z), op, rest, t_area, t_sum,
                       damp_n, damp_p, lm, f.curve_e, f.curve_s, st, fN, mN, fP, mP);
 
     f.lstA[l] = make_double4(st.pos2.x, st.pos2.y, st.pos2.z, st.a1v.x);

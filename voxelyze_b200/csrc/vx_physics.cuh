@@ -101,24 +101,25 @@ __device__ __forceinline__ q4 q_align_to_x(d3 from)
     return q;
 }
 
-// link-axis swizzles: express vectors as if the link pointed along +X (include/VX_Link.h:112-117)
-template <int AXIS> __device__ __forceinline__ d3 to_axis_x(d3 v)
+// link-axis swizzles: express vectors as if the link pointed along +X (include/VX_Link.h:112-117).
+// `axis` is a compile-time constant in the per-axis kernels and a loop variable in the fused one.
+__device__ __forceinline__ d3 to_axis_x(int axis, d3 v)
 {
-    if (AXIS == 1) return mk3(v.y, -v.x, v.z);
-    if (AXIS == 2) return mk3(v.z, v.y, -v.x);
+    if (axis == 1) return mk3(v.y, -v.x, v.z);
+    if (axis == 2) return mk3(v.z, v.y, -v.x);
     return v;
 }
-template <int AXIS> __device__ __forceinline__ q4 to_axis_x(q4 q)
+__device__ __forceinline__ q4 to_axis_x(int axis, q4 q)
 {
     q4 r = q;
-    if (AXIS == 1) { r.x = q.y; r.y = -q.x; }
-    if (AXIS == 2) { r.x = q.z; r.z = -q.x; }
+    if (axis == 1) { r.x = q.y; r.y = -q.x; }
+    if (axis == 2) { r.x = q.z; r.z = -q.x; }
     return r;
 }
-template <int AXIS> __device__ __forceinline__ d3 to_axis_original(d3 v)
+__device__ __forceinline__ d3 to_axis_original(int axis, d3 v)
 {
-    if (AXIS == 1) return mk3(-v.y, v.x, v.z);
-    if (AXIS == 2) return mk3(-v.z, v.y, v.x);
+    if (axis == 1) return mk3(-v.y, v.x, v.z);
+    if (axis == 2) return mk3(-v.z, v.y, v.x);
     return v;
 }
 
@@ -189,8 +190,7 @@ __device__ __forceinline__ float link_update_strain(LinkState& st, const DevLink
 //      (2*sqrtMass*zeta/previousDt of each end, float), link material.
 // I/O: st (old pos2/angle1v/angle2v in, new out; strain memory; flags).
 // Out: force/moment on the negative and positive end voxel in that voxel's local frame.
-template <int AXIS>
-__device__ __forceinline__ void link_forces(d3 pN, q4 oN, d3 pP, q4 oP, double rest_len, float t_area, float t_sum,
+__device__ __forceinline__ void link_forces(const int axis, d3 pN, q4 oN, d3 pP, q4 oP, double rest_len, float t_area, float t_sum,
                                             float damp_n, float damp_p, const DevLinkMat& m,
                                             const float* __restrict__ ce, const float* __restrict__ cs,
                                             LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP)
@@ -198,9 +198,9 @@ __device__ __forceinline__ void link_forces(d3 pN, q4 oN, d3 pP, q4 oP, double r
     d3 old_pos2 = st.pos2, old_a1 = st.a1v, old_a2 = st.a2v;
 
     // --- orientLink
-    d3 pos2 = to_axis_x<AXIS>(pP - pN);
-    q4 ang1 = to_axis_x<AXIS>(oN);
-    q4 ang2 = to_axis_x<AXIS>(oP);
+    d3 pos2 = to_axis_x(axis, pP - pN);
+    q4 ang1 = to_axis_x(axis, oN);
+    q4 ang2 = to_axis_x(axis, oP);
     q4 total = qconj(ang1);
     pos2 = qrot(total, pos2);
     ang2 = qmul(total, ang2);
@@ -266,8 +266,8 @@ __device__ __forceinline__ void link_forces(d3 pN, q4 oN, d3 pP, q4 oP, double r
     if (!st.small_angle) { fN = qrot_inv(ang1, fN); mN = qrot_inv(ang1, mN); }
     fP = qrot_inv(ang2, fP);
     mP = qrot_inv(ang2, mP);
-    fN = to_axis_original<AXIS>(fN); fP = to_axis_original<AXIS>(fP);
-    mN = to_axis_original<AXIS>(mN); mP = to_axis_original<AXIS>(mP);
+    fN = to_axis_original(axis, fN); fP = to_axis_original(axis, fP);
+    mN = to_axis_original(axis, mN); mP = to_axis_original(axis, mP);
 }
 
 // ---------------------------------------------------------------------------------------------

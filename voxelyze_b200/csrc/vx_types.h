@@ -92,5 +92,6 @@ struct DevParams {
     int   div_latched;     // a previous step diverged: everything is frozen
     int   steps_done;      // completed steps since the last vx_step call
     int   col_stale;       // collision watch list must be rebuilt
-    int   pad;
+    int   pending;         // fused path: the previous step still has to be counted
+    int   div_flag[2];     // fused path: divergence flag of the step with that generation parity
 };

@@ -39,9 +39,11 @@ class Scenario:
         return len(self.ijk)
 
 
-def build(lib: VxLib, sc: Scenario, device: int = 0) -> Sim:
+def build(lib: VxLib, sc: Scenario, device: int = 0, path: int = 0) -> Sim:
+    """path: 0 auto, 1 force the general two-kernel path, 2 fused lattice path (CUDA library only)."""
     s = lib.create(sc.voxel_size, device)
     s.set_materials(sc.materials)
+    s.set_path(path)
     s.set_gravity(sc.gravity)
     s.enable_floor(sc.floor)
     s.set_voxels(sc.ijk, sc.mat, sc.sim_id)

@@ -29,6 +29,15 @@ def slab_range(nz: int, rank: int, world: int) -> Tuple[int, int]:
     return z0, z0 + base + (1 if rank < rem else 0)
 
 
+def _kernel_name(sim: Sim) -> str:
+    return ("k_lattice_step (fused link+voxel kernel, 1 launch per step)" if sim.active_path() == 2
+            else "k_link<AXIS> (3 launches per step, one per link axis)")
+
+
+def _path_name(sim: Sim) -> str:
+    return "fused lattice path" if sim.active_path() == 2 else "general two-kernel path"
+
+
 class _DevMem:
     """Exposes a raw device allocation to torch through __cuda_array_interface__."""
 
@@ -61,17 +70,18 @@ class SingleRunner:
         return self.sim.download("pos", self.sim.n_voxels - 1, 1)
 
     def dominant_kernel(self) -> str:
-        return "k_link<AXIS> (3 launches per step, one per link axis)"
+        return _kernel_name(self.sim)
 
     def path_name(self) -> str:
-        return "general two-kernel path"
+        return _path_name(self.sim)
 
 
 class SlabRunner:
     """Cantilever pattern of C5 (x=0 face fixed, -z load on the x=nx-1 face) split along z."""
 
     def __init__(self, lib: VxLib, nx: int, ny: int, nz: int, rank: int, world: int, device: int = 0,
-                 voxel_size: float = 0.005, tip_load: float = 1.0, material: Material = None, host_exchange: bool = False):
+                 voxel_size: float = 0.005, tip_load: float = 1.0, material: Material = None, host_exchange: bool = False,
+                 path: int = 0):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = rank, world
@@ -85,6 +95,7 @@ class SlabRunner:
         flags[(ijk[:, 2] < self.z0) | (ijk[:, 2] >= self.z1)] = VF_GHOST
         sim = lib.create(voxel_size, device)
         sim.set_materials([material or Material(E=1e6, rho=1e3)])
+        sim.set_path(path)
         sim.set_voxels(ijk, np.zeros(len(ijk), np.uint16), flags=flags)
         owned = flags == 0
         fixed = np.nonzero((ijk[:, 0] == 0) & owned)[0]
@@ -135,22 +146,26 @@ class SlabRunner:
         import torch
         dist = self.dist
         if self._bufs is None:
-            self._bufs = {}
-            for peer, send_z, recv_z in self._neighbours():
-                p0, p1, n, rb = self.sim.pose_plane(send_z)
-                assert n == self.plane
-                s0 = torch.as_tensor(_DevMem(p0, n * rb), device="cuda")
-                s1 = torch.as_tensor(_DevMem(p1, n * rb), device="cuda")
-                r0 = torch.empty(n * rb, dtype=torch.uint8, device="cuda")
-                r1 = torch.empty(n * rb, dtype=torch.uint8, device="cuda")
-                self._bufs[peer] = (s0, s1, r0, r1, recv_z)
-        ops = []
-        for peer, (s0, s1, r0, r1, _) in self._bufs.items():
-            ops += [dist.P2POp(dist.isend, s0, peer), dist.P2POp(dist.isend, s1, peer),
+            self._bufs = {"views": {}, "recv": {}}
+        views, recv = self._bufs["views"], self._bufs["recv"]
+        ops, imports = [], []
+        for peer, send_z, recv_z in self._neighbours():
+            # the fused lattice path ping-pongs generations: the current-state arrays move every step
+            p0, p1, n, rb = self.sim.pose_plane(send_z)
+            assert n == self.plane
+            for ptr in (p0, p1):
+                if ptr not in views:
+                    views[ptr] = torch.as_tensor(_DevMem(ptr, n * rb), device="cuda")
+            if peer not in recv:
+                recv[peer] = (torch.empty(n * rb, dtype=torch.uint8, device="cuda"),
+                              torch.empty(n * rb, dtype=torch.uint8, device="cuda"))
+            r0, r1 = recv[peer]
+            ops += [dist.P2POp(dist.isend, views[p0], peer), dist.P2POp(dist.isend, views[p1], peer),
                     dist.P2POp(dist.irecv, r0, peer), dist.P2POp(dist.irecv, r1, peer)]
+            imports.append((recv_z, r0, r1))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        for peer, (_, _, r0, r1, recv_z) in self._bufs.items():
+        for recv_z, r0, r1 in imports:
             self.sim.halo_import(recv_z, r0.data_ptr(), r1.data_ptr(), self.plane)
 
     def _exchange_host(self):
@@ -208,7 +223,7 @@ class SlabRunner:
         return self.sim.download(field, first, self.plane * (self.z1 - self.z0))
 
     def dominant_kernel(self) -> str:
-        return "k_link<AXIS> (3 launches per step, one per link axis)"
+        return _kernel_name(self.sim)
 
     def path_name(self) -> str:
-        return f"general two-kernel path, z-slab {self.rank}/{self.world} layers [{self.z0},{self.z1})"
+        return f"{_path_name(self.sim)}, z-slab {self.rank}/{self.world} layers [{self.z0},{self.z1})"
