@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="override lattice edge (testing only; reported in config)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="edge of the CPU baseline sample lattice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", type=int, default=0, help="kernel variant: 0 auto, 1 general, 2/3 fused lattice variants (ablation)")
     args = ap.parse_args()
     # >= 16 so that the 16-step CUDA graph is captured and instantiated before the timed region
     args.warmup = max(args.warmup, 16) if args.impl == "ours" else max(args.warmup, 1)
@@ -160,10 +161,10 @@ def main():
     stream = torch.cuda.current_stream()
     if world == 1:
         sc = scenarios.cantilever(edge, edge, edge, tip_load=1.0)
-        sim = scenarios.build(lib, sc, device=local)
+        sim = scenarios.build(lib, sc, device=local, path=args.path)
         runner = slab.SingleRunner(sim)
     else:
-        runner = slab.SlabRunner(lib, edge, edge, edge, rank, world, device=local)
+        runner = slab.SlabRunner(lib, edge, edge, edge, rank, world, device=local, path=args.path)
         sim = runner.sim
     sim.set_stream(stream.cuda_stream)
     dt = runner.recommended_dt()

@@ -92,11 +92,25 @@ def test_lattice_path_is_selected_for_full_boxes(product):
 def test_fused_and_general_paths_agree_bitwise(product):
     """Same physics functions, same summation order: the two device layouts give identical bits."""
     sc = scenarios.cantilever(12, 5, 4, tip_load=30.0)
-    a, dt, _ = parity.run(product, sc, 700, path=0)
-    b, _, _ = parity.run(product, sc, 700, path=1)
-    sa, sb = parity.snapshot(a), parity.snapshot(b)
-    for f in sa:
-        assert parity.bit_equal(sa[f], sb[f]), f
+    snaps = {}
+    for path in (0, 1, 3, 4):      # brick kernel (default), general two-kernel, per-voxel fused, z-marching fused
+        sim, dt, _ = parity.run(product, sc, 700, path=path)
+        snaps[path] = parity.snapshot(sim)
+    for path in (1, 3, 4):
+        for f in snaps[0]:
+            assert parity.bit_equal(snaps[0][f], snaps[path][f]), (path, f)
+
+
+@pytest.mark.parametrize("path", [0, 3, 4], ids=["brick", "pervoxel", "march"])
+def test_fused_kernels_odd_sizes(product, oracle, path):
+    """Lattice edges that are not multiples of the brick (8x4x4), the warp segment (31), the CTA
+    rows (4) or the z-chunk (32): partial bricks / segments / row groups, several z-chunks."""
+    sc = scenarios.cantilever(33, 6, 35, tip_load=200.0)
+    g, dt, _ = parity.run(product, sc, 40, path=path)
+    o, _, _ = parity.run(oracle, sc, 40, dt=dt)
+    assert g.active_path() == 2
+    err = parity.rel_errors(parity.snapshot(g), parity.snapshot(o), sc)
+    assert err["pos"] <= 1e-9 and err["orient"] <= 1e-9, err
 
 
 def test_diverging_step_semantics(product, oracle):

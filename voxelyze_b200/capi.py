@@ -387,7 +387,7 @@ def _load(path: str) -> VxLib:
 
 def load_product() -> VxLib:
     """The CUDA library.  Raises if it has not been built; never substitutes a CPU path."""
-    return _load(PRODUCT_SO)
+    return _load(os.environ.get("VX_PRODUCT_SO", PRODUCT_SO))   # override: kernel-variant experiments only
 
 
 def load_oracle() -> VxLib:

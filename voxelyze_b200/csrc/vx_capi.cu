@@ -99,6 +99,7 @@ struct vx_sim {
     DevParams* params_host = nullptr;     // pinned mirror
     unsigned int* freq_host = nullptr;    // pinned
 
+    bool uni = false; DevVoxMat vm0{}; DevLinkMat lm0{};          // single-material model: rows passed by value
     cudaGraphExec_t graph = nullptr; int graph_kernels = 0;      // general mode
     cudaGraphExec_t lgraph[2] = {nullptr, nullptr};              // lattice mode, keyed by starting generation
     int64_t launches = 0;
@@ -114,6 +115,7 @@ struct vx_sim {
         f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
         f.ext = ext_dev.p; f.params = params.p;
         f.col_start = nullptr; f.col_ref = nullptr; f.col_force = nullptr;
+        f.vm0 = vm0; f.lm0 = lm0;
         return f;
     }
     // lattice frame reading generation g and writing generation g^1
@@ -133,6 +135,7 @@ struct vx_sim {
         }
         f.ext_idx = ext_idx.p; f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
         f.pair_lmat = pair_lmat.p; f.ext = ext_dev.p; f.params = params.p;
+        f.vm0 = vm0; f.lm0 = lm0;
         return f;
     }
     void drop_graph()
@@ -187,6 +190,8 @@ static int upload_tables(vx_sim* s)
         d.gravity_force = -p.mass * 9.80665f * s->grav;
         d.nom_f = (float)s->vox_size;
         d.pad = 0;
+        d.mass_inv_d = d.mass_inv; d.inertia_inv_d = d.inertia_inv; d.glob_damp_t_d = d.glob_damp_t;
+        d.glob_damp_r_d = d.glob_damp_r; d.coll_damp_t_d = d.coll_damp_t; d.gravity_force_d = d.gravity_force;
         if (m.nu != 0.0f) s->any_poisson = true;
     }
     std::vector<DevLinkMat> lm(s->lmats.size());
@@ -204,7 +209,7 @@ static int upload_tables(vx_sim* s)
         ce.insert(ce.end(), m.eps.begin(), m.eps.end());
         cs.insert(cs.end(), m.sig.begin(), m.sig.end());
         d.E = m.E; d.nu = m.nu; d.e_hat = m.e_hat; d.eps_yield = m.eps_yield; d.eps_fail = m.eps_fail;
-        d.a1 = k.a1; d.a2 = k.a2; d.b1 = k.b1; d.b2 = k.b2; d.b3 = k.b3;
+        d.pad = 0; d.a1 = k.a1; d.a2 = k.a2; d.b1 = k.b1; d.b2 = k.b2; d.b3 = k.b3;
         d.sq_a1 = k.sq_a1; d.sq_a2_ip = k.sq_a2_ip; d.sq_b1 = k.sq_b1; d.sq_b2_fmp = k.sq_b2_fmp; d.sq_b3_ip = k.sq_b3_ip;
         if (m.nu != 0.0f) s->any_poisson = true;
         pair[(size_t)e.a * nm + e.b] = pair[(size_t)e.b * nm + e.a] = (uint16_t)i;
@@ -223,6 +228,8 @@ static int upload_tables(vx_sim* s)
         CK(cudaMemcpy(s->curve_s.p, cs.data(), cs.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     CK(cudaMemcpy(s->pair_lmat.p, pair.data(), pair.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    s->uni = vm.size() == 1 && lm.size() == 1 && lm[0].linear && !s->any_poisson;
+    if (s->uni) { s->vm0 = vm[0]; s->lm0 = lm[0]; }
     s->drop_graph();
     return VX_OK;
 }
@@ -324,9 +331,15 @@ static void launch_links(vx_sim* s, const Frame& f)
         int cnt = af[a + 1] - af[a];
         if (cnt <= 0) continue;
         int g = blocks_for(cnt);
-        if (a == 0) { if (P) k_link<0, true><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); else k_link<0, false><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); }
-        if (a == 1) { if (P) k_link<1, true><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); else k_link<1, false><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); }
-        if (a == 2) { if (P) k_link<2, true><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); else k_link<2, false><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); }
+        const bool U = s->uni;
+#define VX_LAUNCH_LINK(AX) do { \
+        if (P) k_link<AX, true, false><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); \
+        else if (U) k_link<AX, false, true><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); \
+        else k_link<AX, false, false><<<g, TPB, 0, s->stream>>>(af[a], cnt, f); } while (0)
+        if (a == 0) VX_LAUNCH_LINK(0);
+        if (a == 1) VX_LAUNCH_LINK(1);
+        if (a == 2) VX_LAUNCH_LINK(2);
+#undef VX_LAUNCH_LINK
         s->launches++;
     }
 }
@@ -348,14 +361,20 @@ static void launch_recommended_dt(vx_sim* s)
     s->launches++;
 }
 
+static void launch_voxel(vx_sim* s, const Frame& f)
+{
+    if (s->uni) k_voxel<true><<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0);
+    else k_voxel<false><<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0);
+    s->launches++;
+}
+
 // one doTimeStep (src/Voxelyze.cpp:251-284); per_step_dt: dt < 0 with Poisson materials
 static void launch_step(vx_sim* s, const Frame& f, bool per_step_dt)
 {
     if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
     if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
     launch_links(s, f);
-    k_voxel<<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0);
-    s->launches++;
+    launch_voxel(s, f);
 }
 
 __global__ void k_begin(DevParams* p, float dt, int set_dt)
@@ -387,7 +406,27 @@ static int ensure_graph(vx_sim* s)
 // stepping, lattice mode
 static void launch_lattice(vx_sim* s, int g, int first_of_call)
 {
-    k_lattice_step<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
+    if (s->path == 3) {                  // ablation: one thread per voxel, all six links re-evaluated
+        if (s->uni) k_lattice_step<true><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
+        else k_lattice_step<false><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
+    } else if (s->path != 4) {           // default: 8x4x4 bricks, thread per link evaluation + shared-memory slots
+        const int ntx = (s->nx + VX_TILE_X - 1) / VX_TILE_X, nty = (s->ny + VX_TILE_Y - 1) / VX_TILE_Y, ntz = (s->nz + VX_TILE_Z - 1) / VX_TILE_Z;
+        const long long grid = (long long)ntx * nty * ntz * s->n_members;
+        static bool opted_in = false;    // > 48 KB of dynamic shared memory needs a one-time opt-in per function
+        if (!opted_in) {
+            cudaFuncSetAttribute(k_lattice_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TILE_SMEM);
+            cudaFuncSetAttribute(k_lattice_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TILE_SMEM);
+            opted_in = true;
+        }
+        if (s->uni) k_lattice_tile<true><<<(unsigned)grid, VX_TILE_THREADS, VX_TILE_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ntx, nty, ntz);
+        else k_lattice_tile<false><<<(unsigned)grid, VX_TILE_THREADS, VX_TILE_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ntx, nty, ntz);
+    } else {                             // ablation: z-marching warps, X by shuffle, Z by register carry
+        const int n_seg = (s->nx + 30) / 31, n_yg = (s->ny + VX_MARCH_ROWS - 1) / VX_MARCH_ROWS;
+        const int n_zc = (s->nz + VX_MARCH_ZL - 1) / VX_MARCH_ZL;
+        const long long grid = (long long)n_seg * n_yg * n_zc * s->n_members;
+        if (s->uni) k_lattice_march<true><<<(unsigned)grid, 32 * VX_MARCH_ROWS, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, n_seg, n_yg, n_zc);
+        else k_lattice_march<false><<<(unsigned)grid, 32 * VX_MARCH_ROWS, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, n_seg, n_yg, n_zc);
+    }
     s->launches++;
 }
 
@@ -846,7 +885,7 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
             launch_links(s, f);
             int64_t l2 = s->launches;
             CK(cudaEventRecord(ev[4 * k + 2], s->stream));
-            k_voxel<<<blocks_for(s->N), TPB, 0, s->stream>>>(f, s->floor_on ? 1 : 0, s->collisions ? 1 : 0); s->launches++;
+            launch_voxel(s, f);
             CK(cudaEventRecord(ev[4 * k + 3], s->stream));
             if (launches) { launches[2] += (int)(l1 - l0); launches[0] += (int)(l2 - l1); launches[1] += 1; }
         }

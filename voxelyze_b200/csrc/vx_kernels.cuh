@@ -30,6 +30,9 @@ struct Frame {
     const DevVoxMat* vmat; const DevLinkMat* lmat; const float* curve_e; const float* curve_s;
     const DevExt* ext;
     DevParams* params;
+    // single-material models: the two table rows travel in the kernel parameters (constant bank),
+    // so material constants cost no load instructions (template parameter UNI)
+    DevVoxMat vm0; DevLinkMat lm0;
     // collisions (per voxel CSR of signed contact references)
     const int* col_start; const int* col_ref; const float4* col_force;
 };
@@ -66,7 +69,7 @@ __device__ __forceinline__ float transverse_strain_sum(const DevVoxMat& m, int a
     return ps.x + ps.y;
 }
 
-template <int AXIS, bool POISSON>
+template <int AXIS, bool POISSON, bool UNI>
 __global__ void __launch_bounds__(128) k_link(int first, int count, Frame f)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,9 +88,9 @@ __global__ void __launch_bounds__(128) k_link(int first, int count, Frame f)
 
     const uint32_t hn = meta_hi(n1.w), hp = meta_hi(p1.w);
     const float tn = meta_temp(n1.w), tp = meta_temp(p1.w);
-    const DevVoxMat& vmn = f.vmat[hn & VM_MAT_MASK];
-    const DevVoxMat& vmp = f.vmat[hp & VM_MAT_MASK];
-    const DevLinkMat lm = f.lmat[lm_bits & LM_MAT_MASK];
+    const DevVoxMat& vmn = UNI ? f.vm0 : f.vmat[hn & VM_MAT_MASK];
+    const DevVoxMat& vmp = UNI ? f.vm0 : f.vmat[hp & VM_MAT_MASK];
+    const DevLinkMat& lm = UNI ? f.lm0 : f.lmat[lm_bits & LM_MAT_MASK];
 
     // CVX_Link::updateRestLength (src/VX_Link.cpp:137-140), (1+temp*cte) in float
     double rest = 0.5 * (vmn.size[AXIS] * (1 + tn * vmn.cte) + vmp.size[AXIS] * (1 + tp * vmp.cte));
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(128) k_link(int first, int count, Frame f)
     }
 }
 
+template <bool UNI>
 __global__ void __launch_bounds__(128) k_voxel(Frame f, int floor_on, int collisions)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(128) k_voxel(Frame f, int floor_on, int collis
             M = M + mk3(b.y, c.x, c.y);
         }
     }
-    const DevVoxMat& vm = f.vmat[s.bits & VM_MAT_MASK];
+    const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[s.bits & VM_MAT_MASK];
     const DevExt* ext = (s.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
 
     voxel_integrate(s, F, M, mk3(0.0, 0.0, 0.0), false, vm, ext, dt, floor_on != 0);

@@ -42,6 +42,7 @@ struct LatFrame {
     const uint16_t* pair_lmat;      // [n_mat][n_mat] -> link material
     const DevExt* ext;
     DevParams* params;
+    DevVoxMat vm0; DevLinkMat lm0;  // single-material models: rows in the constant bank (UNI)
 };
 
 __device__ __forceinline__ void lat_decode(double2 a, double2 b, double2 c, float4 s, uint32_t lflags, LinkState& st)
@@ -64,14 +65,15 @@ __device__ __forceinline__ void lat_encode(const LinkState& st, double2& a, doub
 
 // evaluates link (owner, axis) between negative-end voxel N and positive-end voxel P from the
 // current generation; returns forces on both ends and the advanced link state
+template <bool UNI>
 __device__ __forceinline__ void lat_eval_link(const LatFrame& f, int axis, int owner, uint32_t owner_bits,
                                               double4 n0, double4 n1, double4 p0, double4 p1, float prev_dt,
                                               LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP)
 {
     const uint32_t hn = meta_hi(n1.w), hp = meta_hi(p1.w);
-    const DevVoxMat& vmn = f.vmat[hn & VM_MAT_MASK];
-    const DevVoxMat& vmp = f.vmat[hp & VM_MAT_MASK];
-    const DevLinkMat lm = f.lmat[f.pair_lmat[(hn & VM_MAT_MASK) * f.n_mat + (hp & VM_MAT_MASK)]];
+    const DevVoxMat& vmn = UNI ? f.vm0 : f.vmat[hn & VM_MAT_MASK];
+    const DevVoxMat& vmp = UNI ? f.vm0 : f.vmat[hp & VM_MAT_MASK];
+    const DevLinkMat& lm = UNI ? f.lm0 : f.lmat[f.pair_lmat[(hn & VM_MAT_MASK) * f.n_mat + (hp & VM_MAT_MASK)]];
     double2 ra = __ldg(f.c_rec[axis][0] + owner), rb = __ldg(f.c_rec[axis][1] + owner), rc = __ldg(f.c_rec[axis][2] + owner);
     float4 rs = __ldg(f.c_recf[axis] + owner);
     lat_decode(ra, rb, rc, rs, (owner_bits >> (VM_LFLAG_SHIFT + 2 * axis)) & 3u, st);
@@ -89,7 +91,14 @@ __device__ __forceinline__ void lat_eval_link(const LatFrame& f, int axis, int o
 // dt lives in device memory (p->dt) so that captured graphs survive a change of time step.
 // first_of_call: the first step of a vx_step call damps with the previous call's dt
 // (CVX_Voxel::previousDt), all later steps of the call with dt itself.
-__global__ void __launch_bounds__(128) k_lattice_step(LatFrame f, int parity, int first_of_call, int floor_on)
+#ifndef VX_LAT_MINBLOCKS
+#define VX_LAT_MINBLOCKS 1
+#endif
+#ifndef VX_LAT_UNROLL
+#define VX_LAT_UNROLL 1
+#endif
+template <bool UNI>
+__global__ void __launch_bounds__(128, VX_LAT_MINBLOCKS) k_lattice_step(LatFrame f, int parity, int first_of_call, int floor_on)
 {
     DevParams* p = f.params;
     const int frozen = p->div_flag[parity ^ 1] | p->div_latched;   // did the previous step diverge?
@@ -112,7 +121,8 @@ __global__ void __launch_bounds__(128) k_lattice_step(LatFrame f, int parity, in
     uint32_t new_bits = vs.bits;
 
     d3 F = mk3(0.0, 0.0, 0.0), M = mk3(0.0, 0.0, 0.0);
-#pragma unroll 1
+    constexpr int kUnroll = VX_LAT_UNROLL;
+#pragma unroll kUnroll
     for (int k = 0; k < 6; k++) {                                  // slot order = reference summation order
         if (!(mask & (1u << k))) continue;
         const int axis = k >> 1;
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(128) k_lattice_step(LatFrame f, int parity, in
         // one inlined copy of the link physics serves both roles: select the operands first
         const double4 n0 = i_am_neg ? s0 : u0, n1 = i_am_neg ? s1 : u1;
         const double4 p0 = i_am_neg ? u0 : s0, p1 = i_am_neg ? u1 : s1;
-        lat_eval_link(f, axis, i_am_neg ? v : u, i_am_neg ? vs.bits : meta_hi(u1.w), n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
+        lat_eval_link<UNI>(f, axis, i_am_neg ? v : u, i_am_neg ? vs.bits : meta_hi(u1.w), n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
         if (i_am_neg) {
             F = F + fN; M = M + mN;
             double2 ra, rb, rc; float4 rs; uint32_t lf;
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(128) k_lattice_step(LatFrame f, int parity, in
     vs.lin = mk3(m0.x, m0.y, m0.z);
     vs.ang = mk3(m0.w, m1.x, m1.y);
     if (!(vs.bits & VM_GHOST)) {
-        const DevVoxMat& vm = f.vmat[vs.bits & VM_MAT_MASK];
+        const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
         const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
         voxel_integrate(vs, F, M, mk3(0.0, 0.0, 0.0), false, vm, ext, dt, floor_on != 0);
     }
@@ -199,7 +209,7 @@ __global__ void k_lattice_gather_links(LatFrame cur, LatFrame prev, int have_pre
             const int pv = owner + stride;
             double4 n0 = prev.c_pose0[owner], n1 = prev.c_pose1[owner], p0 = prev.c_pose0[pv], p1 = prev.c_pose1[pv];
             LinkState st; d3 fN, mN, fP, mP;
-            lat_eval_link(prev, axis, owner, meta_hi(n1.w), n0, n1, p0, p1, prev_dt_of_last, st, fN, mN, fP, mP);
+            lat_eval_link<false>(prev, axis, owner, meta_hi(n1.w), n0, n1, p0, p1, prev_dt_of_last, st, fN, mN, fP, mP);
             r = what == G_FORCE_NEG ? fN : what == G_FORCE_POS ? fP : what == G_MOMENT_NEG ? mN : mP;
         }
         d[3 * k] = r.x; d[3 * k + 1] = r.y; d[3 * k + 2] = r.z;
@@ -247,6 +257,354 @@ __global__ void __launch_bounds__(256) k_lattice_max_freq(LatFrame f, unsigned i
     }
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
     if ((threadIdx.x & 31) == 0 && best > 0.0f) atomicMax(out, __float_as_uint(best));
+}
+
+// =================================================================================================
+// k_lattice_march -- the fused step with the redundant link evaluations removed where the hardware
+// offers a free exchange path:
+//   X: a warp covers 31 consecutive voxels of one x-row plus one overlap lane (lane 0 = last voxel
+//      of the previous segment).  Every lane evaluates the +X link of its voxel once; the force on
+//      the positive end travels one lane up with __shfl_up_sync.
+//   Z: the warp marches along z over a chunk of ZL planes; the force its +Z link exerts on the
+//      voxel above is carried in registers to the next iteration (where that voxel is "me"), and
+//      the pose of the voxel above is loaded once and becomes the own pose of the next iteration.
+//   Y: the -Y link is still re-evaluated by the positive-end voxel (identical inputs, identical bits).
+// => 1 + 1/31 (X) + 2 (Y) + 1 + 1/ZL (Z) = ~4.1 link evaluations per voxel instead of 6, and the
+//    long-distance (one z-plane) re-read of neighbour poses and link records disappears.
+// Summation order per voxel is unchanged: X+, X-, Y+, Y-, Z+, Z- (src/VX_Voxel.cpp:238-240).
+// =================================================================================================
+struct Pose { double4 a, b; };          // a = {pos.xyz, orient.w}, b = {orient.xyz, meta}
+
+__device__ __forceinline__ Pose lat_load_pose(const LatFrame& f, int v) { Pose p; p.a = ld4(f.c_pose0 + v); p.b = ld4(f.c_pose1 + v); return p; }
+__device__ __forceinline__ double shfl_down_d(double x, int d) { return __shfl_down_sync(0xffffffffu, x, d); }
+__device__ __forceinline__ double shfl_up_d(double x, int d) { return __shfl_up_sync(0xffffffffu, x, d); }
+__device__ __forceinline__ Pose shfl_down_pose(const Pose& p)
+{
+    Pose r;
+    r.a = make_double4(shfl_down_d(p.a.x, 1), shfl_down_d(p.a.y, 1), shfl_down_d(p.a.z, 1), shfl_down_d(p.a.w, 1));
+    r.b = make_double4(shfl_down_d(p.b.x, 1), shfl_down_d(p.b.y, 1), shfl_down_d(p.b.z, 1), shfl_down_d(p.b.w, 1));
+    return r;
+}
+__device__ __forceinline__ d3 shfl_up_d3(d3 v) { return mk3(shfl_up_d(v.x, 1), shfl_up_d(v.y, 1), shfl_up_d(v.z, 1)); }
+
+// evaluates link (owner, AXIS); OWNER: also stores the advanced record and returns the new mode bits
+template <int AXIS, bool OWNER, bool UNI>
+__device__ __forceinline__ void lat_link(const LatFrame& f, int owner, uint32_t owner_bits, const Pose& N, const Pose& P,
+                                         float prev_dt, int parity, uint32_t& new_bits, d3& fN, d3& mN, d3& fP, d3& mP)
+{
+    LinkState st;
+    lat_eval_link<UNI>(f, AXIS, owner, owner_bits, N.a, N.b, P.a, P.b, prev_dt, st, fN, mN, fP, mP);
+    if (OWNER) {
+        double2 ra, rb, rc; float4 rs; uint32_t lf;
+        lat_encode(st, ra, rb, rc, rs, lf);
+        f.n_rec[AXIS][0][owner] = ra; f.n_rec[AXIS][1][owner] = rb; f.n_rec[AXIS][2][owner] = rc; f.n_recf[AXIS][owner] = rs;
+        new_bits = (new_bits & ~(3u << (VM_LFLAG_SHIFT + 2 * AXIS))) | (lf << (VM_LFLAG_SHIFT + 2 * AXIS));
+        if (st.strain > 100) f.params->div_flag[parity] = 1;      // src/Voxelyze.cpp:265
+    }
+}
+
+#ifndef VX_MARCH_ZL
+#define VX_MARCH_ZL 32
+#endif
+#ifndef VX_MARCH_MINBLOCKS
+#define VX_MARCH_MINBLOCKS 3
+#endif
+#define VX_MARCH_ROWS 4                 // warps (y-rows) per CTA
+
+template <bool UNI>
+__global__ void __launch_bounds__(32 * VX_MARCH_ROWS, VX_MARCH_MINBLOCKS)
+k_lattice_march(LatFrame f, int parity, int first_of_call, int floor_on, int n_seg, int n_yg, int n_zc)
+{
+    DevParams* p = f.params;
+    const int frozen = p->div_flag[parity ^ 1] | p->div_latched;
+    const float dt = p->dt;
+    const float prev_dt = first_of_call ? p->prev_dt : dt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (frozen) p->div_latched = 1;
+        else if (p->pending) { p->steps_done += 1; p->time += dt; }
+        if (!frozen) p->pending = 1;
+    }
+    if (frozen) return;
+
+    const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+    int b = blockIdx.x;
+    const int seg = b % n_seg; b /= n_seg;
+    const int yg = b % n_yg; b /= n_yg;
+    const int zc = b % n_zc; const int member = b / n_zc;
+    const int y = yg * VX_MARCH_ROWS + row;
+    if (y >= f.ny) return;                                         // whole warp
+    const int x = seg * 31 - 1 + lane;
+    const bool has_voxel = x >= 0 && x < f.nx;
+    const bool real = has_voxel && lane >= 1;                      // lane 0 only feeds the X- force of lane 1
+    const int z0 = zc * VX_MARCH_ZL;
+    const int z1 = min(z0 + VX_MARCH_ZL, f.nz);
+    const int xs = has_voxel ? x : (x < 0 ? 0 : f.nx - 1);         // clamp so that idle lanes load valid memory
+    int v = ((member * f.nz + z0) * f.ny + y) * f.nx + xs;
+
+    Pose S = lat_load_pose(f, v);
+    d3 zf = mk3(0.0, 0.0, 0.0), zm = mk3(0.0, 0.0, 0.0);           // force/moment of the -Z link on this voxel
+    if (real && z0 > 0 && ((meta_hi(S.b.w) >> VM_LINK_SHIFT) & 0x20u)) {   // chunk start: re-evaluate the link from below
+        Pose D = lat_load_pose(f, v - f.nxy);
+        d3 fN, mN; uint32_t nb = 0;
+        lat_link<2, false, UNI>(f, v - f.nxy, meta_hi(D.b.w), D, S, prev_dt, parity, nb, fN, mN, zf, zm);
+    }
+
+    for (int z = z0; z < z1; z++, v += f.nxy) {
+        const uint32_t bits = meta_hi(S.b.w);
+        const uint32_t mask = has_voxel ? ((bits >> VM_LINK_SHIFT) & 0x3Fu) : 0u;
+        uint32_t new_bits = bits;
+        d3 F = mk3(0.0, 0.0, 0.0), M = mk3(0.0, 0.0, 0.0);
+        d3 fN, mN, fP, mP;
+
+        // ---- X: one evaluation per link, positive-end force shuffled one lane up
+        Pose XP = shfl_down_pose(S);
+        if (lane == 31 && (mask & 0x01u)) XP = lat_load_pose(f, v + 1);
+        d3 xf = mk3(0.0, 0.0, 0.0), xm = mk3(0.0, 0.0, 0.0);
+        if (mask & 0x01u) {
+            if (real) lat_link<0, true, UNI>(f, v, bits, S, XP, prev_dt, parity, new_bits, fN, mN, xf, xm);
+            else lat_link<0, false, UNI>(f, v, bits, S, XP, prev_dt, parity, new_bits, fN, mN, xf, xm);
+            F = F + fN; M = M + mN;
+        }
+        xf = shfl_up_d3(xf); xm = shfl_up_d3(xm);
+        if (mask & 0x02u) { F = F + xf; M = M + xm; }
+
+        // the voxel above becomes "me" in the next iteration
+        Pose U = S;
+        if (z + 1 < f.nz && has_voxel) U = lat_load_pose(f, v + f.nxy);
+
+        if (real) {
+            // ---- Y: own +Y link, then the -Y link re-evaluated from the positive end
+            if (mask & 0x04u) {
+                Pose YP = lat_load_pose(f, v + f.nx);
+                lat_link<1, true, UNI>(f, v, bits, S, YP, prev_dt, parity, new_bits, fN, mN, fP, mP);
+                F = F + fN; M = M + mN;
+            }
+            if (mask & 0x08u) {
+                Pose YM = lat_load_pose(f, v - f.nx);
+                uint32_t nb = 0;
+                lat_link<1, false, UNI>(f, v - f.nx, meta_hi(YM.b.w), YM, S, prev_dt, parity, nb, fN, mN, fP, mP);
+                F = F + fP; M = M + mP;
+            }
+            // ---- Z: own +Z link (its force on the voxel above is carried), then the carried -Z force
+            d3 nzf = mk3(0.0, 0.0, 0.0), nzm = mk3(0.0, 0.0, 0.0);
+            if (mask & 0x10u) {
+                lat_link<2, true, UNI>(f, v, bits, S, U, prev_dt, parity, new_bits, fN, mN, nzf, nzm);
+                F = F + fN; M = M + mN;
+            }
+            if (mask & 0x20u) { F = F + zf; M = M + zm; }
+            zf = nzf; zm = nzm;
+
+            // ---- integrate and store the next generation
+            double4 m0 = ld4(f.c_mom0 + v); double2 m1 = __ldg(f.c_mom1 + v);
+            VoxelState vs;
+            vs.bits = new_bits; vs.temp = meta_temp(S.b.w);
+            vs.pos = mk3(S.a.x, S.a.y, S.a.z);
+            vs.orient.w = S.a.w; vs.orient.x = S.b.x; vs.orient.y = S.b.y; vs.orient.z = S.b.z;
+            vs.lin = mk3(m0.x, m0.y, m0.z);
+            vs.ang = mk3(m0.w, m1.x, m1.y);
+            if (!(vs.bits & VM_GHOST)) {
+                const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
+                const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
+                voxel_integrate(vs, F, M, mk3(0.0, 0.0, 0.0), false, vm, ext, dt, floor_on != 0);
+            }
+            f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
+            f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
+            f.n_mom0[v] = make_double4(vs.lin.x, vs.lin.y, vs.lin.z, vs.ang.x);
+            f.n_mom1[v] = make_double2(vs.ang.y, vs.ang.z);
+        }
+        S = U;
+    }
+}
+
+
+// =================================================================================================
+// k_lattice_tile -- fused step, tile formulation (the default lattice kernel).
+//
+// A CTA owns a TX x TY x TZ = 8 x 4 x 4 brick of voxels.  Phase 1 is "one thread per link
+// evaluation" exactly like the general link kernel (short threads, high occupancy): the 464 links
+// that touch the brick (304 inside it, 160 crossing one of its faces) are evaluated once each and
+// the force/moment on each end that lies inside the brick is written to a shared-memory slot
+// slot[link direction][component][voxel].  Links crossing a face are evaluated by both bricks from
+// identical inputs; only the brick holding the negative end (the owner) stores the advanced record.
+// Phase 2 is "one thread per voxel": gather the six slots in reference order, integrate, store.
+// => 3.6 link evaluations per voxel instead of 6, forces never leave the SM, and both phases keep
+//    the simple, wide thread shape that runs at DRAM speed in the general path.
+// =================================================================================================
+#define VX_TILE_X 8
+#define VX_TILE_Y 4
+#define VX_TILE_Z 4
+#define VX_TILE_VOX (VX_TILE_X * VX_TILE_Y * VX_TILE_Z)                       // 128
+#define VX_TILE_EX ((VX_TILE_X + 1) * VX_TILE_Y * VX_TILE_Z)                  // 144 x-links
+#define VX_TILE_EY (VX_TILE_X * (VX_TILE_Y + 1) * VX_TILE_Z)                  // 160 y-links
+#define VX_TILE_EZ (VX_TILE_X * VX_TILE_Y * (VX_TILE_Z + 1))                  // 160 z-links
+#define VX_TILE_EVALS (VX_TILE_EX + VX_TILE_EY + VX_TILE_EZ)                  // 464
+#define VX_TILE_THREADS 256
+#ifndef VX_TILE_MINBLOCKS
+#define VX_TILE_MINBLOCKS 2
+#endif
+
+#define VX_TILE_HX (VX_TILE_X + 2)
+#define VX_TILE_HY (VX_TILE_Y + 2)
+#define VX_TILE_HZ (VX_TILE_Z + 2)
+#define VX_TILE_HALO (VX_TILE_HX * VX_TILE_HY * VX_TILE_HZ)                    // 360 staged poses
+
+#define VX_TILE_SMEM (2 * VX_TILE_HALO * 32 + 6 * 6 * VX_TILE_VOX * 8 + 3 * VX_TILE_VOX)   // 60 288 B
+
+struct TileEval { int axis, lx, ly, lz, vn; bool ok; };
+
+__device__ __forceinline__ TileEval tile_decode(const LatFrame& f, int e, int tx0, int ty0, int tz0, int vbase)
+{
+    TileEval t;
+    if (e < VX_TILE_EX) { t.axis = 0; t.lx = e % (VX_TILE_X + 1) - 1; int r = e / (VX_TILE_X + 1); t.ly = r % VX_TILE_Y; t.lz = r / VX_TILE_Y; }
+    else if (e < VX_TILE_EX + VX_TILE_EY) { int q = e - VX_TILE_EX; t.axis = 1; t.lx = q % VX_TILE_X; int r = q / VX_TILE_X; t.ly = r % (VX_TILE_Y + 1) - 1; t.lz = r / (VX_TILE_Y + 1); }
+    else { int q = e - VX_TILE_EX - VX_TILE_EY; t.axis = 2; t.lx = q % VX_TILE_X; int r = q / VX_TILE_X; t.ly = r % VX_TILE_Y; t.lz = r / VX_TILE_Y - 1; }
+    const int gx = tx0 + t.lx, gy = ty0 + t.ly, gz = tz0 + t.lz;
+    const int px = gx + (t.axis == 0), py = gy + (t.axis == 1), pz = gz + (t.axis == 2);
+    t.ok = e < VX_TILE_EVALS && gx >= 0 && gy >= 0 && gz >= 0 && px < f.nx && py < f.ny && pz < f.nz;
+    t.vn = vbase + (gz * f.ny + gy) * f.nx + gx;
+    return t;
+}
+
+template <bool UNI>
+__global__ void __launch_bounds__(VX_TILE_THREADS, VX_TILE_MINBLOCKS)
+k_lattice_tile(LatFrame f, int parity, int first_of_call, int floor_on, int ntx, int nty, int ntz)
+{
+    // dynamic shared memory (VX_TILE_SMEM bytes, > 48 KB so it is opted in by the host):
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    double4* sp0 = reinterpret_cast<double4*>(tile_smem);                        // staged poses, brick + halo  11.5 KB
+    double4* sp1 = sp0 + VX_TILE_HALO;                                           //                             11.5 KB
+    double (*slot)[6][VX_TILE_VOX] = reinterpret_cast<double (*)[6][VX_TILE_VOX]>(sp1 + VX_TILE_HALO);   // [dir][comp][voxel] 36 KB
+    unsigned char (*lflag_sh)[VX_TILE_VOX] = reinterpret_cast<unsigned char (*)[VX_TILE_VOX]>(slot + 6); // new mode bits of owned links
+    DevParams* p = f.params;
+    const int frozen = p->div_flag[parity ^ 1] | p->div_latched;
+    const float dt = p->dt;
+    const float prev_dt = first_of_call ? p->prev_dt : dt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (frozen) p->div_latched = 1;
+        else if (p->pending) { p->steps_done += 1; p->time += dt; }
+        if (!frozen) p->pending = 1;
+    }
+    if (frozen) return;
+
+    int b = blockIdx.x;
+    const int tx0 = (b % ntx) * VX_TILE_X; b /= ntx;
+    const int ty0 = (b % nty) * VX_TILE_Y; b /= nty;
+    const int tz0 = (b % ntz) * VX_TILE_Z; const int member = b / ntz;
+    const int vbase = member * f.nz * f.nxy;
+
+    // ---- phase 0: stage the poses the brick needs (its own voxels + face neighbours) in shared memory;
+    //      every thread has its loads in flight at once, the evaluations below never wait on a pose
+    for (int c = threadIdx.x; c < VX_TILE_HALO; c += VX_TILE_THREADS) {
+        const int hx = c % VX_TILE_HX, hy = (c / VX_TILE_HX) % VX_TILE_HY, hz = c / (VX_TILE_HX * VX_TILE_HY);
+        const int gx = tx0 + hx - 1, gy = ty0 + hy - 1, gz = tz0 + hz - 1;
+        const int edge = (hx == 0 || hx == VX_TILE_HX - 1) + (hy == 0 || hy == VX_TILE_HY - 1) + (hz == 0 || hz == VX_TILE_HZ - 1);
+        if (edge <= 1 && gx >= 0 && gy >= 0 && gz >= 0 && gx < f.nx && gy < f.ny && gz < f.nz) {
+            const int v = vbase + (gz * f.ny + gy) * f.nx + gx;
+            sp0[c] = ld4(f.c_pose0 + v); sp1[c] = ld4(f.c_pose1 + v);
+        }
+    }
+    // link records of this thread's (up to two) evaluations: issue the loads before the barrier
+    TileEval ev[2];
+    double2 ra[2], rb[2], rc[2]; float4 rs[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        ev[r] = tile_decode(f, threadIdx.x + r * VX_TILE_THREADS, tx0, ty0, tz0, vbase);
+        if (ev[r].ok) {
+            ra[r] = __ldg(f.c_rec[ev[r].axis][0] + ev[r].vn); rb[r] = __ldg(f.c_rec[ev[r].axis][1] + ev[r].vn);
+            rc[r] = __ldg(f.c_rec[ev[r].axis][2] + ev[r].vn); rs[r] = __ldg(f.c_recf[ev[r].axis] + ev[r].vn);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1: one thread per link evaluation
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        if (!ev[r].ok) continue;
+        const int axis = ev[r].axis, lx = ev[r].lx, ly = ev[r].ly, lz = ev[r].lz, vn = ev[r].vn;
+        const int cn = ((lz + 1) * VX_TILE_HY + (ly + 1)) * VX_TILE_HX + (lx + 1);
+        const int cp = cn + (axis == 0 ? 1 : (axis == 1 ? VX_TILE_HX : VX_TILE_HX * VX_TILE_HY));
+        const double4 n0 = sp0[cn], n1 = sp1[cn];
+        const uint32_t nbits = meta_hi(n1.w);
+        if (!((nbits >> (VM_LINK_SHIFT + 2 * axis)) & 1u)) continue;        // no +axis link at this voxel
+        const double4 p0 = sp0[cp], p1 = sp1[cp];
+
+        const uint32_t hn = nbits, hp = meta_hi(p1.w);
+        const DevVoxMat& vmn = UNI ? f.vm0 : f.vmat[hn & VM_MAT_MASK];
+        const DevVoxMat& vmp = UNI ? f.vm0 : f.vmat[hp & VM_MAT_MASK];
+        const DevLinkMat& lm = UNI ? f.lm0 : f.lmat[f.pair_lmat[(hn & VM_MAT_MASK) * f.n_mat + (hp & VM_MAT_MASK)]];
+        LinkState st;
+        lat_decode(ra[r], rb[r], rc[r], rs[r], (nbits >> (VM_LFLAG_SHIFT + 2 * axis)) & 3u, st);
+        double rest = 0.5 * (vmn.size[axis] * (1 + meta_temp(n1.w) * vmn.cte) + vmp.size[axis] * (1 + meta_temp(p1.w) * vmp.cte));
+        float t_area = 0.5f * (vmn.nom_f * vmn.nom_f + vmp.nom_f * vmp.nom_f);
+        float damp_n = vmn.two_sqrtm_zeta / prev_dt, damp_p = vmp.two_sqrtm_zeta / prev_dt;
+        q4 on, op;
+        on.w = n0.w; on.x = n1.x; on.y = n1.y; on.z = n1.z;
+        op.w = p0.w; op.x = p1.x; op.y = p1.y; op.z = p1.z;
+        d3 fN, mN, fP, mP;
+        link_forces(axis, mk3(n0.x, n0.y, n0.z), on, mk3(p0.x, p0.y, p0.z), op, rest, t_area, 0.0f,
+                    damp_n, damp_p, lm, f.curve_e, f.curve_s, st, fN, mN, fP, mP);
+
+        const bool n_in = lx >= 0 && ly >= 0 && lz >= 0;                     // negative end inside the brick: owner
+        const int px = lx + (axis == 0), py = ly + (axis == 1), pz = lz + (axis == 2);
+        const bool p_in = px < VX_TILE_X && py < VX_TILE_Y && pz < VX_TILE_Z;
+        if (n_in) {
+            double2 wa, wb, wc; float4 ws; uint32_t lf;
+            lat_encode(st, wa, wb, wc, ws, lf);
+            f.n_rec[axis][0][vn] = wa; f.n_rec[axis][1][vn] = wb; f.n_rec[axis][2][vn] = wc; f.n_recf[axis][vn] = ws;
+            if (st.strain > 100) p->div_flag[parity] = 1;                    // src/Voxelyze.cpp:265
+            const int li = (lz * VX_TILE_Y + ly) * VX_TILE_X + lx;
+            double (*s)[VX_TILE_VOX] = slot[2 * axis];
+            s[0][li] = fN.x; s[1][li] = fN.y; s[2][li] = fN.z; s[3][li] = mN.x; s[4][li] = mN.y; s[5][li] = mN.z;
+            lflag_sh[axis][li] = (unsigned char)lf;
+        }
+        if (p_in) {
+            const int li = (pz * VX_TILE_Y + py) * VX_TILE_X + px;
+            double (*s)[VX_TILE_VOX] = slot[2 * axis + 1];
+            s[0][li] = fP.x; s[1][li] = fP.y; s[2][li] = fP.z; s[3][li] = mP.x; s[4][li] = mP.y; s[5][li] = mP.z;
+        }
+    }
+
+    // ---- phase 2: one thread per voxel (momenta requested before the barrier to overlap their latency)
+    const int li = threadIdx.x;
+    const int vlx = li % VX_TILE_X, vly = (li / VX_TILE_X) % VX_TILE_Y, vlz = li / (VX_TILE_X * VX_TILE_Y);
+    const int gx = tx0 + vlx, gy = ty0 + vly, gz = tz0 + vlz;
+    const bool voxel_thread = li < VX_TILE_VOX && gx < f.nx && gy < f.ny && gz < f.nz;
+    const int v = vbase + (gz * f.ny + gy) * f.nx + gx;
+    double4 m0 = make_double4(0.0, 0.0, 0.0, 0.0); double2 m1 = make_double2(0.0, 0.0);
+    if (voxel_thread) { m0 = ld4(f.c_mom0 + v); m1 = __ldg(f.c_mom1 + v); }
+    __syncthreads();
+    if (!voxel_thread) return;
+    const int cs = ((vlz + 1) * VX_TILE_HY + (vly + 1)) * VX_TILE_HX + (vlx + 1);
+    const double4 s0 = sp0[cs], s1 = sp1[cs];
+    VoxelState vs;
+    vs.bits = meta_hi(s1.w);
+    vs.temp = meta_temp(s1.w);
+    const uint32_t mask = (vs.bits >> VM_LINK_SHIFT) & 0x3Fu;
+    d3 F = mk3(0.0, 0.0, 0.0), M = mk3(0.0, 0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {                                            // reference summation order
+        if (mask & (1u << k)) {
+            F = F + mk3(slot[k][0][li], slot[k][1][li], slot[k][2][li]);
+            M = M + mk3(slot[k][3][li], slot[k][4][li], slot[k][5][li]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+        if (mask & (1u << (2 * a)))
+            vs.bits = (vs.bits & ~(3u << (VM_LFLAG_SHIFT + 2 * a))) | ((uint32_t)lflag_sh[a][li] << (VM_LFLAG_SHIFT + 2 * a));
+    vs.pos = mk3(s0.x, s0.y, s0.z);
+    vs.orient.w = s0.w; vs.orient.x = s1.x; vs.orient.y = s1.y; vs.orient.z = s1.z;
+    vs.lin = mk3(m0.x, m0.y, m0.z);
+    vs.ang = mk3(m0.w, m1.x, m1.y);
+    if (!(vs.bits & VM_GHOST)) {
+        const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
+        const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
+        voxel_integrate(vs, F, M, mk3(0.0, 0.0, 0.0), false, vm, ext, dt, floor_on != 0);
+    }
+    f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
+    f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
+    f.n_mom0[v] = make_double4(vs.lin.x, vs.lin.y, vs.lin.z, vs.ang.x);
+    f.n_mom1[v] = make_double2(vs.ang.y, vs.ang.z);
 }
 
 } // namespace vxd

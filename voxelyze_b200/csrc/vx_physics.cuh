@@ -234,7 +234,7 @@ __device__ __forceinline__ void link_forces(const int axis, d3 pN, q4 oN, d3 pP,
         return;
     }
 
-    float b1 = m.b1, b2 = m.b2, b3 = m.b3, a2 = m.a2;
+    const double b1 = m.b1, b2 = m.b2, b3 = m.b3, a2 = m.a2;
     fN = mk3(st.stress * t_area,
              b1 * pos2.y - b2 * (a1v.z + a2v.z),
              b1 * pos2.z + b2 * (a1v.y + a2v.y));
@@ -247,7 +247,7 @@ __device__ __forceinline__ void link_forces(const int axis, d3 pN, q4 oN, d3 pP,
              b2 * pos2.y - b3 * (a1v.z + 2 * a2v.z));
 
     if (st.vel_valid) {
-        float sqA1 = m.sq_a1, sqA2 = m.sq_a2_ip, sqB1 = m.sq_b1, sqB2 = m.sq_b2_fmp, sqB3 = m.sq_b3_ip;
+        const double sqA1 = m.sq_a1, sqA2 = m.sq_a2_ip, sqB1 = m.sq_b1, sqB2 = m.sq_b2_fmp, sqB3 = m.sq_b3_ip;
         d3 pc = mk3(sqA1 * d_pos2.x,
                     sqB1 * d_pos2.y - sqB2 * (d_a1.z + d_a2.z),
                     sqB1 * d_pos2.z + sqB2 * (d_a1.y + d_a2.y));
@@ -292,9 +292,9 @@ __device__ __forceinline__ void voxel_integrate(VoxelState& v, d3 F, d3 M, d3 co
     // force()
     d3 tot = qrot(v.orient, F);
     if (ext) { tot.x += ext->force[0]; tot.y += ext->force[1]; tot.z += ext->force[2]; }
-    d3 vel = (double)m.mass_inv * v.lin;
-    tot = tot - (double)m.glob_damp_t * vel;
-    tot.z += m.gravity_force;
+    d3 vel = m.mass_inv_d * v.lin;
+    tot = tot - m.glob_damp_t_d * vel;
+    tot.z += m.gravity_force_d;
     if (has_contact) tot = tot - contact;
 
     d3 fric = tot;
@@ -305,7 +305,7 @@ __device__ __forceinline__ void voxel_integrate(VoxelState& v, d3 F, d3 M, d3 co
         pen = (float)(bs_avg / 2 - m.nom / 2 - v.pos.z);
         if (pen >= 0) {
             float normal = m.pen_stiff * pen;
-            tot.z += normal - m.coll_damp_t * vel.z;
+            tot.z += normal - m.coll_damp_t_d * vel.z;
             if (static_fric) {
                 float surf = (float)(tot.x * tot.x + tot.y * tot.y);
                 float lim = (m.mu_s * normal) * (m.mu_s * normal);
@@ -325,7 +325,7 @@ __device__ __forceinline__ void voxel_integrate(VoxelState& v, d3 F, d3 M, d3 co
     d3 tr = (double)(dt * m.mass_inv) * v.lin;
     if (floor_on && pen >= 0) {
         double work = fric.x * tr.x + fric.y * tr.y;
-        double hke = 0.5 * m.mass_inv * (v.lin.x * v.lin.x + v.lin.y * v.lin.y);
+        double hke = 0.5 * m.mass_inv_d * (v.lin.x * v.lin.x + v.lin.y * v.lin.y);
         if (hke + work <= 0) static_fric = true;
         if (static_fric) { v.lin.x = v.lin.y = 0.0; tr.x = tr.y = 0.0; }
     } else static_fric = false;
@@ -334,8 +334,8 @@ __device__ __forceinline__ void voxel_integrate(VoxelState& v, d3 F, d3 M, d3 co
     // moment()
     d3 mom = qrot(v.orient, M);
     if (ext) { mom.x += ext->moment[0]; mom.y += ext->moment[1]; mom.z += ext->moment[2]; }
-    d3 avel = (double)m.inertia_inv * v.ang;
-    mom = mom - (double)m.glob_damp_r * avel;
+    d3 avel = m.inertia_inv_d * v.ang;
+    mom = mom - m.glob_damp_r_d * avel;
     v.ang = v.ang + (double)dt * mom;
     v.orient = qmul(q_from_rotvec((double)(dt * m.inertia_inv) * v.ang), v.orient);
 

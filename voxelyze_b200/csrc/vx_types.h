@@ -60,6 +60,8 @@ struct DevVoxMat {
     float  gravity_force;  // -_mass*9.80665f*gravMult                            VX_MaterialVoxel.h:57
     float  nom_f;          // (float)nomSize
     float  pad;
+    // exact double copies of the floats that are only ever used after promotion to double
+    double mass_inv_d, inertia_inv_d, glob_damp_t_d, glob_damp_r_d, coll_damp_t_d, gravity_force_d;
 };
 
 // per link material
@@ -68,8 +70,12 @@ struct DevLinkMat {
     int32_t curve_off, curve_n;   // into the shared curve arrays (incl. the (0,0) point)
     float   E, nu, e_hat;
     float   eps_yield, eps_fail;
-    float   a1, a2, b1, b2, b3;
-    float   sq_a1, sq_a2_ip, sq_b1, sq_b2_fmp, sq_b3_ip;
+    float   a1;
+    float   pad;
+    // beam constants: float values of the reference, stored promoted (they are only used in
+    // double expressions, src/VX_Link.cpp:165-195)
+    double  a2, b1, b2, b3;
+    double  sq_a1, sq_a2_ip, sq_b1, sq_b2_fmp, sq_b3_ip;
 };
 
 // externals table entry (sparse: only voxels with a CVX_External)
