@@ -19,7 +19,7 @@ from voxelyze_b200.capi import Material
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-NOT_BUILT = {"collide_two", "plates_16x4x2"}     # cases needing features that are not on the GPU yet
+NOT_BUILT = set()     # cases needing features that are not on the GPU yet
 
 
 @pytest.mark.parametrize("path", [0, 1], ids=["auto", "general"])

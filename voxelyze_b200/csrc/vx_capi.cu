@@ -21,6 +21,7 @@
 #include "voxelyze_b200.h"
 #include "vx_material.hpp"
 #include "vx_lattice.cuh"
+#include "vx_collide.cuh"
 
 using namespace vxd;
 
@@ -76,6 +77,7 @@ struct vx_sim {
     bool floor_on = false, collisions = false;
     float time_host = 0.f;
     int path = 0;                       // vx_set_path: 0 auto, 1 general, 2 lattice
+    bool relayout = false;
 
     // ---- lattice mode
     bool lattice = false;
@@ -99,6 +101,17 @@ struct vx_sim {
     DevParams* params_host = nullptr;     // pinned mirror
     unsigned int* freq_host = nullptr;    // pinned
 
+    // ---- collisions (general mode only)
+    std::vector<int32_t> nbr;                                      // [N][6] neighbour voxel (caller index) or -1
+    std::vector<int> ext_raw_vox; std::vector<uint8_t> ext_raw_dof; std::vector<float> ext_raw_f, ext_raw_m; std::vector<double> ext_raw_t, ext_raw_r;
+    int n_surf = 0, n_pairs = 0, col_cap = 0, hash_size = 0;
+    bool col_tables = false, col_stale_host = true;
+    DevBuf<int> c_surf_vox, c_surf_orig, c_surf_member, c_slot; DevBuf<short4> c_surf_ijk; DevBuf<uint32_t> c_nearby;
+    DevBuf<float4> c_last_watch; DevBuf<int> c_head, c_next; DevBuf<int4> c_cell;
+    DevBuf<int2> c_pairs; DevBuf<float2> c_pair_kc; DevBuf<float4> c_pair_force;
+    DevBuf<int> c_counters, c_deg, c_ref_start, c_ref_fill, c_refs;
+    int* counters_host = nullptr;                                  // pinned, 4 ints
+
     bool uni = false; DevVoxMat vm0{}; DevLinkMat lm0{};          // single-material model: rows passed by value
     cudaGraphExec_t graph = nullptr; int graph_kernels = 0;      // general mode
     cudaGraphExec_t lgraph[2] = {nullptr, nullptr};              // lattice mode, keyed by starting generation
@@ -114,9 +127,25 @@ struct vx_sim {
         f.lends = lends.p; f.lmeta = lmeta.p; f.lstA = lstA.p; f.lstB = lstB.p; f.lstC = lstC.p; f.lstrain = lstrain.p;
         f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
         f.ext = ext_dev.p; f.params = params.p;
-        f.col_start = nullptr; f.col_ref = nullptr; f.col_force = nullptr;
+        f.col_slot = c_slot.p; f.col_start = c_ref_start.p; f.col_ref = c_refs.p; f.col_force = c_pair_force.p;
         f.vm0 = vm0; f.lm0 = lm0;
         return f;
+    }
+    ColFrame col_frame() const
+    {
+        ColFrame c{};
+        c.n_surf = n_surf; c.surf_vox = c_surf_vox.p; c.surf_orig = c_surf_orig.p; c.surf_member = c_surf_member.p;
+        c.surf_ijk = c_surf_ijk.p; c.nearby = c_nearby.p; c.last_watch = c_last_watch.p;
+        c.head = c_head.p; c.next = c_next.p; c.cell = c_cell.p; c.hash_mask = hash_size - 1;
+        c.pairs = c_pairs.p; c.pair_kc = c_pair_kc.p; c.pair_force = c_pair_force.p; c.cap = col_cap;
+        c.counters = c_counters.p; c.deg = c_deg.p; c.ref_start = c_ref_start.p; c.ref_fill = c_ref_fill.p; c.refs = c_refs.p;
+        // watch radius and re-watch distance of CVoxelyze::updateCollisions (src/Voxelyze.cpp:672-674)
+        const float watch_vx = 2 * 0.75f + 1.0f;
+        const float watch_mm = (float)(vox_size * watch_vx);
+        const float recalc = (float)(vox_size * 1.0f / 2);
+        c.inv_cell = 1.0 / (double)watch_mm;
+        c.thresh_sq = watch_mm * watch_mm; c.recalc_sq = recalc * recalc; c.envelope = envelope;
+        return c;
     }
     // lattice frame reading generation g and writing generation g^1
     LatFrame lat_frame(int g) const
@@ -251,7 +280,7 @@ static int upload_initial_state(vx_sim* s, float temp)
     const int N = s->N, L = s->L;
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
-    s->gen = 0; s->have_prev = false; s->prev_dt_host = 0.f;
+    s->gen = 0; s->have_prev = false; s->prev_dt_host = 0.f; s->col_stale_host = true;
     if (N) {
         std::vector<double4> p0(N), p1(N);
         std::vector<char> has_ext(N, 0);
@@ -359,6 +388,138 @@ static void launch_recommended_dt(vx_sim* s)
         k_max_freq_voxels<<<g, 256, 0, s->stream>>>(s->frame(), s->freq2.p);
     }
     s->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// collisions
+// Surface voxels, their 5-hop exclusion masks (CVX_Voxel::generateNearby, src/VX_Voxel.cpp:395-418:
+// breadth-first over links, depth (int)(2*2.5) = 5) and the device tables.  Topology is static
+// between vx_set_voxels calls, so this runs once on the host.
+static int build_collision_tables(vx_sim* s)
+{
+    const int N = s->N;
+    std::vector<int> surf_vox, surf_orig, surf_member, slot(std::max(N, 1), -1);
+    std::vector<short4> surf_ijk;
+    for (int i = 0; i < N; i++) {                       // internal order
+        int e = s->v_i2e[i];
+        if (s->linkmask[e] == 0x3F) continue;
+        slot[i] = (int)surf_vox.size();
+        surf_vox.push_back(i); surf_orig.push_back(e); surf_member.push_back(s->member[e]);
+        surf_ijk.push_back(make_short4((short)s->ijk[3 * e], (short)s->ijk[3 * e + 1], (short)s->ijk[3 * e + 2], 0));
+    }
+    const int S = s->n_surf = (int)surf_vox.size();
+    std::vector<uint32_t> nearby((size_t)std::max(S, 1) * VX_NEARBY_WORDS, 0u);
+    std::vector<int> frontier, next_frontier, visited_list;
+    std::vector<char> visited(N, 0);
+    for (int k = 0; k < S; k++) {
+        const int root = surf_orig[k];
+        frontier.assign(1, root); visited_list.assign(1, root); visited[root] = 1;
+        for (int depth = 0; depth < 5 && !frontier.empty(); depth++) {
+            next_frontier.clear();
+            for (int v : frontier)
+                for (int d = 0; d < 6; d++) {
+                    if (!(s->linkmask[v] & (1u << d))) continue;
+                    int o = s->nbr[(size_t)v * 6 + d];
+                    if (o < 0 || visited[o]) continue;
+                    visited[o] = 1; visited_list.push_back(o); next_frontier.push_back(o);
+                }
+            frontier.swap(next_frontier);
+        }
+        uint32_t* mask = &nearby[(size_t)k * VX_NEARBY_WORDS];
+        for (int o : visited_list) {
+            visited[o] = 0;
+            int ox = s->ijk[3 * o] - s->ijk[3 * root], oy = s->ijk[3 * o + 1] - s->ijk[3 * root + 1], oz = s->ijk[3 * o + 2] - s->ijk[3 * root + 2];
+            int bit = ((oz + 5) * 11 + (oy + 5)) * 11 + (ox + 5);
+            mask[bit >> 5] |= 1u << (bit & 31);
+        }
+    }
+    s->hash_size = 1024; while (s->hash_size < 2 * S) s->hash_size <<= 1;
+    size_t s1 = std::max(S, 1);
+    CK(s->c_surf_vox.alloc(s1)); CK(s->c_surf_orig.alloc(s1)); CK(s->c_surf_member.alloc(s1)); CK(s->c_surf_ijk.alloc(s1));
+    CK(s->c_nearby.alloc(s1 * VX_NEARBY_WORDS)); CK(s->c_slot.alloc(std::max(N, 1)));
+    CK(s->c_last_watch.alloc(s1)); CK(s->c_head.alloc(s->hash_size)); CK(s->c_next.alloc(s1)); CK(s->c_cell.alloc(s1));
+    CK(s->c_counters.alloc(4)); CK(s->c_deg.alloc(s1)); CK(s->c_ref_start.alloc(s1 + 1)); CK(s->c_ref_fill.alloc(s1));
+    if (!s->counters_host) CK(cudaMallocHost((void**)&s->counters_host, 4 * sizeof(int)));
+    CK(cudaStreamSynchronize(s->stream));
+    if (S) {
+        CK(cudaMemcpy(s->c_surf_vox.p, surf_vox.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->c_surf_orig.p, surf_orig.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->c_surf_member.p, surf_member.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->c_surf_ijk.p, surf_ijk.data(), (size_t)S * sizeof(short4), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s->c_nearby.p, nearby.data(), nearby.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    if (N) CK(cudaMemcpy(s->c_slot.p, slot.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemset(s->c_last_watch.p, 0, s1 * sizeof(float4)));       // new Vec3D<float>() in CVX_Voxel::enableCollisions
+    CK(cudaMemset(s->c_ref_start.p, 0, (s1 + 1) * sizeof(int)));
+    if (s->col_cap == 0) {
+        s->col_cap = std::max(1024, 4 * S);
+        CK(s->c_pairs.alloc(s->col_cap)); CK(s->c_pair_kc.alloc(s->col_cap)); CK(s->c_pair_force.alloc(s->col_cap)); CK(s->c_refs.alloc((size_t)2 * s->col_cap));
+    }
+    s->n_pairs = 0; s->col_tables = true;
+    return VX_OK;
+}
+
+// CVoxelyze::regenerateCollisions (src/Voxelyze.cpp:725-750) on the device
+static int rebuild_collisions(vx_sim* s)
+{
+    const int S = s->n_surf;
+    for (;;) {
+        ColFrame c = s->col_frame();
+        CK(cudaMemsetAsync(s->c_head.p, 0xFF, (size_t)s->hash_size * sizeof(int), s->stream));
+        CK(cudaMemsetAsync(s->c_counters.p, 0, 4 * sizeof(int), s->stream));
+        CK(cudaMemsetAsync(s->c_deg.p, 0, (size_t)std::max(S, 1) * sizeof(int), s->stream));
+        CK(cudaMemsetAsync(s->c_ref_fill.p, 0, (size_t)std::max(S, 1) * sizeof(int), s->stream));
+        if (S) {
+            k_col_insert<<<blocks_for(S), TPB, 0, s->stream>>>(s->frame(), c);
+            k_col_pairs<<<blocks_for(S), TPB, 0, s->stream>>>(s->frame(), c);
+            s->launches += 2;
+        }
+        CK(cudaMemcpyAsync(s->counters_host, s->c_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        if (!s->counters_host[2]) break;
+        s->col_cap = std::max(2 * s->col_cap, s->counters_host[1] + 1024);         // list overflowed: grow and redo
+        CK(s->c_pairs.alloc(s->col_cap)); CK(s->c_pair_kc.alloc(s->col_cap)); CK(s->c_pair_force.alloc(s->col_cap)); CK(s->c_refs.alloc((size_t)2 * s->col_cap));
+    }
+    const int P = s->n_pairs = s->counters_host[1];
+    std::vector<int> start(S + 1, 0);
+    if (P) {
+        ColFrame c = s->col_frame();
+        k_col_degree<<<blocks_for(P), TPB, 0, s->stream>>>(c, P); s->launches++;
+        std::vector<int> deg(S);
+        CK(cudaMemcpyAsync(deg.data(), s->c_deg.p, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        for (int k = 0; k < S; k++) start[k + 1] = start[k] + deg[k];
+    }
+    CK(cudaMemcpy(s->c_ref_start.p, start.data(), (size_t)(S + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    if (P) {
+        ColFrame c = s->col_frame();
+        k_col_fill<<<blocks_for(P), TPB, 0, s->stream>>>(c, P);
+        k_col_sort<<<blocks_for(S), TPB, 0, s->stream>>>(c);
+        s->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return VX_OK;
+}
+
+// CVoxelyze::updateCollisions (src/Voxelyze.cpp:670-710): re-watch if stale, then all contact forces
+static int collision_step(vx_sim* s)
+{
+    DevParams* ph = s->params_host;
+    if (s->n_surf == 0) return VX_OK;
+    ColFrame c = s->col_frame();
+    CK(cudaMemsetAsync(s->c_counters.p, 0, sizeof(int), s->stream));
+    k_col_stale<<<blocks_for(s->n_surf), TPB, 0, s->stream>>>(s->frame(), c); s->launches++;
+    CK(cudaMemcpyAsync(s->counters_host, s->c_counters.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(ph, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (ph->div_now | ph->div_latched) return VX_OK;                 // diverged: the reference returns before collisions
+    if (s->counters_host[0] || s->col_stale_host) {
+        int rc = rebuild_collisions(s);
+        if (rc != VX_OK) return rc;
+        s->col_stale_host = false;
+    }
+    if (s->n_pairs) { k_col_narrow<<<blocks_for(s->n_pairs), TPB, 0, s->stream>>>(s->frame(), s->col_frame(), s->n_pairs); s->launches++; }
+    return VX_OK;
 }
 
 static void launch_voxel(vx_sim* s, const Frame& f)
@@ -533,6 +694,10 @@ void vx_destroy(vx_sim* s)
     s->drop_graph();
     for (int g = 0; g < 2; g++) { s->pose0[g].release(); s->pose1[g].release(); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); s->recf[g].release(); }
     s->pair_lmat.release(); s->link_owner.release(); s->link_axis_dev.release();
+    s->c_surf_vox.release(); s->c_surf_orig.release(); s->c_surf_member.release(); s->c_slot.release(); s->c_surf_ijk.release(); s->c_nearby.release();
+    s->c_last_watch.release(); s->c_head.release(); s->c_next.release(); s->c_cell.release(); s->c_pairs.release(); s->c_pair_kc.release();
+    s->c_pair_force.release(); s->c_counters.release(); s->c_deg.release(); s->c_ref_start.release(); s->c_ref_fill.release(); s->c_refs.release();
+    if (s->counters_host) cudaFreeHost(s->counters_host);
     s->ext_idx.release(); s->ext_vox_dev.release(); s->vox_e2i_dev.release(); s->link_e2i_dev.release(); s->member_dev.release();
     s->pstrain.release(); s->slots.release(); s->slot_strain.release();
     s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release(); s->lstrain.release();
@@ -613,6 +778,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     s->member.assign(n, 0); if (sim_id) s->member.assign(sim_id, sim_id + n);
     s->vflags.clear(); if (flags) s->vflags.assign(flags, flags + n);
     s->ext_vox.clear(); s->ext_rows.clear();
+    if (!s->relayout) { s->ext_raw_vox.clear(); s->ext_raw_dof.clear(); s->ext_raw_f.clear(); s->ext_raw_m.clear(); s->ext_raw_t.clear(); s->ext_raw_r.clear(); }
     s->lmats.clear(); s->lmat_of.clear();
     s->drop_graph();
 
@@ -638,6 +804,8 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     // ---- links in the reference's creation order (src/Voxelyze.cpp:453-455, 508-539)
     s->lk_vn.clear(); s->lk_vp.clear(); s->lk_axis.clear();
     s->linkmask.assign(n, 0);
+    s->nbr.clear(); s->col_tables = false; s->col_stale_host = true; s->n_surf = 0; s->n_pairs = 0;
+    if (s->collisions) s->nbr.assign((size_t)n * 6, -1);
     std::vector<int32_t> plus_link((size_t)n * 3, -1);        // caller link index of the +axis link of each voxel
     static const int dx[6] = {1, -1, 0, 0, 0, 0}, dy[6] = {0, 0, 1, -1, 0, 0}, dz[6] = {0, 0, 0, 0, 1, -1};
     for (int i = 0; i < n; i++) {
@@ -654,6 +822,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
             int li = (int)s->lk_vn.size();
             s->lk_vn.push_back(vn); s->lk_vp.push_back(vp); s->lk_axis.push_back((uint8_t)(d / 2));
             s->linkmask[i] |= (uint8_t)(1u << d); s->linkmask[o] |= (uint8_t)(1u << (d ^ 1));
+            if (s->collisions) { s->nbr[(size_t)i * 6 + d] = o; s->nbr[(size_t)o * 6 + (d ^ 1)] = i; }
             plus_link[(size_t)vn * 3 + d / 2] = li;
         }
     }
@@ -733,6 +902,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     if (L) CK(cudaMemcpy(s->link_e2i_dev.p, s->l_e2i.data(), (size_t)L * sizeof(int), cudaMemcpyHostToDevice));
     int rc = upload_tables(s);                     // new link materials may have appeared
     if (rc != VX_OK) return rc;
+    if (s->collisions) { rc = build_collision_tables(s); if (rc != VX_OK) return rc; }
     return upload_initial_state(s, s->ambient);    // new voxels start at ambient temperature, src/Voxelyze.cpp:449
 }
 
@@ -752,6 +922,14 @@ int vx_set_externals(vx_sim* s, int n, const int32_t* voxel, const uint8_t* dof,
 {
     if (!s || n < 0 || (n && (!voxel || !dof))) return VX_ERR_ARG;
     for (int k = 0; k < n; k++) if (voxel[k] < 0 || voxel[k] >= s->N) return fail(s, VX_ERR_ARG, "external voxel index out of range");
+    if (voxel != s->ext_raw_vox.data()) {
+        s->ext_raw_vox.assign(voxel, voxel + n); s->ext_raw_dof.assign(dof, dof + n);
+        s->ext_raw_f.clear(); s->ext_raw_m.clear(); s->ext_raw_t.clear(); s->ext_raw_r.clear();
+        if (force) s->ext_raw_f.assign(force, force + 3 * (size_t)n);
+        if (moment) s->ext_raw_m.assign(moment, moment + 3 * (size_t)n);
+        if (tr) s->ext_raw_t.assign(tr, tr + 3 * (size_t)n);
+        if (rot) s->ext_raw_r.assign(rot, rot + 3 * (size_t)n);
+    }
     s->ext_vox.assign(voxel, voxel + n);
     s->ext_rows.assign(n, DevExt{});
     for (int k = 0; k < n; k++) {
@@ -779,11 +957,35 @@ int vx_set_externals(vx_sim* s, int n, const int32_t* voxel, const uint8_t* dof,
 
 int vx_set_gravity(vx_sim* s, float g) { if (!s) return VX_ERR_ARG; s->grav = g; return s->mats.empty() ? VX_OK : upload_tables(s); }
 int vx_enable_floor(vx_sim* s, int e) { if (!s) return VX_ERR_ARG; s->floor_on = e != 0; s->drop_graph(); return VX_OK; }
-int vx_enable_collisions(vx_sim* s, int e)
+// the device layout depends on whether collisions are watched (collisions run on the general layout),
+// so switching them on re-lays out a simulation that has not been stepped yet
+static int relayout_fresh(vx_sim* s)
+{
+    std::vector<int32_t> ijk = s->ijk, member = s->member; std::vector<uint16_t> mat = s->vmat_id; std::vector<uint32_t> fl = s->vflags;
+    s->relayout = true;
+    int rc = vx_set_voxels(s, s->N, ijk.data(), mat.data(), s->n_members > 1 ? member.data() : nullptr, fl.empty() ? nullptr : fl.data());
+    s->relayout = false;
+    if (rc != VX_OK) return rc;
+    if (!s->ext_raw_vox.empty()) {
+        int n = (int)s->ext_raw_vox.size();
+        rc = vx_set_externals(s, n, s->ext_raw_vox.data(), s->ext_raw_dof.data(), s->ext_raw_f.empty() ? nullptr : s->ext_raw_f.data(),
+                              s->ext_raw_m.empty() ? nullptr : s->ext_raw_m.data(), s->ext_raw_t.empty() ? nullptr : s->ext_raw_t.data(),
+                              s->ext_raw_r.empty() ? nullptr : s->ext_raw_r.data());
+    }
+    return rc;
+}
+
+int vx_enable_collisions(vx_sim* s, int e)                         // src/Voxelyze.cpp:612-622
 {
     if (!s) return VX_ERR_ARG;
-    if (e) return fail(s, VX_ERR_UNSUPPORTED, "collisions are not built yet");
-    s->collisions = false; s->drop_graph(); return VX_OK;
+    if (s->collisions == (e != 0)) return VX_OK;
+    s->collisions = e != 0;
+    s->col_stale_host = true;
+    s->drop_graph();
+    if (!s->collisions) { s->n_pairs = 0; return VX_OK; }           // clearCollisions()
+    if (s->N == 0 || s->col_tables) return VX_OK;
+    if (s->time_host != 0.f || s->have_prev) { s->collisions = false; return fail(s, VX_ERR_UNSUPPORTED, "enable collisions before the first step"); }
+    return relayout_fresh(s);
 }
 int vx_set_collision_envelope(vx_sim* s, float r) { if (!s) return VX_ERR_ARG; s->envelope = r; return VX_OK; }
 
@@ -829,6 +1031,17 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
         k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++;
     }
     int left = n_steps;
+    if (s->collisions) {                                           // host decides about re-watching every step
+        for (; left > 0; left--) {
+            if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
+            if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+            launch_links(s, f);
+            int rc = collision_step(s);
+            if (rc != VX_OK) return rc;
+            f = s->frame();
+            launch_voxel(s, f);
+        }
+    }
     if (!per_step_dt && left >= GRAPH_STEPS) {
         int rc = ensure_graph(s);
         if (rc != VX_OK) return rc;
@@ -885,6 +1098,7 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
             launch_links(s, f);
             int64_t l2 = s->launches;
             CK(cudaEventRecord(ev[4 * k + 2], s->stream));
+            if (s->collisions) { rc = collision_step(s); if (rc != VX_OK) return rc; f = s->frame(); }
             launch_voxel(s, f);
             CK(cudaEventRecord(ev[4 * k + 3], s->stream));
             if (launches) { launches[2] += (int)(l1 - l0); launches[0] += (int)(l2 - l1); launches[1] += 1; }
@@ -1014,7 +1228,23 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
     return VX_OK;
 }
 
-int vx_collision_pairs(vx_sim* s, int32_t*, int, int* n_pairs) { if (!s) return VX_ERR_ARG; if (n_pairs) *n_pairs = 0; return VX_OK; }
+int vx_collision_pairs(vx_sim* s, int32_t* pairs, int cap, int* n_pairs)
+{
+    if (!s) return VX_ERR_ARG;
+    const int P = (s->collisions && s->col_tables) ? s->n_pairs : 0;
+    if (n_pairs) *n_pairs = P;
+    if (!pairs || P == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    std::vector<int2> raw(P); std::vector<int> orig(s->n_surf);
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy(raw.data(), s->c_pairs.p, (size_t)P * sizeof(int2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(orig.data(), s->c_surf_orig.p, (size_t)s->n_surf * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<std::pair<int, int>> out(P);
+    for (int k = 0; k < P; k++) out[k] = {orig[raw[k].x], orig[raw[k].y]};
+    std::sort(out.begin(), out.end());                              // creation order of the reference: i ascending, then j
+    for (int k = 0; k < P && k < cap; k++) { pairs[2 * k] = out[k].first; pairs[2 * k + 1] = out[k].second; }
+    return VX_OK;
+}
 int vx_state_info(vx_sim* s, int, int, float*) { return fail(s, VX_ERR_UNSUPPORTED, "stateInfo is not built yet"); }
 
 int vx_set_stream(vx_sim* s, uint64_t stream)

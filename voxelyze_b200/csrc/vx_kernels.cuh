@@ -33,8 +33,8 @@ struct Frame {
     // single-material models: the two table rows travel in the kernel parameters (constant bank),
     // so material constants cost no load instructions (template parameter UNI)
     DevVoxMat vm0; DevLinkMat lm0;
-    // collisions (per voxel CSR of signed contact references)
-    const int* col_start; const int* col_ref; const float4* col_force;
+    // collisions: per surface voxel CSR of signed contact references (vx_collide.cuh)
+    const int* col_slot; const int* col_start; const int* col_ref; const float4* col_force;
 };
 
 __device__ __forceinline__ uint32_t meta_hi(double w) { return (uint32_t)(((unsigned long long)__double_as_longlong(w)) >> 32); }
@@ -180,7 +180,13 @@ __global__ void __launch_bounds__(128) k_voxel(Frame f, int floor_on, int collis
     const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[s.bits & VM_MAT_MASK];
     const DevExt* ext = (s.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
 
-    voxel_integrate(s, F, M, mk3(0.0, 0.0, 0.0), false, vm, ext, dt, floor_on != 0);
+    const int* refs = nullptr; int n_refs = 0;
+    if (collisions && mask != 0x3Fu) {                     // only surface voxels are ever watched
+        const int slot = f.col_slot[v];
+        refs = f.col_ref + f.col_start[slot];
+        n_refs = f.col_start[slot + 1] - f.col_start[slot];
+    }
+    voxel_integrate(s, F, M, refs, n_refs, f.col_force, vm, ext, dt, floor_on != 0);
 
     f.pose0[v] = make_double4(s.pos.x, s.pos.y, s.pos.z, s.orient.w);
     f.pose1[v] = make_double4(s.orient.x, s.orient.y, s.orient.z, meta_pack(s.temp, s.bits));

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128, VX_LAT_MINBLOCKS) k_lattice_step(LatFrame
     if (!(vs.bits & VM_GHOST)) {
         const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
         const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
-        voxel_integrate(vs, F, M, mk3(0.0, 0.0, 0.0), false, vm, ext, dt, floor_on != 0);
+        voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext, dt, floor_on != 0);
     }
     f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
     f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
@@ -405,7 +405,7 @@ k_lattice_march(LatFrame f, int parity, int first_of_call, int floor_on, int n_s
             if (!(vs.bits & VM_GHOST)) {
                 const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
                 const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
-                voxel_integrate(vs, F, M, mk3(0.0, 0.0, 0.0), false, vm, ext, dt, floor_on != 0);
+                voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext, dt, floor_on != 0);
             }
             f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
             f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
@@ -599,7 +599,7 @@ k_lattice_tile(LatFrame f, int parity, int first_of_call, int floor_on, int ntx,
     if (!(vs.bits & VM_GHOST)) {
         const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
         const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
-        voxel_integrate(vs, F, M, mk3(0.0, 0.0, 0.0), false, vm, ext, dt, floor_on != 0);
+        voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext, dt, floor_on != 0);
     }
     f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
     f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));

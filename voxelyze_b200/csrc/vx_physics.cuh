@@ -277,8 +277,11 @@ struct VoxelState { d3 pos; q4 orient; d3 lin, ang; float temp; uint32_t bits; }
 __device__ __forceinline__ double base_size(const DevVoxMat& m, int axis, float temp) { return m.size[axis] * (1 + temp * m.cte); }
 
 // F, M: link force / moment sums in the voxel's local frame (slot order already applied);
-// contact: sum of contact forces to subtract (global frame).
-__device__ __forceinline__ void voxel_integrate(VoxelState& v, d3 F, d3 M, d3 contact, bool has_contact,
+// contact_refs: this voxel's watched collisions in creation order, ref = 2*pair + (1 if this voxel
+// is the pair's second voxel); each float force is subtracted on its own like the reference's
+// loop over colWatch (src/VX_Voxel.cpp:249-253, src/VX_Collision.cpp:34-39).
+__device__ __forceinline__ void voxel_integrate(VoxelState& v, d3 F, d3 M, const int* __restrict__ contact_refs, int n_contacts,
+                                                const float4* __restrict__ contact_force,
                                                 const DevVoxMat& m, const DevExt* __restrict__ ext,
                                                 float dt, bool floor_on)
 {
@@ -295,7 +298,12 @@ __device__ __forceinline__ void voxel_integrate(VoxelState& v, d3 F, d3 M, d3 co
     d3 vel = m.mass_inv_d * v.lin;
     tot = tot - m.glob_damp_t_d * vel;
     tot.z += m.gravity_force_d;
-    if (has_contact) tot = tot - contact;
+    for (int k = 0; k < n_contacts; k++) {
+        const int ref = contact_refs[k];
+        const float4 cf = contact_force[ref >> 1];
+        if (ref & 1) { tot.x -= -cf.x; tot.y -= -cf.y; tot.z -= -cf.z; }
+        else { tot.x -= cf.x; tot.y -= cf.y; tot.z -= cf.z; }
+    }
 
     d3 fric = tot;
     bool static_fric = (v.bits & VM_STATIC_FRIC) != 0;
