@@ -1,0 +1,530 @@
+// dropin_tests.cpp -- one test source, two implementations of the same public C++ API.
+//
+//   -DDROPIN_REFERENCE + reference headers/sources  -> tests/cpp/_build/dropin_ref   (CPU, unmodified reference)
+//   facade headers + libvoxelyze_facade/b200        -> tests/cpp/_build/dropin_b200  (B200)
+//
+// Only the public API of include/Voxelyze.h is used, so passing both builds is the drop-in
+// proof.  The scenarios restate the reference's gtest cases (test/tVoxelyze.h, test/tVX_Material.h,
+// test/tVX_MaterialLink.h, test/tVX_Voxel.h; line cited per case) with the reference's own expected
+// values and tolerances; gtest itself is not available in this image, hence the tiny harness.
+#include "Voxelyze.h"
+#include "VX_Voxel.h"
+#include "VX_Link.h"
+#include "VX_MaterialLink.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+static int g_failures = 0, g_checks = 0;
+static const char* g_current = "";
+#define CHECK(cond) do { g_checks++; if (!(cond)) { g_failures++; printf("  FAIL %s:%d  %s   [%s]\n", __FILE__, __LINE__, #cond, g_current); } } while (0)
+#define CHECK_NEAR(a, b, tol) do { g_checks++; double a_ = (a), b_ = (b); if (!(std::fabs(a_ - b_) <= (tol))) { g_failures++; \
+    printf("  FAIL %s:%d  |%s - %s| = |%.10g - %.10g| > %g   [%s]\n", __FILE__, __LINE__, #a, #b, a_, b_, (double)(tol), g_current); } } while (0)
+// gtest's EXPECT_FLOAT_EQ: within 4 ulp of float
+static bool float_eq(float a, float b)
+{
+    if (a == b) return true;
+    int ia, ib; memcpy(&ia, &a, 4); memcpy(&ib, &b, 4);
+    if ((ia < 0) != (ib < 0)) return false;
+    return std::abs(ia - ib) <= 4;
+}
+#define CHECK_FLOAT_EQ(a, b) do { g_checks++; float a_ = (float)(a), b_ = (float)(b); if (!float_eq(a_, b_)) { g_failures++; \
+    printf("  FAIL %s:%d  %s = %.9g != %s = %.9g   [%s]\n", __FILE__, __LINE__, #a, a_, #b, b_, g_current); } } while (0)
+
+static Vec3D<> offsetOf(CVX_Voxel::linkDirection d)
+{
+    switch (d) {
+    case CVX_Voxel::X_POS: return Vec3D<>(1, 0, 0);
+    case CVX_Voxel::X_NEG: return Vec3D<>(-1, 0, 0);
+    case CVX_Voxel::Y_POS: return Vec3D<>(0, 1, 0);
+    case CVX_Voxel::Y_NEG: return Vec3D<>(0, -1, 0);
+    case CVX_Voxel::Z_POS: return Vec3D<>(0, 0, 1);
+    default: return Vec3D<>(0, 0, -1);
+    }
+}
+
+// tVoxelyze.h:63-113: two voxels, one fixed (or mirrored load), returns steps until converged
+static int twoVoxels(bool firstFixed, CVX_Voxel::linkDirection dir, Vec3D<float> force, Vec3D<float> moment, dofObject dofs,
+                     int maxSteps, float expected, int component)
+{
+    const double sz = 0.001;
+    CVoxelyze sim(sz);
+    CVX_Material* mat = sim.addMaterial(1e6, 1e3);
+    mat->setInternalDamping(1.0);
+    mat->setGlobalDamping(0.2f);
+    Vec3D<> off = offsetOf(dir);
+    CVX_Voxel* a = sim.setVoxel(mat, 0, 0, 0);
+    auto fix = [&](CVX_Voxel* v) {
+        v->external()->setFixed(dofIsSet(dofs, X_TRANSLATE), dofIsSet(dofs, Y_TRANSLATE), dofIsSet(dofs, Z_TRANSLATE),
+                                dofIsSet(dofs, X_ROTATE), dofIsSet(dofs, Y_ROTATE), dofIsSet(dofs, Z_ROTATE));
+    };
+    if (firstFixed) a->external()->setFixedAll();
+    else { a->external()->setForce(-force); a->external()->setMoment(-moment); fix(a); }
+    CVX_Voxel* b = sim.setVoxel(mat, (int)off.x, (int)off.y, (int)off.z);
+    b->external()->setForce(force); b->external()->setMoment(moment); fix(b);
+
+    float ts = sim.recommendedTimeStep();
+    int streak = 0, k;
+    for (k = 0; k < maxSteps; k++) {
+        sim.doTimeStep(ts);
+        double value = component < 3 ? (b->position() - off * sz)[component] : b->orientation().ToRotationVector()[component % 3];
+        if (std::fabs(value - expected) < std::fabs(expected) * 1e-5 || (float)value == (float)expected) streak++; else streak = 0;
+        if (streak == 10) break;
+    }
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+static void simpleSetup()               // tVoxelyze.h:117-139
+{
+    CVoxelyze sim(0.001f);
+    CVX_Material* m = sim.addMaterial();
+    sim.setVoxel(m, 0, 0, 0);
+    sim.setVoxel(m, 1, 0, 0);
+    CHECK(sim.indexMinX() == 0 && sim.indexMaxX() == 1 && sim.indexMinY() == 0 && sim.indexMaxY() == 0 && sim.indexMinZ() == 0 && sim.indexMaxZ() == 0);
+    CHECK(sim.voxelCount() == 2);
+    CHECK(sim.voxel(0, 0, 0)->material() == m && sim.voxel(1, 0, 0)->material() == m);
+    CHECK(sim.voxel(2, 0, 0) == NULL);
+    CHECK(sim.linkCount() == 1);
+    CHECK(sim.link(0, 0, 0, CVX_Voxel::X_POS) != NULL && sim.link(0, 0, 0, CVX_Voxel::X_POS) == sim.link(1, 0, 0, CVX_Voxel::X_NEG));
+    CHECK(sim.link(0, 0, 0, CVX_Voxel::Y_POS) == NULL);
+}
+
+static void singleBondFixedFree()       // tVoxelyze.h:142-198 (one case per load type and axis family)
+{
+    const Vec3D<float> none(0, 0, 0);
+    CHECK(150 > twoVoxels(true, CVX_Voxel::X_POS, Vec3D<float>(1e-3f, 0, 0), none, dof(false, true, true, true, true, true), 1000, 1e-6f, 0));
+    CHECK(150 > twoVoxels(true, CVX_Voxel::X_POS, Vec3D<float>(0, -1e-3f, 0), none, dof(true, false, true, true, true, true), 1000, -1e-6f, 1));
+    CHECK(150 > twoVoxels(true, CVX_Voxel::Y_NEG, Vec3D<float>(1e-3f, 0, 0), none, dof(false, true, true, true, true, true), 1000, 1e-6f, 0));
+    CHECK(150 > twoVoxels(true, CVX_Voxel::Z_POS, Vec3D<float>(0, 0, 1e-3f), none, dof(true, true, false, true, true, true), 1000, 1e-6f, 2));
+    CHECK(200 > twoVoxels(true, CVX_Voxel::X_POS, none, Vec3D<float>(1e-9f, 0, 0), dof(true, true, true, false, true, true), 1000, 1.2e-5f, 3));
+    CHECK(200 > twoVoxels(true, CVX_Voxel::X_POS, none, Vec3D<float>(0, 1e-9f, 0), dof(true, true, true, true, false, true), 1000, 3e-6f, 4));
+    CHECK(200 > twoVoxels(true, CVX_Voxel::Z_NEG, none, Vec3D<float>(0, 0, 1e-9f), dof(true, true, true, true, true, false), 1000, 1.2e-5f, 5));
+    CHECK(300 > twoVoxels(true, CVX_Voxel::X_POS, none, Vec3D<float>(0, 1e-9f, 0), dof(true, true, false, true, false, true), 1000, -6e-9f, 2));
+    CHECK(300 > twoVoxels(true, CVX_Voxel::X_POS, Vec3D<float>(0, 1e-3f, 0), none, dof(true, false, true, true, true, false), 1000, 6e-3f, 5));
+}
+
+static void singleBondFreeFree()        // tVoxelyze.h:202-244
+{
+    const Vec3D<float> none(0, 0, 0);
+    CHECK(100 > twoVoxels(false, CVX_Voxel::X_POS, Vec3D<float>(1e-3f, 0, 0), none, dof(false, true, true, true, true, true), 1000, 5e-7f, 0));
+    CHECK(100 > twoVoxels(false, CVX_Voxel::Y_POS, Vec3D<float>(0, 1e-3f, 0), none, dof(true, false, true, true, true, true), 1000, 5e-7f, 1));
+    CHECK(150 > twoVoxels(false, CVX_Voxel::X_POS, none, Vec3D<float>(0, 0, 1e-9f), dof(true, true, true, true, true, false), 1000, 6e-6f, 5));
+    CHECK(150 > twoVoxels(false, CVX_Voxel::Z_NEG, none, Vec3D<float>(1e-9f, 0, 0), dof(true, true, true, false, true, true), 1000, 6e-6f, 3));
+}
+
+static void resetTime()                 // tVoxelyze.h:246-259
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* m = sim.addMaterial(1e6, 1e3);
+    CVX_Voxel* a = sim.setVoxel(m, 0, 0, 0);
+    CVX_Voxel* b = sim.setVoxel(m, 1, 0, 0);
+    a->external()->setFixedAll();
+    b->external()->setForce(1e-3f, 0, 0);
+    for (int i = 0; i < 100; i++) sim.doTimeStep();
+    CHECK(b->position().x > 0.001);
+    sim.resetTime();
+    CHECK_FLOAT_EQ(1e-3f, (float)b->position().x);
+}
+
+static void dampingInternalAndGlobal()  // tVoxelyze.h:261-334
+{
+    for (int variant = 0; variant < 2; variant++) {
+        CVoxelyze sim(0.001);
+        CVX_Material* m = sim.addMaterial(1e6, 1e3);
+        if (variant == 0) m->setInternalDamping(1.0);
+        else { m->setGlobalDamping(1.0); m->setInternalDamping(0); }
+        CVX_Voxel* c = sim.setVoxel(m, 0, 0, 0);
+        c->external()->setForce(1e-6f, 1e-6f, 1e-6f);
+        for (int i = 0; i < 6; i++) {
+            Vec3D<> o = offsetOf((CVX_Voxel::linkDirection)i);
+            sim.setVoxel(m, (int)o.x, (int)o.y, (int)o.z)->external()->setFixedAll();
+        }
+        float ts = sim.recommendedTimeStep();
+        for (int k = 0; k < 100; k++) sim.doTimeStep(ts);
+        CHECK_FLOAT_EQ(1e-9f / 6, (float)c->position().y);
+        if (variant == 1) { CHECK_FLOAT_EQ(1e-9f / 6, (float)c->position().x); CHECK_FLOAT_EQ(1e-9f / 6, (float)c->position().z); }
+    }
+    CVoxelyze sim2(0.001);              // two-voxel cantilever
+    CVX_Material* m2 = sim2.addMaterial(1e6, 1e3);
+    m2->setGlobalDamping(0.25f); m2->setInternalDamping(0);
+    sim2.setVoxel(m2, 0, 0, 0)->external()->setFixedAll();
+    CVX_Voxel* tip = sim2.setVoxel(m2, 1, 0, 0);
+    tip->external()->setForce(1e-6f, 1e-6f, 1e-6f);
+    float ts = sim2.recommendedTimeStep();
+    for (int k = 0; k < 300; k++) sim2.doTimeStep(ts);
+    CHECK_FLOAT_EQ(4e-9f, (float)tip->position().y);
+}
+
+static void combinedDamping()           // tVoxelyze.h:336-379
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* m = sim.addMaterial(1e6, 1e3);
+    m->setInternalDamping(1.0f);
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) {
+        CVX_Voxel* v = sim.setVoxel(m, i, j, k);
+        if (i == 0) v->external()->setFixedAll();
+        else if (i == 3) v->external()->setForce(0, 0, 1e-6f);
+    }
+    for (int i = 0; i < 2; i++) {
+        m->setGlobalDamping(0.05f + 0.05f * i);     // material changed between runs through the handle
+        float ts = sim.recommendedTimeStep();
+        sim.resetTime();
+        for (int k = 0; k < 1000; k++) sim.doTimeStep(ts);
+        CHECK_NEAR(1.742e-8, sim.voxel(3, 0, 0)->position().z, 1e-10);
+    }
+}
+
+static void scaleOfForce()              // tVoxelyze.h:382-412
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* m = sim.addMaterial(1e6, 1e3);
+    m->setInternalDamping(1.0); m->setGlobalDamping(0.2f);
+    sim.setVoxel(m, 0, 0, 0)->external()->setFixedAll();
+    CVX_Voxel* b = sim.setVoxel(m, 1, 0, 0);
+    for (int i = 3; i < 8; i++) {
+        float force = 1 / std::pow(10.0f, i), result = 4 / std::pow(10.0f, i + 3);
+        b->external()->setForce(force, force, force);
+        float ts = sim.recommendedTimeStep();
+        sim.resetTime();
+        for (int k = 0; k < 240; k++) sim.doTimeStep(ts);
+        CHECK_NEAR(result, (float)b->position().y, result / 1000);
+    }
+}
+
+static void axialFrequency()            // tVoxelyze.h:415-443
+{
+    CVoxelyze sim(0.001f);
+    CVX_Material* m = sim.addMaterial(1e6f, 1e3f);
+    m->setInternalDamping(0);
+    sim.setVoxel(m, 0, 0, 0)->external()->setFixedAll();
+    CVX_Voxel* b = sim.setVoxel(m, 1, 0, 0);
+    b->external()->setFixed(false, true, true, true, true, true);
+    b->external()->setForce(1e-3f, 0, 0);
+    float ts = sim.recommendedTimeStep() / 10;
+    std::vector<double> data;
+    for (int i = 0; i < 1000; i++) { sim.doTimeStep(ts); data.push_back(b->position().x - 0.001001); }
+    std::vector<double> crossings;
+    for (size_t i = 1; i < data.size(); i++)
+        if ((data[i - 1] <= 0 && data[i] > 0) || (data[i - 1] >= 0 && data[i] < 0)) crossings.push_back(ts * ((double)i - 1 + data[i - 1] / (data[i - 1] - data[i])));
+    CHECK(crossings.size() >= 2);
+    double acc = 0; for (size_t i = 1; i < crossings.size(); i++) acc += crossings[i] - crossings[i - 1];
+    double period = (float)(acc / (crossings.size() - 1) * 2), expected = 2 * 3.1415926 / std::sqrt(1e9);
+    CHECK_NEAR(expected, period, expected / 1000);
+}
+
+static void largeDeformation()          // tVoxelyze.h:445-522
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* m = sim.addMaterial(1e6, 1e3);
+    m->setInternalDamping(1.0); m->setGlobalDamping(0.2f);
+    sim.setVoxel(m, 0, 0, 0)->external()->setFixedAll();
+    CVX_Voxel* b = sim.setVoxel(m, 1, 0, 0);
+    float ts = sim.recommendedTimeStep();
+    CVX_Link* l = sim.link(0, 0, 0, CVX_Voxel::X_POS);
+    CHECK(l != NULL && l->isSmallAngle());
+    b->external()->setForce(-0.2f, 0.0f, 0.2f);
+    for (int k = 0; k < 200; k++) sim.doTimeStep(ts);
+    CHECK_NEAR(9.5587e-4, b->position().z, 1e-7);
+    CHECK(!l->isSmallAngle());
+}
+
+static void doubleBondCantilever()      // tVoxelyze.h:525-575 (z direction)
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* m = sim.addMaterial(1e6, 1e3);
+    m->setInternalDamping(1.0); m->setGlobalDamping(0.1f);
+    sim.setVoxel(m, 0, 0, 0)->external()->setFixedAll();
+    sim.setVoxel(m, 1, 0, 0);
+    CVX_Voxel* c = sim.setVoxel(m, 2, 0, 0);
+    float ts = sim.recommendedTimeStep();
+    for (int i = 0; i < 3; i += 2) {
+        c->external()->setFixed(!(i == 0), !(i == 1), !(i == 2), true, !(i == 2), !(i == 1));
+        Vec3D<float> f(0, 0, 0); f[i] = 5e-6f;
+        c->external()->setForce(f);
+        float expected = i == 0 ? 1e-8f : 1.6e-7f;
+        sim.resetTime();
+        int streak = 0, k;
+        for (k = 0; k < 3000; k++) {
+            sim.doTimeStep(ts);
+            float value = (float)((c->position() - Vec3D<double>(0.002, 0, 0))[i]);
+            if (std::fabs(value - expected) < std::fabs(expected) * 1e-4) streak++; else streak = 0;
+            if (streak == 10) break;
+        }
+        CHECK(k < (i == 0 ? 200 : 500));
+    }
+}
+
+static void impulse()                   // tVoxelyze.h:577-610
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* m = sim.addMaterial(1e6, 1e3);
+    m->setInternalDamping(1.0); m->setGlobalDamping(0.05f);
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 2; j++) { CVX_Voxel* v = sim.setVoxel(m, i, j, 0); if (i == 0) v->external()->setFixedAll(); }
+    float ts = sim.recommendedTimeStep();
+    for (int k = 0; k < 1000; k++) {
+        CVX_Voxel* v = sim.voxel(3, 0, 0);
+        if (k == 10) v->external()->setForce(0, 0, 100);
+        else if (k == 11) v->external()->setForce(0, 0, 0);
+        sim.doTimeStep(ts);
+    }
+    CHECK_NEAR(0.0f, (float)sim.voxel(3, 0, 0)->position().z, 1e-5);
+}
+
+static void multiMaterial()             // tVoxelyze.h:614-684
+{
+    {
+        CVoxelyze sim(0.001);
+        CVX_Material* soft = sim.addMaterial(1e6, 1e3); CVX_Material* stiff = sim.addMaterial(1e9, 1e3);
+        soft->setGlobalDamping(0.03f); stiff->setGlobalDamping(0.03f); soft->setInternalDamping(0.01f); stiff->setInternalDamping(0.01f);
+        for (int i = 0; i < 2; i++) {
+            CVX_Voxel* a = sim.setVoxel(soft, 2 * i, 0, 0); CVX_Voxel* b = sim.setVoxel(stiff, 2 * i + 1, 0, 0);
+            if (i == 0) a->external()->setFixedAll();
+            if (i == 1) b->external()->setForce(1e-3f, 0, 0);
+        }
+        float ts = sim.recommendedTimeStep();
+        for (int i = 0; i < 800; i++) sim.doTimeStep(ts);
+        CHECK_FLOAT_EQ(1.5015e-6f, (float)(sim.voxel(3, 0, 0)->position().x - 0.003));
+    }
+    {
+        CVoxelyze sim(0.001);
+        CVX_Material* soft = sim.addMaterial(1e6, 1e3); CVX_Material* stiff = sim.addMaterial(1e9, 1e3);
+        soft->setGlobalDamping(0.01f); stiff->setGlobalDamping(0.01f); soft->setInternalDamping(1.0f); stiff->setInternalDamping(1.0f);
+        for (int i = 0; i < 8; i++) {
+            CVX_Voxel* v = sim.setVoxel((i / 2) % 2 == 0 ? soft : stiff, i, 0, 0);
+            if (i == 0) v->external()->setFixedAll();
+            if (i == 7) v->external()->setForce(1e-3f, 0, 0);
+        }
+        float ts = sim.recommendedTimeStep();
+        for (int i = 0; i < 10000; i++) sim.doTimeStep(ts);
+        CHECK_NEAR(3.5035e-6f, (float)(sim.voxel(7, 0, 0)->position().x - 0.007), 1e-10);
+    }
+}
+
+static void deformableMaterial()        // tVoxelyze.h:845-889
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* m = sim.addMaterial(1e6, 1e3);
+    m->setModelBilinear(1e6, 5e5, 1e5);
+    m->setInternalDamping(1.0f); m->setGlobalDamping(0.2f);
+    for (int i = 0; i < 5; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) {
+        CVX_Voxel* v = sim.setVoxel(m, i, j, k);
+        if (i == 0) v->external()->setFixedAll();
+        if (i == 4) v->external()->setForce(Vec3D<float>(0.2f, 0.0f, 0.0f));
+    }
+    float ts = sim.recommendedTimeStep();
+    for (int i = 0; i < 400; i++) sim.doTimeStep(ts);
+    CHECK(sim.link(1, 1, 1, CVX_Voxel::X_POS)->isYielded());
+    for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) sim.voxel(4, j, k)->external()->setForce(Vec3D<float>(0, 0, 0));
+    for (int i = 0; i < 250; i++) sim.doTimeStep(ts);
+    CHECK_NEAR(4e-4, (float)(sim.voxel(4, 1, 1)->position().x - 0.004), 1e-7);
+}
+
+static void replaceMaterialMidRun()     // tVoxelyze.h:946-986
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* a = sim.addMaterial(1e6, 1e3); a->setInternalDamping(1.0f); a->setGlobalDamping(0.08f);
+    CVX_Material* b = sim.addMaterial(1e7, 1e3); b->setInternalDamping(1.0f); b->setGlobalDamping(0.08f);
+    for (int i = 0; i < 5; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+        CVX_Voxel* v = sim.setVoxel(a, i, j, k);
+        if (i == 0) v->external()->setFixedAll();
+        else if (i == 4) v->external()->setForce(0, 0, 1e-6f);
+    }
+    float ts = sim.recommendedTimeStep();
+    for (int l = 0; l < 2000; l++) {
+        sim.doTimeStep(ts);
+        if (l == 150) {
+            for (int i = 0; i < 5; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) if (i % 2 == 1) sim.setVoxel(b, i, j, k);
+            ts = sim.recommendedTimeStep();
+        }
+    }
+    CHECK_NEAR(3.8167e-8, sim.voxel(4, 0, 0)->position().z, 1e-10);
+}
+
+static void temperatureBimorph()        // tVoxelyze.h:989-1032
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* a = sim.addMaterial(1e6, 1e3); a->setInternalDamping(1.0f); a->setGlobalDamping(0.15f); a->setCte(0.01f);
+    CVX_Material* b = sim.addMaterial(1e7f, 1e3f); b->setInternalDamping(1.0f); b->setGlobalDamping(0.15f);
+    for (int i = 0; i < 3; i++) {
+        CVX_Voxel* v1 = sim.setVoxel(a, i, 0, 0); CVX_Voxel* v2 = sim.setVoxel(b, i, 0, 1);
+        if (i == 0) { v1->external()->setFixedAll(); v2->external()->setFixedAll(); }
+    }
+    sim.setAmbientTemperature(5, true);
+    float ts = sim.recommendedTimeStep();
+    for (int l = 0; l < 500; l++) sim.doTimeStep(ts);
+    CHECK_NEAR(2.55e-5, sim.voxel(2, 0, 0)->position().z, 1e-8);
+    sim.resetTime();
+    sim.setAmbientTemperature(-5, true);
+    for (int l = 0; l < 500; l++) sim.doTimeStep(ts);
+    CHECK_NEAR(-2.591e-5, sim.voxel(2, 0, 0)->position().z, 1e-8);
+}
+
+static void staticFriction()            // tVoxelyze.h:1034-1112
+{
+    const double vSize = 0.001; const float density = 1e3f;
+    CVoxelyze sim(vSize);
+    sim.enableFloor(true);
+    sim.setGravity();
+    CVX_Material* m = sim.addMaterial(1e6, density);
+    const float normalForce = (float)(density * vSize * vSize * vSize * 9.80665);
+    CVX_Voxel* v = sim.setVoxel(m, 0, 0, 0);
+    m->setStaticFriction(1.0f); m->setKineticFriction(0.1f); m->setGlobalDamping(1.0f);
+    float ts = sim.recommendedTimeStep();
+    struct Trial { float g, mu, push; bool moves; };
+    const Trial trials[] = {{1, 1, 0.9f, false}, {1, 1, 1.1f, true}, {2, 1, 1.9f, false}, {2, 1, 2.1f, true}, {1, 2, 1.9f, false}, {1, 2, 2.1f, true}};
+    for (const Trial& t : trials) {
+        sim.setGravity(t.g); m->setStaticFriction(t.mu);
+        for (int l = 0; l < 50; l++) sim.doTimeStep(ts);
+        v->external()->setForce(t.push * normalForce, 0.0f, 0.0f);
+        for (int l = 0; l < 10; l++) sim.doTimeStep(ts);
+        if (t.moves) CHECK(v->position().x != 0.0); else CHECK(v->position().x == 0.0);
+        v->external()->setForce(0.0f, 0.0f, 0.0f);
+        sim.resetTime();
+    }
+}
+
+static void kineticFriction()           // tVoxelyze.h:1116-1167
+{
+    const double vSize = 0.001; const float density = 1e3f;
+    CVoxelyze sim(vSize);
+    sim.enableFloor(true); sim.setGravity();
+    CVX_Material* m = sim.addMaterial(1e6, density);
+    const double mass = density * vSize * vSize * vSize; const float normalForce = (float)(mass * 9.80665);
+    CVX_Voxel* v = sim.setVoxel(m, 0, 0, 0);
+    m->setStaticFriction(1.0f); m->setKineticFriction(0.1f); m->setGlobalDamping(1.0f);
+    float ts = sim.recommendedTimeStep();
+    for (int l = 0; l < 50; l++) sim.doTimeStep(ts);
+    m->setGlobalDamping(0.0001f);
+    const float push = 2.0f * normalForce;
+    v->external()->setForce(push, 0.0f, 0.0f);
+    double last = 0, vel = 0, energy = 0;
+    for (int l = 0; l < 10; l++) {
+        sim.doTimeStep(ts);
+        double cur = v->position().x;
+        vel = (cur - last) / ts;
+        energy += (l == 9 ? 0.5f : 1.0f) * (push - m->kineticFriction() * normalForce) * (cur - last);
+        last = cur;
+    }
+    CHECK_NEAR(energy, 0.5 * mass * vel * vel, 2e-16);
+}
+
+static void collisionsHoldUp()          // tVoxelyze.h:1169-1197
+{
+    CVoxelyze sim(0.001);
+    sim.enableFloor(true); sim.setGravity();
+    CVX_Material* m = sim.addMaterial(1e6, 1e6f);
+    m->setGlobalDamping(0.0f);
+    sim.setVoxel(m, 0, 0, 0)->external()->setFixedAll();
+    sim.setVoxel(m, 0, 0, 2);
+    sim.enableCollisions();
+    float ts = sim.recommendedTimeStep();
+    for (int l = 0; l < 150; l++) sim.doTimeStep(ts);
+    CHECK(sim.voxel(0, 0, 2)->position().z > 0.001);
+    CHECK(sim.collisionList()->size() == 1);
+}
+
+static void stateInfoBasics()           // Voxelyze.cpp:752-800 through the public call
+{
+    CVoxelyze sim(0.001);
+    CVX_Material* m = sim.addMaterial(1e6, 1e3);
+    sim.setVoxel(m, 0, 0, 0)->external()->setFixedAll();
+    CVX_Voxel* b = sim.setVoxel(m, 1, 0, 0);
+    b->external()->setForce(1e-3f, 0, 0);
+    float ts = sim.recommendedTimeStep();
+    for (int l = 0; l < 300; l++) sim.doTimeStep(ts);
+    CHECK_NEAR(sim.stateInfo(CVoxelyze::DISPLACEMENT, CVoxelyze::MAX), (float)b->displacement().Length(), 1e-12);
+    CHECK_NEAR(sim.stateInfo(CVoxelyze::ENG_STRAIN, CVoxelyze::MAX), 1e-3, 1e-6);
+    CHECK_NEAR(sim.stateInfo(CVoxelyze::ENG_STRESS, CVoxelyze::AVERAGE), 1e3, 1.0);
+    CHECK_NEAR(sim.stateInfo(CVoxelyze::MASS, CVoxelyze::TOTAL), 2e-6, 1e-12);
+    CHECK_NEAR(sim.stateInfo(CVoxelyze::STRAIN_ENERGY, CVoxelyze::TOTAL), 0.5 * 1e-3 * 1e-6, 1e-11);
+}
+
+// ---- material classes (stand-alone objects, no simulation / no device) ---------------------------
+static void materialModels()            // tVX_Material.h, tVX_MaterialLink.h:3-69
+{
+    CVX_Material mat;
+    CHECK(!mat.setModelLinear(-1.0f));
+    CHECK(std::string(mat.lastError()).find("Young") != std::string::npos);
+    CHECK(mat.setModelBilinear(1e6f, 5e5f, 1e5f, 2e5f));
+    CHECK(!mat.isModelLinear());
+    CHECK_FLOAT_EQ(0.1f, mat.yieldStress() / mat.youngsModulus());
+    CHECK_FLOAT_EQ(5e4f, mat.stress(0.05f));
+    CHECK_FLOAT_EQ(1.5e5f, mat.stress(0.2f));
+    CHECK_FLOAT_EQ(5e5f, mat.modulus(0.2f));
+    CHECK(mat.isYielded(0.11f) && !mat.isYielded(0.09f) && mat.isFailed(0.31f) && !mat.isFailed(0.29f));
+    mat.setPoissonsRatio(0.7f);
+    CHECK(mat.poissonsRatio() < 0.5f);
+    mat.setDensity(-5.0f);
+    CHECK(mat.density() > 0);
+
+    CVX_MaterialVoxel a, b;
+    CHECK(a.setModelLinear(1.0f)); CHECK(b.setModelLinear(10.0f));
+    CVX_MaterialLink ab(&a, &b);
+    CHECK_FLOAT_EQ(20.0f / 11.0f, ab.youngsModulus());
+    CHECK(!ab.isFailed(1));
+    CVX_MaterialVoxel c, d;
+    CHECK(c.setModelLinear(10.0f, 30.0f)); CHECK(d.setModelLinear(1.0f, 2.0f));
+    CVX_MaterialLink cd(&c, &d);
+    CHECK_FLOAT_EQ(20.0f / 11.0f, cd.youngsModulus());
+    CHECK(!cd.isFailed(1.0f) && cd.isFailed(1.2f));
+    CVX_MaterialVoxel e, f;
+    CHECK(e.setModelBilinear(1.0f, 0.5f, 1.0f, 2.0f)); CHECK(f.setModelBilinear(2.0f, 1.0f, 4.0f, 6.0f));
+    CVX_MaterialLink ef(&e, &f);
+    CHECK_FLOAT_EQ(4.0f / 3.0f, ef.youngsModulus());
+    CHECK_FLOAT_EQ(4.0f / 3.0f, ef.modulus(0.5));
+    CHECK_FLOAT_EQ(2.0f / 2.5f, ef.modulus(1.5));
+    CHECK_FLOAT_EQ(0.0f, ef.modulus(2.5));
+    CHECK(!ef.isFailed(1.8) && ef.isFailed(1.9));
+}
+
+static void voxelExternals()            // tVX_Voxel.h:3-68
+{
+    CVX_MaterialVoxel mat;
+    CVX_Voxel vox(&mat, 0, 0, 0);
+    CHECK(!vox.externalExists());
+    CHECK(!vox.external()->isFixed(X_TRANSLATE) && !vox.external()->isFixed(Z_ROTATE));
+    CHECK(vox.externalExists());
+    vox.external()->setFixedAll();
+    CHECK(vox.external()->isFixedAll() && vox.external()->isFixed(Y_TRANSLATE) && vox.external()->isFixed(X_ROTATE));
+    vox.external()->setFixedAll(false);
+    CHECK(!vox.external()->isFixedAny());
+    vox.external()->setFixed(X_TRANSLATE);
+    CHECK(vox.external()->isFixed(X_TRANSLATE) && !vox.external()->isFixed(Y_TRANSLATE));
+    vox.external()->setDisplacement(Z_ROTATE, 0.25);
+    CHECK(vox.external()->isFixed(Z_ROTATE));
+    CHECK_NEAR(vox.external()->rotation().z, 0.25, 0);
+    CHECK_NEAR(vox.external()->rotationQuat().w, std::cos(0.125), 1e-15);
+}
+
+int main(int argc, char** argv)
+{
+    struct T { const char* name; void (*fn)(); bool device; };
+    const T tests[] = {
+        {"materialModels", materialModels, false}, {"voxelExternals", voxelExternals, false},
+        {"simpleSetup", simpleSetup, true}, {"singleBondFixedFree", singleBondFixedFree, true}, {"singleBondFreeFree", singleBondFreeFree, true},
+        {"resetTime", resetTime, true}, {"dampingInternalAndGlobal", dampingInternalAndGlobal, true}, {"combinedDamping", combinedDamping, true},
+        {"scaleOfForce", scaleOfForce, true}, {"axialFrequency", axialFrequency, true}, {"largeDeformation", largeDeformation, true},
+        {"doubleBondCantilever", doubleBondCantilever, true}, {"impulse", impulse, true}, {"multiMaterial", multiMaterial, true},
+        {"deformableMaterial", deformableMaterial, true}, {"replaceMaterialMidRun", replaceMaterialMidRun, true},
+        {"temperatureBimorph", temperatureBimorph, true}, {"staticFriction", staticFriction, true}, {"kineticFriction", kineticFriction, true},
+        {"collisionsHoldUp", collisionsHoldUp, true}, {"stateInfoBasics", stateInfoBasics, true},
+    };
+    bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
+    int ran = 0;
+    for (const T& t : tests) {
+        if (host_only && t.device) continue;
+        if (argc > 1 && !host_only && std::string(argv[1]) != t.name) continue;
+        g_current = t.name;
+        int before = g_failures;
+        t.fn();
+        printf("%s %s\n", g_failures == before ? "PASS" : "FAILED", t.name);
+        ran++;
+    }
+    printf("%d tests, %d checks, %d failures\n", ran, g_checks, g_failures);
+    return g_failures ? 1 : 0;
+}

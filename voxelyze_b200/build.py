@@ -58,6 +58,52 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
     return PRODUCT_SO
 
 
+FACADE_SO = os.path.join(LIBDIR, "libvoxelyze_facade.so")
+FACADE_DIR = os.path.join(ROOT, "voxelyze_b200", "facade")
+
+
+def build_facade(force: bool = False) -> str:
+    """The C++ drop-in class API (CVoxelyze, CVX_*) on top of the C-ABI library."""
+    src = os.path.join(FACADE_DIR, "src", "voxelyze_facade.cpp")
+    inc = os.path.join(FACADE_DIR, "include")
+    deps = [src, PRODUCT_SO] + [os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(CSRC, "vx_material.hpp")]
+    if not force and _newer(FACADE_SO, deps):
+        return FACADE_SO
+    cmd = [_host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable", "-Wno-overloaded-virtual",
+           "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", FACADE_SO, src,
+           "-L", LIBDIR, "-lvoxelyze_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return FACADE_SO
+
+
+def build_cpp_tests() -> dict:
+    """tests/cpp/dropin_tests.cpp compiled twice: against the facade (runs on the GPU) and, where
+    /root/reference exists, against the unmodified reference (runs on the CPU) - same source."""
+    out = {}
+    tdir = os.path.join(ROOT, "tests", "cpp")
+    bdir = os.path.join(tdir, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    src = os.path.join(tdir, "dropin_tests.cpp")
+    inc = os.path.join(FACADE_DIR, "include")
+    exe = os.path.join(bdir, "dropin_b200")
+    if not _newer(exe, [src, FACADE_SO]):
+        subprocess.run([_host_cxx(), "-O2", "-std=c++17", "-Wno-overloaded-virtual", "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                        "-o", exe, src, "-L", LIBDIR, "-lvoxelyze_facade", "-lvoxelyze_b200",
+                        "-Wl,-rpath," + LIBDIR], check=True)
+    out["b200"] = exe
+    ref = "/root/reference"
+    exe_ref = os.path.join(bdir, "dropin_ref")
+    if os.path.isdir(os.path.join(ref, "src")):
+        if not _newer(exe_ref, [src]):
+            names = ["Voxelyze", "VX_Link", "VX_Voxel", "VX_External", "VX_Material", "VX_MaterialVoxel",
+                     "VX_MaterialLink", "VX_Collision", "VX_LinearSolver"]
+            subprocess.run([_host_cxx(), "-O3", "-std=c++11", "-w", "-DDROPIN_REFERENCE", "-I", os.path.join(ref, "include"),
+                            "-o", exe_ref, src] + [os.path.join(ref, "src", n + ".cpp") for n in names], check=True)
+    if os.path.exists(exe_ref):
+        out["ref"] = exe_ref
+    return out
+
+
 def build_oracles() -> None:
     """Builds the checkers (oracle port always; oracle/_ref only where /root/reference exists)."""
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port", "ref"], check=True)
@@ -67,5 +113,6 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "product"):
         print(build_product(force="--force" in sys.argv, verbose="-v" in sys.argv))
+        print(build_facade(force="--force" in sys.argv))
     if what in ("all", "oracle"):
         build_oracles()

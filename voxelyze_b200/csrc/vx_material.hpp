@@ -142,6 +142,27 @@ struct Material {
         return i < 0 ? 0.0f : (sig[i] - sig[i - 1]) / (eps[i] - eps[i - 1]);
     }
 
+    // host copy of the stress law the kernels evaluate (VX_Material.cpp:165-195); used by the facade's
+    // CVX_Material::stress() accessor
+    float stress(float strain, float transverse_sum = 0.0f, bool force_linear = false) const
+    {
+        if (failed(strain)) return 0.0f;
+        if (strain <= eps[1] || linear || force_linear) {
+            if (nu == 0.0f) return E * strain;
+            return e_hat * ((1 - nu) * strain + nu * transverse_sum);
+        }
+        int i = segment(strain);
+        if (i < 0) return 0.0f;
+        float frac = (strain - eps[i - 1]) / (eps[i] - eps[i - 1]);
+        float basic = sig[i - 1] + frac * (sig[i] - sig[i - 1]);
+        if (nu == 0.0f) return basic;
+        float seg_mod = (sig[i] - sig[i - 1]) / (eps[i] - eps[i - 1]);
+        float seg_hat = seg_mod / ((1 - 2 * nu) * (1 + nu));
+        float eff = basic / seg_mod;
+        float eff_sum = transverse_sum * (eff / strain);
+        return seg_hat * ((1 - nu) * eff + nu * eff_sum);
+    }
+
     // inverse lookup (VX_Material.cpp:197-211)
     float strain_at(float stress) const
     {

@@ -1,0 +1,643 @@
+// voxelyze_facade.cpp -- host side of the drop-in C++ API (see facade/include/Voxelyze.h).
+//
+// Everything here is bookkeeping: it records the model the caller builds through the reference's
+// class API, keeps stable CVX_Voxel / CVX_Link / CVX_Material handles, and translates to the flat
+// C-ABI of include/voxelyze_b200.h.  No dynamics are computed on the host: doTimeStep is one
+// vx_step call, accessors are vx_download calls.  There is no CPU fallback; if the CUDA library
+// cannot create a device handle the process stops with a message.
+#include "Voxelyze.h"
+#include "voxelyze_b200.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+float CVX_Collision::envelopeRadius = 0.625f;
+
+// ================================================================================================ CVX_Material
+CVX_Material::CVX_Material(float youngsModulus, float density)
+{
+    clear();
+    m_.rho = density;
+    setModelLinear(youngsModulus);
+}
+
+CVX_Material& CVX_Material::operator=(const CVX_Material& o)
+{
+    m_ = o.m_; name_ = o.name_; r_ = o.r_; g_ = o.g_; b_ = o.b_; a_ = o.a_;
+    changes_++;
+    return *this;
+}
+
+void CVX_Material::clear()
+{
+    r_ = g_ = b_ = a_ = -1;
+    vxm::Material fresh;            // defaults of the reference's clear(): nu 0, rho 1, zeta_internal 1, ...
+    m_ = fresh;
+    m_.model_linear(1.0f);
+    changed();
+}
+
+bool CVX_Material::setModel(int n, float* strain, float* stress) { bool ok = m_.model_data(n, strain, stress); if (ok) changed(); return ok; }
+bool CVX_Material::setModelLinear(float E, float fail) { bool ok = m_.model_linear(E, fail); if (ok) changed(); return ok; }
+bool CVX_Material::setModelBilinear(float E, float plastic, float yield, float fail) { bool ok = m_.model_bilinear(E, plastic, yield, fail); if (ok) changed(); return ok; }
+
+void CVX_Material::setPoissonsRatio(float nu)
+{
+    if (nu < 0) nu = 0;
+    if (nu >= 0.5) nu = 0.5 - FLT_EPSILON * 2;
+    m_.nu = nu;
+    changed();
+}
+void CVX_Material::setDensity(float density) { m_.rho = density <= 0 ? FLT_MIN : density; changed(); }
+void CVX_Material::setExternalScaleFactor(Vec3D<double> f)
+{
+    m_.ext_scale[0] = f.x <= 0 ? (double)FLT_MIN : f.x;
+    m_.ext_scale[1] = f.y <= 0 ? (double)FLT_MIN : f.y;
+    m_.ext_scale[2] = f.z <= 0 ? (double)FLT_MIN : f.z;
+    changed();
+}
+
+// ================================================================================================ CVX_MaterialVoxel
+CVX_MaterialVoxel::CVX_MaterialVoxel(float E, float rho, double nominalSize) : CVX_Material(E, rho) { nom_ = nominalSize; updateDerived(); }
+CVX_MaterialVoxel::CVX_MaterialVoxel(const CVX_Material& mat, double nominalSize) : CVX_Material(mat) { nom_ = nominalSize; updateDerived(); }
+CVX_MaterialVoxel& CVX_MaterialVoxel::operator=(const CVX_MaterialVoxel& o)
+{
+    CVX_Material::operator=(o);
+    nom_ = o.nom_; gravMult_ = o.gravMult_;
+    updateDerived();
+    return *this;
+}
+bool CVX_MaterialVoxel::setNominalSize(double size) { nom_ = size <= 0 ? (double)FLT_MIN : size; changes_++; return updateDerived(); }
+bool CVX_MaterialVoxel::updateDerived()
+{
+    CVX_Material::updateDerived();
+    p_ = vxm::mass_props(m_, nom_);
+    return p_.mass_inv != 0.0f;
+}
+
+// ================================================================================================ CVX_MaterialLink
+CVX_MaterialLink::CVX_MaterialLink(CVX_MaterialVoxel* a, CVX_MaterialVoxel* b) : vox1Mat(a), vox2Mat(b) { updateAll(); }
+CVX_MaterialLink& CVX_MaterialLink::operator=(const CVX_MaterialLink& o)
+{
+    CVX_MaterialVoxel::operator=(o);
+    vox1Mat = o.vox1Mat; vox2Mat = o.vox2Mat; k_ = o.k_;
+    return *this;
+}
+bool CVX_MaterialLink::updateAll()
+{
+    nom_ = 0.5 * (vox1Mat->nom_ + vox2Mat->nom_);
+    m_ = vxm::combine(vox1Mat->model(), vox2Mat->model());
+    r_ = (int)(0.5 * (vox1Mat->r_ + vox2Mat->r_)); g_ = (int)(0.5 * (vox1Mat->g_ + vox2Mat->g_));
+    b_ = (int)(0.5 * (vox1Mat->b_ + vox2Mat->b_)); a_ = (int)(0.5 * (vox1Mat->a_ + vox2Mat->a_));
+    return updateDerived();
+}
+bool CVX_MaterialLink::updateDerived()
+{
+    CVX_MaterialVoxel::updateDerived();
+    k_ = vxm::beam_consts(m_, nom_);
+    return true;
+}
+
+// ================================================================================================ CVX_External
+CVX_External& CVX_External::operator=(const CVX_External& e)
+{
+    dofFixed = e.dofFixed; extForce = e.extForce; extMoment = e.extMoment;
+    extTranslation = e.extTranslation; extRotation = e.extRotation;
+    rotationChanged();
+    return *this;
+}
+void CVX_External::reset()
+{
+    dofFixed = 0;
+    extForce = extMoment = Vec3D<float>();
+    extTranslation = extRotation = Vec3D<double>();
+    rotationChanged();
+}
+void CVX_External::setFixed(bool tx, bool ty, bool tz, bool rx, bool ry, bool rz)
+{
+    dofFixed = dof(tx, ty, tz, rx, ry, rz);
+    extTranslation = extRotation = Vec3D<double>();      // like the reference, the cached quaternion is left as it was
+    touch();
+}
+void CVX_External::setDisplacement(dofComponent d, double displacement)
+{
+    dofSet(dofFixed, d, true);
+    if (displacement != 0.0f) {
+        if (d & X_TRANSLATE) extTranslation.x = displacement;
+        if (d & Y_TRANSLATE) extTranslation.y = displacement;
+        if (d & Z_TRANSLATE) extTranslation.z = displacement;
+        if (d & X_ROTATE) extRotation.x = displacement;
+        if (d & Y_ROTATE) extRotation.y = displacement;
+        if (d & Z_ROTATE) extRotation.z = displacement;
+    }
+    rotationChanged();
+}
+void CVX_External::setDisplacementAll(const Vec3D<double>& t, const Vec3D<double>& r)
+{
+    dofSetAll(dofFixed, true);
+    extTranslation = t; extRotation = r;
+    rotationChanged();
+}
+void CVX_External::clearDisplacement(dofComponent d)
+{
+    dofSet(dofFixed, d, false);
+    if (d & X_TRANSLATE) extTranslation.x = 0.0;
+    if (d & Y_TRANSLATE) extTranslation.y = 0.0;
+    if (d & Z_TRANSLATE) extTranslation.z = 0.0;
+    if (d & X_ROTATE) extRotation.x = 0.0;
+    if (d & Y_ROTATE) extRotation.y = 0.0;
+    if (d & Z_ROTATE) extRotation.z = 0.0;
+    rotationChanged();
+}
+void CVX_External::clearDisplacementAll()
+{
+    dofSetAll(dofFixed, false);
+    extTranslation = extRotation = Vec3D<double>();
+    rotationChanged();
+}
+void CVX_External::rotationChanged()
+{
+    if (extRotation != Vec3D<double>()) rotQ = Quat3D<double>(extRotation);
+    else rotQ = Quat3D<double>();
+    touch();
+}
+
+// ================================================================================================ CVX_Voxel
+CVX_Voxel::CVX_Voxel(CVX_MaterialVoxel* material, short x, short y, short z) : mat(material), ix(x), iy(y), iz(z)
+{
+    for (int i = 0; i < 6; i++) links[i] = nullptr;
+    pos0 = originalPosition();
+}
+CVX_Voxel::~CVX_Voxel() { delete ext; }
+
+CVX_External* CVX_Voxel::external()
+{
+    if (!ext) { ext = new CVX_External(); if (sim) ext->attach(&sim->extChanges); }
+    return ext;
+}
+CVX_Voxel* CVX_Voxel::adjacentVoxel(linkDirection d) const
+{
+    CVX_Link* l = links[d];
+    if (!l) return nullptr;
+    return l->voxel(true) == this ? l->voxel(false) : l->voxel(true);
+}
+Vec3D<double> CVX_Voxel::position() const
+{
+    if (!sim) return pos0;
+    sim->fetchVoxel(index);
+    return Vec3D<double>(sim->mPos[3 * index], sim->mPos[3 * index + 1], sim->mPos[3 * index + 2]);
+}
+Quat3D<double> CVX_Voxel::orientation() const
+{
+    if (!sim) return Quat3D<double>();
+    sim->fetchVoxel(index);
+    return Quat3D<double>(sim->mOrient[4 * index], sim->mOrient[4 * index + 1], sim->mOrient[4 * index + 2], sim->mOrient[4 * index + 3]);
+}
+Vec3D<double> CVX_Voxel::linearMomentum() const
+{
+    if (!sim) return Vec3D<double>();
+    sim->fetchVoxel(index);
+    return Vec3D<double>(sim->mLin[3 * index], sim->mLin[3 * index + 1], sim->mLin[3 * index + 2]);
+}
+Vec3D<double> CVX_Voxel::angularMomentum() const
+{
+    if (!sim) return Vec3D<double>();
+    sim->fetchVoxel(index);
+    return Vec3D<double>(sim->mAng[3 * index], sim->mAng[3 * index + 1], sim->mAng[3 * index + 2]);
+}
+float CVX_Voxel::temperatureValue() const
+{
+    if (!sim) return temp0;
+    sim->fetchVoxel(index);
+    return sim->mTemp[index];
+}
+bool CVX_Voxel::isFloorStaticFriction() const
+{
+    if (!sim) return true;
+    sim->fetchVoxel(index);
+    return (sim->mFlags[index] & VX_VF_STATIC_FRICTION) != 0;
+}
+void CVX_Voxel::setTemperature(float t)
+{
+    if (!sim) { temp0 = t; return; }
+    sim->sync();
+    vx_upload(sim->h, VX_F_TEMP, index, 1, &t);
+    sim->epoch++;
+}
+void CVX_Voxel::haltMotion()
+{
+    if (!sim) return;
+    sim->sync();
+    const double zero[3] = {0, 0, 0};
+    vx_upload(sim->h, VX_F_LINMOM, index, 1, zero);
+    vx_upload(sim->h, VX_F_ANGMOM, index, 1, zero);
+    sim->epoch++;
+}
+bool CVX_Voxel::isYielded() const { for (int i = 0; i < 6; i++) if (links[i] && links[i]->isYielded()) return true; return false; }
+bool CVX_Voxel::isFailed() const { for (int i = 0; i < 6; i++) if (links[i] && links[i]->isFailed()) return true; return false; }
+
+// ================================================================================================ CVX_Link
+static Vec3D<> link_vec(const CVoxelyze* sim, vx_sim* h, int field, int index)
+{
+    (void)sim;
+    double v[3] = {0, 0, 0};
+    vx_download(h, field, index, 1, v);
+    return Vec3D<>(v[0], v[1], v[2]);
+}
+static float link_f32(vx_sim* h, int field, int index) { float v = 0; vx_download(h, field, index, 1, &v); return v; }
+static uint32_t link_flags(vx_sim* h, int index) { uint32_t v = 0; vx_download(h, VX_F_LINKFLAGS, index, 1, &v); return v; }
+
+Vec3D<> CVX_Link::force(bool positiveEnd) const { sim->sync(); return link_vec(sim, sim->h, positiveEnd ? VX_F_FORCE_POS : VX_F_FORCE_NEG, index); }
+Vec3D<> CVX_Link::moment(bool positiveEnd) const { sim->sync(); return link_vec(sim, sim->h, positiveEnd ? VX_F_MOMENT_POS : VX_F_MOMENT_NEG, index); }
+float CVX_Link::axialStrain() const { sim->sync(); return link_f32(sim->h, VX_F_STRAIN, index); }
+float CVX_Link::axialStrain(bool positiveEnd) const
+{
+    float strain = axialStrain();
+    float ratio = pVPos->material()->youngsModulus() / pVNeg->material()->youngsModulus();      // strainRatio, src/VX_Link.cpp:67
+    return positiveEnd ? 2.0f * strain * ratio / (1.0f + ratio) : 2.0f * strain / (1.0f + ratio);
+}
+float CVX_Link::axialStress() const { sim->sync(); return link_f32(sim->h, VX_F_STRESS, index); }
+bool CVX_Link::isSmallAngle() const { sim->sync(); return (link_flags(sim->h, index) & VX_LF_SMALL_ANGLE) != 0; }
+bool CVX_Link::isYielded() const { sim->sync(); return (link_flags(sim->h, index) & VX_LF_YIELDED) != 0; }
+bool CVX_Link::isFailed() const { sim->sync(); return (link_flags(sim->h, index) & VX_LF_FAILED) != 0; }
+float CVX_Link::strainEnergy() const                                                              // src/VX_Link.cpp:251-257
+{
+    Vec3D<> fN = force(false), mN = moment(false), mP = moment(true);
+    return fN.x * fN.x / (2.0f * mat->a1()) + mN.x * mN.x / (2.0 * mat->a2()) +
+           (mN.z * mN.z - mN.z * mP.z + mP.z * mP.z) / (3.0 * mat->b3()) +
+           (mN.y * mN.y - mN.y * mP.y + mP.y * mP.y) / (3.0 * mat->b3());
+}
+float CVX_Link::axialStiffness() { return mat->a1(); }      // nu = 0 value (src/VX_Link.cpp:260)
+
+// ================================================================================================ CVoxelyze
+CVoxelyze::CVoxelyze(double voxelSize) : voxSize(voxelSize) {}
+CVoxelyze::~CVoxelyze() { clear(); if (h) vx_destroy(h); }
+
+void CVoxelyze::die(const char* what) const
+{
+    fprintf(stderr, "voxelyze_b200: %s: %s\n", what, h ? vx_last_error(h) : "no CUDA device handle (this build has no CPU fallback)");
+    abort();
+}
+
+void CVoxelyze::clear()
+{
+    for (auto& kv : linkPool) delete kv.second;
+    linkPool.clear(); linksList.clear();
+    for (CVX_Voxel* v : voxelsList) delete v;
+    voxelsList.clear(); cells.clear();
+    for (CVX_MaterialVoxel* m : voxelMats) delete m;
+    voxelMats.clear();
+    for (CVX_MaterialLink* m : linkMats) delete m;
+    linkMats.clear();
+    for (CVX_Collision* c : collisionsList) delete c;
+    collisionsList.clear();
+    ambientTemp = 0.0f; grav = 0.0f; floor = false; collisions = false;
+    topologyDirty = envDirty = true; stepped = false; epoch++;
+    if (h) { vx_destroy(h); h = nullptr; }
+}
+
+CVX_Material* CVoxelyze::addMaterial(float E, float rho)
+{
+    CVX_MaterialVoxel* m = new CVX_MaterialVoxel(E, rho, voxSize);
+    m->gravMult_ = grav;
+    voxelMats.push_back(m);
+    topologyDirty = true;           // the material table grew: the device model is rebuilt at the next sync
+    return m;
+}
+CVX_Material* CVoxelyze::addMaterial(const CVX_Material& mat)
+{
+    CVX_MaterialVoxel* m = new CVX_MaterialVoxel(mat, voxSize);
+    m->gravMult_ = grav;
+    voxelMats.push_back(m);
+    topologyDirty = true;
+    return m;
+}
+bool CVoxelyze::removeMaterial(CVX_Material* toRemove)
+{
+    auto it = std::find(voxelMats.begin(), voxelMats.end(), (CVX_MaterialVoxel*)toRemove);
+    if (it == voxelMats.end()) return false;
+    std::vector<CVX_Voxel*> doomed;
+    for (CVX_Voxel* v : voxelsList) if (v->mat == *it) doomed.push_back(v);
+    for (CVX_Voxel* v : doomed) removeVoxel(v->ix, v->iy, v->iz);
+    delete *it;
+    voxelMats.erase(it);
+    topologyDirty = true;
+    return true;
+}
+bool CVoxelyze::replaceMaterial(CVX_Material* replaceMe, CVX_Material* replaceWith)
+{
+    auto has = [&](CVX_Material* m) { return std::find(voxelMats.begin(), voxelMats.end(), (CVX_MaterialVoxel*)m) != voxelMats.end(); };
+    if (!has(replaceMe) || !has(replaceWith)) return false;
+    for (CVX_Voxel* v : std::vector<CVX_Voxel*>(voxelsList)) if (v->mat == (CVX_MaterialVoxel*)replaceMe) setVoxel(replaceWith, v->ix, v->iy, v->iz);
+    return true;
+}
+
+CVX_Voxel* CVoxelyze::voxel(int x, int y, int z) const
+{
+    auto it = cells.find(key(x, y, z));
+    return it == cells.end() ? nullptr : it->second;
+}
+
+CVX_Voxel* CVoxelyze::setVoxel(CVX_Material* material, int x, int y, int z)
+{
+    if (material == nullptr) { removeVoxel(x, y, z); return nullptr; }
+    CVX_MaterialVoxel* m = (CVX_MaterialVoxel*)material;
+    CVX_Voxel* v = voxel(x, y, z);
+    if (v) {                                        // replaceVoxel (src/Voxelyze.cpp:485-498)
+        if (v->mat != m) {
+            if (stepped) {                          // keep velocity across the material change (src/VX_Voxel.cpp:78-90)
+                fetchAll();
+                double ls = m->p_.mass / v->mat->p_.mass, as = m->p_.inertia / v->mat->p_.inertia;
+                for (int a = 0; a < 3; a++) { mLin[3 * v->index + a] *= ls; mAng[3 * v->index + a] *= as; }
+                mFlags[v->index] &= ~VX_VF_STATIC_FRICTION;
+                pendingStateEdit.push_back(v->index);
+            }
+            v->mat = m;
+            topologyDirty = true;
+        }
+        return v;
+    }
+    if (stepped) fetchAll();                         // existing voxels keep their state across the re-layout
+    v = new CVX_Voxel(m, (short)x, (short)y, (short)z);
+    v->sim = this; v->index = (int)voxelsList.size();
+    voxelsList.push_back(v);
+    cells[key(x, y, z)] = v;
+    topologyDirty = true;
+    return v;
+}
+
+void CVoxelyze::removeVoxel(int x, int y, int z)
+{
+    CVX_Voxel* v = voxel(x, y, z);
+    if (!v) return;
+    if (stepped) fetchAll();
+    cells.erase(key(x, y, z));
+    removedIndices.push_back(v->index);
+    voxelsList.erase(voxelsList.begin() + v->index);
+    for (size_t i = 0; i < voxelsList.size(); i++) voxelsList[i]->index = (int)i;
+    for (auto it = linkPool.begin(); it != linkPool.end();) {
+        if (it->second->pVNeg == v || it->second->pVPos == v) { delete it->second; it = linkPool.erase(it); } else ++it;
+    }
+    delete v;
+    topologyDirty = true;
+}
+
+int CVoxelyze::bound(int axis, bool max) const
+{
+    if (voxelsList.empty()) return 0;
+    int best = max ? -32768 : 32767;
+    for (CVX_Voxel* v : voxelsList) {
+        int c = axis == 0 ? v->ix : (axis == 1 ? v->iy : v->iz);
+        best = max ? std::max(best, c) : std::min(best, c);
+    }
+    return best;
+}
+
+CVX_MaterialLink* CVoxelyze::combinedMaterial(CVX_MaterialVoxel* a, CVX_MaterialVoxel* b) const
+{
+    for (CVX_MaterialLink* m : linkMats)
+        if ((m->vox1Mat == a && m->vox2Mat == b) || (m->vox1Mat == b && m->vox2Mat == a)) return m;
+    CVX_MaterialLink* m = new CVX_MaterialLink(a, b);
+    linkMats.push_back(m);
+    return m;
+}
+
+// ---- device synchronisation -------------------------------------------------------------------
+void CVoxelyze::uploadMaterials() const
+{
+    std::vector<vx_material_desc> d(voxelMats.size());
+    for (size_t i = 0; i < d.size(); i++) {
+        const vxm::Material& m = voxelMats[i]->model();
+        vx_material_desc& o = d[i];
+        memset(&o, 0, sizeof(o));
+        // the model is handed over as data points: that is what every setModel* call produces, so all
+        // three model kinds round-trip exactly (linear models keep their special flag below)
+        if (m.linear) { o.model = VX_MODEL_LINEAR; o.youngs_modulus = m.E; o.fail_stress = m.sigma_fail; }
+        else { o.model = VX_MODEL_DATA; o.n_points = (int)m.eps.size() - 1; o.strain = m.eps.data() + 1; o.stress = m.sig.data() + 1; }
+        o.density = m.rho; o.poissons_ratio = m.nu; o.cte = m.cte; o.mu_static = m.mu_s; o.mu_kinetic = m.mu_k;
+        o.zeta_internal = m.zeta_int; o.zeta_global = m.zeta_glob; o.zeta_collision = m.zeta_coll;
+        for (int a = 0; a < 3; a++) o.ext_scale[a] = m.ext_scale[a];
+    }
+    if (vx_set_materials(h, (int)d.size(), d.data()) != VX_OK) die("vx_set_materials");
+    for (CVX_MaterialLink* lm : linkMats) lm->updateAll();
+}
+
+void CVoxelyze::uploadExternals() const
+{
+    std::vector<int32_t> vox; std::vector<uint8_t> dof; std::vector<float> f, m; std::vector<double> t, r;
+    for (CVX_Voxel* v : voxelsList) {
+        if (!v->ext) continue;
+        CVX_External* e = v->ext;
+        vox.push_back(v->index); dof.push_back(e->dofMask());
+        Vec3D<float> ef = e->force(), em = e->moment(); Vec3D<double> et = e->translation(), er = e->rotation();
+        f.insert(f.end(), {ef.x, ef.y, ef.z}); m.insert(m.end(), {em.x, em.y, em.z});
+        t.insert(t.end(), {et.x, et.y, et.z}); r.insert(r.end(), {er.x, er.y, er.z});
+    }
+    if (vx_set_externals(h, (int)vox.size(), vox.data(), dof.data(), f.data(), m.data(), t.data(), r.data()) != VX_OK) die("vx_set_externals");
+}
+
+void CVoxelyze::rebuildTopology() const
+{
+    const int n = (int)voxelsList.size();
+    std::vector<int32_t> ijk(3 * (size_t)n); std::vector<uint16_t> mat(n);
+    for (int i = 0; i < n; i++) {
+        CVX_Voxel* v = voxelsList[i];
+        ijk[3 * i] = v->ix; ijk[3 * i + 1] = v->iy; ijk[3 * i + 2] = v->iz;
+        mat[i] = (uint16_t)(std::find(voxelMats.begin(), voxelMats.end(), v->mat) - voxelMats.begin());
+    }
+    const bool keepState = stepped;                 // mirrors were made current by setVoxel/removeVoxel before the edit
+    if (vx_enable_collisions(h, 0) != VX_OK) die("vx_enable_collisions");
+    if (collisions && vx_enable_collisions(h, 1) != VX_OK) die("vx_enable_collisions");
+    if (vx_set_voxels(h, n, ijk.data(), mat.data(), nullptr, nullptr) != VX_OK) die("vx_set_voxels");
+
+    // link handles in C-ABI link order; surviving links keep their handle
+    const int L = vx_link_count(h);
+    std::vector<int32_t> vn(L), vp(L); std::vector<uint8_t> ax(L);
+    vx_get_links(h, vn.data(), vp.data(), ax.data());
+    std::map<std::pair<CVX_Voxel*, int>, CVX_Link*> pool;
+    linksList.assign(L, nullptr);
+    for (CVX_Voxel* v : voxelsList) for (int d = 0; d < 6; d++) v->links[d] = nullptr;
+    for (int i = 0; i < L; i++) {
+        CVX_Voxel* a = voxelsList[vn[i]]; CVX_Voxel* b = voxelsList[vp[i]];
+        std::pair<CVX_Voxel*, int> k(a, ax[i]);
+        CVX_Link* l;
+        auto it = linkPool.find(k);
+        if (it != linkPool.end() && it->second->pVPos == b) { l = it->second; linkPool.erase(it); }
+        else l = new CVX_Link(const_cast<CVoxelyze*>(this), a, b, (CVX_Link::linkAxis)ax[i]);
+        l->index = i; l->mat = combinedMaterial(a->mat, b->mat);
+        pool[k] = l; linksList[i] = l;
+        a->links[2 * ax[i]] = l; b->links[2 * ax[i] + 1] = l;
+    }
+    for (auto& kv : linkPool) delete kv.second;      // links that no longer exist
+    linkPool.swap(pool);
+
+    if (keepState && n) {                            // voxel state survives a topology edit; links restart (documented deviation)
+        // mirrors are indexed by the OLD voxel order minus removed entries: compact them first
+        std::sort(removedIndices.begin(), removedIndices.end());
+        for (int k = (int)removedIndices.size() - 1; k >= 0; k--) {
+            int idx = removedIndices[k];
+            if (idx < (int)mTemp.size()) {
+                mPos.erase(mPos.begin() + 3 * idx, mPos.begin() + 3 * idx + 3); mOrient.erase(mOrient.begin() + 4 * idx, mOrient.begin() + 4 * idx + 4);
+                mLin.erase(mLin.begin() + 3 * idx, mLin.begin() + 3 * idx + 3); mAng.erase(mAng.begin() + 3 * idx, mAng.begin() + 3 * idx + 3);
+                mTemp.erase(mTemp.begin() + idx); mFlags.erase(mFlags.begin() + idx);
+            }
+        }
+        int old = (int)mTemp.size();                 // voxels [0, old) existed before; the rest are new and start fresh
+        if (old > n) old = n;
+        if (old) {
+            vx_upload(h, VX_F_POS, 0, old, mPos.data()); vx_upload(h, VX_F_ORIENT, 0, old, mOrient.data());
+            vx_upload(h, VX_F_LINMOM, 0, old, mLin.data()); vx_upload(h, VX_F_ANGMOM, 0, old, mAng.data());
+            vx_upload(h, VX_F_TEMP, 0, old, mTemp.data()); vx_upload(h, VX_F_VOXFLAGS, 0, old, mFlags.data());
+        }
+    }
+    removedIndices.clear(); pendingStateEdit.clear();
+    mirrorEpoch.assign(n, 0);
+    mPos.resize(3 * (size_t)n); mOrient.resize(4 * (size_t)n); mLin.resize(3 * (size_t)n); mAng.resize(3 * (size_t)n);
+    mTemp.resize(n); mFlags.resize(n);
+    extChangesSeen = ~0ull;
+    epoch++;
+}
+
+void CVoxelyze::sync() const
+{
+    if (!h) {
+        if (vx_create(voxSize, device, &h) != VX_OK) die("vx_create");
+        topologyDirty = envDirty = true; matChangesSeen = ~0ull;
+    }
+    uint64_t matChanges = voxelMats.size();
+    for (CVX_MaterialVoxel* m : voxelMats) matChanges += m->changeCount() * 1315423911ull;
+    if (CVX_Collision::envelopeRadius != envelopeSeen) { vx_set_collision_envelope(h, CVX_Collision::envelopeRadius); envelopeSeen = CVX_Collision::envelopeRadius; }
+    if (envDirty) {
+        if (vx_set_gravity(h, grav) != VX_OK || vx_enable_floor(h, floor) != VX_OK) die("environment");
+    }
+    if (matChanges != matChangesSeen || topologyDirty) { uploadMaterials(); matChangesSeen = matChanges; epoch++; }
+    if (topologyDirty) { rebuildTopology(); topologyDirty = false; }
+    if (envDirty) {
+        if (vx_enable_collisions(h, collisions) != VX_OK) die("vx_enable_collisions");
+        envDirty = false;
+    }
+    if (extChanges != extChangesSeen) { uploadExternals(); extChangesSeen = extChanges; epoch++; }
+    if (tempAllDirty) { vx_set_temperature_all(h, ambientTemp); tempAllDirty = false; epoch++; }
+}
+
+void CVoxelyze::fetchAll() const
+{
+    if (!h || voxelsList.empty() || topologyDirty) return;
+    const int n = (int)mTemp.size();
+    if (n == 0) return;
+    vx_download(h, VX_F_POS, 0, n, mPos.data()); vx_download(h, VX_F_ORIENT, 0, n, mOrient.data());
+    vx_download(h, VX_F_LINMOM, 0, n, mLin.data()); vx_download(h, VX_F_ANGMOM, 0, n, mAng.data());
+    vx_download(h, VX_F_TEMP, 0, n, mTemp.data()); vx_download(h, VX_F_VOXFLAGS, 0, n, mFlags.data());
+    std::fill(mirrorEpoch.begin(), mirrorEpoch.end(), epoch);
+    singleFetches = 0;
+}
+
+void CVoxelyze::fetchVoxel(int i) const
+{
+    sync();
+    if (mirrorEpoch[i] == epoch) return;
+    // a caller polling a handful of voxels per step pays a few 100-byte copies; a caller walking the
+    // whole list gets one bulk download
+    if (++singleFetches > 32) { fetchAll(); return; }
+    vx_download(h, VX_F_POS, i, 1, &mPos[3 * i]); vx_download(h, VX_F_ORIENT, i, 1, &mOrient[4 * i]);
+    vx_download(h, VX_F_LINMOM, i, 1, &mLin[3 * i]); vx_download(h, VX_F_ANGMOM, i, 1, &mAng[3 * i]);
+    vx_download(h, VX_F_TEMP, i, 1, &mTemp[i]); vx_download(h, VX_F_VOXFLAGS, i, 1, &mFlags[i]);
+    mirrorEpoch[i] = epoch;
+}
+
+// ---- the hot path -----------------------------------------------------------------------------
+bool CVoxelyze::doTimeStep(float dt)
+{
+    if (dt == 0) return true;
+    sync();
+    if (voxelsList.empty()) return true;
+    int rc = vx_step(h, dt, 1, nullptr);
+    if (rc != VX_OK && rc != VX_DIVERGED) die("vx_step");
+    stepped = true; epoch++; singleFetches = 0;
+    return rc == VX_OK;
+}
+
+float CVoxelyze::recommendedTimeStep() const
+{
+    sync();
+    float dt = 0.0f;
+    if (vx_recommended_dt(h, &dt) != VX_OK) die("vx_recommended_dt");
+    return dt;
+}
+
+void CVoxelyze::resetTime()
+{
+    sync();
+    if (vx_reset(h) != VX_OK) die("vx_reset");
+    stepped = false; epoch++;
+}
+
+void CVoxelyze::setAmbientTemperature(float t, bool allVoxels) { ambientTemp = t; if (allVoxels) { tempAllDirty = true; } }
+void CVoxelyze::setGravity(float g) { grav = g; for (CVX_MaterialVoxel* m : voxelMats) m->gravMult_ = g; envDirty = true; }
+void CVoxelyze::enableFloor(bool e) { floor = e; envDirty = true; }
+void CVoxelyze::enableCollisions(bool e) { if (collisions == e) return; collisions = e; envDirty = true; if (!stepped) topologyDirty = true; }
+
+// ---- links / collisions -------------------------------------------------------------------------
+int CVoxelyze::linkCount() const { sync(); return (int)linksList.size(); }
+CVX_Link* CVoxelyze::link(int i) { sync(); return linksList[i]; }
+const std::vector<CVX_Link*>* CVoxelyze::linkList() const { sync(); return &linksList; }
+CVX_Link* CVoxelyze::link(int x, int y, int z, CVX_Voxel::linkDirection d) const
+{
+    sync();
+    CVX_Voxel* v = voxel(x, y, z);
+    return v ? v->links[d] : nullptr;
+}
+const std::vector<CVX_Collision*>* CVoxelyze::collisionList() const
+{
+    sync();
+    for (CVX_Collision* c : collisionsList) delete c;
+    collisionsList.clear();
+    int n = 0;
+    vx_collision_pairs(h, nullptr, 0, &n);
+    std::vector<int32_t> p(2 * (size_t)n);
+    if (n) vx_collision_pairs(h, p.data(), n, &n);
+    for (int k = 0; k < n; k++) collisionsList.push_back(new CVX_Collision(voxelsList[p[2 * k]], voxelsList[p[2 * k + 1]]));
+    return &collisionsList;
+}
+
+// CVoxelyze::stateInfo (src/Voxelyze.cpp:752-800): float accumulation in list order
+float CVoxelyze::stateInfo(stateInfoType info, valueType type)
+{
+    sync();
+    float ret = 0;
+    if (type == MAX) ret = -FLT_MAX; else if (type == MIN) ret = FLT_MAX;
+    auto acc = [&](float v) { switch (type) { case MIN: if (v < ret) ret = v; break; case MAX: if (v > ret) ret = v; break; default: ret += v; } };
+    if (info == STRAIN_ENERGY || info == ENG_STRESS || info == ENG_STRAIN) {
+        const int L = (int)linksList.size();
+        if (L == 0) return 0.0f;
+        if (info == STRAIN_ENERGY) { for (CVX_Link* l : linksList) acc(l->strainEnergy()); }
+        else {
+            std::vector<float> v(L);
+            vx_download(h, info == ENG_STRESS ? VX_F_STRESS : VX_F_STRAIN, 0, L, v.data());
+            for (float x : v) acc(x);
+        }
+        if (type == AVERAGE) ret /= L;
+    } else {
+        const int n = (int)voxelsList.size();
+        if (n == 0) return 0.0f;
+        fetchAll();
+        for (CVX_Voxel* v : voxelsList) {
+            float val = 0;
+            switch (info) {
+            case DISPLACEMENT: val = v->displacementMagnitude(); break;
+            case VELOCITY: val = v->velocityMagnitude(); break;
+            case KINETIC_ENERGY: val = v->kineticEnergy(); break;
+            case ANGULAR_DISPLACEMENT: val = v->angularDisplacementMagnitude(); break;
+            case ANGULAR_VELOCITY: val = v->angularVelocityMagnitude(); break;
+            case MASS: val = v->material()->mass(); break;
+            default: val = 0;
+            }
+            acc(val);
+        }
+        if (type == AVERAGE) ret /= n;
+    }
+    return ret;
+}
