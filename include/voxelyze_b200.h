@@ -258,8 +258,11 @@ int  vx_collision_pairs(vx_sim* s, int32_t* pairs, int cap, int* n_pairs);
 int  vx_state_info(vx_sim* s, int info, int type, float* out);
 
 /* ---- device side hooks (CUDA build only; oracles return VX_ERR_UNSUPPORTED) -- */
-/* run all work of this handle on the given cudaStream_t (as an integer); 0 = the
- * library's own stream.  Lets a caller order NCCL halo traffic with the step.        */
+/* run all work of this handle on the given cudaStream_t (passed as an integer; 0 is CUDA's
+ * legacy default stream and is used as such).  VX_OWN_STREAM selects the library's own
+ * non-blocking stream again (the initial state).  Lets a caller order NCCL halo traffic
+ * and event timing with the step.                                                     */
+#define VX_OWN_STREAM (~(uint64_t)0)
 int  vx_set_stream(vx_sim* s, uint64_t cuda_stream);
 /* z-slab halo exchange support: device address and element
  * range of the two packed pose record arrays (pose0: pos.xyz+orient.w, pose1:

@@ -345,8 +345,9 @@ class Sim:
         return v.value
 
     # -- device hooks ------------------------------------------------------------
-    def set_stream(self, stream: int):
-        self._chk(self.L.lib.vx_set_stream(self.h, stream))
+    def set_stream(self, stream):
+        """stream: a cudaStream_t as int (0 = CUDA's legacy default stream), or None for the library's own stream."""
+        self._chk(self.L.lib.vx_set_stream(self.h, 0xFFFFFFFFFFFFFFFF if stream is None else int(stream)))
 
     def pose_plane(self, iz: int):
         p0, p1, n, rb = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_int()

@@ -1251,7 +1251,7 @@ int vx_set_stream(vx_sim* s, uint64_t stream)
 {
     if (!s) return VX_ERR_ARG;
     cudaStreamSynchronize(s->stream);
-    s->stream = stream ? (cudaStream_t)(uintptr_t)stream : s->own_stream;
+    s->stream = stream == VX_OWN_STREAM ? s->own_stream : (cudaStream_t)(uintptr_t)stream;
     s->drop_graph();
     return VX_OK;
 }
