@@ -137,8 +137,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="kernel variant: 0 auto, 1 general, 2/3 fused lattice variants (ablation)")
     args = ap.parse_args()
-    # >= 16 so that the 16-step CUDA graph is captured and instantiated before the timed region
-    args.warmup = max(args.warmup, 16) if args.impl == "ours" else max(args.warmup, 1)
+    # >= 17 (one direct step + one 16-step graph) so that the CUDA graphs are captured and instantiated before the timed region
+    args.warmup = max(args.warmup, 20) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 

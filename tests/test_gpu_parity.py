@@ -242,3 +242,35 @@ def test_full_size_properties_256(product):
     assert np.max(np.abs(d[..., 1] + mirror[..., 1])) <= tol
     lm = s.download("linmom")
     assert abs(lm[:, 1].sum()) <= 1e-9 * np.abs(lm).sum()
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["lattice", "general"])
+def test_state_info_reductions(product, oracle, path):
+    """vx_state_info (device reductions) against the oracle's sequential float loops
+    (CVoxelyze::stateInfo, src/Voxelyze.cpp:752-800); summation order differs, tolerance 1e-6 relative."""
+    sc = scenarios.cantilever(10, 4, 3, tip_load=5.0)
+    g, dt, _ = parity.run(product, sc, 400, path=path)
+    o, _, _ = parity.run(oracle, sc, 400)
+    for info in (0, 1, 2, 3, 4, 5, 6, 7, 9):          # everything except PRESSURE
+        for typ in (0, 1, 2, 3):
+            a, b = g.state_info(info, typ), o.state_info(info, typ)
+            assert abs(a - b) <= 1e-6 * max(abs(b), 1e-30) + 1e-30, (info, typ, a, b)
+
+
+def test_collision_case_energy_and_centre_of_mass(product, oracle):
+    """BASELINE north_star: cases with collisions are judged on energy and centre-of-mass trajectory.
+    Plates case: kinetic energy within 1e-4 relative (or 1e-12 J absolute) and COM within 1e-9 m of the
+    oracle at several checkpoints; watched pair sets identical at each checkpoint."""
+    c = cases.BY_NAME["plates_16x4x2"]
+    sc = c.make()
+    g = scenarios.build(product, sc); o = scenarios.build(oracle, sc)
+    dt = g.recommended_dt()
+    assert dt == o.recommended_dt()
+    for _ in range(6):
+        g.step(dt, 500); o.step(dt, 500)
+        ke_g, ke_o = g.state_info(2, 2), o.state_info(2, 2)
+        assert abs(ke_g - ke_o) <= 1e-4 * abs(ke_o) + 1e-12, (ke_g, ke_o)
+        com_g, com_o = g.download("pos").mean(axis=0), o.download("pos").mean(axis=0)
+        assert np.max(np.abs(com_g - com_o)) <= 1e-9
+        assert np.array_equal(g.collision_pairs(), o.collision_pairs())
+        assert np.array_equal(g.download("linkflags") & 0xC, o.download("linkflags") & 0xC)

@@ -111,6 +111,9 @@ struct vx_sim {
     DevBuf<int2> c_pairs; DevBuf<float2> c_pair_kc; DevBuf<float4> c_pair_force;
     DevBuf<int> c_counters, c_deg, c_ref_start, c_ref_fill, c_refs;
     int* counters_host = nullptr;                                  // pinned, 4 ints
+    // stateInfo reductions
+    DevBuf<float> si_minmax; DevBuf<double> si_sum; DevBuf<double4> si_nominal; DevBuf<float> si_consts; DevBuf<unsigned char> si_buf;
+    bool si_nominal_ok = false, si_consts_ok = false;
 
     bool uni = false; DevVoxMat vm0{}; DevLinkMat lm0{};          // single-material model: rows passed by value
     cudaGraphExec_t graph = nullptr; int graph_kernels = 0;      // general mode
@@ -259,6 +262,7 @@ static int upload_tables(vx_sim* s)
     CK(cudaMemcpy(s->pair_lmat.p, pair.data(), pair.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     s->uni = vm.size() == 1 && lm.size() == 1 && lm[0].linear && !s->any_poisson;
     if (s->uni) { s->vm0 = vm[0]; s->lm0 = lm[0]; }
+    s->si_consts_ok = false;
     s->drop_graph();
     return VX_OK;
 }
@@ -551,9 +555,14 @@ static int ensure_graph(vx_sim* s)
     Frame f = s->frame();
     cudaGraph_t g = nullptr;
     int64_t before = s->launches;
-    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    // capture on the library's own stream (the caller's stream may be the legacy default stream,
+    // which cannot be captured); the instantiated graph is launched into the caller's stream
+    cudaStream_t user = s->stream; s->stream = s->own_stream;
+    cudaError_t e0 = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+    if (e0 != cudaSuccess) { s->stream = user; return cuda_fail(s, e0, "cudaStreamBeginCapture"); }
     for (int k = 0; k < GRAPH_STEPS; k++) launch_step(s, f, false);
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    s->stream = user;
     s->graph_kernels = (int)(s->launches - before);
     s->launches = before;
     if (e != cudaSuccess) return cuda_fail(s, e, "cudaStreamEndCapture");
@@ -596,9 +605,12 @@ static int ensure_lattice_graph(vx_sim* s, int g0)
     if (s->lgraph[g0]) return VX_OK;
     cudaGraph_t g = nullptr;
     int64_t before = s->launches;
-    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    cudaStream_t user = s->stream; s->stream = s->own_stream;       // see ensure_graph
+    cudaError_t e0 = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+    if (e0 != cudaSuccess) { s->stream = user; return cuda_fail(s, e0, "cudaStreamBeginCapture"); }
     for (int k = 0; k < GRAPH_STEPS; k++) launch_lattice(s, (g0 + k) & 1, 0);
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    s->stream = user;
     s->launches = before;
     if (e != cudaSuccess) return cuda_fail(s, e, "cudaStreamEndCapture");
     e = cudaGraphInstantiate(&s->lgraph[g0], g, 0);
@@ -651,7 +663,8 @@ static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     launch_lattice(s, g0, 1); done++;
     while (n_steps - done >= GRAPH_STEPS) {
         const int g = (g0 + done) & 1;
-        int rc = ensure_lattice_graph(s, g);
+        int rc = ensure_lattice_graph(s, g);                 // both generations at once: a later call may start on the other one
+        if (rc == VX_OK) rc = ensure_lattice_graph(s, g ^ 1);
         if (rc != VX_OK) return rc;
         CK(cudaGraphLaunch(s->lgraph[g], s->stream));
         s->launches += GRAPH_STEPS; done += GRAPH_STEPS;
@@ -698,6 +711,7 @@ void vx_destroy(vx_sim* s)
     s->c_last_watch.release(); s->c_head.release(); s->c_next.release(); s->c_cell.release(); s->c_pairs.release(); s->c_pair_kc.release();
     s->c_pair_force.release(); s->c_counters.release(); s->c_deg.release(); s->c_ref_start.release(); s->c_ref_fill.release(); s->c_refs.release();
     if (s->counters_host) cudaFreeHost(s->counters_host);
+    s->si_minmax.release(); s->si_sum.release(); s->si_nominal.release(); s->si_consts.release(); s->si_buf.release();
     s->ext_idx.release(); s->ext_vox_dev.release(); s->vox_e2i_dev.release(); s->link_e2i_dev.release(); s->member_dev.release();
     s->pstrain.release(); s->slots.release(); s->slot_strain.release();
     s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release(); s->lstrain.release();
@@ -858,6 +872,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     s->lattice = n > 0 && cells == (long long)n && !poisson && !s->collisions && s->path != 1;
     s->nx = (int)ext3[0]; s->ny = (int)ext3[1]; s->nz = (int)ext3[2];
     s->link_owner.release(); s->link_axis_dev.release();
+    s->si_nominal_ok = false; s->si_consts_ok = false;
 
     for (int i = 0; i < L; i++) {
         int id = link_material(s, s->vmat_id[s->lk_vn[i]], s->vmat_id[s->lk_vp[i]]);
@@ -1245,7 +1260,88 @@ int vx_collision_pairs(vx_sim* s, int32_t* pairs, int cap, int* n_pairs)
     for (int k = 0; k < P && k < cap; k++) { pairs[2 * k] = out[k].first; pairs[2 * k + 1] = out[k].second; }
     return VX_OK;
 }
-int vx_state_info(vx_sim* s, int, int, float*) { return fail(s, VX_ERR_UNSUPPORTED, "stateInfo is not built yet"); }
+// fills `dst` (device) with one link field for all links, caller order
+static int gather_link_field(vx_sim* s, int what, void* dst)
+{
+    if (s->lattice) {
+        int rc = ensure_link_refs(s);
+        if (rc != VX_OK) return rc;
+        LatLinkRef ref{s->link_owner.p, s->link_axis_dev.p};
+        k_lattice_gather_links<<<blocks_for(s->L), TPB, 0, s->stream>>>(s->lat_frame(s->gen), s->lat_frame(s->gen ^ 1), s->have_prev ? 1 : 0,
+                                                                        s->last_prev_dt, what, s->link_e2i_dev.p, ref, 0, s->L, dst);
+    } else {
+        k_gather<<<blocks_for(s->L), TPB, 0, s->stream>>>(s->frame(), what, s->link_e2i_dev.p, 0, s->L, dst, s->axis_first[1], s->axis_first[2]);
+    }
+    s->launches++;
+    return VX_OK;
+}
+
+int vx_state_info(vx_sim* s, int info, int type, float* out)
+{
+    if (!s || !out || info < 0 || info > SI_MASS || type < 0 || type > SI_AVERAGE) return VX_ERR_ARG;
+    *out = 0.0f;
+    const bool link_info = info == SI_STRAIN_ENERGY || info == SI_ENG_STRESS || info == SI_ENG_STRAIN;
+    const int count = link_info ? s->L : s->N;
+    if (count == 0) return VX_OK;                                  // src/Voxelyze.cpp:759,777
+    if (info == SI_PRESSURE) return fail(s, VX_ERR_UNSUPPORTED, "stateInfo(PRESSURE) is not available on the device yet");
+    CK(cudaSetDevice(s->device));
+    CK(s->si_minmax.alloc(2)); CK(s->si_sum.alloc(1));
+    const float init[2] = {3.402823466e38f, -3.402823466e38f};
+    CK(cudaMemcpyAsync(s->si_minmax.p, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemsetAsync(s->si_sum.p, 0, sizeof(double), s->stream));
+    const int grid = std::min(blocks_for(count, 256), 148 * 8);
+    if (!link_info) {
+        if (info == SI_DISPLACEMENT && !s->si_nominal_ok) {
+            std::vector<double4> nom(s->N);
+            for (int i = 0; i < s->N; i++) { int e = s->v_i2e[i]; nom[i] = make_double4(s->ijk[3 * e] * s->vox_size, s->ijk[3 * e + 1] * s->vox_size, s->ijk[3 * e + 2] * s->vox_size, 0.0); }
+            CK(s->si_nominal.alloc(s->N));
+            CK(cudaMemcpy(s->si_nominal.p, nom.data(), (size_t)s->N * sizeof(double4), cudaMemcpyHostToDevice));
+            s->si_nominal_ok = true;
+        }
+        k_state_voxels<<<grid, 256, 0, s->stream>>>(s->frame(), info, s->si_nominal.p, s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
+        s->launches++;
+    } else if (info != SI_STRAIN_ENERGY) {
+        CK(s->si_buf.alloc((size_t)s->L * sizeof(float)));
+        int rc = gather_link_field(s, info == SI_ENG_STRESS ? G_STRESS : G_STRAIN, s->si_buf.p);
+        if (rc != VX_OK) return rc;
+        k_state_links<<<grid, 256, 0, s->stream>>>(s->L, (const float*)s->si_buf.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                   s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
+        s->launches++;
+    } else {
+        if (!s->si_consts_ok) {                                    // a1, a2, b3 of every link's material (caller order)
+            std::vector<float> c(3 * (size_t)s->L);
+            for (int l = 0; l < s->L; l++) {
+                vxm::BeamConsts k = vxm::beam_consts(s->lmats[link_material(s, s->vmat_id[s->lk_vn[l]], s->vmat_id[s->lk_vp[l]])].mat, s->vox_size);
+                c[l] = k.a1; c[(size_t)s->L + l] = k.a2; c[2 * (size_t)s->L + l] = k.b3;
+            }
+            CK(s->si_consts.alloc(c.size()));
+            CK(cudaMemcpy(s->si_consts.p, c.data(), c.size() * sizeof(float), cudaMemcpyHostToDevice));
+            s->si_consts_ok = true;
+        }
+        const size_t stride = (size_t)s->L * 3 * sizeof(double);
+        CK(s->si_buf.alloc(3 * stride));
+        double* fneg = (double*)s->si_buf.p; double* mneg = (double*)(s->si_buf.p + stride); double* mpos = (double*)(s->si_buf.p + 2 * stride);
+        int rc = gather_link_field(s, G_FORCE_NEG, fneg);
+        if (rc == VX_OK) rc = gather_link_field(s, G_MOMENT_NEG, mneg);
+        if (rc == VX_OK) rc = gather_link_field(s, G_MOMENT_POS, mpos);
+        if (rc != VX_OK) return rc;
+        k_state_links<<<grid, 256, 0, s->stream>>>(s->L, nullptr, fneg, mneg, mpos, s->si_consts.p, s->si_consts.p + s->L, s->si_consts.p + 2 * (size_t)s->L,
+                                                   s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
+        s->launches++;
+    }
+    CK(cudaGetLastError());
+    float mm[2]; double sum;
+    CK(cudaMemcpyAsync(mm, s->si_minmax.p, sizeof(mm), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(&sum, s->si_sum.p, sizeof(sum), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    switch (type) {
+    case SI_MIN: *out = mm[0]; break;
+    case SI_MAX: *out = mm[1]; break;
+    case SI_TOTAL: *out = (float)sum; break;
+    default: *out = (float)sum / count; break;
+    }
+    return VX_OK;
+}
 
 int vx_set_stream(vx_sim* s, uint64_t stream)
 {

@@ -168,3 +168,76 @@ __global__ void k_col_narrow(Frame f, ColFrame c, int n_pairs)
 }
 
 } // namespace vxd
+
+// =================================================================================================
+// stateInfo reductions (CVoxelyze::stateInfo, src/Voxelyze.cpp:752-800): per-element float value
+// exactly as the reference computes it, reduced with warp shuffles + one atomic per block.
+// MIN/MAX use ordered-integer atomics on the float bit pattern, TOTAL accumulates in double
+// (the reference adds floats in list order; the difference is below 1e-6 relative).
+// =================================================================================================
+namespace vxd {
+
+enum { SI_DISPLACEMENT, SI_VELOCITY, SI_KINETIC_ENERGY, SI_ANGULAR_DISPLACEMENT, SI_ANGULAR_VELOCITY,
+       SI_ENG_STRESS, SI_ENG_STRAIN, SI_STRAIN_ENERGY, SI_PRESSURE, SI_MASS };
+enum { SI_MIN, SI_MAX, SI_TOTAL, SI_AVERAGE };
+
+struct StateAcc { float mn, mx; double sum; };
+
+__device__ __forceinline__ void si_block_reduce(StateAcc a, float* out_min, float* out_max, double* out_sum)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        a.mn = fminf(a.mn, __shfl_xor_sync(0xffffffffu, a.mn, o));
+        a.mx = fmaxf(a.mx, __shfl_xor_sync(0xffffffffu, a.mx, o));
+        a.sum += __shfl_xor_sync(0xffffffffu, a.sum, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // float atomic min/max through the monotone int mapping of IEEE floats
+        int imn = __float_as_int(a.mn), imx = __float_as_int(a.mx);
+        if (imn >= 0) atomicMin((int*)out_min, imn); else atomicMax((unsigned int*)out_min, (unsigned int)imn);
+        if (imx >= 0) atomicMax((int*)out_max, imx); else atomicMin((unsigned int*)out_max, (unsigned int)imx);
+        atomicAdd(out_sum, a.sum);
+    }
+}
+
+// voxel quantities; ijk_size = nominal position source: displacement needs the lattice index, passed as a
+// per-voxel nominal position array only when info == DISPLACEMENT
+__global__ void __launch_bounds__(256) k_state_voxels(Frame f, int info, const double4* nominal, float* out_min, float* out_max, double* out_sum)
+{
+    StateAcc a; a.mn = 3.402823466e38f; a.mx = -3.402823466e38f; a.sum = 0.0;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < f.n_vox; v += gridDim.x * blockDim.x) {
+        const double4 p0 = f.pose0[v], p1 = f.pose1[v];
+        const DevVoxMat& m = f.vmat[meta_hi(p1.w) & VM_MAT_MASK];
+        float val = 0.0f;
+        if (info == SI_DISPLACEMENT) { double4 n = nominal[v]; double dx = p0.x - n.x, dy = p0.y - n.y, dz = p0.z - n.z; val = (float)sqrt(dx * dx + dy * dy + dz * dz); }
+        else if (info == SI_VELOCITY) { double4 l = f.mom0[v]; val = (float)(sqrt(l.x * l.x + l.y * l.y + l.z * l.z) * m.mass_inv); }
+        else if (info == SI_ANGULAR_VELOCITY) { double4 l = f.mom0[v]; double2 l1 = f.mom1[v]; val = (float)(sqrt(l.w * l.w + l1.x * l1.x + l1.y * l1.y) * m.inertia_inv); }
+        else if (info == SI_KINETIC_ENERGY) {
+            double4 l = f.mom0[v]; double2 l1 = f.mom1[v];
+            val = (float)(0.5 * (m.mass_inv * (l.x * l.x + l.y * l.y + l.z * l.z) + m.inertia_inv * (l.w * l.w + l1.x * l1.x + l1.y * l1.y)));
+        }
+        else if (info == SI_ANGULAR_DISPLACEMENT) { double w = p0.w; val = (float)(2.0 * acos(w > 1 ? 1.0 : w)); }
+        else if (info == SI_MASS) val = m.mass;
+        a.mn = fminf(a.mn, val); a.mx = fmaxf(a.mx, val); a.sum += (double)val;
+    }
+    si_block_reduce(a, out_min, out_max, out_sum);
+}
+
+// link quantities from a flat value array produced by the gather kernels (strain / stress) or from
+// force+moment triples (strain energy, src/VX_Link.cpp:251-257)
+__global__ void __launch_bounds__(256) k_state_links(int n, const float* scalar, const double* fneg, const double* mneg, const double* mpos,
+                                                     const float* a1, const float* a2, const float* b3, float* out_min, float* out_max, double* out_sum)
+{
+    StateAcc a; a.mn = 3.402823466e38f; a.mx = -3.402823466e38f; a.sum = 0.0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
+        float val;
+        if (scalar) val = scalar[l];
+        else {
+            const double fx = fneg[3 * l], nx = mneg[3 * l], ny = mneg[3 * l + 1], nz = mneg[3 * l + 2], py = mpos[3 * l + 1], pz = mpos[3 * l + 2];
+            val = fx * fx / (2.0f * a1[l]) + nx * nx / (2.0 * a2[l]) + (nz * nz - nz * pz + pz * pz) / (3.0 * b3[l]) + (ny * ny - ny * py + py * py) / (3.0 * b3[l]);
+        }
+        a.mn = fminf(a.mn, val); a.mx = fmaxf(a.mx, val); a.sum += (double)val;
+    }
+    si_block_reduce(a, out_min, out_max, out_sum);
+}
+
+} // namespace vxd

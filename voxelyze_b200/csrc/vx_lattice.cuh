@@ -430,15 +430,24 @@ k_lattice_march(LatFrame f, int parity, int first_of_call, int floor_on, int n_s
 // => 3.6 link evaluations per voxel instead of 6, forces never leave the SM, and both phases keep
 //    the simple, wide thread shape that runs at DRAM speed in the general path.
 // =================================================================================================
+#ifndef VX_TILE_X
 #define VX_TILE_X 8
+#endif
+#ifndef VX_TILE_Y
 #define VX_TILE_Y 4
+#endif
+#ifndef VX_TILE_Z
 #define VX_TILE_Z 4
+#endif
 #define VX_TILE_VOX (VX_TILE_X * VX_TILE_Y * VX_TILE_Z)                       // 128
 #define VX_TILE_EX ((VX_TILE_X + 1) * VX_TILE_Y * VX_TILE_Z)                  // 144 x-links
 #define VX_TILE_EY (VX_TILE_X * (VX_TILE_Y + 1) * VX_TILE_Z)                  // 160 y-links
 #define VX_TILE_EZ (VX_TILE_X * VX_TILE_Y * (VX_TILE_Z + 1))                  // 160 z-links
 #define VX_TILE_EVALS (VX_TILE_EX + VX_TILE_EY + VX_TILE_EZ)                  // 464
+#ifndef VX_TILE_THREADS
 #define VX_TILE_THREADS 256
+#endif
+#define VX_TILE_ROUNDS ((VX_TILE_EVALS + VX_TILE_THREADS - 1) / VX_TILE_THREADS)
 #ifndef VX_TILE_MINBLOCKS
 #define VX_TILE_MINBLOCKS 2
 #endif
@@ -504,10 +513,10 @@ k_lattice_tile(LatFrame f, int parity, int first_of_call, int floor_on, int ntx,
         }
     }
     // link records of this thread's (up to two) evaluations: issue the loads before the barrier
-    TileEval ev[2];
-    double2 ra[2], rb[2], rc[2]; float4 rs[2];
+    TileEval ev[VX_TILE_ROUNDS];
+    double2 ra[VX_TILE_ROUNDS], rb[VX_TILE_ROUNDS], rc[VX_TILE_ROUNDS]; float4 rs[VX_TILE_ROUNDS];
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
+    for (int r = 0; r < VX_TILE_ROUNDS; r++) {
         ev[r] = tile_decode(f, threadIdx.x + r * VX_TILE_THREADS, tx0, ty0, tz0, vbase);
         if (ev[r].ok) {
             ra[r] = __ldg(f.c_rec[ev[r].axis][0] + ev[r].vn); rb[r] = __ldg(f.c_rec[ev[r].axis][1] + ev[r].vn);
@@ -518,7 +527,7 @@ k_lattice_tile(LatFrame f, int parity, int first_of_call, int floor_on, int ntx,
 
     // ---- phase 1: one thread per link evaluation
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
+    for (int r = 0; r < VX_TILE_ROUNDS; r++) {
         if (!ev[r].ok) continue;
         const int axis = ev[r].axis, lx = ev[r].lx, ly = ev[r].ly, lz = ev[r].lz, vn = ev[r].vn;
         const int cn = ((lz + 1) * VX_TILE_HY + (ly + 1)) * VX_TILE_HX + (lx + 1);

@@ -603,41 +603,12 @@ const std::vector<CVX_Collision*>* CVoxelyze::collisionList() const
     return &collisionsList;
 }
 
-// CVoxelyze::stateInfo (src/Voxelyze.cpp:752-800): float accumulation in list order
+// CVoxelyze::stateInfo (src/Voxelyze.cpp:752-800): min / max / sum reductions run on the device
 float CVoxelyze::stateInfo(stateInfoType info, valueType type)
 {
     sync();
-    float ret = 0;
-    if (type == MAX) ret = -FLT_MAX; else if (type == MIN) ret = FLT_MAX;
-    auto acc = [&](float v) { switch (type) { case MIN: if (v < ret) ret = v; break; case MAX: if (v > ret) ret = v; break; default: ret += v; } };
-    if (info == STRAIN_ENERGY || info == ENG_STRESS || info == ENG_STRAIN) {
-        const int L = (int)linksList.size();
-        if (L == 0) return 0.0f;
-        if (info == STRAIN_ENERGY) { for (CVX_Link* l : linksList) acc(l->strainEnergy()); }
-        else {
-            std::vector<float> v(L);
-            vx_download(h, info == ENG_STRESS ? VX_F_STRESS : VX_F_STRAIN, 0, L, v.data());
-            for (float x : v) acc(x);
-        }
-        if (type == AVERAGE) ret /= L;
-    } else {
-        const int n = (int)voxelsList.size();
-        if (n == 0) return 0.0f;
-        fetchAll();
-        for (CVX_Voxel* v : voxelsList) {
-            float val = 0;
-            switch (info) {
-            case DISPLACEMENT: val = v->displacementMagnitude(); break;
-            case VELOCITY: val = v->velocityMagnitude(); break;
-            case KINETIC_ENERGY: val = v->kineticEnergy(); break;
-            case ANGULAR_DISPLACEMENT: val = v->angularDisplacementMagnitude(); break;
-            case ANGULAR_VELOCITY: val = v->angularVelocityMagnitude(); break;
-            case MASS: val = v->material()->mass(); break;
-            default: val = 0;
-            }
-            acc(val);
-        }
-        if (type == AVERAGE) ret /= n;
-    }
-    return ret;
+    float v = 0.0f;
+    int rc = vx_state_info(h, (int)info, (int)type, &v);
+    if (rc != VX_OK && rc != VX_ERR_UNSUPPORTED) die("vx_state_info");
+    return v;
 }
