@@ -39,6 +39,19 @@ def measured_hbm_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
+def ncu_traffic(kernel: str, voxels: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json); None when no capture matches this kernel and size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            for row in json.load(f):
+                if kernel.startswith(row["kernel"]) and row["voxels"] == voxels:
+                    return row["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -135,7 +148,7 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="override lattice edge (testing only; reported in config)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="edge of the CPU baseline sample lattice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--path", type=int, default=0, help="kernel variant: 0 auto, 1 general, 2/3 fused lattice variants (ablation)")
+    ap.add_argument("--path", type=int, default=0, help="kernel variant (vx_set_path): 0 auto, 1 general, 2..5 fused lattice variants (ablation)")
     args = ap.parse_args()
     # >= 17 (one direct step + one 16-step graph) so that the CUDA graphs are captured and instantiated before the timed region
     args.warmup = max(args.warmup, 20) if args.impl == "ours" else max(args.warmup, 1)
@@ -201,10 +214,14 @@ def main():
     own_vox, own_link = runner.local_counts()
     peak, peak_src = measured_hbm_peak()
     link_ms = kms["link"] / prof_steps
-    achieved = (B_LINK * own_link) / (link_ms * 1e-3) / 1e9 if link_ms > 0 else 0.0
+    fused = kl[1] == 0                  # lattice path: the one kernel does the link AND the voxel updates
+    launch_bytes = (B_LINK * own_link + (B_VOXEL * own_vox if fused else 0)) / max(kl[0] // prof_steps, 1)
+    launch_ms = link_ms / max(kl[0] // prof_steps, 1)
+    achieved = launch_bytes / (launch_ms * 1e-3) / 1e9 if link_ms > 0 else 0.0
     step_gbs = (B_VOXEL * n_vox + B_LINK * n_link) * args.steps / (ms * 1e-3) / 1e9 / world
     roofline = {"bound": "hbm", "kernel": runner.dominant_kernel(), "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(runner.dominant_kernel(), own_vox),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": launch_bytes, "launch_ms": launch_ms,
                 "launches_per_step": kl[0] // prof_steps,
                 "kernel_ms_per_step": {k: v / prof_steps for k, v in kms.items()},
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,

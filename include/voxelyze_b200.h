@@ -285,11 +285,18 @@ int  vx_sync(vx_sim* s);
  * else (Poisson pre-pass, collisions), ms[3] whole steps; launches[0..2] = kernel launches
  * per group.  Same arithmetic as vx_step.                                                 */
 int  vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches);
-/* select kernel variant: 0 = auto, 1 = general two-kernel path, 2 = fused lattice
- * path (dense boxes).  For tests and ablations.                                       */
+/* select kernel variant (tests and ablations; takes effect at the next vx_set_voxels):
+ *   0 auto: fused lattice kernel for dense boxes without Poisson coupling or collisions,
+ *           general path otherwise
+ *   1 general two-kernel path (k_link<AXIS> x3 + k_voxel), any topology
+ *   fused lattice variants, all bit-identical to path 1:
+ *   2 block bricks 8x4x4 (k_lattice_tile)     3 one thread per voxel (k_lattice_step)
+ *   4 z-marching columns (k_lattice_march)    5 warp bricks 4x4x2 (k_lattice_warp) = what 0 picks */
 int  vx_set_path(vx_sim* s, int path);
-/* which variant the handle runs: 1 general, 2 fused lattice (decided by vx_set_voxels)  */
+/* which layout the handle runs: 1 general, 2 fused lattice (decided by vx_set_voxels)  */
 int  vx_active_path(const vx_sim* s);
+/* name of the kernel that dominates a step of this handle (static string, for reports)  */
+const char* vx_kernel_name(const vx_sim* s);
 
 #ifdef __cplusplus
 }

@@ -407,6 +407,7 @@ int64_t vx_launch_count(const vx_sim*) { return 0; }
 int vx_sync(vx_sim*) { return VX_OK; }
 int vx_set_path(vx_sim*, int) { return VX_OK; }
 int vx_active_path(const vx_sim*) { return 0; }
+const char* vx_kernel_name(const vx_sim*) { return "cpu (reference CVoxelyze::doTimeStep)"; }
 int vx_step_profile(vx_sim*, float, int, float*, int*) { return VX_ERR_UNSUPPORTED; }
 
 } // extern "C"

@@ -93,17 +93,17 @@ def test_fused_and_general_paths_agree_bitwise(product):
     """Same physics functions, same summation order: the two device layouts give identical bits."""
     sc = scenarios.cantilever(12, 5, 4, tip_load=30.0)
     snaps = {}
-    for path in (0, 1, 3, 4):      # brick kernel (default), general two-kernel, per-voxel fused, z-marching fused
+    for path in (0, 1, 2, 3, 4, 5):   # auto (= warp bricks), general two-kernel, block bricks, per-voxel fused, z-marching fused, warp bricks
         sim, dt, _ = parity.run(product, sc, 700, path=path)
         snaps[path] = parity.snapshot(sim)
-    for path in (1, 3, 4):
+    for path in (1, 2, 3, 4, 5):
         for f in snaps[0]:
             assert parity.bit_equal(snaps[0][f], snaps[path][f]), (path, f)
 
 
-@pytest.mark.parametrize("path", [0, 3, 4], ids=["brick", "pervoxel", "march"])
+@pytest.mark.parametrize("path", [0, 2, 3, 4], ids=["warpbrick", "blockbrick", "pervoxel", "march"])
 def test_fused_kernels_odd_sizes(product, oracle, path):
-    """Lattice edges that are not multiples of the brick (8x4x4), the warp segment (31), the CTA
+    """Lattice edges that are not multiples of the bricks (4x4x2, 8x4x4), the warp segment (31), the CTA
     rows (4) or the z-chunk (32): partial bricks / segments / row groups, several z-chunks."""
     sc = scenarios.cantilever(33, 6, 35, tip_load=200.0)
     g, dt, _ = parity.run(product, sc, 40, path=path)

@@ -160,6 +160,7 @@ class VxLib:
             "vx_sync": (i32, [vp]),
             "vx_set_path": (i32, [vp, i32]),
             "vx_active_path": (i32, [vp]),
+            "vx_kernel_name": (C.c_char_p, [vp]),
             "vx_step_profile": (i32, [vp, f32, i32, P(f32), P(i32)]),
         }
         self.symbols = list(sig)
@@ -372,6 +373,9 @@ class Sim:
 
     def active_path(self) -> int:
         return self.L.lib.vx_active_path(self.h)
+
+    def kernel_name(self) -> str:
+        return self.L.lib.vx_kernel_name(self.h).decode()
 
     def set_path(self, path: int):
         self._chk(self.L.lib.vx_set_path(self.h, path))

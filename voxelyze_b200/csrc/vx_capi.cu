@@ -76,7 +76,7 @@ struct vx_sim {
     float grav = 0.f, ambient = 0.f, envelope = 0.625f;
     bool floor_on = false, collisions = false;
     float time_host = 0.f;
-    int path = 0;                       // vx_set_path: 0 auto, 1 general, 2 lattice
+    int path = 0;                       // vx_set_path: 0 auto, 1 general, 2..5 fused lattice variants
     bool relayout = false;
 
     // ---- lattice mode
@@ -579,7 +579,19 @@ static void launch_lattice(vx_sim* s, int g, int first_of_call)
     if (s->path == 3) {                  // ablation: one thread per voxel, all six links re-evaluated
         if (s->uni) k_lattice_step<true><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
         else k_lattice_step<false><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
-    } else if (s->path != 4) {           // default: 8x4x4 bricks, thread per link evaluation + shared-memory slots
+    } else if (s->path != 2 && s->path != 4) {   // default: one warp per 4x4x2 brick, no block barriers
+        const int nbx = (s->nx + 2 * VX_WB_X - 1) / (2 * VX_WB_X), nby = (s->ny + 2 * VX_WB_Y - 1) / (2 * VX_WB_Y), nbz = (s->nz + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z);
+        const long long bricks = (long long)nbx * nby * nbz * 8 * s->n_members;      // 2x2x2 groups of 4x4x2 bricks
+        const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
+        static bool wb_opted_in = false;
+        if (!wb_opted_in) {
+            cudaFuncSetAttribute(k_lattice_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+            cudaFuncSetAttribute(k_lattice_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+            wb_opted_in = true;
+        }
+        if (s->uni) k_lattice_warp<true><<<(unsigned)grid, 32 * VX_WB_WARPS, VX_WB_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, nbx, nby, nbz);
+        else k_lattice_warp<false><<<(unsigned)grid, 32 * VX_WB_WARPS, VX_WB_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, nbx, nby, nbz);
+    } else if (s->path == 2) {           // 8x4x4 bricks per block, thread per link evaluation + shared-memory slots
         const int ntx = (s->nx + VX_TILE_X - 1) / VX_TILE_X, nty = (s->ny + VX_TILE_Y - 1) / VX_TILE_Y, ntz = (s->nz + VX_TILE_Z - 1) / VX_TILE_Z;
         const long long grid = (long long)ntx * nty * ntz * s->n_members;
         static bool opted_in = false;    // > 48 KB of dynamic shared memory needs a one-time opt-in per function
@@ -1398,5 +1410,15 @@ int vx_sync(vx_sim* s) { if (!s) return VX_ERR_ARG; CK(cudaSetDevice(s->device))
 /* takes effect at the next vx_set_voxels */
 int vx_set_path(vx_sim* s, int path) { if (!s) return VX_ERR_ARG; s->path = path; return VX_OK; }
 int vx_active_path(const vx_sim* s) { return s && s->lattice ? 2 : 1; }
+const char* vx_kernel_name(const vx_sim* s)
+{
+    if (!s || !s->lattice) return "k_link<AXIS> (3 launches per step, one per link axis)";
+    switch (s->path) {
+    case 2: return "k_lattice_tile (fused link+voxel, 8x4x4 brick per block, 1 launch per step)";
+    case 3: return "k_lattice_step (fused link+voxel, one thread per voxel, 1 launch per step)";
+    case 4: return "k_lattice_march (fused link+voxel, z-marching columns, 1 launch per step)";
+    default: return "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, 1 launch per step)";
+    }
+}
 
 } // extern "C"

@@ -66,16 +66,15 @@ __device__ __forceinline__ void lat_encode(const LinkState& st, double2& a, doub
 // evaluates link (owner, axis) between negative-end voxel N and positive-end voxel P from the
 // current generation; returns forces on both ends and the advanced link state
 template <bool UNI>
-__device__ __forceinline__ void lat_eval_link(const LatFrame& f, int axis, int owner, uint32_t owner_bits,
-                                              double4 n0, double4 n1, double4 p0, double4 p1, float prev_dt,
-                                              LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP)
+__device__ __forceinline__ void lat_eval_link_rec(const LatFrame& f, int axis, uint32_t owner_bits,
+                                                  double2 ra, double2 rb, double2 rc, float4 rs,
+                                                  double4 n0, double4 n1, double4 p0, double4 p1, float prev_dt,
+                                                  LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP)
 {
     const uint32_t hn = meta_hi(n1.w), hp = meta_hi(p1.w);
     const DevVoxMat& vmn = UNI ? f.vm0 : f.vmat[hn & VM_MAT_MASK];
     const DevVoxMat& vmp = UNI ? f.vm0 : f.vmat[hp & VM_MAT_MASK];
     const DevLinkMat& lm = UNI ? f.lm0 : f.lmat[f.pair_lmat[(hn & VM_MAT_MASK) * f.n_mat + (hp & VM_MAT_MASK)]];
-    double2 ra = __ldg(f.c_rec[axis][0] + owner), rb = __ldg(f.c_rec[axis][1] + owner), rc = __ldg(f.c_rec[axis][2] + owner);
-    float4 rs = __ldg(f.c_recf[axis] + owner);
     lat_decode(ra, rb, rc, rs, (owner_bits >> (VM_LFLAG_SHIFT + 2 * axis)) & 3u, st);
     // CVX_Link::updateRestLength (src/VX_Link.cpp:137-140)
     double rest = 0.5 * (vmn.size[axis] * (1 + meta_temp(n1.w) * vmn.cte) + vmp.size[axis] * (1 + meta_temp(p1.w) * vmp.cte));
@@ -86,6 +85,15 @@ __device__ __forceinline__ void lat_eval_link(const LatFrame& f, int axis, int o
     op.w = p0.w; op.x = p1.x; op.y = p1.y; op.z = p1.z;
     link_forces(axis, mk3(n0.x, n0.y, n0.z), on, mk3(p0.x, p0.y, p0.z), op, rest, t_area, 0.0f,
                 damp_n, damp_p, lm, f.curve_e, f.curve_s, st, fN, mN, fP, mP);
+}
+template <bool UNI>
+__device__ __forceinline__ void lat_eval_link(const LatFrame& f, int axis, int owner, uint32_t owner_bits,
+                                              double4 n0, double4 n1, double4 p0, double4 p1, float prev_dt,
+                                              LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP)
+{
+    double2 ra = __ldg(f.c_rec[axis][0] + owner), rb = __ldg(f.c_rec[axis][1] + owner), rc = __ldg(f.c_rec[axis][2] + owner);
+    float4 rs = __ldg(f.c_recf[axis] + owner);
+    lat_eval_link_rec<UNI>(f, axis, owner_bits, ra, rb, rc, rs, n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
 }
 
 // dt lives in device memory (p->dt) so that captured graphs survive a change of time step.
@@ -605,6 +613,235 @@ k_lattice_tile(LatFrame f, int parity, int first_of_call, int floor_on, int ntx,
     vs.orient.w = s0.w; vs.orient.x = s1.x; vs.orient.y = s1.y; vs.orient.z = s1.z;
     vs.lin = mk3(m0.x, m0.y, m0.z);
     vs.ang = mk3(m0.w, m1.x, m1.y);
+    if (!(vs.bits & VM_GHOST)) {
+        const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
+        const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
+        voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext, dt, floor_on != 0);
+    }
+    f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
+    f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
+    f.n_mom0[v] = make_double4(vs.lin.x, vs.lin.y, vs.lin.z, vs.ang.x);
+    f.n_mom1[v] = make_double2(vs.ang.y, vs.ang.z);
+}
+
+
+// =================================================================================================
+// k_lattice_warp -- fused step, one WARP per 4 x 4 x 2 brick (32 voxels = 32 lanes).
+//
+// No block-wide barrier, no idle phase, no dependent global load in the arithmetic: each warp first
+// requests everything it will read (link records, the poses just outside the brick, later the
+// momenta) with cp.async into its private shared-memory window, then runs four rounds of 32 link
+// evaluations and one round of 32 voxel integrations out of shared memory and registers.
+//   round H      the 32 links that ENTER the brick through its three negative faces (8 through -X,
+//                8 through -Y, 16 through -Z), evaluated from the positive end; the force on the
+//                in-brick voxel is parked in shared memory (hslot)
+//   rounds 0..2  lane = voxel, evaluates its own +X / +Y / +Z link (owner: stores the new record).
+//                The force on the partner goes to the lane that holds it by warp shuffle, so the six contributions of a voxel
+//                are accumulated in registers in the reference's order X+ X- Y+ Y- Z+ Z-.
+//   last         lane = voxel: integrate, store
+// 4.0 link evaluations per voxel (3 + 32/32), all 32 lanes busy in every round of a full brick.
+// Shared memory per warp: two record windows 2x4x32x16 B + 72 poses (32 of the brick, 40 just
+// outside it) x 64 B + hslot 6x32x8 B = 10 240 B; requests run one round ahead of their use; the round-H windows are re-used for round 2 and the round-0 window for the momenta.
+// Link existence is geometric here (the lattice path is only chosen for full boxes), which lets
+// the requests go out before the first byte of voxel state has arrived.
+// =================================================================================================
+#define VX_WB_X 4
+#define VX_WB_Y 4
+#define VX_WB_Z 2
+#ifndef VX_WB_WARPS
+#define VX_WB_WARPS 8                                   // bricks per CTA (consecutive brick ids; ids walk 2x2x2 groups of bricks)
+#endif
+#define VX_WB_POSES 72
+#define VX_WB_WARP_BYTES (2 * 4 * 32 * 16 + 4 * VX_WB_POSES * 16 + 6 * 32 * 8)
+#define VX_WB_SMEM (VX_WB_WARPS * VX_WB_WARP_BYTES)
+#ifndef VX_WB_MINBLOCKS
+#define VX_WB_MINBLOCKS 2
+#endif
+
+__device__ __forceinline__ double4 shfl_d4(double4 v, int src)
+{
+    return make_double4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
+                        __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool UNI>
+__global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
+k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz)
+{
+    extern __shared__ __align__(16) unsigned char wb_smem[];
+    DevParams* p = f.params;
+    const int frozen = p->div_flag[parity ^ 1] | p->div_latched;
+    const float dt = p->dt;
+    const float prev_dt = first_of_call ? p->prev_dt : dt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (frozen) p->div_latched = 1;
+        else if (p->pending) { p->steps_done += 1; p->time += dt; }
+        if (!frozen) p->pending = 1;
+    }
+    if (frozen) return;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = wb_smem + (size_t)warp * VX_WB_WARP_BYTES;
+    uint4 (*rec_sh)[4][32] = reinterpret_cast<uint4 (*)[4][32]>(wbase);                       // [window][part][lane]: 0 = H, round 1, momenta; 1 = round 0, round 2
+    uint4 (*pose_sh)[VX_WB_POSES] = reinterpret_cast<uint4 (*)[VX_WB_POSES]>(wbase + 2 * 4 * 32 * 16);   // [part][entry]: 0..31 brick, 32..63 H then round 2 (32..47) and round 1 (48..55), 64..71 round 0
+    double (*hslot)[32] = reinterpret_cast<double (*)[32]>(wbase + 2 * 4 * 32 * 16 + 4 * VX_WB_POSES * 16);   // [comp][entering link]
+
+    // warp -> brick: consecutive ids walk a 2x2x2 group of bricks, groups x-fastest
+    int b = blockIdx.x * VX_WB_WARPS + warp;
+    const int w8 = b & 7; b >>= 3;
+    const int gx = b % nbx; b /= nbx;
+    const int gy = b % nby; b /= nby;
+    const int gz = b % nbz; const int member = b / nbz;
+    const int x0 = (gx * 2 + (w8 & 1)) * VX_WB_X, y0 = (gy * 2 + ((w8 >> 1) & 1)) * VX_WB_Y, z0 = (gz * 2 + (w8 >> 2)) * VX_WB_Z;
+    if (member * f.nz * f.nxy >= f.n_vox || x0 >= f.nx || y0 >= f.ny || z0 >= f.nz) return;            // whole warp
+    const int vbase = member * f.nz * f.nxy;
+
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
+    const bool has_voxel = x < f.nx && y < f.ny && z < f.nz;
+    const int v = vbase + (min(z, f.nz - 1) * f.ny + min(y, f.ny - 1)) * f.nx + min(x, f.nx - 1);   // clamped: idle lanes load valid memory
+
+    // ---- entering link of this lane (round H): axis, in-brick target lane, negative-end voxel
+    int h_axis, h_tl;
+    if (lane < 8) { h_axis = 0; h_tl = ((lane >> 2) << 4) | ((lane & 3) << 2); }              // target lx = 0: (ly, lz) = (lane&3, lane>>2)
+    else if (lane < 16) { h_axis = 1; h_tl = (((lane - 8) >> 2) << 4) | ((lane - 8) & 3); }  // target ly = 0: (lx, lz)
+    else { h_axis = 2; h_tl = lane - 16; }                                                    // target lz = 0: (lx, ly)
+    const int h_tx = x0 + (h_tl & 3), h_ty = y0 + ((h_tl >> 2) & 3), h_tz = z0 + (h_tl >> 4);
+    const int h_stride = h_axis == 0 ? 1 : (h_axis == 1 ? f.nx : f.nxy);
+    const bool h_geo = h_tx < f.nx && h_ty < f.ny && h_tz < f.nz && (h_axis == 0 ? x0 : (h_axis == 1 ? y0 : z0)) > 0;
+    const int h_vn = vbase + (h_tz * f.ny + h_ty) * f.nx + h_tx - h_stride;
+
+    // ---- requests, one round ahead.  cp.async groups in issue order: H (+ the brick's own poses), round 0,
+    //      [after H] round 1 and the round-2 poses, [after round 0] round 2, [after round 1] momenta
+    auto request_pose = [&](int entry, int vox) {
+        cp_async16(&pose_sh[0][entry], reinterpret_cast<const uint4*>(f.c_pose0 + vox));
+        cp_async16(&pose_sh[1][entry], reinterpret_cast<const uint4*>(f.c_pose0 + vox) + 1);
+        cp_async16(&pose_sh[2][entry], reinterpret_cast<const uint4*>(f.c_pose1 + vox));
+        cp_async16(&pose_sh[3][entry], reinterpret_cast<const uint4*>(f.c_pose1 + vox) + 1);
+    };
+    auto load_pose = [&](int entry, double4& a, double4& c) {
+        const uint4 e0 = pose_sh[0][entry], e1 = pose_sh[1][entry], e2 = pose_sh[2][entry], e3 = pose_sh[3][entry];
+        a = make_double4(__hiloint2double(e0.y, e0.x), __hiloint2double(e0.w, e0.z), __hiloint2double(e1.y, e1.x), __hiloint2double(e1.w, e1.z));
+        c = make_double4(__hiloint2double(e2.y, e2.x), __hiloint2double(e2.w, e2.z), __hiloint2double(e3.y, e3.x), __hiloint2double(e3.w, e3.z));
+    };
+    auto ext_entry = [&](int a) { return a == 0 ? 64 + ly + 4 * lz : (a == 1 ? 48 + lx + 4 * lz : 32 + lx + 4 * ly); };
+    auto request_link = [&](int a, bool records, bool poses) {
+        const int coord = a == 0 ? x : (a == 1 ? y : z), nn = a == 0 ? f.nx : (a == 1 ? f.ny : f.nz);
+        const bool inside = a == 0 ? lx < VX_WB_X - 1 : (a == 1 ? ly < VX_WB_Y - 1 : lz < VX_WB_Z - 1);
+        if (has_voxel && coord + 1 < nn) {
+            if (records) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) cp_async16(&rec_sh[(a & 1) ^ 1][k][lane], f.c_rec[a][k] + v);
+                cp_async16(&rec_sh[(a & 1) ^ 1][3][lane], f.c_recf[a] + v);
+            }
+            if (poses && !inside) request_pose(ext_entry(a), v + (a == 0 ? 1 : (a == 1 ? f.nx : f.nxy)));
+        }
+    };
+    request_pose(lane, v);
+    if (h_geo) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) cp_async16(&rec_sh[0][k][lane], f.c_rec[h_axis][k] + h_vn);
+        cp_async16(&rec_sh[0][3][lane], f.c_recf[h_axis] + h_vn);
+        request_pose(32 + lane, h_vn);
+    }
+    cp_async_commit();
+    request_link(0, true, true);
+    cp_async_commit();
+
+    // ---- round H
+    cp_async_wait<1>();
+    __syncwarp();                     // the brick's poses were requested by other lanes
+    const uint32_t bits = pose_sh[3][lane].w;                      // high word of pose1.w: the meta word
+    const uint32_t mask = has_voxel ? ((bits >> VM_LINK_SHIFT) & 0x3Fu) : 0u;
+    uint32_t new_bits = bits;
+    if (h_geo && ((pose_sh[3][h_tl].w >> (VM_LINK_SHIFT + 2 * h_axis + 1)) & 1u)) {
+        double4 n0, n1, p0, p1;
+        load_pose(32 + lane, n0, n1);
+        load_pose(h_tl, p0, p1);
+        const uint4 r0 = rec_sh[0][0][lane], r1 = rec_sh[0][1][lane], r2 = rec_sh[0][2][lane], r3 = rec_sh[0][3][lane];
+        LinkState st; d3 fN, mN, fP, mP;
+        lat_eval_link_rec<UNI>(f, h_axis, meta_hi(n1.w),
+                               make_double2(__hiloint2double(r0.y, r0.x), __hiloint2double(r0.w, r0.z)),
+                               make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
+                               make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
+                               make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
+                               n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
+        hslot[0][lane] = fP.x; hslot[1][lane] = fP.y; hslot[2][lane] = fP.z; hslot[3][lane] = mP.x; hslot[4][lane] = mP.y; hslot[5][lane] = mP.z;
+    }
+    __syncwarp();
+    request_link(1, true, true);      // into the windows round H has left
+    request_link(2, false, true);
+    cp_async_commit();
+
+    // ---- rounds 0..2: own links, forces accumulated in reference order
+    d3 F = mk3(0.0, 0.0, 0.0), M = mk3(0.0, 0.0, 0.0);
+#pragma unroll 1
+    for (int a = 0; a < 3; a++) {
+        cp_async_wait<1>();
+        const int win = (a & 1) ^ 1;
+        const bool inside = a == 0 ? lx < VX_WB_X - 1 : (a == 1 ? ly < VX_WB_Y - 1 : lz < VX_WB_Z - 1);
+        const bool first = a == 0 ? lx == 0 : (a == 1 ? ly == 0 : lz == 0);
+        const int dl = a == 0 ? 1 : (a == 1 ? 4 : 16);
+        d3 fN = mk3(0.0, 0.0, 0.0), mN = fN, fP = fN, mP = fN;
+        if ((mask >> (2 * a)) & 1u) {
+            double4 n0, n1, p0, p1;
+            load_pose(lane, n0, n1);
+            load_pose(inside ? lane + dl : ext_entry(a), p0, p1);
+            const uint4 r0 = rec_sh[win][0][lane], r1 = rec_sh[win][1][lane], r2 = rec_sh[win][2][lane], r3 = rec_sh[win][3][lane];
+            LinkState st;
+            lat_eval_link_rec<UNI>(f, a, bits,
+                                   make_double2(__hiloint2double(r0.y, r0.x), __hiloint2double(r0.w, r0.z)),
+                                   make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
+                                   make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
+                                   make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
+                                   n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
+            double2 wa, wb, wc; float4 ws; uint32_t lf;
+            lat_encode(st, wa, wb, wc, ws, lf);
+            f.n_rec[a][0][v] = wa; f.n_rec[a][1][v] = wb; f.n_rec[a][2][v] = wc; f.n_recf[a][v] = ws;
+            new_bits = (new_bits & ~(3u << (VM_LFLAG_SHIFT + 2 * a))) | (lf << (VM_LFLAG_SHIFT + 2 * a));
+            if (st.strain > 100) p->div_flag[parity] = 1;          // src/Voxelyze.cpp:265
+            F = F + fN; M = M + mN;
+        }
+        // force on the positive end travels to the lane that holds that voxel
+        const int src = (lane - dl) & 31;
+        d3 inF = mk3(__shfl_sync(0xffffffffu, fP.x, src), __shfl_sync(0xffffffffu, fP.y, src), __shfl_sync(0xffffffffu, fP.z, src));
+        d3 inM = mk3(__shfl_sync(0xffffffffu, mP.x, src), __shfl_sync(0xffffffffu, mP.y, src), __shfl_sync(0xffffffffu, mP.z, src));
+        if ((mask >> (2 * a + 1)) & 1u) {
+            if (first) {
+                const int hl = a == 0 ? ly + 4 * lz : (a == 1 ? 8 + lx + 4 * lz : 16 + lx + 4 * ly);
+                inF = mk3(hslot[0][hl], hslot[1][hl], hslot[2][hl]);
+                inM = mk3(hslot[3][hl], hslot[4][hl], hslot[5][hl]);
+            }
+            F = F + inF; M = M + inM;
+        }
+        // next request into the window this round has left (a lane only ever touches its own column of a window)
+        if (a == 0) request_link(2, true, false);
+        else if (a == 1 && has_voxel) {
+            cp_async16(&rec_sh[0][0][lane], reinterpret_cast<const uint4*>(f.c_mom0 + v));
+            cp_async16(&rec_sh[0][1][lane], reinterpret_cast<const uint4*>(f.c_mom0 + v) + 1);
+            cp_async16(&rec_sh[0][2][lane], reinterpret_cast<const uint4*>(f.c_mom1 + v));
+        }
+        if (a < 2) cp_async_commit();
+    }
+
+    // ---- last round: one lane per voxel
+    cp_async_wait<0>();
+    if (!has_voxel) return;
+    const uint4 q0 = rec_sh[0][0][lane], q1 = rec_sh[0][1][lane], q2 = rec_sh[0][2][lane];
+    double4 s0, s1;
+    load_pose(lane, s0, s1);
+    VoxelState vs;
+    vs.bits = new_bits; vs.temp = meta_temp(s1.w);
+    vs.pos = mk3(s0.x, s0.y, s0.z);
+    vs.orient.w = s0.w; vs.orient.x = s1.x; vs.orient.y = s1.y; vs.orient.z = s1.z;
+    vs.lin = mk3(__hiloint2double(q0.y, q0.x), __hiloint2double(q0.w, q0.z), __hiloint2double(q1.y, q1.x));
+    vs.ang = mk3(__hiloint2double(q1.w, q1.z), __hiloint2double(q2.y, q2.x), __hiloint2double(q2.w, q2.z));
     if (!(vs.bits & VM_GHOST)) {
         const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
         const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;

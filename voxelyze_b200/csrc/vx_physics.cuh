@@ -133,7 +133,7 @@ __device__ __forceinline__ float mat_stress(const DevLinkMat& m, const float* __
 {
     if (mat_failed(m, strain)) return 0.0f;
     const float* e = ce + m.curve_off; const float* s = cs + m.curve_off;
-    if (strain <= __ldg(e + 1) || m.linear || force_linear) {
+    if (m.linear || force_linear || strain <= __ldg(e + 1)) {       // same predicate as src/VX_Material.cpp:170, ordered so linear models never touch the curve
         if (m.nu == 0.0f) return m.E * strain;
         return m.e_hat * ((1 - m.nu) * strain + m.nu * tss);
     }

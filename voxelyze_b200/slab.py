@@ -30,8 +30,7 @@ def slab_range(nz: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def _kernel_name(sim: Sim) -> str:
-    return ("k_lattice_tile (fused link+voxel brick kernel, 1 launch per step)" if sim.active_path() == 2
-            else "k_link<AXIS> (3 launches per step, one per link axis)")
+    return sim.kernel_name()
 
 
 def _path_name(sim: Sim) -> str:
