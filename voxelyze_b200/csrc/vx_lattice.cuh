@@ -719,6 +719,9 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
 
     // ---- requests, one round ahead.  cp.async groups in issue order: H (+ the brick's own poses), round 0,
     //      [after H] round 1 and the round-2 poses, [after round 0] round 2, [after round 1] momenta
+    // record arrays of one generation are one allocation: [axis][part][voxel] (vx_capi.cu lat_frame)
+    auto c_rec = [&](int a, int k) { return f.c_rec[0][0] + (size_t)(a * 3 + k) * f.n_vox; };
+    auto c_recf = [&](int a) { return f.c_recf[0] + (size_t)a * f.n_vox; };
     auto request_pose = [&](int entry, int vox) {
         cp_async16(&pose_sh[0][entry], reinterpret_cast<const uint4*>(f.c_pose0 + vox));
         cp_async16(&pose_sh[1][entry], reinterpret_cast<const uint4*>(f.c_pose0 + vox) + 1);
@@ -737,8 +740,8 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
         if (has_voxel && coord + 1 < nn) {
             if (records) {
 #pragma unroll
-                for (int k = 0; k < 3; k++) cp_async16(&rec_sh[(a & 1) ^ 1][k][lane], f.c_rec[a][k] + v);
-                cp_async16(&rec_sh[(a & 1) ^ 1][3][lane], f.c_recf[a] + v);
+                for (int k = 0; k < 3; k++) cp_async16(&rec_sh[(a & 1) ^ 1][k][lane], c_rec(a, k) + v);
+                cp_async16(&rec_sh[(a & 1) ^ 1][3][lane], c_recf(a) + v);
             }
             if (poses && !inside) request_pose(ext_entry(a), v + (a == 0 ? 1 : (a == 1 ? f.nx : f.nxy)));
         }
@@ -746,8 +749,8 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
     request_pose(lane, v);
     if (h_geo) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) cp_async16(&rec_sh[0][k][lane], f.c_rec[h_axis][k] + h_vn);
-        cp_async16(&rec_sh[0][3][lane], f.c_recf[h_axis] + h_vn);
+        for (int k = 0; k < 3; k++) cp_async16(&rec_sh[0][k][lane], c_rec(h_axis, k) + h_vn);
+        cp_async16(&rec_sh[0][3][lane], c_recf(h_axis) + h_vn);
         request_pose(32 + lane, h_vn);
     }
     cp_async_commit();
@@ -803,7 +806,8 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
                                    n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
             double2 wa, wb, wc; float4 ws; uint32_t lf;
             lat_encode(st, wa, wb, wc, ws, lf);
-            f.n_rec[a][0][v] = wa; f.n_rec[a][1][v] = wb; f.n_rec[a][2][v] = wc; f.n_recf[a][v] = ws;
+            double2* nr = f.n_rec[0][0] + (size_t)(a * 3) * f.n_vox + v;       // the nine record arrays are one allocation
+            nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; (f.n_recf[0] + (size_t)a * f.n_vox)[v] = ws;
             new_bits = (new_bits & ~(3u << (VM_LFLAG_SHIFT + 2 * a))) | (lf << (VM_LFLAG_SHIFT + 2 * a));
             if (st.strain > 100) p->div_flag[parity] = 1;          // src/Voxelyze.cpp:265
             F = F + fN; M = M + mN;
