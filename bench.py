@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="override lattice edge (testing only; reported in config)")
     ap.add_argument("--cpu-sample", type=int, default=48, help="edge of the CPU baseline sample lattice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="N>1: NCCL send/recv for the halo instead of peer-memory stores")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange the halo after the step instead of overlapping it with the interior")
     ap.add_argument("--path", type=int, default=0, help="kernel variant (vx_set_path): 0 auto, 1 general, 2..5 fused lattice variants (ablation)")
     args = ap.parse_args()
     # >= 17 (one direct step + one 16-step graph) so that the CUDA graphs are captured and instantiated before the timed region
@@ -177,7 +179,7 @@ def main():
         sim = scenarios.build(lib, sc, device=local, path=args.path)
         runner = slab.SingleRunner(sim)
     else:
-        runner = slab.SlabRunner(lib, edge, edge, edge, rank, world, device=local, path=args.path)
+        runner = slab.SlabRunner(lib, edge, edge, edge, rank, world, device=local, path=args.path, overlap=not args.no_overlap, peer=not args.no_peer)
         sim = runner.sim
     sim.set_stream(stream.cuda_stream)
     dt = runner.recommended_dt()
@@ -249,7 +251,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(world) if not args.size else f"{edge}^3 cantilever (size override)",
-                           "voxels": n_vox, "links": n_link, "dt": dt, "path": runner.path_name(),
+                           "voxels": n_vox, "links": n_link, "dt": dt, "path": runner.path_name(), **({"halo": runner.halo_name()} if world > 1 else {}),
                            "l2": "inputs larger than L2 (no flush needed)"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
         if not args.no_cpu_baseline:

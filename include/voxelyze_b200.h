@@ -275,6 +275,51 @@ int  vx_pose_plane(vx_sim* s, int iz, uint64_t* dev_ptr0, uint64_t* dev_ptr1,
  * the receiving voxel keeps its own flag word (it stays a ghost) and takes the sender's
  * temperature.                                                                        */
 int  vx_halo_import(vx_sim* s, int iz, uint64_t src_ptr0, uint64_t src_ptr1, int count);
+/* same, queued on the given cudaStream_t instead of the handle's stream (the stream the
+ * halo messages arrive on)                                                            */
+int  vx_halo_import_on(vx_sim* s, int iz, uint64_t src_ptr0, uint64_t src_ptr1, int count,
+                       uint64_t cuda_stream);
+/* asynchronous stepping, for z-slab runs that overlap the halo exchange with the step
+ * ("boundary-plane voxels integrated first -> halo push -> interior").
+ * A call is vx_step_begin, any number of steps queued with vx_step_enqueue, and
+ * vx_step_end, which blocks and reports exactly like vx_step.  Nothing in between blocks
+ * the host.  One step is either vx_step_enqueue(VX_PART_ALL) or VX_PART_Z_BOUNDARY followed
+ * by VX_PART_Z_INTERIOR: the boundary part advances the layers that hold ghost planes
+ * (VX_VF_GHOST) and their neighbours, i.e. everything an exchange sends or receives, the
+ * interior part the rest.  After a boundary part vx_pose_plane/vx_halo_import* address the
+ * NEW state, so the caller can ship the fresh boundary poses on a second stream (ordered
+ * by events: after the boundary part, before the next step) while the interior part runs.
+ * Same arithmetic, same bits as vx_step.  Fused lattice path only; no other call on the
+ * handle between begin and end except vx_pose_plane, vx_halo_import*, vx_launch_count.      */
+#define VX_PART_ALL        0
+#define VX_PART_Z_BOUNDARY 1
+#define VX_PART_Z_INTERIOR 2
+int  vx_step_begin(vx_sim* s, float dt);
+int  vx_step_enqueue(vx_sim* s, int part);
+int  vx_step_end(vx_sim* s, int* diverged_step);
+/* peer-memory halo for z-slab runs, one process per GPU on one NVLink/NVSwitch node: each
+ * slab stores its fresh boundary poses straight into its neighbours' ghost layers (CUDA IPC
+ * mappings) from its own kernel and bumps an arrival counter there; no NCCL call and no host
+ * work per step.  Setup, after vx_set_voxels on every slab:
+ *   owner of a ghost layer:  vx_peer_export(s, ghost_iz, from_above, &desc)  (from_above: the
+ *       writer is the slab above, i.e. this is the top ghost layer) and hands the descriptor
+ *       to that neighbour by any means (bench.py: torch.distributed all_gather of the bytes);
+ *   the neighbour:           vx_peer_attach(s, send_iz, &desc)  -- its layer send_iz is the
+ *       one mirrored into that ghost layer.
+ * vx_slab_step(s, dt, n, &div) then runs n steps like vx_step, each as: wait for the
+ * neighbours' previous delivery -> boundary part -> [second stream: push + signal] overlapped
+ * with the interior part.  All slabs must make the same sequence of vx_slab_step /
+ * vx_slab_exchange calls.  vx_slab_exchange ships the CURRENT boundary poses (needed once after
+ * state was changed by vx_upload or vx_reset); the neighbours' deliveries are awaited by the next
+ * vx_slab_step.  A neighbour that does not deliver within ~4 s makes vx_slab_step fail
+ * (VX_ERR_CUDA) instead of hanging the GPU.                                                  */
+#define VX_PEER_DESC_BYTES 512
+typedef struct vx_peer_desc { unsigned char bytes[VX_PEER_DESC_BYTES]; } vx_peer_desc;
+int  vx_peer_export(vx_sim* s, int ghost_iz, int from_above, vx_peer_desc* out);
+int  vx_peer_attach(vx_sim* s, int send_iz, const vx_peer_desc* peer_ghost);
+int  vx_peer_detach(vx_sim* s);
+int  vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step);
+int  vx_slab_exchange(vx_sim* s);
 /* number of kernels this handle has launched so far (bench.py "gpu_launches").       */
 int64_t vx_launch_count(const vx_sim* s);
 /* block until all queued work of this handle is done.                                */

@@ -403,6 +403,15 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
 int vx_set_stream(vx_sim*, uint64_t) { return VX_ERR_UNSUPPORTED; }
 int vx_pose_plane(vx_sim*, int, uint64_t*, uint64_t*, int*, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_halo_import(vx_sim*, int, uint64_t, uint64_t, int) { return VX_ERR_UNSUPPORTED; }
+int vx_halo_import_on(vx_sim*, int, uint64_t, uint64_t, int, uint64_t) { return VX_ERR_UNSUPPORTED; }
+int vx_step_begin(vx_sim*, float) { return VX_ERR_UNSUPPORTED; }
+int vx_step_enqueue(vx_sim*, int) { return VX_ERR_UNSUPPORTED; }
+int vx_step_end(vx_sim*, int*) { return VX_ERR_UNSUPPORTED; }
+int vx_peer_export(vx_sim*, int, int, vx_peer_desc*) { return VX_ERR_UNSUPPORTED; }
+int vx_peer_attach(vx_sim*, int, const vx_peer_desc*) { return VX_ERR_UNSUPPORTED; }
+int vx_peer_detach(vx_sim*) { return VX_ERR_UNSUPPORTED; }
+int vx_slab_step(vx_sim*, float, int, int*) { return VX_ERR_UNSUPPORTED; }
+int vx_slab_exchange(vx_sim*) { return VX_ERR_UNSUPPORTED; }
 int64_t vx_launch_count(const vx_sim*) { return 0; }
 int vx_sync(vx_sim*) { return VX_OK; }
 int vx_set_path(vx_sim*, int) { return VX_OK; }

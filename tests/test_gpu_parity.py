@@ -274,3 +274,90 @@ def test_collision_case_energy_and_centre_of_mass(product, oracle):
         assert np.max(np.abs(com_g - com_o)) <= 1e-9
         assert np.array_equal(g.collision_pairs(), o.collision_pairs())
         assert np.array_equal(g.download("linkflags") & 0xC, o.download("linkflags") & 0xC)
+
+
+def test_split_asynchronous_steps_match_whole_steps_bitwise(product):
+    """vx_step_begin / vx_step_enqueue(boundary, interior) / vx_step_end with the halo shipped on a second
+    stream between the two parts (the multi-GPU overlap of SURVEY.md section 8e), emulated on ONE GPU:
+    two z-slabs of a cantilever live in one process and trade pose planes by device copies."""
+    import torch
+    from voxelyze_b200 import slab
+    nx, ny, nz, steps = 10, 9, 23, 37
+    sc = scenarios.cantilever(nx, ny, nz, tip_load=25.0)
+    whole, dt, _ = parity.run(product, sc, steps)
+    main, comm = torch.cuda.current_stream(), torch.cuda.Stream()
+    runs = [slab.SlabRunner(product, nx, ny, nz, r, 2, tip_load=25.0) for r in range(2)]
+    for r in runs:
+        assert r.sim.active_path() == 2
+        r.sim.set_stream(main.cuda_stream)
+    views = {}
+
+    def plane(sim, z):
+        p0, p1, n, rb = sim.pose_plane(z)
+        for p in (p0, p1):
+            if p not in views:
+                views[p] = torch.as_tensor(slab._DevMem(p, n * rb), device="cuda")
+        return views[p0], views[p1], n
+
+    done = 0
+    for chunk in (1, 20, steps - 21):                  # several calls: generations alternate across calls too
+        for r in runs:
+            r.sim.step_begin(dt)
+        imported = None
+        for _ in range(chunk):
+            if imported is not None:
+                main.wait_event(imported)
+            for r in runs:
+                r.sim.step_enqueue(r.sim.PART_Z_BOUNDARY)
+            ready = torch.cuda.Event(); ready.record(main)
+            for r in runs:
+                r.sim.step_enqueue(r.sim.PART_Z_INTERIOR)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                for me, other in ((runs[0], runs[1]), (runs[1], runs[0])):
+                    (peer, send_z, recv_z), = me._neighbours()
+                    a0, a1, n = plane(other.sim, recv_z)         # the peer owns my ghost layer
+                    b0, b1 = a0.clone(), a1.clone()              # the message
+                    me.sim.halo_import(recv_z, b0.data_ptr(), b1.data_ptr(), n, comm.cuda_stream)
+                imported = torch.cuda.Event(); imported.record(comm)
+        main.wait_event(imported)
+        for r in runs:
+            assert r.sim.step_end() is None
+        done += chunk
+    assert done == steps
+    for f in ("pos", "orient", "linmom", "angmom"):
+        got = np.concatenate([r.owned_state(f) for r in runs])
+        assert parity.bit_equal(got, whole.download(f)), f
+
+
+def test_peer_memory_halo_steps_match_whole_steps_bitwise(product):
+    """vx_peer_export/attach + vx_slab_step: each slab stores its boundary poses straight into the other's
+    ghost layer from its own stream and spins on an arrival counter; here both slabs live in one process
+    on one GPU (plain addresses instead of CUDA IPC mappings) and are stepped alternately."""
+    from voxelyze_b200 import slab
+    nx, ny, nz, steps = 9, 10, 21, 30
+    sc = scenarios.cantilever(nx, ny, nz, tip_load=25.0)
+    whole, dt, _ = parity.run(product, sc, steps)
+    runs = [slab.SlabRunner(product, nx, ny, nz, r, 3, tip_load=25.0) for r in range(3)]
+    slab.SlabRunner.connect_local(runs)
+    for _ in range(steps):
+        for r in runs:
+            assert r.step(dt, 1) is None
+    for f in ("pos", "orient", "linmom", "angmom"):
+        got = np.concatenate([r.owned_state(f) for r in runs])
+        assert parity.bit_equal(got, whole.download(f)), f
+    # perturb one slab's boundary, re-publish with vx_slab_exchange on every slab, and keep matching
+    first, n = runs[1].layer_index_range(runs[1].z0)
+    pos = runs[1].sim.download("pos", first, n); pos[:, 2] += 1e-7
+    runs[1].sim.upload("pos", pos, first)
+    wfirst = runs[1].z0 * nx * ny
+    wpos = whole.download("pos", wfirst, n); wpos[:, 2] += 1e-7
+    whole.upload("pos", wpos, wfirst)
+    for r in runs:
+        r.exchange()
+    whole.step(dt, 5)
+    for _ in range(5):
+        for r in runs:
+            r.step(dt, 1)
+    got = np.concatenate([r.owned_state("pos") for r in runs])
+    assert parity.bit_equal(got, whole.download("pos"))

@@ -158,6 +158,15 @@ class VxLib:
             "vx_halo_import": (i32, [vp, i32, u64, u64, i32]),
             "vx_launch_count": (C.c_int64, [vp]),
             "vx_sync": (i32, [vp]),
+            "vx_halo_import_on": (i32, [vp, i32, C.c_uint64, C.c_uint64, i32, C.c_uint64]),
+            "vx_step_begin": (i32, [vp, C.c_float]),
+            "vx_step_enqueue": (i32, [vp, i32]),
+            "vx_step_end": (i32, [vp, C.POINTER(i32)]),
+            "vx_peer_export": (i32, [vp, i32, i32, C.c_void_p]),
+            "vx_peer_attach": (i32, [vp, i32, C.c_void_p]),
+            "vx_peer_detach": (i32, [vp]),
+            "vx_slab_step": (i32, [vp, C.c_float, i32, C.POINTER(i32)]),
+            "vx_slab_exchange": (i32, [vp]),
             "vx_set_path": (i32, [vp, i32]),
             "vx_active_path": (i32, [vp]),
             "vx_kernel_name": (C.c_char_p, [vp]),
@@ -355,8 +364,46 @@ class Sim:
         self._chk(self.L.lib.vx_pose_plane(self.h, iz, C.byref(p0), C.byref(p1), C.byref(n), C.byref(rb)))
         return p0.value, p1.value, n.value, rb.value
 
-    def halo_import(self, iz: int, ptr0: int, ptr1: int, count: int):
-        self._chk(self.L.lib.vx_halo_import(self.h, iz, ptr0, ptr1, count))
+    def halo_import(self, iz: int, ptr0: int, ptr1: int, count: int, stream: Optional[int] = None):
+        if stream is None:
+            self._chk(self.L.lib.vx_halo_import(self.h, iz, ptr0, ptr1, count))
+        else:
+            self._chk(self.L.lib.vx_halo_import_on(self.h, iz, ptr0, ptr1, count, stream))
+
+    # asynchronous call: step_begin, step_enqueue(part)..., step_end (include/voxelyze_b200.h)
+    PART_ALL, PART_Z_BOUNDARY, PART_Z_INTERIOR = 0, 1, 2
+
+    def step_begin(self, dt: float):
+        self._chk(self.L.lib.vx_step_begin(self.h, dt))
+
+    def step_enqueue(self, part: int = 0):
+        self._chk(self.L.lib.vx_step_enqueue(self.h, part))
+
+    PEER_DESC_BYTES = 512
+
+    def peer_export(self, ghost_iz: int, from_above: bool) -> bytes:
+        buf = C.create_string_buffer(self.PEER_DESC_BYTES)
+        self._chk(self.L.lib.vx_peer_export(self.h, ghost_iz, 1 if from_above else 0, buf))
+        return buf.raw
+
+    def peer_attach(self, send_iz: int, desc: bytes):
+        self._chk(self.L.lib.vx_peer_attach(self.h, send_iz, C.create_string_buffer(desc, self.PEER_DESC_BYTES)))
+
+    def peer_detach(self):
+        self._chk(self.L.lib.vx_peer_detach(self.h))
+
+    def slab_step(self, dt: float, n: int = 1) -> Optional[int]:
+        div = C.c_int(-1)
+        rc = self._chk(self.L.lib.vx_slab_step(self.h, dt, n, C.byref(div)), ok=(VX_OK, VX_DIVERGED))
+        return div.value if rc == VX_DIVERGED else None
+
+    def slab_exchange(self):
+        self._chk(self.L.lib.vx_slab_exchange(self.h))
+
+    def step_end(self) -> Optional[int]:
+        div = C.c_int(-1)
+        rc = self._chk(self.L.lib.vx_step_end(self.h, C.byref(div)), ok=(VX_OK, VX_DIVERGED))
+        return div.value if rc == VX_DIVERGED else None
 
     def launch_count(self) -> int:
         return self.L.lib.vx_launch_count(self.h)

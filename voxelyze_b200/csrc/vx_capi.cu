@@ -9,6 +9,7 @@
 // There is deliberately no CPU code path for stepping: without a usable CUDA device
 // vx_create fails with VX_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -86,6 +87,25 @@ struct vx_sim {
     bool have_prev = false;             // gen^1 holds the inputs of the last executed step
     float last_prev_dt = 0.f;           // previousDt that step used
     float prev_dt_host = 0.f;           // mirror of DevParams::prev_dt
+    // asynchronous call (vx_step_begin .. vx_step_end), used by z-slab runs to overlap the halo exchange
+    bool call_active = false, call_half = false;
+    int call_g0 = 0, call_done = 0;     // starting generation, steps whose boundary part has been enqueued
+    std::vector<int> zb_layers;         // brick-group layers (4 planes each) that hold ghost planes or their neighbours
+    // peer-memory halo (vx_peer_*): my boundary layer -> the ghost layer of the neighbouring slab, over NVLink
+    struct PeerLink {
+        size_t src_first = 0, count = 0;                  // my layer (internal voxel range)
+        double4* dst0[2] = {nullptr, nullptr};            // the peer's ghost layer in its pose0/pose1 arrays, per generation
+        double4* dst1[2] = {nullptr, nullptr};
+        int* dst_flag = nullptr;                          // the peer's arrival counter for messages from me
+        void* opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cudaIpcOpenMemHandle results (other-process peers)
+    };
+    std::vector<PeerLink> peers;
+    DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
+    int n_expect[2] = {0, 0};           // exchanges a neighbour on that side takes part in (0 or 1 per exchange)
+    bool expect_side[2] = {false, false};
+    int xseq = 0;                       // exchanges completed or queued so far (same on all slabs)
+    cudaStream_t comm_stream = nullptr; cudaEvent_t ev_boundary = nullptr, ev_comm = nullptr;
+    int newest_gen() const { return call_active ? (call_g0 + call_done) & 1 : gen; }
 
     // ---- device
     DevBuf<double4> pose0[2], pose1[2], mom0[2]; DevBuf<double2> mom1[2];   // general mode uses [0] only
@@ -574,23 +594,34 @@ static int ensure_graph(vx_sim* s)
 
 // ------------------------------------------------------------------------------------------------
 // stepping, lattice mode
+// default fused kernel over the brick-group layers [gz_off, gz_off + ngz) (ngz < 0: all)
+static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off, int ngz, int book)
+{
+    const int nbx = (s->nx + 2 * VX_WB_X - 1) / (2 * VX_WB_X), nby = (s->ny + 2 * VX_WB_Y - 1) / (2 * VX_WB_Y);
+    const int nbz = ngz < 0 ? (s->nz + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z) : ngz;
+    const long long bricks = (long long)nbx * nby * nbz * 8 * s->n_members;      // 2x2x2 groups of 4x4x2 bricks
+    const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
+    static bool wb_opted_in = false;     // > 48 KB of dynamic shared memory needs a one-time opt-in per function
+    if (!wb_opted_in) {
+        cudaFuncSetAttribute(k_lattice_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+        cudaFuncSetAttribute(k_lattice_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+        wb_opted_in = true;
+    }
+    if (grid > 0) {
+        if (s->uni) k_lattice_warp<true><<<(unsigned)grid, 32 * VX_WB_WARPS, VX_WB_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, nbx, nby, nbz, gz_off, book);
+        else k_lattice_warp<false><<<(unsigned)grid, 32 * VX_WB_WARPS, VX_WB_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, nbx, nby, nbz, gz_off, book);
+        s->launches++;
+    }
+}
+
 static void launch_lattice(vx_sim* s, int g, int first_of_call)
 {
     if (s->path == 3) {                  // ablation: one thread per voxel, all six links re-evaluated
         if (s->uni) k_lattice_step<true><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
         else k_lattice_step<false><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
     } else if (s->path != 2 && s->path != 4) {   // default: one warp per 4x4x2 brick, no block barriers
-        const int nbx = (s->nx + 2 * VX_WB_X - 1) / (2 * VX_WB_X), nby = (s->ny + 2 * VX_WB_Y - 1) / (2 * VX_WB_Y), nbz = (s->nz + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z);
-        const long long bricks = (long long)nbx * nby * nbz * 8 * s->n_members;      // 2x2x2 groups of 4x4x2 bricks
-        const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
-        static bool wb_opted_in = false;
-        if (!wb_opted_in) {
-            cudaFuncSetAttribute(k_lattice_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
-            cudaFuncSetAttribute(k_lattice_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
-            wb_opted_in = true;
-        }
-        if (s->uni) k_lattice_warp<true><<<(unsigned)grid, 32 * VX_WB_WARPS, VX_WB_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, nbx, nby, nbz);
-        else k_lattice_warp<false><<<(unsigned)grid, 32 * VX_WB_WARPS, VX_WB_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, nbx, nby, nbz);
+        launch_lattice_warp(s, g, first_of_call, 0, -1, 1);
+        return;
     } else if (s->path == 2) {           // 8x4x4 bricks per block, thread per link evaluation + shared-memory slots
         const int ntx = (s->nx + VX_TILE_X - 1) / VX_TILE_X, nty = (s->ny + VX_TILE_Y - 1) / VX_TILE_Y, ntz = (s->nz + VX_TILE_Z - 1) / VX_TILE_Z;
         const long long grid = (long long)ntx * nty * ntz * s->n_members;
@@ -685,7 +716,250 @@ static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     return finish_lattice_call(s, g0, n_steps, diverged_step);
 }
 
+// ------------------------------------------------------------------------------------------------
+// peer-memory halo: after the boundary part of a step each slab stores its fresh boundary poses straight
+// into the ghost planes of its neighbours (CUDA IPC mappings, NVLink) and then bumps the neighbour's
+// arrival counter; the neighbour's next boundary part spins on that counter first.
+__global__ void k_halo_push(const double4* __restrict__ src0, const double4* __restrict__ src1, double4* dst0, double4* dst1, int count)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const double4 a = src0[k], b = src1[k];
+    dst0[k] = a;
+    double* d = reinterpret_cast<double*>(dst1 + k);
+    d[0] = b.x; d[1] = b.y; d[2] = b.z;
+    // the receiver owns the upper half of w (its flag word, see k_lattice_warp); the lower half is the temperature
+    reinterpret_cast<uint32_t*>(d + 3)[0] = (uint32_t)(unsigned long long)__double_as_longlong(b.w);
+}
+__global__ void k_peer_signal(int* flag, int seq)
+{
+    __threadfence_system();
+    *(volatile int*)flag = seq;
+    __threadfence_system();
+}
+__global__ void k_peer_wait(const int* flags, int need_lo, int need_hi, int* timed_out)
+{
+    const long long t0 = clock64();
+    const long long limit = 8000000000LL;                  // ~4 s of SM clocks: a lost peer must not hang the GPU
+    while (*(volatile const int*)(flags + 0) < need_lo || *(volatile const int*)(flags + 1) < need_hi) {
+        if (clock64() - t0 > limit) { *timed_out = 1; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// brick-group layers that a halo exchange touches: those holding an all-ghost plane or a plane next to one
+static void find_boundary_layers(vx_sim* s)
+{
+    s->zb_layers.clear();
+    if (!s->lattice || s->n_members != 1 || s->vflags.empty()) return;
+    const size_t plane = (size_t)s->nx * s->ny;
+    std::vector<char> ghost(s->nz, 0);
+    for (int z = 0; z < s->nz; z++) {
+        bool all = true;
+        for (size_t k = 0; k < plane && all; k++) all = (s->vflags[s->v_i2e[(size_t)z * plane + k]] & VX_VF_GHOST) != 0;
+        ghost[z] = all;
+    }
+    const int per = 2 * VX_WB_Z;
+    for (int z = 0; z < s->nz; z++) {
+        bool b = ghost[z] || (z > 0 && ghost[z - 1]) || (z + 1 < s->nz && ghost[z + 1]);
+        if (b && (s->zb_layers.empty() || s->zb_layers.back() != z / per)) s->zb_layers.push_back(z / per);
+    }
+}
+
 extern "C" {
+
+int vx_step_begin(vx_sim* s, float dt)
+{
+    if (!s) return VX_ERR_ARG;
+    if (!s->lattice || (s->path != 0 && s->path != 5)) return fail(s, VX_ERR_UNSUPPORTED, "asynchronous stepping needs the fused lattice path");
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_step_begin: a call is already open");
+    if (dt <= 0) return fail(s, VX_ERR_ARG, "vx_step_begin needs an explicit dt");
+    CK(cudaSetDevice(s->device));
+    k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
+    s->call_active = true; s->call_half = false; s->call_g0 = s->gen; s->call_done = 0;
+    return VX_OK;
+}
+
+int vx_step_enqueue(vx_sim* s, int part)
+{
+    if (!s || !s->call_active || part < 0 || part > 2) return VX_ERR_ARG;
+    const int ngz = (s->nz + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z);
+    const bool split = !s->zb_layers.empty() && (int)s->zb_layers.size() < ngz;
+    if (part == VX_PART_Z_INTERIOR) {
+        if (!s->call_half) return fail(s, VX_ERR_ARG, "vx_step_enqueue: interior part without its boundary part");
+        s->call_half = false;
+        if (!split) return VX_OK;                    // the boundary part was the whole step
+        const int g = (s->call_g0 + s->call_done - 1) & 1, first = s->call_done == 1;
+        int from = 0;                                // the complement of zb_layers, as contiguous ranges
+        for (size_t k = 0; k <= s->zb_layers.size(); k++) {
+            const int to = k < s->zb_layers.size() ? s->zb_layers[k] : ngz;
+            if (to > from) launch_lattice_warp(s, g, first, from, to - from, 0);
+            from = to + 1;
+        }
+        CK(cudaGetLastError());
+        return VX_OK;
+    }
+    if (s->call_half) return fail(s, VX_ERR_ARG, "vx_step_enqueue: the previous step still lacks its interior part");
+    const int g = (s->call_g0 + s->call_done) & 1, first = s->call_done == 0;
+    if (part == VX_PART_ALL || !split) launch_lattice_warp(s, g, first, 0, -1, 1);
+    else for (size_t k = 0; k < s->zb_layers.size(); k++) launch_lattice_warp(s, g, first, s->zb_layers[k], 1, k == 0);
+    s->call_done++;
+    s->call_half = part == VX_PART_Z_BOUNDARY;
+    CK(cudaGetLastError());
+    return VX_OK;
+}
+
+int vx_step_end(vx_sim* s, int* diverged_step)
+{
+    if (!s || !s->call_active) return VX_ERR_ARG;
+    if (s->call_half) return fail(s, VX_ERR_ARG, "vx_step_end: the last step lacks its interior part");
+    s->call_active = false;
+    if (diverged_step) *diverged_step = -1;
+    if (s->call_done == 0) return VX_OK;
+    return finish_lattice_call(s, s->call_g0, s->call_done, diverged_step);
+}
+
+// ---- peer-memory halo ---------------------------------------------------------------------------
+struct PeerDescWire {                       // what vx_peer_export writes into vx_peer_desc::bytes
+    uint64_t magic; int64_t pid; int32_t device, side; uint64_t first, count;
+    cudaIpcMemHandle_t mem[4]; cudaIpcMemHandle_t flag;      // pose0[0], pose0[1], pose1[0], pose1[1]; flag array
+    uint64_t raw[4]; uint64_t raw_flag;                      // same-process peers use the addresses directly
+};
+static_assert(sizeof(PeerDescWire) <= VX_PEER_DESC_BYTES, "vx_peer_desc too small");
+
+static int plane_range(vx_sim* s, int iz, size_t& first, size_t& count)
+{
+    int64_t key = (int64_t)(iz + 32768);
+    auto lo = std::lower_bound(s->sort_key.begin(), s->sort_key.end(), key);
+    auto hi = std::upper_bound(s->sort_key.begin(), s->sort_key.end(), key);
+    first = lo - s->sort_key.begin(); count = hi - lo;
+    return count ? VX_OK : VX_ERR_ARG;
+}
+
+static int ensure_peer_state(vx_sim* s)
+{
+    CK(cudaSetDevice(s->device));
+    if (!s->peer_flags.p) { CK(s->peer_flags.alloc(4)); CK(cudaMemset(s->peer_flags.p, 0, 4 * sizeof(int))); }
+    if (!s->comm_stream) CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    if (!s->ev_boundary) CK(cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
+    if (!s->ev_comm) CK(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
+    return VX_OK;
+}
+
+int vx_peer_export(vx_sim* s, int ghost_iz, int from_above, vx_peer_desc* out)
+{
+    if (!s || !out || !s->lattice || s->n_members != 1) return VX_ERR_ARG;
+    int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
+    size_t first, count;
+    if (plane_range(s, ghost_iz, first, count) != VX_OK) return fail(s, VX_ERR_ARG, "vx_peer_export: empty layer");
+    PeerDescWire w{}; w.magic = 0x56585045455231ULL; w.pid = (int64_t)getpid(); w.device = s->device; w.side = from_above ? 1 : 0;
+    w.first = first; w.count = count;
+    double4* base[4] = {s->pose0[0].p, s->pose0[1].p, s->pose1[0].p, s->pose1[1].p};
+    for (int k = 0; k < 4; k++) { CK(cudaIpcGetMemHandle(&w.mem[k], base[k])); w.raw[k] = (uint64_t)(uintptr_t)base[k]; }
+    CK(cudaIpcGetMemHandle(&w.flag, s->peer_flags.p)); w.raw_flag = (uint64_t)(uintptr_t)s->peer_flags.p;
+    memset(out->bytes, 0, VX_PEER_DESC_BYTES); memcpy(out->bytes, &w, sizeof(w));
+    s->expect_side[w.side] = true;                                   // a neighbour will write here
+    return VX_OK;
+}
+
+int vx_peer_attach(vx_sim* s, int send_iz, const vx_peer_desc* peer_ghost)
+{
+    if (!s || !peer_ghost || !s->lattice || s->n_members != 1) return VX_ERR_ARG;
+    int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
+    PeerDescWire w; memcpy(&w, peer_ghost->bytes, sizeof(w));
+    if (w.magic != 0x56585045455231ULL) return fail(s, VX_ERR_ARG, "vx_peer_attach: not a peer descriptor");
+    vx_sim::PeerLink pl;
+    if (plane_range(s, send_iz, pl.src_first, pl.count) != VX_OK || pl.count != w.count) return fail(s, VX_ERR_ARG, "vx_peer_attach: layer size mismatch");
+    void* base[5];
+    if (w.pid == (int64_t)getpid()) {                                 // same process (tests): plain addresses
+        for (int k = 0; k < 4; k++) base[k] = (void*)(uintptr_t)w.raw[k];
+        base[4] = (void*)(uintptr_t)w.raw_flag;
+        if (w.device != s->device) { int can = 0; cudaDeviceCanAccessPeer(&can, s->device, w.device); if (!can) return fail(s, VX_ERR_UNSUPPORTED, "no peer access"); cudaError_t e = cudaDeviceEnablePeerAccess(w.device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(s, e, "cudaDeviceEnablePeerAccess"); cudaGetLastError(); }
+    } else {
+        for (int k = 0; k < 4; k++) {
+            cudaError_t e = cudaIpcOpenMemHandle(&base[k], w.mem[k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(s, VX_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+            pl.opened[k] = base[k];
+        }
+        cudaError_t e = cudaIpcOpenMemHandle(&base[4], w.flag, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(s, VX_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+        pl.opened[4] = base[4];
+    }
+    pl.dst0[0] = (double4*)base[0] + w.first; pl.dst0[1] = (double4*)base[1] + w.first;
+    pl.dst1[0] = (double4*)base[2] + w.first; pl.dst1[1] = (double4*)base[3] + w.first;
+    pl.dst_flag = (int*)base[4] + w.side;
+    s->peers.push_back(pl);
+    return VX_OK;
+}
+
+int vx_peer_detach(vx_sim* s)
+{
+    if (!s) return VX_ERR_ARG;
+    cudaSetDevice(s->device);
+    if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+    for (auto& pl : s->peers) for (void* q : pl.opened) if (q) cudaIpcCloseMemHandle(q);
+    s->peers.clear(); s->expect_side[0] = s->expect_side[1] = false;
+    return VX_OK;
+}
+
+// queue: wait for every exchange so far (compute stream)
+static void peer_wait(vx_sim* s, cudaStream_t st)
+{
+    if (s->xseq == 0 || (!s->expect_side[0] && !s->expect_side[1])) return;
+    k_peer_wait<<<1, 1, 0, st>>>(s->peer_flags.p, s->expect_side[0] ? s->xseq : 0, s->expect_side[1] ? s->xseq : 0, s->peer_flags.p + 2);
+    s->launches++;
+}
+// queue: ship generation g of my boundary layers and signal (comm stream)
+static void peer_push(vx_sim* s, int g)
+{
+    s->xseq++;
+    for (auto& pl : s->peers) {
+        k_halo_push<<<blocks_for((long long)pl.count), TPB, 0, s->comm_stream>>>(s->pose0[g].p + pl.src_first, s->pose1[g].p + pl.src_first,
+                                                                                 pl.dst0[g], pl.dst1[g], (int)pl.count);
+        k_peer_signal<<<1, 1, 0, s->comm_stream>>>(pl.dst_flag, s->xseq);
+        s->launches += 2;
+    }
+}
+static int peer_check(vx_sim* s)
+{
+    int t = 0;
+    CK(cudaMemcpy(&t, s->peer_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    return t ? fail(s, VX_ERR_CUDA, "peer halo: a neighbouring slab did not deliver in time") : VX_OK;
+}
+
+int vx_slab_exchange(vx_sim* s)
+{
+    if (!s || !s->lattice || s->call_active) return VX_ERR_ARG;
+    int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
+    CK(cudaEventRecord(s->ev_boundary, s->stream));
+    CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
+    peer_push(s, s->gen);
+    CK(cudaStreamSynchronize(s->comm_stream));       // delivered; the neighbours' deliveries are awaited by the next vx_slab_step
+    return VX_OK;
+}
+
+int vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
+{
+    if (!s || n_steps < 0) return VX_ERR_ARG;
+    if (n_steps == 0) return VX_OK;
+    int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
+    rc = vx_step_begin(s, dt); if (rc != VX_OK) return rc;
+    for (int k = 0; k < n_steps; k++) {
+        peer_wait(s, s->stream);                            // the boundary part reads the ghosts of the previous exchange
+        rc = vx_step_enqueue(s, VX_PART_Z_BOUNDARY); if (rc != VX_OK) return rc;
+        CK(cudaEventRecord(s->ev_boundary, s->stream));
+        rc = vx_step_enqueue(s, VX_PART_Z_INTERIOR); if (rc != VX_OK) return rc;
+        CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
+        peer_push(s, s->newest_gen());
+    }
+    CK(cudaEventRecord(s->ev_comm, s->comm_stream));
+    CK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
+    rc = vx_step_end(s, diverged_step);
+    if (rc != VX_OK && rc != VX_DIVERGED) return rc;
+    int rc2 = peer_check(s);
+    return rc2 != VX_OK ? rc2 : rc;
+}
 
 int vx_abi_version(void) { return VX_ABI_VERSION; }
 const char* vx_backend(void) { return "cuda-sm100a"; }
@@ -716,6 +990,11 @@ void vx_destroy(vx_sim* s)
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    vx_peer_detach(s);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
+    if (s->ev_comm) cudaEventDestroy(s->ev_comm);
+    s->peer_flags.release();
     s->drop_graph();
     for (int g = 0; g < 2; g++) { s->pose0[g].release(); s->pose1[g].release(); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); s->recf[g].release(); }
     s->pair_lmat.release(); s->link_owner.release(); s->link_axis_dev.release();
@@ -930,6 +1209,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     int rc = upload_tables(s);                     // new link materials may have appeared
     if (rc != VX_OK) return rc;
     if (s->collisions) { rc = build_collision_tables(s); if (rc != VX_OK) return rc; }
+    find_boundary_layers(s);
     return upload_initial_state(s, s->ambient);    // new voxels start at ambient temperature, src/Voxelyze.cpp:449
 }
 
@@ -1371,9 +1651,10 @@ int vx_pose_plane(vx_sim* s, int iz, uint64_t* p0, uint64_t* p1, int* count, int
     auto lo = std::lower_bound(s->sort_key.begin(), s->sort_key.end(), key);
     auto hi = std::upper_bound(s->sort_key.begin(), s->sort_key.end(), key);
     size_t first = lo - s->sort_key.begin();
-    Frame f = s->frame();                          // current generation in lattice mode
-    if (p0) *p0 = (uint64_t)(uintptr_t)(f.pose0 + first);
-    if (p1) *p1 = (uint64_t)(uintptr_t)(f.pose1 + first);
+    const int g = s->lattice ? s->newest_gen() : 0;  // lattice mode ping-pongs generations; inside an asynchronous call the
+                                                     // newest one is the output of the last enqueued boundary part
+    if (p0) *p0 = (uint64_t)(uintptr_t)(s->pose0[g].p + first);
+    if (p1) *p1 = (uint64_t)(uintptr_t)(s->pose1[g].p + first);
     if (count) *count = (int)(hi - lo);
     if (rec_bytes) *rec_bytes = (int)sizeof(double4);
     return VX_OK;
@@ -1391,6 +1672,11 @@ __global__ void k_halo_import(double4* pose0, double4* pose1, const double4* src
 
 int vx_halo_import(vx_sim* s, int iz, uint64_t src0, uint64_t src1, int count)
 {
+    return vx_halo_import_on(s, iz, src0, src1, count, s ? (uint64_t)(uintptr_t)s->stream : 0);
+}
+
+int vx_halo_import_on(vx_sim* s, int iz, uint64_t src0, uint64_t src1, int count, uint64_t stream)
+{
     if (!s || !src0 || !src1) return VX_ERR_ARG;
     uint64_t p0, p1; int n, rb;
     int rc = vx_pose_plane(s, iz, &p0, &p1, &n, &rb);
@@ -1398,7 +1684,7 @@ int vx_halo_import(vx_sim* s, int iz, uint64_t src0, uint64_t src1, int count)
     if (n != count) return fail(s, VX_ERR_ARG, "halo layer size mismatch");
     if (n == 0) return VX_OK;
     CK(cudaSetDevice(s->device));
-    k_halo_import<<<blocks_for(n), TPB, 0, s->stream>>>((double4*)(uintptr_t)p0, (double4*)(uintptr_t)p1,
+    k_halo_import<<<blocks_for(n), TPB, 0, (cudaStream_t)(uintptr_t)stream>>>((double4*)(uintptr_t)p0, (double4*)(uintptr_t)p1,
                                                        (const double4*)(uintptr_t)src0, (const double4*)(uintptr_t)src1, n);
     s->launches++;
     CK(cudaGetLastError());

@@ -672,14 +672,16 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <bool UNI>
 __global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
-k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz)
+k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book)
 {
+    // nbz layers of brick groups starting at layer gz_off (a whole step: all of them, gz_off = 0);
+    // book: this launch does the step bookkeeping (exactly one launch per step does)
     extern __shared__ __align__(16) unsigned char wb_smem[];
     DevParams* p = f.params;
     const int frozen = p->div_flag[parity ^ 1] | p->div_latched;
     const float dt = p->dt;
     const float prev_dt = first_of_call ? p->prev_dt : dt;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (book && blockIdx.x == 0 && threadIdx.x == 0) {
         if (frozen) p->div_latched = 1;
         else if (p->pending) { p->steps_done += 1; p->time += dt; }
         if (!frozen) p->pending = 1;
@@ -697,7 +699,7 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
     const int w8 = b & 7; b >>= 3;
     const int gx = b % nbx; b /= nbx;
     const int gy = b % nby; b /= nby;
-    const int gz = b % nbz; const int member = b / nbz;
+    const int gz = gz_off + b % nbz; const int member = b / nbz;
     const int x0 = (gx * 2 + (w8 & 1)) * VX_WB_X, y0 = (gy * 2 + ((w8 >> 1) & 1)) * VX_WB_Y, z0 = (gz * 2 + (w8 >> 2)) * VX_WB_Z;
     if (member * f.nz * f.nxy >= f.n_vox || x0 >= f.nx || y0 >= f.ny || z0 >= f.nz) return;            // whole warp
     const int vbase = member * f.nz * f.nxy;
@@ -846,7 +848,14 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
     vs.orient.w = s0.w; vs.orient.x = s1.x; vs.orient.y = s1.y; vs.orient.z = s1.z;
     vs.lin = mk3(__hiloint2double(q0.y, q0.x), __hiloint2double(q0.w, q0.z), __hiloint2double(q1.y, q1.x));
     vs.ang = mk3(__hiloint2double(q1.w, q1.z), __hiloint2double(q2.y, q2.x), __hiloint2double(q2.w, q2.z));
-    if (!(vs.bits & VM_GHOST)) {
+    if (vs.bits & VM_GHOST) {
+        // a ghost's pose and temperature arrive from the slab that owns the voxel (vx_halo_import, or the
+        // peer's k_halo_push straight into this array, possibly while this kernel runs): only the flag word,
+        // which carries the mode bits of the links this ghost owns, is ours to write
+        reinterpret_cast<uint32_t*>(&f.n_pose1[v].w)[1] = vs.bits;
+        return;
+    }
+    {
         const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
         const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
         voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext, dt, floor_on != 0);

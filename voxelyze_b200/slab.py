@@ -14,7 +14,7 @@ against an unsplit run.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 
@@ -80,7 +80,7 @@ class SlabRunner:
 
     def __init__(self, lib: VxLib, nx: int, ny: int, nz: int, rank: int, world: int, device: int = 0,
                  voxel_size: float = 0.005, tip_load: float = 1.0, material: Material = None, host_exchange: bool = False,
-                 path: int = 0):
+                 path: int = 0, overlap: bool = True, peer: bool = True):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = rank, world
@@ -107,6 +107,14 @@ class SlabRunner:
         self.sim, self.ijk = sim, ijk
         self.host_exchange = host_exchange
         self._bufs = None
+        # overlap the exchange with the interior of the step (device exchange on the fused lattice path only)
+        self.overlap = overlap and not host_exchange and world > 1 and path in (0, 5) and sim.active_path() == 2
+        self._comm = None
+        # peer-memory halo: boundary poses stored straight into the neighbours' ghost layers (CUDA IPC over NVLink),
+        # stepping loop in the library (vx_slab_step); falls back to NCCL send/recv when the mappings cannot be made
+        self.peer = False
+        if peer and self.overlap and dist.is_available() and dist.is_initialized():
+            self.peer = self._connect_peers()
 
     # ---- bookkeeping -------------------------------------------------------------------
     def global_counts(self):
@@ -131,6 +139,43 @@ class SlabRunner:
             dt = float(t.item())
         return dt
 
+    # ---- peer-memory halo ------------------------------------------------------------
+    def _connect_peers(self) -> bool:
+        import torch
+        from .capi import VxError
+        dist, sim, n = self.dist, self.sim, Sim.PEER_DESC_BYTES
+        mine = torch.zeros(2, n, dtype=torch.uint8)
+        if self.rank > 0:
+            mine[0] = torch.frombuffer(bytearray(sim.peer_export(self.z0 - 1, False)), dtype=torch.uint8)
+        if self.rank < self.world - 1:
+            mine[1] = torch.frombuffer(bytearray(sim.peer_export(self.z1, True)), dtype=torch.uint8)
+        everyone = [torch.empty(2, n, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
+        dist.all_gather(everyone, mine.cuda())
+        ok = 1
+        try:
+            if self.rank > 0:          # my first layer is the top ghost of the slab below
+                sim.peer_attach(self.z0, bytes(everyone[self.rank - 1][1].cpu().numpy()))
+            if self.rank < self.world - 1:
+                sim.peer_attach(self.z1 - 1, bytes(everyone[self.rank + 1][0].cpu().numpy()))
+        except VxError as e:
+            self.peer_error = str(e)
+            ok = 0
+        t = torch.tensor([ok], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            sim.peer_detach()
+            return False
+        return True
+
+    @staticmethod
+    def connect_local(runners):
+        """Wires the slabs of ONE process to each other (tests on a single GPU)."""
+        for lo, hi in zip(runners[:-1], runners[1:]):
+            hi.sim.peer_attach(hi.z0, lo.sim.peer_export(lo.z1, True))
+            lo.sim.peer_attach(lo.z1 - 1, hi.sim.peer_export(hi.z0 - 1, False))
+        for r in runners:
+            r.peer = True
+
     # ---- halo exchange -----------------------------------------------------------------
     def _neighbours(self):
         """(peer rank, layer I send, ghost layer I receive into)"""
@@ -141,7 +186,9 @@ class SlabRunner:
             out.append((self.rank + 1, self.z1 - 1, self.z1))
         return out
 
-    def _exchange_device(self):
+    def _exchange_device(self, import_stream: Optional[int] = None):
+        """Queues send/recv of the boundary pose planes and the ghost imports after the work already queued on
+        torch's current stream; import_stream: cudaStream_t the import kernels go to (None: the handle's)."""
         import torch
         dist = self.dist
         if self._bufs is None:
@@ -165,7 +212,7 @@ class SlabRunner:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         for recv_z, r0, r1 in imports:
-            self.sim.halo_import(recv_z, r0.data_ptr(), r1.data_ptr(), self.plane)
+            self.sim.halo_import(recv_z, r0.data_ptr(), r1.data_ptr(), self.plane, import_stream)
 
     def _exchange_host(self):
         import torch
@@ -189,13 +236,19 @@ class SlabRunner:
     def exchange(self):
         if self.world == 1:
             return
-        if self.host_exchange:
+        if self.peer:
+            self.sim.slab_exchange()
+        elif self.host_exchange:
             self._exchange_host()
         else:
             self._exchange_device()
 
     # ---- stepping ------------------------------------------------------------------------
     def step(self, dt: float, n: int):
+        if self.peer:
+            return self.sim.slab_step(dt, n)
+        if self.overlap:
+            return self._step_overlapped(dt, n)
         div = None
         for _ in range(n):
             d = self.sim.step(dt, 1)
@@ -204,11 +257,37 @@ class SlabRunner:
             self.exchange()
         return div
 
+    def _step_overlapped(self, dt: float, n: int):
+        """boundary layers first, halo push on a second stream, interior meanwhile.
+        The host never blocks inside the loop; the handle must run on torch's current stream (bench.py, tests)."""
+        import torch
+        main = torch.cuda.current_stream()
+        if self._comm is None:
+            self._comm = torch.cuda.Stream()
+            self.sim.set_stream(main.cuda_stream)
+        comm = self._comm
+        sim = self.sim
+        sim.step_begin(dt)
+        imported = None
+        for _ in range(n):
+            if imported is not None:
+                main.wait_event(imported)                 # the boundary part reads the ghost poses of the previous step
+            sim.step_enqueue(sim.PART_Z_BOUNDARY)
+            ready = torch.cuda.Event(); ready.record(main)
+            sim.step_enqueue(sim.PART_Z_INTERIOR)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                self._exchange_device(import_stream=comm.cuda_stream)
+                imported = torch.cuda.Event(); imported.record(comm)
+        if imported is not None:
+            main.wait_event(imported)
+        return sim.step_end()
+
     def step_profile(self, dt: float, n: int):
         tot, launches = None, None
         for _ in range(n):
             ms, ln = self.sim.step_profile(dt, 1)
-            self.exchange()
+            self.exchange()                              # un-overlapped here: the kernel is what is being timed
             tot = ms if tot is None else {k: tot[k] + ms[k] for k in ms}
             launches = ln if launches is None else [a + b for a, b in zip(launches, ln)]
         return tot, launches
@@ -226,3 +305,10 @@ class SlabRunner:
 
     def path_name(self) -> str:
         return f"{_path_name(self.sim)}, z-slab {self.rank}/{self.world} layers [{self.z0},{self.z1})"
+
+    def halo_name(self) -> str:
+        if self.peer:
+            return "peer stores into the neighbours' ghost layers over NVLink (CUDA IPC), overlapped with the interior part"
+        if self.overlap:
+            return "NCCL send/recv on a second stream, overlapped with the interior part"
+        return "host copies (gloo)" if self.host_exchange else "NCCL send/recv after the step"
