@@ -216,6 +216,10 @@ def main():
     own_vox, own_link = runner.local_counts()
     peak, peak_src = measured_hbm_peak()
     link_ms = kms["link"] / prof_steps
+    per_rank_ms = [link_ms]
+    if world > 1:                       # the slabs are coupled through the halo: the slowest GPU sets the pace
+        t = torch.zeros(world, device="cuda"); t[rank] = link_ms
+        dist.all_reduce(t); per_rank_ms = [round(float(x), 4) for x in t.tolist()]
     fused = kl[1] == 0                  # lattice path: the one kernel does the link AND the voxel updates
     launch_bytes = (B_LINK * own_link + (B_VOXEL * own_vox if fused else 0)) / max(kl[0] // prof_steps, 1)
     launch_ms = link_ms / max(kl[0] // prof_steps, 1)
@@ -224,7 +228,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": runner.dominant_kernel(), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(runner.dominant_kernel(), own_vox),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": launch_bytes, "launch_ms": launch_ms,
-                "launches_per_step": kl[0] // prof_steps,
+                "launches_per_step": kl[0] // prof_steps, **({"kernel_ms_per_rank": per_rank_ms} if world > 1 else {}),
                 "kernel_ms_per_step": {k: v / prof_steps for k, v in kms.items()},
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak,
                                "bytes_per_step": B_VOXEL * n_vox + B_LINK * n_link}}

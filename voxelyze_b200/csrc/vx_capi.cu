@@ -100,6 +100,8 @@ struct vx_sim {
         void* opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cudaIpcOpenMemHandle results (other-process peers)
     };
     std::vector<PeerLink> peers;
+    bool wb_opted_in = false;
+    bool push_in_kernel = false;        // set around the boundary launches of vx_slab_step
     DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
     int n_expect[2] = {0, 0};           // exchanges a neighbour on that side takes part in (0 or 1 per exchange)
     bool expect_side[2] = {false, false};
@@ -188,6 +190,13 @@ struct vx_sim {
         f.ext_idx = ext_idx.p; f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
         f.pair_lmat = pair_lmat.p; f.ext = ext_dev.p; f.params = params.p;
         f.vm0 = vm0; f.lm0 = lm0;
+        f.push_z[0] = f.push_z[1] = -1;
+        if (push_in_kernel) {
+            for (size_t k = 0; k < peers.size() && k < 2; k++) {
+                f.push_z[k] = (int)(peers[k].src_first / ((size_t)nx * ny));
+                f.push0[k] = peers[k].dst0[g ^ 1]; f.push1[k] = peers[k].dst1[g ^ 1];
+            }
+        }
         return f;
     }
     void drop_graph()
@@ -601,15 +610,24 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     const int nbz = ngz < 0 ? (s->nz + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z) : ngz;
     const long long bricks = (long long)nbx * nby * nbz * 8 * s->n_members;      // 2x2x2 groups of 4x4x2 bricks
     const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
-    static bool wb_opted_in = false;     // > 48 KB of dynamic shared memory needs a one-time opt-in per function
-    if (!wb_opted_in) {
-        cudaFuncSetAttribute(k_lattice_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
-        cudaFuncSetAttribute(k_lattice_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
-        wb_opted_in = true;
+    if (!s->wb_opted_in) {               // > 48 KB of dynamic shared memory needs a one-time opt-in per function and device
+        cudaFuncSetAttribute(k_lattice_warp<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+        cudaFuncSetAttribute(k_lattice_warp<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+        cudaFuncSetAttribute(k_lattice_warp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+        cudaFuncSetAttribute(k_lattice_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+        s->wb_opted_in = true;
     }
     if (grid > 0) {
-        if (s->uni) k_lattice_warp<true><<<(unsigned)grid, 32 * VX_WB_WARPS, VX_WB_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, nbx, nby, nbz, gz_off, book);
-        else k_lattice_warp<false><<<(unsigned)grid, 32 * VX_WB_WARPS, VX_WB_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, nbx, nby, nbz, gz_off, book);
+        const LatFrame f = s->lat_frame(g);
+        const int fl = s->floor_on ? 1 : 0;
+        const dim3 gr((unsigned)grid), bl(32 * VX_WB_WARPS);
+        if (s->push_in_kernel) {         // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
+            if (s->uni) k_lattice_warp<true, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book);
+            else k_lattice_warp<false, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book);
+        } else {
+            if (s->uni) k_lattice_warp<true, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book);
+            else k_lattice_warp<false, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book);
+        }
         s->launches++;
     }
 }
@@ -841,7 +859,11 @@ static int ensure_peer_state(vx_sim* s)
 {
     CK(cudaSetDevice(s->device));
     if (!s->peer_flags.p) { CK(s->peer_flags.alloc(4)); CK(cudaMemset(s->peer_flags.p, 0, 4 * sizeof(int))); }
-    if (!s->comm_stream) CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    if (!s->comm_stream) {             // highest priority: its few blocks must not queue behind the interior part's
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, greatest));
+    }
     if (!s->ev_boundary) CK(cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
     if (!s->ev_comm) CK(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
     return VX_OK;
@@ -910,15 +932,19 @@ static void peer_wait(vx_sim* s, cudaStream_t st)
     k_peer_wait<<<1, 1, 0, st>>>(s->peer_flags.p, s->expect_side[0] ? s->xseq : 0, s->expect_side[1] ? s->xseq : 0, s->peer_flags.p + 2);
     s->launches++;
 }
-// queue: ship generation g of my boundary layers and signal (comm stream)
-static void peer_push(vx_sim* s, int g)
+// queue on the comm stream: ship generation g of my boundary layers (unless the step kernel already stored
+// them into the neighbours' ghost layers itself) and signal
+static void peer_push(vx_sim* s, int g, bool already_stored)
 {
     s->xseq++;
     for (auto& pl : s->peers) {
-        k_halo_push<<<blocks_for((long long)pl.count), TPB, 0, s->comm_stream>>>(s->pose0[g].p + pl.src_first, s->pose1[g].p + pl.src_first,
-                                                                                 pl.dst0[g], pl.dst1[g], (int)pl.count);
+        if (!already_stored) {
+            k_halo_push<<<blocks_for((long long)pl.count), TPB, 0, s->comm_stream>>>(s->pose0[g].p + pl.src_first, s->pose1[g].p + pl.src_first,
+                                                                                     pl.dst0[g], pl.dst1[g], (int)pl.count);
+            s->launches++;
+        }
         k_peer_signal<<<1, 1, 0, s->comm_stream>>>(pl.dst_flag, s->xseq);
-        s->launches += 2;
+        s->launches++;
     }
 }
 static int peer_check(vx_sim* s)
@@ -934,7 +960,7 @@ int vx_slab_exchange(vx_sim* s)
     int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
     CK(cudaEventRecord(s->ev_boundary, s->stream));
     CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
-    peer_push(s, s->gen);
+    peer_push(s, s->gen, false);
     CK(cudaStreamSynchronize(s->comm_stream));       // delivered; the neighbours' deliveries are awaited by the next vx_slab_step
     return VX_OK;
 }
@@ -947,11 +973,15 @@ int vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     rc = vx_step_begin(s, dt); if (rc != VX_OK) return rc;
     for (int k = 0; k < n_steps; k++) {
         peer_wait(s, s->stream);                            // the boundary part reads the ghosts of the previous exchange
-        rc = vx_step_enqueue(s, VX_PART_Z_BOUNDARY); if (rc != VX_OK) return rc;
+        s->push_in_kernel = s->peers.size() <= 2;          // the boundary kernels store into the neighbours' ghost layers themselves
+        const bool fused = s->push_in_kernel;
+        rc = vx_step_enqueue(s, VX_PART_Z_BOUNDARY);
+        s->push_in_kernel = false;
+        if (rc != VX_OK) return rc;
         CK(cudaEventRecord(s->ev_boundary, s->stream));
         rc = vx_step_enqueue(s, VX_PART_Z_INTERIOR); if (rc != VX_OK) return rc;
         CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
-        peer_push(s, s->newest_gen());
+        peer_push(s, s->newest_gen(), fused);
     }
     CK(cudaEventRecord(s->ev_comm, s->comm_stream));
     CK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));

@@ -43,6 +43,9 @@ struct LatFrame {
     const DevExt* ext;
     DevParams* params;
     DevVoxMat vm0; DevLinkMat lm0;  // single-material models: rows in the constant bank (UNI)
+    // z-slab runs (k_lattice_warp only): voxels of plane push_z[k] also store their new pose into the ghost
+    // plane of the neighbouring slab, push0/1[k] = that plane in the neighbour's pose0/pose1 arrays (peer memory)
+    int push_z[2]; double4* push0[2]; double4* push1[2];
 };
 
 __device__ __forceinline__ void lat_decode(double2 a, double2 b, double2 c, float4 s, uint32_t lflags, LinkState& st)
@@ -670,7 +673,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool UNI>
+template <bool UNI, bool PUSH>
 __global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
 k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book)
 {
@@ -864,6 +867,17 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
     f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
     f.n_mom0[v] = make_double4(vs.lin.x, vs.lin.y, vs.lin.z, vs.ang.x);
     f.n_mom1[v] = make_double2(vs.ang.y, vs.ang.z);
+    // halo push fused into the step: posted stores over NVLink; the receiver owns the upper half of pose1.w
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (PUSH && z == f.push_z[k]) {
+            const int q = y * f.nx + x;
+            f.push0[k][q] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
+            double* d = reinterpret_cast<double*>(f.push1[k] + q);
+            d[0] = vs.orient.x; d[1] = vs.orient.y; d[2] = vs.orient.z;
+            reinterpret_cast<float*>(d + 3)[0] = vs.temp;
+        }
+    }
 }
 
 } // namespace vxd
