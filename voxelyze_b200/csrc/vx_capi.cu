@@ -606,9 +606,12 @@ static int ensure_graph(vx_sim* s)
 // default fused kernel over the brick-group layers [gz_off, gz_off + ngz) (ngz < 0: all)
 static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off, int ngz, int book)
 {
-    const int nbx = (s->nx + 2 * VX_WB_X - 1) / (2 * VX_WB_X), nby = (s->ny + 2 * VX_WB_Y - 1) / (2 * VX_WB_Y);
-    const int nbz = ngz < 0 ? (s->nz + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z) : ngz;
-    const long long bricks = (long long)nbx * nby * nbz * 8 * s->n_members;      // 2x2x2 groups of 4x4x2 bricks
+    const int bx = (s->nx + VX_WB_X - 1) / VX_WB_X, by = (s->ny + VX_WB_Y - 1) / VX_WB_Y, bz = (s->nz + VX_WB_Z - 1) / VX_WB_Z;
+    const int gx = (bx + 1) / 2, gy = (by + 1) / 2, gz = (bz + 1) / 2;
+    // 2x2x2 groups of bricks unless their padding would waste more than a tenth of the warps (small boxes)
+    const bool grouped = ngz >= 0 || (double)gx * gy * gz * 8 <= 1.1 * (double)bx * by * bz;
+    const int nbx = grouped ? gx : bx, nby = grouped ? gy : by, nbz = ngz >= 0 ? ngz : (grouped ? gz : bz);
+    const long long bricks = (long long)nbx * nby * nbz * (grouped ? 8 : 1) * s->n_members;
     const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
     if (!s->wb_opted_in) {               // > 48 KB of dynamic shared memory needs a one-time opt-in per function and device
         cudaFuncSetAttribute(k_lattice_warp<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
@@ -622,11 +625,11 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
         const int fl = s->floor_on ? 1 : 0;
         const dim3 gr((unsigned)grid), bl(32 * VX_WB_WARPS);
         if (s->push_in_kernel) {         // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
-            if (s->uni) k_lattice_warp<true, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book);
-            else k_lattice_warp<false, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book);
+            if (s->uni) k_lattice_warp<true, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, grouped ? 1 : 0);
+            else k_lattice_warp<false, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, grouped ? 1 : 0);
         } else {
-            if (s->uni) k_lattice_warp<true, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book);
-            else k_lattice_warp<false, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book);
+            if (s->uni) k_lattice_warp<true, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, grouped ? 1 : 0);
+            else k_lattice_warp<false, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, grouped ? 1 : 0);
         }
         s->launches++;
     }

@@ -675,10 +675,12 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <bool UNI, bool PUSH>
 __global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
-k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book)
+k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book, int grouped)
 {
-    // nbz layers of brick groups starting at layer gz_off (a whole step: all of them, gz_off = 0);
-    // book: this launch does the step bookkeeping (exactly one launch per step does)
+    // grouped: nbx x nby x nbz counts 2x2x2 GROUPS of bricks, nbz layers of them starting at layer gz_off (a whole
+    //          step: all layers, gz_off = 0); good L1/L2 locality on large lattices, pads odd brick counts
+    // else:    nbx x nby x nbz counts bricks, x fastest, no padding (ensembles of small boxes)
+    // book:    this launch does the step bookkeeping (exactly one launch per step does)
     extern __shared__ __align__(16) unsigned char wb_smem[];
     DevParams* p = f.params;
     const int frozen = p->div_flag[parity ^ 1] | p->div_latched;
@@ -699,11 +701,13 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
 
     // warp -> brick: consecutive ids walk a 2x2x2 group of bricks, groups x-fastest
     int b = blockIdx.x * VX_WB_WARPS + warp;
-    const int w8 = b & 7; b >>= 3;
+    const int w8 = grouped ? b & 7 : 0;
+    if (grouped) b >>= 3;
     const int gx = b % nbx; b /= nbx;
     const int gy = b % nby; b /= nby;
     const int gz = gz_off + b % nbz; const int member = b / nbz;
-    const int x0 = (gx * 2 + (w8 & 1)) * VX_WB_X, y0 = (gy * 2 + ((w8 >> 1) & 1)) * VX_WB_Y, z0 = (gz * 2 + (w8 >> 2)) * VX_WB_Z;
+    const int x0 = grouped ? (gx * 2 + (w8 & 1)) * VX_WB_X : gx * VX_WB_X, y0 = grouped ? (gy * 2 + ((w8 >> 1) & 1)) * VX_WB_Y : gy * VX_WB_Y,
+              z0 = grouped ? (gz * 2 + (w8 >> 2)) * VX_WB_Z : gz * VX_WB_Z;
     if (member * f.nz * f.nxy >= f.n_vox || x0 >= f.nx || y0 >= f.ny || z0 >= f.nz) return;            // whole warp
     const int vbase = member * f.nz * f.nxy;
 
