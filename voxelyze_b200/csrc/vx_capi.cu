@@ -100,7 +100,7 @@ struct vx_sim {
         void* opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cudaIpcOpenMemHandle results (other-process peers)
     };
     std::vector<PeerLink> peers;
-    bool wb_opted_in = false;
+    bool wb_opted_in = false, zm_opted_in = false;
     bool push_in_kernel = false;        // set around the boundary launches of vx_slab_step
     DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
     int n_expect[2] = {0, 0};           // exchanges a neighbour on that side takes part in (0 or 1 per exchange)
@@ -640,6 +640,17 @@ static void launch_lattice(vx_sim* s, int g, int first_of_call)
     if (s->path == 3) {                  // ablation: one thread per voxel, all six links re-evaluated
         if (s->uni) k_lattice_step<true><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
         else k_lattice_step<false><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
+    } else if (s->path == 6) {           // marching warp bricks: 3.5 link evaluations per voxel
+        const int ncx = (s->nx + VX_WB_X - 1) / VX_WB_X, ncy = (s->ny + VX_WB_Y - 1) / VX_WB_Y, ncz = (s->nz + 4 * VX_ZM_PAIRS - 1) / (4 * VX_ZM_PAIRS);
+        const long long warps = (long long)ncx * ncy * ncz * s->n_members;
+        const long long grid = (warps + VX_ZM_WARPS - 1) / VX_ZM_WARPS;
+        if (!s->zm_opted_in) {
+            cudaFuncSetAttribute(k_lattice_zmarch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_ZM_SMEM);
+            cudaFuncSetAttribute(k_lattice_zmarch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_ZM_SMEM);
+            s->zm_opted_in = true;
+        }
+        if (s->uni) k_lattice_zmarch<true><<<(unsigned)grid, 32 * VX_ZM_WARPS, VX_ZM_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ncx, ncy, ncz);
+        else k_lattice_zmarch<false><<<(unsigned)grid, 32 * VX_ZM_WARPS, VX_ZM_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ncx, ncy, ncz);
     } else if (s->path != 2 && s->path != 4) {   // default: one warp per 4x4x2 brick, no block barriers
         launch_lattice_warp(s, g, first_of_call, 0, -1, 1);
         return;
@@ -1736,6 +1747,7 @@ const char* vx_kernel_name(const vx_sim* s)
     case 2: return "k_lattice_tile (fused link+voxel, 8x4x4 brick per block, 1 launch per step)";
     case 3: return "k_lattice_step (fused link+voxel, one thread per voxel, 1 launch per step)";
     case 4: return "k_lattice_march (fused link+voxel, z-marching columns, 1 launch per step)";
+    case 6: return "k_lattice_zmarch (fused link+voxel, 4x4 column per warp marching in z, 1 launch per step)";
     default: return "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, 1 launch per step)";
     }
 }

@@ -884,4 +884,279 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
     }
 }
 
+
+// =================================================================================================
+// k_lattice_zmarch -- the warp-brick step, marching.  One warp owns a 4 x 4 column of the lattice and walks
+// up a chunk of it two bricks (A below, B above; 4 planes) at a time.
+//   * The force a brick's top layer exerts on the layer above is computed once, by the brick below, and
+//     carried over in shared memory (zslot): no -Z entering links are re-evaluated (only once per chunk).
+//   * The -X / -Y entering links of A and of B (2 x 16) fill ONE round H of 32 lanes.
+//   -> 7 rounds of link evaluations per 64 voxels = 3.5 per voxel (warp bricks: 4.0), all lanes busy.
+//   * Everything is requested with cp.async one round before it is read: the payload of round k+1 (link
+//     records or momenta) goes into the window round k-1 has left; poses of brick B, of the next A and
+//     of the next B's -X/-Y faces go into regions of the pose table as they fall free.  Only the 32 outside
+//     poses of round H are waited for (once per 64 voxels).
+// Shared memory per warp: 2 windows x 2 KB + 96 poses x 64 B + hslot 1.5 KB + zslot 2 x 768 B = 13 312 B.
+// Pose table regions: OA 0..31 own poses of A | HB 32..63 outside poses of round H, then own poses of B |
+//                     EB 64..79 B's x=0 / y=0 voxels for round H, then the poses beyond B's +X/+Y faces |
+//                     EA 80..95 the poses beyond A's +X/+Y faces.
+// =================================================================================================
+#define VX_ZM_WARPS 8
+#define VX_ZM_POSES 96
+#ifndef VX_ZM_PAIRS
+#define VX_ZM_PAIRS 8                                   // brick pairs per warp: 32 planes
+#endif
+#define VX_ZM_WARP_BYTES (2 * 4 * 32 * 16 + 4 * VX_ZM_POSES * 16 + 6 * 32 * 8 + 2 * 6 * 16 * 8)
+#define VX_ZM_SMEM (VX_ZM_WARPS * VX_ZM_WARP_BYTES)
+
+template <bool UNI>
+__global__ void __launch_bounds__(32 * VX_ZM_WARPS, 2)
+k_lattice_zmarch(LatFrame f, int parity, int first_of_call, int floor_on, int ncx, int ncy, int ncz)
+{
+    extern __shared__ __align__(16) unsigned char wb_smem[];
+    DevParams* p = f.params;
+    const int frozen = p->div_flag[parity ^ 1] | p->div_latched;
+    const float dt = p->dt;
+    const float prev_dt = first_of_call ? p->prev_dt : dt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (frozen) p->div_latched = 1;
+        else if (p->pending) { p->steps_done += 1; p->time += dt; }
+        if (!frozen) p->pending = 1;
+    }
+    if (frozen) return;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = wb_smem + (size_t)warp * VX_ZM_WARP_BYTES;
+    uint4 (*win)[4][32] = reinterpret_cast<uint4 (*)[4][32]>(wbase);                                      // [window][part][lane]
+    uint4 (*pose_sh)[VX_ZM_POSES] = reinterpret_cast<uint4 (*)[VX_ZM_POSES]>(wbase + 4096);               // [part][entry]
+    double (*hslot)[32] = reinterpret_cast<double (*)[32]>(wbase + 4096 + 4 * VX_ZM_POSES * 16);          // [comp][entering link]
+    double (*zslot)[6][16] = reinterpret_cast<double (*)[6][16]>(wbase + 4096 + 4 * VX_ZM_POSES * 16 + 1536);   // [ping][comp][x + 4 y]
+    constexpr int OA = 0, HB = 32, EB = 64, EA = 80;
+
+    int b = blockIdx.x * VX_ZM_WARPS + warp;
+    const int cx = b % ncx; b /= ncx;
+    const int cy = b % ncy; b /= ncy;
+    const int cz = b % ncz; const int member = b / ncz;
+    const int x0 = cx * VX_WB_X, y0 = cy * VX_WB_Y;
+    const int z_begin = cz * (4 * VX_ZM_PAIRS), z_end = min(f.nz, z_begin + 4 * VX_ZM_PAIRS);
+    if ((size_t)member * f.nz * f.nxy >= (size_t)f.n_vox) return;
+    const int vbase = member * f.nz * f.nxy;
+
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    const int x = x0 + lx, y = y0 + ly;
+    const bool xy_ok = x < f.nx && y < f.ny;
+    const int vxy = vbase + min(y, f.ny - 1) * f.nx + min(x, f.nx - 1);
+    auto vox = [&](int z) { return vxy + min(z, f.nz - 1) * f.nxy; };                // clamped: idle lanes address valid memory
+
+    auto c_rec = [&](int a, int k) { return f.c_rec[0][0] + (size_t)(a * 3 + k) * f.n_vox; };
+    auto c_recf = [&](int a) { return f.c_recf[0] + (size_t)a * f.n_vox; };
+    auto request_pose = [&](int entry, int v) {
+        cp_async16(&pose_sh[0][entry], reinterpret_cast<const uint4*>(f.c_pose0 + v));
+        cp_async16(&pose_sh[1][entry], reinterpret_cast<const uint4*>(f.c_pose0 + v) + 1);
+        cp_async16(&pose_sh[2][entry], reinterpret_cast<const uint4*>(f.c_pose1 + v));
+        cp_async16(&pose_sh[3][entry], reinterpret_cast<const uint4*>(f.c_pose1 + v) + 1);
+    };
+    auto load_pose = [&](int entry, double4& a, double4& c) {
+        const uint4 e0 = pose_sh[0][entry], e1 = pose_sh[1][entry], e2 = pose_sh[2][entry], e3 = pose_sh[3][entry];
+        a = make_double4(__hiloint2double(e0.y, e0.x), __hiloint2double(e0.w, e0.z), __hiloint2double(e1.y, e1.x), __hiloint2double(e1.w, e1.z));
+        c = make_double4(__hiloint2double(e2.y, e2.x), __hiloint2double(e2.w, e2.z), __hiloint2double(e3.y, e3.x), __hiloint2double(e3.w, e3.z));
+    };
+    auto request_rec = [&](int w, int a, int owner) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) cp_async16(&win[w][k][lane], c_rec(a, k) + owner);
+        cp_async16(&win[w][3][lane], c_recf(a) + owner);
+    };
+    // own poses of the brick at z0 -> region `own`; the poses beyond its +X / +Y faces -> region `ext`
+    auto request_own = [&](int own, int z0) { if (z0 < f.nz) request_pose(own + lane, vox(z0 + lz)); };
+    auto request_ext = [&](int ext, int z0) {
+        if (!xy_ok || z0 + lz >= f.nz) return;
+        if (lx == VX_WB_X - 1 && x + 1 < f.nx) request_pose(ext + ly + 4 * lz, vox(z0 + lz) + 1);
+        if (ly == VX_WB_Y - 1 && y + 1 < f.ny) request_pose(ext + 8 + lx + 4 * lz, vox(z0 + lz) + f.nx);
+    };
+    // round H: lanes 0..15 serve brick A, 16..31 brick B; q < 8: the link through -X into voxel (0, q&3, q>>2), else through -Y into ((q-8)&3, 0, (q-8)>>2)
+    const int hq = lane & 15, hb = lane >> 4;
+    const int h_axis = hq < 8 ? 0 : 1;
+    const int h_tl = hq < 8 ? ((hq >> 2) << 4) | ((hq & 3) << 2) : (((hq - 8) >> 2) << 4) | ((hq - 8) & 3);
+    const bool h_xy = x0 + (h_tl & 3) < f.nx && y0 + ((h_tl >> 2) & 3) < f.ny && (h_axis == 0 ? x0 : y0) > 0;
+    const int h_vxy = vbase + (y0 + ((h_tl >> 2) & 3)) * f.nx + x0 + (h_tl & 3) - (h_axis == 0 ? 1 : f.nx);   // negative-end voxel, plane 0
+    // B's x = 0 / y = 0 voxels (targets of B's entering links) -> EB 0..15; requested by lanes 16..31 for themselves
+    auto request_h_targets = [&](int zB) {
+        if (hb == 1 && h_xy && zB + (h_tl >> 4) < f.nz) request_pose(EB + hq, h_vxy + (h_axis == 0 ? 1 : f.nx) + (zB + (h_tl >> 4)) * f.nxy);
+    };
+    auto request_h = [&](int w, int zp) {                              // outside poses -> HB, records -> window w
+        const int z = zp + 2 * hb + (h_tl >> 4);
+        if (h_xy && z < f.nz) { request_pose(HB + lane, h_vxy + z * f.nxy); request_rec(w, h_axis, h_vxy + z * f.nxy); }
+    };
+    auto request_h_rec = [&](int w, int zp) {
+        const int z = zp + 2 * hb + (h_tl >> 4);
+        if (h_xy && z < f.nz) request_rec(w, h_axis, h_vxy + z * f.nxy);
+    };
+
+    // ---- chunk prologue
+    int r = 0;                                   // round counter: round r reads window r & 1
+    int kb = 0;                                  // bricks done: brick kb takes its -Z forces from zslot[kb & 1], leaves its +Z forces in zslot[(kb + 1) & 1]
+    int zp = z_begin;
+    int mode = z_begin > 0 ? 0 : 1;              // 0: the 16 links entering the chunk from below still have to be evaluated
+    request_own(OA, zp); request_ext(EA, zp); request_h_targets(zp + 2);
+    if (mode == 0) {
+        if (lane < 16 && xy_ok) { request_pose(HB + lane, vox(zp) - f.nxy); request_rec(0, 2, vox(zp) - f.nxy); }   // lane = (lx, ly) of the bottom layer
+    } else request_h_rec(0, zp);
+    cp_async_commit();
+
+#pragma unroll 1
+    while (zp < z_end) {
+        // ================= entering links: round ZH (chunk start only) or round H of this pair
+        if (mode == 0) request_h_rec(1, zp);
+        else {
+            const int z = zp + 2 * hb + (h_tl >> 4);
+            if (h_xy && z < f.nz) request_pose(HB + lane, h_vxy + z * f.nxy);
+            if (xy_ok && zp + lz < f.nz && x + 1 < f.nx) request_rec((r + 1) & 1, 0, vox(zp + lz));      // payload of A's round 0
+        }
+        cp_async_commit();
+        if (mode == 0) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
+        {
+            int axis, tgt_entry; bool act; double* dst; int dst_stride;
+            if (mode == 0) {
+                axis = 2; tgt_entry = OA + lane; act = lane < 16 && xy_ok;
+                dst = &zslot[0][0][lane & 15]; dst_stride = 16;
+            } else {
+                axis = h_axis; tgt_entry = hb ? EB + hq : OA + h_tl; act = h_xy && zp + 2 * hb + (h_tl >> 4) < f.nz;
+                dst = &hslot[0][lane]; dst_stride = 32;
+            }
+            if (act && ((pose_sh[3][tgt_entry].w >> (VM_LINK_SHIFT + 2 * axis + 1)) & 1u)) {
+                double4 n0, n1, p0, p1;
+                load_pose(HB + lane, n0, n1);
+                load_pose(tgt_entry, p0, p1);
+                const uint4 r0 = win[r & 1][0][lane], r1 = win[r & 1][1][lane], r2 = win[r & 1][2][lane], r3 = win[r & 1][3][lane];
+                LinkState st; d3 fN, mN, fP, mP;
+                lat_eval_link_rec<UNI>(f, axis, meta_hi(n1.w),
+                                       make_double2(__hiloint2double(r0.y, r0.x), __hiloint2double(r0.w, r0.z)),
+                                       make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
+                                       make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
+                                       make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
+                                       n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
+                dst[0] = fP.x; dst[dst_stride] = fP.y; dst[2 * dst_stride] = fP.z; dst[3 * dst_stride] = mP.x; dst[4 * dst_stride] = mP.y; dst[5 * dst_stride] = mP.z;
+            }
+        }
+        __syncwarp();
+        r++;
+        if (mode == 0) { mode = 1; continue; }
+
+        // ================= bricks A (h = 0) and B (h = 1): rounds 0..2 = own +X/+Y/+Z links, round 3 = voxels
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int z0 = zp + 2 * h;
+            const int own = h ? HB : OA, ext = h ? EB : EA;
+            const int z = z0 + lz;
+            const bool has_voxel = xy_ok && z < f.nz;
+            const int v = vox(z);
+            uint32_t bits = 0, mask = 0, new_bits = 0;
+            d3 F = mk3(0.0, 0.0, 0.0), M = mk3(0.0, 0.0, 0.0);
+#pragma unroll 1
+            for (int a = 0; a < 4; a++) {
+                // ---- requests: the payload of the next round, and poses into regions that have just fallen free
+                const int wn = (r + 1) & 1;
+                if (a < 2) { if (has_voxel && (a == 0 ? y + 1 < f.ny : z + 1 < f.nz)) request_rec(wn, a + 1, v); }
+                else if (a == 2) {
+                    if (has_voxel) {
+                        cp_async16(&win[wn][0][lane], reinterpret_cast<const uint4*>(f.c_mom0 + v));
+                        cp_async16(&win[wn][1][lane], reinterpret_cast<const uint4*>(f.c_mom0 + v) + 1);
+                        cp_async16(&win[wn][2][lane], reinterpret_cast<const uint4*>(f.c_mom1 + v));
+                    }
+                } else if (h == 0) { if (xy_ok && z + 2 < f.nz && x + 1 < f.nx) request_rec(wn, 0, vox(z + 2)); }     // B's round 0
+                else if (zp + 4 < z_end) request_h_rec(wn, zp + 4);                                              // the next pair's round H
+                if (h == 0 && a == 0) { request_own(HB, zp + 2); request_ext(EB, zp + 2); }                    // round H has left HB and EB
+                if (h == 1 && a == 0 && zp + 4 < f.nz) { request_own(OA, zp + 4); request_ext(EA, zp + 4); }   // A is done with OA and EA
+                if (h == 1 && a == 2 && zp + 4 < z_end) request_h_targets(zp + 6);                               // B's round 1 was the last reader of EB
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+
+                if (a == 0) {
+                    bits = pose_sh[3][own + lane].w;
+                    mask = has_voxel ? ((bits >> VM_LINK_SHIFT) & 0x3Fu) : 0u;
+                    new_bits = bits;
+                }
+                if (a < 3) {
+                    const bool inside = a == 0 ? lx < VX_WB_X - 1 : (a == 1 ? ly < VX_WB_Y - 1 : lz < VX_WB_Z - 1);
+                    const bool first = a == 0 ? lx == 0 : (a == 1 ? ly == 0 : lz == 0);
+                    const int dl = a == 0 ? 1 : (a == 1 ? 4 : 16);
+                    d3 fN = mk3(0.0, 0.0, 0.0), mN = fN, fP = fN, mP = fN;
+                    if ((mask >> (2 * a)) & 1u) {
+                        // partner: inside the brick, beyond its +X/+Y face, or (a == 2, top layer) the bottom layer of the brick above
+                        const int pe = inside ? own + lane + dl : (a == 0 ? ext + ly + 4 * lz : (a == 1 ? ext + 8 + lx + 4 * lz : (h ? OA : HB) + lane - 16));
+                        double4 n0, n1, p0, p1;
+                        load_pose(own + lane, n0, n1);
+                        load_pose(pe, p0, p1);
+                        const uint4 r0 = win[r & 1][0][lane], r1 = win[r & 1][1][lane], r2 = win[r & 1][2][lane], r3 = win[r & 1][3][lane];
+                        LinkState st;
+                        lat_eval_link_rec<UNI>(f, a, bits,
+                                               make_double2(__hiloint2double(r0.y, r0.x), __hiloint2double(r0.w, r0.z)),
+                                               make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
+                                               make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
+                                               make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
+                                               n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
+                        double2 wa, wb, wc; float4 ws; uint32_t lf;
+                        lat_encode(st, wa, wb, wc, ws, lf);
+                        double2* nr = f.n_rec[0][0] + (size_t)(a * 3) * f.n_vox + v;
+                        nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; (f.n_recf[0] + (size_t)a * f.n_vox)[v] = ws;
+                        new_bits = (new_bits & ~(3u << (VM_LFLAG_SHIFT + 2 * a))) | (lf << (VM_LFLAG_SHIFT + 2 * a));
+                        if (st.strain > 100) p->div_flag[parity] = 1;          // src/Voxelyze.cpp:265
+                        F = F + fN; M = M + mN;
+                        if (a == 2 && lz == 1) {                               // carried to the brick above
+                            double (*zs)[16] = zslot[(kb + 1) & 1];
+                            const int q = lane - 16;
+                            zs[0][q] = fP.x; zs[1][q] = fP.y; zs[2][q] = fP.z; zs[3][q] = mP.x; zs[4][q] = mP.y; zs[5][q] = mP.z;
+                        }
+                    }
+                    const int src = (lane - dl) & 31;
+                    d3 inF = mk3(__shfl_sync(0xffffffffu, fP.x, src), __shfl_sync(0xffffffffu, fP.y, src), __shfl_sync(0xffffffffu, fP.z, src));
+                    d3 inM = mk3(__shfl_sync(0xffffffffu, mP.x, src), __shfl_sync(0xffffffffu, mP.y, src), __shfl_sync(0xffffffffu, mP.z, src));
+                    if ((mask >> (2 * a + 1)) & 1u) {
+                        if (first) {
+                            if (a < 2) {
+                                const int hl = 16 * h + (a == 0 ? ly + 4 * lz : 8 + lx + 4 * lz);
+                                inF = mk3(hslot[0][hl], hslot[1][hl], hslot[2][hl]);
+                                inM = mk3(hslot[3][hl], hslot[4][hl], hslot[5][hl]);
+                            } else {
+                                double (*zs)[16] = zslot[kb & 1];
+                                inF = mk3(zs[0][lane], zs[1][lane], zs[2][lane]);
+                                inM = mk3(zs[3][lane], zs[4][lane], zs[5][lane]);
+                            }
+                        }
+                        F = F + inF; M = M + inM;
+                    }
+                } else if (has_voxel) {
+                    // ---- round 3: one lane per voxel
+                    const uint4 q0 = win[r & 1][0][lane], q1 = win[r & 1][1][lane], q2 = win[r & 1][2][lane];
+                    double4 s0, s1;
+                    load_pose(own + lane, s0, s1);
+                    VoxelState vs;
+                    vs.bits = new_bits; vs.temp = meta_temp(s1.w);
+                    if (vs.bits & VM_GHOST) reinterpret_cast<uint32_t*>(&f.n_pose1[v].w)[1] = vs.bits;      // see k_lattice_warp
+                    else {
+                        vs.pos = mk3(s0.x, s0.y, s0.z);
+                        vs.orient.w = s0.w; vs.orient.x = s1.x; vs.orient.y = s1.y; vs.orient.z = s1.z;
+                        vs.lin = mk3(__hiloint2double(q0.y, q0.x), __hiloint2double(q0.w, q0.z), __hiloint2double(q1.y, q1.x));
+                        vs.ang = mk3(__hiloint2double(q1.w, q1.z), __hiloint2double(q2.y, q2.x), __hiloint2double(q2.w, q2.z));
+                        const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
+                        const DevExt* ext_row = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
+                        voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext_row, dt, floor_on != 0);
+                        f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
+                        f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
+                        f.n_mom0[v] = make_double4(vs.lin.x, vs.lin.y, vs.lin.z, vs.ang.x);
+                        f.n_mom1[v] = make_double2(vs.ang.y, vs.ang.z);
+                    }
+                }
+                __syncwarp();
+                r++;
+            }
+            kb++;
+        }
+        zp += 4;
+    }
+    cp_async_wait<0>();
+}
+
 } // namespace vxd
