@@ -330,6 +330,14 @@ int  vx_sync(vx_sim* s);
  * else (Poisson pre-pass, collisions), ms[3] whole steps; launches[0..2] = kernel launches
  * per group.  Same arithmetic as vx_step.                                                 */
 int  vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches);
+/* dynamic-state checkpoint (the reference has none: saveJSON stores the initial configuration only,
+ * include/Voxelyze.h:78).  vx_save_state writes every time-dependent device array of the handle
+ * (voxel poses and momenta, link state, step bookkeeping) to a file; vx_load_state restores it
+ * into a handle that was built with the same materials, voxels, externals and options
+ * (VX_ERR_ARG otherwise) so that continuing is bit-identical to never having stopped.
+ * Collision watch lists are rebuilt at the next step.                                        */
+int  vx_save_state(vx_sim* s, const char* path);
+int  vx_load_state(vx_sim* s, const char* path);
 /* select kernel variant (tests and ablations; takes effect at the next vx_set_voxels):
  *   0 auto: fused lattice kernel for dense boxes without Poisson coupling or collisions,
  *           general path otherwise

@@ -412,6 +412,8 @@ int vx_peer_attach(vx_sim*, int, const vx_peer_desc*) { return VX_ERR_UNSUPPORTE
 int vx_peer_detach(vx_sim*) { return VX_ERR_UNSUPPORTED; }
 int vx_slab_step(vx_sim*, float, int, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_slab_exchange(vx_sim*) { return VX_ERR_UNSUPPORTED; }
+int vx_save_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
+int vx_load_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
 int64_t vx_launch_count(const vx_sim*) { return 0; }
 int vx_sync(vx_sim*) { return VX_OK; }
 int vx_set_path(vx_sim*, int) { return VX_OK; }

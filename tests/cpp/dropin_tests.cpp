@@ -14,6 +14,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -501,8 +502,109 @@ static void voxelExternals()            // tVX_Voxel.h:3-68
     CHECK_NEAR(vox.external()->rotationQuat().w, std::cos(0.125), 1e-15);
 }
 
+// ---- *.vxl.json (Voxelyze.cpp:61-241, VX_Material.cpp:75-163): a model with two materials and three kinds of
+// externals; written by one implementation, it must load into the same model in either.
+static void buildJsonModel(CVoxelyze& Vx)
+{
+    CVX_Material* a = Vx.addMaterial(1e6f, 1000.0f);
+    a->setName("soft"); a->setColor(200, 30, 40); a->setStaticFriction(0.7f); a->setKineticFriction(0.3f); a->setGlobalDamping(0.02f);
+    a->setCte(0.01f); a->setModelLinear(1e6f, 2e5f);
+    CVX_Material* b = Vx.addMaterial(5e6f, 1500.0f);
+    b->setPoissonsRatio(0.3f); b->setInternalDamping(0.8f); b->setCollisionDamping(0.5f); b->setExternalScaleFactor(Vec3D<double>(1.0, 1.25, 0.75));
+    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) for (int i = 0; i < 5; i++) Vx.setVoxel((i + j + k) % 3 == 0 ? b : a, i, j - 1, k + 3);
+    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) Vx.voxel(0, j - 1, k + 3)->external()->setFixedAll();
+    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) Vx.voxel(4, j - 1, k + 3)->external()->setForce(0.0f, 0.001f, -0.002f);
+    Vx.voxel(2, 0, 4)->external()->setDisplacement(Z_TRANSLATE, 1e-4);
+    Vx.voxel(2, 0, 4)->external()->setMoment(1e-6f, 0.0f, 0.0f);
+    Vx.setGravity(1.0f); Vx.enableFloor(true);
+}
+static void printJsonDigest(CVoxelyze& Vx)
+{
+    printf("voxelSize %.17g materials %d voxels %d\n", Vx.voxelSize(), Vx.materialCount(), Vx.voxelCount());
+    printf("env gravity %g floor %d collisions %d ambient %g\n", Vx.gravity(), (int)Vx.isFloorEnabled(), (int)Vx.isCollisionsEnabled(), Vx.ambientTemperature());
+    for (int i = 0; i < Vx.materialCount(); i++) {
+        CVX_Material* m = Vx.material(i);
+        printf("mat %d '%s' rgba %d %d %d %d linear %d E %.9g fail %.9g rho %.9g nu %.9g cte %.9g mu %.9g %.9g zeta %.9g %.9g %.9g scale %.17g %.17g %.17g\n", i, m->name(),
+               m->red(), m->green(), m->blue(), m->alpha(), (int)m->isModelLinear(), m->youngsModulus(), m->failureStress(), m->density(), m->poissonsRatio(), m->cte(),
+               m->staticFriction(), m->kineticFriction(), m->internalDamping(), m->globalDamping(), m->collisionDamping(),
+               m->externalScaleFactor().x, m->externalScaleFactor().y, m->externalScaleFactor().z);
+    }
+    for (int i = 0; i < Vx.voxelCount(); i++) {
+        CVX_Voxel* v = Vx.voxel(i);
+        int mi = -1;
+        for (int k = 0; k < Vx.materialCount(); k++) if (Vx.material(k) == v->material()) mi = k;
+        printf("vox %d at %d %d %d mat %d", i, v->indexX(), v->indexY(), v->indexZ(), mi);
+        if (v->externalExists() && !v->external()->isEmpty()) {
+            CVX_External* e = v->external();
+            printf(" fixed %d%d%d%d%d%d T %.17g %.17g %.17g R %.17g %.17g %.17g F %.9g %.9g %.9g M %.9g %.9g %.9g", (int)e->isFixed(X_TRANSLATE), (int)e->isFixed(Y_TRANSLATE),
+                   (int)e->isFixed(Z_TRANSLATE), (int)e->isFixed(X_ROTATE), (int)e->isFixed(Y_ROTATE), (int)e->isFixed(Z_ROTATE), e->translation().x, e->translation().y, e->translation().z,
+                   e->rotation().x, e->rotation().y, e->rotation().z, e->force().x, e->force().y, e->force().z, e->moment().x, e->moment().y, e->moment().z);
+        }
+        printf("\n");
+    }
+}
+static std::string g_tmpdir = "/tmp";
+static void jsonRoundTrip()             // Voxelyze.h:70,77-78: save, load into a second object, same model and same motion
+{
+    CVoxelyze A(0.002);
+    buildJsonModel(A);
+    std::string path = g_tmpdir + "/dropin_roundtrip.vxl.json";
+    CHECK(A.saveJSON(path.c_str()));
+    CVoxelyze B(path.c_str());
+    CHECK(B.voxelSize() == 0.002);
+    CHECK(B.materialCount() == 2); CHECK(B.voxelCount() == 20);
+    if (B.materialCount() != 2 || B.voxelCount() != 20) return;
+    CHECK(std::string(B.material(0)->name()) == "soft"); CHECK(B.material(0)->red() == 200);
+    CHECK_FLOAT_EQ(B.material(0)->failureStress(), 2e5f); CHECK_FLOAT_EQ(B.material(0)->cte(), 0.01f);
+    CHECK_FLOAT_EQ(B.material(1)->youngsModulus(), 5e6f); CHECK_FLOAT_EQ(B.material(1)->density(), 1500.0f);
+    CHECK_FLOAT_EQ(B.material(1)->poissonsRatio(), 0.3f); CHECK(B.material(1)->externalScaleFactor().y == 1.25);
+    for (int i = 0; i < 20; i++) {
+        CHECK(B.voxel(i)->indexX() == A.voxel(i)->indexX() && B.voxel(i)->indexY() == A.voxel(i)->indexY() && B.voxel(i)->indexZ() == A.voxel(i)->indexZ());
+        CHECK((B.voxel(i)->material() == B.material(0)) == (A.voxel(i)->material() == A.material(0)));
+    }
+    CHECK(B.voxel(0, -1, 3)->external()->isFixedAll());
+    CHECK_FLOAT_EQ(B.voxel(4, 0, 4)->external()->force().z, -0.002f);
+    CHECK(B.voxel(2, 0, 4)->external()->isFixed(Z_TRANSLATE) && !B.voxel(2, 0, 4)->external()->isFixed(X_TRANSLATE));
+    CHECK(B.voxel(2, 0, 4)->external()->translation().z == 1e-4);
+    CHECK_FLOAT_EQ(B.voxel(2, 0, 4)->external()->moment().x, 1e-6f);
+    CHECK(B.gravity() == 0.0f && !B.isFloorEnabled());      // written, never read back (Voxelyze.cpp:168-171 vs :95-161)
+    B.setGravity(1.0f); B.enableFloor(true);
+    float dt = A.recommendedTimeStep();
+    CHECK_FLOAT_EQ(B.recommendedTimeStep(), dt);
+    for (int i = 0; i < 300; i++) { A.doTimeStep(dt); B.doTimeStep(dt); }
+    for (int i = 0; i < 20; i++) {
+        CHECK(A.voxel(i)->position().x == B.voxel(i)->position().x && A.voxel(i)->position().y == B.voxel(i)->position().y && A.voxel(i)->position().z == B.voxel(i)->position().z);
+    }
+    CHECK(std::fabs(A.voxel(19)->position().z - 4 * 0.002) > 1e-7);    // it did move
+}
+
+#ifndef DROPIN_REFERENCE
+static void stateCheckpoint()           // facade extra: saveState / loadState (the reference cannot checkpoint, Voxelyze.h:78)
+{
+    std::string path = g_tmpdir + "/dropin_state.bin";
+    CVoxelyze A(0.002), B(0.002);
+    buildJsonModel(A); buildJsonModel(B);
+    float dt = A.recommendedTimeStep();
+    for (int i = 0; i < 150; i++) A.doTimeStep(dt);
+    CHECK(A.saveState(path.c_str()));
+    for (int i = 0; i < 100; i++) A.doTimeStep(dt);
+    CHECK(B.loadState(path.c_str()));
+    for (int i = 0; i < 100; i++) B.doTimeStep(dt);
+    for (int i = 0; i < 20; i++) {
+        CHECK(A.voxel(i)->position().x == B.voxel(i)->position().x && A.voxel(i)->position().z == B.voxel(i)->position().z);
+        CHECK(A.voxel(i)->velocity().z == B.voxel(i)->velocity().z);
+    }
+    CVoxelyze C(0.002);
+    C.setVoxel(C.addMaterial(), 0, 0, 0);
+    CHECK(!C.loadState(path.c_str()));                      // another model: refused
+}
+#endif
+
 int main(int argc, char** argv)
 {
+    if (const char* t = getenv("TMPDIR")) g_tmpdir = t;
+    if (argc > 2 && std::string(argv[1]) == "--json-save") { CVoxelyze Vx(0.002); buildJsonModel(Vx); return Vx.saveJSON(argv[2]) ? 0 : 1; }
+    if (argc > 2 && std::string(argv[1]) == "--json-digest") { CVoxelyze Vx(argv[2]); printJsonDigest(Vx); return 0; }
     struct T { const char* name; void (*fn)(); bool device; };
     const T tests[] = {
         {"materialModels", materialModels, false}, {"voxelExternals", voxelExternals, false},
@@ -512,7 +614,10 @@ int main(int argc, char** argv)
         {"doubleBondCantilever", doubleBondCantilever, true}, {"impulse", impulse, true}, {"multiMaterial", multiMaterial, true},
         {"deformableMaterial", deformableMaterial, true}, {"replaceMaterialMidRun", replaceMaterialMidRun, true},
         {"temperatureBimorph", temperatureBimorph, true}, {"staticFriction", staticFriction, true}, {"kineticFriction", kineticFriction, true},
-        {"collisionsHoldUp", collisionsHoldUp, true}, {"stateInfoBasics", stateInfoBasics, true},
+        {"collisionsHoldUp", collisionsHoldUp, true}, {"stateInfoBasics", stateInfoBasics, true}, {"jsonRoundTrip", jsonRoundTrip, true},
+#ifndef DROPIN_REFERENCE
+        {"stateCheckpoint", stateCheckpoint, true},
+#endif
     };
     bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
     int ran = 0;

@@ -361,3 +361,31 @@ def test_peer_memory_halo_steps_match_whole_steps_bitwise(product):
             r.step(dt, 1)
     got = np.concatenate([r.owned_state("pos") for r in runs])
     assert parity.bit_equal(got, whole.download("pos"))
+
+
+@pytest.mark.parametrize("case", ["cantilever", "plates", "robots"])
+def test_checkpoint_resume_is_bit_identical(product, tmp_path, case):
+    """vx_save_state / vx_load_state: stop, restore into a freshly built handle, continue == never stopped.
+    Lattice path (cantilever, ensemble with temperature) and general path with collisions and plastic links."""
+    sc = {"cantilever": lambda: scenarios.cantilever(14, 5, 6, tip_load=40.0),
+          "plates": lambda: scenarios.plate_stack(16, 8, 2, thick=3, gap=2, tip_load=1.0),
+          "robots": lambda: scenarios.robot_ensemble(5, 4)}[case]()
+    a = scenarios.build(product, sc); dt = a.recommended_dt()
+    if case == "robots":
+        a.set_temperature_all(7.5)
+    a.step(dt, 333)
+    path = str(tmp_path / "state.bin")
+    a.save_state(path)
+    a.step(dt, 200)
+    b = scenarios.build(product, sc)
+    b.load_state(path)
+    assert b.time() == pytest.approx(333 * dt, rel=1e-4)
+    b.step(dt, 200)
+    sa, sb = parity.snapshot(a), parity.snapshot(b)
+    for f in sa:
+        assert parity.bit_equal(sa[f], sb[f]), f
+    assert a.time() == b.time()
+    # a file of another model is refused
+    other = scenarios.build(product, scenarios.cantilever(14, 5, 7))
+    with pytest.raises(capi.VxError):
+        other.load_state(path)

@@ -65,12 +65,13 @@ FACADE_DIR = os.path.join(ROOT, "voxelyze_b200", "facade")
 def build_facade(force: bool = False) -> str:
     """The C++ drop-in class API (CVoxelyze, CVX_*) on top of the C-ABI library."""
     src = os.path.join(FACADE_DIR, "src", "voxelyze_facade.cpp")
+    src_json = os.path.join(FACADE_DIR, "src", "voxelyze_json.cpp")
     inc = os.path.join(FACADE_DIR, "include")
-    deps = [src, PRODUCT_SO] + [os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(CSRC, "vx_material.hpp")]
+    deps = [src, src_json, PRODUCT_SO] + [os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(CSRC, "vx_material.hpp")]
     if not force and _newer(FACADE_SO, deps):
         return FACADE_SO
     cmd = [_host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable", "-Wno-overloaded-virtual",
-           "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", FACADE_SO, src,
+           "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", FACADE_SO, src, src_json,
            "-L", LIBDIR, "-lvoxelyze_b200", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)
     return FACADE_SO

@@ -167,6 +167,8 @@ class VxLib:
             "vx_peer_detach": (i32, [vp]),
             "vx_slab_step": (i32, [vp, C.c_float, i32, C.POINTER(i32)]),
             "vx_slab_exchange": (i32, [vp]),
+            "vx_save_state": (i32, [vp, C.c_char_p]),
+            "vx_load_state": (i32, [vp, C.c_char_p]),
             "vx_set_path": (i32, [vp, i32]),
             "vx_active_path": (i32, [vp]),
             "vx_kernel_name": (C.c_char_p, [vp]),
@@ -420,6 +422,12 @@ class Sim:
 
     def active_path(self) -> int:
         return self.L.lib.vx_active_path(self.h)
+
+    def save_state(self, path: str):
+        self._chk(self.L.lib.vx_save_state(self.h, os.fsencode(path)))
+
+    def load_state(self, path: str):
+        self._chk(self.L.lib.vx_load_state(self.h, os.fsencode(path)))
 
     def kernel_name(self) -> str:
         return self.L.lib.vx_kernel_name(self.h).decode()

@@ -1005,6 +1005,99 @@ int vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     return rc2 != VX_OK ? rc2 : rc;
 }
 
+// ---- dynamic-state checkpoint (the reference has none) -----------------
+namespace {
+struct StateHeader {
+    char magic[8]; int32_t abi, lattice, N, L, nx, ny, nz, n_members, gen, have_prev, collisions, reserved;
+    float last_prev_dt, prev_dt_host, time_host, ambient; uint64_t topo_hash; DevParams params;
+};
+struct Chunk { void* p; size_t bytes; };
+static uint64_t topo_hash(const vx_sim* s)
+{
+    uint64_t h = 1469598103934665603ULL;                                   // FNV-1a over the model the arrays belong to
+    auto mix = [&](const void* d, size_t n) { const unsigned char* b = (const unsigned char*)d; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; } };
+    mix(s->ijk.data(), s->ijk.size() * sizeof(int32_t)); mix(s->vmat_id.data(), s->vmat_id.size() * sizeof(uint16_t));
+    mix(s->member.data(), s->member.size() * sizeof(int32_t)); mix(s->vflags.data(), s->vflags.size() * sizeof(uint32_t));
+    return h;
+}
+static std::vector<Chunk> state_chunks(vx_sim* s)
+{
+    std::vector<Chunk> c;
+    const size_t N = s->N, L = s->L;
+    if (s->lattice) {
+        for (int g = 0; g < 2; g++) {
+            c.push_back({s->pose0[g].p, N * sizeof(double4)}); c.push_back({s->pose1[g].p, N * sizeof(double4)});
+            c.push_back({s->mom0[g].p, N * sizeof(double4)}); c.push_back({s->mom1[g].p, N * sizeof(double2)});
+            c.push_back({s->rec[g].p, N * 9 * sizeof(double2)}); c.push_back({s->recf[g].p, N * 3 * sizeof(float4)});
+        }
+    } else {
+        c.push_back({s->pose0[0].p, N * sizeof(double4)}); c.push_back({s->pose1[0].p, N * sizeof(double4)});
+        c.push_back({s->mom0[0].p, N * sizeof(double4)}); c.push_back({s->mom1[0].p, N * sizeof(double2)});
+        c.push_back({s->slots.p, N * 36 * sizeof(double)}); c.push_back({s->slot_strain.p, N * 6 * sizeof(float)});
+        c.push_back({s->pstrain.p, N * sizeof(float4)});
+        c.push_back({s->lstA.p, L * sizeof(double4)}); c.push_back({s->lstB.p, L * sizeof(double4)}); c.push_back({s->lstC.p, L * sizeof(double)});
+        c.push_back({s->lstrain.p, L * sizeof(float4)}); c.push_back({s->lmeta.p, L * sizeof(uint32_t)});
+    }
+    return c;
+}
+} // namespace
+
+int vx_save_state(vx_sim* s, const char* path)
+{
+    if (!s || !path || s->call_active) return VX_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(s, VX_ERR_ARG, std::string("cannot write ") + path);
+    StateHeader h{};
+    memcpy(h.magic, "VXB2ST01", 8);
+    h.abi = VX_ABI_VERSION; h.lattice = s->lattice; h.N = s->N; h.L = s->L; h.nx = s->nx; h.ny = s->ny; h.nz = s->nz; h.n_members = s->n_members;
+    h.gen = s->gen; h.have_prev = s->have_prev; h.collisions = s->collisions;
+    h.last_prev_dt = s->last_prev_dt; h.prev_dt_host = s->prev_dt_host; h.time_host = s->time_host; h.ambient = s->ambient;
+    h.topo_hash = topo_hash(s);
+    cudaError_t e = cudaMemcpy(&h.params, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost);
+    bool ok = e == cudaSuccess && fwrite(&h, sizeof(h), 1, fp) == 1;
+    std::vector<unsigned char> bounce(64u << 20);
+    for (const Chunk& c : state_chunks(s)) {
+        for (size_t off = 0; ok && off < c.bytes; off += bounce.size()) {
+            const size_t n = std::min(bounce.size(), c.bytes - off);
+            ok = cudaMemcpy(bounce.data(), (const unsigned char*)c.p + off, n, cudaMemcpyDeviceToHost) == cudaSuccess && fwrite(bounce.data(), 1, n, fp) == n;
+        }
+    }
+    ok = fclose(fp) == 0 && ok;
+    return ok ? VX_OK : fail(s, VX_ERR_CUDA, std::string("writing ") + path + " failed");
+}
+
+int vx_load_state(vx_sim* s, const char* path)
+{
+    if (!s || !path || s->call_active) return VX_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(s, VX_ERR_ARG, std::string("cannot read ") + path);
+    StateHeader h{};
+    bool ok = fread(&h, sizeof(h), 1, fp) == 1 && memcmp(h.magic, "VXB2ST01", 8) == 0 && h.abi == VX_ABI_VERSION;
+    if (ok && (h.lattice != (int)s->lattice || h.N != s->N || h.L != s->L || h.nx != s->nx || h.ny != s->ny || h.nz != s->nz ||
+               h.n_members != s->n_members || h.collisions != (int)s->collisions || h.topo_hash != topo_hash(s))) {
+        fclose(fp);
+        return fail(s, VX_ERR_ARG, "vx_load_state: the file belongs to a different model (voxels, materials layout or options differ)");
+    }
+    std::vector<unsigned char> bounce(64u << 20);
+    for (const Chunk& c : state_chunks(s)) {
+        for (size_t off = 0; ok && off < c.bytes; off += bounce.size()) {
+            const size_t n = std::min(bounce.size(), c.bytes - off);
+            ok = fread(bounce.data(), 1, n, fp) == n && cudaMemcpy((unsigned char*)c.p + off, bounce.data(), n, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+    }
+    fclose(fp);
+    if (!ok) return fail(s, VX_ERR_ARG, std::string("reading ") + path + " failed (truncated or not a state file)");
+    h.params.col_stale = 1;                                  // watch lists are rebuilt from the restored positions at the next step
+    CK(cudaMemcpy(s->params.p, &h.params, sizeof(DevParams), cudaMemcpyHostToDevice));
+    s->gen = h.gen; s->have_prev = h.have_prev != 0; s->last_prev_dt = h.last_prev_dt; s->prev_dt_host = h.prev_dt_host;
+    s->time_host = h.time_host; s->ambient = h.ambient; s->col_stale_host = true;
+    return VX_OK;
+}
+
 int vx_abi_version(void) { return VX_ABI_VERSION; }
 const char* vx_backend(void) { return "cuda-sm100a"; }
 

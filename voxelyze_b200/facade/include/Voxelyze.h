@@ -9,8 +9,8 @@
 // and is produced by the CUDA kernels through the C-ABI of include/voxelyze_b200.h.  Changes a
 // caller makes through returned handles (material setters, external()->set*, setVoxel mid-run)
 // are detected by change counters at the next doTimeStep / accessor and uploaded then.
-// Not provided (outside the hot path): loadJSON/saveJSON, doLinearSolve,
-// mesh rendering.
+// *.vxl.json files load and save like the reference's (facade/src/voxelyze_json.cpp; the RapidJSON-typed
+// overloads are not provided).  Not provided: doLinearSolve, mesh rendering.
 #ifndef VXB200_VOXELYZE_H
 #define VXB200_VOXELYZE_H
 
@@ -37,7 +37,11 @@ public:
     enum valueType { MIN, MAX, TOTAL, AVERAGE };
 
     CVoxelyze(double voxelSize = DEFAULT_VOXEL_SIZE);
+    CVoxelyze(const char* jsonFilePath) : voxSize(DEFAULT_VOXEL_SIZE) { loadJSON(jsonFilePath); }   // include/Voxelyze.h:70
     ~CVoxelyze();
+
+    bool loadJSON(const char* jsonFilePath);    // include/Voxelyze.h:77
+    bool saveJSON(const char* jsonFilePath);    // include/Voxelyze.h:78 (initial configuration only, like the reference)
 
     void clear();
 
@@ -84,7 +88,11 @@ public:
 
     float stateInfo(stateInfoType info, valueType type);
 
-    // facade extras (additive): device ordinal before the first step; the raw C-ABI handle
+    // facade extras (additive): the dynamic state, which saveJSON does not capture (vx_save_state / vx_load_state);
+    // loadState needs an object built with the same materials, voxels and externals
+    bool saveState(const char* path);
+    bool loadState(const char* path);
+    // device ordinal before the first step; the raw C-ABI handle
     void setDevice(int cudaDevice) { device = cudaDevice; }
     vx_sim* handle() const { sync(); return h; }
 
