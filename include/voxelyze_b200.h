@@ -330,6 +330,19 @@ int  vx_sync(vx_sim* s);
  * else (Poisson pre-pass, collisions), ms[3] whole steps; launches[0..2] = kernel launches
  * per group.  Same arithmetic as vx_step.                                                 */
 int  vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches);
+/* persistent state of links [first, first+count) (caller link order, vx_get_links) as packed records:
+ * what CVX_Link keeps between steps (include/VX_Link.h:74-107).  Upload is how a caller carries
+ * the state of surviving links across vx_set_voxels (the reference's setVoxel only recreates the
+ * links of the edited voxel, src/Voxelyze.cpp:485-498) or across a change of layout
+ * (vx_enable_collisions mid-run).  flags: VX_LF_SMALL_ANGLE | VX_LF_LOCAL_VEL_VALID are stored,
+ * yielded/failed are derived from max_strain.                                               */
+typedef struct vx_link_state {
+    double pos2[3], angle1v[3], angle2v[3];
+    float strain, max_strain, strain_offset, stress;
+    uint32_t flags, reserved;
+} vx_link_state;
+int  vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst);
+int  vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* src);
 /* dynamic-state checkpoint (the reference has none: saveJSON stores the initial configuration only,
  * include/Voxelyze.h:78).  vx_save_state writes every time-dependent device array of the handle
  * (voxel poses and momenta, link state, step bookkeeping) to a file; vx_load_state restores it

@@ -578,6 +578,40 @@ static void jsonRoundTrip()             // Voxelyze.h:70,77-78: save, load into 
     CHECK(std::fabs(A.voxel(19)->position().z - 4 * 0.002) > 1e-7);    // it did move
 }
 
+// A plastically bent beam whose middle voxel gets a new material mid-run: only that voxel's links restart
+// (src/Voxelyze.cpp:485-498), every other link keeps its plastic memory; then collisions are switched on mid-run
+// (a change of device layout for the facade).  Prints the final state for a cross-implementation comparison.
+static void printEditScenario()
+{
+    CVoxelyze Vx(0.001);
+    CVX_Material* m = Vx.addMaterial(1e6f, 1000.0f);
+    m->setModelBilinear(1e6f, 1e5f, 2e4f); m->setGlobalDamping(0.05f);
+    CVX_Material* m2 = Vx.addMaterial(1e6f, 1000.0f);
+    m2->setModelBilinear(1e6f, 1e5f, 2e4f); m2->setGlobalDamping(0.05f);
+    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) for (int i = 0; i < 8; i++) Vx.setVoxel(m, i, j, k);
+    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) {
+        Vx.voxel(0, j, k)->external()->setFixedAll();
+        Vx.voxel(7, j, k)->external()->setForce(0.0f, 0.0f, -0.004f);
+    }
+    float dt = Vx.recommendedTimeStep();
+    for (int i = 0; i < 1500; i++) Vx.doTimeStep(dt);
+    int yielded = 0;
+    for (int i = 0; i < Vx.linkCount(); i++) if (Vx.link(i)->isYielded()) yielded++;
+    printf("after loading: yielded links %d tip z %.12e\n", yielded, Vx.voxel(7, 0, 0)->position().z);
+    Vx.setVoxel(m2, 3, 0, 1);                                        // swap one voxel's material mid-run
+    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) Vx.voxel(7, j, k)->external()->setForce(0.0f, 0.0f, 0.0f);
+    for (int i = 0; i < 800; i++) Vx.doTimeStep(dt);
+    Vx.enableCollisions(true);                                       // mid-run
+    for (int i = 0; i < 700; i++) Vx.doTimeStep(dt);
+    yielded = 0;
+    for (int i = 0; i < Vx.linkCount(); i++) if (Vx.link(i)->isYielded()) yielded++;
+    printf("after unloading: yielded links %d\n", yielded);
+    for (int i = 0; i < Vx.voxelCount(); i++) {
+        Vec3D<double> p = Vx.voxel(i)->position();
+        printf("vox %d %.12e %.12e %.12e\n", i, p.x, p.y, p.z);
+    }
+}
+
 #ifndef DROPIN_REFERENCE
 static void stateCheckpoint()           // facade extra: saveState / loadState (the reference cannot checkpoint, Voxelyze.h:78)
 {
@@ -604,6 +638,7 @@ int main(int argc, char** argv)
 {
     if (const char* t = getenv("TMPDIR")) g_tmpdir = t;
     if (argc > 2 && std::string(argv[1]) == "--json-save") { CVoxelyze Vx(0.002); buildJsonModel(Vx); return Vx.saveJSON(argv[2]) ? 0 : 1; }
+    if (argc > 1 && std::string(argv[1]) == "--edit-scenario") { printEditScenario(); return 0; }
     if (argc > 2 && std::string(argv[1]) == "--json-digest") { CVoxelyze Vx(argv[2]); printJsonDigest(Vx); return 0; }
     struct T { const char* name; void (*fn)(); bool device; };
     const T tests[] = {

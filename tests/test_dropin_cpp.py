@@ -78,3 +78,23 @@ def test_facade_loads_the_unterminated_files_the_reference_writes(binaries, tmp_
         closed = tmp_path / "closed.vxl.json"
         closed.write_text(path.read_text() + "}\n")
         assert _run(binaries["ref"], "--json-digest", str(closed)) == _run(binaries["b200"], "--json-digest", str(closed)) == out
+
+
+@pytest.mark.gpu
+def test_mid_run_edits_keep_the_state_of_untouched_links(binaries):
+    """A yielded beam, one voxel's material swapped mid-run (only ITS links restart, src/Voxelyze.cpp:485-498), the load
+    removed, collisions enabled mid-run: the facade (device re-layouts carrying voxel and link state) ends where the
+    unmodified reference ends.  The residual bend is plastic memory of the untouched links."""
+    if "ref" not in binaries:
+        pytest.skip("reference sources not available at build time")
+    ref = _run(binaries["ref"], "--edit-scenario").splitlines()
+    got = _run(binaries["b200"], "--edit-scenario").splitlines()
+    assert ref[0].split()[:5] == got[0].split()[:5] and int(ref[0].split()[4]) > 0          # same number of yielded links
+    assert ref[1] == got[1]
+    import numpy as np
+    a = np.array([[float(x) for x in l.split()[2:]] for l in ref[2:]])
+    b = np.array([[float(x) for x in l.split()[2:]] for l in got[2:]])
+    nominal = np.array([[i, j, k] for k in range(2) for j in range(2) for i in range(8)]) * 0.001
+    scale = np.abs(a - nominal).max()
+    assert scale > 1e-5                                                                    # a residual (plastic) deflection remains
+    assert np.abs(a - b).max() <= 1e-7 * scale, np.abs(a - b).max() / scale

@@ -180,7 +180,11 @@ def test_edge_cases_on_device(product):
     s.set_voxels([[0, 0, 0], [1, 0, 0], [-1, 0, 0]], [0, 0, 0])
     vn, vp, ax = s.links()
     assert list(vn) == [0, 2] and list(vp) == [1, 0]
-    assert s.step(0.0, 5) is None and s.time() == 0.0
+    t = s.time()                           # a voxel set replaced mid-run: simulation time goes on (src/Voxelyze.cpp:422-498)
+    assert t == pytest.approx(20e-6, rel=1e-4)
+    assert s.step(0.0, 5) is None and s.time() == t          # dt == 0: no step (src/Voxelyze.cpp:253)
+    s.reset()
+    assert s.time() == 0.0
 
 
 def test_reset_restores_initial_state(product, oracle):
@@ -389,3 +393,44 @@ def test_checkpoint_resume_is_bit_identical(product, tmp_path, case):
     other = scenarios.build(product, scenarios.cantilever(14, 5, 7))
     with pytest.raises(capi.VxError):
         other.load_state(path)
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["lattice", "general"])
+def test_link_state_upload_round_trip(product, path):
+    """vx_download_link_state / vx_upload_link_state: a fresh handle that receives the voxel and link state of a
+    running one continues bit-identically (what the facade does across setVoxel edits)."""
+    sc = scenarios.cantilever(12, 4, 3, tip_load=60.0)
+    a = scenarios.build(product, sc, path=path); dt = a.recommended_dt()
+    a.step(dt, 400)
+    b = scenarios.build(product, sc, path=path)
+    b.step(dt, 1)                          # so that both handles damp their next step with the same previous dt
+    for f in ("pos", "orient", "linmom", "angmom", "temp"):
+        b.upload(f, a.download(f))
+    rec = a.download_link_state()
+    assert (rec["flags"] & 2).all() and np.abs(rec["pos2"]).max() > 0
+    b.upload_link_state(rec)
+    back = b.download_link_state()
+    for name in ("pos2", "angle1v", "angle2v", "strain", "max_strain", "strain_offset", "stress", "flags"):
+        assert np.array_equal(back[name], rec[name]), name
+    a.step(dt, 150); b.step(dt, 150)
+    for f in ("pos", "orient", "linmom", "angmom"):
+        assert parity.bit_equal(a.download(f), b.download(f)), f
+    sa, sb = a.download_link_state(), b.download_link_state()
+    assert sa.tobytes() == sb.tobytes()
+
+
+def test_enabling_collisions_mid_run_matches_the_oracle(product, oracle):
+    """CVoxelyze::enableCollisions may be called at any time (src/Voxelyze.cpp:612-622); on the device it changes the
+    layout (fused lattice -> general) while every voxel and link keeps its state."""
+    sc = scenarios.drop_block(6)
+    g = scenarios.build(product, sc); o = scenarios.build(oracle, sc)
+    assert g.active_path() == 2
+    dt = g.recommended_dt()
+    g.step(dt, 300); o.step(dt, 300)
+    g.enable_collisions(True); o.enable_collisions(True)
+    assert g.active_path() == 1
+    assert abs(g.time() - o.time()) <= 1e-9
+    g.step(dt, 500); o.step(dt, 500)
+    err = parity.rel_errors(parity.snapshot(g), parity.snapshot(o), sc)
+    assert err["pos"] <= 1e-7 and err["orient"] <= 1e-7, err
+    assert np.array_equal(g.collision_pairs(), o.collision_pairs())

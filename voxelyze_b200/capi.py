@@ -169,6 +169,8 @@ class VxLib:
             "vx_slab_exchange": (i32, [vp]),
             "vx_save_state": (i32, [vp, C.c_char_p]),
             "vx_load_state": (i32, [vp, C.c_char_p]),
+            "vx_download_link_state": (i32, [vp, i32, i32, C.c_void_p]),
+            "vx_upload_link_state": (i32, [vp, i32, i32, C.c_void_p]),
             "vx_set_path": (i32, [vp, i32]),
             "vx_active_path": (i32, [vp]),
             "vx_kernel_name": (C.c_char_p, [vp]),
@@ -422,6 +424,19 @@ class Sim:
 
     def active_path(self) -> int:
         return self.L.lib.vx_active_path(self.h)
+
+    LINK_STATE_DTYPE = np.dtype([("pos2", "<f8", 3), ("angle1v", "<f8", 3), ("angle2v", "<f8", 3), ("strain", "<f4"), ("max_strain", "<f4"),
+                                 ("strain_offset", "<f4"), ("stress", "<f4"), ("flags", "<u4"), ("reserved", "<u4")])
+
+    def download_link_state(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n_links - first if count is None else count
+        out = np.zeros(count, self.LINK_STATE_DTYPE)
+        self._chk(self.L.lib.vx_download_link_state(self.h, first, count, out.ctypes.data))
+        return out
+
+    def upload_link_state(self, rec: np.ndarray, first: int = 0):
+        rec = np.ascontiguousarray(rec, dtype=self.LINK_STATE_DTYPE)
+        self._chk(self.L.lib.vx_upload_link_state(self.h, first, len(rec), rec.ctypes.data))
 
     def save_state(self, path: str):
         self._chk(self.L.lib.vx_save_state(self.h, os.fsencode(path)))

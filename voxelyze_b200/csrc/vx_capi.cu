@@ -1098,6 +1098,61 @@ int vx_load_state(vx_sim* s, const char* path)
     return VX_OK;
 }
 
+// ---- packed link state (topology edits and layout changes keep the state of surviving links) -------
+int vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst)
+{
+    if (!s || !dst || first < 0 || count < 0 || first + count > s->L) return VX_ERR_ARG;
+    if (count == 0) return VX_OK;
+    std::vector<double> p2(3 * (size_t)count), a1(3 * (size_t)count), a2(3 * (size_t)count);
+    std::vector<float> e(count), em(count), eo(count), sg(count); std::vector<uint32_t> fl(count);
+    int rc = vx_download(s, VX_F_POS2, first, count, p2.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_ANGLE1V, first, count, a1.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_ANGLE2V, first, count, a2.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_STRAIN, first, count, e.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_MAXSTRAIN, first, count, em.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_STRAINOFFSET, first, count, eo.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_STRESS, first, count, sg.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_LINKFLAGS, first, count, fl.data());
+    if (rc != VX_OK) return rc;
+    for (int k = 0; k < count; k++) {
+        vx_link_state& r = dst[k];
+        for (int c = 0; c < 3; c++) { r.pos2[c] = p2[3 * (size_t)k + c]; r.angle1v[c] = a1[3 * (size_t)k + c]; r.angle2v[c] = a2[3 * (size_t)k + c]; }
+        r.strain = e[k]; r.max_strain = em[k]; r.strain_offset = eo[k]; r.stress = sg[k]; r.flags = fl[k]; r.reserved = 0;
+    }
+    return VX_OK;
+}
+
+int vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* src)
+{
+    static_assert(sizeof(vx_link_state) == sizeof(LinkStateRec), "vx_link_state layout");
+    if (!s || !src || first < 0 || count < 0 || first + count > s->L || s->call_active) return VX_ERR_ARG;
+    if (count == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    const size_t bytes = (size_t)count * sizeof(vx_link_state);
+    CK(s->staging.alloc(bytes));
+    CK(cudaMemcpyAsync(s->staging.p, src, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (!s->lattice) {
+        k_scatter_link_state<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), s->link_e2i_dev.p, first, count, (const LinkStateRec*)s->staging.p);
+    } else {
+        std::vector<int> of((size_t)3 * s->N, -1);              // (axis, owner voxel) -> caller link index
+        for (int e = 0; e < s->L; e++) of[(size_t)s->lk_axis[e] * s->N + s->v_e2i[s->lk_vn[e]]] = e;
+        DevBuf<int> of_dev;
+        CK(of_dev.alloc(of.size()));
+        CK(cudaMemcpyAsync(of_dev.p, of.data(), of.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        const int g = s->gen;
+        k_lattice_scatter_link_state<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->pose1[g].p, s->rec[g].p, s->recf[g].p, of_dev.p, s->N,
+                                                                              (const LinkStateRec*)s->staging.p, first, count);
+        CK(cudaStreamSynchronize(s->stream));
+        of_dev.release();
+        s->have_prev = false;                                    // link forces are recomputed from the previous generation, which no longer matches
+    }
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s->stream));
+    return VX_OK;
+}
+
 int vx_abi_version(void) { return VX_ABI_VERSION; }
 const char* vx_backend(void) { return "cuda-sm100a"; }
 
@@ -1347,7 +1402,15 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     if (rc != VX_OK) return rc;
     if (s->collisions) { rc = build_collision_tables(s); if (rc != VX_OK) return rc; }
     find_boundary_layers(s);
-    return upload_initial_state(s, s->ambient);    // new voxels start at ambient temperature, src/Voxelyze.cpp:449
+    // a voxel set replaced in the middle of a run: simulation time and CVX_Voxel::previousDt go on (setVoxel does not
+    // touch them, src/Voxelyze.cpp:422-498); vx_reset is what rewinds them
+    const float time = s->time_host, prev_dt = s->prev_dt_host;
+    rc = upload_initial_state(s, s->ambient);      // new voxels start at ambient temperature, src/Voxelyze.cpp:449
+    if (rc != VX_OK || (time == 0.f && prev_dt == 0.f)) return rc;
+    DevParams p{}; p.col_stale = 1; p.time = time; p.prev_dt = prev_dt;
+    CK(cudaMemcpy(s->params.p, &p, sizeof(p), cudaMemcpyHostToDevice));
+    s->time_host = time; s->prev_dt_host = prev_dt;
+    return VX_OK;
 }
 
 int vx_voxel_count(const vx_sim* s) { return s ? s->N : 0; }
@@ -1419,6 +1482,38 @@ static int relayout_fresh(vx_sim* s)
     return rc;
 }
 
+// change of layout in the middle of a run (collisions switched on: lattice -> general): every voxel and link keeps its state
+static int relayout_keep_state(vx_sim* s)
+{
+    const int N = s->N, L = s->L;
+    std::vector<double> pos(3 * (size_t)N), ori(4 * (size_t)N), lin(3 * (size_t)N), ang(3 * (size_t)N);
+    std::vector<float> temp(N); std::vector<uint32_t> vfl(N); std::vector<vx_link_state> ls(L);
+    int rc = vx_download(s, VX_F_POS, 0, N, pos.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_ORIENT, 0, N, ori.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_LINMOM, 0, N, lin.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_ANGMOM, 0, N, ang.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_TEMP, 0, N, temp.data());
+    if (rc == VX_OK) rc = vx_download(s, VX_F_VOXFLAGS, 0, N, vfl.data());
+    if (rc == VX_OK && L) rc = vx_download_link_state(s, 0, L, ls.data());
+    if (rc != VX_OK) return rc;
+    const float time = s->time_host, prev_dt = s->prev_dt_host, ambient = s->ambient;
+    rc = relayout_fresh(s);
+    if (rc != VX_OK) return rc;
+    if (s->L != L || s->N != N) return fail(s, VX_ERR_CUDA, "relayout changed the model");
+    rc = vx_upload(s, VX_F_POS, 0, N, pos.data());
+    if (rc == VX_OK) rc = vx_upload(s, VX_F_ORIENT, 0, N, ori.data());
+    if (rc == VX_OK) rc = vx_upload(s, VX_F_LINMOM, 0, N, lin.data());
+    if (rc == VX_OK) rc = vx_upload(s, VX_F_ANGMOM, 0, N, ang.data());
+    if (rc == VX_OK) rc = vx_upload(s, VX_F_TEMP, 0, N, temp.data());
+    if (rc == VX_OK) rc = vx_upload(s, VX_F_VOXFLAGS, 0, N, vfl.data());
+    if (rc == VX_OK && L) rc = vx_upload_link_state(s, 0, L, ls.data());
+    if (rc != VX_OK) return rc;
+    DevParams p{}; p.col_stale = 1; p.time = time; p.prev_dt = prev_dt;
+    CK(cudaMemcpy(s->params.p, &p, sizeof(p), cudaMemcpyHostToDevice));
+    s->time_host = time; s->prev_dt_host = prev_dt; s->ambient = ambient;
+    return VX_OK;
+}
+
 int vx_enable_collisions(vx_sim* s, int e)                         // src/Voxelyze.cpp:612-622
 {
     if (!s) return VX_ERR_ARG;
@@ -1428,7 +1523,7 @@ int vx_enable_collisions(vx_sim* s, int e)                         // src/Voxely
     s->drop_graph();
     if (!s->collisions) { s->n_pairs = 0; return VX_OK; }           // clearCollisions()
     if (s->N == 0 || s->col_tables) return VX_OK;
-    if (s->time_host != 0.f || s->have_prev) { s->collisions = false; return fail(s, VX_ERR_UNSUPPORTED, "enable collisions before the first step"); }
+    if (s->time_host != 0.f || s->have_prev) return relayout_keep_state(s);   // mid-run: the layout changes, the state does not
     return relayout_fresh(s);
 }
 int vx_set_collision_envelope(vx_sim* s, float r) { if (!s) return VX_ERR_ARG; s->envelope = r; return VX_OK; }

@@ -347,6 +347,21 @@ __global__ void k_scatter(Frame f, int what, const int* e2i, int first, int coun
     }
 }
 
+// persistent state of links [first, first+count) in caller order <- packed vx_link_state records (96 B each)
+struct LinkStateRec { double pos2[3], a1v[3], a2v[3]; float strain, max_strain, strain_offset, stress; uint32_t flags, pad; };
+__global__ void k_scatter_link_state(Frame f, const int* e2i, int first, int count, const LinkStateRec* src)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int l = e2i[first + k];
+    const LinkStateRec r = src[k];
+    f.lstA[l] = make_double4(r.pos2[0], r.pos2[1], r.pos2[2], r.a1v[0]);
+    f.lstB[l] = make_double4(r.a1v[1], r.a1v[2], r.a2v[0], r.a2v[1]);
+    f.lstC[l] = r.a2v[2];
+    f.lstrain[l] = make_float4(r.strain, r.max_strain, r.strain_offset, r.stress);
+    f.lmeta[l] = (f.lmeta[l] & LM_MAT_MASK) | ((r.flags & 1u) ? LM_SMALL_ANGLE : 0u) | ((r.flags & 2u) ? LM_VEL_VALID : 0u);
+}
+
 __global__ void k_fill_temp(Frame f, float t, const float* member_t, const int* member_of)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;

@@ -247,6 +247,33 @@ __global__ void k_lattice_gather_links(LatFrame cur, LatFrame prev, int have_pre
     }
 }
 
+// persistent link state <- packed records (see k_scatter_link_state); the mode bits go to the owner's meta word.
+// One thread per OWNER VOXEL and axis pass (no two threads touch the same meta word).
+__global__ void k_lattice_scatter_link_state(double4* pose1, double2* rec, float4* recf, const int* link_of_owner, int n_vox,
+                                             const LinkStateRec* src, int first, int count)
+{
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vox) return;
+    uint32_t bits = meta_hi(pose1[v].w);
+    bool touched = false;
+    for (int axis = 0; axis < 3; axis++) {
+        const int ext = link_of_owner[axis * n_vox + v];          // caller index of the link this voxel owns on that axis, or -1
+        if (ext < first || ext >= first + count) continue;
+        const LinkStateRec r = src[ext - first];
+        LinkState st;
+        st.small_angle = (r.flags & 1u) != 0; st.vel_valid = (r.flags & 2u) != 0;
+        st.pos2 = mk3(r.pos2[0], r.pos2[1], r.pos2[2]); st.a1v = mk3(r.a1v[0], r.a1v[1], r.a1v[2]); st.a2v = mk3(r.a2v[0], r.a2v[1], r.a2v[2]);
+        st.strain = r.strain; st.max_strain = r.max_strain; st.strain_offset = r.strain_offset; st.stress = r.stress;
+        double2 a, b, c; float4 s4; uint32_t lf;
+        lat_encode(st, a, b, c, s4, lf);
+        rec[(size_t)(axis * 3 + 0) * n_vox + v] = a; rec[(size_t)(axis * 3 + 1) * n_vox + v] = b; rec[(size_t)(axis * 3 + 2) * n_vox + v] = c;
+        recf[(size_t)axis * n_vox + v] = s4;
+        bits = (bits & ~(3u << (VM_LFLAG_SHIFT + 2 * axis))) | (lf << (VM_LFLAG_SHIFT + 2 * axis));
+        touched = true;
+    }
+    if (touched) reinterpret_cast<uint32_t*>(&pose1[v].w)[1] = bits;
+}
+
 // max over links of a1/min(m1,m2) for the dense lattice (nu = 0 only), same reduction as k_max_freq
 __global__ void __launch_bounds__(256) k_lattice_max_freq(LatFrame f, unsigned int* out)
 {

@@ -124,6 +124,10 @@ private:
     mutable std::vector<float> mTemp; mutable std::vector<uint32_t> mFlags;
     mutable int singleFetches = 0;
     mutable std::vector<int> removedIndices, pendingStateEdit;   // topology edits since the last device rebuild
+    mutable std::vector<unsigned char> linkStateMirror;          // vx_link_state records fetched before the first edit of a batch
+    mutable bool linkStateFetched = false;
+    mutable std::vector<CVX_Voxel*> editedVoxels;                // voxels whose links restart (material swapped), src/Voxelyze.cpp:485-498
+    void fetchLinkState() const;
 
     static uint64_t key(int x, int y, int z) { return ((uint64_t)(uint16_t)(int16_t)x << 32) | ((uint64_t)(uint16_t)(int16_t)y << 16) | (uint64_t)(uint16_t)(int16_t)z; }
     int bound(int axis, bool max) const;

@@ -349,7 +349,8 @@ CVX_Voxel* CVoxelyze::setVoxel(CVX_Material* material, int x, int y, int z)
     if (v) {                                        // replaceVoxel (src/Voxelyze.cpp:485-498)
         if (v->mat != m) {
             if (stepped) {                          // keep velocity across the material change (src/VX_Voxel.cpp:78-90)
-                fetchAll();
+                fetchAll(); fetchLinkState();
+                editedVoxels.push_back(v);
                 double ls = m->p_.mass / v->mat->p_.mass, as = m->p_.inertia / v->mat->p_.inertia;
                 for (int a = 0; a < 3; a++) { mLin[3 * v->index + a] *= ls; mAng[3 * v->index + a] *= as; }
                 mFlags[v->index] &= ~VX_VF_STATIC_FRICTION;
@@ -360,7 +361,7 @@ CVX_Voxel* CVoxelyze::setVoxel(CVX_Material* material, int x, int y, int z)
         }
         return v;
     }
-    if (stepped) fetchAll();                         // existing voxels keep their state across the re-layout
+    if (stepped) { fetchAll(); fetchLinkState(); }   // existing voxels and links keep their state across the re-layout
     v = new CVX_Voxel(m, (short)x, (short)y, (short)z);
     v->sim = this; v->index = (int)voxelsList.size();
     voxelsList.push_back(v);
@@ -373,7 +374,7 @@ void CVoxelyze::removeVoxel(int x, int y, int z)
 {
     CVX_Voxel* v = voxel(x, y, z);
     if (!v) return;
-    if (stepped) fetchAll();
+    if (stepped) { fetchAll(); fetchLinkState(); }
     cells.erase(key(x, y, z));
     removedIndices.push_back(v->index);
     voxelsList.erase(voxelsList.begin() + v->index);
@@ -439,6 +440,16 @@ void CVoxelyze::uploadExternals() const
     if (vx_set_externals(h, (int)vox.size(), vox.data(), dof.data(), f.data(), m.data(), t.data(), r.data()) != VX_OK) die("vx_set_externals");
 }
 
+// state of every link of the model the device currently holds, fetched once before the first edit of a batch
+void CVoxelyze::fetchLinkState() const
+{
+    if (!stepped || linkStateFetched || !h || topologyDirty) return;
+    const int L = vx_link_count(h);
+    linkStateMirror.resize((size_t)L * sizeof(vx_link_state));
+    if (L && vx_download_link_state(h, 0, L, (vx_link_state*)linkStateMirror.data()) != VX_OK) die("vx_download_link_state");
+    linkStateFetched = true;
+}
+
 void CVoxelyze::rebuildTopology() const
 {
     const int n = (int)voxelsList.size();
@@ -458,6 +469,15 @@ void CVoxelyze::rebuildTopology() const
     std::vector<int32_t> vn(L), vp(L); std::vector<uint8_t> ax(L);
     vx_get_links(h, vn.data(), vp.data(), ax.data());
     std::map<std::pair<CVX_Voxel*, int>, CVX_Link*> pool;
+    // links that survive the edit keep their state; the links of a voxel whose material was swapped restart, like
+    // every new link (the reference destroys and recreates exactly those, src/Voxelyze.cpp:485-498)
+    std::vector<vx_link_state> carried;
+    const vx_link_state* oldState = (const vx_link_state*)linkStateMirror.data();
+    const int oldL = (int)(linkStateMirror.size() / sizeof(vx_link_state));
+    if (keepState && linkStateFetched) {
+        vx_link_state fresh; memset(&fresh, 0, sizeof(fresh)); fresh.flags = VX_LF_SMALL_ANGLE;     // CVX_Link::reset, src/VX_Link.cpp:61-75
+        carried.assign(L, fresh);
+    }
     linksList.assign(L, nullptr);
     for (CVX_Voxel* v : voxelsList) for (int d = 0; d < 6; d++) v->links[d] = nullptr;
     for (int i = 0; i < L; i++) {
@@ -465,8 +485,12 @@ void CVoxelyze::rebuildTopology() const
         std::pair<CVX_Voxel*, int> k(a, ax[i]);
         CVX_Link* l;
         auto it = linkPool.find(k);
-        if (it != linkPool.end() && it->second->pVPos == b) { l = it->second; linkPool.erase(it); }
-        else l = new CVX_Link(const_cast<CVoxelyze*>(this), a, b, (CVX_Link::linkAxis)ax[i]);
+        if (it != linkPool.end() && it->second->pVPos == b) {
+            l = it->second; linkPool.erase(it);
+            const bool restarted = std::find(editedVoxels.begin(), editedVoxels.end(), a) != editedVoxels.end() ||
+                                   std::find(editedVoxels.begin(), editedVoxels.end(), b) != editedVoxels.end();
+            if (!carried.empty() && !restarted && l->index >= 0 && l->index < oldL) carried[i] = oldState[l->index];
+        } else l = new CVX_Link(const_cast<CVoxelyze*>(this), a, b, (CVX_Link::linkAxis)ax[i]);
         l->index = i; l->mat = combinedMaterial(a->mat, b->mat);
         pool[k] = l; linksList[i] = l;
         a->links[2 * ax[i]] = l; b->links[2 * ax[i] + 1] = l;
@@ -474,7 +498,7 @@ void CVoxelyze::rebuildTopology() const
     for (auto& kv : linkPool) delete kv.second;      // links that no longer exist
     linkPool.swap(pool);
 
-    if (keepState && n) {                            // voxel state survives a topology edit; links restart (documented deviation)
+    if (keepState && n) {                            // voxel state survives a topology edit
         // mirrors are indexed by the OLD voxel order minus removed entries: compact them first
         std::sort(removedIndices.begin(), removedIndices.end());
         for (int k = (int)removedIndices.size() - 1; k >= 0; k--) {
@@ -493,7 +517,9 @@ void CVoxelyze::rebuildTopology() const
             vx_upload(h, VX_F_TEMP, 0, old, mTemp.data()); vx_upload(h, VX_F_VOXFLAGS, 0, old, mFlags.data());
         }
     }
-    removedIndices.clear(); pendingStateEdit.clear();
+    if (!carried.empty() && vx_upload_link_state(h, 0, L, carried.data()) != VX_OK) die("vx_upload_link_state");
+    removedIndices.clear(); pendingStateEdit.clear(); editedVoxels.clear();
+    linkStateMirror.clear(); linkStateFetched = false;
     mirrorEpoch.assign(n, 0);
     mPos.resize(3 * (size_t)n); mOrient.resize(4 * (size_t)n); mLin.resize(3 * (size_t)n); mAng.resize(3 * (size_t)n);
     mTemp.resize(n); mFlags.resize(n);
