@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=0, help="override lattice edge (testing only; reported in config)")
-    ap.add_argument("--cpu-sample", type=int, default=48, help="edge of the CPU baseline sample lattice")
+    ap.add_argument("--cpu-sample", type=int, default=128, help="edge of the CPU baseline sample lattice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N>1: NCCL send/recv for the halo instead of peer-memory stores")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange the halo after the step instead of overlapping it with the interior")
@@ -259,7 +259,7 @@ def main():
                            "l2": "inputs larger than L2 (no flush needed)"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
         if not args.no_cpu_baseline:
-            cb_args = argparse.Namespace(**vars(args)); cb_args.steps, cb_args.warmup = 6, 1
+            cb_args = argparse.Namespace(**vars(args)); cb_args.steps, cb_args.warmup = 10, 2
             line["cpu_baseline"] = cpu_reference_arm(cb_args, args.cpu_sample, emit=False)
         print(json.dumps(line), flush=True)
     if world > 1:

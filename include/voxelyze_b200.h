@@ -311,8 +311,8 @@ int  vx_step_end(vx_sim* s, int* diverged_step);
  * with the interior part.  All slabs must make the same sequence of vx_slab_step /
  * vx_slab_exchange calls.  vx_slab_exchange ships the CURRENT boundary poses (needed once after
  * state was changed by vx_upload or vx_reset); the neighbours' deliveries are awaited by the next
- * vx_slab_step.  A neighbour that does not deliver within ~4 s makes vx_slab_step fail
- * (VX_ERR_CUDA) instead of hanging the GPU.                                                  */
+ * vx_slab_step.  A neighbour that does not deliver within 30 s (environment variable
+ * VX_PEER_TIMEOUT_S) makes vx_slab_step fail (VX_ERR_CUDA) instead of hanging the GPU.         */
 #define VX_PEER_DESC_BYTES 512
 typedef struct vx_peer_desc { unsigned char bytes[VX_PEER_DESC_BYTES]; } vx_peer_desc;
 int  vx_peer_export(vx_sim* s, int ghost_iz, int from_above, vx_peer_desc* out);

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -100,7 +101,7 @@ struct vx_sim {
         void* opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cudaIpcOpenMemHandle results (other-process peers)
     };
     std::vector<PeerLink> peers;
-    bool wb_opted_in = false, zm_opted_in = false;
+    bool wb_opted_in = false, zm_opted_in = false, tile_opted_in = false;
     bool push_in_kernel = false;        // set around the boundary launches of vx_slab_step
     DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
     int n_expect[2] = {0, 0};           // exchanges a neighbour on that side takes part in (0 or 1 per exchange)
@@ -657,11 +658,10 @@ static void launch_lattice(vx_sim* s, int g, int first_of_call)
     } else if (s->path == 2) {           // 8x4x4 bricks per block, thread per link evaluation + shared-memory slots
         const int ntx = (s->nx + VX_TILE_X - 1) / VX_TILE_X, nty = (s->ny + VX_TILE_Y - 1) / VX_TILE_Y, ntz = (s->nz + VX_TILE_Z - 1) / VX_TILE_Z;
         const long long grid = (long long)ntx * nty * ntz * s->n_members;
-        static bool opted_in = false;    // > 48 KB of dynamic shared memory needs a one-time opt-in per function
-        if (!opted_in) {
+        if (!s->tile_opted_in) {         // > 48 KB of dynamic shared memory needs a one-time opt-in per function and device
             cudaFuncSetAttribute(k_lattice_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TILE_SMEM);
             cudaFuncSetAttribute(k_lattice_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TILE_SMEM);
-            opted_in = true;
+            s->tile_opted_in = true;
         }
         if (s->uni) k_lattice_tile<true><<<(unsigned)grid, VX_TILE_THREADS, VX_TILE_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ntx, nty, ntz);
         else k_lattice_tile<false><<<(unsigned)grid, VX_TILE_THREADS, VX_TILE_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ntx, nty, ntz);
@@ -769,10 +769,9 @@ __global__ void k_peer_signal(int* flag, int seq)
     *(volatile int*)flag = seq;
     __threadfence_system();
 }
-__global__ void k_peer_wait(const int* flags, int need_lo, int need_hi, int* timed_out)
+__global__ void k_peer_wait(const int* flags, int need_lo, int need_hi, int* timed_out, long long limit)
 {
-    const long long t0 = clock64();
-    const long long limit = 8000000000LL;                  // ~4 s of SM clocks: a lost peer must not hang the GPU
+    const long long t0 = clock64();                        // limit in SM clocks: a lost peer must not hang the GPU
     while (*(volatile const int*)(flags + 0) < need_lo || *(volatile const int*)(flags + 1) < need_hi) {
         if (clock64() - t0 > limit) { *timed_out = 1; break; }
         __nanosleep(200);
@@ -943,7 +942,9 @@ int vx_peer_detach(vx_sim* s)
 static void peer_wait(vx_sim* s, cudaStream_t st)
 {
     if (s->xseq == 0 || (!s->expect_side[0] && !s->expect_side[1])) return;
-    k_peer_wait<<<1, 1, 0, st>>>(s->peer_flags.p, s->expect_side[0] ? s->xseq : 0, s->expect_side[1] ? s->xseq : 0, s->peer_flags.p + 2);
+    static long long limit = 0;                            // VX_PEER_TIMEOUT_S (default 30 s) at ~2 GHz
+    if (limit == 0) { const char* e = getenv("VX_PEER_TIMEOUT_S"); double sec = e ? atof(e) : 30.0; limit = (long long)(std::max(sec, 0.1) * 2.0e9); }
+    k_peer_wait<<<1, 1, 0, st>>>(s->peer_flags.p, s->expect_side[0] ? s->xseq : 0, s->expect_side[1] ? s->xseq : 0, s->peer_flags.p + 2, limit);
     s->launches++;
 }
 // queue on the comm stream: ship generation g of my boundary layers (unless the step kernel already stored
