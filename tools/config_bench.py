@@ -41,7 +41,7 @@ def make(config: str, scale: int, rank: int, world: int):
 
 def run(lib, config: str, args, rank: int, world: int, sync):
     sc, what = make(config, args.scale, rank, world)
-    sim = scenarios.build(lib, sc)
+    sim = scenarios.build(lib, sc, device=int(os.environ.get("LOCAL_RANK", "0")) if lib.backend.startswith("cuda") else 0)
     dt = sim.recommended_dt()
     units = sim.n_voxels + sim.n_links
     per_step_host = config == "c4"
