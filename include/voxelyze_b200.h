@@ -357,7 +357,8 @@ int  vx_load_state(vx_sim* s, const char* path);
  *   1 general two-kernel path (k_link<AXIS> x3 + k_voxel), any topology
  *   fused lattice variants, all bit-identical to path 1:
  *   2 block bricks 8x4x4 (k_lattice_tile)     3 one thread per voxel (k_lattice_step)
- *   4 z-marching columns (k_lattice_march)    5 warp bricks 4x4x2 (k_lattice_warp) = what 0 picks */
+ *   4 z-marching columns (k_lattice_march)    5 warp bricks 4x4x2, cp.async staging (k_lattice_warp)
+ *   6 marching warp bricks (k_lattice_zmarch) 7 warp bricks 4x4x2, TMA staging (k_lattice_tma) = what 0 picks */
 int  vx_set_path(vx_sim* s, int path);
 /* which layout the handle runs: 1 general, 2 fused lattice (decided by vx_set_voxels)  */
 int  vx_active_path(const vx_sim* s);

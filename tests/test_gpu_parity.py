@@ -93,15 +93,15 @@ def test_fused_and_general_paths_agree_bitwise(product):
     """Same physics functions, same summation order: the two device layouts give identical bits."""
     sc = scenarios.cantilever(12, 5, 4, tip_load=30.0)
     snaps = {}
-    for path in (0, 1, 2, 3, 4, 5, 6):   # auto (= warp bricks), general two-kernel, block bricks, per-voxel fused, z-marching fused, warp bricks
+    for path in (0, 1, 2, 3, 4, 5, 6, 7):   # auto (= warp bricks), general two-kernel, block bricks, per-voxel fused, z-marching fused, warp bricks
         sim, dt, _ = parity.run(product, sc, 700, path=path)
         snaps[path] = parity.snapshot(sim)
-    for path in (1, 2, 3, 4, 5, 6):
+    for path in (1, 2, 3, 4, 5, 6, 7):
         for f in snaps[0]:
             assert parity.bit_equal(snaps[0][f], snaps[path][f]), (path, f)
 
 
-@pytest.mark.parametrize("path", [0, 2, 3, 4, 6], ids=["warpbrick", "blockbrick", "pervoxel", "march", "zmarch"])
+@pytest.mark.parametrize("path", [0, 2, 3, 4, 5, 6], ids=["warpbrick-tma", "blockbrick", "pervoxel", "march", "warpbrick-cpasync", "zmarch"])
 def test_fused_kernels_odd_sizes(product, oracle, path):
     """Lattice edges that are not multiples of the bricks (4x4x2, 8x4x4), the warp segment (31), the CTA
     rows (4) or the z-chunk (32): partial bricks / segments / row groups, several z-chunks."""

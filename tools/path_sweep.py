@@ -7,7 +7,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from voxelyze_b200 import capi, scenarios
 
-NAMES = {0: "auto (warp brick 4x4x2)", 1: "general two-kernel", 2: "block brick 8x4x4", 3: "per-voxel fused", 4: "z-march fused", 5: "warp brick 4x4x2", 6: "marching warp brick"}
+NAMES = {0: "auto (warp brick, TMA)", 1: "general two-kernel", 2: "block brick 8x4x4", 3: "per-voxel fused", 4: "z-march fused", 5: "warp brick, cp.async", 6: "marching warp brick", 7: "warp brick, TMA staging"}
 
 def main():
     what = "cantilever"

@@ -8,6 +8,7 @@
 //   general mode  any voxel set, Poisson materials: link kernels + voxel kernel, vx_kernels.cuh
 // There is deliberately no CPU code path for stepping: without a usable CUDA device
 // vx_create fails with VX_ERR_NO_DEVICE.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <unistd.h>
 
@@ -102,6 +103,7 @@ struct vx_sim {
     };
     std::vector<PeerLink> peers;
     bool wb_opted_in = false, zm_opted_in = false, tile_opted_in = false;
+    DevBuf<unsigned char> tmaps;        // CUtensorMap descriptors of the lattice arrays (k_lattice_tma), rebuilt with the arrays
     bool push_in_kernel = false;        // set around the boundary launches of vx_slab_step
     DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
     int n_expect[2] = {0, 0};           // exchanges a neighbour on that side takes part in (0 or 1 per exchange)
@@ -604,6 +606,47 @@ static int ensure_graph(vx_sim* s)
 
 // ------------------------------------------------------------------------------------------------
 // stepping, lattice mode
+// ---- tensor maps of the lattice arrays for k_lattice_tma (u64 elements; members stacked along z) --------------
+static int build_tensor_maps(vx_sim* s)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return fail(s, VX_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t nx = s->nx, ny = s->ny, NZ = (cuuint64_t)s->nz * s->n_members, N = s->N;
+    std::vector<CUtensorMap> maps(2 * TM_COUNT);
+    // box of bx x by x bz voxels (x bp parts) of an array with per_voxel_u64 eight-byte words per voxel and `parts` sub-arrays
+    auto make = [&](CUtensorMap* m, void* base, int per_voxel_u64, int parts, cuuint32_t bx, cuuint32_t by, cuuint32_t bz, cuuint32_t bp) -> bool {
+        const cuuint64_t rec = (cuuint64_t)per_voxel_u64 * 8;                    // bytes per voxel
+        cuuint64_t dims[4] = {nx * per_voxel_u64, ny, NZ, (cuuint64_t)parts};
+        cuuint64_t strides[3] = {nx * rec, nx * ny * rec, N * rec};
+        cuuint32_t box[4] = {bx * per_voxel_u64, by, bz, bp}, es[4] = {1, 1, 1, 1};
+        const cuuint32_t rank = parts ? 4 : 3;
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = true;
+    for (int g = 0; g < 2 && ok; g++) {
+        CUtensorMap* m = maps.data() + g * TM_COUNT;
+        void* p0 = s->pose0[g].p; void* p1 = s->pose1[g].p;
+        ok = make(m + TM_P0_OWN, p0, 4, 0, 4, 4, 2, 0) && make(m + TM_P0_XF, p0, 4, 0, 1, 4, 2, 0) && make(m + TM_P0_YF, p0, 4, 0, 4, 1, 2, 0) && make(m + TM_P0_ZF, p0, 4, 0, 4, 4, 1, 0) &&
+             make(m + TM_P1_OWN, p1, 4, 0, 4, 4, 2, 0) && make(m + TM_P1_XF, p1, 4, 0, 1, 4, 2, 0) && make(m + TM_P1_YF, p1, 4, 0, 4, 1, 2, 0) && make(m + TM_P1_ZF, p1, 4, 0, 4, 4, 1, 0) &&
+             make(m + TM_M0, s->mom0[g].p, 4, 0, 4, 4, 2, 0) && make(m + TM_M1, s->mom1[g].p, 2, 0, 4, 4, 2, 0) &&
+             make(m + TM_REC_OWN, s->rec[g].p, 2, 9, 4, 4, 2, 9) && make(m + TM_REC_XF, s->rec[g].p, 2, 9, 1, 4, 2, 3) && make(m + TM_REC_YF, s->rec[g].p, 2, 9, 4, 1, 2, 3) &&
+             make(m + TM_REC_ZF, s->rec[g].p, 2, 9, 4, 4, 1, 3) &&
+             make(m + TM_RECF_OWN, s->recf[g].p, 2, 3, 4, 4, 2, 3) && make(m + TM_RECF_XF, s->recf[g].p, 2, 3, 1, 4, 2, 1) && make(m + TM_RECF_YF, s->recf[g].p, 2, 3, 4, 1, 2, 1) &&
+             make(m + TM_RECF_ZF, s->recf[g].p, 2, 3, 4, 4, 1, 1);
+    }
+    if (!ok) return fail(s, VX_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    CK(s->tmaps.alloc(maps.size() * sizeof(CUtensorMap)));
+    CK(cudaMemcpy(s->tmaps.p, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    return VX_OK;
+}
+
 // default fused kernel over the brick-group layers [gz_off, gz_off + ngz) (ngz < 0: all)
 static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off, int ngz, int book)
 {
@@ -614,23 +657,40 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     const int nbx = grouped ? gx : bx, nby = grouped ? gy : by, nbz = ngz >= 0 ? ngz : (grouped ? gz : bz);
     const long long bricks = (long long)nbx * nby * nbz * (grouped ? 8 : 1) * s->n_members;
     const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
+    // staging: TMA bulk tensor copies (7, and what 0 picks on large lattices) or per-lane cp.async (5, and what 0 picks for
+    // ensembles of small boxes, where whole-box copies fetch too much padding: 1.15 against 1.19 ms on 4096 robots of 10^3)
+    const bool want_tma = s->path == 7 || (s->path != 5 && grouped);
+    const bool tma = want_tma && (s->tmaps.p || build_tensor_maps(s) == VX_OK);
     if (!s->wb_opted_in) {               // > 48 KB of dynamic shared memory needs a one-time opt-in per function and device
         cudaFuncSetAttribute(k_lattice_warp<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
         cudaFuncSetAttribute(k_lattice_warp<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
         cudaFuncSetAttribute(k_lattice_warp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
         cudaFuncSetAttribute(k_lattice_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+        cudaFuncSetAttribute(k_lattice_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+        cudaFuncSetAttribute(k_lattice_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+        cudaFuncSetAttribute(k_lattice_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+        cudaFuncSetAttribute(k_lattice_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
         s->wb_opted_in = true;
     }
     if (grid > 0) {
         const LatFrame f = s->lat_frame(g);
-        const int fl = s->floor_on ? 1 : 0;
+        const int fl = s->floor_on ? 1 : 0, gr_ = grouped ? 1 : 0;
         const dim3 gr((unsigned)grid), bl(32 * VX_WB_WARPS);
-        if (s->push_in_kernel) {         // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
-            if (s->uni) k_lattice_warp<true, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, grouped ? 1 : 0);
-            else k_lattice_warp<false, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, grouped ? 1 : 0);
+        const unsigned char* tm = s->tmaps.p;
+        if (tma) {
+            if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
+                if (s->uni) k_lattice_tma<true, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+                else k_lattice_tma<false, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+            } else {
+                if (s->uni) k_lattice_tma<true, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+                else k_lattice_tma<false, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+            }
+        } else if (s->push_in_kernel) {
+            if (s->uni) k_lattice_warp<true, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+            else k_lattice_warp<false, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
         } else {
-            if (s->uni) k_lattice_warp<true, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, grouped ? 1 : 0);
-            else k_lattice_warp<false, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, grouped ? 1 : 0);
+            if (s->uni) k_lattice_warp<true, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+            else k_lattice_warp<false, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
         }
         s->launches++;
     }
@@ -803,7 +863,7 @@ extern "C" {
 int vx_step_begin(vx_sim* s, float dt)
 {
     if (!s) return VX_ERR_ARG;
-    if (!s->lattice || (s->path != 0 && s->path != 5)) return fail(s, VX_ERR_UNSUPPORTED, "asynchronous stepping needs the fused lattice path");
+    if (!s->lattice || (s->path != 0 && s->path != 5 && s->path != 7)) return fail(s, VX_ERR_UNSUPPORTED, "asynchronous stepping needs the fused lattice path");
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_step_begin: a call is already open");
     if (dt <= 0) return fail(s, VX_ERR_ARG, "vx_step_begin needs an explicit dt");
     CK(cudaSetDevice(s->device));
@@ -1187,7 +1247,7 @@ void vx_destroy(vx_sim* s)
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
     if (s->ev_comm) cudaEventDestroy(s->ev_comm);
-    s->peer_flags.release();
+    s->peer_flags.release(); s->tmaps.release();
     s->drop_graph();
     for (int g = 0; g < 2; g++) { s->pose0[g].release(); s->pose1[g].release(); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); s->recf[g].release(); }
     s->pair_lmat.release(); s->link_owner.release(); s->link_axis_dev.release();
@@ -1374,6 +1434,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
         s->slots.release(); s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release();
         s->lstrain.release(); s->pstrain.release(); s->slot_strain.release();
         s->lk_mat.clear();
+        s->tmaps.release();                           // describe the old arrays
     } else {
         CK(s->pose0[0].alloc(n1)); CK(s->pose1[0].alloc(n1)); CK(s->mom0[0].alloc(n1)); CK(s->mom1[0].alloc(n1));
         for (int g = 0; g < 2; g++) { s->rec[g].release(); s->recf[g].release(); }
@@ -1937,7 +1998,14 @@ const char* vx_kernel_name(const vx_sim* s)
     case 3: return "k_lattice_step (fused link+voxel, one thread per voxel, 1 launch per step)";
     case 4: return "k_lattice_march (fused link+voxel, z-marching columns, 1 launch per step)";
     case 6: return "k_lattice_zmarch (fused link+voxel, 4x4 column per warp marching in z, 1 launch per step)";
-    default: return "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, 1 launch per step)";
+    case 5: return "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, cp.async staging, 1 launch per step)";
+    case 7: return "k_lattice_tma (fused link+voxel, 4x4x2 brick per warp, TMA staging, 1 launch per step)";
+    default: {
+        const int bx = (s->nx + VX_WB_X - 1) / VX_WB_X, by = (s->ny + VX_WB_Y - 1) / VX_WB_Y, bz = (s->nz + VX_WB_Z - 1) / VX_WB_Z;
+        const bool grouped = (double)((bx + 1) / 2) * ((by + 1) / 2) * ((bz + 1) / 2) * 8 <= 1.1 * (double)bx * by * bz;
+        return grouped ? "k_lattice_tma (fused link+voxel, 4x4x2 brick per warp, TMA staging, 1 launch per step)"
+                       : "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, cp.async staging, 1 launch per step)";
+    }
     }
 }
 

@@ -1186,4 +1186,269 @@ k_lattice_zmarch(LatFrame f, int parity, int first_of_call, int floor_on, int nc
     cp_async_wait<0>();
 }
 
+
+// =================================================================================================
+// k_lattice_tma -- the warp-brick step with its staging done by the Tensor Memory Accelerator.
+//
+// Same arithmetic, same rounds as k_lattice_warp.  What changes is how a brick's inputs reach shared
+// memory: instead of ~70 cp.async instructions per lane, ONE lane issues 24 bulk tensor copies
+// (cp.async.bulk.tensor, boxes of the lattice arrays described by CUtensorMap descriptors):
+//   group 0 (mbarrier 0)  the brick's own poses; the three faces just outside -X/-Y/-Z (poses and the
+//                         records of the links entering through them)                    -> round H
+//   group 1 (mbarrier 1)  all nine record parts of the brick's own links in one 4-D box; the +X/+Y faces
+//   group 2 (mbarrier 2)  issued after round H into the space its inputs leave: momenta, the +Z face
+// Boxes that poke out of the lattice are zero-filled by the hardware, so the requests need no
+// predicates and no index arithmetic.  Waiting is mbarrier.try_wait.parity with a bounded spin.
+// Shared memory per warp 13 440 B:
+//   0      own pose0 [32]x32      1024   | 9216  -X pose0/pose1 [8]x32  2x256  \
+//   1024   own pose1              1024   | 9728  -Y pose0/pose1         2x256   > after H: hslot 1536, +Z pose0 512
+//   2048   own rec  [9][32]x16    4608   | 10240 -Z pose0/pose1 [16]x32 2x512  /
+//   6656   own recf [3][32]x16    1536   | 11264 -X rec [3][8]x16 384, recf 128 \  after H: +Z pose1 512,
+//   8192   +X pose0/pose1 [8]x32  2x256  | 11776 -Y rec 384, recf 128            > momenta mom0 1024, mom1 512
+//   8704   +Y pose0/pose1         2x256  | 12288 -Z rec [3][16]x16 768, recf 256 /
+//   13312  three mbarriers
+// Tensor maps (built on the host, vx_capi.cu build_tensor_maps), u64 elements, per generation:
+enum { TM_P0_OWN, TM_P0_XF, TM_P0_YF, TM_P0_ZF, TM_P1_OWN, TM_P1_XF, TM_P1_YF, TM_P1_ZF, TM_M0, TM_M1,
+       TM_REC_OWN, TM_REC_XF, TM_REC_YF, TM_REC_ZF, TM_RECF_OWN, TM_RECF_XF, TM_RECF_YF, TM_RECF_ZF, TM_COUNT };
+// =================================================================================================
+#define VX_TMA_WARP_BYTES 13440
+#define VX_TMA_SMEM (VX_WB_WARPS * VX_TMA_WARP_BYTES)
+
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar)
+{
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+        if (done) return;
+    }
+    __trap();                            // a copy that never lands must fail the launch, not hang the GPU
+}
+__device__ __forceinline__ void tma_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_4d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <bool UNI, bool PUSH>
+__global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
+k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book, int grouped)
+{
+    // nbx/nby/nbz, gz_off, book, grouped, PUSH: as in k_lattice_warp
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    DevParams* p = f.params;
+    const int frozen = p->div_flag[parity ^ 1] | p->div_latched;
+    const float dt = p->dt;
+    const float prev_dt = first_of_call ? p->prev_dt : dt;
+    if (book && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (frozen) p->div_latched = 1;
+        else if (p->pending) { p->steps_done += 1; p->time += dt; }
+        if (!frozen) p->pending = 1;
+    }
+    if (frozen) return;
+
+    // the warp index through a shuffle: the compiler then knows it (and the brick origin, the shared-memory window, the
+    // tensor coordinates) to be warp-uniform and issues the bulk copies from uniform registers without a per-lane loop
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    unsigned char* wbase = tma_smem + (size_t)warp * VX_TMA_WARP_BYTES;
+    const uint32_t sb = smem_u32(wbase);
+    const uint32_t bar0 = sb + 13312, bar1 = sb + 13320, bar2 = sb + 13328;
+
+    int b = blockIdx.x * VX_WB_WARPS + warp;
+    const int w8 = grouped ? b & 7 : 0;
+    if (grouped) b >>= 3;
+    const int gx = b % nbx; b /= nbx;
+    const int gy = b % nby; b /= nby;
+    const int gz = gz_off + b % nbz; const int member = b / nbz;
+    const int x0 = grouped ? (gx * 2 + (w8 & 1)) * VX_WB_X : gx * VX_WB_X, y0 = grouped ? (gy * 2 + ((w8 >> 1) & 1)) * VX_WB_Y : gy * VX_WB_Y,
+              z0 = grouped ? (gz * 2 + (w8 >> 2)) * VX_WB_Z : gz * VX_WB_Z;
+    if (member * f.nz * f.nxy >= f.n_vox || x0 >= f.nx || y0 >= f.ny || z0 >= f.nz) return;            // whole warp
+    const int vbase = member * f.nz * f.nxy;
+    const int Z0 = member * f.nz + z0;             // the tensors see the members stacked along z
+
+    // ---- one lane arms the barriers and issues every copy of groups 0 and 1
+    if (elect_one()) {
+        mbar_init(bar0); mbar_init(bar1); mbar_init(bar2);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const unsigned char* tm = tmaps + (size_t)parity * TM_COUNT * 128;
+        auto map = [&](int k) { return tm + k * 128; };
+        mbar_expect(bar0, 2048 + 2048 + 2048);
+        tma_3d(sb + 0, map(TM_P0_OWN), bar0, 4 * x0, y0, Z0);
+        tma_3d(sb + 1024, map(TM_P1_OWN), bar0, 4 * x0, y0, Z0);
+        tma_3d(sb + 9216, map(TM_P0_XF), bar0, 4 * (x0 - 1), y0, Z0);
+        tma_3d(sb + 9472, map(TM_P1_XF), bar0, 4 * (x0 - 1), y0, Z0);
+        tma_3d(sb + 9728, map(TM_P0_YF), bar0, 4 * x0, y0 - 1, Z0);
+        tma_3d(sb + 9984, map(TM_P1_YF), bar0, 4 * x0, y0 - 1, Z0);
+        tma_3d(sb + 10240, map(TM_P0_ZF), bar0, 4 * x0, y0, Z0 - 1);
+        tma_3d(sb + 10752, map(TM_P1_ZF), bar0, 4 * x0, y0, Z0 - 1);
+        tma_4d(sb + 11264, map(TM_REC_XF), bar0, 2 * (x0 - 1), y0, Z0, 0);
+        tma_4d(sb + 11648, map(TM_RECF_XF), bar0, 2 * (x0 - 1), y0, Z0, 0);
+        tma_4d(sb + 11776, map(TM_REC_YF), bar0, 2 * x0, y0 - 1, Z0, 3);
+        tma_4d(sb + 12160, map(TM_RECF_YF), bar0, 2 * x0, y0 - 1, Z0, 1);
+        tma_4d(sb + 12288, map(TM_REC_ZF), bar0, 2 * x0, y0, Z0 - 1, 6);
+        tma_4d(sb + 13056, map(TM_RECF_ZF), bar0, 2 * x0, y0, Z0 - 1, 2);
+        mbar_expect(bar1, 4608 + 1536 + 1024);
+        tma_4d(sb + 2048, map(TM_REC_OWN), bar1, 2 * x0, y0, Z0, 0);
+        tma_4d(sb + 6656, map(TM_RECF_OWN), bar1, 2 * x0, y0, Z0, 0);
+        tma_3d(sb + 8192, map(TM_P0_XF), bar1, 4 * (x0 + VX_WB_X), y0, Z0);
+        tma_3d(sb + 8448, map(TM_P1_XF), bar1, 4 * (x0 + VX_WB_X), y0, Z0);
+        tma_3d(sb + 8704, map(TM_P0_YF), bar1, 4 * x0, y0 + VX_WB_Y, Z0);
+        tma_3d(sb + 8960, map(TM_P1_YF), bar1, 4 * x0, y0 + VX_WB_Y, Z0);
+    }
+    __syncwarp();
+
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
+    const bool has_voxel = x < f.nx && y < f.ny && z < f.nz;
+    const int v = vbase + (min(z, f.nz - 1) * f.ny + min(y, f.ny - 1)) * f.nx + min(x, f.nx - 1);
+
+    auto load_pose = [&](int off0, int off1, int entry, double4& a, double4& c) {        // two 32-byte records of one voxel
+        const uint4* q0 = reinterpret_cast<const uint4*>(wbase + off0 + entry * 32);
+        const uint4* q1 = reinterpret_cast<const uint4*>(wbase + off1 + entry * 32);
+        const uint4 e0 = q0[0], e1 = q0[1], e2 = q1[0], e3 = q1[1];
+        a = make_double4(__hiloint2double(e0.y, e0.x), __hiloint2double(e0.w, e0.z), __hiloint2double(e1.y, e1.x), __hiloint2double(e1.w, e1.z));
+        c = make_double4(__hiloint2double(e2.y, e2.x), __hiloint2double(e2.w, e2.z), __hiloint2double(e3.y, e3.x), __hiloint2double(e3.w, e3.z));
+    };
+    auto meta_of = [&](int entry) { return reinterpret_cast<const uint32_t*>(wbase + 1024 + entry * 32)[7]; };   // high word of own pose1.w
+
+    // ---- entering link of this lane (round H)
+    int h_axis, h_tl, h_pose, h_rec, h_recf, h_part;             // face regions: poses, records (part stride), recf
+    if (lane < 8) { h_axis = 0; h_tl = ((lane >> 2) << 4) | ((lane & 3) << 2); h_pose = 9216 + lane * 32; h_rec = 11264 + lane * 16; h_part = 128; h_recf = 11648 + lane * 16; }
+    else if (lane < 16) { h_axis = 1; h_tl = (((lane - 8) >> 2) << 4) | ((lane - 8) & 3); h_pose = 9728 + (lane - 8) * 32; h_rec = 11776 + (lane - 8) * 16; h_part = 128; h_recf = 12160 + (lane - 8) * 16; }
+    else { h_axis = 2; h_tl = lane - 16; h_pose = 10240 + (lane - 16) * 32; h_rec = 12288 + (lane - 16) * 16; h_part = 256; h_recf = 13056 + (lane - 16) * 16; }
+    const int h_face = h_axis == 2 ? 512 : 256;                  // pose1 of a face follows its pose0
+
+    mbar_wait(bar0);
+    const uint32_t bits = meta_of(lane);
+    const uint32_t mask = has_voxel ? ((bits >> VM_LINK_SHIFT) & 0x3Fu) : 0u;
+    uint32_t new_bits = bits;
+    d3 hF = mk3(0.0, 0.0, 0.0), hM = hF;
+    // zero-filled (out of range) voxels carry no link bits; the z test keeps the next ensemble member's planes out
+    const bool h_active = x0 + (h_tl & 3) < f.nx && y0 + ((h_tl >> 2) & 3) < f.ny && z0 + (h_tl >> 4) < f.nz &&
+                          ((meta_of(h_tl) >> (VM_LINK_SHIFT + 2 * h_axis + 1)) & 1u);
+    if (h_active) {
+        double4 n0, n1, p0, p1;
+        load_pose(h_pose, h_pose + h_face, 0, n0, n1);
+        load_pose(0, 1024, h_tl, p0, p1);
+        const uint4 r0 = *reinterpret_cast<const uint4*>(wbase + h_rec), r1 = *reinterpret_cast<const uint4*>(wbase + h_rec + h_part),
+                    r2 = *reinterpret_cast<const uint4*>(wbase + h_rec + 2 * h_part), r3 = *reinterpret_cast<const uint4*>(wbase + h_recf);
+        LinkState st; d3 fN, mN;
+        lat_eval_link_rec<UNI>(f, h_axis, meta_hi(n1.w),
+                               make_double2(__hiloint2double(r0.y, r0.x), __hiloint2double(r0.w, r0.z)),
+                               make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
+                               make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
+                               make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
+                               n0, n1, p0, p1, prev_dt, st, fN, mN, hF, hM);
+    }
+    __syncwarp();                          // every lane has read its round-H inputs: their space is re-used now
+    double (*hslot)[32] = reinterpret_cast<double (*)[32]>(wbase + 9216);                 // [comp][entering link]
+    if (h_active) { hslot[0][lane] = hF.x; hslot[1][lane] = hF.y; hslot[2][lane] = hF.z; hslot[3][lane] = hM.x; hslot[4][lane] = hM.y; hslot[5][lane] = hM.z; }
+    if (elect_one()) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const unsigned char* tm = tmaps + (size_t)parity * TM_COUNT * 128;
+        mbar_expect(bar2, 512 + 512 + 1024 + 512);
+        tma_3d(sb + 10752, tm + TM_P0_ZF * 128, bar2, 4 * x0, y0, Z0 + VX_WB_Z);
+        tma_3d(sb + 11264, tm + TM_P1_ZF * 128, bar2, 4 * x0, y0, Z0 + VX_WB_Z);
+        tma_3d(sb + 11776, tm + TM_M0 * 128, bar2, 4 * x0, y0, Z0);
+        tma_3d(sb + 12800, tm + TM_M1 * 128, bar2, 2 * x0, y0, Z0);
+    }
+    __syncwarp();
+    mbar_wait(bar1);
+
+    // ---- rounds 0..2: own links, forces accumulated in reference order
+    d3 F = mk3(0.0, 0.0, 0.0), M = mk3(0.0, 0.0, 0.0);
+#pragma unroll 1
+    for (int a = 0; a < 3; a++) {
+        if (a == 2) mbar_wait(bar2);
+        const bool inside = a == 0 ? lx < VX_WB_X - 1 : (a == 1 ? ly < VX_WB_Y - 1 : lz < VX_WB_Z - 1);
+        const bool first = a == 0 ? lx == 0 : (a == 1 ? ly == 0 : lz == 0);
+        const int dl = a == 0 ? 1 : (a == 1 ? 4 : 16);
+        d3 fN = mk3(0.0, 0.0, 0.0), mN = fN, fP = fN, mP = fN;
+        if ((mask >> (2 * a)) & 1u) {
+            double4 n0, n1, p0, p1;
+            load_pose(0, 1024, lane, n0, n1);
+            if (inside) load_pose(0, 1024, lane + dl, p0, p1);
+            else if (a == 0) load_pose(8192, 8448, lz * 4 + ly, p0, p1);
+            else if (a == 1) load_pose(8704, 8960, lz * 4 + lx, p0, p1);
+            else load_pose(10752, 11264, ly * 4 + lx, p0, p1);
+            const uint4* rr = reinterpret_cast<const uint4*>(wbase + 2048 + a * 3 * 512) + lane;
+            const uint4 r0 = rr[0], r1 = rr[32], r2 = rr[64], r3 = reinterpret_cast<const uint4*>(wbase + 6656 + a * 512)[lane];
+            LinkState st;
+            lat_eval_link_rec<UNI>(f, a, bits,
+                                   make_double2(__hiloint2double(r0.y, r0.x), __hiloint2double(r0.w, r0.z)),
+                                   make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
+                                   make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
+                                   make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
+                                   n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
+            double2 wa, wb, wc; float4 ws; uint32_t lf;
+            lat_encode(st, wa, wb, wc, ws, lf);
+            double2* nr = f.n_rec[0][0] + (size_t)(a * 3) * f.n_vox + v;
+            nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; (f.n_recf[0] + (size_t)a * f.n_vox)[v] = ws;
+            new_bits = (new_bits & ~(3u << (VM_LFLAG_SHIFT + 2 * a))) | (lf << (VM_LFLAG_SHIFT + 2 * a));
+            if (st.strain > 100) p->div_flag[parity] = 1;          // src/Voxelyze.cpp:265
+            F = F + fN; M = M + mN;
+        }
+        const int src = (lane - dl) & 31;
+        d3 inF = mk3(__shfl_sync(0xffffffffu, fP.x, src), __shfl_sync(0xffffffffu, fP.y, src), __shfl_sync(0xffffffffu, fP.z, src));
+        d3 inM = mk3(__shfl_sync(0xffffffffu, mP.x, src), __shfl_sync(0xffffffffu, mP.y, src), __shfl_sync(0xffffffffu, mP.z, src));
+        if ((mask >> (2 * a + 1)) & 1u) {
+            if (first) {
+                const int hl = a == 0 ? ly + 4 * lz : (a == 1 ? 8 + lx + 4 * lz : 16 + lx + 4 * ly);
+                inF = mk3(hslot[0][hl], hslot[1][hl], hslot[2][hl]);
+                inM = mk3(hslot[3][hl], hslot[4][hl], hslot[5][hl]);
+            }
+            F = F + inF; M = M + inM;
+        }
+    }
+
+    // ---- last round: one lane per voxel
+    if (!has_voxel) return;
+    double4 s0, s1;
+    load_pose(0, 1024, lane, s0, s1);
+    const uint4* mq = reinterpret_cast<const uint4*>(wbase + 11776 + lane * 32);
+    const uint4 q0 = mq[0], q1 = mq[1], q2 = *reinterpret_cast<const uint4*>(wbase + 12800 + lane * 16);
+    VoxelState vs;
+    vs.bits = new_bits; vs.temp = meta_temp(s1.w);
+    vs.pos = mk3(s0.x, s0.y, s0.z);
+    vs.orient.w = s0.w; vs.orient.x = s1.x; vs.orient.y = s1.y; vs.orient.z = s1.z;
+    vs.lin = mk3(__hiloint2double(q0.y, q0.x), __hiloint2double(q0.w, q0.z), __hiloint2double(q1.y, q1.x));
+    vs.ang = mk3(__hiloint2double(q1.w, q1.z), __hiloint2double(q2.y, q2.x), __hiloint2double(q2.w, q2.z));
+    if (vs.bits & VM_GHOST) { reinterpret_cast<uint32_t*>(&f.n_pose1[v].w)[1] = vs.bits; return; }   // see k_lattice_warp
+    {
+        const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
+        const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
+        voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext, dt, floor_on != 0);
+    }
+    f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
+    f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
+    f.n_mom0[v] = make_double4(vs.lin.x, vs.lin.y, vs.lin.z, vs.ang.x);
+    f.n_mom1[v] = make_double2(vs.ang.y, vs.ang.z);
+    // halo push fused into the step (z-slab runs): posted stores over NVLink; the receiver owns the upper half of pose1.w
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (PUSH && z == f.push_z[k]) {
+            const int q = y * f.nx + x;
+            f.push0[k][q] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
+            double* d = reinterpret_cast<double*>(f.push1[k] + q);
+            d[0] = vs.orient.x; d[1] = vs.orient.y; d[2] = vs.orient.z;
+            reinterpret_cast<float*>(d + 3)[0] = vs.temp;
+        }
+    }
+}
+
 } // namespace vxd

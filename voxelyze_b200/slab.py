@@ -108,7 +108,7 @@ class SlabRunner:
         self.host_exchange = host_exchange
         self._bufs = None
         # overlap the exchange with the interior of the step (device exchange on the fused lattice path only)
-        self.overlap = overlap and not host_exchange and world > 1 and path in (0, 5) and sim.active_path() == 2
+        self.overlap = overlap and not host_exchange and world > 1 and path in (0, 5, 7) and sim.active_path() == 2
         self._comm = None
         # peer-memory halo: boundary poses stored straight into the neighbours' ghost layers (CUDA IPC over NVLink),
         # stepping loop in the library (vx_slab_step); falls back to NCCL send/recv when the mappings cannot be made
