@@ -606,6 +606,9 @@ static int ensure_graph(vx_sim* s)
 
 // ------------------------------------------------------------------------------------------------
 // stepping, lattice mode
+#ifndef VX_TMA_L2PROMO
+#define VX_TMA_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
 // ---- tensor maps of the lattice arrays for k_lattice_tma (u64 elements; members stacked along z) --------------
 static int build_tensor_maps(vx_sim* s)
 {
@@ -627,7 +630,7 @@ static int build_tensor_maps(vx_sim* s)
         cuuint32_t box[4] = {bx * per_voxel_u64, by, bz, bp}, es[4] = {1, 1, 1, 1};
         const cuuint32_t rank = parts ? 4 : 3;
         return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                      VX_TMA_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
     bool ok = true;
     for (int g = 0; g < 2 && ok; g++) {
