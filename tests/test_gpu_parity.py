@@ -434,3 +434,21 @@ def test_enabling_collisions_mid_run_matches_the_oracle(product, oracle):
     err = parity.rel_errors(parity.snapshot(g), parity.snapshot(o), sc)
     assert err["pos"] <= 1e-7 and err["orient"] <= 1e-7, err
     assert np.array_equal(g.collision_pairs(), o.collision_pairs())
+
+
+@pytest.mark.parametrize("path", [5, 7], ids=["cpasync", "tma"])
+def test_ensemble_members_stay_independent_on_both_stagings(product, path):
+    """Ensemble members are stacked along z in the device arrays; a brick at the top of one member sees the next member's
+    bottom planes in its +Z face (and, with TMA boxes, in its own box when nz is odd).  Odd box edges, several materials,
+    floor contact and temperature: both staging flavours must equal the general path bit for bit."""
+    sc = scenarios.robot_ensemble(7, 5)                  # 5 x 5 x 5 robots: partial bricks on every axis
+    snaps = {}
+    for p in (1, path):
+        sim = scenarios.build(product, sc, path=p); dt = sim.recommended_dt()
+        assert sim.active_path() == (1 if p == 1 else 2)
+        for k in range(60):
+            sim.set_temperature_all(scenarios.robot_temperature(k * dt) * 3)
+            sim.step(dt, 5)
+        snaps[p] = parity.snapshot(sim)
+    for f in snaps[1]:
+        assert parity.bit_equal(snaps[1][f], snaps[path][f]), f
