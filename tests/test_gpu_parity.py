@@ -255,10 +255,24 @@ def test_state_info_reductions(product, oracle, path):
     sc = scenarios.cantilever(10, 4, 3, tip_load=5.0)
     g, dt, _ = parity.run(product, sc, 400, path=path)
     o, _, _ = parity.run(oracle, sc, 400)
-    for info in (0, 1, 2, 3, 4, 5, 6, 7, 9):          # everything except PRESSURE
+    for info in range(10):
+        # signed quantities (stress, strain, pressure) cancel in TOTAL/AVERAGE: the reference's sequential float sum carries
+        # up to n * eps * max|value| of rounding, so that is the scale the tolerance is tied to
+        scale = max(abs(o.state_info(info, 0)), abs(o.state_info(info, 1)))
+        n = g.n_links if info in (5, 6, 7) else g.n_voxels
         for typ in (0, 1, 2, 3):
             a, b = g.state_info(info, typ), o.state_info(info, typ)
-            assert abs(a - b) <= 1e-6 * max(abs(b), 1e-30) + 1e-30, (info, typ, a, b)
+            slack = (n if typ == 2 else 1) * 1.2e-7 * scale if typ >= 2 else 0.0
+            assert abs(a - b) <= 1e-6 * max(abs(b), 1e-30) + slack + 1e-30, (info, typ, a, b, scale)
+    # PRESSURE with different materials on the two ends of a link (strainRatio != 1) and Poisson's ratio in the denominator
+    sc = cases.BY_NAME["mixed_six"].make()
+    g, dt, _ = parity.run(product, sc, 300)
+    o, _, _ = parity.run(oracle, sc, 300)
+    scale = max(abs(o.state_info(8, 0)), abs(o.state_info(8, 1)))
+    assert scale > 0
+    for typ in (0, 1, 2, 3):
+        a, b = g.state_info(8, typ), o.state_info(8, typ)
+        assert abs(a - b) <= 1e-5 * scale, (typ, a, b, scale)
 
 
 def test_collision_case_energy_and_centre_of_mass(product, oracle):

@@ -138,7 +138,8 @@ struct vx_sim {
     int* counters_host = nullptr;                                  // pinned, 4 ints
     // stateInfo reductions
     DevBuf<float> si_minmax; DevBuf<double> si_sum; DevBuf<double4> si_nominal; DevBuf<float> si_consts; DevBuf<unsigned char> si_buf;
-    bool si_nominal_ok = false, si_consts_ok = false;
+    bool si_nominal_ok = false, si_consts_ok = false, si_pressure_ok = false;
+    DevBuf<int> si_vlinks; DevBuf<float> si_ratio; DevBuf<float2> si_en;
 
     bool uni = false; DevVoxMat vm0{}; DevLinkMat lm0{};          // single-material model: rows passed by value
     cudaGraphExec_t graph = nullptr; int graph_kernels = 0;      // general mode
@@ -1259,6 +1260,7 @@ void vx_destroy(vx_sim* s)
     s->c_pair_force.release(); s->c_counters.release(); s->c_deg.release(); s->c_ref_start.release(); s->c_ref_fill.release(); s->c_refs.release();
     if (s->counters_host) cudaFreeHost(s->counters_host);
     s->si_minmax.release(); s->si_sum.release(); s->si_nominal.release(); s->si_consts.release(); s->si_buf.release();
+    s->si_vlinks.release(); s->si_ratio.release(); s->si_en.release();
     s->ext_idx.release(); s->ext_vox_dev.release(); s->vox_e2i_dev.release(); s->link_e2i_dev.release(); s->member_dev.release();
     s->pstrain.release(); s->slots.release(); s->slot_strain.release();
     s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release(); s->lstrain.release();
@@ -1419,7 +1421,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     s->lattice = n > 0 && cells == (long long)n && !poisson && !s->collisions && s->path != 1;
     s->nx = (int)ext3[0]; s->ny = (int)ext3[1]; s->nz = (int)ext3[2];
     s->link_owner.release(); s->link_axis_dev.release();
-    s->si_nominal_ok = false; s->si_consts_ok = false;
+    s->si_nominal_ok = false; s->si_consts_ok = false; s->si_pressure_ok = false;
 
     for (int i = 0; i < L; i++) {
         int id = link_material(s, s->vmat_id[s->lk_vn[i]], s->vmat_id[s->lk_vp[i]]);
@@ -1872,14 +1874,33 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
     const bool link_info = info == SI_STRAIN_ENERGY || info == SI_ENG_STRESS || info == SI_ENG_STRAIN;
     const int count = link_info ? s->L : s->N;
     if (count == 0) return VX_OK;                                  // src/Voxelyze.cpp:759,777
-    if (info == SI_PRESSURE) return fail(s, VX_ERR_UNSUPPORTED, "stateInfo(PRESSURE) is not available on the device yet");
     CK(cudaSetDevice(s->device));
     CK(s->si_minmax.alloc(2)); CK(s->si_sum.alloc(1));
     const float init[2] = {3.402823466e38f, -3.402823466e38f};
     CK(cudaMemcpyAsync(s->si_minmax.p, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemsetAsync(s->si_sum.p, 0, sizeof(double), s->stream));
     const int grid = std::min(blocks_for(count, 256), 148 * 8);
-    if (!link_info) {
+    if (info == SI_PRESSURE) {
+        if (!s->si_pressure_ok) {                                  // per-voxel link table, strain ratios, {E, nu}: caller order
+            std::vector<int> vl((size_t)6 * s->N, -1); std::vector<float> ratio(std::max(s->L, 1)); std::vector<float2> en(s->N);
+            for (int l = 0; l < s->L; l++) {
+                vl[(size_t)(2 * s->lk_axis[l]) * s->N + s->lk_vn[l]] = l;          // +axis slot of the negative-end voxel
+                vl[(size_t)(2 * s->lk_axis[l] + 1) * s->N + s->lk_vp[l]] = l;      // -axis slot of the positive-end voxel
+                ratio[l] = s->mats[s->vmat_id[s->lk_vp[l]]].E / s->mats[s->vmat_id[s->lk_vn[l]]].E;
+            }
+            for (int v = 0; v < s->N; v++) en[v] = make_float2(s->mats[s->vmat_id[v]].E, s->mats[s->vmat_id[v]].nu);
+            CK(s->si_vlinks.alloc(vl.size())); CK(s->si_ratio.alloc(ratio.size())); CK(s->si_en.alloc(en.size()));
+            CK(cudaMemcpy(s->si_vlinks.p, vl.data(), vl.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(s->si_ratio.p, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(s->si_en.p, en.data(), en.size() * sizeof(float2), cudaMemcpyHostToDevice));
+            s->si_pressure_ok = true;
+        }
+        CK(s->si_buf.alloc((size_t)std::max(s->L, 1) * sizeof(float)));
+        if (s->L) { int rc = gather_link_field(s, G_STRAIN, s->si_buf.p); if (rc != VX_OK) return rc; }
+        k_state_pressure<<<grid, 256, 0, s->stream>>>(s->N, s->si_vlinks.p, (const float*)s->si_buf.p, s->si_ratio.p, s->si_en.p,
+                                                      s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
+        s->launches++;
+    } else if (!link_info) {
         if (info == SI_DISPLACEMENT && !s->si_nominal_ok) {
             std::vector<double4> nom(s->N);
             for (int i = 0; i < s->N; i++) { int e = s->v_i2e[i]; nom[i] = make_double4(s->ijk[3 * e] * s->vox_size, s->ijk[3 * e + 1] * s->vox_size, s->ijk[3 * e + 2] * s->vox_size, 0.0); }

@@ -222,6 +222,33 @@ __global__ void __launch_bounds__(256) k_state_voxels(Frame f, int info, const d
     si_block_reduce(a, out_min, out_max, out_sum);
 }
 
+// CVX_Voxel::pressure (include/VX_Voxel.h:103-104): -E * volumetricStrain / (3 (1 - 2 nu)), volumetric strain = sum over the
+// axes of the voxel's strain (src/VX_Voxel.cpp:300-317: half-link strains, averaged when links exist on both sides), float.
+// vlinks[d * n + v]: caller index of the link of voxel v (caller order) in direction d or -1; strain: per-link axial strain;
+// ratio: CVX_Link::strainRatio (src/VX_Link.cpp:67); en: per voxel {E, nu}
+__global__ void __launch_bounds__(256) k_state_pressure(int n, const int* vlinks, const float* strain, const float* ratio, const float2* en,
+                                                        float* out_min, float* out_max, double* out_sum)
+{
+    StateAcc a; a.mn = 3.402823466e38f; a.mx = -3.402823466e38f; a.sum = 0.0;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        float s3[3] = {0.0f, 0.0f, 0.0f}; int cnt[3] = {0, 0, 0};
+        for (int d = 0; d < 6; d++) {
+            const int l = vlinks[(size_t)d * n + v];
+            if (l < 0) continue;
+            const float e = strain[l], r = ratio[l];
+            // direction d even: this voxel is the link's negative end (src/VX_Link.cpp:121-124)
+            s3[d >> 1] += (d & 1) ? 2.0f * e * r / (1.0f + r) : 2.0f * e / (1.0f + r);
+            cnt[d >> 1]++;
+        }
+        for (int k = 0; k < 3; k++) if (cnt[k] == 2) s3[k] *= 0.5f;
+        const float vol = (float)(s3[0] + s3[1] + s3[2]);
+        const float2 m = en[v];
+        const float val = -m.x * vol / (3 * (1 - 2 * m.y));
+        a.mn = fminf(a.mn, val); a.mx = fmaxf(a.mx, val); a.sum += (double)val;
+    }
+    si_block_reduce(a, out_min, out_max, out_sum);
+}
+
 // link quantities from a flat value array produced by the gather kernels (strain / stress) or from
 // force+moment triples (strain energy, src/VX_Link.cpp:251-257)
 __global__ void __launch_bounds__(256) k_state_links(int n, const float* scalar, const double* fneg, const double* mneg, const double* mpos,
