@@ -1,21 +1,27 @@
 // vx_lattice.cuh -- fused single-pass step for dense box lattices (the headline path).
 //
-// One kernel per doTimeStep: every thread owns one voxel of a full nx*ny*nz box (x fastest),
-// evaluates the (up to) six links that touch it, sums their forces in the reference's slot order
-// X+,X-,Y+,Y-,Z+,Z- and integrates the voxel -- link forces never travel through HBM.
-//   * The voxel reads only OLD poses (its own and its six face neighbours'), which is exactly
-//     what the reference's "all links, then all voxels" order does (src/Voxelyze.cpp:251-284),
-//     so state is kept in ping-pong buffers: read `cur`, write `nxt`, swap per step.
-//   * A link is owned by its negative-end voxel (its +X/+Y/+Z link).  The owner thread advances
-//     the link's persistent state; the positive-end voxel's thread re-evaluates the same link
-//     from the same old inputs (identical bits) just to obtain its own force -- 2x the FP64 work
-//     in exchange for ~45 % of the memory traffic of the two-kernel path.
+// One kernel launch per doTimeStep: the (up to) six links that touch a voxel are evaluated, their forces summed in
+// the reference's slot order X+,X-,Y+,Y-,Z+,Z- and the voxel integrated -- link forces never travel through HBM.
+//   * A voxel update reads only OLD poses (its own and its six face neighbours'), which is exactly what the
+//     reference's "all links, then all voxels" order does (src/Voxelyze.cpp:251-284), so state is kept in
+//     ping-pong buffers: read generation g, write g^1, swap per step.
+//   * A link is owned by its negative-end voxel (its +X/+Y/+Z link); the owner advances the link's persistent
+//     state.  Where the two ends of a link are handled by different warps/blocks the link is re-evaluated
+//     from the same old inputs (identical bits) instead of shipping its force.
 //   * Implicit indexing: neighbour = v +- {1, nx, nx*ny}; no index arrays are read.
+//
+// Kernels (all produce identical bits; vx_set_path selects, tests/test_gpu_parity.py compares them):
+//   k_lattice_tma     7, and what 0 picks on large lattices: one warp per 4x4x2 brick, staged by TMA  (2.9 ms @256^3)
+//   k_lattice_warp    5, and what 0 picks for ensembles of small boxes: same, staged by cp.async       (3.1 ms)
+//   k_lattice_tile    2: one block per 8x4x4 brick, thread per link evaluation, block barriers         (3.7 ms)
+//   k_lattice_step    3: one thread per voxel, all six links re-evaluated                              (4.0 ms)
+//   k_lattice_march   4: z-marching warps, X by shuffle, Z by register carry                           (4.6 ms)
+//   k_lattice_zmarch  6: marching warp bricks, 3.5 evaluations per voxel                               (4.1 ms)
 //
 // HBM traffic per voxel per step (nu = 0):  read 64 B pose + 48 B momenta + 3 x 64 B link records,
 // write the same = 608 B, vs. 216 + 3 x 268 = 1020 B "algorithmic" bytes of SURVEY.md section 8d (the
-// 96 B/link force write of the reference layout is not needed: forces of the last step can be
-// recomputed on demand from the two buffer generations, see k_lattice_link_forces).
+// 96 B/link force write of the reference layout is not needed: forces of the last step are
+// recomputed on demand from the two buffer generations, see k_lattice_gather_links).
 //
 // Link record (64 B): six doubles + float4 {strain, maxStrain, strainOffset, stress}.
 // The nine doubles pos2/angle1v/angle2v of the reference collapse to six without loss:
