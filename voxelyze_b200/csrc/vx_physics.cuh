@@ -57,6 +57,14 @@ __device__ __forceinline__ d3 qrot_inv(const q4& q, d3 f)
                tw * q.y - tx * q.z + ty * q.w + tz * q.x,
                tw * q.z + tx * q.y - ty * q.x + tz * q.w);
 }
+// Rare branches (rotations beyond a few degrees, non-linear material curves) are kept out of line: the hot path of a
+// link evaluation then is a third of the code, which matters because a fused kernel holds several copies of it and
+// the instruction cache is 128 KB.  Same arithmetic either way.
+__device__ __noinline__ void q_to_rotvec_acos(double w, double sl, double& scale_u, double& inv)
+{
+    scale_u = acos(w);
+    inv = 1.0 / sqrt(sl);
+}
 // quaternion -> rotation vector (include/Quat3D.h:117-122)
 __device__ __forceinline__ d3 q_to_rotvec(const q4& q)
 {
@@ -64,9 +72,14 @@ __device__ __forceinline__ d3 q_to_rotvec(const q4& q)
     double sl = 1.0 - q.w * q.w;
     d3 v = mk3(2.0 * q.x, 2.0 * q.y, 2.0 * q.z);
     if (sl < 2.4e-3) return sqrt((2 - 2 * q.w) / sl) * v;
-    d3 u = acos(q.w) * v;
-    double inv = 1.0 / sqrt(sl);
+    double a, inv;
+    q_to_rotvec_acos(q.w, sl, a, inv);
+    d3 u = a * v;
     return inv * u;
+}
+__device__ __noinline__ void q_from_rotvec_trig(double m2, double& w, double& s)
+{
+    double m = sqrt(m2); w = cos(m); s = sin(m) / m;
 }
 // rotation vector -> quaternion (include/Quat3D.h:124-139)
 __device__ __forceinline__ q4 q_from_rotvec(d3 v)
@@ -74,9 +87,20 @@ __device__ __forceinline__ q4 q_from_rotvec(d3 v)
     d3 h = 0.5 * v;
     double m2 = norm2(h), w, s;
     if (m2 * m2 < 5.328e-15) { w = 1.0 - 0.5 * m2; s = 1.0 - m2 / 6.0; }
-    else { double m = sqrt(m2); w = cos(m); s = sin(m) / m; }
+    else q_from_rotvec_trig(m2, w, s);
     q4 r; r.w = w; r.x = h.x * s; r.y = h.y * s; r.z = h.z * s;
     return r;
+}
+__device__ __noinline__ void q_align_to_x_large(double fx, double fy, double fz, double& qw, double& qy, double& qz)
+{
+    double l = sqrt(fx * fx + fy * fy + fz * fz);
+    double nx = fx, ny = fy, nz = fz;
+    if (l > 0) { double li = 1.0 / l; nx *= li; ny *= li; nz *= li; }
+    double theta = acos(nx);
+    if (theta > 3.14159265358979 - 1e-7) { qw = 0.0; qy = 1.0; qz = 0.0; return; }
+    double ami = 1.0 / sqrt(nz * nz + ny * ny);
+    double a = 0.5 * theta, s = sin(a);
+    qw = cos(a); qy = nz * ami * s; qz = -ny * ami * s;
 }
 // rotation that takes `from` onto +X (include/Quat3D.h:141-166), starting from identity
 __device__ __forceinline__ q4 q_align_to_x(d3 from)
@@ -90,14 +114,8 @@ __device__ __forceinline__ q4 q_align_to_x(d3 from)
         q.w = 1 + 0.5 * (-q.y * q.y - q.z * q.z);
         return q;
     }
-    double l = sqrt(from.x * from.x + from.y * from.y + from.z * from.z);
-    d3 n = from;
-    if (l > 0) { double li = 1.0 / l; n.x *= li; n.y *= li; n.z *= li; }
-    double theta = acos(n.x);
-    if (theta > 3.14159265358979 - 1e-7) { q.w = 0.0; q.x = 0.0; q.y = 1.0; q.z = 0.0; return q; }
-    double ami = 1.0 / sqrt(n.z * n.z + n.y * n.y);
-    double a = 0.5 * theta, s = sin(a);
-    q.w = cos(a); q.x = 0.0; q.y = n.z * ami * s; q.z = -n.y * ami * s;
+    q_align_to_x_large(from.x, from.y, from.z, q.w, q.y, q.z);
+    q.x = 0.0;
     return q;
 }
 
@@ -128,6 +146,25 @@ __device__ __forceinline__ d3 to_axis_original(int axis, d3 v)
 __device__ __forceinline__ bool mat_failed(const DevLinkMat& m, float strain) { return m.eps_fail != -1.0f && strain > m.eps_fail; }
 __device__ __forceinline__ bool mat_yielded(const DevLinkMat& m, float strain) { return m.eps_yield != -1.0f && strain > m.eps_yield; }
 
+// beyond the first segment of a data curve (src/VX_Material.cpp:176-194)
+__device__ __noinline__ float mat_stress_curve(const float* __restrict__ e, const float* __restrict__ s, int n, float nu, float strain, float tss)
+{
+    for (int i = 2; i < n; i++) {
+        float ei = __ldg(e + i);
+        if (strain <= ei || i == n - 1) {
+            float e0 = __ldg(e + i - 1), s0 = __ldg(s + i - 1), s1 = __ldg(s + i);
+            float perc = (strain - e0) / (ei - e0);
+            float basic = s0 + perc * (s1 - s0);
+            if (nu == 0.0f) return basic;
+            float modulus = (s1 - s0) / (ei - e0);
+            float mod_hat = modulus / ((1 - 2 * nu) * (1 + nu));
+            float eff = basic / modulus;
+            float eff_tss = tss * (eff / strain);
+            return mod_hat * ((1 - nu) * eff + nu * eff_tss);
+        }
+    }
+    return 0.0f;
+}
 __device__ __forceinline__ float mat_stress(const DevLinkMat& m, const float* __restrict__ ce, const float* __restrict__ cs,
                                             float strain, float tss, bool force_linear)
 {
@@ -137,22 +174,7 @@ __device__ __forceinline__ float mat_stress(const DevLinkMat& m, const float* __
         if (m.nu == 0.0f) return m.E * strain;
         return m.e_hat * ((1 - m.nu) * strain + m.nu * tss);
     }
-    int n = m.curve_n;
-    for (int i = 2; i < n; i++) {
-        float ei = __ldg(e + i);
-        if (strain <= ei || i == n - 1) {
-            float e0 = __ldg(e + i - 1), s0 = __ldg(s + i - 1), s1 = __ldg(s + i);
-            float perc = (strain - e0) / (ei - e0);
-            float basic = s0 + perc * (s1 - s0);
-            if (m.nu == 0.0f) return basic;
-            float modulus = (s1 - s0) / (ei - e0);
-            float mod_hat = modulus / ((1 - 2 * m.nu) * (1 + m.nu));
-            float eff = basic / modulus;
-            float eff_tss = tss * (eff / strain);
-            return mod_hat * ((1 - m.nu) * eff + m.nu * eff_tss);
-        }
-    }
-    return 0.0f;
+    return mat_stress_curve(e, s, m.curve_n, m.nu, strain, tss);
 }
 
 // persistent state of one link (include/VX_Link.h:74-107)
