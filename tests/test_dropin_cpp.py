@@ -98,3 +98,21 @@ def test_mid_run_edits_keep_the_state_of_untouched_links(binaries):
     scale = np.abs(a - nominal).max()
     assert scale > 1e-5                                                                    # a residual (plastic) deflection remains
     assert np.abs(a - b).max() <= 1e-7 * scale, np.abs(a - b).max() / scale
+
+
+def test_json_loader_survives_malformed_files(binaries, tmp_path):
+    """Truncated / wrong-typed / out-of-range input never crashes the loader; what is valid is kept
+    (like CVoxelyze::loadJSON, which reports success whenever the file could be opened, src/Voxelyze.cpp:61-76)."""
+    samples = ['', '{', '{"voxelSize": 0.01', '{"voxelSize": 0.01, "materials": [', '[1,2,3]', '{"voxelSize": "x", "materials": 5}',
+               '{"voxelSize": 0.01, "materials": [{"youngsModulus": 1e6}], "voxels": [0,0,0']
+    for k, text in enumerate(samples):
+        p = tmp_path / f"bad{k}.json"
+        p.write_text(text)
+        out = _run(binaries["b200"], "--json-digest", str(p))
+        assert "voxels 0" in out, (text, out)
+    p = tmp_path / "partly.json"
+    p.write_text('{"voxelSize": 0.01, "materials": [{"strainData": [0.0, 0.1, 0.2], "stressData": [0.0, 1e5, 1.5e5]}], '
+                 '"voxels": [0,0,0,0, 1,0,0,0, 2,0,0,7], '
+                 '"externals": [{"voxelIndices": [0, 99], "fixed": [true,true,true,true,true,true]}, {"fixed": [true]}]}')
+    out = _run(binaries["b200"], "--json-digest", str(p))
+    assert "materials 1 voxels 2" in out and "linear 0" in out and "vox 0 at 0 0 0 mat 0 fixed 111111" in out
