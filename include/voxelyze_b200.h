@@ -330,6 +330,10 @@ int  vx_sync(vx_sim* s);
  * else (Poisson pre-pass, collisions), ms[3] whole steps; launches[0..2] = kernel launches
  * per group.  Same arithmetic as vx_step.                                                 */
 int  vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches);
+/* the watched pairs like vx_collision_pairs plus the contact force of the last step on each
+ * (CVX_Collision::contactForce, src/VX_Collision.cpp:34-56: `force` acts on the first voxel, -force
+ * on the second); forces: 3 floats per pair, same order as pairs.                              */
+int  vx_collision_forces(vx_sim* s, int32_t* pairs, float* forces, int cap, int* n_pairs);
 /* persistent state of links [first, first+count) (caller link order, vx_get_links) as packed records:
  * what CVX_Link keeps between steps (include/VX_Link.h:74-107).  Upload is how a caller carries
  * the state of surviving links across vx_set_voxels (the reference's setVoxel only recreates the

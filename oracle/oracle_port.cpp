@@ -1116,6 +1116,7 @@ int vx_slab_step(vx_sim*, float, int, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_slab_exchange(vx_sim*) { return VX_ERR_UNSUPPORTED; }
 int vx_save_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
 int vx_load_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
+int vx_collision_forces(vx_sim*, int32_t*, float*, int, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_download_link_state(vx_sim*, int, int, vx_link_state*) { return VX_ERR_UNSUPPORTED; }
 int vx_upload_link_state(vx_sim*, int, int, const vx_link_state*) { return VX_ERR_UNSUPPORTED; }
 int64_t vx_launch_count(const vx_sim*) { return 0; }

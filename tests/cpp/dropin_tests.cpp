@@ -502,6 +502,87 @@ static void voxelExternals()            // tVX_Voxel.h:3-68
     CHECK_NEAR(vox.external()->rotationQuat().w, std::cos(0.125), 1e-15);
 }
 
+static void largeDeformationDamping()    // tVoxelyze.h:445-473
+{
+    CVoxelyze Sim(0.001);
+    CVX_Material* pMat1 = Sim.addMaterial(1e6f, 1e3f);
+    pMat1->setInternalDamping(1.0);
+    pMat1->setGlobalDamping(0.2f);
+    CVX_Voxel* pV1 = Sim.setVoxel(pMat1, 0, 0, 0);
+    CVX_Voxel* pV2 = Sim.setVoxel(pMat1, 1, 0, 0);
+    float ts = Sim.recommendedTimeStep();
+    pV1->external()->setFixedAll();
+    pV2->external()->setForce(-0.2f, 0.0f, 0.2f);
+    for (int k = 0; k < 200; k++) Sim.doTimeStep(ts);
+    CHECK_NEAR(9.5587e-4, pV2->position().z, 1e-7);
+}
+
+static void poissonsLarge()              // tVoxelyze.h:715-769, 9x2x2, nu = 0.3: corner offsets, size(), reaction forces
+{
+    CVoxelyze Sim(0.001);
+    CVX_Material* pMat1 = Sim.addMaterial(1e6f, 1e3f);
+    float mu = 0.3f;
+    pMat1->setPoissonsRatio(mu);
+    pMat1->setInternalDamping(1.0f);
+    pMat1->setGlobalDamping(0.2f);
+    for (int i = 0; i < 9; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+        CVX_Voxel* pV = Sim.setVoxel(pMat1, i, j, k);
+        if (i == 0) pV->external()->setFixedAll();
+        if (i == 8) pV->external()->setDisplacementAll(Vec3D<>(1e-3f, 0, 0));
+    }
+    float ts = Sim.recommendedTimeStep();
+    for (int i = 0; i < 300; i++) Sim.doTimeStep(ts);
+    CHECK_NEAR(5e-4, (float)(Sim.voxel(4, 0, 0)->position().x - 0.004), 1e-7);
+    Vec3D<float> curSize = 2 * Sim.voxel(4, 0, 0)->cornerOffset(CVX_Voxel::PPP);
+    Vec3D<float> curStrain = curSize - Vec3D<float>(0.001f, 0.001f, 0.001f);
+    curStrain /= 0.001f;
+    CHECK_NEAR(1.306e-1, curStrain.x, 1e-3);
+    CHECK_NEAR(-4.048e-2, curStrain.y, 1e-5);
+    CHECK_NEAR(-4.048e-2, curStrain.z, 1e-5);
+    float eHat = pMat1->youngsModulus() / ((1 - 2 * mu) * (1 + mu));
+    float sigmaX = eHat * ((1 - mu) * curStrain.x + mu * (curStrain.y + curStrain.z));
+    Vec3D<float> curSize2 = Sim.voxel(4, 0, 0)->size();
+    float fX = sigmaX * 4 * curSize2.y * curSize2.z;
+    float totalForce = 0;
+    for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) totalForce += Sim.voxel(8, j, k)->externalForce().x;
+    CHECK_NEAR(totalForce, fX, 0.01);
+    CHECK(totalForce > 0.05f);                                    // the reaction really is there (about 0.5 N)
+}
+
+static void poissonsHigh()               // tVoxelyze.h:771-803, 5x3x3, nu = 0.495
+{
+    CVoxelyze Sim(0.001);
+    CVX_Material* pMat1 = Sim.addMaterial(1e6f, 1e3f);
+    pMat1->setPoissonsRatio(0.495f);
+    pMat1->setInternalDamping(1.0f);
+    pMat1->setGlobalDamping(2.0f);
+    for (int i = 0; i < 5; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) {
+        CVX_Voxel* pV = Sim.setVoxel(pMat1, i, j, k);
+        if (i == 0) pV->external()->setFixedAll();
+        if (i == 4) pV->external()->setDisplacementAll(Vec3D<>(1e-5f, 0, 0));
+    }
+    float ts = Sim.recommendedTimeStep();
+    for (int i = 0; i < 300; i++) Sim.doTimeStep(ts);
+    CHECK_NEAR(5e-6, (float)(Sim.voxel(2, 1, 1)->position().x - 0.002), 1e-9);
+}
+
+static void poissonsMixed()              // tVoxelyze.h:806-842, 7x3x3, nu = 0.3 around a nu = 0 core
+{
+    CVoxelyze Sim(0.001);
+    CVX_Material* pMat1 = Sim.addMaterial(1e6f, 1e3f);
+    pMat1->setPoissonsRatio(0.3f); pMat1->setInternalDamping(1.0f); pMat1->setGlobalDamping(0.3f);
+    CVX_Material* pMat2 = Sim.addMaterial(1e6f, 1e3f);
+    pMat2->setPoissonsRatio(0.0f); pMat2->setInternalDamping(1.0f); pMat2->setGlobalDamping(0.3f);
+    for (int i = 0; i < 7; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) {
+        CVX_Voxel* pV = Sim.setVoxel((i > 1 && i < 6) ? pMat2 : pMat1, i, j, k);
+        if (i == 0) pV->external()->setFixedAll();
+        if (i == 6) pV->external()->setDisplacementAll(Vec3D<>(1e-3f, 0, 0));
+    }
+    float ts = Sim.recommendedTimeStep();
+    for (int i = 0; i < 300; i++) Sim.doTimeStep(ts);
+    CHECK_NEAR(5e-4, (float)(Sim.voxel(3, 1, 1)->position().x - 0.003), 5e-6);
+}
+
 // ---- *.vxl.json (Voxelyze.cpp:61-241, VX_Material.cpp:75-163): a model with two materials and three kinds of
 // externals; written by one implementation, it must load into the same model in either.
 static void buildJsonModel(CVoxelyze& Vx)
@@ -650,6 +731,8 @@ int main(int argc, char** argv)
         {"deformableMaterial", deformableMaterial, true}, {"replaceMaterialMidRun", replaceMaterialMidRun, true},
         {"temperatureBimorph", temperatureBimorph, true}, {"staticFriction", staticFriction, true}, {"kineticFriction", kineticFriction, true},
         {"collisionsHoldUp", collisionsHoldUp, true}, {"stateInfoBasics", stateInfoBasics, true}, {"jsonRoundTrip", jsonRoundTrip, true},
+        {"largeDeformationDamping", largeDeformationDamping, true}, {"poissonsLarge", poissonsLarge, true}, {"poissonsHigh", poissonsHigh, true},
+        {"poissonsMixed", poissonsMixed, true},
 #ifndef DROPIN_REFERENCE
         {"stateCheckpoint", stateCheckpoint, true},
 #endif

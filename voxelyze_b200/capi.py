@@ -171,6 +171,7 @@ class VxLib:
             "vx_load_state": (i32, [vp, C.c_char_p]),
             "vx_download_link_state": (i32, [vp, i32, i32, C.c_void_p]),
             "vx_upload_link_state": (i32, [vp, i32, i32, C.c_void_p]),
+            "vx_collision_forces": (i32, [vp, C.c_void_p, C.c_void_p, i32, C.POINTER(i32)]),
             "vx_set_path": (i32, [vp, i32]),
             "vx_active_path": (i32, [vp]),
             "vx_kernel_name": (C.c_char_p, [vp]),

@@ -1163,6 +1163,30 @@ int vx_load_state(vx_sim* s, const char* path)
     return VX_OK;
 }
 
+int vx_collision_forces(vx_sim* s, int32_t* pairs, float* forces, int cap, int* n_pairs)
+{
+    if (!s) return VX_ERR_ARG;
+    const int P = (s->collisions && s->col_tables) ? s->n_pairs : 0;
+    if (n_pairs) *n_pairs = P;
+    if ((!pairs && !forces) || P == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    std::vector<int2> raw(P); std::vector<float4> fr(P); std::vector<int> orig(s->n_surf);
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy(raw.data(), s->c_pairs.p, (size_t)P * sizeof(int2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(fr.data(), s->c_pair_force.p, (size_t)P * sizeof(float4), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(orig.data(), s->c_surf_orig.p, (size_t)s->n_surf * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> order(P);
+    for (int k = 0; k < P; k++) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        return std::make_pair(orig[raw[a].x], orig[raw[a].y]) < std::make_pair(orig[raw[b].x], orig[raw[b].y]); });
+    for (int k = 0; k < P && k < cap; k++) {
+        const int q = order[k];
+        if (pairs) { pairs[2 * k] = orig[raw[q].x]; pairs[2 * k + 1] = orig[raw[q].y]; }
+        if (forces) { forces[3 * k] = fr[q].x; forces[3 * k + 1] = fr[q].y; forces[3 * k + 2] = fr[q].z; }
+    }
+    return VX_OK;
+}
+
 // ---- packed link state (topology edits and layout changes keep the state of surviving links) -------
 int vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst)
 {

@@ -37,6 +37,9 @@ public:
     Vec3D<double> position() const;
     Vec3D<double> originalPosition() const { double s = mat->nominalSize(); return Vec3D<double>(ix * s, iy * s, iz * s); }
     Vec3D<double> displacement() const { return position() - originalPosition(); }
+    Vec3D<float> size() const { return cornerOffset(PPP) - cornerOffset(NNN); }       // VX_Voxel.h:82
+    Vec3D<float> cornerPosition(voxelCorner corner) const;                               // VX_Voxel.cpp:141-144
+    Vec3D<float> cornerOffset(voxelCorner corner) const;                                 // VX_Voxel.cpp:146-159
     bool isInterior() const { return linkCount() == 6; }
     bool isSurface() const { return !isInterior(); }
 
@@ -58,12 +61,24 @@ public:
     float kineticEnergy() const
     { return (float)(0.5 * (mat->massProps().mass_inv * linearMomentum().Length2() + mat->massProps().inertia_inv * angularMomentum().Length2())); }
 
+    float volumetricStrain() const { Vec3D<float> s = strain(false); return (float)(s.x + s.y + s.z); }     // VX_Voxel.h:103
+    float pressure() const { return -mat->youngsModulus() * volumetricStrain() / (3 * (1 - 2 * mat->poissonsRatio())); }
+
     bool isYielded() const;
     bool isFailed() const;
 
     float temperature() { return temperatureValue(); }
     void setTemperature(float temperature);
     void haltMotion();
+
+    Vec3D<float> externalForce();                  // applied force, or the reaction on fixed degrees of freedom (VX_Voxel.cpp:115-125)
+    Vec3D<float> externalMoment();
+    Vec3D<double> force();                         // sum of the forces on this voxel, GCS (VX_Voxel.cpp:234-256)
+    Vec3D<double> moment();
+    float transverseArea(CVX_Link::linkAxis axis);
+    float transverseStrainSum(CVX_Link::linkAxis axis);
+    Vec3D<float> strain(bool poissonsStrain) const;            // LCS voxel strain (VX_Voxel.cpp:300-334; private in the reference)
+    bool isFloorEnabled() const;                   // the floor is a property of the whole simulation here (CVoxelyze::enableFloor)
 
     bool isFloorStaticFriction() const;
     float floorPenetration() const { return (float)(baseSizeAverage() / 2 - mat->nominalSize() / 2 - position().z); }

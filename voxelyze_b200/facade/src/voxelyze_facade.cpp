@@ -236,6 +236,113 @@ void CVX_Voxel::haltMotion()
     vx_upload(sim->h, VX_F_ANGMOM, index, 1, zero);
     sim->epoch++;
 }
+// ---- derived quantities, computed on the host from the mirrored state exactly as the reference does
+Vec3D<float> CVX_Voxel::cornerOffset(voxelCorner corner) const
+{
+    Vec3D<> strains;
+    for (int i = 0; i < 3; i++) {
+        bool posLink = (corner & (1 << (2 - i))) != 0;
+        CVX_Link* pL = links[2 * i + (posLink ? 0 : 1)];
+        if (pL && !pL->isFailed()) strains[i] = (1 + pL->axialStrain(posLink)) * (posLink ? 1 : -1);
+        else strains[i] = posLink ? 1.0 : -1.0;
+    }
+    return (Vec3D<float>)((0.5 * baseSize()).Scale(strains));
+}
+Vec3D<float> CVX_Voxel::cornerPosition(voxelCorner corner) const
+{
+    return (Vec3D<float>)position() + (Vec3D<float>)orientation().RotateVec3D((Vec3D<double>)cornerOffset(corner));
+}
+Vec3D<float> CVX_Voxel::strain(bool poissonsStrain) const
+{
+    Vec3D<float> ret(0, 0, 0);
+    int n[3] = {0, 0, 0};
+    bool tension[3] = {false, false, false};
+    for (int i = 0; i < 6; i++) {
+        if (!links[i]) continue;
+        int axis = toAxis((linkDirection)i);
+        ret[axis] += links[i]->axialStrain(isNegative((linkDirection)i));
+        n[axis]++;
+    }
+    for (int i = 0; i < 3; i++) {
+        if (n[i] == 2) ret[i] *= 0.5f;
+        if (poissonsStrain) tension[i] = (n[i] == 2) || (ext && (n[i] == 1 && (ext->isFixed((dofComponent)(1 << i)) || ext->force()[i] != 0)));
+    }
+    if (poissonsStrain && !(tension[0] && tension[1] && tension[2])) {
+        float add = 0;
+        for (int i = 0; i < 3; i++) if (tension[i]) add += ret[i];
+        float value = (float)pow(1.0f + add, -mat->poissonsRatio()) - 1.0f;
+        for (int i = 0; i < 3; i++) if (!tension[i]) ret[i] = value;
+    }
+    return ret;
+}
+float CVX_Voxel::transverseStrainSum(CVX_Link::linkAxis axis)
+{
+    if (mat->poissonsRatio() == 0) return 0;
+    Vec3D<float> ps = strain(true);
+    switch (axis) {
+    case CVX_Link::X_AXIS: return ps.y + ps.z;
+    case CVX_Link::Y_AXIS: return ps.x + ps.z;
+    case CVX_Link::Z_AXIS: return ps.x + ps.y;
+    default: return 0.0f;
+    }
+}
+float CVX_Voxel::transverseArea(CVX_Link::linkAxis axis)
+{
+    float size = (float)mat->nominalSize();
+    if (mat->poissonsRatio() == 0) return size * size;
+    Vec3D<> ps = (Vec3D<>)strain(true);
+    switch (axis) {
+    case CVX_Link::X_AXIS: return (float)(size * size * (1 + ps.y) * (1 + ps.z));
+    case CVX_Link::Y_AXIS: return (float)(size * size * (1 + ps.x) * (1 + ps.z));
+    case CVX_Link::Z_AXIS: return (float)(size * size * (1 + ps.x) * (1 + ps.y));
+    default: return size * size;
+    }
+}
+bool CVX_Voxel::isFloorEnabled() const { return sim ? sim->isFloorEnabled() : false; }
+Vec3D<double> CVX_Voxel::force()
+{
+    Vec3D<double> total(0, 0, 0);
+    for (int i = 0; i < 6; i++) if (links[i]) total += links[i]->force(isNegative((linkDirection)i));     // LCS
+    total = orientation().RotateVec3D(total);
+    if (externalExists()) total += (Vec3D<double>)external()->force();
+    total -= velocity() * (double)mat->globalDampingTranslateC();
+    total.z += -mat->mass() * 9.80665f * mat->gravMult_;                                                       // gravityForce(), VX_MaterialVoxel.h:44
+    if (sim && sim->isCollisionsEnabled()) {
+        for (CVX_Collision* c : *sim->collisionList()) total -= (Vec3D<double>)c->contactForce(this);
+    }
+    return total;
+}
+Vec3D<double> CVX_Voxel::moment()
+{
+    Vec3D<double> total(0, 0, 0);
+    for (int i = 0; i < 6; i++) if (links[i]) total += links[i]->moment(isNegative((linkDirection)i));
+    total = orientation().RotateVec3D(total);
+    if (externalExists()) total += (Vec3D<double>)external()->moment();
+    total -= angularVelocity() * (double)mat->globalDampingRotateC();
+    return total;
+}
+Vec3D<float> CVX_Voxel::externalForce()
+{
+    Vec3D<float> ret(external()->force());
+    if (ext->isFixed(X_TRANSLATE) || ext->isFixed(Y_TRANSLATE) || ext->isFixed(Z_TRANSLATE)) {
+        Vec3D<float> reaction = (Vec3D<float>)(-force());
+        if (ext->isFixed(X_TRANSLATE)) ret.x = reaction.x;
+        if (ext->isFixed(Y_TRANSLATE)) ret.y = reaction.y;
+        if (ext->isFixed(Z_TRANSLATE)) ret.z = reaction.z;
+    }
+    return ret;
+}
+Vec3D<float> CVX_Voxel::externalMoment()
+{
+    Vec3D<float> ret(external()->moment());
+    if (ext->isFixed(X_ROTATE) || ext->isFixed(Y_ROTATE) || ext->isFixed(Z_ROTATE)) {
+        Vec3D<float> reaction = (Vec3D<float>)(-moment());
+        if (ext->isFixed(X_ROTATE)) ret.x = reaction.x;
+        if (ext->isFixed(Y_ROTATE)) ret.y = reaction.y;
+        if (ext->isFixed(Z_ROTATE)) ret.z = reaction.z;
+    }
+    return ret;
+}
 bool CVX_Voxel::isYielded() const { for (int i = 0; i < 6; i++) if (links[i] && links[i]->isYielded()) return true; return false; }
 bool CVX_Voxel::isFailed() const { for (int i = 0; i < 6; i++) if (links[i] && links[i]->isFailed()) return true; return false; }
 
@@ -622,10 +729,14 @@ const std::vector<CVX_Collision*>* CVoxelyze::collisionList() const
     for (CVX_Collision* c : collisionsList) delete c;
     collisionsList.clear();
     int n = 0;
-    vx_collision_pairs(h, nullptr, 0, &n);
-    std::vector<int32_t> p(2 * (size_t)n);
-    if (n) vx_collision_pairs(h, p.data(), n, &n);
-    for (int k = 0; k < n; k++) collisionsList.push_back(new CVX_Collision(voxelsList[p[2 * k]], voxelsList[p[2 * k + 1]]));
+    vx_collision_forces(h, nullptr, nullptr, 0, &n);
+    std::vector<int32_t> p(2 * (size_t)n); std::vector<float> fr(3 * (size_t)n);
+    if (n) vx_collision_forces(h, p.data(), fr.data(), n, &n);
+    for (int k = 0; k < n; k++) {
+        CVX_Collision* c = new CVX_Collision(voxelsList[p[2 * k]], voxelsList[p[2 * k + 1]]);
+        c->f_ = Vec3D<float>(fr[3 * k], fr[3 * k + 1], fr[3 * k + 2]);
+        collisionsList.push_back(c);
+    }
     return &collisionsList;
 }
 
