@@ -691,9 +691,32 @@ static void printEditScenario()
         Vec3D<double> p = Vx.voxel(i)->position();
         printf("vox %d %.12e %.12e %.12e\n", i, p.x, p.y, p.z);
     }
+    // a new voxel size scales positions, halts motion and restarts the links (Voxelyze.cpp:643-668)
+    Vx.setVoxelSize(0.0015);
+    float dt2 = Vx.recommendedTimeStep();
+    for (int i = 0; i < 200; i++) Vx.doTimeStep(dt2);
+    for (int i = 0; i < Vx.voxelCount(); i += 5) {
+        Vec3D<double> q = Vx.voxel(i)->position();
+        printf("vox %d %.12e %.12e %.12e\n", 200 + i, q.x, q.y, q.z);
+    }
 }
 
 #ifndef DROPIN_REFERENCE
+static void copyTakesTheModel()         // Voxelyze.cpp:39-58; in the reference the copied materials come out broken (_sqrtMass negated,
+{                                       // VX_MaterialVoxel.cpp:47) and the copy diverges at once, so this can only be checked on the facade
+    CVoxelyze A(0.002);
+    buildJsonModel(A);
+    float dt = A.recommendedTimeStep();
+    for (int i = 0; i < 50; i++) A.doTimeStep(dt);
+    CVoxelyze B(0.001);
+    B = A;                                                           // model only: B starts at rest
+    CVoxelyze C(0.002);
+    buildJsonModel(C);
+    CHECK(B.voxelSize() == 0.002 && B.voxelCount() == C.voxelCount() && B.materialCount() == C.materialCount());
+    CHECK(B.gravity() == 1.0f && B.isFloorEnabled());
+    for (int i = 0; i < 120; i++) { B.doTimeStep(dt); C.doTimeStep(dt); }
+    for (int i = 0; i < B.voxelCount(); i++) CHECK(B.voxel(i)->position().z == C.voxel(i)->position().z && B.voxel(i)->position().x == C.voxel(i)->position().x);
+}
 static void stateCheckpoint()           // facade extra: saveState / loadState (the reference cannot checkpoint, Voxelyze.h:78)
 {
     std::string path = g_tmpdir + "/dropin_state.bin";
@@ -734,7 +757,7 @@ int main(int argc, char** argv)
         {"largeDeformationDamping", largeDeformationDamping, true}, {"poissonsLarge", poissonsLarge, true}, {"poissonsHigh", poissonsHigh, true},
         {"poissonsMixed", poissonsMixed, true},
 #ifndef DROPIN_REFERENCE
-        {"stateCheckpoint", stateCheckpoint, true},
+        {"stateCheckpoint", stateCheckpoint, true}, {"copyTakesTheModel", copyTakesTheModel, true},
 #endif
     };
     bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";

@@ -42,7 +42,7 @@ def test_facade_host_only_classes(binaries):
 @pytest.mark.gpu
 def test_facade_passes_the_dropin_source_on_gpu(binaries):
     out = _run(binaries["b200"])
-    assert "0 failures" in out and "27 tests" in out
+    assert "0 failures" in out and "28 tests" in out
 
 
 def test_vxl_json_files_are_interchangeable(binaries, tmp_path):
@@ -95,7 +95,7 @@ def test_mid_run_edits_keep_the_state_of_untouched_links(binaries):
     a = np.array([[float(x) for x in l.split()[2:]] for l in ref[2:]])
     b = np.array([[float(x) for x in l.split()[2:]] for l in got[2:]])
     nominal = np.array([[i, j, k] for k in range(2) for j in range(2) for i in range(8)]) * 0.001
-    scale = np.abs(a - nominal).max()
+    scale = np.abs(a[:32] - nominal).max()          # rows 32.. : a few voxels after setVoxelSize(0.0015) and 200 more steps
     assert scale > 1e-5                                                                    # a residual (plastic) deflection remains
     assert np.abs(a - b).max() <= 1e-7 * scale, np.abs(a - b).max() / scale
 

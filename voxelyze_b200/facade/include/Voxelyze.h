@@ -39,6 +39,8 @@ public:
     CVoxelyze(double voxelSize = DEFAULT_VOXEL_SIZE);
     CVoxelyze(const char* jsonFilePath) : voxSize(DEFAULT_VOXEL_SIZE) { loadJSON(jsonFilePath); }   // include/Voxelyze.h:70
     ~CVoxelyze();
+    CVoxelyze(CVoxelyze& VIn) : voxSize(DEFAULT_VOXEL_SIZE) { *this = VIn; }     // include/Voxelyze.h:73: a copy of the MODEL (materials, voxels,
+    CVoxelyze& operator=(CVoxelyze& VIn);                                           // externals, environment), not of the dynamic state
 
     bool loadJSON(const char* jsonFilePath);    // include/Voxelyze.h:77
     bool saveJSON(const char* jsonFilePath);    // include/Voxelyze.h:78 (initial configuration only, like the reference)
@@ -75,6 +77,7 @@ public:
     const std::vector<CVX_Link*>* linkList() const;
     const std::vector<CVX_Collision*>* collisionList() const;
 
+    void setVoxelSize(double voxelSize);            // src/Voxelyze.cpp:643-668: positions scale, motion halts, links restart
     double voxelSize() const { return voxSize; }
 
     void setAmbientTemperature(float relativeTemperature, bool allVoxels = false);

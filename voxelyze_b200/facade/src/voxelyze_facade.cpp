@@ -383,6 +383,43 @@ float CVX_Link::axialStiffness() { return mat->a1(); }      // nu = 0 value (src
 CVoxelyze::CVoxelyze(double voxelSize) : voxSize(voxelSize) {}
 CVoxelyze::~CVoxelyze() { clear(); if (h) vx_destroy(h); }
 
+CVoxelyze& CVoxelyze::operator=(CVoxelyze& VIn)             // src/Voxelyze.cpp:39-58
+{
+    setVoxelSize(VIn.voxSize);
+    setAmbientTemperature(VIn.ambientTemperature(), true);
+    setGravity(VIn.gravity());
+    enableFloor(VIn.isFloorEnabled());
+    enableCollisions(VIn.isCollisionsEnabled());
+    std::unordered_map<CVX_Material*, CVX_Material*> matMap;
+    for (int i = 0; i < VIn.materialCount(); i++) matMap[VIn.material(i)] = addMaterial(*(VIn.material(i)));
+    for (int i = 0; i < VIn.voxelCount(); i++) {
+        CVX_Voxel* pVIn = VIn.voxel(i);
+        CVX_Voxel* pVOut = setVoxel(matMap[pVIn->material()], pVIn->indexX(), pVIn->indexY(), pVIn->indexZ());
+        *pVOut->external() = *pVIn->external();
+    }
+    return *this;
+}
+
+void CVoxelyze::setVoxelSize(double voxelSize)
+{
+    const double scale = voxelSize / voxSize;
+    const bool had = stepped && h && !voxelsList.empty();
+    if (had) fetchAll();
+    voxSize = voxelSize;
+    for (CVX_MaterialVoxel* m : voxelMats) m->setNominalSize(voxelSize);
+    for (CVX_MaterialLink* m : linkMats) delete m;            // combined materials depend on the size: rebuilt on demand
+    linkMats.clear();
+    if (h) { vx_destroy(h); h = nullptr; }                    // the voxel size is a property of the device handle
+    topologyDirty = envDirty = true; matChangesSeen = ~0ull; extChangesSeen = ~0ull;
+    linkStateFetched = false; linkStateMirror.clear(); editedVoxels.clear();        // links restart (CVX_Link::reset)
+    if (had) {
+        for (double& p : mPos) p *= scale;
+        std::fill(mLin.begin(), mLin.end(), 0.0); std::fill(mAng.begin(), mAng.end(), 0.0);     // haltMotion()
+        for (uint32_t& fl : mFlags) fl &= ~VX_VF_STATIC_FRICTION;
+    }
+    epoch++;
+}
+
 void CVoxelyze::die(const char* what) const
 {
     fprintf(stderr, "voxelyze_b200: %s: %s\n", what, h ? vx_last_error(h) : "no CUDA device handle (this build has no CPU fallback)");
