@@ -100,6 +100,8 @@ def cpu_reference_arm(args, sample_n: int, emit: bool):
     from voxelyze_b200 import capi, scenarios
     kind, cores = "reference", os.cpu_count() or 1
     if os.path.exists(capi.REF_OMP_SO):
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            os.environ["OMP_NUM_THREADS"] = str(cores)      # torchrun pins it to 1; rank 0 is the only rank that computes here
         os.environ.setdefault("OMP_NUM_THREADS", str(cores))
         os.environ.setdefault("OMP_PROC_BIND", "close")
         lib = capi.load_reference(omp=True)
