@@ -260,7 +260,7 @@ def main():
                            "voxels": n_vox, "links": n_link, "dt": dt, "path": runner.path_name(), **({"halo": runner.halo_name()} if world > 1 else {}),
                            "l2": "inputs larger than L2 (no flush needed)"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # the CPU baseline is reported at N = 1 only (other ranks would wait on it)
             cb_args = argparse.Namespace(**vars(args)); cb_args.steps, cb_args.warmup = 10, 2
             line["cpu_baseline"] = cpu_reference_arm(cb_args, args.cpu_sample, emit=False)
         print(json.dumps(line), flush=True)
