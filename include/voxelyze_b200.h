@@ -356,8 +356,8 @@ int  vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* 
 int  vx_save_state(vx_sim* s, const char* path);
 int  vx_load_state(vx_sim* s, const char* path);
 /* select kernel variant (tests and ablations; takes effect at the next vx_set_voxels):
- *   0 auto: fused lattice kernel for dense boxes without Poisson coupling or collisions,
- *           general path otherwise
+ *   0 auto: fused lattice kernel for bodies that fill at least 62.5 % of their bounding box (holes are
+ *           padded with inert cells) without Poisson coupling or collisions, general path otherwise
  *   1 general two-kernel path (k_link<AXIS> x3 + k_voxel), any topology
  *   fused lattice variants, all bit-identical to path 1:
  *   2 block bricks 8x4x4 (k_lattice_tile)     3 one thread per voxel (k_lattice_step)

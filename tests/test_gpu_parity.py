@@ -85,7 +85,13 @@ def test_lattice_path_is_selected_for_full_boxes(product):
     assert scenarios.build(product, scenarios.cantilever(6, 3, 3), path=1).active_path() == 1
     assert scenarios.build(product, scenarios.robot_ensemble(2, 3)).active_path() == 2
     assert scenarios.build(product, cases.BY_NAME["temperature_bimorph"].make()).active_path() == 2
-    assert scenarios.build(product, cases.BY_NAME["mixed_six"].make()).active_path() == 1      # not a full box
+    # a box with holes (6 of 2x2x2 cells) is filled up with inert cells and still runs fused; a sparse shape does not
+    six = scenarios.build(product, cases.BY_NAME["mixed_six"].make())
+    assert six.active_path() == 2 and six.n_voxels == 6
+    assert scenarios.build(product, cases.BY_NAME["mixed_six"].make(), path=1).active_path() == 1
+    ell = [[i, 0, 0] for i in range(5)] + [[0, j, 0] for j in range(1, 5)]
+    sparse = scenarios.Scenario("ell", 0.001, [Material()], np.array(ell, np.int32), np.zeros(len(ell), np.uint16))
+    assert scenarios.build(product, sparse).active_path() == 1
     assert scenarios.build(product, cases.BY_NAME["poisson_block"].make()).active_path() == 1  # nu != 0
 
 
@@ -466,3 +472,37 @@ def test_ensemble_members_stay_independent_on_both_stagings(product, path):
         snaps[p] = parity.snapshot(sim)
     for f in snaps[1]:
         assert parity.bit_equal(snaps[1][f], snaps[path][f]), f
+
+
+def test_box_with_holes_runs_fused_and_matches_the_general_path_bitwise(product, oracle):
+    """An irregular body (a block with a notch, a pocket and a through hole; two materials) is padded with inert fill
+    cells to its bounding box and stepped by the fused lattice kernels: same bits as the general path, same voxel and
+    link lists for the caller, stateInfo over real voxels only, and the usual parity with the oracle."""
+    ijk = [[i, j, k] for k in range(5) for j in range(6) for i in range(9)
+           if not (i >= 6 and k >= 3) and not (2 <= i <= 3 and 2 <= j <= 3) and not (i == 7 and j == 1 and k <= 1)]
+    ijk = np.array(ijk, np.int32)
+    mats = [Material(E=1e6, rho=1e3, zeta_global=0.02), Material(E=4e6, rho=2e3, zeta_global=0.02)]
+    mat = ((ijk[:, 0] + ijk[:, 2]) % 2).astype(np.uint16)
+    sc = scenarios.Scenario("holes", 0.002, mats, ijk, mat, gravity=1.0, floor=True)
+    fixed = np.nonzero(ijk[:, 0] == 0)[0]; load = np.nonzero(ijk[:, 0] == 8)[0]
+    sc = scenarios._externals(sc, fixed, load, [0.0, 0.002, -0.004])
+    assert len(ijk) < 9 * 6 * 5 and 9 * 6 * 5 <= 1.6 * len(ijk)
+    runs = {}
+    for path in (0, 5, 1):
+        g = scenarios.build(product, sc, path=path); dt = g.recommended_dt()
+        assert g.active_path() == (1 if path == 1 else 2) and g.n_voxels == len(ijk)
+        g.step(dt, 1200)
+        runs[path] = g
+    o = scenarios.build(oracle, sc); o.step(dt, 1200)
+    a, b, c = parity.snapshot(runs[0]), parity.snapshot(runs[5]), parity.snapshot(runs[1])
+    for f in a:
+        assert parity.bit_equal(a[f], c[f]), f
+        assert parity.bit_equal(b[f], c[f]), f
+    assert np.array_equal(np.stack(runs[0].links()), np.stack(o.links()))
+    err = parity.rel_errors(a, parity.snapshot(o), sc)
+    assert err["pos"] <= 1e-9 and err["orient"] <= 1e-9, err
+    for info in (0, 2, 6, 8, 9):
+        for typ in (0, 1, 3):
+            x, y = runs[0].state_info(info, typ), o.state_info(info, typ)
+            scale = max(abs(o.state_info(info, 0)), abs(o.state_info(info, 1)))
+            assert abs(x - y) <= 1e-5 * scale + 1e-30, (info, typ, x, y)

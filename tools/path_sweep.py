@@ -19,7 +19,13 @@ def main():
     lib = capi.load_product()
     for path in paths:
         sc = {"cantilever": lambda: scenarios.cantilever(n, n, n), "drop": lambda: scenarios.drop_block(n),
-              "robots": lambda: scenarios.robot_ensemble(n, 10), "robots1": lambda: scenarios.robot_ensemble(n, 10)}[what]()
+              "robots": lambda: scenarios.robot_ensemble(n, 10), "robots1": lambda: scenarios.robot_ensemble(n, 10),
+              "holes": lambda: None}[what]()
+        if what == "holes":                                # n^3 block with a square through-hole and a notch: 77 % of its bounding box
+            ijk = scenarios.box_ijk(n, n, n)
+            keep = ~((abs(ijk[:, 0] - n // 2) < n // 5) & (abs(ijk[:, 1] - n // 2) < n // 5)) & ~((ijk[:, 0] > 3 * n // 4) & (ijk[:, 2] > 3 * n // 4))
+            ijk = ijk[keep]
+            sc = scenarios.Scenario("holes_%d" % n, 0.005, [capi.Material(E=1e6, rho=1e3)], ijk, __import__("numpy").zeros(len(ijk), "uint16"))
         if what == "robots1":
             sc.mat[:] = 0                                  # same geometry, one material: isolates the cost of the table look-ups
             sc.materials = sc.materials[:1]

@@ -66,6 +66,7 @@ struct vx_sim {
     bool any_poisson = false;
 
     int N = 0, L = 0, n_members = 1;
+    int N_user = 0;                     // voxels the caller created; [N_user, N) are inert fill cells of a box with holes (lattice mode)
     std::vector<int32_t> ijk; std::vector<uint16_t> vmat_id; std::vector<int32_t> member; std::vector<uint32_t> vflags;
     std::vector<int32_t> lk_vn, lk_vp; std::vector<uint8_t> lk_axis;   // caller (creation) order, caller voxel indices
     std::vector<int32_t> v_e2i, v_i2e, l_e2i, l_i2e;
@@ -1341,7 +1342,49 @@ int vx_get_linkmat_curve(vx_sim* s, int a, int b, float* eps, float* sig, int ca
     return n;
 }
 
+#define VF_FILL 0x80000000u               // internal voxel flag: inert cell that fills a hole of the bounding box
+
+static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags, int n_user);
+
+// A box with holes still runs on the fused lattice path: the missing cells are appended as inert voxels (never
+// integrated, no links, invisible to the caller) when that costs at most 60 % more cells.
 int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags)
+{
+    if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
+    bool poisson = false;
+    for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
+    if (n == 0 || poisson || s->collisions || s->path == 1) return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
+    int lo[3] = {32767, 32767, 32767}, hi[3] = {-32768, -32768, -32768}, members = 1;
+    for (int i = 0; i < n; i++) {
+        for (int a = 0; a < 3; a++) {
+            int c = ijk[3 * i + a];
+            if (c < -32768 || c > 32767) return fail(s, VX_ERR_ARG, "lattice index does not fit a short");
+            lo[a] = std::min(lo[a], c); hi[a] = std::max(hi[a], c);
+        }
+        if (sim_id) { if (sim_id[i] < 0 || sim_id[i] > 65535) return fail(s, VX_ERR_ARG, "bad member id"); members = std::max(members, sim_id[i] + 1); }
+    }
+    const long long ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1, cells = ex * ey * ez * members;
+    if (cells == n || cells > (long long)(1.6 * n) || cells > 2000000000LL) return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
+    std::vector<char> used((size_t)cells, 0);
+    for (int i = 0; i < n; i++) {
+        const long long c = ((((long long)(sim_id ? sim_id[i] : 0) * ez + (ijk[3 * i + 2] - lo[2])) * ey + (ijk[3 * i + 1] - lo[1])) * ex + (ijk[3 * i] - lo[0]));
+        if (used[(size_t)c]) return fail(s, VX_ERR_TOPOLOGY, "duplicate voxel");
+        used[(size_t)c] = 1;
+    }
+    std::vector<int32_t> ijk2(ijk, ijk + 3 * (size_t)n), sim2; std::vector<uint16_t> mat2(mat, mat + n); std::vector<uint32_t> fl2(n, 0u);
+    if (flags) fl2.assign(flags, flags + n);
+    if (sim_id || members > 1) sim2.assign(sim_id, sim_id + n);
+    for (long long c = 0; c < cells; c++) {
+        if (used[(size_t)c]) continue;
+        long long r = c; const int x = (int)(r % ex); r /= ex; const int y = (int)(r % ey); r /= ey; const int z = (int)(r % ez); const int m = (int)(r / ez);
+        ijk2.push_back(lo[0] + x); ijk2.push_back(lo[1] + y); ijk2.push_back(lo[2] + z);
+        mat2.push_back(mat[0]); fl2.push_back(VX_VF_GHOST | VF_FILL);
+        if (!sim2.empty()) sim2.push_back(m);
+    }
+    return set_voxels_impl(s, (int)cells, ijk2.data(), mat2.data(), sim2.empty() ? nullptr : sim2.data(), fl2.data(), n);
+}
+
+static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags, int n_user)
 {
     if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
     CK(cudaSetDevice(s->device));
@@ -1359,7 +1402,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
         if (m < 0 || m > 65535) return fail(s, VX_ERR_ARG, "bad member id");
         max_member = std::max(max_member, m);
     }
-    s->N = n; s->n_members = max_member + 1;
+    s->N = n; s->N_user = n_user; s->n_members = max_member + 1;
     s->ijk.assign(ijk, ijk + 3 * (size_t)n);
     s->vmat_id.assign(mat, mat + n);
     s->member.assign(n, 0); if (sim_id) s->member.assign(sim_id, sim_id + n);
@@ -1400,9 +1443,11 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
         if (lookup(m, x, y, z) >= 0) return fail(s, VX_ERR_TOPOLOGY, "duplicate voxel");
         if (dense) grid[(size_t)cell_of(m, x, y, z)] = i; else hash[key_of(m, x, y, z)] = i;
         bool gi = flags && (flags[i] & VX_VF_GHOST);
+        if (flags && (flags[i] & VF_FILL)) continue;            // a fill cell has no links
         for (int d = 0; d < 6; d++) {
             int o = lookup(m, x + dx[d], y + dy[d], z + dz[d]);
             if (o < 0) continue;
+            if (flags && (flags[o] & VF_FILL)) continue;
             if (gi && (flags[o] & VX_VF_GHOST)) continue;      // halo-halo links are never needed
             bool this_neg = (d % 2) == 0;                      // src/VX_Link.cpp:31-53
             int vn = this_neg ? i : o, vp = this_neg ? o : i;
@@ -1504,7 +1549,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     return VX_OK;
 }
 
-int vx_voxel_count(const vx_sim* s) { return s ? s->N : 0; }
+int vx_voxel_count(const vx_sim* s) { return s ? s->N_user : 0; }
 int vx_link_count(const vx_sim* s) { return s ? s->L : 0; }
 int vx_get_links(const vx_sim* s, int32_t* vn, int32_t* vp, uint8_t* ax)
 {
@@ -1519,7 +1564,7 @@ int vx_set_externals(vx_sim* s, int n, const int32_t* voxel, const uint8_t* dof,
                      const double* tr, const double* rot)
 {
     if (!s || n < 0 || (n && (!voxel || !dof))) return VX_ERR_ARG;
-    for (int k = 0; k < n; k++) if (voxel[k] < 0 || voxel[k] >= s->N) return fail(s, VX_ERR_ARG, "external voxel index out of range");
+    for (int k = 0; k < n; k++) if (voxel[k] < 0 || voxel[k] >= s->N_user) return fail(s, VX_ERR_ARG, "external voxel index out of range");
     if (voxel != s->ext_raw_vox.data()) {
         s->ext_raw_vox.assign(voxel, voxel + n); s->ext_raw_dof.assign(dof, dof + n);
         s->ext_raw_f.clear(); s->ext_raw_m.clear(); s->ext_raw_t.clear(); s->ext_raw_r.clear();
@@ -1559,9 +1604,15 @@ int vx_enable_floor(vx_sim* s, int e) { if (!s) return VX_ERR_ARG; s->floor_on =
 // so switching them on re-lays out a simulation that has not been stepped yet
 static int relayout_fresh(vx_sim* s)
 {
-    std::vector<int32_t> ijk = s->ijk, member = s->member; std::vector<uint16_t> mat = s->vmat_id; std::vector<uint32_t> fl = s->vflags;
+    const int nu = s->N_user;                                      // only the caller's voxels; fill cells are derived again (or dropped)
+    std::vector<int32_t> ijk(s->ijk.begin(), s->ijk.begin() + 3 * (size_t)nu), member(s->member.begin(), s->member.begin() + nu);
+    std::vector<uint16_t> mat(s->vmat_id.begin(), s->vmat_id.begin() + nu); std::vector<uint32_t> fl;
+    if (!s->vflags.empty()) fl.assign(s->vflags.begin(), s->vflags.begin() + nu);
+    bool any_flag = false;
+    for (uint32_t f : fl) if (f) any_flag = true;
+    if (!any_flag) fl.clear();
     s->relayout = true;
-    int rc = vx_set_voxels(s, s->N, ijk.data(), mat.data(), s->n_members > 1 ? member.data() : nullptr, fl.empty() ? nullptr : fl.data());
+    int rc = vx_set_voxels(s, nu, ijk.data(), mat.data(), s->n_members > 1 ? member.data() : nullptr, fl.empty() ? nullptr : fl.data());
     s->relayout = false;
     if (rc != VX_OK) return rc;
     if (!s->ext_raw_vox.empty()) {
@@ -1576,7 +1627,7 @@ static int relayout_fresh(vx_sim* s)
 // change of layout in the middle of a run (collisions switched on: lattice -> general): every voxel and link keeps its state
 static int relayout_keep_state(vx_sim* s)
 {
-    const int N = s->N, L = s->L;
+    const int N = s->N_user, L = s->L;
     std::vector<double> pos(3 * (size_t)N), ori(4 * (size_t)N), lin(3 * (size_t)N), ang(3 * (size_t)N);
     std::vector<float> temp(N); std::vector<uint32_t> vfl(N); std::vector<vx_link_state> ls(L);
     int rc = vx_download(s, VX_F_POS, 0, N, pos.data());
@@ -1590,7 +1641,7 @@ static int relayout_keep_state(vx_sim* s)
     const float time = s->time_host, prev_dt = s->prev_dt_host, ambient = s->ambient;
     rc = relayout_fresh(s);
     if (rc != VX_OK) return rc;
-    if (s->L != L || s->N != N) return fail(s, VX_ERR_CUDA, "relayout changed the model");
+    if (s->L != L || s->N_user != N) return fail(s, VX_ERR_CUDA, "relayout changed the model");
     rc = vx_upload(s, VX_F_POS, 0, N, pos.data());
     if (rc == VX_OK) rc = vx_upload(s, VX_F_ORIENT, 0, N, ori.data());
     if (rc == VX_OK) rc = vx_upload(s, VX_F_LINMOM, 0, N, lin.data());
@@ -1643,7 +1694,7 @@ int vx_set_temperature_members(vx_sim* s, int n, const float* t)
 }
 int vx_set_temperature(vx_sim* s, int n, const float* t)
 {
-    if (!s || !t || n != s->N) return VX_ERR_ARG;
+    if (!s || !t || n != s->N_user) return VX_ERR_ARG;
     return vx_upload(s, VX_F_TEMP, 0, n, t);
 }
 
@@ -1816,7 +1867,7 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
 {
     int what, comps, esize; bool is_link;
     if (!s || !dst || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
-    if (first + count > (is_link ? s->L : s->N)) return VX_ERR_ARG;
+    if (first + count > (is_link ? s->L : s->N_user)) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
     CK(cudaSetDevice(s->device));
     size_t bytes = (size_t)count * comps * esize;
@@ -1844,7 +1895,7 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
     int what, comps, esize; bool is_link;
     if (!s || !src || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
     if (is_link || what == G_PSTRAIN) return fail(s, VX_ERR_UNSUPPORTED, "only voxel state can be uploaded");
-    if (first + count > s->N) return VX_ERR_ARG;
+    if (first + count > s->N_user) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
     CK(cudaSetDevice(s->device));
     size_t bytes = (size_t)count * comps * esize;
@@ -1896,7 +1947,7 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
     if (!s || !out || info < 0 || info > SI_MASS || type < 0 || type > SI_AVERAGE) return VX_ERR_ARG;
     *out = 0.0f;
     const bool link_info = info == SI_STRAIN_ENERGY || info == SI_ENG_STRESS || info == SI_ENG_STRAIN;
-    const int count = link_info ? s->L : s->N;
+    const int count = link_info ? s->L : s->N_user;                 // fill cells of a box with holes are not voxels
     if (count == 0) return VX_OK;                                  // src/Voxelyze.cpp:759,777
     CK(cudaSetDevice(s->device));
     CK(s->si_minmax.alloc(2)); CK(s->si_sum.alloc(1));
@@ -1906,13 +1957,14 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
     const int grid = std::min(blocks_for(count, 256), 148 * 8);
     if (info == SI_PRESSURE) {
         if (!s->si_pressure_ok) {                                  // per-voxel link table, strain ratios, {E, nu}: caller order
-            std::vector<int> vl((size_t)6 * s->N, -1); std::vector<float> ratio(std::max(s->L, 1)); std::vector<float2> en(s->N);
+            const size_t nu = (size_t)s->N_user;
+            std::vector<int> vl(6 * nu, -1); std::vector<float> ratio(std::max(s->L, 1)); std::vector<float2> en(nu);
             for (int l = 0; l < s->L; l++) {
-                vl[(size_t)(2 * s->lk_axis[l]) * s->N + s->lk_vn[l]] = l;          // +axis slot of the negative-end voxel
-                vl[(size_t)(2 * s->lk_axis[l] + 1) * s->N + s->lk_vp[l]] = l;      // -axis slot of the positive-end voxel
+                vl[(size_t)(2 * s->lk_axis[l]) * nu + s->lk_vn[l]] = l;            // +axis slot of the negative-end voxel
+                vl[(size_t)(2 * s->lk_axis[l] + 1) * nu + s->lk_vp[l]] = l;        // -axis slot of the positive-end voxel
                 ratio[l] = s->mats[s->vmat_id[s->lk_vp[l]]].E / s->mats[s->vmat_id[s->lk_vn[l]]].E;
             }
-            for (int v = 0; v < s->N; v++) en[v] = make_float2(s->mats[s->vmat_id[v]].E, s->mats[s->vmat_id[v]].nu);
+            for (size_t v = 0; v < nu; v++) en[v] = make_float2(s->mats[s->vmat_id[v]].E, s->mats[s->vmat_id[v]].nu);
             CK(s->si_vlinks.alloc(vl.size())); CK(s->si_ratio.alloc(ratio.size())); CK(s->si_en.alloc(en.size()));
             CK(cudaMemcpy(s->si_vlinks.p, vl.data(), vl.size() * sizeof(int), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(s->si_ratio.p, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1921,7 +1973,7 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
         }
         CK(s->si_buf.alloc((size_t)std::max(s->L, 1) * sizeof(float)));
         if (s->L) { int rc = gather_link_field(s, G_STRAIN, s->si_buf.p); if (rc != VX_OK) return rc; }
-        k_state_pressure<<<grid, 256, 0, s->stream>>>(s->N, s->si_vlinks.p, (const float*)s->si_buf.p, s->si_ratio.p, s->si_en.p,
+        k_state_pressure<<<grid, 256, 0, s->stream>>>(s->N_user, s->si_vlinks.p, (const float*)s->si_buf.p, s->si_ratio.p, s->si_en.p,
                                                       s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
         s->launches++;
     } else if (!link_info) {

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(256) k_state_voxels(Frame f, int info, const d
     StateAcc a; a.mn = 3.402823466e38f; a.mx = -3.402823466e38f; a.sum = 0.0;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < f.n_vox; v += gridDim.x * blockDim.x) {
         const double4 p0 = f.pose0[v], p1 = f.pose1[v];
+        if (meta_hi(p1.w) & VM_GHOST) continue;           // halo copies and the fill cells of a box with holes are not voxels of this model
         const DevVoxMat& m = f.vmat[meta_hi(p1.w) & VM_MAT_MASK];
         float val = 0.0f;
         if (info == SI_DISPLACEMENT) { double4 n = nominal[v]; double dx = p0.x - n.x, dy = p0.y - n.y, dz = p0.z - n.z; val = (float)sqrt(dx * dx + dy * dy + dz * dz); }
