@@ -357,7 +357,7 @@ int  vx_save_state(vx_sim* s, const char* path);
 int  vx_load_state(vx_sim* s, const char* path);
 /* select kernel variant (tests and ablations; takes effect at the next vx_set_voxels):
  *   0 auto: fused lattice kernel for bodies that fill at least 62.5 % of their bounding box (holes are
- *           padded with inert cells) without Poisson coupling or collisions, general path otherwise
+ *           padded with inert cells) without Poisson coupling, general path otherwise
  *   1 general two-kernel path (k_link<AXIS> x3 + k_voxel), any topology
  *   fused lattice variants, all bit-identical to path 1:
  *   2 block bricks 8x4x4 (k_lattice_tile)     3 one thread per voxel (k_lattice_step)

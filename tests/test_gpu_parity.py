@@ -440,15 +440,15 @@ def test_link_state_upload_round_trip(product, path):
 
 
 def test_enabling_collisions_mid_run_matches_the_oracle(product, oracle):
-    """CVoxelyze::enableCollisions may be called at any time (src/Voxelyze.cpp:612-622); on the device it changes the
-    layout (fused lattice -> general) while every voxel and link keeps its state."""
+    """CVoxelyze::enableCollisions may be called at any time (src/Voxelyze.cpp:612-622); on the device the model is laid
+    out again (collision tables) while every voxel and link keeps its state."""
     sc = scenarios.drop_block(6)
     g = scenarios.build(product, sc); o = scenarios.build(oracle, sc)
     assert g.active_path() == 2
     dt = g.recommended_dt()
     g.step(dt, 300); o.step(dt, 300)
     g.enable_collisions(True); o.enable_collisions(True)
-    assert g.active_path() == 1
+    assert g.active_path() == 2                       # the fused kernels gather contact forces themselves
     assert abs(g.time() - o.time()) <= 1e-9
     g.step(dt, 500); o.step(dt, 500)
     err = parity.rel_errors(parity.snapshot(g), parity.snapshot(o), sc)
@@ -506,3 +506,21 @@ def test_box_with_holes_runs_fused_and_matches_the_general_path_bitwise(product,
             x, y = runs[0].state_info(info, typ), o.state_info(info, typ)
             scale = max(abs(o.state_info(info, 0)), abs(o.state_info(info, 1)))
             assert abs(x - y) <= 1e-5 * scale + 1e-30, (info, typ, x, y)
+
+
+def test_collisions_on_the_fused_path_match_the_general_path_bitwise(product):
+    """Plates bending onto each other (self-collisions, two bilinear materials, gaps between the plates = a box with holes):
+    the fused lattice kernels with their contact-force gather against the general path, bit for bit, pair sets included."""
+    sc = scenarios.plate_stack(16, 4, 2, 3, 2, tip_load=0.5)
+    runs = {}
+    for path in (0, 5, 1):
+        g = scenarios.build(product, sc, path=path); dt = g.recommended_dt()
+        assert g.active_path() == (1 if path == 1 else 2)
+        g.step(dt, 2500)
+        runs[path] = g
+    assert len(runs[1].collision_pairs()) > 0
+    for path in (0, 5):
+        a, c = parity.snapshot(runs[path]), parity.snapshot(runs[1])
+        for f in a:
+            assert parity.bit_equal(a[f], c[f]), (path, f)
+        assert np.array_equal(runs[path].collision_pairs(), runs[1].collision_pairs())

@@ -46,6 +46,7 @@ template <typename T> struct DevBuf {
 
 struct LinkMatEntry { int a, b; vxm::Material mat; };
 
+#define VF_FILL 0x80000000u               // internal voxel flag: inert cell that fills a hole of the bounding box
 constexpr int GRAPH_STEPS = 16;     // steps per captured CUDA graph (even: generations re-align)
 constexpr int TPB = 128;
 
@@ -87,6 +88,7 @@ struct vx_sim {
     bool lattice = false;
     int nx = 0, ny = 0, nz = 0;
     int gen = 0;                        // generation that holds the current state
+    int gen_view = -1;                  // inside a multi-step lattice call: the generation frame() shows (collision kernels)
     bool have_prev = false;             // gen^1 holds the inputs of the last executed step
     float last_prev_dt = 0.f;           // previousDt that step used
     float prev_dt_host = 0.f;           // mirror of DevParams::prev_dt
@@ -150,7 +152,7 @@ struct vx_sim {
     Frame frame() const
     {
         Frame f{};
-        const int g = lattice ? gen : 0;
+        const int g = lattice ? (gen_view >= 0 ? gen_view : gen) : 0;
         f.n_vox = N; f.n_link = L;
         f.pose0 = pose0[g].p; f.pose1 = pose1[g].p; f.mom0 = mom0[g].p; f.mom1 = mom1[g].p;
         f.ext_idx = ext_idx.p; f.pstrain = lattice ? nullptr : pstrain.p; f.slots = slots.p; f.slot_strain = slot_strain.p;
@@ -195,6 +197,8 @@ struct vx_sim {
         f.ext_idx = ext_idx.p; f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
         f.pair_lmat = pair_lmat.p; f.ext = ext_dev.p; f.params = params.p;
         f.vm0 = vm0; f.lm0 = lm0;
+        f.col_slot = (collisions && col_tables) ? c_slot.p : nullptr;
+        f.col_start = c_ref_start.p; f.col_ref = c_refs.p; f.col_force = c_pair_force.p;
         f.push_z[0] = f.push_z[1] = -1;
         if (push_in_kernel) {
             for (size_t k = 0; k < peers.size() && k < 2; k++) {
@@ -441,6 +445,7 @@ static int build_collision_tables(vx_sim* s)
     for (int i = 0; i < N; i++) {                       // internal order
         int e = s->v_i2e[i];
         if (s->linkmask[e] == 0x3F) continue;
+        if (!s->vflags.empty() && (s->vflags[e] & VF_FILL)) continue;      // the inert cells that fill a box with holes
         slot[i] = (int)surf_vox.size();
         surf_vox.push_back(i); surf_orig.push_back(e); surf_member.push_back(s->member[e]);
         surf_ijk.push_back(make_short4((short)s->ijk[3 * e], (short)s->ijk[3 * e + 1], (short)s->ijk[3 * e + 2], 0));
@@ -800,6 +805,16 @@ static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
     const int g0 = s->gen;
     int done = 0;
+    if (s->collisions) {                            // contact forces come from the OLD state, i.e. before the fused kernel of the step;
+        for (; done < n_steps; done++) {            // the host decides about re-watching every step, so no graphs here
+            s->gen_view = (g0 + done) & 1;
+            int rc = collision_step(s);
+            s->gen_view = -1;
+            if (rc != VX_OK) return rc;
+            launch_lattice(s, (g0 + done) & 1, done == 0 ? 1 : 0);
+        }
+        return finish_lattice_call(s, g0, n_steps, diverged_step);
+    }
     launch_lattice(s, g0, 1); done++;
     while (n_steps - done >= GRAPH_STEPS) {
         const int g = (g0 + done) & 1;
@@ -1342,8 +1357,6 @@ int vx_get_linkmat_curve(vx_sim* s, int a, int b, float* eps, float* sig, int ca
     return n;
 }
 
-#define VF_FILL 0x80000000u               // internal voxel flag: inert cell that fills a hole of the bounding box
-
 static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags, int n_user);
 
 // A box with holes still runs on the fused lattice path: the missing cells are appended as inert voxels (never
@@ -1353,7 +1366,8 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
     bool poisson = false;
     for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
-    if (n == 0 || poisson || s->collisions || s->path == 1) return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
+    if (n == 0 || poisson || s->path == 1 || (s->collisions && s->path != 0 && s->path != 5 && s->path != 7))
+        return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
     int lo[3] = {32767, 32767, 32767}, hi[3] = {-32768, -32768, -32768}, members = 1;
     for (int i = 0; i < n; i++) {
         for (int a = 0; a < 3; a++) {
@@ -1487,7 +1501,8 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     // ---- layout: a completely filled box (per member) without Poisson materials runs fused
     bool poisson = false;
     for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
-    s->lattice = n > 0 && cells == (long long)n && !poisson && !s->collisions && s->path != 1;
+    const bool fused_default = s->path == 0 || s->path == 5 || s->path == 7;     // the kernels that gather contact forces
+    s->lattice = n > 0 && cells == (long long)n && !poisson && (!s->collisions || fused_default) && s->path != 1;
     s->nx = (int)ext3[0]; s->ny = (int)ext3[1]; s->nz = (int)ext3[2];
     s->link_owner.release(); s->link_axis_dev.release();
     s->si_nominal_ok = false; s->si_consts_ok = false; s->si_pressure_ok = false;
@@ -1758,6 +1773,7 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
         const int g0 = s->gen;
         for (int k = 0; k < n_steps; k++) {
             CK(cudaEventRecord(ev[4 * k + 0], s->stream));
+            if (s->collisions) { s->gen_view = (g0 + k) & 1; rc = collision_step(s); s->gen_view = -1; if (rc != VX_OK) return rc; }
             launch_lattice(s, (g0 + k) & 1, k == 0 ? 1 : 0);
             CK(cudaEventRecord(ev[4 * k + 3], s->stream));
             if (launches) launches[0] += 1;

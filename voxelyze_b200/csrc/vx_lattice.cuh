@@ -49,6 +49,8 @@ struct LatFrame {
     const DevExt* ext;
     DevParams* params;
     DevVoxMat vm0; DevLinkMat lm0;  // single-material models: rows in the constant bank (UNI)
+    // collisions (k_lattice_warp / k_lattice_tma): per surface voxel CSR of signed contact references, as in Frame
+    const int* col_slot; const int* col_start; const int* col_ref; const float4* col_force;
     // z-slab runs (k_lattice_warp only): voxels of plane push_z[k] also store their new pose into the ghost
     // plane of the neighbouring slab, push0/1[k] = that plane in the neighbour's pose0/pose1 arrays (peer memory)
     int push_z[2]; double4* push0[2]; double4* push1[2];
@@ -898,7 +900,13 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
     {
         const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
         const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
-        voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext, dt, floor_on != 0);
+        const int* refs = nullptr; int n_refs = 0;
+        if (f.col_slot && ((vs.bits >> VM_LINK_SHIFT) & 0x3Fu) != 0x3Fu) {        // only surface voxels are ever watched
+            const int cs = f.col_slot[v];
+            refs = f.col_ref + f.col_start[cs];
+            n_refs = f.col_start[cs + 1] - f.col_start[cs];
+        }
+        voxel_integrate(vs, F, M, refs, n_refs, f.col_force, vm, ext, dt, floor_on != 0);
     }
     f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
     f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
@@ -1438,7 +1446,13 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     {
         const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
         const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
-        voxel_integrate(vs, F, M, nullptr, 0, nullptr, vm, ext, dt, floor_on != 0);
+        const int* refs = nullptr; int n_refs = 0;
+        if (f.col_slot && ((vs.bits >> VM_LINK_SHIFT) & 0x3Fu) != 0x3Fu) {        // only surface voxels are ever watched
+            const int cs = f.col_slot[v];
+            refs = f.col_ref + f.col_start[cs];
+            n_refs = f.col_start[cs + 1] - f.col_start[cs];
+        }
+        voxel_integrate(vs, F, M, refs, n_refs, f.col_force, vm, ext, dt, floor_on != 0);
     }
     f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
     f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
