@@ -3,8 +3,9 @@
 // Host side of the drop-in boundary: owns the device-resident structure-of-arrays state of
 // one simulation, translates the flat model description into it, and drives the kernels.
 // Two device layouts exist behind the same ABI:
-//   lattice mode  dense box lattices (every cell of the bounding box filled, nu = 0): fused
-//                 single-pass kernel on ping-pong generations, vx_lattice.cuh  (headline path)
+//   lattice mode  bodies that fill >= 62.5 % of their bounding box (holes padded with inert cells), nu = 0,
+//                 self-collisions included: fused single-pass kernel on ping-pong generations,
+//                 vx_lattice.cuh  (headline path)
 //   general mode  any voxel set, Poisson materials: link kernels + voxel kernel, vx_kernels.cuh
 // There is deliberately no CPU code path for stepping: without a usable CUDA device
 // vx_create fails with VX_ERR_NO_DEVICE.
@@ -129,7 +130,7 @@ struct vx_sim {
     DevParams* params_host = nullptr;     // pinned mirror
     unsigned int* freq_host = nullptr;    // pinned
 
-    // ---- collisions (general mode only)
+    // ---- collisions (tables indexed by internal voxel index: both layouts)
     std::vector<int32_t> nbr;                                      // [N][6] neighbour voxel (caller index) or -1
     std::vector<int> ext_raw_vox; std::vector<uint8_t> ext_raw_dof; std::vector<float> ext_raw_f, ext_raw_m; std::vector<double> ext_raw_t, ext_raw_r;
     int n_surf = 0, n_pairs = 0, col_cap = 0, hash_size = 0;

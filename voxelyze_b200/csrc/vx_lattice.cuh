@@ -680,8 +680,9 @@ k_lattice_tile(LatFrame f, int parity, int first_of_call, int floor_on, int ntx,
 // 4.0 link evaluations per voxel (3 + 32/32), all 32 lanes busy in every round of a full brick.
 // Shared memory per warp: two record windows 2x4x32x16 B + 72 poses (32 of the brick, 40 just
 // outside it) x 64 B + hslot 6x32x8 B = 10 240 B; requests run one round ahead of their use; the round-H windows are re-used for round 2 and the round-0 window for the momenta.
-// Link existence is geometric here (the lattice path is only chosen for full boxes), which lets
-// the requests go out before the first byte of voxel state has arrived.
+// Requests are predicated on GEOMETRY only (is there a cell on the other side?), which lets them go out before the
+// first byte of voxel state has arrived; whether the link exists is decided later from the voxel's link mask
+// (a box with holes has cells without voxels: their data is fetched and ignored).
 // =================================================================================================
 #define VX_WB_X 4
 #define VX_WB_Y 4
