@@ -829,36 +829,7 @@ static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     return finish_lattice_call(s, g0, n_steps, diverged_step);
 }
 
-// ------------------------------------------------------------------------------------------------
-// peer-memory halo: after the boundary part of a step each slab stores its fresh boundary poses straight
-// into the ghost planes of its neighbours (CUDA IPC mappings, NVLink) and then bumps the neighbour's
-// arrival counter; the neighbour's next boundary part spins on that counter first.
-__global__ void k_halo_push(const double4* __restrict__ src0, const double4* __restrict__ src1, double4* dst0, double4* dst1, int count)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    const double4 a = src0[k], b = src1[k];
-    dst0[k] = a;
-    double* d = reinterpret_cast<double*>(dst1 + k);
-    d[0] = b.x; d[1] = b.y; d[2] = b.z;
-    // the receiver owns the upper half of w (its flag word, see k_lattice_warp); the lower half is the temperature
-    reinterpret_cast<uint32_t*>(d + 3)[0] = (uint32_t)(unsigned long long)__double_as_longlong(b.w);
-}
-__global__ void k_peer_signal(int* flag, int seq)
-{
-    __threadfence_system();
-    *(volatile int*)flag = seq;
-    __threadfence_system();
-}
-__global__ void k_peer_wait(const int* flags, int need_lo, int need_hi, int* timed_out, long long limit)
-{
-    const long long t0 = clock64();                        // limit in SM clocks: a lost peer must not hang the GPU
-    while (*(volatile const int*)(flags + 0) < need_lo || *(volatile const int*)(flags + 1) < need_hi) {
-        if (clock64() - t0 > limit) { *timed_out = 1; break; }
-        __nanosleep(200);
-    }
-    __threadfence_system();
-}
+#include "vx_slab_kernels.cuh"
 
 // brick-group layers that a halo exchange touches: those holding an all-ghost plane or a plane next to one
 static void find_boundary_layers(vx_sim* s)
@@ -932,332 +903,8 @@ int vx_step_end(vx_sim* s, int* diverged_step)
     return finish_lattice_call(s, s->call_g0, s->call_done, diverged_step);
 }
 
-// ---- peer-memory halo ---------------------------------------------------------------------------
-struct PeerDescWire {                       // what vx_peer_export writes into vx_peer_desc::bytes
-    uint64_t magic; int64_t pid; int32_t device, side; uint64_t first, count;
-    cudaIpcMemHandle_t mem[4]; cudaIpcMemHandle_t flag;      // pose0[0], pose0[1], pose1[0], pose1[1]; flag array
-    uint64_t raw[4]; uint64_t raw_flag;                      // same-process peers use the addresses directly
-};
-static_assert(sizeof(PeerDescWire) <= VX_PEER_DESC_BYTES, "vx_peer_desc too small");
-
-static int plane_range(vx_sim* s, int iz, size_t& first, size_t& count)
-{
-    int64_t key = (int64_t)(iz + 32768);
-    auto lo = std::lower_bound(s->sort_key.begin(), s->sort_key.end(), key);
-    auto hi = std::upper_bound(s->sort_key.begin(), s->sort_key.end(), key);
-    first = lo - s->sort_key.begin(); count = hi - lo;
-    return count ? VX_OK : VX_ERR_ARG;
-}
-
-static int ensure_peer_state(vx_sim* s)
-{
-    CK(cudaSetDevice(s->device));
-    if (!s->peer_flags.p) { CK(s->peer_flags.alloc(4)); CK(cudaMemset(s->peer_flags.p, 0, 4 * sizeof(int))); }
-    if (!s->comm_stream) {             // highest priority: its few blocks must not queue behind the interior part's
-        int least = 0, greatest = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        CK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, greatest));
-    }
-    if (!s->ev_boundary) CK(cudaEventCreateWithFlags(&s->ev_boundary, cudaEventDisableTiming));
-    if (!s->ev_comm) CK(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
-    return VX_OK;
-}
-
-int vx_peer_export(vx_sim* s, int ghost_iz, int from_above, vx_peer_desc* out)
-{
-    if (!s || !out || !s->lattice || s->n_members != 1) return VX_ERR_ARG;
-    int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
-    size_t first, count;
-    if (plane_range(s, ghost_iz, first, count) != VX_OK) return fail(s, VX_ERR_ARG, "vx_peer_export: empty layer");
-    PeerDescWire w{}; w.magic = 0x56585045455231ULL; w.pid = (int64_t)getpid(); w.device = s->device; w.side = from_above ? 1 : 0;
-    w.first = first; w.count = count;
-    double4* base[4] = {s->pose0[0].p, s->pose0[1].p, s->pose1[0].p, s->pose1[1].p};
-    for (int k = 0; k < 4; k++) { CK(cudaIpcGetMemHandle(&w.mem[k], base[k])); w.raw[k] = (uint64_t)(uintptr_t)base[k]; }
-    CK(cudaIpcGetMemHandle(&w.flag, s->peer_flags.p)); w.raw_flag = (uint64_t)(uintptr_t)s->peer_flags.p;
-    memset(out->bytes, 0, VX_PEER_DESC_BYTES); memcpy(out->bytes, &w, sizeof(w));
-    s->expect_side[w.side] = true;                                   // a neighbour will write here
-    return VX_OK;
-}
-
-int vx_peer_attach(vx_sim* s, int send_iz, const vx_peer_desc* peer_ghost)
-{
-    if (!s || !peer_ghost || !s->lattice || s->n_members != 1) return VX_ERR_ARG;
-    int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
-    PeerDescWire w; memcpy(&w, peer_ghost->bytes, sizeof(w));
-    if (w.magic != 0x56585045455231ULL) return fail(s, VX_ERR_ARG, "vx_peer_attach: not a peer descriptor");
-    vx_sim::PeerLink pl;
-    if (plane_range(s, send_iz, pl.src_first, pl.count) != VX_OK || pl.count != w.count) return fail(s, VX_ERR_ARG, "vx_peer_attach: layer size mismatch");
-    void* base[5];
-    if (w.pid == (int64_t)getpid()) {                                 // same process (tests): plain addresses
-        for (int k = 0; k < 4; k++) base[k] = (void*)(uintptr_t)w.raw[k];
-        base[4] = (void*)(uintptr_t)w.raw_flag;
-        if (w.device != s->device) { int can = 0; cudaDeviceCanAccessPeer(&can, s->device, w.device); if (!can) return fail(s, VX_ERR_UNSUPPORTED, "no peer access"); cudaError_t e = cudaDeviceEnablePeerAccess(w.device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(s, e, "cudaDeviceEnablePeerAccess"); cudaGetLastError(); }
-    } else {
-        for (int k = 0; k < 4; k++) {
-            cudaError_t e = cudaIpcOpenMemHandle(&base[k], w.mem[k], cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) { cudaGetLastError(); return fail(s, VX_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
-            pl.opened[k] = base[k];
-        }
-        cudaError_t e = cudaIpcOpenMemHandle(&base[4], w.flag, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(s, VX_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
-        pl.opened[4] = base[4];
-    }
-    pl.dst0[0] = (double4*)base[0] + w.first; pl.dst0[1] = (double4*)base[1] + w.first;
-    pl.dst1[0] = (double4*)base[2] + w.first; pl.dst1[1] = (double4*)base[3] + w.first;
-    pl.dst_flag = (int*)base[4] + w.side;
-    s->peers.push_back(pl);
-    return VX_OK;
-}
-
-int vx_peer_detach(vx_sim* s)
-{
-    if (!s) return VX_ERR_ARG;
-    cudaSetDevice(s->device);
-    if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
-    for (auto& pl : s->peers) for (void* q : pl.opened) if (q) cudaIpcCloseMemHandle(q);
-    s->peers.clear(); s->expect_side[0] = s->expect_side[1] = false;
-    return VX_OK;
-}
-
-// queue: wait for every exchange so far (compute stream)
-static void peer_wait(vx_sim* s, cudaStream_t st)
-{
-    if (s->xseq == 0 || (!s->expect_side[0] && !s->expect_side[1])) return;
-    static long long limit = 0;                            // VX_PEER_TIMEOUT_S (default 30 s) at ~2 GHz
-    if (limit == 0) { const char* e = getenv("VX_PEER_TIMEOUT_S"); double sec = e ? atof(e) : 30.0; limit = (long long)(std::max(sec, 0.1) * 2.0e9); }
-    k_peer_wait<<<1, 1, 0, st>>>(s->peer_flags.p, s->expect_side[0] ? s->xseq : 0, s->expect_side[1] ? s->xseq : 0, s->peer_flags.p + 2, limit);
-    s->launches++;
-}
-// queue on the comm stream: ship generation g of my boundary layers (unless the step kernel already stored
-// them into the neighbours' ghost layers itself) and signal
-static void peer_push(vx_sim* s, int g, bool already_stored)
-{
-    s->xseq++;
-    for (auto& pl : s->peers) {
-        if (!already_stored) {
-            k_halo_push<<<blocks_for((long long)pl.count), TPB, 0, s->comm_stream>>>(s->pose0[g].p + pl.src_first, s->pose1[g].p + pl.src_first,
-                                                                                     pl.dst0[g], pl.dst1[g], (int)pl.count);
-            s->launches++;
-        }
-        k_peer_signal<<<1, 1, 0, s->comm_stream>>>(pl.dst_flag, s->xseq);
-        s->launches++;
-    }
-}
-static int peer_check(vx_sim* s)
-{
-    int t = 0;
-    CK(cudaMemcpy(&t, s->peer_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost));
-    return t ? fail(s, VX_ERR_CUDA, "peer halo: a neighbouring slab did not deliver in time") : VX_OK;
-}
-
-int vx_slab_exchange(vx_sim* s)
-{
-    if (!s || !s->lattice || s->call_active) return VX_ERR_ARG;
-    int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
-    CK(cudaEventRecord(s->ev_boundary, s->stream));
-    CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
-    peer_push(s, s->gen, false);
-    CK(cudaStreamSynchronize(s->comm_stream));       // delivered; the neighbours' deliveries are awaited by the next vx_slab_step
-    return VX_OK;
-}
-
-int vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
-{
-    if (!s || n_steps < 0) return VX_ERR_ARG;
-    if (n_steps == 0) return VX_OK;
-    int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
-    rc = vx_step_begin(s, dt); if (rc != VX_OK) return rc;
-    for (int k = 0; k < n_steps; k++) {
-        peer_wait(s, s->stream);                            // the boundary part reads the ghosts of the previous exchange
-        s->push_in_kernel = s->peers.size() <= 2;          // the boundary kernels store into the neighbours' ghost layers themselves
-        const bool fused = s->push_in_kernel;
-        rc = vx_step_enqueue(s, VX_PART_Z_BOUNDARY);
-        s->push_in_kernel = false;
-        if (rc != VX_OK) return rc;
-        CK(cudaEventRecord(s->ev_boundary, s->stream));
-        rc = vx_step_enqueue(s, VX_PART_Z_INTERIOR); if (rc != VX_OK) return rc;
-        CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
-        peer_push(s, s->newest_gen(), fused);
-    }
-    CK(cudaEventRecord(s->ev_comm, s->comm_stream));
-    CK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
-    rc = vx_step_end(s, diverged_step);
-    if (rc != VX_OK && rc != VX_DIVERGED) return rc;
-    int rc2 = peer_check(s);
-    return rc2 != VX_OK ? rc2 : rc;
-}
-
-// ---- dynamic-state checkpoint (the reference has none) -----------------
-namespace {
-struct StateHeader {
-    char magic[8]; int32_t abi, lattice, N, L, nx, ny, nz, n_members, gen, have_prev, collisions, reserved;
-    float last_prev_dt, prev_dt_host, time_host, ambient; uint64_t topo_hash; DevParams params;
-};
-struct Chunk { void* p; size_t bytes; };
-static uint64_t topo_hash(const vx_sim* s)
-{
-    uint64_t h = 1469598103934665603ULL;                                   // FNV-1a over the model the arrays belong to
-    auto mix = [&](const void* d, size_t n) { const unsigned char* b = (const unsigned char*)d; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; } };
-    mix(s->ijk.data(), s->ijk.size() * sizeof(int32_t)); mix(s->vmat_id.data(), s->vmat_id.size() * sizeof(uint16_t));
-    mix(s->member.data(), s->member.size() * sizeof(int32_t)); mix(s->vflags.data(), s->vflags.size() * sizeof(uint32_t));
-    return h;
-}
-static std::vector<Chunk> state_chunks(vx_sim* s)
-{
-    std::vector<Chunk> c;
-    const size_t N = s->N, L = s->L;
-    if (s->lattice) {
-        for (int g = 0; g < 2; g++) {
-            c.push_back({s->pose0[g].p, N * sizeof(double4)}); c.push_back({s->pose1[g].p, N * sizeof(double4)});
-            c.push_back({s->mom0[g].p, N * sizeof(double4)}); c.push_back({s->mom1[g].p, N * sizeof(double2)});
-            c.push_back({s->rec[g].p, N * 9 * sizeof(double2)}); c.push_back({s->recf[g].p, N * 3 * sizeof(float4)});
-        }
-    } else {
-        c.push_back({s->pose0[0].p, N * sizeof(double4)}); c.push_back({s->pose1[0].p, N * sizeof(double4)});
-        c.push_back({s->mom0[0].p, N * sizeof(double4)}); c.push_back({s->mom1[0].p, N * sizeof(double2)});
-        c.push_back({s->slots.p, N * 36 * sizeof(double)}); c.push_back({s->slot_strain.p, N * 6 * sizeof(float)});
-        c.push_back({s->pstrain.p, N * sizeof(float4)});
-        c.push_back({s->lstA.p, L * sizeof(double4)}); c.push_back({s->lstB.p, L * sizeof(double4)}); c.push_back({s->lstC.p, L * sizeof(double)});
-        c.push_back({s->lstrain.p, L * sizeof(float4)}); c.push_back({s->lmeta.p, L * sizeof(uint32_t)});
-    }
-    return c;
-}
-} // namespace
-
-int vx_save_state(vx_sim* s, const char* path)
-{
-    if (!s || !path || s->call_active) return VX_ERR_ARG;
-    CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
-    FILE* fp = fopen(path, "wb");
-    if (!fp) return fail(s, VX_ERR_ARG, std::string("cannot write ") + path);
-    StateHeader h{};
-    memcpy(h.magic, "VXB2ST01", 8);
-    h.abi = VX_ABI_VERSION; h.lattice = s->lattice; h.N = s->N; h.L = s->L; h.nx = s->nx; h.ny = s->ny; h.nz = s->nz; h.n_members = s->n_members;
-    h.gen = s->gen; h.have_prev = s->have_prev; h.collisions = s->collisions;
-    h.last_prev_dt = s->last_prev_dt; h.prev_dt_host = s->prev_dt_host; h.time_host = s->time_host; h.ambient = s->ambient;
-    h.topo_hash = topo_hash(s);
-    cudaError_t e = cudaMemcpy(&h.params, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost);
-    bool ok = e == cudaSuccess && fwrite(&h, sizeof(h), 1, fp) == 1;
-    std::vector<unsigned char> bounce(64u << 20);
-    for (const Chunk& c : state_chunks(s)) {
-        for (size_t off = 0; ok && off < c.bytes; off += bounce.size()) {
-            const size_t n = std::min(bounce.size(), c.bytes - off);
-            ok = cudaMemcpy(bounce.data(), (const unsigned char*)c.p + off, n, cudaMemcpyDeviceToHost) == cudaSuccess && fwrite(bounce.data(), 1, n, fp) == n;
-        }
-    }
-    ok = fclose(fp) == 0 && ok;
-    return ok ? VX_OK : fail(s, VX_ERR_CUDA, std::string("writing ") + path + " failed");
-}
-
-int vx_load_state(vx_sim* s, const char* path)
-{
-    if (!s || !path || s->call_active) return VX_ERR_ARG;
-    CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
-    FILE* fp = fopen(path, "rb");
-    if (!fp) return fail(s, VX_ERR_ARG, std::string("cannot read ") + path);
-    StateHeader h{};
-    bool ok = fread(&h, sizeof(h), 1, fp) == 1 && memcmp(h.magic, "VXB2ST01", 8) == 0 && h.abi == VX_ABI_VERSION;
-    if (ok && (h.lattice != (int)s->lattice || h.N != s->N || h.L != s->L || h.nx != s->nx || h.ny != s->ny || h.nz != s->nz ||
-               h.n_members != s->n_members || h.collisions != (int)s->collisions || h.topo_hash != topo_hash(s))) {
-        fclose(fp);
-        return fail(s, VX_ERR_ARG, "vx_load_state: the file belongs to a different model (voxels, materials layout or options differ)");
-    }
-    std::vector<unsigned char> bounce(64u << 20);
-    for (const Chunk& c : state_chunks(s)) {
-        for (size_t off = 0; ok && off < c.bytes; off += bounce.size()) {
-            const size_t n = std::min(bounce.size(), c.bytes - off);
-            ok = fread(bounce.data(), 1, n, fp) == n && cudaMemcpy((unsigned char*)c.p + off, bounce.data(), n, cudaMemcpyHostToDevice) == cudaSuccess;
-        }
-    }
-    fclose(fp);
-    if (!ok) return fail(s, VX_ERR_ARG, std::string("reading ") + path + " failed (truncated or not a state file)");
-    h.params.col_stale = 1;                                  // watch lists are rebuilt from the restored positions at the next step
-    CK(cudaMemcpy(s->params.p, &h.params, sizeof(DevParams), cudaMemcpyHostToDevice));
-    s->gen = h.gen; s->have_prev = h.have_prev != 0; s->last_prev_dt = h.last_prev_dt; s->prev_dt_host = h.prev_dt_host;
-    s->time_host = h.time_host; s->ambient = h.ambient; s->col_stale_host = true;
-    return VX_OK;
-}
-
-int vx_collision_forces(vx_sim* s, int32_t* pairs, float* forces, int cap, int* n_pairs)
-{
-    if (!s) return VX_ERR_ARG;
-    const int P = (s->collisions && s->col_tables) ? s->n_pairs : 0;
-    if (n_pairs) *n_pairs = P;
-    if ((!pairs && !forces) || P == 0) return VX_OK;
-    CK(cudaSetDevice(s->device));
-    std::vector<int2> raw(P); std::vector<float4> fr(P); std::vector<int> orig(s->n_surf);
-    CK(cudaStreamSynchronize(s->stream));
-    CK(cudaMemcpy(raw.data(), s->c_pairs.p, (size_t)P * sizeof(int2), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(fr.data(), s->c_pair_force.p, (size_t)P * sizeof(float4), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(orig.data(), s->c_surf_orig.p, (size_t)s->n_surf * sizeof(int), cudaMemcpyDeviceToHost));
-    std::vector<int> order(P);
-    for (int k = 0; k < P; k++) order[k] = k;
-    std::sort(order.begin(), order.end(), [&](int a, int b) {
-        return std::make_pair(orig[raw[a].x], orig[raw[a].y]) < std::make_pair(orig[raw[b].x], orig[raw[b].y]); });
-    for (int k = 0; k < P && k < cap; k++) {
-        const int q = order[k];
-        if (pairs) { pairs[2 * k] = orig[raw[q].x]; pairs[2 * k + 1] = orig[raw[q].y]; }
-        if (forces) { forces[3 * k] = fr[q].x; forces[3 * k + 1] = fr[q].y; forces[3 * k + 2] = fr[q].z; }
-    }
-    return VX_OK;
-}
-
-// ---- packed link state (topology edits and layout changes keep the state of surviving links) -------
-int vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst)
-{
-    if (!s || !dst || first < 0 || count < 0 || first + count > s->L) return VX_ERR_ARG;
-    if (count == 0) return VX_OK;
-    std::vector<double> p2(3 * (size_t)count), a1(3 * (size_t)count), a2(3 * (size_t)count);
-    std::vector<float> e(count), em(count), eo(count), sg(count); std::vector<uint32_t> fl(count);
-    int rc = vx_download(s, VX_F_POS2, first, count, p2.data());
-    if (rc == VX_OK) rc = vx_download(s, VX_F_ANGLE1V, first, count, a1.data());
-    if (rc == VX_OK) rc = vx_download(s, VX_F_ANGLE2V, first, count, a2.data());
-    if (rc == VX_OK) rc = vx_download(s, VX_F_STRAIN, first, count, e.data());
-    if (rc == VX_OK) rc = vx_download(s, VX_F_MAXSTRAIN, first, count, em.data());
-    if (rc == VX_OK) rc = vx_download(s, VX_F_STRAINOFFSET, first, count, eo.data());
-    if (rc == VX_OK) rc = vx_download(s, VX_F_STRESS, first, count, sg.data());
-    if (rc == VX_OK) rc = vx_download(s, VX_F_LINKFLAGS, first, count, fl.data());
-    if (rc != VX_OK) return rc;
-    for (int k = 0; k < count; k++) {
-        vx_link_state& r = dst[k];
-        for (int c = 0; c < 3; c++) { r.pos2[c] = p2[3 * (size_t)k + c]; r.angle1v[c] = a1[3 * (size_t)k + c]; r.angle2v[c] = a2[3 * (size_t)k + c]; }
-        r.strain = e[k]; r.max_strain = em[k]; r.strain_offset = eo[k]; r.stress = sg[k]; r.flags = fl[k]; r.reserved = 0;
-    }
-    return VX_OK;
-}
-
-int vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* src)
-{
-    static_assert(sizeof(vx_link_state) == sizeof(LinkStateRec), "vx_link_state layout");
-    if (!s || !src || first < 0 || count < 0 || first + count > s->L || s->call_active) return VX_ERR_ARG;
-    if (count == 0) return VX_OK;
-    CK(cudaSetDevice(s->device));
-    CK(cudaStreamSynchronize(s->stream));
-    const size_t bytes = (size_t)count * sizeof(vx_link_state);
-    CK(s->staging.alloc(bytes));
-    CK(cudaMemcpyAsync(s->staging.p, src, bytes, cudaMemcpyHostToDevice, s->stream));
-    if (!s->lattice) {
-        k_scatter_link_state<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), s->link_e2i_dev.p, first, count, (const LinkStateRec*)s->staging.p);
-    } else {
-        std::vector<int> of((size_t)3 * s->N, -1);              // (axis, owner voxel) -> caller link index
-        for (int e = 0; e < s->L; e++) of[(size_t)s->lk_axis[e] * s->N + s->v_e2i[s->lk_vn[e]]] = e;
-        DevBuf<int> of_dev;
-        CK(of_dev.alloc(of.size()));
-        CK(cudaMemcpyAsync(of_dev.p, of.data(), of.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
-        const int g = s->gen;
-        k_lattice_scatter_link_state<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->pose1[g].p, s->rec[g].p, s->recf[g].p, of_dev.p, s->N,
-                                                                              (const LinkStateRec*)s->staging.p, first, count);
-        CK(cudaStreamSynchronize(s->stream));
-        of_dev.release();
-        s->have_prev = false;                                    // link forces are recomputed from the previous generation, which no longer matches
-    }
-    s->launches++;
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(s->stream));
-    return VX_OK;
-}
+#include "vx_slab.inl"
+#include "vx_state_io.inl"
 
 int vx_abi_version(void) { return VX_ABI_VERSION; }
 const char* vx_backend(void) { return "cuda-sm100a"; }
