@@ -355,14 +355,14 @@ int  vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* 
  * Collision watch lists are rebuilt at the next step.                                        */
 int  vx_save_state(vx_sim* s, const char* path);
 int  vx_load_state(vx_sim* s, const char* path);
-/* select kernel variant (tests and ablations; takes effect at the next vx_set_voxels):
+/* select kernel variant (tests; the layout part takes effect at the next vx_set_voxels):
  *   0 auto: fused lattice kernel for bodies that fill at least 62.5 % of their bounding box (holes are
- *           padded with inert cells) without Poisson coupling, general path otherwise
+ *           padded with inert cells), general path otherwise
  *   1 general two-kernel path (k_link<AXIS> x3 + k_voxel), any topology
- *   fused lattice variants, all bit-identical to path 1:
- *   2 block bricks 8x4x4 (k_lattice_tile)     3 one thread per voxel (k_lattice_step)
- *   4 z-marching columns (k_lattice_march)    5 warp bricks 4x4x2, cp.async staging (k_lattice_warp)
- *   6 marching warp bricks (k_lattice_zmarch) 7 warp bricks 4x4x2, TMA staging (k_lattice_tma) = what 0 picks */
+ *   fused lattice kernel (one warp per 4x4x2 brick), bit-identical to path 1, with a fixed staging flavour:
+ *   5 cp.async staging (k_lattice_warp; what 0 picks for ensembles of small boxes)
+ *   7 TMA staging (k_lattice_tma; what 0 picks on large lattices)
+ * any other value: VX_ERR_ARG */
 int  vx_set_path(vx_sim* s, int path);
 /* which layout the handle runs: 1 general, 2 fused lattice (decided by vx_set_voxels)  */
 int  vx_active_path(const vx_sim* s);

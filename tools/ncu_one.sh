@@ -2,7 +2,7 @@
 # One `ncu --set full` capture of a lattice kernel variant.  usage: tools/ncu_one.sh <path> <kernel-regex> <out-name> [edge]
 set -e
 P=${1:-0}; K=${2:-k_lattice_tile}; OUT=${3:-cap}; N=${4:-256}
-mkdir -p gpurun_out
+mkdir -p gpurun_out/$(dirname $OUT)
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:$K -s 20 -c 1 -f -o gpurun_out/$OUT \
   python -c "
 import sys; sys.path.insert(0,'.')

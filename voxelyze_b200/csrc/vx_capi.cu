@@ -31,6 +31,7 @@ using namespace vxd;
 
 namespace {
 
+template <typename T> struct DevView { T* p = nullptr; };      // a part of another buffer's allocation
 template <typename T> struct DevBuf {
     T* p = nullptr; size_t n = 0;
     cudaError_t alloc(size_t count)
@@ -82,7 +83,7 @@ struct vx_sim {
     float grav = 0.f, ambient = 0.f, envelope = 0.625f;
     bool floor_on = false, collisions = false;
     float time_host = 0.f;
-    int path = 0;                       // vx_set_path: 0 auto, 1 general, 2..5 fused lattice variants
+    int path = 0;                       // vx_set_path: 0 auto, 1 general, 5 / 7 fused lattice with cp.async / TMA staging
     bool relayout = false;
 
     // ---- lattice mode
@@ -103,10 +104,10 @@ struct vx_sim {
         double4* dst0[2] = {nullptr, nullptr};            // the peer's ghost layer in its pose0/pose1 arrays, per generation
         double4* dst1[2] = {nullptr, nullptr};
         int* dst_flag = nullptr;                          // the peer's arrival counter for messages from me
-        void* opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // cudaIpcOpenMemHandle results (other-process peers)
+        void* opened[3] = {nullptr, nullptr, nullptr};     // cudaIpcOpenMemHandle results (other-process peers)
     };
     std::vector<PeerLink> peers;
-    bool wb_opted_in = false, zm_opted_in = false, tile_opted_in = false;
+    bool wb_opted_in = false;
     DevBuf<unsigned char> tmaps;        // CUtensorMap descriptors of the lattice arrays (k_lattice_tma), rebuilt with the arrays
     bool push_in_kernel = false;        // set around the boundary launches of vx_slab_step
     DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
@@ -117,8 +118,14 @@ struct vx_sim {
     int newest_gen() const { return call_active ? (call_g0 + call_done) & 1 : gen; }
 
     // ---- device
-    DevBuf<double4> pose0[2], pose1[2], mom0[2]; DevBuf<double2> mom1[2];   // general mode uses [0] only
-    DevBuf<double2> rec[2]; DevBuf<float4> recf[2];                         // lattice link records
+    // pose0 and pose1 of a generation are ONE allocation ([2][N] double4, pose1 = pose0 + N) so that a single 4-D TMA
+    // box brings both records of a voxel set; general mode uses [0] only
+    DevBuf<double4> pose0[2], mom0[2]; DevView<double4> pose1[2]; DevBuf<double2> mom1[2];
+    // lattice link records, one allocation of VX_REC_PARTS x N sixteen-byte parts per generation: for axis a the
+    // parts 4a..4a+2 are the three double2 of the record, part 4a+3 its float4 {strain, maxStrain, strainOffset, stress}
+    DevBuf<double2> rec[2];
+    cudaError_t alloc_pose(int g, size_t n1) { cudaError_t e = pose0[g].alloc(2 * n1); pose1[g].p = e == cudaSuccess ? pose0[g].p + n1 : nullptr; return e; }
+    void release_pose(int g) { pose0[g].release(); pose1[g].p = nullptr; }
     DevBuf<uint16_t> pair_lmat; DevBuf<int> link_owner; DevBuf<unsigned char> link_axis_dev;
     DevBuf<int> ext_idx, ext_vox_dev, vox_e2i_dev, link_e2i_dev, member_dev;
     DevBuf<float4> pstrain; DevBuf<double> slots; DevBuf<float> slot_strain;
@@ -189,11 +196,11 @@ struct vx_sim {
         f.n_pose0 = pose0[g ^ 1].p; f.n_pose1 = pose1[g ^ 1].p; f.n_mom0 = mom0[g ^ 1].p; f.n_mom1 = mom1[g ^ 1].p;
         for (int a = 0; a < 3; a++) {
             for (int k = 0; k < 3; k++) {
-                f.c_rec[a][k] = rec[g].p + (size_t)(a * 3 + k) * N;
-                f.n_rec[a][k] = rec[g ^ 1].p + (size_t)(a * 3 + k) * N;
+                f.c_rec[a][k] = rec[g].p + (size_t)(a * 4 + k) * N;
+                f.n_rec[a][k] = rec[g ^ 1].p + (size_t)(a * 4 + k) * N;
             }
-            f.c_recf[a] = recf[g].p + (size_t)a * N;
-            f.n_recf[a] = recf[g ^ 1].p + (size_t)a * N;
+            f.c_recf[a] = reinterpret_cast<const float4*>(rec[g].p + (size_t)(a * 4 + 3) * N);
+            f.n_recf[a] = reinterpret_cast<float4*>(rec[g ^ 1].p + (size_t)(a * 4 + 3) * N);
         }
         f.ext_idx = ext_idx.p; f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
         f.pair_lmat = pair_lmat.p; f.ext = ext_dev.p; f.params = params.p;
@@ -345,8 +352,7 @@ static int upload_initial_state(vx_sim* s, float temp)
             CK(cudaMemset(s->mom0[g].p, 0, (size_t)N * sizeof(double4)));
             CK(cudaMemset(s->mom1[g].p, 0, (size_t)N * sizeof(double2)));
             if (s->lattice) {
-                CK(cudaMemset(s->rec[g].p, 0, (size_t)N * 9 * sizeof(double2)));
-                CK(cudaMemset(s->recf[g].p, 0, (size_t)N * 3 * sizeof(float4)));
+                CK(cudaMemset(s->rec[g].p, 0, (size_t)N * VX_REC_PARTS * sizeof(double2)));
             }
         }
         if (!s->lattice) {
@@ -643,14 +649,12 @@ static int build_tensor_maps(vx_sim* s)
     bool ok = true;
     for (int g = 0; g < 2 && ok; g++) {
         CUtensorMap* m = maps.data() + g * TM_COUNT;
-        void* p0 = s->pose0[g].p; void* p1 = s->pose1[g].p;
-        ok = make(m + TM_P0_OWN, p0, 4, 0, 4, 4, 2, 0) && make(m + TM_P0_XF, p0, 4, 0, 1, 4, 2, 0) && make(m + TM_P0_YF, p0, 4, 0, 4, 1, 2, 0) && make(m + TM_P0_ZF, p0, 4, 0, 4, 4, 1, 0) &&
-             make(m + TM_P1_OWN, p1, 4, 0, 4, 4, 2, 0) && make(m + TM_P1_XF, p1, 4, 0, 1, 4, 2, 0) && make(m + TM_P1_YF, p1, 4, 0, 4, 1, 2, 0) && make(m + TM_P1_ZF, p1, 4, 0, 4, 4, 1, 0) &&
+        void* po = s->pose0[g].p;                      // [2][N] double4: part 0 = pose0, part 1 = pose1
+        void* rc = s->rec[g].p;                        // [12][N] sixteen-byte parts, four per axis
+        ok = make(m + TM_P_OWN, po, 4, 2, 4, 4, 2, 2) && make(m + TM_P_XF, po, 4, 2, 1, 4, 2, 2) && make(m + TM_P_YF, po, 4, 2, 4, 1, 2, 2) && make(m + TM_P_ZF, po, 4, 2, 4, 4, 1, 2) &&
              make(m + TM_M0, s->mom0[g].p, 4, 0, 4, 4, 2, 0) && make(m + TM_M1, s->mom1[g].p, 2, 0, 4, 4, 2, 0) &&
-             make(m + TM_REC_OWN, s->rec[g].p, 2, 9, 4, 4, 2, 9) && make(m + TM_REC_XF, s->rec[g].p, 2, 9, 1, 4, 2, 3) && make(m + TM_REC_YF, s->rec[g].p, 2, 9, 4, 1, 2, 3) &&
-             make(m + TM_REC_ZF, s->rec[g].p, 2, 9, 4, 4, 1, 3) &&
-             make(m + TM_RECF_OWN, s->recf[g].p, 2, 3, 4, 4, 2, 3) && make(m + TM_RECF_XF, s->recf[g].p, 2, 3, 1, 4, 2, 1) && make(m + TM_RECF_YF, s->recf[g].p, 2, 3, 4, 1, 2, 1) &&
-             make(m + TM_RECF_ZF, s->recf[g].p, 2, 3, 4, 4, 1, 1);
+             make(m + TM_REC_OWN, rc, 2, VX_REC_PARTS, 4, 4, 2, VX_REC_PARTS) && make(m + TM_REC_XF, rc, 2, VX_REC_PARTS, 1, 4, 2, 4) &&
+             make(m + TM_REC_YF, rc, 2, VX_REC_PARTS, 4, 1, 2, 4) && make(m + TM_REC_ZF, rc, 2, VX_REC_PARTS, 4, 4, 1, 4);
     }
     if (!ok) return fail(s, VX_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     CK(s->tmaps.alloc(maps.size() * sizeof(CUtensorMap)));
@@ -685,66 +689,39 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     }
     if (grid > 0) {
         const LatFrame f = s->lat_frame(g);
-        const int fl = s->floor_on ? 1 : 0, gr_ = grouped ? 1 : 0;
-        const dim3 gr((unsigned)grid), bl(32 * VX_WB_WARPS);
+        const int fl = s->floor_on ? 1 : 0;
+        const dim3 bl(32 * VX_WB_WARPS);
         const unsigned char* tm = s->tmaps.p;
         if (tma) {
+            // grouped: one CTA per 2x2x2 group of bricks on a 3-D grid (no index divisions in the kernel); a grid too tall for
+            // blockIdx.y/z falls back to the 1-D brick enumeration, which covers the same bricks
+            const long long zdim = (long long)nbz * s->n_members;
+            const bool g3 = grouped && VX_WB_WARPS == 8 && nby <= 65535 && zdim <= 65535;
+            const dim3 gr = g3 ? dim3((unsigned)nbx, (unsigned)nby, (unsigned)zdim) : dim3((unsigned)(((long long)bx * by * (ngz >= 0 ? 2 * ngz : bz) * s->n_members + VX_WB_WARPS - 1) / VX_WB_WARPS));
+            const int kx = g3 ? nbx : bx, ky = g3 ? nby : by, kz = g3 ? nbz : (ngz >= 0 ? 2 * ngz : bz), koff = g3 ? gz_off : 2 * gz_off, gr_ = g3 ? 1 : 0;
             if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
-                if (s->uni) k_lattice_tma<true, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
-                else k_lattice_tma<false, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+                if (s->uni) k_lattice_tma<true, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
+                else k_lattice_tma<false, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
             } else {
-                if (s->uni) k_lattice_tma<true, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
-                else k_lattice_tma<false, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+                if (s->uni) k_lattice_tma<true, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
+                else k_lattice_tma<false, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
             }
-        } else if (s->push_in_kernel) {
-            if (s->uni) k_lattice_warp<true, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
-            else k_lattice_warp<false, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
         } else {
-            if (s->uni) k_lattice_warp<true, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
-            else k_lattice_warp<false, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+            const dim3 gr((unsigned)grid);
+            const int gr_ = grouped ? 1 : 0;
+            if (s->push_in_kernel) {
+                if (s->uni) k_lattice_warp<true, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+                else k_lattice_warp<false, true><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+            } else {
+                if (s->uni) k_lattice_warp<true, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+                else k_lattice_warp<false, false><<<gr, bl, VX_WB_SMEM, s->stream>>>(f, g, first_of_call, fl, nbx, nby, nbz, gz_off, book, gr_);
+            }
         }
         s->launches++;
     }
 }
 
-static void launch_lattice(vx_sim* s, int g, int first_of_call)
-{
-    if (s->path == 3) {                  // ablation: one thread per voxel, all six links re-evaluated
-        if (s->uni) k_lattice_step<true><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
-        else k_lattice_step<false><<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0);
-    } else if (s->path == 6) {           // marching warp bricks: 3.5 link evaluations per voxel
-        const int ncx = (s->nx + VX_WB_X - 1) / VX_WB_X, ncy = (s->ny + VX_WB_Y - 1) / VX_WB_Y, ncz = (s->nz + 4 * VX_ZM_PAIRS - 1) / (4 * VX_ZM_PAIRS);
-        const long long warps = (long long)ncx * ncy * ncz * s->n_members;
-        const long long grid = (warps + VX_ZM_WARPS - 1) / VX_ZM_WARPS;
-        if (!s->zm_opted_in) {
-            cudaFuncSetAttribute(k_lattice_zmarch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_ZM_SMEM);
-            cudaFuncSetAttribute(k_lattice_zmarch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_ZM_SMEM);
-            s->zm_opted_in = true;
-        }
-        if (s->uni) k_lattice_zmarch<true><<<(unsigned)grid, 32 * VX_ZM_WARPS, VX_ZM_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ncx, ncy, ncz);
-        else k_lattice_zmarch<false><<<(unsigned)grid, 32 * VX_ZM_WARPS, VX_ZM_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ncx, ncy, ncz);
-    } else if (s->path != 2 && s->path != 4) {   // default: one warp per 4x4x2 brick, no block barriers
-        launch_lattice_warp(s, g, first_of_call, 0, -1, 1);
-        return;
-    } else if (s->path == 2) {           // 8x4x4 bricks per block, thread per link evaluation + shared-memory slots
-        const int ntx = (s->nx + VX_TILE_X - 1) / VX_TILE_X, nty = (s->ny + VX_TILE_Y - 1) / VX_TILE_Y, ntz = (s->nz + VX_TILE_Z - 1) / VX_TILE_Z;
-        const long long grid = (long long)ntx * nty * ntz * s->n_members;
-        if (!s->tile_opted_in) {         // > 48 KB of dynamic shared memory needs a one-time opt-in per function and device
-            cudaFuncSetAttribute(k_lattice_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TILE_SMEM);
-            cudaFuncSetAttribute(k_lattice_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TILE_SMEM);
-            s->tile_opted_in = true;
-        }
-        if (s->uni) k_lattice_tile<true><<<(unsigned)grid, VX_TILE_THREADS, VX_TILE_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ntx, nty, ntz);
-        else k_lattice_tile<false><<<(unsigned)grid, VX_TILE_THREADS, VX_TILE_SMEM, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, ntx, nty, ntz);
-    } else {                             // ablation: z-marching warps, X by shuffle, Z by register carry
-        const int n_seg = (s->nx + 30) / 31, n_yg = (s->ny + VX_MARCH_ROWS - 1) / VX_MARCH_ROWS;
-        const int n_zc = (s->nz + VX_MARCH_ZL - 1) / VX_MARCH_ZL;
-        const long long grid = (long long)n_seg * n_yg * n_zc * s->n_members;
-        if (s->uni) k_lattice_march<true><<<(unsigned)grid, 32 * VX_MARCH_ROWS, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, n_seg, n_yg, n_zc);
-        else k_lattice_march<false><<<(unsigned)grid, 32 * VX_MARCH_ROWS, 0, s->stream>>>(s->lat_frame(g), g, first_of_call, s->floor_on ? 1 : 0, n_seg, n_yg, n_zc);
-    }
-    s->launches++;
-}
+static void launch_lattice(vx_sim* s, int g, int first_of_call) { launch_lattice_warp(s, g, first_of_call, 0, -1, 1); }
 
 static int ensure_lattice_graph(vx_sim* s, int g0)
 {
@@ -855,7 +832,7 @@ extern "C" {
 int vx_step_begin(vx_sim* s, float dt)
 {
     if (!s) return VX_ERR_ARG;
-    if (!s->lattice || (s->path != 0 && s->path != 5 && s->path != 7)) return fail(s, VX_ERR_UNSUPPORTED, "asynchronous stepping needs the fused lattice path");
+    if (!s->lattice) return fail(s, VX_ERR_UNSUPPORTED, "asynchronous stepping needs the fused lattice path");
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_step_begin: a call is already open");
     if (dt <= 0) return fail(s, VX_ERR_ARG, "vx_step_begin needs an explicit dt");
     CK(cudaSetDevice(s->device));
@@ -941,7 +918,7 @@ void vx_destroy(vx_sim* s)
     if (s->ev_comm) cudaEventDestroy(s->ev_comm);
     s->peer_flags.release(); s->tmaps.release();
     s->drop_graph();
-    for (int g = 0; g < 2; g++) { s->pose0[g].release(); s->pose1[g].release(); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); s->recf[g].release(); }
+    for (int g = 0; g < 2; g++) { s->release_pose(g); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); }
     s->pair_lmat.release(); s->link_owner.release(); s->link_axis_dev.release();
     s->c_surf_vox.release(); s->c_surf_orig.release(); s->c_surf_member.release(); s->c_slot.release(); s->c_surf_ijk.release(); s->c_nearby.release();
     s->c_last_watch.release(); s->c_head.release(); s->c_next.release(); s->c_cell.release(); s->c_pairs.release(); s->c_pair_kc.release();
@@ -1014,7 +991,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
     if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
     bool poisson = false;
     for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
-    if (n == 0 || poisson || s->path == 1 || (s->collisions && s->path != 0 && s->path != 5 && s->path != 7))
+    if (n == 0 || poisson || s->path == 1)
         return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
     int lo[3] = {32767, 32767, 32767}, hi[3] = {-32768, -32768, -32768}, members = 1;
     for (int i = 0; i < n; i++) {
@@ -1149,8 +1126,7 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     // ---- layout: a completely filled box (per member) without Poisson materials runs fused
     bool poisson = false;
     for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
-    const bool fused_default = s->path == 0 || s->path == 5 || s->path == 7;     // the kernels that gather contact forces
-    s->lattice = n > 0 && cells == (long long)n && !poisson && (!s->collisions || fused_default) && s->path != 1;
+    s->lattice = n > 0 && cells == (long long)n && !poisson && s->path != 1;
     s->nx = (int)ext3[0]; s->ny = (int)ext3[1]; s->nz = (int)ext3[2];
     s->link_owner.release(); s->link_axis_dev.release();
     s->si_nominal_ok = false; s->si_consts_ok = false; s->si_pressure_ok = false;
@@ -1165,17 +1141,17 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     CK(s->ext_idx.alloc(n1)); CK(s->vox_e2i_dev.alloc(n1)); CK(s->link_e2i_dev.alloc(l1)); CK(s->member_dev.alloc(n1));
     if (s->lattice) {
         for (int g = 0; g < 2; g++) {
-            CK(s->pose0[g].alloc(n1)); CK(s->pose1[g].alloc(n1)); CK(s->mom0[g].alloc(n1)); CK(s->mom1[g].alloc(n1));
-            CK(s->rec[g].alloc(n1 * 9)); CK(s->recf[g].alloc(n1 * 3));
+            CK(s->alloc_pose(g, n1)); CK(s->mom0[g].alloc(n1)); CK(s->mom1[g].alloc(n1));
+            CK(s->rec[g].alloc(n1 * VX_REC_PARTS));
         }
         s->slots.release(); s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release();
         s->lstrain.release(); s->pstrain.release(); s->slot_strain.release();
         s->lk_mat.clear();
         s->tmaps.release();                           // describe the old arrays
     } else {
-        CK(s->pose0[0].alloc(n1)); CK(s->pose1[0].alloc(n1)); CK(s->mom0[0].alloc(n1)); CK(s->mom1[0].alloc(n1));
-        for (int g = 0; g < 2; g++) { s->rec[g].release(); s->recf[g].release(); }
-        s->pose0[1].release(); s->pose1[1].release(); s->mom0[1].release(); s->mom1[1].release();
+        CK(s->alloc_pose(0, n1)); CK(s->mom0[0].alloc(n1)); CK(s->mom1[0].alloc(n1));
+        for (int g = 0; g < 2; g++) s->rec[g].release();
+        s->release_pose(1); s->mom0[1].release(); s->mom1[1].release();
         CK(s->slots.alloc(n1 * 36));
         CK(s->lends.alloc(l1)); CK(s->lmeta.alloc(l1)); CK(s->lstA.alloc(l1)); CK(s->lstB.alloc(l1)); CK(s->lstC.alloc(l1)); CK(s->lstrain.alloc(l1));
         CK(s->pstrain.alloc(n1)); CK(s->slot_strain.alloc(n1 * 6));
@@ -1751,26 +1727,27 @@ int vx_halo_import_on(vx_sim* s, int iz, uint64_t src0, uint64_t src1, int count
 
 int64_t vx_launch_count(const vx_sim* s) { return s ? s->launches : 0; }
 int vx_sync(vx_sim* s) { if (!s) return VX_ERR_ARG; CK(cudaSetDevice(s->device)); CK(cudaStreamSynchronize(s->stream)); return VX_OK; }
-/* takes effect at the next vx_set_voxels */
-int vx_set_path(vx_sim* s, int path) { if (!s) return VX_ERR_ARG; s->path = path; return VX_OK; }
+/* takes effect at the next vx_set_voxels (the device layout depends on it); 5 <-> 7 <-> 0 on a lattice handle switch at once */
+int vx_set_path(vx_sim* s, int path)
+{
+    if (!s) return VX_ERR_ARG;
+    if (path != 0 && path != 1 && path != 5 && path != 7) return fail(s, VX_ERR_ARG, "vx_set_path: 0 (auto), 1 (general), 5 (fused, cp.async) or 7 (fused, TMA)");
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_path inside vx_step_begin .. vx_step_end");
+    if (path != s->path) s->drop_graph();            // captured graphs hold the kernel variant
+    s->path = path;
+    return VX_OK;
+}
 int vx_active_path(const vx_sim* s) { return s && s->lattice ? 2 : 1; }
 const char* vx_kernel_name(const vx_sim* s)
 {
     if (!s || !s->lattice) return "k_link<AXIS> (3 launches per step, one per link axis)";
-    switch (s->path) {
-    case 2: return "k_lattice_tile (fused link+voxel, 8x4x4 brick per block, 1 launch per step)";
-    case 3: return "k_lattice_step (fused link+voxel, one thread per voxel, 1 launch per step)";
-    case 4: return "k_lattice_march (fused link+voxel, z-marching columns, 1 launch per step)";
-    case 6: return "k_lattice_zmarch (fused link+voxel, 4x4 column per warp marching in z, 1 launch per step)";
-    case 5: return "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, cp.async staging, 1 launch per step)";
-    case 7: return "k_lattice_tma (fused link+voxel, 4x4x2 brick per warp, TMA staging, 1 launch per step)";
-    default: {
+    bool tma = s->path == 7;
+    if (s->path == 0) {
         const int bx = (s->nx + VX_WB_X - 1) / VX_WB_X, by = (s->ny + VX_WB_Y - 1) / VX_WB_Y, bz = (s->nz + VX_WB_Z - 1) / VX_WB_Z;
-        const bool grouped = (double)((bx + 1) / 2) * ((by + 1) / 2) * ((bz + 1) / 2) * 8 <= 1.1 * (double)bx * by * bz;
-        return grouped ? "k_lattice_tma (fused link+voxel, 4x4x2 brick per warp, TMA staging, 1 launch per step)"
-                       : "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, cp.async staging, 1 launch per step)";
+        tma = (double)((bx + 1) / 2) * ((by + 1) / 2) * ((bz + 1) / 2) * 8 <= 1.1 * (double)bx * by * bz;
     }
-    }
+    return tma ? "k_lattice_tma (fused link+voxel, 4x4x2 brick per warp, TMA staging, 1 launch per step)"
+               : "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, cp.async staging, 1 launch per step)";
 }
 
 } // extern "C"

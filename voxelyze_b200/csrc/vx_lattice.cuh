@@ -10,14 +10,12 @@
 //     from the same old inputs (identical bits) instead of shipping its force.
 //   * Implicit indexing: neighbour = v +- {1, nx, nx*ny}; no index arrays are read.
 //
-// Kernels (all produce identical bits; vx_set_path selects, tests/test_gpu_parity.py compares them):
-//   k_lattice_tma     7, and what 0 picks on large lattices: one warp per 4x4x2 brick, staged by TMA  (2.9 ms @256^3)
-//   k_lattice_warp    5, and what 0 picks for ensembles of small boxes: same, staged by cp.async       (3.1 ms)
-//   (vx_lattice_variants.cuh:)
-//   k_lattice_tile    2: one block per 8x4x4 brick, thread per link evaluation, block barriers         (3.7 ms)
-//   k_lattice_step    3: one thread per voxel, all six links re-evaluated                              (4.0 ms)
-//   k_lattice_march   4: z-marching warps, X by shuffle, Z by register carry                           (4.6 ms)
-//   k_lattice_zmarch  6: marching warp bricks, 3.5 evaluations per voxel                               (4.1 ms)
+// Kernels (both produce identical bits, and the same bits as the general path; vx_set_path selects,
+// tests/test_gpu_parity.py compares them):
+//   k_lattice_tma     7, and what 0 picks on large lattices: one warp per 4x4x2 brick, staged by TMA
+//   k_lattice_warp    5, and what 0 picks for ensembles of small boxes: same, staged by cp.async
+// (Round 1 also carried four slower formulations -- block bricks with barriers, one thread per voxel, z-marching
+// warps, marching warp bricks; they were ablations, are documented in profiles/r1_*_ncu_summary.md and no longer ship.)
 //
 // HBM traffic per voxel per step (nu = 0):  read 64 B pose + 48 B momenta + 3 x 64 B link records,
 // write the same = 608 B, vs. 216 + 3 x 268 = 1020 B "algorithmic" bytes of SURVEY.md section 8d (the
@@ -35,13 +33,15 @@
 namespace vxd {
 
 #define VM_LFLAG_SHIFT 26     // 2 bits per owned link: bit 0 small-angle, bit 1 local-velocity-valid
+#define VX_REC_PARTS 12       // sixteen-byte parts of the link records of one voxel: axis a -> parts 4a..4a+2 (double2) and 4a+3 (float4)
 
 struct LatFrame {
     int nx, ny, nz, nxy, n_vox, n_mat;
     // voxel state, current (read) and next (write) generation
     const double4* c_pose0; const double4* c_pose1; const double4* c_mom0; const double2* c_mom1;
     double4* n_pose0; double4* n_pose1; double4* n_mom0; double2* n_mom1;
-    // link records owned by voxel v for axis a: rec[a][0..2][v] (double2 x3) + recf[a][v] (float4)
+    // link records owned by voxel v for axis a: rec[a][0..2][v] (double2 x3) + recf[a][v] (float4); all twelve arrays of a
+    // generation are one allocation, part (4a + k) at c_rec[0][0] + (4a + k) * n_vox, recf[a] being part 4a + 3
     const double2* c_rec[3][3]; const float4* c_recf[3];
     double2* n_rec[3][3]; float4* n_recf[3];
     const int* ext_idx;
@@ -181,7 +181,7 @@ __global__ void k_lattice_gather_links(LatFrame cur, LatFrame prev, int have_pre
 
 // persistent link state <- packed records (see k_scatter_link_state); the mode bits go to the owner's meta word.
 // One thread per OWNER VOXEL and axis pass (no two threads touch the same meta word).
-__global__ void k_lattice_scatter_link_state(double4* pose1, double2* rec, float4* recf, const int* link_of_owner, int n_vox,
+__global__ void k_lattice_scatter_link_state(double4* pose1, double2* rec, const int* link_of_owner, int n_vox,
                                              const LinkStateRec* src, int first, int count)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,8 +198,8 @@ __global__ void k_lattice_scatter_link_state(double4* pose1, double2* rec, float
         st.strain = r.strain; st.max_strain = r.max_strain; st.strain_offset = r.strain_offset; st.stress = r.stress;
         double2 a, b, c; float4 s4; uint32_t lf;
         lat_encode(st, a, b, c, s4, lf);
-        rec[(size_t)(axis * 3 + 0) * n_vox + v] = a; rec[(size_t)(axis * 3 + 1) * n_vox + v] = b; rec[(size_t)(axis * 3 + 2) * n_vox + v] = c;
-        recf[(size_t)axis * n_vox + v] = s4;
+        rec[(size_t)(axis * 4 + 0) * n_vox + v] = a; rec[(size_t)(axis * 4 + 1) * n_vox + v] = b; rec[(size_t)(axis * 4 + 2) * n_vox + v] = c;
+        reinterpret_cast<float4*>(rec + (size_t)(axis * 4 + 3) * n_vox)[v] = s4;
         bits = (bits & ~(3u << (VM_LFLAG_SHIFT + 2 * axis))) | (lf << (VM_LFLAG_SHIFT + 2 * axis));
         touched = true;
     }
@@ -331,8 +331,8 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
     // ---- requests, one round ahead.  cp.async groups in issue order: H (+ the brick's own poses), round 0,
     //      [after H] round 1 and the round-2 poses, [after round 0] round 2, [after round 1] momenta
     // record arrays of one generation are one allocation: [axis][part][voxel] (vx_capi.cu lat_frame)
-    auto c_rec = [&](int a, int k) { return f.c_rec[0][0] + (size_t)(a * 3 + k) * f.n_vox; };
-    auto c_recf = [&](int a) { return f.c_recf[0] + (size_t)a * f.n_vox; };
+    auto c_rec = [&](int a, int k) { return f.c_rec[0][0] + (size_t)(a * 4 + k) * f.n_vox; };
+    auto c_recf = [&](int a) { return f.c_rec[0][0] + (size_t)(a * 4 + 3) * f.n_vox; };
     auto request_pose = [&](int entry, int vox) {
         cp_async16(&pose_sh[0][entry], reinterpret_cast<const uint4*>(f.c_pose0 + vox));
         cp_async16(&pose_sh[1][entry], reinterpret_cast<const uint4*>(f.c_pose0 + vox) + 1);
@@ -417,8 +417,8 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
                                    n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
             double2 wa, wb, wc; float4 ws; uint32_t lf;
             lat_encode(st, wa, wb, wc, ws, lf);
-            double2* nr = f.n_rec[0][0] + (size_t)(a * 3) * f.n_vox + v;       // the nine record arrays are one allocation
-            nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; (f.n_recf[0] + (size_t)a * f.n_vox)[v] = ws;
+            double2* nr = f.n_rec[0][0] + (size_t)(a * 4) * f.n_vox + v;       // the twelve record arrays are one allocation
+            nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; *reinterpret_cast<float4*>(nr + 3 * (size_t)f.n_vox) = ws;
             new_bits = (new_bits & ~(3u << (VM_LFLAG_SHIFT + 2 * a))) | (lf << (VM_LFLAG_SHIFT + 2 * a));
             if (st.strain > 100) p->div_flag[parity] = 1;          // src/Voxelyze.cpp:265
             F = F + fN; M = M + mN;
@@ -497,25 +497,26 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
 // k_lattice_tma -- the warp-brick step with its staging done by the Tensor Memory Accelerator.
 //
 // Same arithmetic, same rounds as k_lattice_warp.  What changes is how a brick's inputs reach shared
-// memory: instead of ~70 cp.async instructions per lane, ONE lane issues 24 bulk tensor copies
-// (cp.async.bulk.tensor, boxes of the lattice arrays described by CUtensorMap descriptors):
+// memory: instead of ~70 cp.async instructions per lane, ONE lane issues 13 bulk tensor copies
+// (cp.async.bulk.tensor, boxes of the lattice arrays described by CUtensorMap descriptors; both pose
+// records of a voxel set, and all four parts of a link record, are one 4-D box because their arrays
+// share an allocation):
 //   group 0 (mbarrier 0)  the brick's own poses; the three faces just outside -X/-Y/-Z (poses and the
 //                         records of the links entering through them)                    -> round H
-//   group 1 (mbarrier 1)  all nine record parts of the brick's own links in one 4-D box; the +X/+Y faces
+//   group 1 (mbarrier 1)  all twelve record parts of the brick's own links in one box; the +X/+Y faces
 //   group 2 (mbarrier 2)  issued after round H into the space its inputs leave: momenta, the +Z face
 // Boxes that poke out of the lattice are zero-filled by the hardware, so the requests need no
 // predicates and no index arithmetic.  Waiting is mbarrier.try_wait.parity with a bounded spin.
 // Shared memory per warp 13 440 B:
 //   0      own pose0 [32]x32      1024   | 9216  -X pose0/pose1 [8]x32  2x256  \
 //   1024   own pose1              1024   | 9728  -Y pose0/pose1         2x256   > after H: hslot 1536, +Z pose0 512
-//   2048   own rec  [9][32]x16    4608   | 10240 -Z pose0/pose1 [16]x32 2x512  /
-//   6656   own recf [3][32]x16    1536   | 11264 -X rec [3][8]x16 384, recf 128 \  after H: +Z pose1 512,
-//   8192   +X pose0/pose1 [8]x32  2x256  | 11776 -Y rec 384, recf 128            > momenta mom0 1024, mom1 512
-//   8704   +Y pose0/pose1         2x256  | 12288 -Z rec [3][16]x16 768, recf 256 /
+//   2048   own rec  [12][32]x16   6144   | 10240 -Z pose0/pose1 [16]x32 2x512  /
+//          (part 4a+k, k = 3: float4)    | 11264 -X rec [4][8]x16  512 \  after H: +Z pose1 512,
+//   8192   +X pose0/pose1 [8]x32  2x256  | 11776 -Y rec            512  > momenta mom0 1024, mom1 512
+//   8704   +Y pose0/pose1         2x256  | 12288 -Z rec [4][16]x16 1024 /
 //   13312  three mbarriers
 // Tensor maps (built on the host, vx_capi.cu build_tensor_maps), u64 elements, per generation:
-enum { TM_P0_OWN, TM_P0_XF, TM_P0_YF, TM_P0_ZF, TM_P1_OWN, TM_P1_XF, TM_P1_YF, TM_P1_ZF, TM_M0, TM_M1,
-       TM_REC_OWN, TM_REC_XF, TM_REC_YF, TM_REC_ZF, TM_RECF_OWN, TM_RECF_XF, TM_RECF_YF, TM_RECF_ZF, TM_COUNT };
+enum { TM_P_OWN, TM_P_XF, TM_P_YF, TM_P_ZF, TM_M0, TM_M1, TM_REC_OWN, TM_REC_XF, TM_REC_YF, TM_REC_ZF, TM_COUNT };
 // =================================================================================================
 #define VX_TMA_WARP_BYTES 13440
 #define VX_TMA_SMEM (VX_WB_WARPS * VX_TMA_WARP_BYTES)
@@ -529,15 +530,23 @@ __device__ __forceinline__ bool elect_one()
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+// A bulk copy that never lands must fail the launch, not hang the GPU -- but a healthy copy can take arbitrarily long
+// under a debugger, compute-sanitizer or an MPS time slice, so the bound is wall time (globaltimer, 20 s), not a poll count.
 __device__ __forceinline__ void mbar_wait(uint32_t bar)
 {
+    unsigned long long t0 = 0;
 #pragma unroll 1
-    for (int spin = 0; spin < (1 << 24); spin++) {
+    for (unsigned spin = 0;; spin++) {
         uint32_t done;
         asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(done) : "r"(bar) : "memory");
         if (done) return;
+        if ((spin & 0xFFFu) == 0xFFFu) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 20000000000ull) __trap();
+        }
     }
-    __trap();                            // a copy that never lands must fail the launch, not hang the GPU
 }
 __device__ __forceinline__ void tma_3d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2)
 {
@@ -550,6 +559,8 @@ __device__ __forceinline__ void tma_4d(uint32_t dst, const void* map, uint32_t b
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// Grid: grouped (large lattices) -> 3-D, one CTA per 2x2x2 group of bricks: blockIdx = (group x, group y, member * nbz + group layer);
+//       else (ensembles of small boxes) -> 1-D, eight consecutive bricks per CTA, bricks x-fastest, no padding.
 template <bool UNI, bool PUSH>
 __global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
 k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book, int grouped)
@@ -557,15 +568,9 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     // nbx/nby/nbz, gz_off, book, grouped, PUSH: as in k_lattice_warp
     extern __shared__ __align__(128) unsigned char tma_smem[];
     DevParams* p = f.params;
-    const int frozen = p->div_flag[parity ^ 1] | p->div_latched;
-    const float dt = p->dt;
-    const float prev_dt = first_of_call ? p->prev_dt : dt;
-    if (book && blockIdx.x == 0 && threadIdx.x == 0) {
-        if (frozen) p->div_latched = 1;
-        else if (p->pending) { p->steps_done += 1; p->time += dt; }
-        if (!frozen) p->pending = 1;
-    }
-    if (frozen) return;
+    // the step scalars are requested first and looked at only after the bulk copies are on their way
+    const int div_prev = p->div_flag[parity ^ 1], div_latched = p->div_latched;
+    const float dt = p->dt, prev_dt_call = p->prev_dt;
 
     // the warp index through a shuffle: the compiler then knows it (and the brick origin, the shared-memory window, the
     // tensor coordinates) to be warp-uniform and issues the bulk copies from uniform registers without a per-lane loop
@@ -574,49 +579,54 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     const uint32_t sb = smem_u32(wbase);
     const uint32_t bar0 = sb + 13312, bar1 = sb + 13320, bar2 = sb + 13328;
 
-    int b = blockIdx.x * VX_WB_WARPS + warp;
-    const int w8 = grouped ? b & 7 : 0;
-    if (grouped) b >>= 3;
-    const int gx = b % nbx; b /= nbx;
-    const int gy = b % nby; b /= nby;
-    const int gz = gz_off + b % nbz; const int member = b / nbz;
-    const int x0 = grouped ? (gx * 2 + (w8 & 1)) * VX_WB_X : gx * VX_WB_X, y0 = grouped ? (gy * 2 + ((w8 >> 1) & 1)) * VX_WB_Y : gy * VX_WB_Y,
-              z0 = grouped ? (gz * 2 + (w8 >> 2)) * VX_WB_Z : gz * VX_WB_Z;
-    if (member * f.nz * f.nxy >= f.n_vox || x0 >= f.nx || y0 >= f.ny || z0 >= f.nz) return;            // whole warp
+    int x0, y0, z0, member;
+    if (grouped) {
+        const unsigned zz = blockIdx.z;
+        member = gridDim.z > (unsigned)nbz ? (int)(zz / (unsigned)nbz) : 0;
+        const int gz = gz_off + (int)zz - member * nbz;
+        x0 = ((int)blockIdx.x * 2 + (warp & 1)) * VX_WB_X; y0 = ((int)blockIdx.y * 2 + ((warp >> 1) & 1)) * VX_WB_Y; z0 = (gz * 2 + (warp >> 2)) * VX_WB_Z;
+    } else {
+        unsigned b = blockIdx.x * VX_WB_WARPS + warp;
+        const unsigned gx = b % (unsigned)nbx; b /= (unsigned)nbx;
+        const unsigned gy = b % (unsigned)nby; b /= (unsigned)nby;
+        const unsigned gz = b % (unsigned)nbz; member = (int)(b / (unsigned)nbz);
+        x0 = (int)gx * VX_WB_X; y0 = (int)gy * VX_WB_Y; z0 = (gz_off + (int)gz) * VX_WB_Z;
+    }
+    const bool no_brick = member * f.nz * f.nxy >= f.n_vox || x0 >= f.nx || y0 >= f.ny || z0 >= f.nz;            // whole warp
     const int vbase = member * f.nz * f.nxy;
     const int Z0 = member * f.nz + z0;             // the tensors see the members stacked along z
 
     // ---- one lane arms the barriers and issues every copy of groups 0 and 1
-    if (elect_one()) {
+    if (!no_brick && elect_one()) {
         mbar_init(bar0); mbar_init(bar1); mbar_init(bar2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const unsigned char* tm = tmaps + (size_t)parity * TM_COUNT * 128;
         auto map = [&](int k) { return tm + k * 128; };
         mbar_expect(bar0, 2048 + 2048 + 2048);
-        tma_3d(sb + 0, map(TM_P0_OWN), bar0, 4 * x0, y0, Z0);
-        tma_3d(sb + 1024, map(TM_P1_OWN), bar0, 4 * x0, y0, Z0);
-        tma_3d(sb + 9216, map(TM_P0_XF), bar0, 4 * (x0 - 1), y0, Z0);
-        tma_3d(sb + 9472, map(TM_P1_XF), bar0, 4 * (x0 - 1), y0, Z0);
-        tma_3d(sb + 9728, map(TM_P0_YF), bar0, 4 * x0, y0 - 1, Z0);
-        tma_3d(sb + 9984, map(TM_P1_YF), bar0, 4 * x0, y0 - 1, Z0);
-        tma_3d(sb + 10240, map(TM_P0_ZF), bar0, 4 * x0, y0, Z0 - 1);
-        tma_3d(sb + 10752, map(TM_P1_ZF), bar0, 4 * x0, y0, Z0 - 1);
+        tma_4d(sb + 0, map(TM_P_OWN), bar0, 4 * x0, y0, Z0, 0);
+        tma_4d(sb + 9216, map(TM_P_XF), bar0, 4 * (x0 - 1), y0, Z0, 0);
+        tma_4d(sb + 9728, map(TM_P_YF), bar0, 4 * x0, y0 - 1, Z0, 0);
+        tma_4d(sb + 10240, map(TM_P_ZF), bar0, 4 * x0, y0, Z0 - 1, 0);
         tma_4d(sb + 11264, map(TM_REC_XF), bar0, 2 * (x0 - 1), y0, Z0, 0);
-        tma_4d(sb + 11648, map(TM_RECF_XF), bar0, 2 * (x0 - 1), y0, Z0, 0);
-        tma_4d(sb + 11776, map(TM_REC_YF), bar0, 2 * x0, y0 - 1, Z0, 3);
-        tma_4d(sb + 12160, map(TM_RECF_YF), bar0, 2 * x0, y0 - 1, Z0, 1);
-        tma_4d(sb + 12288, map(TM_REC_ZF), bar0, 2 * x0, y0, Z0 - 1, 6);
-        tma_4d(sb + 13056, map(TM_RECF_ZF), bar0, 2 * x0, y0, Z0 - 1, 2);
-        mbar_expect(bar1, 4608 + 1536 + 1024);
+        tma_4d(sb + 11776, map(TM_REC_YF), bar0, 2 * x0, y0 - 1, Z0, 4);
+        tma_4d(sb + 12288, map(TM_REC_ZF), bar0, 2 * x0, y0, Z0 - 1, 8);
+        mbar_expect(bar1, 6144 + 1024);
         tma_4d(sb + 2048, map(TM_REC_OWN), bar1, 2 * x0, y0, Z0, 0);
-        tma_4d(sb + 6656, map(TM_RECF_OWN), bar1, 2 * x0, y0, Z0, 0);
-        tma_3d(sb + 8192, map(TM_P0_XF), bar1, 4 * (x0 + VX_WB_X), y0, Z0);
-        tma_3d(sb + 8448, map(TM_P1_XF), bar1, 4 * (x0 + VX_WB_X), y0, Z0);
-        tma_3d(sb + 8704, map(TM_P0_YF), bar1, 4 * x0, y0 + VX_WB_Y, Z0);
-        tma_3d(sb + 8960, map(TM_P1_YF), bar1, 4 * x0, y0 + VX_WB_Y, Z0);
+        tma_4d(sb + 8192, map(TM_P_XF), bar1, 4 * (x0 + VX_WB_X), y0, Z0, 0);
+        tma_4d(sb + 8704, map(TM_P_YF), bar1, 4 * x0, y0 + VX_WB_Y, Z0, 0);
     }
     __syncwarp();
+
+    const int frozen = div_prev | div_latched;
+    const float prev_dt = first_of_call ? prev_dt_call : dt;
+    if (book && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+        if (frozen) p->div_latched = 1;
+        else if (p->pending) { p->steps_done += 1; p->time += dt; }
+        if (!frozen) p->pending = 1;
+    }
+    if (no_brick) return;
+    if (frozen) { mbar_wait(bar0); mbar_wait(bar1); return; }      // the copies must have landed before the CTA's shared memory is released
 
     const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
     const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
@@ -633,10 +643,10 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     auto meta_of = [&](int entry) { return reinterpret_cast<const uint32_t*>(wbase + 1024 + entry * 32)[7]; };   // high word of own pose1.w
 
     // ---- entering link of this lane (round H)
-    int h_axis, h_tl, h_pose, h_rec, h_recf, h_part;             // face regions: poses, records (part stride), recf
-    if (lane < 8) { h_axis = 0; h_tl = ((lane >> 2) << 4) | ((lane & 3) << 2); h_pose = 9216 + lane * 32; h_rec = 11264 + lane * 16; h_part = 128; h_recf = 11648 + lane * 16; }
-    else if (lane < 16) { h_axis = 1; h_tl = (((lane - 8) >> 2) << 4) | ((lane - 8) & 3); h_pose = 9728 + (lane - 8) * 32; h_rec = 11776 + (lane - 8) * 16; h_part = 128; h_recf = 12160 + (lane - 8) * 16; }
-    else { h_axis = 2; h_tl = lane - 16; h_pose = 10240 + (lane - 16) * 32; h_rec = 12288 + (lane - 16) * 16; h_part = 256; h_recf = 13056 + (lane - 16) * 16; }
+    int h_axis, h_tl, h_pose, h_rec, h_part;                     // face regions: poses, records (part stride)
+    if (lane < 8) { h_axis = 0; h_tl = ((lane >> 2) << 4) | ((lane & 3) << 2); h_pose = 9216 + lane * 32; h_rec = 11264 + lane * 16; h_part = 128; }
+    else if (lane < 16) { h_axis = 1; h_tl = (((lane - 8) >> 2) << 4) | ((lane - 8) & 3); h_pose = 9728 + (lane - 8) * 32; h_rec = 11776 + (lane - 8) * 16; h_part = 128; }
+    else { h_axis = 2; h_tl = lane - 16; h_pose = 10240 + (lane - 16) * 32; h_rec = 12288 + (lane - 16) * 16; h_part = 256; }
     const int h_face = h_axis == 2 ? 512 : 256;                  // pose1 of a face follows its pose0
 
     mbar_wait(bar0);
@@ -652,7 +662,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         load_pose(h_pose, h_pose + h_face, 0, n0, n1);
         load_pose(0, 1024, h_tl, p0, p1);
         const uint4 r0 = *reinterpret_cast<const uint4*>(wbase + h_rec), r1 = *reinterpret_cast<const uint4*>(wbase + h_rec + h_part),
-                    r2 = *reinterpret_cast<const uint4*>(wbase + h_rec + 2 * h_part), r3 = *reinterpret_cast<const uint4*>(wbase + h_recf);
+                    r2 = *reinterpret_cast<const uint4*>(wbase + h_rec + 2 * h_part), r3 = *reinterpret_cast<const uint4*>(wbase + h_rec + 3 * h_part);
         LinkState st; d3 fN, mN;
         lat_eval_link_rec<UNI>(f, h_axis, meta_hi(n1.w),
                                make_double2(__hiloint2double(r0.y, r0.x), __hiloint2double(r0.w, r0.z)),
@@ -667,9 +677,8 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     if (elect_one()) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const unsigned char* tm = tmaps + (size_t)parity * TM_COUNT * 128;
-        mbar_expect(bar2, 512 + 512 + 1024 + 512);
-        tma_3d(sb + 10752, tm + TM_P0_ZF * 128, bar2, 4 * x0, y0, Z0 + VX_WB_Z);
-        tma_3d(sb + 11264, tm + TM_P1_ZF * 128, bar2, 4 * x0, y0, Z0 + VX_WB_Z);
+        mbar_expect(bar2, 1024 + 1024 + 512);
+        tma_4d(sb + 10752, tm + TM_P_ZF * 128, bar2, 4 * x0, y0, Z0 + VX_WB_Z, 0);
         tma_3d(sb + 11776, tm + TM_M0 * 128, bar2, 4 * x0, y0, Z0);
         tma_3d(sb + 12800, tm + TM_M1 * 128, bar2, 2 * x0, y0, Z0);
     }
@@ -692,8 +701,8 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
             else if (a == 0) load_pose(8192, 8448, lz * 4 + ly, p0, p1);
             else if (a == 1) load_pose(8704, 8960, lz * 4 + lx, p0, p1);
             else load_pose(10752, 11264, ly * 4 + lx, p0, p1);
-            const uint4* rr = reinterpret_cast<const uint4*>(wbase + 2048 + a * 3 * 512) + lane;
-            const uint4 r0 = rr[0], r1 = rr[32], r2 = rr[64], r3 = reinterpret_cast<const uint4*>(wbase + 6656 + a * 512)[lane];
+            const uint4* rr = reinterpret_cast<const uint4*>(wbase + 2048 + a * 4 * 512) + lane;
+            const uint4 r0 = rr[0], r1 = rr[32], r2 = rr[64], r3 = rr[96];
             LinkState st;
             lat_eval_link_rec<UNI>(f, a, bits,
                                    make_double2(__hiloint2double(r0.y, r0.x), __hiloint2double(r0.w, r0.z)),
@@ -703,8 +712,8 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                                    n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
             double2 wa, wb, wc; float4 ws; uint32_t lf;
             lat_encode(st, wa, wb, wc, ws, lf);
-            double2* nr = f.n_rec[0][0] + (size_t)(a * 3) * f.n_vox + v;
-            nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; (f.n_recf[0] + (size_t)a * f.n_vox)[v] = ws;
+            double2* nr = f.n_rec[0][0] + (size_t)(a * 4) * f.n_vox + v;
+            nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; *reinterpret_cast<float4*>(nr + 3 * (size_t)f.n_vox) = ws;
             new_bits = (new_bits & ~(3u << (VM_LFLAG_SHIFT + 2 * a))) | (lf << (VM_LFLAG_SHIFT + 2 * a));
             if (st.strain > 100) p->div_flag[parity] = 1;          // src/Voxelyze.cpp:265
             F = F + fN; M = M + mN;
@@ -765,4 +774,3 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
 
 } // namespace vxd
 
-#include "vx_lattice_variants.cuh"   // the ablation kernels (vx_set_path 2, 3, 4, 6)

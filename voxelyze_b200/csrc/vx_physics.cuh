@@ -22,6 +22,17 @@ __device__ __forceinline__ d3 operator-(d3 a) { return mk3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ d3 operator*(double f, d3 a) { return mk3(f * a.x, f * a.y, f * a.z); }
 __device__ __forceinline__ double norm2(d3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
 
+// a / b, bit for bit.  CUDA's double division leaves its inline path whenever the numerator is zero (a ~70-instruction
+// subroutine), and zero numerators are the rule wherever a lattice is still at rest (transverse offsets, strains and
+// rotation increments are exactly 0 there).  0 * b has the sign of 0 / b for every finite non-zero b.
+__device__ __forceinline__ double ddiv(double a, double b)
+{
+#ifndef VX_NO_DDIV            // ablation switch (tools/build_variant.sh)
+    if (a == 0.0 && b != 0.0 && fabs(b) <= 1.7976931348623157e308) return a * b;
+#endif
+    return a / b;
+}
+
 // quaternion product (include/Quat3D.h:83)
 __device__ __forceinline__ q4 qmul(const q4& a, const q4& b)
 {
@@ -86,7 +97,7 @@ __device__ __forceinline__ q4 q_from_rotvec(d3 v)
 {
     d3 h = 0.5 * v;
     double m2 = norm2(h), w, s;
-    if (m2 * m2 < 5.328e-15) { w = 1.0 - 0.5 * m2; s = 1.0 - m2 / 6.0; }
+    if (m2 * m2 < 5.328e-15) { w = 1.0 - 0.5 * m2; s = 1.0 - ddiv(m2, 6.0); }
     else q_from_rotvec_trig(m2, w, s);
     q4 r; r.w = w; r.x = h.x * s; r.y = h.y * s; r.z = h.z * s;
     return r;
@@ -228,7 +239,7 @@ __device__ __forceinline__ void link_forces(const int axis, d3 pN, q4 oN, d3 pP,
     ang2 = qmul(total, ang2);
     ang1 = qident();
 
-    float small_turn = (float)((fabs(pos2.z) + fabs(pos2.y)) / pos2.x);
+    float small_turn = (float)ddiv(fabs(pos2.z) + fabs(pos2.y), pos2.x);
     float extend = (float)(fabs(1 - pos2.x / rest_len));
     const float HYST = 1.2f, BEND = 0.05f, EXT = 0.50f;                     // src/VX_Link.cpp:21-23
     if (!st.small_angle && small_turn < BEND && extend < EXT) { st.small_angle = true; st.vel_valid = false; }
@@ -250,7 +261,7 @@ __device__ __forceinline__ void link_forces(const int axis, d3 pN, q4 oN, d3 pP,
     d3 d_a1 = 0.5 * (a1v - old_a1);
     d3 d_a2 = 0.5 * (a2v - old_a2);
 
-    st.stress = link_update_strain(st, m, ce, cs, (float)(pos2.x / rest_len), t_sum);
+    st.stress = link_update_strain(st, m, ce, cs, (float)ddiv(pos2.x, rest_len), t_sum);
     if (mat_failed(m, st.max_strain)) {
         fN = mN = fP = mP = mk3(0.0, 0.0, 0.0);
         return;

@@ -5,8 +5,9 @@
 // ---- peer-memory halo ---------------------------------------------------------------------------
 struct PeerDescWire {                       // what vx_peer_export writes into vx_peer_desc::bytes
     uint64_t magic; int64_t pid; int32_t device, side; uint64_t first, count;
-    cudaIpcMemHandle_t mem[4]; cudaIpcMemHandle_t flag;      // pose0[0], pose0[1], pose1[0], pose1[1]; flag array
-    uint64_t raw[4]; uint64_t raw_flag;                      // same-process peers use the addresses directly
+    cudaIpcMemHandle_t mem[2]; cudaIpcMemHandle_t flag;      // the pose allocation of generation 0 and 1 (pose0, then pose1 at +pose1_off); flag array
+    uint64_t raw[2]; uint64_t raw_flag;                      // same-process peers use the addresses directly
+    uint64_t pose1_off;                                      // in double4 elements
 };
 static_assert(sizeof(PeerDescWire) <= VX_PEER_DESC_BYTES, "vx_peer_desc too small");
 
@@ -41,8 +42,10 @@ int vx_peer_export(vx_sim* s, int ghost_iz, int from_above, vx_peer_desc* out)
     if (plane_range(s, ghost_iz, first, count) != VX_OK) return fail(s, VX_ERR_ARG, "vx_peer_export: empty layer");
     PeerDescWire w{}; w.magic = 0x56585045455231ULL; w.pid = (int64_t)getpid(); w.device = s->device; w.side = from_above ? 1 : 0;
     w.first = first; w.count = count;
-    double4* base[4] = {s->pose0[0].p, s->pose0[1].p, s->pose1[0].p, s->pose1[1].p};
-    for (int k = 0; k < 4; k++) { CK(cudaIpcGetMemHandle(&w.mem[k], base[k])); w.raw[k] = (uint64_t)(uintptr_t)base[k]; }
+    double4* base[2] = {s->pose0[0].p, s->pose0[1].p};
+    for (int k = 0; k < 2; k++) { CK(cudaIpcGetMemHandle(&w.mem[k], base[k])); w.raw[k] = (uint64_t)(uintptr_t)base[k]; }
+    w.pose1_off = (uint64_t)(s->pose1[0].p - s->pose0[0].p);
+    if ((uint64_t)(s->pose1[1].p - s->pose0[1].p) != w.pose1_off) return fail(s, VX_ERR_CUDA, "vx_peer_export: generations laid out differently");
     CK(cudaIpcGetMemHandle(&w.flag, s->peer_flags.p)); w.raw_flag = (uint64_t)(uintptr_t)s->peer_flags.p;
     memset(out->bytes, 0, VX_PEER_DESC_BYTES); memcpy(out->bytes, &w, sizeof(w));
     s->expect_side[w.side] = true;                                   // a neighbour will write here
@@ -57,24 +60,24 @@ int vx_peer_attach(vx_sim* s, int send_iz, const vx_peer_desc* peer_ghost)
     if (w.magic != 0x56585045455231ULL) return fail(s, VX_ERR_ARG, "vx_peer_attach: not a peer descriptor");
     vx_sim::PeerLink pl;
     if (plane_range(s, send_iz, pl.src_first, pl.count) != VX_OK || pl.count != w.count) return fail(s, VX_ERR_ARG, "vx_peer_attach: layer size mismatch");
-    void* base[5];
+    void* base[3];
     if (w.pid == (int64_t)getpid()) {                                 // same process (tests): plain addresses
-        for (int k = 0; k < 4; k++) base[k] = (void*)(uintptr_t)w.raw[k];
-        base[4] = (void*)(uintptr_t)w.raw_flag;
+        for (int k = 0; k < 2; k++) base[k] = (void*)(uintptr_t)w.raw[k];
+        base[2] = (void*)(uintptr_t)w.raw_flag;
         if (w.device != s->device) { int can = 0; cudaDeviceCanAccessPeer(&can, s->device, w.device); if (!can) return fail(s, VX_ERR_UNSUPPORTED, "no peer access"); cudaError_t e = cudaDeviceEnablePeerAccess(w.device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(s, e, "cudaDeviceEnablePeerAccess"); cudaGetLastError(); }
     } else {
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 2; k++) {
             cudaError_t e = cudaIpcOpenMemHandle(&base[k], w.mem[k], cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) { cudaGetLastError(); return fail(s, VX_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
             pl.opened[k] = base[k];
         }
-        cudaError_t e = cudaIpcOpenMemHandle(&base[4], w.flag, cudaIpcMemLazyEnablePeerAccess);
+        cudaError_t e = cudaIpcOpenMemHandle(&base[2], w.flag, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) { cudaGetLastError(); return fail(s, VX_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
-        pl.opened[4] = base[4];
+        pl.opened[2] = base[2];
     }
     pl.dst0[0] = (double4*)base[0] + w.first; pl.dst0[1] = (double4*)base[1] + w.first;
-    pl.dst1[0] = (double4*)base[2] + w.first; pl.dst1[1] = (double4*)base[3] + w.first;
-    pl.dst_flag = (int*)base[4] + w.side;
+    pl.dst1[0] = (double4*)base[0] + w.pose1_off + w.first; pl.dst1[1] = (double4*)base[1] + w.pose1_off + w.first;
+    pl.dst_flag = (int*)base[2] + w.side;
     s->peers.push_back(pl);
     return VX_OK;
 }

@@ -24,7 +24,7 @@ static std::vector<Chunk> state_chunks(vx_sim* s)
         for (int g = 0; g < 2; g++) {
             c.push_back({s->pose0[g].p, N * sizeof(double4)}); c.push_back({s->pose1[g].p, N * sizeof(double4)});
             c.push_back({s->mom0[g].p, N * sizeof(double4)}); c.push_back({s->mom1[g].p, N * sizeof(double2)});
-            c.push_back({s->rec[g].p, N * 9 * sizeof(double2)}); c.push_back({s->recf[g].p, N * 3 * sizeof(float4)});
+            c.push_back({s->rec[g].p, N * VX_REC_PARTS * sizeof(double2)});
         }
     } else {
         c.push_back({s->pose0[0].p, N * sizeof(double4)}); c.push_back({s->pose1[0].p, N * sizeof(double4)});
@@ -46,7 +46,7 @@ int vx_save_state(vx_sim* s, const char* path)
     FILE* fp = fopen(path, "wb");
     if (!fp) return fail(s, VX_ERR_ARG, std::string("cannot write ") + path);
     StateHeader h{};
-    memcpy(h.magic, "VXB2ST01", 8);
+    memcpy(h.magic, "VXB2ST02", 8);
     h.abi = VX_ABI_VERSION; h.lattice = s->lattice; h.N = s->N; h.L = s->L; h.nx = s->nx; h.ny = s->ny; h.nz = s->nz; h.n_members = s->n_members;
     h.gen = s->gen; h.have_prev = s->have_prev; h.collisions = s->collisions;
     h.last_prev_dt = s->last_prev_dt; h.prev_dt_host = s->prev_dt_host; h.time_host = s->time_host; h.ambient = s->ambient;
@@ -72,7 +72,7 @@ int vx_load_state(vx_sim* s, const char* path)
     FILE* fp = fopen(path, "rb");
     if (!fp) return fail(s, VX_ERR_ARG, std::string("cannot read ") + path);
     StateHeader h{};
-    bool ok = fread(&h, sizeof(h), 1, fp) == 1 && memcmp(h.magic, "VXB2ST01", 8) == 0 && h.abi == VX_ABI_VERSION;
+    bool ok = fread(&h, sizeof(h), 1, fp) == 1 && memcmp(h.magic, "VXB2ST02", 8) == 0 && h.abi == VX_ABI_VERSION;
     if (ok && (h.lattice != (int)s->lattice || h.N != s->N || h.L != s->L || h.nx != s->nx || h.ny != s->ny || h.nz != s->nz ||
                h.n_members != s->n_members || h.collisions != (int)s->collisions || h.topo_hash != topo_hash(s))) {
         fclose(fp);
@@ -161,7 +161,7 @@ int vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* s
         CK(of_dev.alloc(of.size()));
         CK(cudaMemcpyAsync(of_dev.p, of.data(), of.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
         const int g = s->gen;
-        k_lattice_scatter_link_state<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->pose1[g].p, s->rec[g].p, s->recf[g].p, of_dev.p, s->N,
+        k_lattice_scatter_link_state<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->pose1[g].p, s->rec[g].p, of_dev.p, s->N,
                                                                               (const LinkStateRec*)s->staging.p, first, count);
         CK(cudaStreamSynchronize(s->stream));
         of_dev.release();
