@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define VX_ABI_VERSION 1
+#define VX_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 #define VX_OK              0
@@ -235,6 +235,10 @@ int  vx_set_temperature(vx_sim* s, int n, const float* t);
  * completed before the diverging one; like the reference, on the diverging step the
  * links are updated but the voxels are not advanced, and no later step is run.       */
 int  vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step);
+/* optional: builds everything vx_step would otherwise build lazily on its first long call (the captured
+ * CUDA graphs of 16 steps, tensor maps) without touching the state, so that a caller who times
+ * steps does not time the set-up.  No reference counterpart.                          */
+int  vx_prepare(vx_sim* s);
 /* replaces CVoxelyze::recommendedTimeStep()           src/Voxelyze.cpp:286-311      */
 int  vx_recommended_dt(vx_sim* s, float* dt);
 /* replaces CVoxelyze::resetTime()                     src/Voxelyze.cpp:313-321      */

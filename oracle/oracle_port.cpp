@@ -1125,5 +1125,6 @@ int vx_set_path(vx_sim*, int) { return VX_OK; }
 int vx_active_path(const vx_sim*) { return 0; }
 const char* vx_kernel_name(const vx_sim*) { return "cpu (oracle port)"; }
 int vx_step_profile(vx_sim*, float, int, float*, int*) { return VX_ERR_UNSUPPORTED; }
+int vx_prepare(vx_sim*) { return VX_OK; }
 
 } // extern "C"

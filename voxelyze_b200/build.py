@@ -51,7 +51,7 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
         return PRODUCT_SO
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, *NVCC_FLAGS, "-ccbin", _host_cxx(), "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-o", PRODUCT_SO, os.path.join(CSRC, "vx_capi.cu")]
+           "-o", PRODUCT_SO, os.path.join(CSRC, "vx_capi.cu"), "-ldl"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.run(cmd, check=True)

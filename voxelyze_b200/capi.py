@@ -146,6 +146,7 @@ class VxLib:
             "vx_set_temperature_members": (i32, [vp, i32, vp]),
             "vx_set_temperature": (i32, [vp, i32, vp]),
             "vx_step": (i32, [vp, f32, i32, P(i32)]),
+            "vx_prepare": (i32, [vp]),
             "vx_recommended_dt": (i32, [vp, P(f32)]),
             "vx_reset": (i32, [vp]),
             "vx_time": (f32, [vp]),
@@ -318,6 +319,10 @@ class Sim:
         div = C.c_int(-1)
         rc = self._chk(self.L.lib.vx_step(self.h, dt, n, C.byref(div)), ok=(VX_OK, VX_DIVERGED))
         return div.value if rc == VX_DIVERGED else None
+
+    def prepare(self):
+        """Builds the captured step graphs now instead of inside the first long step call."""
+        self._chk(self.L.lib.vx_prepare(self.h))
 
     def recommended_dt(self) -> float:
         dt = C.c_float()

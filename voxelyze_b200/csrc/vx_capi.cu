@@ -11,6 +11,7 @@
 // vx_create fails with VX_ERR_NO_DEVICE.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -54,10 +55,13 @@ constexpr int TPB = 128;
 
 inline int blocks_for(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
 
+// NVTX range around the entry points a timeline should show (nsys / ncu --nvtx); costs nothing without a tool attached
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
+
 } // namespace
 
 struct vx_sim {
-    int device = 0;
+    int device = 0, sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     double vox_size = 0.001;
     std::string err;
@@ -896,7 +900,7 @@ int vx_create(double voxel_size, int device, vx_sim** out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return VX_ERR_NO_DEVICE;   // sm_100a code only
     vx_sim* s = new vx_sim;
-    s->device = device; s->vox_size = voxel_size;
+    s->device = device; s->vox_size = voxel_size; s->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return VX_ERR_CUDA; }
     s->stream = s->own_stream;
     if (s->params.alloc(1) != cudaSuccess || s->freq2.alloc(1) != cudaSuccess ||
@@ -989,6 +993,7 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
 int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags)
 {
     if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_voxels inside vx_step_begin .. vx_step_end");
     bool poisson = false;
     for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
     if (n == 0 || poisson || s->path == 1)
@@ -1340,7 +1345,9 @@ int vx_set_temperature(vx_sim* s, int n, const float* t)
 int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
 {
     if (!s || n_steps < 0) return VX_ERR_ARG;
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_step inside vx_step_begin .. vx_step_end");
     if (n_steps == 0 || dt == 0 || s->N == 0) return VX_OK;       // dt == 0: src/Voxelyze.cpp:253
+    NvtxRange nvtx("vx_step");
     CK(cudaSetDevice(s->device));
     if (s->lattice) return lattice_step(s, dt, n_steps, diverged_step);
     Frame f = s->frame();
@@ -1383,11 +1390,18 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
 int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
 {
     if (!s || n_steps < 0 || !ms) return VX_ERR_ARG;
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_step_profile inside vx_step_begin .. vx_step_end");
     ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
     if (launches) launches[0] = launches[1] = launches[2] = 0;
     if (n_steps == 0 || dt == 0 || s->N == 0) return VX_OK;
+    NvtxRange nvtx("vx_step_profile");
     CK(cudaSetDevice(s->device));
-    std::vector<cudaEvent_t> ev((size_t)n_steps * 4);
+    struct Events {                                                // destroyed on every return path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (cudaEvent_t e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    evs.v.assign((size_t)n_steps * 4, nullptr);
+    std::vector<cudaEvent_t>& ev = evs.v;
     for (auto& e : ev) CK(cudaEventCreate(&e));
     int rc = VX_OK;
     if (s->lattice) {
@@ -1439,8 +1453,21 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
         s->prev_dt_host = s->params_host->prev_dt;
         rc = s->params_host->div_latched ? VX_DIVERGED : VX_OK;
     }
-    for (auto& e : ev) cudaEventDestroy(e);
     return rc;
+}
+
+int vx_prepare(vx_sim* s)
+{
+    if (!s) return VX_ERR_ARG;
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_prepare inside vx_step_begin .. vx_step_end");
+    if (s->N == 0 || s->collisions) return VX_OK;                 // colliding models are not graph-captured
+    CK(cudaSetDevice(s->device));
+    if (s->lattice) {
+        int rc = ensure_lattice_graph(s, 0);
+        if (rc == VX_OK) rc = ensure_lattice_graph(s, 1);
+        return rc;
+    }
+    return s->any_poisson ? VX_OK : ensure_graph(s);
 }
 
 int vx_recommended_dt(vx_sim* s, float* dt)
@@ -1461,6 +1488,7 @@ int vx_recommended_dt(vx_sim* s, float* dt)
 int vx_reset(vx_sim* s)
 {
     if (!s) return VX_ERR_ARG;
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_reset inside vx_step_begin .. vx_step_end");
     return upload_initial_state(s, 0.0f);          // CVX_Voxel::reset zeroes the temperature, src/VX_Voxel.cpp:53
 }
 float vx_time(const vx_sim* s) { return s ? s->time_host : 0.f; }
@@ -1535,6 +1563,7 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
     int what, comps, esize; bool is_link;
     if (!s || !src || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
     if (is_link || what == G_PSTRAIN) return fail(s, VX_ERR_UNSUPPORTED, "only voxel state can be uploaded");
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_upload inside vx_step_begin .. vx_step_end");
     if (first + count > s->N_user) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
     CK(cudaSetDevice(s->device));

@@ -81,8 +81,9 @@ template <bool UNI>
 __device__ __forceinline__ void lat_eval_link_rec(const LatFrame& f, int axis, uint32_t owner_bits,
                                                   double2 ra, double2 rb, double2 rc, float4 rs,
                                                   double4 n0, double4 n1, double4 p0, double4 p1, float prev_dt,
-                                                  LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP)
+                                                  LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP, float damp_uni = -1.0f)
 {
+    // damp_uni: single-material models may pass 2*sqrtMass*zeta/previousDt computed once per kernel (same float division)
     const uint32_t hn = meta_hi(n1.w), hp = meta_hi(p1.w);
     const DevVoxMat& vmn = UNI ? f.vm0 : f.vmat[hn & VM_MAT_MASK];
     const DevVoxMat& vmp = UNI ? f.vm0 : f.vmat[hp & VM_MAT_MASK];
@@ -91,7 +92,9 @@ __device__ __forceinline__ void lat_eval_link_rec(const LatFrame& f, int axis, u
     // CVX_Link::updateRestLength (src/VX_Link.cpp:137-140)
     double rest = 0.5 * (vmn.size[axis] * (1 + meta_temp(n1.w) * vmn.cte) + vmp.size[axis] * (1 + meta_temp(p1.w) * vmp.cte));
     float t_area = 0.5f * (vmn.nom_f * vmn.nom_f + vmp.nom_f * vmp.nom_f);
-    float damp_n = vmn.two_sqrtm_zeta / prev_dt, damp_p = vmp.two_sqrtm_zeta / prev_dt;
+    float damp_n, damp_p;
+    if (UNI && damp_uni >= 0.0f) damp_n = damp_p = damp_uni;
+    else { damp_n = vmn.two_sqrtm_zeta / prev_dt; damp_p = vmp.two_sqrtm_zeta / prev_dt; }
     q4 on, op;
     on.w = n0.w; on.x = n1.x; on.y = n1.y; on.z = n1.z;
     op.w = p0.w; op.x = p1.x; op.y = p1.y; op.z = p1.z;
@@ -617,9 +620,9 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         tma_4d(sb + 8704, map(TM_P_YF), bar1, 4 * x0, y0 + VX_WB_Y, Z0, 0);
     }
     __syncwarp();
-
     const int frozen = div_prev | div_latched;
     const float prev_dt = first_of_call ? prev_dt_call : dt;
+    const float damp_u = UNI ? f.vm0.two_sqrtm_zeta / prev_dt : -1.0f;
     if (book && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
         if (frozen) p->div_latched = 1;
         else if (p->pending) { p->steps_done += 1; p->time += dt; }
@@ -669,7 +672,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                                make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
                                make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
                                make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
-                               n0, n1, p0, p1, prev_dt, st, fN, mN, hF, hM);
+                               n0, n1, p0, p1, prev_dt, st, fN, mN, hF, hM, damp_u);
     }
     __syncwarp();                          // every lane has read its round-H inputs: their space is re-used now
     double (*hslot)[32] = reinterpret_cast<double (*)[32]>(wbase + 9216);                 // [comp][entering link]
@@ -709,7 +712,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                                    make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
                                    make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
                                    make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
-                                   n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
+                                   n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP, damp_u);
             double2 wa, wb, wc; float4 ws; uint32_t lf;
             lat_encode(st, wa, wb, wc, ws, lf);
             double2* nr = f.n_rec[0][0] + (size_t)(a * 4) * f.n_vox + v;

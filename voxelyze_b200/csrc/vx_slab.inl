@@ -139,17 +139,19 @@ int vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     if (!s || n_steps < 0) return VX_ERR_ARG;
     if (n_steps == 0) return VX_OK;
     int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
+    NvtxRange nvtx("vx_slab_step");
     rc = vx_step_begin(s, dt); if (rc != VX_OK) return rc;
+    auto abandon = [&](int code) { s->call_active = false; s->call_half = false; s->push_in_kernel = false; return code; };   // leave no call open behind an error
     for (int k = 0; k < n_steps; k++) {
         peer_wait(s, s->stream);                            // the boundary part reads the ghosts of the previous exchange
         s->push_in_kernel = s->peers.size() <= 2;          // the boundary kernels store into the neighbours' ghost layers themselves
         const bool fused = s->push_in_kernel;
         rc = vx_step_enqueue(s, VX_PART_Z_BOUNDARY);
         s->push_in_kernel = false;
-        if (rc != VX_OK) return rc;
-        CK(cudaEventRecord(s->ev_boundary, s->stream));
-        rc = vx_step_enqueue(s, VX_PART_Z_INTERIOR); if (rc != VX_OK) return rc;
-        CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
+        if (rc != VX_OK) return abandon(rc);
+        if (cudaEventRecord(s->ev_boundary, s->stream) != cudaSuccess) return abandon(cuda_fail(s, cudaGetLastError(), "cudaEventRecord"));
+        rc = vx_step_enqueue(s, VX_PART_Z_INTERIOR); if (rc != VX_OK) return abandon(rc);
+        if (cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0) != cudaSuccess) return abandon(cuda_fail(s, cudaGetLastError(), "cudaStreamWaitEvent"));
         peer_push(s, s->newest_gen(), fused);
     }
     CK(cudaEventRecord(s->ev_comm, s->comm_stream));

@@ -74,6 +74,51 @@ class SingleRunner:
     def path_name(self) -> str:
         return _path_name(self.sim)
 
+    def h2d_bytes_per_step(self) -> int:
+        return 4                                    # dt
+
+    def close(self):
+        self.sim.close()
+
+
+class EnsembleRunner(SingleRunner):
+    """C4: this rank's share of a population of independent robots in ONE handle (members never interact), the
+    ambient temperature program of SURVEY.md section 8d set from the host before EVERY step like a caller of
+    CVoxelyze::setAmbientTemperature would; `world` ranks hold equal shares and never communicate."""
+
+    def __init__(self, sim: Sim, world: int = 1):
+        super().__init__(sim)
+        self.world = world
+
+    def _advance(self, dt: float):
+        self.sim.set_temperature_all(scenarios.robot_temperature(self.sim.time()))
+
+    def step(self, dt: float, n: int):
+        div = None
+        for _ in range(n):
+            self._advance(dt)
+            d = self.sim.step(dt, 1)
+            div = d if d is not None else div
+        return div
+
+    def step_profile(self, dt: float, n: int):
+        tot, launches = None, None
+        for _ in range(n):
+            self._advance(dt)
+            ms, ln = self.sim.step_profile(dt, 1)
+            tot = ms if tot is None else {k: tot[k] + ms[k] for k in ms}
+            launches = ln if launches is None else [a + b for a, b in zip(launches, ln)]
+        return tot, launches
+
+    def global_counts(self):
+        return self.sim.n_voxels * self.world, self.sim.n_links * self.world
+
+    def h2d_bytes_per_step(self) -> int:
+        return 8                                    # dt + ambient temperature
+
+    def path_name(self) -> str:
+        return f"{_path_name(self.sim)}, {self.sim.n_voxels // 1000} robots on this GPU"
+
 
 class SlabRunner:
     """Cantilever pattern of C5 (x=0 face fixed, -z load on the x=nx-1 face) split along z."""
@@ -305,6 +350,14 @@ class SlabRunner:
 
     def path_name(self) -> str:
         return f"{_path_name(self.sim)}, z-slab {self.rank}/{self.world} layers [{self.z0},{self.z1})"
+
+    def h2d_bytes_per_step(self) -> int:
+        return 4
+
+    def close(self):
+        if self.peer:
+            self.sim.peer_detach()
+        self.sim.close()
 
     def halo_name(self) -> str:
         if self.peer:
