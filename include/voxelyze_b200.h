@@ -257,6 +257,10 @@ int  vx_upload(vx_sim* s, int field, int first, int count, const void* src);
  * (src/Voxelyze.cpp:730-747).  pairs may be NULL to query the count.                 */
 int  vx_collision_pairs(vx_sim* s, int32_t* pairs, int cap, int* n_pairs);
 
+/* number of watched pairs and of watch-list rebuilds (CVoxelyze::regenerateCollisions, src/Voxelyze.cpp:725-750) since
+ * the voxels were set, as of the end of the last step call; -1 rebuilds where an implementation does not count them   */
+int  vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds);
+
 /* replaces CVoxelyze::stateInfo (src/Voxelyze.cpp:752-800); info/type use the
  * reference's enum values (include/Voxelyze.h:48-67).                                */
 int  vx_state_info(vx_sim* s, int info, int type, float* out);

@@ -1126,5 +1126,10 @@ int vx_active_path(const vx_sim*) { return 0; }
 const char* vx_kernel_name(const vx_sim*) { return "cpu (oracle port)"; }
 int vx_step_profile(vx_sim*, float, int, float*, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_prepare(vx_sim*) { return VX_OK; }
+int vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds)
+{
+    if (n_rebuilds) *n_rebuilds = -1;                  // not counted here
+    return vx_collision_pairs(s, nullptr, 0, n_pairs);
+}
 
 } // extern "C"

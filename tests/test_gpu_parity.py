@@ -525,3 +525,29 @@ def test_collisions_on_the_fused_path_match_the_general_path_bitwise(product):
         for f in a:
             assert parity.bit_equal(a[f], c[f]), (path, f)
         assert np.array_equal(runs[path].collision_pairs(), runs[1].collision_pairs())
+
+
+def test_poissons_ratio_switched_on_mid_run_keeps_the_state(product, oracle):
+    """The reference lets a caller change Poisson's ratio at any time (src/VX_Link.cpp:160-166 'catches when we disable
+    poissons mid-simulation').  A model on the fused layout moves to the general layout when nu becomes non-zero; voxel and
+    link state, time and previousDt go on, and later calls (gravity, more steps) keep working."""
+    import copy
+
+    def run(lib):
+        sc = scenarios.cantilever(8, 3, 3, tip_load=20.0)
+        s = scenarios.build(lib, sc); dt = s.recommended_dt()
+        s.step(dt, 150)
+        m = copy.copy(sc.materials[0]); m.nu = 0.3
+        s.set_materials([m])
+        dt2 = s.recommended_dt()
+        assert s.step(dt2 * 0.5, 150) is None
+        s.set_gravity(0.5)                                  # every later table upload must still work
+        assert s.step(dt2 * 0.5, 50) is None
+        return s, sc, dt, dt2
+
+    (g, sc, dtg, dtg2), (o, _, dto, dto2) = run(product), run(oracle)
+    assert g.active_path() == 1 and dtg == dto
+    assert abs(dtg2 - dto2) <= 1e-6 * dto2
+    err = parity.rel_errors(parity.snapshot(g), parity.snapshot(o), sc)
+    assert err["pos"] <= 1e-6 and err["orient"] <= 1e-6, err
+    assert abs(g.time() - o.time()) <= 1e-6 * o.time()

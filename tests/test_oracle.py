@@ -159,3 +159,22 @@ def test_edge_cases(oracle):
     vn, vp, ax = s.links()
     assert list(vn) == [0, 2] and list(vp) == [1, 0] and list(ax) == [0, 0]
     assert s.step(0.0, 5) is None and s.time() == 0.0                       # dt == 0 is a no-op
+
+
+def test_oracle_follows_the_reference_when_poissons_ratio_is_switched_on_mid_run(oracle, reference):
+    """Material edits between steps (SURVEY 8b hazard 2): nu 0 -> 0.3 after 150 steps, then 150 more; bit for bit."""
+    import copy
+
+    def run(lib):
+        sc = scenarios.cantilever(8, 3, 3, tip_load=20.0)
+        s = scenarios.build(lib, sc); dt = s.recommended_dt()
+        s.step(dt, 150)
+        m = copy.copy(sc.materials[0]); m.nu = 0.3
+        s.set_materials([m])
+        dt2 = s.recommended_dt()
+        s.step(dt2 * 0.5, 150)
+        return parity.snapshot(s), dt2
+    (a, dta), (b, dtb) = run(oracle), run(reference)
+    assert dta == dtb
+    for f in a:
+        assert parity.bit_equal(a[f], b[f]), f

@@ -153,6 +153,7 @@ class VxLib:
             "vx_download": (i32, [vp, i32, i32, i32, vp]),
             "vx_upload": (i32, [vp, i32, i32, i32, vp]),
             "vx_collision_pairs": (i32, [vp, vp, i32, P(i32)]),
+            "vx_collision_stats": (i32, [vp, P(i32), P(i32)]),
             "vx_state_info": (i32, [vp, i32, i32, P(f32)]),
             "vx_set_stream": (i32, [vp, u64]),
             "vx_pose_plane": (i32, [vp, i32, P(u64), P(u64), P(i32), P(i32)]),
@@ -358,6 +359,12 @@ class Sim:
         if n.value:
             self._chk(self.L.lib.vx_collision_pairs(self.h, _ptr(out), n.value, C.byref(n)))
         return out
+
+    def collision_stats(self):
+        """(watched pairs, watch-list rebuilds so far; -1 where not counted)."""
+        a, b = C.c_int(0), C.c_int(0)
+        self._chk(self.L.lib.vx_collision_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def state_info(self, info: int, typ: int) -> float:
         v = C.c_float()

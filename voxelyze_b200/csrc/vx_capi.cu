@@ -73,6 +73,9 @@ struct vx_sim {
     bool any_poisson = false;
 
     int N = 0, L = 0, n_members = 1;
+    // lattice mode: ensemble members are tiled pack[0] x pack[1] x pack[2] into ONE device lattice (their link masks keep
+    // them apart), lat_members = 1; unpacked ensembles are stacked along z as lat_members separate boxes
+    int pack[3] = {1, 1, 1}, lat_members = 1;
     int N_user = 0;                     // voxels the caller created; [N_user, N) are inert fill cells of a box with holes (lattice mode)
     std::vector<int32_t> ijk; std::vector<uint16_t> vmat_id; std::vector<int32_t> member; std::vector<uint32_t> vflags;
     std::vector<int32_t> lk_vn, lk_vp; std::vector<uint8_t> lk_axis;   // caller (creation) order, caller voxel indices
@@ -85,6 +88,10 @@ struct vx_sim {
     std::vector<int32_t> ext_vox; std::vector<DevExt> ext_rows;        // externals, caller voxel indices
 
     float grav = 0.f, ambient = 0.f, envelope = 0.625f;
+    // lattice mode: vx_set_temperature_all is applied by the first fused kernel of the next vx_step (LatFrame::amb) instead
+    // of by a pass of its own; flush_ambient() materialises it for every other reader.  last_amb: the last executed
+    // step was such a step (its inputs, generation gen^1, still hold the old temperatures)
+    bool amb_pending = false, last_amb = false; float amb_value = 0.f, last_amb_value = 0.f;
     bool floor_on = false, collisions = false;
     float time_host = 0.f;
     int path = 0;                       // vx_set_path: 0 auto, 1 general, 5 / 7 fused lattice with cp.async / TMA staging
@@ -111,7 +118,7 @@ struct vx_sim {
         void* opened[3] = {nullptr, nullptr, nullptr};     // cudaIpcOpenMemHandle results (other-process peers)
     };
     std::vector<PeerLink> peers;
-    bool wb_opted_in = false;
+    bool wb_opted_in = false, capturing = false;
     DevBuf<unsigned char> tmaps;        // CUtensorMap descriptors of the lattice arrays (k_lattice_tma), rebuilt with the arrays
     bool push_in_kernel = false;        // set around the boundary launches of vx_slab_step
     DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
@@ -147,10 +154,13 @@ struct vx_sim {
     int n_surf = 0, n_pairs = 0, col_cap = 0, hash_size = 0;
     bool col_tables = false, col_stale_host = true;
     DevBuf<int> c_surf_vox, c_surf_orig, c_surf_member, c_slot; DevBuf<short4> c_surf_ijk; DevBuf<uint32_t> c_nearby;
-    DevBuf<float4> c_last_watch; DevBuf<int> c_head, c_next; DevBuf<int4> c_cell;
+    DevBuf<float4> c_last_watch; DevBuf<int> c_cell_count, c_cell_start, c_sorted; DevBuf<int4> c_cell;
     DevBuf<int2> c_pairs; DevBuf<float2> c_pair_kc; DevBuf<float4> c_pair_force;
     DevBuf<int> c_counters, c_deg, c_ref_start, c_ref_fill, c_refs;
-    int* counters_host = nullptr;                                  // pinned, 4 ints
+    int* counters_host = nullptr;                                  // pinned, CC_COUNT ints: mirror of c_counters after every step call
+    int col_rebuilds = 0;                                          // watch-list rebuilds since vx_set_voxels
+    cudaStream_t aux_stream = nullptr;                             // capture stream of conditional-node bodies
+    int cond_nodes = 1;                                            // 1: rebuild chain inside a conditional IF node of the step graphs; 0: predicated kernels only
     // stateInfo reductions
     DevBuf<float> si_minmax; DevBuf<double> si_sum; DevBuf<double4> si_nominal; DevBuf<float> si_consts; DevBuf<unsigned char> si_buf;
     bool si_nominal_ok = false, si_consts_ok = false, si_pressure_ok = false;
@@ -159,6 +169,7 @@ struct vx_sim {
     bool uni = false; DevVoxMat vm0{}; DevLinkMat lm0{};          // single-material model: rows passed by value
     cudaGraphExec_t graph = nullptr; int graph_kernels = 0;      // general mode
     cudaGraphExec_t lgraph[2] = {nullptr, nullptr};              // lattice mode, keyed by starting generation
+    int lgraph_kernels = GRAPH_STEPS;                            // launches one lattice graph stands for
     int64_t launches = 0;
 
     Frame frame() const
@@ -180,7 +191,8 @@ struct vx_sim {
         ColFrame c{};
         c.n_surf = n_surf; c.surf_vox = c_surf_vox.p; c.surf_orig = c_surf_orig.p; c.surf_member = c_surf_member.p;
         c.surf_ijk = c_surf_ijk.p; c.nearby = c_nearby.p; c.last_watch = c_last_watch.p;
-        c.head = c_head.p; c.next = c_next.p; c.cell = c_cell.p; c.hash_mask = hash_size - 1;
+        c.cell_count = c_cell_count.p; c.cell_start = c_cell_start.p; c.sorted = c_sorted.p; c.cell = c_cell.p; c.hash_mask = hash_size - 1;
+        c.params = params.p; c.parity = lattice ? (gen_view >= 0 ? gen_view : gen) : -1;
         c.pairs = c_pairs.p; c.pair_kc = c_pair_kc.p; c.pair_force = c_pair_force.p; c.cap = col_cap;
         c.counters = c_counters.p; c.deg = c_deg.p; c.ref_start = c_ref_start.p; c.ref_fill = c_ref_fill.p; c.refs = c_refs.p;
         // watch radius and re-watch distance of CVoxelyze::updateCollisions (src/Voxelyze.cpp:672-674)
@@ -211,6 +223,7 @@ struct vx_sim {
         f.vm0 = vm0; f.lm0 = lm0;
         f.col_slot = (collisions && col_tables) ? c_slot.p : nullptr;
         f.col_start = c_ref_start.p; f.col_ref = c_refs.p; f.col_force = c_pair_force.p;
+        f.amb_set = 0; f.amb = 0.f;
         f.push_z[0] = f.push_z[1] = -1;
         if (push_in_kernel) {
             for (size_t k = 0; k < peers.size() && k < 2; k++) {
@@ -296,7 +309,7 @@ static int upload_tables(vx_sim* s)
         if (m.nu != 0.0f) s->any_poisson = true;
         pair[(size_t)e.a * nm + e.b] = pair[(size_t)e.b * nm + e.a] = (uint16_t)i;
     }
-    if (s->lattice && s->any_poisson) return fail(s, VX_ERR_UNSUPPORTED, "Poisson's ratio on a lattice-mode handle: set materials before the voxels");
+    if (s->lattice && s->any_poisson) return fail(s, VX_ERR_UNSUPPORTED, "internal: Poisson material on the fused layout (vx_set_materials re-lays the model out first)");
     CK(s->vmat_dev.alloc(std::max<size_t>(vm.size(), 1)));
     CK(s->lmat_dev.alloc(std::max<size_t>(lm.size(), 1)));
     CK(s->curve_e.alloc(std::max<size_t>(ce.size(), 2)));
@@ -335,6 +348,7 @@ static int upload_initial_state(vx_sim* s, float temp)
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
     s->gen = 0; s->have_prev = false; s->prev_dt_host = 0.f; s->col_stale_host = true;
+    s->amb_pending = false; s->last_amb = false;
     if (N) {
         std::vector<double4> p0(N), p1(N);
         std::vector<char> has_ext(N, 0);
@@ -379,6 +393,25 @@ static int upload_initial_state(vx_sim* s, float temp)
     s->time_host = 0.f;
     s->drop_graph();
     return VX_OK;
+}
+
+// a pending vx_set_temperature_all written into the voxel records (for every reader that is not the fused step)
+static int flush_ambient(vx_sim* s)
+{
+    if (!s->amb_pending) return VX_OK;
+    s->amb_pending = false;
+    if (s->N == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    k_fill_temp<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->frame(), s->amb_value, nullptr, nullptr); s->launches++;
+    CK(cudaGetLastError());
+    return VX_OK;
+}
+// the inputs of the last executed step, as that step saw them (k_lattice_gather_links recomputes its link forces)
+static LatFrame prev_frame(const vx_sim* s)
+{
+    LatFrame f = s->lat_frame(s->gen ^ 1);
+    if (s->last_amb) { f.amb_set = 1; f.amb = s->last_amb_value; }
+    return f;
 }
 
 static int upload_externals(vx_sim* s)
@@ -487,13 +520,15 @@ static int build_collision_tables(vx_sim* s)
             mask[bit >> 5] |= 1u << (bit & 31);
         }
     }
-    s->hash_size = 1024; while (s->hash_size < 2 * S) s->hash_size <<= 1;
+    s->hash_size = 1024; while (s->hash_size < S) s->hash_size <<= 1;
     size_t s1 = std::max(S, 1);
     CK(s->c_surf_vox.alloc(s1)); CK(s->c_surf_orig.alloc(s1)); CK(s->c_surf_member.alloc(s1)); CK(s->c_surf_ijk.alloc(s1));
     CK(s->c_nearby.alloc(s1 * VX_NEARBY_WORDS)); CK(s->c_slot.alloc(std::max(N, 1)));
-    CK(s->c_last_watch.alloc(s1)); CK(s->c_head.alloc(s->hash_size)); CK(s->c_next.alloc(s1)); CK(s->c_cell.alloc(s1));
-    CK(s->c_counters.alloc(4)); CK(s->c_deg.alloc(s1)); CK(s->c_ref_start.alloc(s1 + 1)); CK(s->c_ref_fill.alloc(s1));
-    if (!s->counters_host) CK(cudaMallocHost((void**)&s->counters_host, 4 * sizeof(int)));
+    CK(s->c_last_watch.alloc(s1)); CK(s->c_cell_count.alloc(s->hash_size)); CK(s->c_cell_start.alloc((size_t)s->hash_size + 1)); CK(s->c_sorted.alloc(s1)); CK(s->c_cell.alloc(s1));
+    CK(s->c_counters.alloc(CC_COUNT)); CK(s->c_deg.alloc(s1)); CK(s->c_ref_start.alloc(s1 + 1)); CK(s->c_ref_fill.alloc(s1));
+    if (!s->counters_host) CK(cudaMallocHost((void**)&s->counters_host, CC_COUNT * sizeof(int)));
+    if (!s->aux_stream) CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+    memset(s->counters_host, 0, CC_COUNT * sizeof(int));
     CK(cudaStreamSynchronize(s->stream));
     if (S) {
         CK(cudaMemcpy(s->c_surf_vox.p, surf_vox.data(), (size_t)S * sizeof(int), cudaMemcpyHostToDevice));
@@ -505,74 +540,107 @@ static int build_collision_tables(vx_sim* s)
     if (N) CK(cudaMemcpy(s->c_slot.p, slot.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemset(s->c_last_watch.p, 0, s1 * sizeof(float4)));       // new Vec3D<float>() in CVX_Voxel::enableCollisions
     CK(cudaMemset(s->c_ref_start.p, 0, (s1 + 1) * sizeof(int)));
-    if (s->col_cap == 0) {
-        s->col_cap = std::max(1024, 4 * S);
-        CK(s->c_pairs.alloc(s->col_cap)); CK(s->c_pair_kc.alloc(s->col_cap)); CK(s->c_pair_force.alloc(s->col_cap)); CK(s->c_refs.alloc((size_t)2 * s->col_cap));
-    }
-    s->n_pairs = 0; s->col_tables = true;
+    // the pair list cannot grow while steps are queued: generous to begin with, doubled between calls when half full
+    s->col_cap = std::max(s->col_cap, std::max(4096, 16 * S));
+    CK(s->c_pairs.alloc(s->col_cap)); CK(s->c_pair_kc.alloc(s->col_cap)); CK(s->c_pair_force.alloc(s->col_cap)); CK(s->c_refs.alloc((size_t)2 * s->col_cap));
+    const int init[CC_COUNT] = {1, 0, 0, 0};                         // stale: the first step builds the lists
+    CK(cudaMemcpy(s->c_counters.p, init, sizeof(init), cudaMemcpyHostToDevice));
+    s->n_pairs = 0; s->col_rebuilds = 0; s->col_tables = true; s->col_stale_host = false;
+    s->drop_graph();
     return VX_OK;
 }
 
-// CVoxelyze::regenerateCollisions (src/Voxelyze.cpp:725-750) on the device
-static int rebuild_collisions(vx_sim* s)
+// CVoxelyze::regenerateCollisions (src/Voxelyze.cpp:725-750): the rebuild chain, every kernel predicated on the stale flag
+static void launch_collision_rebuild(vx_sim* s, const Frame& f, const ColFrame& c, cudaStream_t st)
 {
     const int S = s->n_surf;
-    for (;;) {
-        ColFrame c = s->col_frame();
-        CK(cudaMemsetAsync(s->c_head.p, 0xFF, (size_t)s->hash_size * sizeof(int), s->stream));
-        CK(cudaMemsetAsync(s->c_counters.p, 0, 4 * sizeof(int), s->stream));
-        CK(cudaMemsetAsync(s->c_deg.p, 0, (size_t)std::max(S, 1) * sizeof(int), s->stream));
-        CK(cudaMemsetAsync(s->c_ref_fill.p, 0, (size_t)std::max(S, 1) * sizeof(int), s->stream));
-        if (S) {
-            k_col_insert<<<blocks_for(S), TPB, 0, s->stream>>>(s->frame(), c);
-            k_col_pairs<<<blocks_for(S), TPB, 0, s->stream>>>(s->frame(), c);
-            s->launches += 2;
+    const int gs = std::min(blocks_for(S), 148 * 16), gh = std::min(blocks_for(std::max(S, s->hash_size)), 148 * 16);
+    k_col_clear<<<gh, TPB, 0, st>>>(c);
+    k_col_keys<<<gs, TPB, 0, st>>>(f, c);
+    k_col_scan<<<1, 1024, 0, st>>>(c, c.cell_count, c.cell_start, s->hash_size);
+    k_col_scatter<<<gs, TPB, 0, st>>>(c);
+    k_col_pairs<<<gs, TPB, 0, st>>>(f, c);
+    k_col_scan<<<1, 1024, 0, st>>>(c, c.deg, s->c_ref_start.p, S);
+    k_col_fill<<<std::min(blocks_for(s->col_cap), 148 * 16), TPB, 0, st>>>(c);
+    k_col_sort<<<gs, TPB, 0, st>>>(c);
+    k_col_done<<<1, 1, 0, st>>>(c);
+    s->launches += 9;
+}
+
+// CVoxelyze::updateCollisions (src/Voxelyze.cpp:670-710) queued on the handle's stream: stale test, rebuild if stale, contact
+// forces.  Nothing here waits for the device.  capturing: the stream is being captured into a step graph; the rebuild chain
+// then becomes the body of a conditional IF node (it is not even launched on the steps that keep their lists).
+static int enqueue_collision_step(vx_sim* s, bool capturing)
+{
+    if (s->n_surf == 0) return VX_OK;
+    const Frame f = s->frame();
+    const ColFrame c = s->col_frame();
+    cudaStream_t st = s->stream;
+    const int gs = std::min(blocks_for(s->n_surf), 148 * 16);
+    k_col_stale<<<gs, TPB, 0, st>>>(f, c); s->launches++;
+    bool chained = false;
+    if (capturing && s->cond_nodes) {
+        // IF node: condition set by k_col_decide, body = the rebuild chain captured on a second stream
+        cudaStreamCaptureStatus status; cudaGraph_t graph = nullptr; const cudaGraphNode_t* deps = nullptr; size_t n_deps = 0;
+        cudaGraphConditionalHandle handle;
+        bool ok = cudaStreamGetCaptureInfo_v2(st, &status, nullptr, &graph, &deps, &n_deps) == cudaSuccess && status == cudaStreamCaptureStatusActive &&
+                  cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault) == cudaSuccess;
+        if (ok) {
+            k_col_decide<<<1, 1, 0, st>>>(handle, c); s->launches++;
+            ok = cudaStreamGetCaptureInfo_v2(st, &status, nullptr, &graph, &deps, &n_deps) == cudaSuccess;
         }
-        CK(cudaMemcpyAsync(s->counters_host, s->c_counters.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        CK(cudaStreamSynchronize(s->stream));
-        if (!s->counters_host[2]) break;
-        s->col_cap = std::max(2 * s->col_cap, s->counters_host[1] + 1024);         // list overflowed: grow and redo
-        CK(s->c_pairs.alloc(s->col_cap)); CK(s->c_pair_kc.alloc(s->col_cap)); CK(s->c_pair_force.alloc(s->col_cap)); CK(s->c_refs.alloc((size_t)2 * s->col_cap));
+        cudaGraphNode_t node = nullptr;
+        cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+        if (ok) {
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = handle; np.conditional.type = cudaGraphCondTypeIf; np.conditional.size = 1;
+            ok = cudaGraphAddNode(&node, graph, deps, n_deps, &np) == cudaSuccess && np.conditional.phGraph_out && np.conditional.phGraph_out[0];
+        }
+        if (ok) {
+            ok = s->aux_stream != nullptr;               // created by build_collision_tables (not while a capture is open)
+            if (ok) ok = cudaStreamBeginCaptureToGraph(s->aux_stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int64_t before = s->launches;
+                launch_collision_rebuild(s, f, c, s->aux_stream);
+                s->launches = before;                     // body launches are conditional: not counted as launches of the step
+                ok = cudaStreamEndCapture(s->aux_stream, nullptr) == cudaSuccess;
+            }
+            if (ok) ok = cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies) == cudaSuccess;
+        }
+        if (!ok) { cudaGetLastError(); return fail(s, VX_ERR_CUDA, "conditional graph node for the collision rebuild could not be built"); }
+        chained = true;
     }
-    const int P = s->n_pairs = s->counters_host[1];
-    std::vector<int> start(S + 1, 0);
-    if (P) {
-        ColFrame c = s->col_frame();
-        k_col_degree<<<blocks_for(P), TPB, 0, s->stream>>>(c, P); s->launches++;
-        std::vector<int> deg(S);
-        CK(cudaMemcpyAsync(deg.data(), s->c_deg.p, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-        CK(cudaStreamSynchronize(s->stream));
-        for (int k = 0; k < S; k++) start[k + 1] = start[k] + deg[k];
-    }
-    CK(cudaMemcpy(s->c_ref_start.p, start.data(), (size_t)(S + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    if (P) {
-        ColFrame c = s->col_frame();
-        k_col_fill<<<blocks_for(P), TPB, 0, s->stream>>>(c, P);
-        k_col_sort<<<blocks_for(S), TPB, 0, s->stream>>>(c);
-        s->launches += 2;
-    }
-    CK(cudaGetLastError());
+    if (!chained) launch_collision_rebuild(s, f, c, st);
+    k_col_narrow<<<std::min(blocks_for(s->col_cap), 148 * 16), TPB, 0, st>>>(f, c); s->launches++;
     return VX_OK;
 }
 
-// CVoxelyze::updateCollisions (src/Voxelyze.cpp:670-710): re-watch if stale, then all contact forces
-static int collision_step(vx_sim* s)
+// start of a stepping call: events the host knows about (reset, new externals, loaded state, ...) raise the device's stale flag
+static void collision_call_begin(vx_sim* s)
 {
-    DevParams* ph = s->params_host;
-    if (s->n_surf == 0) return VX_OK;
-    ColFrame c = s->col_frame();
-    CK(cudaMemsetAsync(s->c_counters.p, 0, sizeof(int), s->stream));
-    k_col_stale<<<blocks_for(s->n_surf), TPB, 0, s->stream>>>(s->frame(), c); s->launches++;
-    CK(cudaMemcpyAsync(s->counters_host, s->c_counters.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaMemcpyAsync(ph, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    if (ph->div_now | ph->div_latched) return VX_OK;                 // diverged: the reference returns before collisions
-    if (s->counters_host[0] || s->col_stale_host) {
-        int rc = rebuild_collisions(s);
-        if (rc != VX_OK) return rc;
-        s->col_stale_host = false;
+    if (!s->collisions || !s->col_tables || !s->col_stale_host) return;
+    k_col_mark_stale<<<1, 1, 0, s->stream>>>(s->c_counters.p); s->launches++;
+    s->col_stale_host = false;
+}
+// end of a stepping call (the stream has been synchronised and counters_host holds the device counters): mirror the
+// pair count, grow the pair list for the next call when it is half full, report an overflow
+static int collision_call_end(vx_sim* s)
+{
+    if (!s->collisions || !s->col_tables) return VX_OK;
+    const int* c = s->counters_host;
+    s->n_pairs = std::min(c[CC_PAIRS], s->col_cap);
+    s->col_rebuilds = c[CC_REBUILDS];
+    const bool overflow = c[CC_OVERFLOW] != 0;
+    if (overflow || 2LL * c[CC_PAIRS] > s->col_cap) {
+        s->col_cap = (int)std::min<long long>(std::max(2LL * s->col_cap, 2LL * c[CC_PAIRS]), 1LL << 30);
+        s->c_pairs.release(); s->c_pair_kc.release(); s->c_pair_force.release(); s->c_refs.release();
+        CK(s->c_pairs.alloc(s->col_cap)); CK(s->c_pair_kc.alloc(s->col_cap)); CK(s->c_pair_force.alloc(s->col_cap)); CK(s->c_refs.alloc((size_t)2 * s->col_cap));
+        const int init[CC_COUNT] = {1, 0, 0, c[CC_REBUILDS]};      // the lists are rebuilt into the new arrays by the next step
+        CK(cudaMemcpy(s->c_counters.p, init, sizeof(init), cudaMemcpyHostToDevice));
+        s->n_pairs = 0;
+        s->drop_graph();
     }
-    if (s->n_pairs) { k_col_narrow<<<blocks_for(s->n_pairs), TPB, 0, s->stream>>>(s->frame(), s->col_frame(), s->n_pairs); s->launches++; }
+    if (overflow) return fail(s, VX_ERR_ALLOC, "the watched-pair list overflowed during this call (its capacity has been doubled): contacts were missed, reload or reset the state");
     return VX_OK;
 }
 
@@ -583,13 +651,16 @@ static void launch_voxel(vx_sim* s, const Frame& f)
     s->launches++;
 }
 
-// one doTimeStep (src/Voxelyze.cpp:251-284); per_step_dt: dt < 0 with Poisson materials
-static void launch_step(vx_sim* s, const Frame& f, bool per_step_dt)
+// one doTimeStep (src/Voxelyze.cpp:251-284): links, [divergence test inside the kernels], collisions, voxels;
+// per_step_dt: dt < 0 with Poisson materials; capturing: the stream is being captured into a step graph
+static int launch_step(vx_sim* s, const Frame& f, bool per_step_dt, bool capturing = false)
 {
     if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
     if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
     launch_links(s, f);
+    if (s->collisions) { int rc = enqueue_collision_step(s, capturing); if (rc != VX_OK) return rc; }
     launch_voxel(s, f);
+    return VX_OK;
 }
 
 __global__ void k_begin(DevParams* p, float dt, int set_dt)
@@ -610,11 +681,13 @@ static int ensure_graph(vx_sim* s)
     cudaStream_t user = s->stream; s->stream = s->own_stream;
     cudaError_t e0 = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
     if (e0 != cudaSuccess) { s->stream = user; return cuda_fail(s, e0, "cudaStreamBeginCapture"); }
-    for (int k = 0; k < GRAPH_STEPS; k++) launch_step(s, f, false);
+    int rc = VX_OK;
+    for (int k = 0; k < GRAPH_STEPS && rc == VX_OK; k++) rc = launch_step(s, f, false, true);
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
     s->stream = user;
     s->graph_kernels = (int)(s->launches - before);
     s->launches = before;
+    if (rc != VX_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
     if (e != cudaSuccess) return cuda_fail(s, e, "cudaStreamEndCapture");
     e = cudaGraphInstantiate(&s->graph, g, 0);
     cudaGraphDestroy(g);
@@ -638,7 +711,7 @@ static int build_tensor_maps(vx_sim* s)
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return fail(s, VX_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
         encode = (EncodeFn)fn;
     }
-    const cuuint64_t nx = s->nx, ny = s->ny, NZ = (cuuint64_t)s->nz * s->n_members, N = s->N;
+    const cuuint64_t nx = s->nx, ny = s->ny, NZ = (cuuint64_t)s->nz * s->lat_members, N = s->N;
     std::vector<CUtensorMap> maps(2 * TM_COUNT);
     // box of bx x by x bz voxels (x bp parts) of an array with per_voxel_u64 eight-byte words per voxel and `parts` sub-arrays
     auto make = [&](CUtensorMap* m, void* base, int per_voxel_u64, int parts, cuuint32_t bx, cuuint32_t by, cuuint32_t bz, cuuint32_t bp) -> bool {
@@ -666,6 +739,21 @@ static int build_tensor_maps(vx_sim* s)
     return VX_OK;
 }
 
+// > 48 KB of dynamic shared memory needs a one-time opt-in per function and device
+static void lattice_opt_in(vx_sim* s)
+{
+    if (s->wb_opted_in) return;
+    cudaFuncSetAttribute(k_lattice_warp<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+    cudaFuncSetAttribute(k_lattice_warp<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+    cudaFuncSetAttribute(k_lattice_warp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+    cudaFuncSetAttribute(k_lattice_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    s->wb_opted_in = true;
+}
+
 // default fused kernel over the brick-group layers [gz_off, gz_off + ngz) (ngz < 0: all)
 static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off, int ngz, int book)
 {
@@ -674,34 +762,26 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     // 2x2x2 groups of bricks unless their padding would waste more than a tenth of the warps (small boxes)
     const bool grouped = ngz >= 0 || (double)gx * gy * gz * 8 <= 1.1 * (double)bx * by * bz;
     const int nbx = grouped ? gx : bx, nby = grouped ? gy : by, nbz = ngz >= 0 ? ngz : (grouped ? gz : bz);
-    const long long bricks = (long long)nbx * nby * nbz * (grouped ? 8 : 1) * s->n_members;
+    const long long bricks = (long long)nbx * nby * nbz * (grouped ? 8 : 1) * s->lat_members;
     const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
     // staging: TMA bulk tensor copies (7, and what 0 picks on large lattices) or per-lane cp.async (5, and what 0 picks for
     // ensembles of small boxes, where whole-box copies fetch too much padding: 1.15 against 1.19 ms on 4096 robots of 10^3)
     const bool want_tma = s->path == 7 || (s->path != 5 && grouped);
-    const bool tma = want_tma && (s->tmaps.p || build_tensor_maps(s) == VX_OK);
-    if (!s->wb_opted_in) {               // > 48 KB of dynamic shared memory needs a one-time opt-in per function and device
-        cudaFuncSetAttribute(k_lattice_warp<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
-        cudaFuncSetAttribute(k_lattice_warp<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
-        cudaFuncSetAttribute(k_lattice_warp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
-        cudaFuncSetAttribute(k_lattice_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
-        cudaFuncSetAttribute(k_lattice_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
-        cudaFuncSetAttribute(k_lattice_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
-        cudaFuncSetAttribute(k_lattice_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
-        cudaFuncSetAttribute(k_lattice_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
-        s->wb_opted_in = true;
-    }
+    // (tensor maps are built outside stream capture: ensure_lattice_graph launches nothing before they exist)
+    const bool tma = want_tma && (s->tmaps.p || (!s->capturing && build_tensor_maps(s) == VX_OK));
+    lattice_opt_in(s);
     if (grid > 0) {
-        const LatFrame f = s->lat_frame(g);
+        LatFrame f = s->lat_frame(g);
+        if (first_of_call && s->amb_pending) { f.amb_set = 1; f.amb = s->amb_value; }
         const int fl = s->floor_on ? 1 : 0;
         const dim3 bl(32 * VX_WB_WARPS);
         const unsigned char* tm = s->tmaps.p;
         if (tma) {
             // grouped: one CTA per 2x2x2 group of bricks on a 3-D grid (no index divisions in the kernel); a grid too tall for
             // blockIdx.y/z falls back to the 1-D brick enumeration, which covers the same bricks
-            const long long zdim = (long long)nbz * s->n_members;
+            const long long zdim = (long long)nbz * s->lat_members;
             const bool g3 = grouped && VX_WB_WARPS == 8 && nby <= 65535 && zdim <= 65535;
-            const dim3 gr = g3 ? dim3((unsigned)nbx, (unsigned)nby, (unsigned)zdim) : dim3((unsigned)(((long long)bx * by * (ngz >= 0 ? 2 * ngz : bz) * s->n_members + VX_WB_WARPS - 1) / VX_WB_WARPS));
+            const dim3 gr = g3 ? dim3((unsigned)nbx, (unsigned)nby, (unsigned)zdim) : dim3((unsigned)(((long long)bx * by * (ngz >= 0 ? 2 * ngz : bz) * s->lat_members + VX_WB_WARPS - 1) / VX_WB_WARPS));
             const int kx = g3 ? nbx : bx, ky = g3 ? nby : by, kz = g3 ? nbz : (ngz >= 0 ? 2 * ngz : bz), koff = g3 ? gz_off : 2 * gz_off, gr_ = g3 ? 1 : 0;
             if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
                 if (s->uni) k_lattice_tma<true, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
@@ -725,20 +805,38 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     }
 }
 
-static void launch_lattice(vx_sim* s, int g, int first_of_call) { launch_lattice_warp(s, g, first_of_call, 0, -1, 1); }
+// one doTimeStep on the fused path: contact forces from the OLD state (generation g), then the fused kernel
+static int launch_lattice(vx_sim* s, int g, int first_of_call, bool capturing = false)
+{
+    if (s->collisions) {
+        s->gen_view = g;
+        int rc = enqueue_collision_step(s, capturing);
+        s->gen_view = -1;
+        if (rc != VX_OK) return rc;
+    }
+    launch_lattice_warp(s, g, first_of_call, 0, -1, 1);
+    return VX_OK;
+}
 
 static int ensure_lattice_graph(vx_sim* s, int g0)
 {
     if (s->lgraph[g0]) return VX_OK;
+    if (!s->tmaps.p) build_tensor_maps(s);            // allocates and copies: not allowed while a capture is open (a failure falls back to cp.async staging)
+    lattice_opt_in(s);
     cudaGraph_t g = nullptr;
     int64_t before = s->launches;
     cudaStream_t user = s->stream; s->stream = s->own_stream;       // see ensure_graph
     cudaError_t e0 = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
     if (e0 != cudaSuccess) { s->stream = user; return cuda_fail(s, e0, "cudaStreamBeginCapture"); }
-    for (int k = 0; k < GRAPH_STEPS; k++) launch_lattice(s, (g0 + k) & 1, 0);
+    int rc = VX_OK;
+    s->capturing = true;
+    for (int k = 0; k < GRAPH_STEPS && rc == VX_OK; k++) rc = launch_lattice(s, (g0 + k) & 1, 0, true);
+    s->capturing = false;
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
     s->stream = user;
+    s->lgraph_kernels = (int)(s->launches - before);
     s->launches = before;
+    if (rc != VX_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
     if (e != cudaSuccess) return cuda_fail(s, e, "cudaStreamEndCapture");
     e = cudaGraphInstantiate(&s->lgraph[g0], g, 0);
     cudaGraphDestroy(g);
@@ -752,12 +850,18 @@ static int finish_lattice_call(vx_sim* s, int g_start, int launched, int* diverg
     k_lattice_finish<<<1, 1, 0, s->stream>>>(s->params.p, (g_start + launched - 1) & 1); s->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
+    if (s->collisions && s->col_tables) CK(cudaMemcpyAsync(s->counters_host, s->c_counters.p, CC_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     const DevParams& p = *s->params_host;
     s->time_host = p.time;
+    const bool amb_used = s->amb_pending;            // the first step of this call applied a pending ambient temperature
+    s->amb_pending = false;
+    const int col_rc = collision_call_end(s);
+    if (col_rc != VX_OK) return col_rc;
     if (!p.div_latched) {
         s->gen = (g_start + launched) & 1;
         s->have_prev = true;
+        s->last_amb = amb_used && launched == 1; s->last_amb_value = s->amb_value;
         s->last_prev_dt = launched > 1 ? p.dt : s->prev_dt_host;
         s->prev_dt_host = p.prev_dt;
         return VX_OK;
@@ -768,8 +872,12 @@ static int finish_lattice_call(vx_sim* s, int g_start, int launched, int* diverg
     k_lattice_copy_voxels<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->N, s->pose0[g].p, s->pose1[g].p, s->mom0[g].p, s->mom1[g].p,
                                                                   s->pose0[g ^ 1].p, s->pose1[g ^ 1].p, s->mom0[g ^ 1].p, s->mom1[g ^ 1].p, 1);
     s->launches++;
-    CK(cudaStreamSynchronize(s->stream));
     s->gen = g ^ 1;
+    if (amb_used && p.steps_done == 0) {             // the voxels that were not advanced still got their new temperature
+        k_fill_temp<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->frame(), s->amb_value, nullptr, nullptr); s->launches++;
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    s->last_amb = amb_used && p.steps_done == 0; s->last_amb_value = s->amb_value;
     s->have_prev = true;
     s->last_prev_dt = p.steps_done > 0 ? p.dt : s->prev_dt_host;
     s->prev_dt_host = p.prev_dt;
@@ -785,28 +893,20 @@ static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
         if (dt <= 0) return VX_OK;
     }
     k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
+    collision_call_begin(s);
     const int g0 = s->gen;
     int done = 0;
-    if (s->collisions) {                            // contact forces come from the OLD state, i.e. before the fused kernel of the step;
-        for (; done < n_steps; done++) {            // the host decides about re-watching every step, so no graphs here
-            s->gen_view = (g0 + done) & 1;
-            int rc = collision_step(s);
-            s->gen_view = -1;
-            if (rc != VX_OK) return rc;
-            launch_lattice(s, (g0 + done) & 1, done == 0 ? 1 : 0);
-        }
-        return finish_lattice_call(s, g0, n_steps, diverged_step);
-    }
-    launch_lattice(s, g0, 1); done++;
+    { int rc = launch_lattice(s, g0, 1); if (rc != VX_OK) return rc; }
+    done++;
     while (n_steps - done >= GRAPH_STEPS) {
         const int g = (g0 + done) & 1;
         int rc = ensure_lattice_graph(s, g);                 // both generations at once: a later call may start on the other one
         if (rc == VX_OK) rc = ensure_lattice_graph(s, g ^ 1);
         if (rc != VX_OK) return rc;
         CK(cudaGraphLaunch(s->lgraph[g], s->stream));
-        s->launches += GRAPH_STEPS; done += GRAPH_STEPS;
+        s->launches += s->lgraph_kernels; done += GRAPH_STEPS;
     }
-    for (; done < n_steps; done++) launch_lattice(s, (g0 + done) & 1, 0);
+    for (; done < n_steps; done++) { int rc = launch_lattice(s, (g0 + done) & 1, 0); if (rc != VX_OK) return rc; }
     return finish_lattice_call(s, g0, n_steps, diverged_step);
 }
 
@@ -925,7 +1025,8 @@ void vx_destroy(vx_sim* s)
     for (int g = 0; g < 2; g++) { s->release_pose(g); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); }
     s->pair_lmat.release(); s->link_owner.release(); s->link_axis_dev.release();
     s->c_surf_vox.release(); s->c_surf_orig.release(); s->c_surf_member.release(); s->c_slot.release(); s->c_surf_ijk.release(); s->c_nearby.release();
-    s->c_last_watch.release(); s->c_head.release(); s->c_next.release(); s->c_cell.release(); s->c_pairs.release(); s->c_pair_kc.release();
+    s->c_last_watch.release(); s->c_cell_count.release(); s->c_cell_start.release(); s->c_sorted.release(); s->c_cell.release();
+    if (s->aux_stream) cudaStreamDestroy(s->aux_stream); s->c_pairs.release(); s->c_pair_kc.release();
     s->c_pair_force.release(); s->c_counters.release(); s->c_deg.release(); s->c_ref_start.release(); s->c_ref_fill.release(); s->c_refs.release();
     if (s->counters_host) cudaFreeHost(s->counters_host);
     s->si_minmax.release(); s->si_sum.release(); s->si_nominal.release(); s->si_consts.release(); s->si_buf.release();
@@ -942,6 +1043,9 @@ void vx_destroy(vx_sim* s)
 }
 
 const char* vx_last_error(const vx_sim* s) { return s ? s->err.c_str() : "null handle"; }
+
+static int relayout_fresh(vx_sim* s);
+static int relayout_keep_state(vx_sim* s);
 
 int vx_set_materials(vx_sim* s, int n, const vx_material_desc* d)
 {
@@ -961,6 +1065,14 @@ int vx_set_materials(vx_sim* s, int n, const vx_material_desc* d)
     s->descs.assign(d, d + n);
     for (auto& x : s->descs) x.strain = x.stress = nullptr;
     s->d_eps.swap(ne); s->d_sig.swap(ns); s->mats.swap(nm);
+    // Poisson's ratio switched on for a model that runs on the fused layout (the reference allows toggling it at any time,
+    // src/VX_Link.cpp:160-166): the model moves to the general layout, every voxel and link keeps its state
+    bool poisson = false;
+    for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
+    if (s->N > 0 && s->lattice && poisson) {
+        if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_materials inside vx_step_begin .. vx_step_end");
+        return (s->time_host != 0.f || s->have_prev) ? relayout_keep_state(s) : relayout_fresh(s);
+    }
     return upload_tables(s);
 }
 
@@ -1104,10 +1216,37 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     }
     const int L = s->L = (int)s->lk_vn.size();
 
-    // ---- internal voxel order: (member, z, y, x)
+    // ---- layout: a completely filled box (per member) runs fused.  The members of an ensemble are tiled side by side into
+    // one device lattice when that fills the 8 x 8 x 4 voxel tiles of the fused kernel better than one box per member
+    // (4096 robots of 10^3: 4 x 4 x 256 robots = a 40 x 40 x 2560 lattice without a single idle lane, against 69 % lane
+    // use for 10^3 boxes on their own).  Members never link: every link bit comes from a per-member neighbour lookup.
+    bool poisson = false;
+    for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
+    s->lattice = n > 0 && cells == (long long)n && !poisson && s->path != 1;
+    s->pack[0] = s->pack[1] = 1; s->pack[2] = s->n_members; s->lat_members = s->n_members;
+    if (s->lattice && s->n_members > 1 && !getenv("VX_NO_PACK")) {
+        auto up = [](long long v, long long q) { return (v + q - 1) / q * q; };
+        double best = 0; int bx_ = 1, by_ = 1;
+        for (int px = 1; px <= 8; px *= 2)
+            for (int py = 1; py <= px; py *= 2) {
+                if (s->n_members % (px * py) || px * ext3[0] > 30000 || py * ext3[1] > 30000) continue;
+                const long long pz = s->n_members / (px * py);
+                const double cost = (double)up(px * ext3[0], 2 * VX_WB_X) * up(py * ext3[1], 2 * VX_WB_Y) * up(pz * ext3[2], 2 * VX_WB_Z);
+                if (best == 0 || cost < best * 0.999) { best = cost; bx_ = px; by_ = py; }
+            }
+        if (bx_ * by_ > 1) { s->pack[0] = bx_; s->pack[1] = by_; s->pack[2] = s->n_members / (bx_ * by_); s->lat_members = 1; }
+    }
+    const bool packed = s->lat_members == 1 && s->n_members > 1;
+
+    // ---- internal voxel order: (member, z, y, x), or (Z, Y, X) in the tiled lattice of a packed ensemble
     s->v_i2e.resize(n);
     for (int i = 0; i < n; i++) s->v_i2e[i] = i;
     auto vkey = [&](int e) -> int64_t {
+        if (packed) {
+            const int m = s->member[e], mi = m % s->pack[0], mj = (m / s->pack[0]) % s->pack[1], mk = m / (s->pack[0] * s->pack[1]);
+            const int64_t X = (int64_t)mi * ext3[0] + (ijk[3 * e] - lo[0]), Y = (int64_t)mj * ext3[1] + (ijk[3 * e + 1] - lo[1]), Z = (int64_t)mk * ext3[2] + (ijk[3 * e + 2] - lo[2]);
+            return (Z << 40) | (Y << 20) | X;
+        }
         return ((int64_t)s->member[e] << 48) | ((int64_t)(ijk[3 * e + 2] + 32768) << 32) | ((int64_t)(ijk[3 * e + 1] + 32768) << 16) | (int64_t)(ijk[3 * e] + 32768);
     };
     {
@@ -1128,11 +1267,8 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     s->l_e2i.resize(L);
     for (int i = 0; i < L; i++) s->l_e2i[s->l_i2e[i]] = i;
 
-    // ---- layout: a completely filled box (per member) without Poisson materials runs fused
-    bool poisson = false;
-    for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
-    s->lattice = n > 0 && cells == (long long)n && !poisson && s->path != 1;
     s->nx = (int)ext3[0]; s->ny = (int)ext3[1]; s->nz = (int)ext3[2];
+    if (packed) { s->nx *= s->pack[0]; s->ny *= s->pack[1]; s->nz *= s->pack[2]; }
     s->link_owner.release(); s->link_axis_dev.release();
     s->si_nominal_ok = false; s->si_consts_ok = false; s->si_pressure_ok = false;
 
@@ -1304,6 +1440,7 @@ int vx_enable_collisions(vx_sim* s, int e)                         // src/Voxely
 {
     if (!s) return VX_ERR_ARG;
     if (s->collisions == (e != 0)) return VX_OK;
+    { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     s->collisions = e != 0;
     s->col_stale_host = true;
     s->drop_graph();
@@ -1319,15 +1456,15 @@ int vx_set_temperature_all(vx_sim* s, float t)
     if (!s) return VX_ERR_ARG;
     s->ambient = t;
     if (s->N == 0) return VX_OK;
-    CK(cudaSetDevice(s->device));
-    k_fill_temp<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->frame(), t, nullptr, nullptr); s->launches++;
-    CK(cudaGetLastError());
-    return VX_OK;
+    s->amb_pending = true; s->amb_value = t;
+    if (s->lattice && !s->collisions && !s->call_active) return VX_OK;     // the next fused step applies it (LatFrame::amb)
+    return flush_ambient(s);
 }
 int vx_set_temperature_members(vx_sim* s, int n, const float* t)
 {
     if (!s || !t || n != s->n_members) return VX_ERR_ARG;
     if (s->N == 0) return VX_OK;
+    s->amb_pending = false;                                          // every voxel is overwritten
     CK(cudaSetDevice(s->device));
     CK(s->member_t.alloc(n));
     CK(cudaMemcpyAsync(s->member_t.p, t, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
@@ -1358,28 +1495,20 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
         k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++;
     }
     int left = n_steps;
-    if (s->collisions) {                                           // host decides about re-watching every step
-        for (; left > 0; left--) {
-            if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
-            if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
-            launch_links(s, f);
-            int rc = collision_step(s);
-            if (rc != VX_OK) return rc;
-            f = s->frame();
-            launch_voxel(s, f);
-        }
-    }
+    collision_call_begin(s);
     if (!per_step_dt && left >= GRAPH_STEPS) {
         int rc = ensure_graph(s);
         if (rc != VX_OK) return rc;
         while (left >= GRAPH_STEPS) { CK(cudaGraphLaunch(s->graph, s->stream)); s->launches += s->graph_kernels; left -= GRAPH_STEPS; }
     }
-    for (; left > 0; left--) launch_step(s, f, per_step_dt);
+    for (; left > 0; left--) { int rc = launch_step(s, f, per_step_dt); if (rc != VX_OK) return rc; }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
+    if (s->collisions && s->col_tables) CK(cudaMemcpyAsync(s->counters_host, s->c_counters.p, CC_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->time_host = s->params_host->time;
     s->prev_dt_host = s->params_host->prev_dt;
+    { int rc = collision_call_end(s); if (rc != VX_OK) return rc; }
     if (s->params_host->div_latched) {
         if (diverged_step) *diverged_step = s->params_host->steps_done;
         return VX_DIVERGED;
@@ -1408,11 +1537,11 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
         // one fused kernel per step: reported as the "link" group (it is the dominant kernel)
         if (dt < 0) { rc = vx_recommended_dt(s, &dt); if (rc != VX_OK || dt <= 0) return rc; }
         k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
+        collision_call_begin(s);
         const int g0 = s->gen;
         for (int k = 0; k < n_steps; k++) {
             CK(cudaEventRecord(ev[4 * k + 0], s->stream));
-            if (s->collisions) { s->gen_view = (g0 + k) & 1; rc = collision_step(s); s->gen_view = -1; if (rc != VX_OK) return rc; }
-            launch_lattice(s, (g0 + k) & 1, k == 0 ? 1 : 0);
+            rc = launch_lattice(s, (g0 + k) & 1, k == 0 ? 1 : 0); if (rc != VX_OK) return rc;
             CK(cudaEventRecord(ev[4 * k + 3], s->stream));
             if (launches) launches[0] += 1;
         }
@@ -1423,6 +1552,7 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
         const bool per_step_dt = dt < 0 && s->any_poisson;
         k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, dt > 0 ? 1 : 0); s->launches++;
         if (dt < 0 && !per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+        collision_call_begin(s);
         for (int k = 0; k < n_steps; k++) {
             int64_t l0 = s->launches;
             CK(cudaEventRecord(ev[4 * k + 0], s->stream));
@@ -1433,14 +1563,16 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
             launch_links(s, f);
             int64_t l2 = s->launches;
             CK(cudaEventRecord(ev[4 * k + 2], s->stream));
-            if (s->collisions) { rc = collision_step(s); if (rc != VX_OK) return rc; f = s->frame(); }
+            if (s->collisions) { rc = enqueue_collision_step(s, false); if (rc != VX_OK) return rc; }
             launch_voxel(s, f);
             CK(cudaEventRecord(ev[4 * k + 3], s->stream));
             if (launches) { launches[2] += (int)(l1 - l0); launches[0] += (int)(l2 - l1); launches[1] += 1; }
         }
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
+        if (s->collisions && s->col_tables) CK(cudaMemcpyAsync(s->counters_host, s->c_counters.p, CC_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
+        { int rc2 = collision_call_end(s); if (rc2 != VX_OK) return rc2; }
         for (int k = 0; k < n_steps; k++) {
             float a = 0, b = 0, c = 0, d = 0;
             cudaEventElapsedTime(&a, ev[4 * k + 0], ev[4 * k + 1]);
@@ -1460,7 +1592,7 @@ int vx_prepare(vx_sim* s)
 {
     if (!s) return VX_ERR_ARG;
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_prepare inside vx_step_begin .. vx_step_end");
-    if (s->N == 0 || s->collisions) return VX_OK;                 // colliding models are not graph-captured
+    if (s->N == 0) return VX_OK;
     CK(cudaSetDevice(s->device));
     if (s->lattice) {
         int rc = ensure_lattice_graph(s, 0);
@@ -1537,6 +1669,7 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
     if (!s || !dst || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
     if (first + count > (is_link ? s->L : s->N_user)) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
+    { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     CK(cudaSetDevice(s->device));
     size_t bytes = (size_t)count * comps * esize;
     CK(cudaStreamSynchronize(s->stream));
@@ -1545,7 +1678,7 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
         int rc = ensure_link_refs(s);
         if (rc != VX_OK) return rc;
         LatLinkRef ref{s->link_owner.p, s->link_axis_dev.p};
-        k_lattice_gather_links<<<blocks_for(count), TPB, 0, s->stream>>>(s->lat_frame(s->gen), s->lat_frame(s->gen ^ 1), s->have_prev ? 1 : 0,
+        k_lattice_gather_links<<<blocks_for(count), TPB, 0, s->stream>>>(s->lat_frame(s->gen), prev_frame(s), s->have_prev ? 1 : 0,
                                                                          s->last_prev_dt, what, s->link_e2i_dev.p, ref, first, count, s->staging.p);
     } else {
         k_gather<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), what, is_link ? s->link_e2i_dev.p : s->vox_e2i_dev.p, first, count,
@@ -1566,6 +1699,7 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_upload inside vx_step_begin .. vx_step_end");
     if (first + count > s->N_user) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
+    { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     CK(cudaSetDevice(s->device));
     size_t bytes = (size_t)count * comps * esize;
     CK(cudaStreamSynchronize(s->stream));
@@ -1595,6 +1729,14 @@ int vx_collision_pairs(vx_sim* s, int32_t* pairs, int cap, int* n_pairs)
     for (int k = 0; k < P && k < cap; k++) { pairs[2 * k] = out[k].first; pairs[2 * k + 1] = out[k].second; }
     return VX_OK;
 }
+int vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds)
+{
+    if (!s) return VX_ERR_ARG;
+    const bool on = s->collisions && s->col_tables;
+    if (n_pairs) *n_pairs = on ? s->n_pairs : 0;
+    if (n_rebuilds) *n_rebuilds = on ? s->col_rebuilds : 0;
+    return VX_OK;
+}
 // fills `dst` (device) with one link field for all links, caller order
 static int gather_link_field(vx_sim* s, int what, void* dst)
 {
@@ -1602,7 +1744,7 @@ static int gather_link_field(vx_sim* s, int what, void* dst)
         int rc = ensure_link_refs(s);
         if (rc != VX_OK) return rc;
         LatLinkRef ref{s->link_owner.p, s->link_axis_dev.p};
-        k_lattice_gather_links<<<blocks_for(s->L), TPB, 0, s->stream>>>(s->lat_frame(s->gen), s->lat_frame(s->gen ^ 1), s->have_prev ? 1 : 0,
+        k_lattice_gather_links<<<blocks_for(s->L), TPB, 0, s->stream>>>(s->lat_frame(s->gen), prev_frame(s), s->have_prev ? 1 : 0,
                                                                         s->last_prev_dt, what, s->link_e2i_dev.p, ref, 0, s->L, dst);
     } else {
         k_gather<<<blocks_for(s->L), TPB, 0, s->stream>>>(s->frame(), what, s->link_e2i_dev.p, 0, s->L, dst, s->axis_first[1], s->axis_first[2]);
@@ -1618,6 +1760,7 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
     const bool link_info = info == SI_STRAIN_ENERGY || info == SI_ENG_STRESS || info == SI_ENG_STRAIN;
     const int count = link_info ? s->L : s->N_user;                 // fill cells of a box with holes are not voxels
     if (count == 0) return VX_OK;                                  // src/Voxelyze.cpp:759,777
+    { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     CK(cudaSetDevice(s->device));
     CK(s->si_minmax.alloc(2)); CK(s->si_sum.alloc(1));
     const float init[2] = {3.402823466e38f, -3.402823466e38f};
@@ -1710,6 +1853,7 @@ int vx_set_stream(vx_sim* s, uint64_t stream)
 int vx_pose_plane(vx_sim* s, int iz, uint64_t* p0, uint64_t* p1, int* count, int* rec_bytes)
 {
     if (!s || s->n_members != 1) return VX_ERR_ARG;
+    if (!s->call_active) { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     int64_t key = (int64_t)(iz + 32768);
     auto lo = std::lower_bound(s->sort_key.begin(), s->sort_key.end(), key);
     auto hi = std::upper_bound(s->sort_key.begin(), s->sort_key.end(), key);

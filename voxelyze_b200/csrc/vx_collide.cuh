@@ -1,4 +1,4 @@
-// vx_collide.cuh -- self-collision: uniform-grid broadphase + narrowphase (general path).
+// vx_collide.cuh -- self-collision: uniform-grid broadphase with a sort-by-cell pass + narrowphase, device resident.
 //
 // Replaces the reference's watch-list machinery:
 //   CVoxelyze::updateCollisions / regenerateCollisions   src/Voxelyze.cpp:670-750   (serial O(N*S))
@@ -11,16 +11,29 @@
 // subtracted from each voxel one by one in ascending partner index (= the reference's colWatch
 // creation order), so the per-voxel sum has the reference's bit pattern.
 //
-// Broadphase = spatial hash of surface voxels by cell of their current position (cell edge = watch
-// radius), per-cell linked lists built with atomicExch, 27-cell scan per surface voxel.  The
-// 5-hop exclusion is a precomputed 11^3-bit mask per surface voxel (graph BFS on the host when the
-// topology is set), tested by lattice offset.
+// Everything is decided and done on the device; the host only enqueues (no synchronisation per step, so colliding
+// runs are captured in CUDA graphs like all others):
+//   every step      k_col_stale    any surface voxel further than recalcDist from its last watch position -> stale flag
+//   if stale        k_col_clear .. k_col_done: the rebuild.  In a captured graph this chain is the body of a conditional IF node
+//                   whose condition k_col_decide sets (cudaGraphSetConditional); launched directly, every kernel of the chain
+//                   returns at once unless the flag is up.
+//                     k_col_keys     cell of every surface voxel (cell edge = watch radius), hashed into a power-of-two table;
+//                                    histogram of the buckets
+//                     k_col_scan     exclusive prefix sum of the histogram -> bucket ranges          (one block, shuffles)
+//                     k_col_scatter  counting sort: surface voxels ordered by bucket
+//                     k_col_pairs    27-cell scan per surface voxel over the sorted ranges; distance, member and 5-hop tests
+//                                    (the 5-hop exclusion is a precomputed 11^3-bit mask per surface voxel, tested by lattice
+//                                    offset); appends the pair, counts it for both voxels
+//                     k_col_scan     prefix sum of the per-voxel pair counts -> CSR of contact references
+//                     k_col_fill, k_col_sort   the references of every voxel, ordered by the partner's caller index
+//   every step      k_col_narrow   contact force of every watched pair from the OLD state
 #pragma once
 #include "vx_kernels.cuh"
 
 namespace vxd {
 
 #define VX_NEARBY_WORDS 42           // 11*11*11 = 1331 bits
+enum { CC_STALE, CC_PAIRS, CC_OVERFLOW, CC_REBUILDS, CC_COUNT };
 
 struct ColFrame {
     int n_surf;
@@ -30,141 +43,218 @@ struct ColFrame {
     const short4* surf_ijk;          // lattice index
     const uint32_t* nearby;          // [n_surf][VX_NEARBY_WORDS]
     float4* last_watch;              // CVX_Voxel::lastColWatchPosition (float copy of pos)
-    int* head; int* next; int4* cell; int hash_mask;
+    int* cell_count; int* cell_start; int* sorted; int4* cell; int hash_mask;      // buckets: histogram, ranges, surface voxels by bucket
     int2* pairs; float2* pair_kc; float4* pair_force; int cap;
-    int* counters;                   // [0] stale flag, [1] number of pairs, [2] overflow
-    int* deg; const int* ref_start; int* ref_fill; int* refs;
+    int* counters;                   // CC_*: rebuild wanted, number of pairs, list overflowed (sticky), rebuilds so far
+    int* deg; int* ref_start; int* ref_fill; int* refs;
     double inv_cell;
     float thresh_sq, recalc_sq, envelope;
+    const DevParams* params; int parity;     // divergence test: general path (parity < 0) or the fused step that reads generation `parity`
 };
 
 __device__ __forceinline__ int col_hash(int cx, int cy, int cz, int mask)
 {
     return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)cz * 83492791u)) & mask;
 }
+// a diverged step returns before updateCollisions (src/Voxelyze.cpp:265-271)
+__device__ __forceinline__ bool col_frozen(const ColFrame& c)
+{
+    const DevParams* p = c.params;
+    return c.parity < 0 ? (p->div_now | p->div_latched) != 0 : (p->div_flag[c.parity ^ 1] | p->div_latched) != 0;
+}
+__device__ __forceinline__ bool col_rebuilding(const ColFrame& c) { return c.counters[CC_STALE] != 0 && !col_frozen(c); }
+__device__ __forceinline__ int col_pair_count(const ColFrame& c) { const int n = c.counters[CC_PAIRS]; return n < c.cap ? n : c.cap; }
 
 // any surface voxel moved further than recalcDist since the last rebuild?  (src/Voxelyze.cpp:688-696)
 __global__ void k_col_stale(Frame f, ColFrame c)
 {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= c.n_surf) return;
-    double4 p = f.pose0[c.surf_vox[s]];
-    float4 w = c.last_watch[s];
-    double dx = p.x - w.x, dy = p.y - w.y, dz = p.z - w.z;
-    if (dx * dx + dy * dy + dz * dz > c.recalc_sq) c.counters[0] = 1;
+    if (col_frozen(c)) return;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < c.n_surf; s += gridDim.x * blockDim.x) {
+        double4 p = f.pose0[c.surf_vox[s]];
+        float4 w = c.last_watch[s];
+        double dx = p.x - w.x, dy = p.y - w.y, dz = p.z - w.z;
+        if (dx * dx + dy * dy + dz * dz > c.recalc_sq) c.counters[CC_STALE] = 1;
+    }
+}
+// condition of the graph's IF node around the rebuild chain
+__global__ void k_col_decide(cudaGraphConditionalHandle handle, ColFrame c)
+{
+    cudaGraphSetConditional(handle, col_rebuilding(c) ? 1u : 0u);
+}
+__global__ void k_col_mark_stale(int* counters) { counters[CC_STALE] = 1; }
+
+__global__ void k_col_clear(ColFrame c)
+{
+    if (!col_rebuilding(c)) return;
+    const int n = max(c.hash_mask + 1, c.n_surf);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i <= c.hash_mask) c.cell_count[i] = 0;
+        if (i < c.n_surf) { c.deg[i] = 0; c.ref_fill[i] = 0; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { c.counters[CC_PAIRS] = 0; c.counters[CC_REBUILDS] += 1; }
 }
 
-__global__ void k_col_insert(Frame f, ColFrame c)
+__global__ void k_col_keys(Frame f, ColFrame c)
 {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= c.n_surf) return;
-    double4 p = f.pose0[c.surf_vox[s]];
-    c.last_watch[s] = make_float4((float)p.x, (float)p.y, (float)p.z, 0.0f);        // src/Voxelyze.cpp:733
-    int cx = (int)floor(p.x * c.inv_cell), cy = (int)floor(p.y * c.inv_cell), cz = (int)floor(p.z * c.inv_cell);
-    c.cell[s] = make_int4(cx, cy, cz, 0);
-    c.next[s] = atomicExch(&c.head[col_hash(cx, cy, cz, c.hash_mask)], s);
+    if (!col_rebuilding(c)) return;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < c.n_surf; s += gridDim.x * blockDim.x) {
+        double4 p = f.pose0[c.surf_vox[s]];
+        c.last_watch[s] = make_float4((float)p.x, (float)p.y, (float)p.z, 0.0f);        // src/Voxelyze.cpp:733
+        int cx = (int)floor(p.x * c.inv_cell), cy = (int)floor(p.y * c.inv_cell), cz = (int)floor(p.z * c.inv_cell);
+        const int key = col_hash(cx, cy, cz, c.hash_mask);
+        c.cell[s] = make_int4(cx, cy, cz, key);
+        atomicAdd(&c.cell_count[key], 1);
+    }
+}
+
+// out[i] = in[0] + .. + in[i-1] for i in [0, n]; ONE block of 1024 threads (rebuilds are rare and n is a few 10^5 at most)
+__global__ void __launch_bounds__(1024) k_col_scan(ColFrame c, const int* in, int* out, int n)
+{
+    if (!col_rebuilding(c)) return;
+    __shared__ int warp_sum[32];
+    __shared__ int carry_sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sum[lane], t = w;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+            warp_sum[lane] = t - w;                                   // exclusive over the warps
+        }
+        __syncthreads();
+        const int carry = carry_sh;
+        if (i < n) out[i] = carry + warp_sum[warp] + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_sh = carry + warp_sum[warp] + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_sh;
+}
+
+// counting sort by bucket (the histogram is consumed)
+__global__ void k_col_scatter(ColFrame c)
+{
+    if (!col_rebuilding(c)) return;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < c.n_surf; s += gridDim.x * blockDim.x) {
+        const int key = c.cell[s].w;
+        c.sorted[c.cell_start[key] + atomicSub(&c.cell_count[key], 1) - 1] = s;
+    }
 }
 
 // watched pairs found by the voxel with the smaller caller index (src/Voxelyze.cpp:730-747)
 __global__ void k_col_pairs(Frame f, ColFrame c)
 {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= c.n_surf) return;
-    const double4 pa = f.pose0[c.surf_vox[a]];
-    const int4 ca = c.cell[a];
-    const short4 ia = c.surf_ijk[a];
-    const int oa = c.surf_orig[a], ma = c.surf_member[a];
-    const uint32_t* near_a = c.nearby + (size_t)a * VX_NEARBY_WORDS;
-    for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
-        const int cx = ca.x + dx, cy = ca.y + dy, cz = ca.z + dz;
-        for (int b = c.head[col_hash(cx, cy, cz, c.hash_mask)]; b >= 0; b = c.next[b]) {
-            const int4 cb = c.cell[b];
-            if (cb.x != cx || cb.y != cy || cb.z != cz) continue;      // other cell sharing the bucket
-            if (c.surf_orig[b] <= oa || c.surf_member[b] != ma) continue;
-            const double4 pb = f.pose0[c.surf_vox[b]];
-            const double ex = pa.x - pb.x, ey = pa.y - pb.y, ez = pa.z - pb.z;
-            if (ex * ex + ey * ey + ez * ez > c.thresh_sq) continue;    // double > float, like the reference
-            const short4 ib = c.surf_ijk[b];
-            const int ox = ib.x - ia.x, oy = ib.y - ia.y, oz = ib.z - ia.z;
-            if (ox >= -5 && ox <= 5 && oy >= -5 && oy <= 5 && oz >= -5 && oz <= 5) {
-                const int bit = ((oz + 5) * 11 + (oy + 5)) * 11 + (ox + 5);
-                if (near_a[bit >> 5] & (1u << (bit & 31))) continue;    // within 5 link hops
+    if (!col_rebuilding(c)) return;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < c.n_surf; a += gridDim.x * blockDim.x) {
+        const double4 pa = f.pose0[c.surf_vox[a]];
+        const int4 ca = c.cell[a];
+        const short4 ia = c.surf_ijk[a];
+        const int oa = c.surf_orig[a], ma = c.surf_member[a];
+        const uint32_t* near_a = c.nearby + (size_t)a * VX_NEARBY_WORDS;
+        for (int dz = -1; dz <= 1; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+            const int cx = ca.x + dx, cy = ca.y + dy, cz = ca.z + dz;
+            const int key = col_hash(cx, cy, cz, c.hash_mask);
+            for (int j = c.cell_start[key], je = c.cell_start[key + 1]; j < je; j++) {
+                const int b = c.sorted[j];
+                const int4 cb = c.cell[b];
+                if (cb.x != cx || cb.y != cy || cb.z != cz) continue;      // another cell sharing the bucket
+                if (c.surf_orig[b] <= oa || c.surf_member[b] != ma) continue;
+                const double4 pb = f.pose0[c.surf_vox[b]];
+                const double ex = pa.x - pb.x, ey = pa.y - pb.y, ez = pa.z - pb.z;
+                if (ex * ex + ey * ey + ez * ez > c.thresh_sq) continue;    // double > float, like the reference
+                const short4 ib = c.surf_ijk[b];
+                const int ox = ib.x - ia.x, oy = ib.y - ia.y, oz = ib.z - ia.z;
+                if (ox >= -5 && ox <= 5 && oy >= -5 && oy <= 5 && oz >= -5 && oz <= 5) {
+                    const int bit = ((oz + 5) * 11 + (oy + 5)) * 11 + (ox + 5);
+                    if (near_a[bit >> 5] & (1u << (bit & 31))) continue;    // within 5 link hops
+                }
+                const int slot = atomicAdd(&c.counters[CC_PAIRS], 1);
+                if (slot >= c.cap) { c.counters[CC_OVERFLOW] = 1; continue; }
+                c.pairs[slot] = make_int2(a, b);
+                atomicAdd(&c.deg[a], 1); atomicAdd(&c.deg[b], 1);
+                // CVX_Collision constructor (src/VX_Collision.cpp:17-23)
+                const DevVoxMat& m1 = f.vmat[meta_hi(f.pose1[c.surf_vox[a]].w) & VM_MAT_MASK];
+                const DevVoxMat& m2 = f.vmat[meta_hi(f.pose1[c.surf_vox[b]].w) & VM_MAT_MASK];
+                c.pair_kc[slot] = make_float2(2.0f / (1.0f / m1.pen_stiff + 1.0f / m2.pen_stiff), 0.5f * (m1.coll_damp_t + m2.coll_damp_t));
+                c.pair_force[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            const int slot = atomicAdd(&c.counters[1], 1);
-            if (slot >= c.cap) { c.counters[2] = 1; continue; }
-            c.pairs[slot] = make_int2(a, b);
-            // CVX_Collision constructor (src/VX_Collision.cpp:17-23)
-            const DevVoxMat& m1 = f.vmat[meta_hi(f.pose1[c.surf_vox[a]].w) & VM_MAT_MASK];
-            const DevVoxMat& m2 = f.vmat[meta_hi(f.pose1[c.surf_vox[b]].w) & VM_MAT_MASK];
-            c.pair_kc[slot] = make_float2(2.0f / (1.0f / m1.pen_stiff + 1.0f / m2.pen_stiff), 0.5f * (m1.coll_damp_t + m2.coll_damp_t));
-            c.pair_force[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
 
-__global__ void k_col_degree(ColFrame c, int n_pairs)
+__global__ void k_col_fill(ColFrame c)
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    int2 ab = c.pairs[p];
-    atomicAdd(&c.deg[ab.x], 1); atomicAdd(&c.deg[ab.y], 1);
-}
-
-__global__ void k_col_fill(ColFrame c, int n_pairs)
-{
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    int2 ab = c.pairs[p];
-    c.refs[c.ref_start[ab.x] + atomicAdd(&c.ref_fill[ab.x], 1)] = p * 2;          // this voxel is voxel1: +force
-    c.refs[c.ref_start[ab.y] + atomicAdd(&c.ref_fill[ab.y], 1)] = p * 2 + 1;      // voxel2: -force
+    if (!col_rebuilding(c)) return;
+    const int n_pairs = col_pair_count(c);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x) {
+        int2 ab = c.pairs[p];
+        c.refs[c.ref_start[ab.x] + atomicAdd(&c.ref_fill[ab.x], 1)] = p * 2;          // this voxel is voxel1: +force
+        c.refs[c.ref_start[ab.y] + atomicAdd(&c.ref_fill[ab.y], 1)] = p * 2 + 1;      // voxel2: -force
+    }
 }
 
 // order every voxel's contact list by the partner's caller index = colWatch creation order
 __global__ void k_col_sort(ColFrame c)
 {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= c.n_surf) return;
-    const int b = c.ref_start[s], e = c.ref_start[s + 1];
-    auto partner = [&](int ref) { int2 ab = c.pairs[ref >> 1]; return c.surf_orig[(ref & 1) ? ab.x : ab.y]; };
-    for (int i = b + 1; i < e; i++) {
-        int r = c.refs[i], key = partner(r), j = i - 1;
-        while (j >= b && partner(c.refs[j]) > key) { c.refs[j + 1] = c.refs[j]; j--; }
-        c.refs[j + 1] = r;
+    if (!col_rebuilding(c)) return;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < c.n_surf; s += gridDim.x * blockDim.x) {
+        const int b = c.ref_start[s], e = c.ref_start[s + 1];
+        auto partner = [&](int ref) { int2 ab = c.pairs[ref >> 1]; return c.surf_orig[(ref & 1) ? ab.x : ab.y]; };
+        for (int i = b + 1; i < e; i++) {
+            int r = c.refs[i], key = partner(r), j = i - 1;
+            while (j >= b && partner(c.refs[j]) > key) { c.refs[j + 1] = c.refs[j]; j--; }
+            c.refs[j + 1] = r;
+        }
     }
+}
+// last kernel of the rebuild chain
+__global__ void k_col_done(ColFrame c)
+{
+    if (!col_rebuilding(c)) return;
+    c.counters[CC_STALE] = 0;
 }
 
 // CVX_Collision::updateContactForce (src/VX_Collision.cpp:42-56), float arithmetic
-__global__ void k_col_narrow(Frame f, ColFrame c, int n_pairs)
+__global__ void k_col_narrow(Frame f, ColFrame c)
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    const int2 ab = c.pairs[p];
-    const int v1 = c.surf_vox[ab.x], v2 = c.surf_vox[ab.y];
-    const double4 a0 = f.pose0[v1], b0 = f.pose0[v2];
-    const double w1 = f.pose1[v1].w, w2 = f.pose1[v2].w;
-    const DevVoxMat& m1 = f.vmat[meta_hi(w1) & VM_MAT_MASK];
-    const DevVoxMat& m2 = f.vmat[meta_hi(w2) & VM_MAT_MASK];
-    const float ox = (float)(b0.x - a0.x), oy = (float)(b0.y - a0.y), oz = (float)(b0.z - a0.z);
-    const float t1 = meta_temp(w1), t2 = meta_temp(w2);
-    const double bs1 = (base_size(m1, 0, t1) + base_size(m1, 1, t1) + base_size(m1, 2, t1)) / 3.0f;
-    const double bs2 = (base_size(m2, 0, t2) + base_size(m2, 1, t2) + base_size(m2, 2, t2)) / 3.0f;
-    const float nom_dist = (float)((bs1 + bs2) * c.envelope);
-    const float len = sqrtf(ox * ox + oy * oy + oz * oz);
-    const float rel = nom_dist - len;
-    float4 force = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rel > 0) {
-        float ux = ox, uy = oy, uz = oz;
-        if (len > 0) { float inv = 1.0f / len; ux = inv * ox; uy = inv * oy; uz = inv * oz; }
-        const double4 ma = f.mom0[v1], mb = f.mom0[v2];
-        const double dux = ux, duy = uy, duz = uz;
-        const double va = (m1.mass_inv_d * ma.x) * dux + (m1.mass_inv_d * ma.y) * duy + (m1.mass_inv_d * ma.z) * duz;
-        const double vb = (m2.mass_inv_d * mb.x) * dux + (m2.mass_inv_d * mb.y) * duy + (m2.mass_inv_d * mb.z) * duz;
-        const float rel_vel = (float)(va - vb);
-        const float2 kc = c.pair_kc[p];
-        const float mag = kc.x * rel + kc.y * rel_vel;
-        force = make_float4(mag * ux, mag * uy, mag * uz, 0.f);
+    if (col_frozen(c)) return;
+    const int n_pairs = col_pair_count(c);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x) {
+        const int2 ab = c.pairs[p];
+        const int v1 = c.surf_vox[ab.x], v2 = c.surf_vox[ab.y];
+        const double4 a0 = f.pose0[v1], b0 = f.pose0[v2];
+        const double w1 = f.pose1[v1].w, w2 = f.pose1[v2].w;
+        const DevVoxMat& m1 = f.vmat[meta_hi(w1) & VM_MAT_MASK];
+        const DevVoxMat& m2 = f.vmat[meta_hi(w2) & VM_MAT_MASK];
+        const float ox = (float)(b0.x - a0.x), oy = (float)(b0.y - a0.y), oz = (float)(b0.z - a0.z);
+        const float t1 = meta_temp(w1), t2 = meta_temp(w2);
+        const double bs1 = (base_size(m1, 0, t1) + base_size(m1, 1, t1) + base_size(m1, 2, t1)) / 3.0f;
+        const double bs2 = (base_size(m2, 0, t2) + base_size(m2, 1, t2) + base_size(m2, 2, t2)) / 3.0f;
+        const float nom_dist = (float)((bs1 + bs2) * c.envelope);
+        const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+        const float rel = nom_dist - len;
+        float4 force = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rel > 0) {
+            float ux = ox, uy = oy, uz = oz;
+            if (len > 0) { float inv = 1.0f / len; ux = inv * ox; uy = inv * oy; uz = inv * oz; }
+            const double4 ma = f.mom0[v1], mb = f.mom0[v2];
+            const double dux = ux, duy = uy, duz = uz;
+            const double va = (m1.mass_inv_d * ma.x) * dux + (m1.mass_inv_d * ma.y) * duy + (m1.mass_inv_d * ma.z) * duz;
+            const double vb = (m2.mass_inv_d * mb.x) * dux + (m2.mass_inv_d * mb.y) * duy + (m2.mass_inv_d * mb.z) * duz;
+            const float rel_vel = (float)(va - vb);
+            const float2 kc = c.pair_kc[p];
+            const float mag = kc.x * rel + kc.y * rel_vel;
+            force = make_float4(mag * ux, mag * uy, mag * uz, 0.f);
+        }
+        c.pair_force[p] = force;
     }
-    c.pair_force[p] = force;
 }
 
 } // namespace vxd

@@ -349,12 +349,20 @@ __global__ void k_scatter(Frame f, int what, const int* e2i, int first, int coun
 
 // persistent state of links [first, first+count) in caller order <- packed vx_link_state records (96 B each)
 struct LinkStateRec { double pos2[3], a1v[3], a2v[3]; float strain, max_strain, strain_offset, stress; uint32_t flags, pad; };
-__global__ void k_scatter_link_state(Frame f, const int* e2i, int first, int count, const LinkStateRec* src)
+__global__ void k_scatter_link_state(Frame f, const int* e2i, int first, int count, const LinkStateRec* src, int axis_first1, int axis_first2)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const int l = e2i[first + k];
     const LinkStateRec r = src[k];
+    {   // the per-end axial strains the Poisson pre-pass reads (CVX_Link::axialStrain(bool), src/VX_Link.cpp:121-124)
+        const int2 e = f.lends[l];
+        const int axis = l >= axis_first2 ? 2 : (l >= axis_first1 ? 1 : 0);
+        const float ratio = f.vmat[meta_hi(f.pose1[e.y].w) & VM_MAT_MASK].E / f.vmat[meta_hi(f.pose1[e.x].w) & VM_MAT_MASK].E;
+        const size_t nv = (size_t)f.n_vox;
+        f.slot_strain[(size_t)(2 * axis) * nv + e.x] = 2.0f * r.strain / (1.0f + ratio);
+        f.slot_strain[(size_t)(2 * axis + 1) * nv + e.y] = 2.0f * r.strain * ratio / (1.0f + ratio);
+    }
     f.lstA[l] = make_double4(r.pos2[0], r.pos2[1], r.pos2[2], r.a1v[0]);
     f.lstB[l] = make_double4(r.a1v[1], r.a1v[2], r.a2v[0], r.a2v[1]);
     f.lstC[l] = r.a2v[2];

@@ -55,6 +55,9 @@ struct LatFrame {
     // z-slab runs (k_lattice_warp only): voxels of plane push_z[k] also store their new pose into the ghost
     // plane of the neighbouring slab, push0/1[k] = that plane in the neighbour's pose0/pose1 arrays (peer memory)
     int push_z[2]; double4* push0[2]; double4* push1[2];
+    // CVoxelyze::setAmbientTemperature(t, true) applied by the step itself: every voxel reads temperature `amb` instead of
+    // its stored one in this launch and carries it into the new generation (no separate pass over the voxels)
+    int amb_set; float amb;
 };
 
 __device__ __forceinline__ void lat_decode(double2 a, double2 b, double2 c, float4 s, uint32_t lflags, LinkState& st)
@@ -90,7 +93,8 @@ __device__ __forceinline__ void lat_eval_link_rec(const LatFrame& f, int axis, u
     const DevLinkMat& lm = UNI ? f.lm0 : f.lmat[f.pair_lmat[(hn & VM_MAT_MASK) * f.n_mat + (hp & VM_MAT_MASK)]];
     lat_decode(ra, rb, rc, rs, (owner_bits >> (VM_LFLAG_SHIFT + 2 * axis)) & 3u, st);
     // CVX_Link::updateRestLength (src/VX_Link.cpp:137-140)
-    double rest = 0.5 * (vmn.size[axis] * (1 + meta_temp(n1.w) * vmn.cte) + vmp.size[axis] * (1 + meta_temp(p1.w) * vmp.cte));
+    const float tn = f.amb_set ? f.amb : meta_temp(n1.w), tp = f.amb_set ? f.amb : meta_temp(p1.w);
+    double rest = 0.5 * (vmn.size[axis] * (1 + tn * vmn.cte) + vmp.size[axis] * (1 + tp * vmp.cte));
     float t_area = 0.5f * (vmn.nom_f * vmn.nom_f + vmp.nom_f * vmp.nom_f);
     float damp_n, damp_p;
     if (UNI && damp_uni >= 0.0f) damp_n = damp_p = damp_uni;
@@ -455,7 +459,7 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
     double4 s0, s1;
     load_pose(lane, s0, s1);
     VoxelState vs;
-    vs.bits = new_bits; vs.temp = meta_temp(s1.w);
+    vs.bits = new_bits; vs.temp = f.amb_set ? f.amb : meta_temp(s1.w);
     vs.pos = mk3(s0.x, s0.y, s0.z);
     vs.orient.w = s0.w; vs.orient.x = s1.x; vs.orient.y = s1.y; vs.orient.z = s1.z;
     vs.lin = mk3(__hiloint2double(q0.y, q0.x), __hiloint2double(q0.w, q0.z), __hiloint2double(q1.y, q1.x));
@@ -741,7 +745,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     const uint4* mq = reinterpret_cast<const uint4*>(wbase + 11776 + lane * 32);
     const uint4 q0 = mq[0], q1 = mq[1], q2 = *reinterpret_cast<const uint4*>(wbase + 12800 + lane * 16);
     VoxelState vs;
-    vs.bits = new_bits; vs.temp = meta_temp(s1.w);
+    vs.bits = new_bits; vs.temp = f.amb_set ? f.amb : meta_temp(s1.w);
     vs.pos = mk3(s0.x, s0.y, s0.z);
     vs.orient.w = s0.w; vs.orient.x = s1.x; vs.orient.y = s1.y; vs.orient.z = s1.z;
     vs.lin = mk3(__hiloint2double(q0.y, q0.x), __hiloint2double(q0.w, q0.z), __hiloint2double(q1.y, q1.x));

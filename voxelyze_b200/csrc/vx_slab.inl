@@ -127,6 +127,7 @@ int vx_slab_exchange(vx_sim* s)
 {
     if (!s || !s->lattice || s->call_active) return VX_ERR_ARG;
     int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
+    rc = flush_ambient(s); if (rc != VX_OK) return rc;
     CK(cudaEventRecord(s->ev_boundary, s->stream));
     CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
     peer_push(s, s->gen, false);

@@ -41,6 +41,7 @@ static std::vector<Chunk> state_chunks(vx_sim* s)
 int vx_save_state(vx_sim* s, const char* path)
 {
     if (!s || !path || s->call_active) return VX_ERR_ARG;
+    { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
     FILE* fp = fopen(path, "wb");
@@ -153,7 +154,7 @@ int vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* s
     CK(s->staging.alloc(bytes));
     CK(cudaMemcpyAsync(s->staging.p, src, bytes, cudaMemcpyHostToDevice, s->stream));
     if (!s->lattice) {
-        k_scatter_link_state<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), s->link_e2i_dev.p, first, count, (const LinkStateRec*)s->staging.p);
+        k_scatter_link_state<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), s->link_e2i_dev.p, first, count, (const LinkStateRec*)s->staging.p, s->axis_first[1], s->axis_first[2]);
     } else {
         std::vector<int> of((size_t)3 * s->N, -1);              // (axis, owner voxel) -> caller link index
         for (int e = 0; e < s->L; e++) of[(size_t)s->lk_axis[e] * s->N + s->v_e2i[s->lk_vn[e]]] = e;
