@@ -102,6 +102,48 @@ def build_cpp_tests() -> dict:
                             "-o", exe_ref, src] + [os.path.join(ref, "src", n + ".cpp") for n in names], check=True)
     if os.path.exists(exe_ref):
         out["ref"] = exe_ref
+    out.update(build_ref_gtests())
+    return out
+
+
+def build_ref_gtests() -> dict:
+    """The reference's OWN gtest headers (test/tVX_Material.h, tVX_MaterialLink.h, tVX_Voxel.h, tVoxelyze.h), unmodified and
+    not copied: compiled where they lie under /root/reference through per-file symbolic links (tests/cpp/_build/rt_*/reftests/
+    test/) whose sibling `include` link selects the implementation under test -- the reference's headers (+ its sources) or the
+    facade's.  GoogleTest is not in the image: tests/cpp/gtest_shim/gtest/gtest.h stands in.  Only where /root/reference
+    exists (this container); the GPU box runs the prebuilt binaries."""
+    out = {}
+    tdir = os.path.join(ROOT, "tests", "cpp")
+    bdir = os.path.join(tdir, "_build")
+    ref = "/root/reference"
+    main = os.path.join(tdir, "ref_gtests_main.cpp")
+    shim = os.path.join(tdir, "gtest_shim")
+    exes = {"gtests_ref": os.path.join(bdir, "ref_gtests_ref"), "gtests_b200": os.path.join(bdir, "ref_gtests_b200")}
+    if os.path.isdir(os.path.join(ref, "test")):
+        tests = sorted(f for f in os.listdir(os.path.join(ref, "test")) if f.startswith("t") and f.endswith(".h"))
+        for variant, inc in (("ref", os.path.join(ref, "include")), ("b200", os.path.join(FACADE_DIR, "include"))):
+            d = os.path.join(bdir, "rt_" + variant, "reftests")
+            os.makedirs(os.path.join(d, "test"), exist_ok=True)
+            for f in tests:                              # file links, not a directory link: `..` must stay inside rt_*/reftests
+                link = os.path.join(d, "test", f)
+                if not os.path.islink(link):
+                    os.symlink(os.path.join(ref, "test", f), link)
+            link = os.path.join(d, "include")
+            if not os.path.islink(link):
+                os.symlink(inc, link)
+        deps = [main, os.path.join(shim, "gtest", "gtest.h")]
+        if not _newer(exes["gtests_ref"], deps):
+            names = ["Voxelyze", "VX_Link", "VX_Voxel", "VX_External", "VX_Material", "VX_MaterialVoxel",
+                     "VX_MaterialLink", "VX_Collision", "VX_LinearSolver"]
+            subprocess.run([_host_cxx(), "-O3", "-std=c++11", "-w", "-I", shim, "-I", os.path.join(bdir, "rt_ref"), "-I", os.path.join(ref, "include"),
+                            "-o", exes["gtests_ref"], main] + [os.path.join(ref, "src", n + ".cpp") for n in names], check=True)
+        inc = os.path.join(FACADE_DIR, "include")
+        if not _newer(exes["gtests_b200"], deps + [FACADE_SO] + [os.path.join(inc, f) for f in os.listdir(inc)]):
+            subprocess.run([_host_cxx(), "-O2", "-std=c++17", "-w", "-I", shim, "-I", os.path.join(bdir, "rt_b200"), "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                            "-o", exes["gtests_b200"], main, "-L", LIBDIR, "-lvoxelyze_facade", "-lvoxelyze_b200", "-Wl,-rpath," + LIBDIR], check=True)
+    for k, exe in exes.items():
+        if os.path.exists(exe):
+            out[k] = exe
     return out
 
 
