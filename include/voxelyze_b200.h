@@ -265,6 +265,21 @@ int  vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds);
  * reference's enum values (include/Voxelyze.h:48-67).                                */
 int  vx_state_info(vx_sim* s, int info, int type, float* out);
 
+/* ---- deformed surface mesh ---------------------------------------------
+ * replaces CVX_MeshRender (include/VX_MeshRender.h:26-62, src/VX_MeshRender.cpp:49-218) and what it calls per vertex,
+ * CVX_Voxel::cornerPosition / cornerOffset (src/VX_Voxel.cpp:141-159).  vx_mesh_build = generateMesh (exposed faces as
+ * quads over shared vertices, numbered like the reference so that saveObj output is identical), vx_mesh_update =
+ * updateMesh(colorScheme, stateType) (coloring: 0 material, 1 failure, 2 state info with a CVoxelyze::stateInfoType);
+ * the float buffers (3 per vertex, 3 normal + 3 colour components per quad) stay on the device: vx_mesh_device returns
+ * their addresses, vx_mesh_download copies any of them (NULL = skip).  One simulation per mesh (no ensembles).
+ * The reference shim drives the real CVX_MeshRender; the oracle port returns VX_ERR_UNSUPPORTED.                  */
+int  vx_mesh_set_material_colors(vx_sim* s, int n_materials, const unsigned char* rgba);
+int  vx_mesh_build(vx_sim* s, int* n_vertices, int* n_quads);
+int  vx_mesh_update(vx_sim* s, int coloring, int state_type);
+int  vx_mesh_counts(vx_sim* s, int* n_vertices, int* n_quads);
+int  vx_mesh_download(vx_sim* s, float* vertices, int32_t* quads, float* normals, float* colors, int32_t* quad_voxel);
+int  vx_mesh_device(vx_sim* s, uint64_t* vertices, uint64_t* quads, uint64_t* normals, uint64_t* colors);
+
 /* ---- device side hooks (CUDA build only; oracles return VX_ERR_UNSUPPORTED) -- */
 /* run all work of this handle on the given cudaStream_t (passed as an integer; 0 is CUDA's
  * legacy default stream and is used as such).  VX_OWN_STREAM selects the library's own

@@ -1126,6 +1126,13 @@ int vx_active_path(const vx_sim*) { return 0; }
 const char* vx_kernel_name(const vx_sim*) { return "cpu (oracle port)"; }
 int vx_step_profile(vx_sim*, float, int, float*, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_prepare(vx_sim*) { return VX_OK; }
+// surface mesh: pinned directly against the reference's CVX_MeshRender (oracle/ref_shim.cpp), not restated here
+int vx_mesh_set_material_colors(vx_sim*, int, const unsigned char*) { return VX_ERR_UNSUPPORTED; }
+int vx_mesh_build(vx_sim*, int*, int*) { return VX_ERR_UNSUPPORTED; }
+int vx_mesh_update(vx_sim*, int, int) { return VX_ERR_UNSUPPORTED; }
+int vx_mesh_counts(vx_sim*, int*, int*) { return VX_ERR_UNSUPPORTED; }
+int vx_mesh_download(vx_sim*, float*, int32_t*, float*, float*, int32_t*) { return VX_ERR_UNSUPPORTED; }
+int vx_mesh_device(vx_sim*, uint64_t*, uint64_t*, uint64_t*, uint64_t*) { return VX_ERR_UNSUPPORTED; }
 int vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds)
 {
     if (n_rebuilds) *n_rebuilds = -1;                  // not counted here

@@ -33,6 +33,7 @@
 #include "VX_MaterialLink.h"
 #include "VX_External.h"
 #include "VX_Collision.h"
+#include "VX_MeshRender.h"
 #undef private
 #undef protected
 
@@ -64,6 +65,8 @@ struct vx_sim {
     float grav = 0.f;
     bool floor_on = false, collisions = false;
     std::string err;
+    CVX_MeshRender* mesh = nullptr;
+    std::vector<unsigned char> colors;     // rgba per material
 };
 
 static int fail(vx_sim* s, int code, const char* msg) { if (s) s->err = msg; return code; }
@@ -424,6 +427,57 @@ int vx_active_path(const vx_sim*) { return 0; }
 const char* vx_kernel_name(const vx_sim*) { return "cpu (reference CVoxelyze::doTimeStep)"; }
 int vx_step_profile(vx_sim*, float, int, float*, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_prepare(vx_sim*) { return VX_OK; }
+
+// ---- surface mesh: the reference's own CVX_MeshRender (src/VX_MeshRender.cpp), members read through the opened-up header
+static void apply_colors(vx_sim* s)
+{
+    if (s->members.size() != 1) return;
+    for (size_t i = 0; i < s->members[0].mats.size() && 4 * i + 3 < s->colors.size(); i++)
+        s->members[0].mats[i]->setColor(s->colors[4 * i], s->colors[4 * i + 1], s->colors[4 * i + 2], s->colors[4 * i + 3]);
+}
+int vx_mesh_set_material_colors(vx_sim* s, int n, const unsigned char* rgba)
+{
+    if (!s || n < 0 || (n && !rgba)) return VX_ERR_ARG;
+    s->colors.assign(rgba, rgba + 4 * (size_t)n);
+    apply_colors(s);
+    return VX_OK;
+}
+int vx_mesh_build(vx_sim* s, int* nv, int* nq)
+{
+    if (!s || s->members.size() != 1) return VX_ERR_UNSUPPORTED;
+    delete s->mesh;
+    apply_colors(s);
+    s->mesh = new CVX_MeshRender(s->members[0].sim);
+    if (nv) *nv = (int)s->mesh->vertices.size() / 3;
+    if (nq) *nq = (int)s->mesh->quads.size() / 4;
+    return VX_OK;
+}
+int vx_mesh_update(vx_sim* s, int coloring, int state_type)
+{
+    if (!s) return VX_ERR_ARG;
+    if (!s->mesh) { int rc = vx_mesh_build(s, nullptr, nullptr); if (rc != VX_OK) return rc; }
+    s->mesh->updateMesh((CVX_MeshRender::viewColoring)coloring, (CVoxelyze::stateInfoType)state_type);
+    return VX_OK;
+}
+int vx_mesh_counts(vx_sim* s, int* nv, int* nq)
+{
+    if (!s) return VX_ERR_ARG;
+    if (nv) *nv = s->mesh ? (int)s->mesh->vertices.size() / 3 : 0;
+    if (nq) *nq = s->mesh ? (int)s->mesh->quads.size() / 4 : 0;
+    return VX_OK;
+}
+int vx_mesh_download(vx_sim* s, float* vertices, int32_t* quads, float* normals, float* colors, int32_t* quad_voxel)
+{
+    if (!s || !s->mesh) return VX_ERR_ARG;
+    CVX_MeshRender& m = *s->mesh;
+    if (vertices) std::copy(m.vertices.begin(), m.vertices.end(), vertices);
+    if (quads) std::copy(m.quads.begin(), m.quads.end(), quads);
+    if (normals) std::copy(m.quadNormals.begin(), m.quadNormals.end(), normals);
+    if (colors) std::copy(m.quadColors.begin(), m.quadColors.end(), colors);
+    if (quad_voxel) for (size_t i = 0; i < m.quadVoxIndices.size(); i++) quad_voxel[i] = s->members[0].voxels[m.quadVoxIndices[i]];
+    return VX_OK;
+}
+int vx_mesh_device(vx_sim*, uint64_t*, uint64_t*, uint64_t*, uint64_t*) { return VX_ERR_UNSUPPORTED; }
 int vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds)
 {
     if (n_rebuilds) *n_rebuilds = -1;                  // not counted here

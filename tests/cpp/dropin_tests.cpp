@@ -11,6 +11,7 @@
 #include "VX_Voxel.h"
 #include "VX_Link.h"
 #include "VX_MaterialLink.h"
+#include "VX_MeshRender.h"
 
 #include <cmath>
 #include <cstdio>
@@ -738,9 +739,44 @@ static void stateCheckpoint()           // facade extra: saveState / loadState (
 }
 #endif
 
+// the deformed surface mesh of a stepped model written by CVX_MeshRender::saveObj (src/VX_MeshRender.cpp:238-251): the file of
+// the facade must equal the reference's line for line
+static int meshObj(const char* path)
+{
+    CVoxelyze Vx(0.002);
+    buildJsonModel(Vx);
+    float dt = Vx.recommendedTimeStep();
+    for (int i = 0; i < 200; i++) Vx.doTimeStep(dt);
+    CVX_MeshRender mesh(&Vx);
+    mesh.updateMesh(CVX_MeshRender::STATE_INFO, CVoxelyze::KINETIC_ENERGY);
+    mesh.saveObj(path);
+    return 0;
+}
+// Poisson's ratio switched on in the middle of a run through the material handle (this used to abort the facade)
+static void printPoissonScenario()
+{
+    CVoxelyze Vx(0.001);
+    CVX_Material* m = Vx.addMaterial(1e6f, 1e3f);
+    m->setGlobalDamping(0.05f);
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) Vx.setVoxel(m, i, j, k);
+    for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) { Vx.voxel(0, j, k)->external()->setFixedAll(); Vx.voxel(5, j, k)->external()->setForce(2e-3f, 0, -1e-3f); }
+    float dt = Vx.recommendedTimeStep();
+    for (int i = 0; i < 300; i++) Vx.doTimeStep(dt);
+    m->setPoissonsRatio(0.3f);
+    float dt2 = Vx.recommendedTimeStep();
+    bool ok = true;
+    for (int i = 0; i < 300; i++) ok = Vx.doTimeStep(0.5f * dt2) && ok;
+    m->setPoissonsRatio(0.0f);
+    for (int i = 0; i < 100; i++) ok = Vx.doTimeStep(0.5f * dt2) && ok;
+    printf("ok %d dt %.9e dt2 %.9e\n", (int)ok, dt, dt2);
+    for (int i = 0; i < Vx.voxelCount(); i++) { Vec3D<double> q = Vx.voxel(i)->position(); printf("vox %d %.12e %.12e %.12e\n", i, q.x, q.y, q.z); }
+}
+
 int main(int argc, char** argv)
 {
     if (const char* t = getenv("TMPDIR")) g_tmpdir = t;
+    if (argc > 2 && std::string(argv[1]) == "--mesh-obj") return meshObj(argv[2]);
+    if (argc > 1 && std::string(argv[1]) == "--poisson-scenario") { printPoissonScenario(); return 0; }
     if (argc > 2 && std::string(argv[1]) == "--json-save") { CVoxelyze Vx(0.002); buildJsonModel(Vx); return Vx.saveJSON(argv[2]) ? 0 : 1; }
     if (argc > 1 && std::string(argv[1]) == "--edit-scenario") { printEditScenario(); return 0; }
     if (argc > 2 && std::string(argv[1]) == "--json-digest") { CVoxelyze Vx(argv[2]); printJsonDigest(Vx); return 0; }

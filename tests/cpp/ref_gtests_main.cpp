@@ -12,6 +12,10 @@
 #include "reftests/test/tVX_Voxel.h"
 #include "reftests/test/tVoxelyze.h"
 
+#include <type_traits>
+// the tests call abs() on doubles unqualified (tVoxelyze.h:101,557): the headers under test must bring the floating overload
+static_assert(std::is_same<decltype(abs(1.5)), double>::value, "abs(double) must not be the integer abs");
+
 int main(int argc, char** argv)
 {
     return ::testing::run_all(argc > 1 ? argv[1] : nullptr) > 250 ? 1 : 0;      // the caller reads the per-test lines

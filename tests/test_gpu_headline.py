@@ -94,3 +94,37 @@ def test_c4_one_robot_2000_steps_against_the_reference(product, cpu):
     assert np.array_equal(sg["voxflags"], so["voxflags"])            # static-friction state machine
     assert np.array_equal(sg["temp"], so["temp"])
     assert np.array_equal(sg["linkflags"] & 0xD, so["linkflags"] & 0xD)
+
+
+@pytest.mark.parametrize("case_name,steps", [("data_curve_fail", 300), ("large_deformation", 400), ("multi_material", 300), ("temperature_bimorph", 300)])
+def test_surface_mesh_matches_the_references_mesh_render(product, built, case_name, steps):
+    """the device mesh (vertices averaged from deformed voxel corners, quad normals, all colour schemes)
+    against the reference's own CVX_MeshRender driven through oracle/_ref.  Topology (vertex numbering, quads, quad owners):
+    exact.  Vertices: 1e-6 of the voxel size (the corner arithmetic is float; voxel state differs by <= 1e-9).  Colours: 2e-3
+    (jet map of a value divided by a float-accumulated maximum)."""
+    import cases
+    if not os.path.exists(capi.REF_SO):
+        pytest.skip("oracle/_ref not built")
+    ref = capi.load_reference()
+    sc = cases.BY_NAME[case_name].make()
+    rgba = [[255, 40, 0, 255], [0, 128, 255, 255], [10, 200, 30, 128], [77, 77, 77, 255]][:len(sc.materials)]
+    sims = []
+    for lib in (product, ref):
+        s = scenarios.build(lib, sc); dt = sc.dt or s.recommended_dt()
+        program = cases.BY_NAME[case_name].program
+        if program is None:
+            s.step(dt, steps)
+        else:
+            t = 0.0
+            for k in range(steps):
+                program(s, k, t); s.step(dt, 1); t = float(np.float32(t) + np.float32(dt))
+        s.mesh_set_material_colors(rgba)
+        sims.append(s)
+    g, r = sims
+    for coloring, state in ((0, 0), (1, 0), (2, 2), (2, 0), (2, 6), (2, 5), (2, 7), (2, 8)):
+        a, b = g.mesh(coloring, state), r.mesh(coloring, state)
+        assert np.array_equal(a["quads"], b["quads"]) and np.array_equal(a["quad_voxel"], b["quad_voxel"])
+        assert a["vertices"].shape == b["vertices"].shape and len(a["quads"]) > 0
+        assert np.abs(a["vertices"] - b["vertices"]).max() <= 1e-6 * sc.voxel_size, (coloring, state)
+        assert np.abs(a["normals"] - b["normals"]).max() <= 1e-4, (coloring, state)
+        assert np.abs(a["colors"] - b["colors"]).max() <= 2e-3, (coloring, state, np.abs(a["colors"] - b["colors"]).max())

@@ -66,12 +66,13 @@ def build_facade(force: bool = False) -> str:
     """The C++ drop-in class API (CVoxelyze, CVX_*) on top of the C-ABI library."""
     src = os.path.join(FACADE_DIR, "src", "voxelyze_facade.cpp")
     src_json = os.path.join(FACADE_DIR, "src", "voxelyze_json.cpp")
+    src_mesh = os.path.join(FACADE_DIR, "src", "voxelyze_mesh.cpp")
     inc = os.path.join(FACADE_DIR, "include")
-    deps = [src, src_json, PRODUCT_SO] + [os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(CSRC, "vx_material.hpp")]
+    deps = [src, src_json, src_mesh, PRODUCT_SO] + [os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(CSRC, "vx_material.hpp")]
     if not force and _newer(FACADE_SO, deps):
         return FACADE_SO
     cmd = [_host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable", "-Wno-overloaded-virtual",
-           "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", FACADE_SO, src, src_json,
+           "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", FACADE_SO, src, src_json, src_mesh,
            "-L", LIBDIR, "-lvoxelyze_b200", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)
     return FACADE_SO
@@ -97,7 +98,7 @@ def build_cpp_tests() -> dict:
     if os.path.isdir(os.path.join(ref, "src")):
         if not _newer(exe_ref, [src]):
             names = ["Voxelyze", "VX_Link", "VX_Voxel", "VX_External", "VX_Material", "VX_MaterialVoxel",
-                     "VX_MaterialLink", "VX_Collision", "VX_LinearSolver"]
+                     "VX_MaterialLink", "VX_Collision", "VX_LinearSolver", "VX_MeshRender"]
             subprocess.run([_host_cxx(), "-O3", "-std=c++11", "-w", "-DDROPIN_REFERENCE", "-I", os.path.join(ref, "include"),
                             "-o", exe_ref, src] + [os.path.join(ref, "src", n + ".cpp") for n in names], check=True)
     if os.path.exists(exe_ref):

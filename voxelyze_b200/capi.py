@@ -155,6 +155,12 @@ class VxLib:
             "vx_collision_pairs": (i32, [vp, vp, i32, P(i32)]),
             "vx_collision_stats": (i32, [vp, P(i32), P(i32)]),
             "vx_state_info": (i32, [vp, i32, i32, P(f32)]),
+            "vx_mesh_set_material_colors": (i32, [vp, i32, vp]),
+            "vx_mesh_build": (i32, [vp, P(i32), P(i32)]),
+            "vx_mesh_update": (i32, [vp, i32, i32]),
+            "vx_mesh_counts": (i32, [vp, P(i32), P(i32)]),
+            "vx_mesh_download": (i32, [vp, vp, vp, vp, vp, vp]),
+            "vx_mesh_device": (i32, [vp, P(u64), P(u64), P(u64), P(u64)]),
             "vx_set_stream": (i32, [vp, u64]),
             "vx_pose_plane": (i32, [vp, i32, P(u64), P(u64), P(i32), P(i32)]),
             "vx_halo_import": (i32, [vp, i32, u64, u64, i32]),
@@ -365,6 +371,25 @@ class Sim:
         a, b = C.c_int(0), C.c_int(0)
         self._chk(self.L.lib.vx_collision_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    # -- surface mesh (CVX_MeshRender) --------------------------------------------
+    MESH_MATERIAL, MESH_FAILURE, MESH_STATE_INFO = 0, 1, 2
+
+    def mesh_set_material_colors(self, rgba):
+        a = np.ascontiguousarray(rgba, dtype=np.uint8).reshape(-1, 4)
+        self._chk(self.L.lib.vx_mesh_set_material_colors(self.h, len(a), _ptr(a)))
+
+    def mesh(self, coloring: int = 0, state_type: int = 0) -> dict:
+        """generateMesh (first call) + updateMesh; returns vertices (nv,3), quads (nq,4), normals, colors (nq,3), quad_voxel."""
+        nv, nq = C.c_int(0), C.c_int(0)
+        self._chk(self.L.lib.vx_mesh_counts(self.h, C.byref(nv), C.byref(nq)))
+        if nv.value == 0:
+            self._chk(self.L.lib.vx_mesh_build(self.h, C.byref(nv), C.byref(nq)))
+        self._chk(self.L.lib.vx_mesh_update(self.h, coloring, state_type))
+        out = dict(vertices=np.zeros((nv.value, 3), np.float32), quads=np.zeros((nq.value, 4), np.int32), normals=np.zeros((nq.value, 3), np.float32),
+                   colors=np.zeros((nq.value, 3), np.float32), quad_voxel=np.zeros(nq.value, np.int32))
+        self._chk(self.L.lib.vx_mesh_download(self.h, _ptr(out["vertices"]), _ptr(out["quads"]), _ptr(out["normals"]), _ptr(out["colors"]), _ptr(out["quad_voxel"])))
+        return out
 
     def state_info(self, info: int, typ: int) -> float:
         v = C.c_float()

@@ -27,6 +27,7 @@
 #include "vx_material.hpp"
 #include "vx_lattice.cuh"
 #include "vx_collide.cuh"
+#include "vx_mesh.cuh"
 
 using namespace vxd;
 
@@ -165,6 +166,14 @@ struct vx_sim {
     DevBuf<float> si_minmax; DevBuf<double> si_sum; DevBuf<double4> si_nominal; DevBuf<float> si_consts; DevBuf<unsigned char> si_buf;
     bool si_nominal_ok = false, si_consts_ok = false, si_pressure_ok = false;
     DevBuf<int> si_vlinks; DevBuf<float> si_ratio; DevBuf<float2> si_en;
+    // surface mesh (vx_mesh.inl): topology tables built by vx_mesh_build, float buffers refreshed by vx_mesh_update
+    struct Mesh {
+        bool built = false; int n_vert = 0, n_quad = 0;
+        DevBuf<int> vert_vox, quads, quad_vox; DevBuf<float> vertices, normals, colors, strain, max_strain, eps_fail, eps_yield, mat_rgb, vals;
+        std::vector<float> rgb_host;
+        void release() { vert_vox.release(); quads.release(); quad_vox.release(); vertices.release(); normals.release(); colors.release(); strain.release();
+                         max_strain.release(); eps_fail.release(); eps_yield.release(); mat_rgb.release(); vals.release(); built = false; n_vert = n_quad = 0; }
+    } mesh;
 
     bool uni = false; DevVoxMat vm0{}; DevLinkMat lm0{};          // single-material model: rows passed by value
     cudaGraphExec_t graph = nullptr; int graph_kernels = 0;      // general mode
@@ -1030,7 +1039,7 @@ void vx_destroy(vx_sim* s)
     s->c_pair_force.release(); s->c_counters.release(); s->c_deg.release(); s->c_ref_start.release(); s->c_ref_fill.release(); s->c_refs.release();
     if (s->counters_host) cudaFreeHost(s->counters_host);
     s->si_minmax.release(); s->si_sum.release(); s->si_nominal.release(); s->si_consts.release(); s->si_buf.release();
-    s->si_vlinks.release(); s->si_ratio.release(); s->si_en.release();
+    s->si_vlinks.release(); s->si_ratio.release(); s->si_en.release(); s->mesh.release();
     s->ext_idx.release(); s->ext_vox_dev.release(); s->vox_e2i_dev.release(); s->link_e2i_dev.release(); s->member_dev.release();
     s->pstrain.release(); s->slots.release(); s->slot_strain.release();
     s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release(); s->lstrain.release();
@@ -1270,7 +1279,7 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     s->nx = (int)ext3[0]; s->ny = (int)ext3[1]; s->nz = (int)ext3[2];
     if (packed) { s->nx *= s->pack[0]; s->ny *= s->pack[1]; s->nz *= s->pack[2]; }
     s->link_owner.release(); s->link_axis_dev.release();
-    s->si_nominal_ok = false; s->si_consts_ok = false; s->si_pressure_ok = false;
+    s->si_nominal_ok = false; s->si_consts_ok = false; s->si_pressure_ok = false; s->mesh.built = false;
 
     for (int i = 0; i < L; i++) {
         int id = link_material(s, s->vmat_id[s->lk_vn[i]], s->vmat_id[s->lk_vp[i]]);
@@ -1753,7 +1762,32 @@ static int gather_link_field(vx_sim* s, int what, void* dst)
     return VX_OK;
 }
 
-int vx_state_info(vx_sim* s, int info, int type, float* out)
+// per voxel (caller order) the caller index of its link in each of the six directions, the strain ratio of every link and
+// {E, nu} of every voxel: shared by the pressure reduction and the surface mesh
+static int ensure_vlinks(vx_sim* s)
+{
+    if (s->si_pressure_ok) return VX_OK;
+    const size_t nu = (size_t)s->N_user;
+    std::vector<int> vl(6 * std::max<size_t>(nu, 1), -1); std::vector<float> ratio(std::max(s->L, 1)); std::vector<float2> en(std::max<size_t>(nu, 1));
+    for (int l = 0; l < s->L; l++) {
+        vl[(size_t)(2 * s->lk_axis[l]) * nu + s->lk_vn[l]] = l;            // +axis slot of the negative-end voxel
+        vl[(size_t)(2 * s->lk_axis[l] + 1) * nu + s->lk_vp[l]] = l;        // -axis slot of the positive-end voxel
+        ratio[l] = s->mats[s->vmat_id[s->lk_vp[l]]].E / s->mats[s->vmat_id[s->lk_vn[l]]].E;
+    }
+    for (size_t v = 0; v < nu; v++) en[v] = make_float2(s->mats[s->vmat_id[v]].E, s->mats[s->vmat_id[v]].nu);
+    CK(s->si_vlinks.alloc(vl.size())); CK(s->si_ratio.alloc(ratio.size())); CK(s->si_en.alloc(en.size()));
+    CK(cudaMemcpy(s->si_vlinks.p, vl.data(), vl.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->si_ratio.p, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->si_en.p, en.data(), en.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    s->si_pressure_ok = true;
+    return VX_OK;
+}
+
+static int state_info_impl(vx_sim* s, int info, int type, float* out, float* vals);
+int vx_state_info(vx_sim* s, int info, int type, float* out) { return state_info_impl(s, info, type, out, nullptr); }
+
+// vals (device, optional): the value of every element -- voxels in internal order (pressure: caller order), links in caller order
+static int state_info_impl(vx_sim* s, int info, int type, float* out, float* vals)
 {
     if (!s || !out || info < 0 || info > SI_MASS || type < 0 || type > SI_AVERAGE) return VX_ERR_ARG;
     *out = 0.0f;
@@ -1768,25 +1802,11 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
     CK(cudaMemsetAsync(s->si_sum.p, 0, sizeof(double), s->stream));
     const int grid = std::min(blocks_for(count, 256), 148 * 8);
     if (info == SI_PRESSURE) {
-        if (!s->si_pressure_ok) {                                  // per-voxel link table, strain ratios, {E, nu}: caller order
-            const size_t nu = (size_t)s->N_user;
-            std::vector<int> vl(6 * nu, -1); std::vector<float> ratio(std::max(s->L, 1)); std::vector<float2> en(nu);
-            for (int l = 0; l < s->L; l++) {
-                vl[(size_t)(2 * s->lk_axis[l]) * nu + s->lk_vn[l]] = l;            // +axis slot of the negative-end voxel
-                vl[(size_t)(2 * s->lk_axis[l] + 1) * nu + s->lk_vp[l]] = l;        // -axis slot of the positive-end voxel
-                ratio[l] = s->mats[s->vmat_id[s->lk_vp[l]]].E / s->mats[s->vmat_id[s->lk_vn[l]]].E;
-            }
-            for (size_t v = 0; v < nu; v++) en[v] = make_float2(s->mats[s->vmat_id[v]].E, s->mats[s->vmat_id[v]].nu);
-            CK(s->si_vlinks.alloc(vl.size())); CK(s->si_ratio.alloc(ratio.size())); CK(s->si_en.alloc(en.size()));
-            CK(cudaMemcpy(s->si_vlinks.p, vl.data(), vl.size() * sizeof(int), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(s->si_ratio.p, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(s->si_en.p, en.data(), en.size() * sizeof(float2), cudaMemcpyHostToDevice));
-            s->si_pressure_ok = true;
-        }
+        { int rc = ensure_vlinks(s); if (rc != VX_OK) return rc; }
         CK(s->si_buf.alloc((size_t)std::max(s->L, 1) * sizeof(float)));
         if (s->L) { int rc = gather_link_field(s, G_STRAIN, s->si_buf.p); if (rc != VX_OK) return rc; }
         k_state_pressure<<<grid, 256, 0, s->stream>>>(s->N_user, s->si_vlinks.p, (const float*)s->si_buf.p, s->si_ratio.p, s->si_en.p,
-                                                      s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
+                                                      s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p, vals);
         s->launches++;
     } else if (!link_info) {
         if (info == SI_DISPLACEMENT && !s->si_nominal_ok) {
@@ -1796,14 +1816,14 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
             CK(cudaMemcpy(s->si_nominal.p, nom.data(), (size_t)s->N * sizeof(double4), cudaMemcpyHostToDevice));
             s->si_nominal_ok = true;
         }
-        k_state_voxels<<<grid, 256, 0, s->stream>>>(s->frame(), info, s->si_nominal.p, s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
+        k_state_voxels<<<grid, 256, 0, s->stream>>>(s->frame(), info, s->si_nominal.p, s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p, vals);
         s->launches++;
     } else if (info != SI_STRAIN_ENERGY) {
         CK(s->si_buf.alloc((size_t)s->L * sizeof(float)));
         int rc = gather_link_field(s, info == SI_ENG_STRESS ? G_STRESS : G_STRAIN, s->si_buf.p);
         if (rc != VX_OK) return rc;
         k_state_links<<<grid, 256, 0, s->stream>>>(s->L, (const float*)s->si_buf.p, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                   s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
+                                                   s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p, vals);
         s->launches++;
     } else {
         if (!s->si_consts_ok) {                                    // a1, a2, b3 of every link's material (caller order)
@@ -1824,7 +1844,7 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
         if (rc == VX_OK) rc = gather_link_field(s, G_MOMENT_POS, mpos);
         if (rc != VX_OK) return rc;
         k_state_links<<<grid, 256, 0, s->stream>>>(s->L, nullptr, fneg, mneg, mpos, s->si_consts.p, s->si_consts.p + s->L, s->si_consts.p + 2 * (size_t)s->L,
-                                                   s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p);
+                                                   s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p, vals);
         s->launches++;
     }
     CK(cudaGetLastError());
@@ -1922,5 +1942,7 @@ const char* vx_kernel_name(const vx_sim* s)
     return tma ? "k_lattice_tma (fused link+voxel, 4x4x2 brick per warp, TMA staging, 1 launch per step)"
                : "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, cp.async staging, 1 launch per step)";
 }
+
+#include "vx_mesh.inl"
 
 } // extern "C"

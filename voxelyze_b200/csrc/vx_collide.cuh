@@ -291,7 +291,8 @@ __device__ __forceinline__ void si_block_reduce(StateAcc a, float* out_min, floa
 
 // voxel quantities; ijk_size = nominal position source: displacement needs the lattice index, passed as a
 // per-voxel nominal position array only when info == DISPLACEMENT
-__global__ void __launch_bounds__(256) k_state_voxels(Frame f, int info, const double4* nominal, float* out_min, float* out_max, double* out_sum)
+// vals (optional): the value of every voxel, internal order (the mesh colouring reads it)
+__global__ void __launch_bounds__(256) k_state_voxels(Frame f, int info, const double4* nominal, float* out_min, float* out_max, double* out_sum, float* vals = nullptr)
 {
     StateAcc a; a.mn = 3.402823466e38f; a.mx = -3.402823466e38f; a.sum = 0.0;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < f.n_vox; v += gridDim.x * blockDim.x) {
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(256) k_state_voxels(Frame f, int info, const d
         }
         else if (info == SI_ANGULAR_DISPLACEMENT) { double w = p0.w; val = (float)(2.0 * acos(w > 1 ? 1.0 : w)); }
         else if (info == SI_MASS) val = m.mass;
+        if (vals) vals[v] = val;
         a.mn = fminf(a.mn, val); a.mx = fmaxf(a.mx, val); a.sum += (double)val;
     }
     si_block_reduce(a, out_min, out_max, out_sum);
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(256) k_state_voxels(Frame f, int info, const d
 // vlinks[d * n + v]: caller index of the link of voxel v (caller order) in direction d or -1; strain: per-link axial strain;
 // ratio: CVX_Link::strainRatio (src/VX_Link.cpp:67); en: per voxel {E, nu}
 __global__ void __launch_bounds__(256) k_state_pressure(int n, const int* vlinks, const float* strain, const float* ratio, const float2* en,
-                                                        float* out_min, float* out_max, double* out_sum)
+                                                        float* out_min, float* out_max, double* out_sum, float* vals = nullptr)
 {
     StateAcc a; a.mn = 3.402823466e38f; a.mx = -3.402823466e38f; a.sum = 0.0;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
@@ -335,6 +337,7 @@ __global__ void __launch_bounds__(256) k_state_pressure(int n, const int* vlinks
         const float vol = (float)(s3[0] + s3[1] + s3[2]);
         const float2 m = en[v];
         const float val = -m.x * vol / (3 * (1 - 2 * m.y));
+        if (vals) vals[v] = val;
         a.mn = fminf(a.mn, val); a.mx = fmaxf(a.mx, val); a.sum += (double)val;
     }
     si_block_reduce(a, out_min, out_max, out_sum);
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(256) k_state_pressure(int n, const int* vlinks
 // link quantities from a flat value array produced by the gather kernels (strain / stress) or from
 // force+moment triples (strain energy, src/VX_Link.cpp:251-257)
 __global__ void __launch_bounds__(256) k_state_links(int n, const float* scalar, const double* fneg, const double* mneg, const double* mpos,
-                                                     const float* a1, const float* a2, const float* b3, float* out_min, float* out_max, double* out_sum)
+                                                     const float* a1, const float* a2, const float* b3, float* out_min, float* out_max, double* out_sum, float* vals = nullptr)
 {
     StateAcc a; a.mn = 3.402823466e38f; a.mx = -3.402823466e38f; a.sum = 0.0;
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(256) k_state_links(int n, const float* scalar,
             const double fx = fneg[3 * l], nx = mneg[3 * l], ny = mneg[3 * l + 1], nz = mneg[3 * l + 2], py = mpos[3 * l + 1], pz = mpos[3 * l + 2];
             val = fx * fx / (2.0f * a1[l]) + nx * nx / (2.0 * a2[l]) + (nz * nz - nz * pz + pz * pz) / (3.0 * b3[l]) + (ny * ny - ny * py + py * py) / (3.0 * b3[l]);
         }
+        if (vals) vals[l] = val;
         a.mn = fminf(a.mn, val); a.mx = fmaxf(a.mx, val); a.sum += (double)val;
     }
     si_block_reduce(a, out_min, out_max, out_sum);

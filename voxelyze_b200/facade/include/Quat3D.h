@@ -6,6 +6,8 @@
 #ifndef VXB200_QUAT3D_H
 #define VXB200_QUAT3D_H
 
+#include <math.h>      // like the reference (include/Vec3D.h:17-18): callers rely on the global abs(double) / sqrt overloads it brings
+#include <float.h>
 #include <cmath>
 #include "Vec3D.h"
 

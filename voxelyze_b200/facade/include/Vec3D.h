@@ -7,6 +7,8 @@
 #ifndef VXB200_VEC3D_H
 #define VXB200_VEC3D_H
 
+#include <math.h>      // like the reference (include/Vec3D.h:17-18): callers rely on the global abs(double) / sqrt overloads it brings
+#include <float.h>
 #include <cmath>
 
 #define vec3_X 0

@@ -16,6 +16,7 @@
 
 #include <vector>
 #include <list>
+#include <algorithm>
 #include <map>
 #include <unordered_map>
 #include <cstdint>
