@@ -92,7 +92,8 @@ def test_lattice_path_is_selected_for_full_boxes(product):
     ell = [[i, 0, 0] for i in range(5)] + [[0, j, 0] for j in range(1, 5)]
     sparse = scenarios.Scenario("ell", 0.001, [Material()], np.array(ell, np.int32), np.zeros(len(ell), np.uint16))
     assert scenarios.build(product, sparse).active_path() == 1
-    assert scenarios.build(product, cases.BY_NAME["poisson_block"].make()).active_path() == 1  # nu != 0
+    assert scenarios.build(product, cases.BY_NAME["poisson_block"].make()).active_path() == 2  # nu != 0: fused too (k_lattice_tma<.., POISSON>)
+    assert scenarios.build(product, cases.BY_NAME["poisson_mixed_bilinear"].make()).active_path() == 2
 
 
 def test_fused_and_general_paths_agree_bitwise(product):
@@ -387,6 +388,32 @@ def test_peer_memory_halo_steps_match_whole_steps_bitwise(product):
     assert parity.bit_equal(got, whole.download("pos"))
 
 
+def test_any_scenario_runs_as_peer_memory_slabs_bitwise(product):
+    """SlabRunner.from_scenario on the fused path with the in-kernel halo push: two materials with CTE, gravity, floor, a fixed
+    face, forced voxels, a prescribed displacement, per-step ambient temperature (applied by the fused kernel on every slab) --
+    three slabs of one process on one GPU against the unsplit run, bit for bit."""
+    from voxelyze_b200 import slab
+    from test_slab_gloo import _general_scenario
+    sc = _general_scenario()
+    whole = scenarios.build(product, sc); dt = whole.recommended_dt()
+    runs = [slab.SlabRunner.from_scenario(product, sc, r, 3) for r in range(3)]
+    assert all(r.sim.active_path() == 2 for r in runs) and whole.active_path() == 2
+    slab.SlabRunner.connect_local(runs)
+    for r in runs:
+        r.exchange()                                     # initial temperature of the ghosts
+    for k in range(120):
+        t = 3.0 * np.sin(k / 10.0)
+        whole.set_temperature_all(t)
+        assert whole.step(dt, 1) is None
+        for r in runs:
+            r.set_temperature_all(t)
+            assert r.step(dt, 1) is None
+    index = np.concatenate([r.scenario_index[(r.z0 - r.lo) * r.plane:(r.z1 - r.lo) * r.plane] for r in runs])
+    for f in ("pos", "orient", "linmom", "angmom", "temp", "voxflags"):
+        got = np.concatenate([r.owned_state(f) for r in runs])
+        assert parity.bit_equal(got, whole.download(f)[index]), f
+
+
 @pytest.mark.parametrize("case", ["cantilever", "plates", "robots"])
 def test_checkpoint_resume_is_bit_identical(product, tmp_path, case):
     """vx_save_state / vx_load_state: stop, restore into a freshly built handle, continue == never stopped.
@@ -529,8 +556,9 @@ def test_collisions_on_the_fused_path_match_the_general_path_bitwise(product):
 
 def test_poissons_ratio_switched_on_mid_run_keeps_the_state(product, oracle):
     """The reference lets a caller change Poisson's ratio at any time (src/VX_Link.cpp:160-166 'catches when we disable
-    poissons mid-simulation').  A model on the fused layout moves to the general layout when nu becomes non-zero; voxel and
-    link state, time and previousDt go on, and later calls (gravity, more steps) keep working."""
+    poissons mid-simulation').  A model on the fused layout stays there: its per-voxel Poisson strains are created from the
+    current link strains when nu becomes non-zero; voxel and link state, time and previousDt go on, and later calls (gravity,
+    more steps) keep working."""
     import copy
 
     def run(lib):
@@ -546,7 +574,7 @@ def test_poissons_ratio_switched_on_mid_run_keeps_the_state(product, oracle):
         return s, sc, dt, dt2
 
     (g, sc, dtg, dtg2), (o, _, dto, dto2) = run(product), run(oracle)
-    assert g.active_path() == 1 and dtg == dto
+    assert g.active_path() == 2 and dtg == dto
     assert abs(dtg2 - dto2) <= 1e-6 * dto2
     err = parity.rel_errors(parity.snapshot(g), parity.snapshot(o), sc)
     assert err["pos"] <= 1e-6 and err["orient"] <= 1e-6, err

@@ -58,3 +58,63 @@ def test_two_slabs_equal_unsplit_run_bitwise(built, tmp_path, world):
     for f in ("pos", "orient", "linmom"):
         stitched = np.concatenate([p[f] for p in parts])
         assert np.array_equal(stitched, whole.download(f)), f
+
+
+def _worker_scenario(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r = slab.SlabRunner.from_scenario(capi.load_oracle(), _general_scenario(), rank, world, host_exchange=True)
+    dt = r.recommended_dt()
+    div = None
+    for k in range(90):
+        r.set_temperature_all(3.0 * np.sin(k / 10.0))
+        div = r.step(dt, 1, check_divergence=True) if div is None else div
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), pos=r.owned_state("pos"), orient=r.owned_state("orient"), temp=r.owned_state("temp"),
+             index=r.scenario_index[(r.z0 - r.lo) * r.plane:(r.z1 - r.lo) * r.plane], dt=dt, div=-1 if div is None else div)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _general_scenario():
+    """Two materials with different CTE, gravity + floor, a fixed face, forced voxels and a prescribed displacement, lattice
+    indices that do not start at zero, setVoxel order NOT plane-major: everything from_scenario has to carry."""
+    from voxelyze_b200.capi import Material, DOF_ALL
+    ijk = scenarios.box_ijk(5, 3, 9, origin=(2, -1, 1))
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(ijk))
+    ijk = ijk[perm]
+    mats = [Material(E=1e6, rho=1e3, cte=0.01, zeta_global=0.02, mu_static=1.0, mu_kinetic=0.5), Material(E=3e6, rho=2e3, cte=-0.005, zeta_global=0.02)]
+    mat = ((ijk[:, 0] + ijk[:, 2]) & 1).astype(np.uint16)
+    sc = scenarios.Scenario("slab_general", 0.005, mats, ijk, mat, gravity=0.3, floor=True, temperature=1.5)
+    fixed = np.nonzero(ijk[:, 0] == 2)[0]
+    load = np.nonzero(ijk[:, 0] == 6)[0]
+    moved = np.nonzero((ijk[:, 0] == 4) & (ijk[:, 1] == 0) & (ijk[:, 2] == 5))[0]
+    sc.ext_voxel = np.concatenate([fixed, load, moved]).astype(np.int32)
+    sc.ext_dof = np.concatenate([np.full(len(fixed), DOF_ALL), np.zeros(len(load)), np.full(len(moved), 0x07)]).astype(np.uint8)
+    f = np.zeros((len(sc.ext_voxel), 3), np.float32); f[len(fixed):len(fixed) + len(load)] = [0.0, 0.002, -0.004]
+    t = np.zeros((len(sc.ext_voxel), 3), np.float64); t[-len(moved):] = [0.0, 0.0, 1e-4]
+    sc.ext_force, sc.ext_translation = f, t
+    return sc
+
+
+def test_any_scenario_splits_into_slabs_bitwise(built, tmp_path):
+    """SlabRunner.from_scenario: materials, externals, gravity, floor, initial and per-step temperature of an arbitrary full
+    box, three slabs over gloo, against the unsplit run of the same calls."""
+    import torch.multiprocessing as mp
+    world = 3
+    mp.spawn(_worker_scenario, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
+    sc = _general_scenario()
+    whole = scenarios.build(capi.load_oracle(), sc)
+    dt = whole.recommended_dt()
+    assert np.float32(dt) == np.float32(parts[0]["dt"])
+    for k in range(90):
+        whole.set_temperature_all(3.0 * np.sin(k / 10.0))
+        assert whole.step(dt, 1) is None
+    index = np.concatenate([p["index"] for p in parts])
+    assert sorted(index.tolist()) == list(range(sc.n_voxels)) and all(int(p["div"]) == -1 for p in parts)
+    for f in ("pos", "orient", "temp"):
+        stitched = np.concatenate([p[f] for p in parts])
+        assert np.array_equal(stitched, whole.download(f)[index]), f

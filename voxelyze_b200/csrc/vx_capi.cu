@@ -120,6 +120,8 @@ struct vx_sim {
     };
     std::vector<PeerLink> peers;
     bool wb_opted_in = false, capturing = false;
+    bool launch_failed = false;                     // a step kernel could not be launched at all (reported by the call that queued it)
+    bool state_ready = false;                       // the device arrays hold a valid state (false while vx_set_voxels rebuilds them)
     DevBuf<unsigned char> tmaps;        // CUtensorMap descriptors of the lattice arrays (k_lattice_tma), rebuilt with the arrays
     bool push_in_kernel = false;        // set around the boundary launches of vx_slab_step
     DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
@@ -136,6 +138,7 @@ struct vx_sim {
     // lattice link records, one allocation of VX_REC_PARTS x N sixteen-byte parts per generation: for axis a the
     // parts 4a..4a+2 are the three double2 of the record, part 4a+3 its float4 {strain, maxStrain, strainOffset, stress}
     DevBuf<double2> rec[2];
+    DevBuf<float4> ps[2];                               // lattice mode with Poisson materials: CVX_Voxel::pStrain per generation
     cudaError_t alloc_pose(int g, size_t n1) { cudaError_t e = pose0[g].alloc(2 * n1); pose1[g].p = e == cudaSuccess ? pose0[g].p + n1 : nullptr; return e; }
     void release_pose(int g) { pose0[g].release(); pose1[g].p = nullptr; }
     DevBuf<uint16_t> pair_lmat; DevBuf<int> link_owner; DevBuf<unsigned char> link_axis_dev;
@@ -187,7 +190,7 @@ struct vx_sim {
         const int g = lattice ? (gen_view >= 0 ? gen_view : gen) : 0;
         f.n_vox = N; f.n_link = L;
         f.pose0 = pose0[g].p; f.pose1 = pose1[g].p; f.mom0 = mom0[g].p; f.mom1 = mom1[g].p;
-        f.ext_idx = ext_idx.p; f.pstrain = lattice ? nullptr : pstrain.p; f.slots = slots.p; f.slot_strain = slot_strain.p;
+        f.ext_idx = ext_idx.p; f.pstrain = lattice ? ps[g].p : pstrain.p; f.slots = slots.p; f.slot_strain = slot_strain.p;
         f.lends = lends.p; f.lmeta = lmeta.p; f.lstA = lstA.p; f.lstB = lstB.p; f.lstC = lstC.p; f.lstrain = lstrain.p;
         f.vmat = vmat_dev.p; f.lmat = lmat_dev.p; f.curve_e = curve_e.p; f.curve_s = curve_s.p;
         f.ext = ext_dev.p; f.params = params.p;
@@ -233,6 +236,7 @@ struct vx_sim {
         f.col_slot = (collisions && col_tables) ? c_slot.p : nullptr;
         f.col_start = c_ref_start.p; f.col_ref = c_refs.p; f.col_force = c_pair_force.p;
         f.amb_set = 0; f.amb = 0.f;
+        f.c_ps = any_poisson ? ps[g].p : nullptr; f.n_ps = any_poisson ? ps[g ^ 1].p : nullptr;
         f.push_z[0] = f.push_z[1] = -1;
         if (push_in_kernel) {
             for (size_t k = 0; k < peers.size() && k < 2; k++) {
@@ -318,7 +322,6 @@ static int upload_tables(vx_sim* s)
         if (m.nu != 0.0f) s->any_poisson = true;
         pair[(size_t)e.a * nm + e.b] = pair[(size_t)e.b * nm + e.a] = (uint16_t)i;
     }
-    if (s->lattice && s->any_poisson) return fail(s, VX_ERR_UNSUPPORTED, "internal: Poisson material on the fused layout (vx_set_materials re-lays the model out first)");
     CK(s->vmat_dev.alloc(std::max<size_t>(vm.size(), 1)));
     CK(s->lmat_dev.alloc(std::max<size_t>(lm.size(), 1)));
     CK(s->curve_e.alloc(std::max<size_t>(ce.size(), 2)));
@@ -397,10 +400,27 @@ static int upload_initial_state(vx_sim* s, float temp)
         for (int i = 0; i < L; i++) lm[i] = s->lk_mat[i] | LM_SMALL_ANGLE;    // CVX_Link::reset, src/VX_Link.cpp:61-75
         CK(cudaMemcpy(s->lmeta.p, lm.data(), (size_t)L * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    for (int g = 0; g < 2; g++) if (s->lattice && s->ps[g].p && N) CK(cudaMemset(s->ps[g].p, 0, (size_t)N * sizeof(float4)));   // zero strains: zero pStrain
     DevParams p{}; p.col_stale = 1;
     CK(cudaMemcpy(s->params.p, &p, sizeof(p), cudaMemcpyHostToDevice));
     s->time_host = 0.f;
     s->drop_graph();
+    s->state_ready = true;
+    return VX_OK;
+}
+
+// lattice mode with Poisson materials: (re)computes CVX_Voxel::pStrain of the current generation from the link strains in
+// its records -- after Poisson's ratio was switched on, after externals or link state were replaced
+static int refresh_lattice_ps(vx_sim* s)
+{
+    if (!s->lattice || !s->any_poisson || s->N == 0 || !s->state_ready) return VX_OK;
+    CK(cudaSetDevice(s->device));
+    const size_t n1 = (size_t)s->N;
+    for (int g = 0; g < 2; g++)
+        if (!s->ps[g].p) { CK(s->ps[g].alloc(n1)); CK(cudaMemsetAsync(s->ps[g].p, 0, n1 * sizeof(float4), s->stream)); }
+    k_lattice_pstrain_init<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->lat_frame(s->gen), s->ps[s->gen].p); s->launches++;
+    CK(cudaGetLastError());
+    s->drop_graph();                                    // frames now carry the pStrain arrays
     return VX_OK;
 }
 
@@ -442,7 +462,7 @@ static int upload_externals(vx_sim* s)
     }
     CK(cudaGetLastError());
     s->drop_graph();      // the ext table pointer may have moved
-    return VX_OK;
+    return refresh_lattice_ps(s);                       // Poisson: which axes count as "in tension" depends on the externals
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,12 +488,12 @@ static void launch_links(vx_sim* s, const Frame& f)
     }
 }
 
-static void launch_recommended_dt(vx_sim* s)
+static void launch_recommended_dt(vx_sim* s, int gen = -1)
 {
     cudaMemsetAsync(s->freq2.p, 0, sizeof(unsigned int), s->stream);
     if (s->lattice) {
         int g = std::min(blocks_for(s->N, 256), 148 * 8);
-        if (s->L > 0) k_lattice_max_freq<<<g, 256, 0, s->stream>>>(s->lat_frame(s->gen), s->freq2.p);
+        if (s->L > 0) k_lattice_max_freq<<<g, 256, 0, s->stream>>>(s->lat_frame(gen >= 0 ? gen : s->gen), s->freq2.p);
         else k_max_freq_voxels<<<g, 256, 0, s->stream>>>(s->frame(), s->freq2.p);
     } else if (s->L > 0) {
         int g = std::min(blocks_for(s->L, 256), 148 * 8);
@@ -760,6 +780,7 @@ static void lattice_opt_in(vx_sim* s)
     cudaFuncSetAttribute(k_lattice_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
     cudaFuncSetAttribute(k_lattice_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
     cudaFuncSetAttribute(k_lattice_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
     s->wb_opted_in = true;
 }
 
@@ -775,7 +796,7 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
     // staging: TMA bulk tensor copies (7, and what 0 picks on large lattices) or per-lane cp.async (5, and what 0 picks for
     // ensembles of small boxes, where whole-box copies fetch too much padding: 1.15 against 1.19 ms on 4096 robots of 10^3)
-    const bool want_tma = s->path == 7 || (s->path != 5 && grouped);
+    const bool want_tma = s->path == 7 || (s->path != 5 && grouped) || s->any_poisson;     // Poisson coupling lives in the TMA-staged kernel only
     // (tensor maps are built outside stream capture: ensure_lattice_graph launches nothing before they exist)
     const bool tma = want_tma && (s->tmaps.p || (!s->capturing && build_tensor_maps(s) == VX_OK));
     lattice_opt_in(s);
@@ -792,13 +813,16 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
             const bool g3 = grouped && VX_WB_WARPS == 8 && nby <= 65535 && zdim <= 65535;
             const dim3 gr = g3 ? dim3((unsigned)nbx, (unsigned)nby, (unsigned)zdim) : dim3((unsigned)(((long long)bx * by * (ngz >= 0 ? 2 * ngz : bz) * s->lat_members + VX_WB_WARPS - 1) / VX_WB_WARPS));
             const int kx = g3 ? nbx : bx, ky = g3 ? nby : by, kz = g3 ? nbz : (ngz >= 0 ? 2 * ngz : bz), koff = g3 ? gz_off : 2 * gz_off, gr_ = g3 ? 1 : 0;
-            if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
+            if (s->any_poisson) k_lattice_tma<false, false, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
+            else if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
                 if (s->uni) k_lattice_tma<true, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
                 else k_lattice_tma<false, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
             } else {
                 if (s->uni) k_lattice_tma<true, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
                 else k_lattice_tma<false, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
             }
+        } else if (s->any_poisson) {
+            s->err = "Poisson materials on the fused layout need the TMA-staged kernel (tensor maps could not be built)"; s->launch_failed = true;
         } else {
             const dim3 gr((unsigned)grid);
             const int gr_ = grouped ? 1 : 0;
@@ -858,6 +882,7 @@ static int finish_lattice_call(vx_sim* s, int g_start, int launched, int* diverg
 {
     k_lattice_finish<<<1, 1, 0, s->stream>>>(s->params.p, (g_start + launched - 1) & 1); s->launches++;
     CK(cudaGetLastError());
+    if (s->launch_failed) { s->launch_failed = false; cudaStreamSynchronize(s->stream); return VX_ERR_UNSUPPORTED; }
     CK(cudaMemcpyAsync(s->params_host, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost, s->stream));
     if (s->collisions && s->col_tables) CK(cudaMemcpyAsync(s->counters_host, s->c_counters.p, CC_COUNT * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -896,15 +921,24 @@ static int finish_lattice_call(vx_sim* s, int g_start, int launched, int* diverg
 
 static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
 {
-    if (dt < 0) {                                   // nu = 0: the recommended step is a constant of the model
+    const bool per_step_dt = dt < 0 && s->any_poisson;      // with Poisson coupling the stable step depends on the state (src/VX_Link.cpp:259-267)
+    if (dt < 0 && !per_step_dt) {                   // nu = 0: the recommended step is a constant of the model
         int rc = vx_recommended_dt(s, &dt);
         if (rc != VX_OK) return rc;
         if (dt <= 0) return VX_OK;
     }
-    k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
+    k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, per_step_dt ? 0 : 1); s->launches++;
     collision_call_begin(s);
     const int g0 = s->gen;
     int done = 0;
+    if (per_step_dt) {
+        for (; done < n_steps; done++) {
+            launch_recommended_dt(s, (g0 + done) & 1);
+            k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++;
+            int rc = launch_lattice(s, (g0 + done) & 1, done == 0 ? 1 : 0); if (rc != VX_OK) return rc;
+        }
+        return finish_lattice_call(s, g0, n_steps, diverged_step);
+    }
     { int rc = launch_lattice(s, g0, 1); if (rc != VX_OK) return rc; }
     done++;
     while (n_steps - done >= GRAPH_STEPS) {
@@ -1031,7 +1065,7 @@ void vx_destroy(vx_sim* s)
     if (s->ev_comm) cudaEventDestroy(s->ev_comm);
     s->peer_flags.release(); s->tmaps.release();
     s->drop_graph();
-    for (int g = 0; g < 2; g++) { s->release_pose(g); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); }
+    for (int g = 0; g < 2; g++) { s->release_pose(g); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); s->ps[g].release(); }
     s->pair_lmat.release(); s->link_owner.release(); s->link_axis_dev.release();
     s->c_surf_vox.release(); s->c_surf_orig.release(); s->c_surf_member.release(); s->c_slot.release(); s->c_surf_ijk.release(); s->c_nearby.release();
     s->c_last_watch.release(); s->c_cell_count.release(); s->c_cell_start.release(); s->c_sorted.release(); s->c_cell.release();
@@ -1074,15 +1108,17 @@ int vx_set_materials(vx_sim* s, int n, const vx_material_desc* d)
     s->descs.assign(d, d + n);
     for (auto& x : s->descs) x.strain = x.stress = nullptr;
     s->d_eps.swap(ne); s->d_sig.swap(ns); s->mats.swap(nm);
-    // Poisson's ratio switched on for a model that runs on the fused layout (the reference allows toggling it at any time,
-    // src/VX_Link.cpp:160-166): the model moves to the general layout, every voxel and link keeps its state
-    bool poisson = false;
-    for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
-    if (s->N > 0 && s->lattice && poisson) {
-        if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_materials inside vx_step_begin .. vx_step_end");
-        return (s->time_host != 0.f || s->have_prev) ? relayout_keep_state(s) : relayout_fresh(s);
+    // Poisson's ratio may be switched on or off at any time (the reference allows it, src/VX_Link.cpp:160-166): on the fused
+    // layout the per-voxel pStrain arrays are created from the current link strains the first time it becomes non-zero
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_materials inside vx_step_begin .. vx_step_end");
+    int rc = upload_tables(s);
+    if (rc != VX_OK) return rc;
+    if (s->lattice && s->any_poisson && !s->vflags.empty()) {
+        bool ghosts = false;
+        for (uint32_t f : s->vflags) if ((f & VX_VF_GHOST) && !(f & VF_FILL)) ghosts = true;
+        if (ghosts) return fail(s, VX_ERR_UNSUPPORTED, "Poisson materials on a z-slab (halo voxels carry no Poisson strains)");
     }
-    return upload_tables(s);
+    return refresh_lattice_ps(s);
 }
 
 int vx_get_voxmat(const vx_sim* s, int i, vx_voxmat_row* o)
@@ -1115,9 +1151,7 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
 {
     if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_voxels inside vx_step_begin .. vx_step_end");
-    bool poisson = false;
-    for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
-    if (n == 0 || poisson || s->path == 1)
+    if (n == 0 || s->path == 1)
         return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
     int lo[3] = {32767, 32767, 32767}, hi[3] = {-32768, -32768, -32768}, members = 1;
     for (int i = 0; i < n; i++) {
@@ -1229,9 +1263,13 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     // one device lattice when that fills the 8 x 8 x 4 voxel tiles of the fused kernel better than one box per member
     // (4096 robots of 10^3: 4 x 4 x 256 robots = a 40 x 40 x 2560 lattice without a single idle lane, against 69 % lane
     // use for 10^3 boxes on their own).  Members never link: every link bit comes from a per-member neighbour lookup.
-    bool poisson = false;
+    bool poisson = false, halo = false;
     for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
-    s->lattice = n > 0 && cells == (long long)n && !poisson && s->path != 1;
+    if (flags) for (int i = 0; i < n && !halo; i++) halo = (flags[i] & VX_VF_GHOST) && !(flags[i] & VF_FILL);
+    // fused layout: a completely filled box; Poisson materials too (k_lattice_tma<.., POISSON>) unless the box is a z-slab
+    // with halo voxels, whose Poisson strains nobody exchanges
+    s->lattice = n > 0 && cells == (long long)n && !(poisson && halo) && s->path != 1;
+    s->state_ready = false;
     s->pack[0] = s->pack[1] = 1; s->pack[2] = s->n_members; s->lat_members = s->n_members;
     if (s->lattice && s->n_members > 1 && !getenv("VX_NO_PACK")) {
         auto up = [](long long v, long long q) { return (v + q - 1) / q * q; };
@@ -1293,6 +1331,7 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
         for (int g = 0; g < 2; g++) {
             CK(s->alloc_pose(g, n1)); CK(s->mom0[g].alloc(n1)); CK(s->mom1[g].alloc(n1));
             CK(s->rec[g].alloc(n1 * VX_REC_PARTS));
+            if (poisson) CK(s->ps[g].alloc(n1)); else s->ps[g].release();
         }
         s->slots.release(); s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release();
         s->lstrain.release(); s->pstrain.release(); s->slot_strain.release();
@@ -1300,7 +1339,7 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
         s->tmaps.release();                           // describe the old arrays
     } else {
         CK(s->alloc_pose(0, n1)); CK(s->mom0[0].alloc(n1)); CK(s->mom1[0].alloc(n1));
-        for (int g = 0; g < 2; g++) s->rec[g].release();
+        for (int g = 0; g < 2; g++) { s->rec[g].release(); s->ps[g].release(); }
         s->release_pose(1); s->mom0[1].release(); s->mom1[1].release();
         CK(s->slots.alloc(n1 * 36));
         CK(s->lends.alloc(l1)); CK(s->lmeta.alloc(l1)); CK(s->lstA.alloc(l1)); CK(s->lstB.alloc(l1)); CK(s->lstC.alloc(l1)); CK(s->lstrain.alloc(l1));

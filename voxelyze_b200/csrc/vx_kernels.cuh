@@ -194,6 +194,27 @@ __global__ void __launch_bounds__(128) k_voxel(Frame f, int floor_on, int collis
     f.mom1[v] = make_double2(s.ang.y, s.ang.z);
 }
 
+// CVX_Voxel::strain(true) (src/VX_Voxel.cpp:300-343) from the sums r[] and counts nb[] of the per-end axial strains of the
+// voxel's links along each axis
+__device__ __forceinline__ float4 voxel_pstrain(const DevVoxMat& vm, const DevExt* ext, float r[3], const int nb[3])
+{
+    const uint32_t dof = ext ? ext->dof : 0u;
+    bool tension[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (nb[i] == 2) r[i] *= 0.5f;
+        tension[i] = (nb[i] == 2) || (ext && nb[i] == 1 && ((dof & (1u << i)) || ext->force[i] != 0));
+    }
+    if (!(tension[0] && tension[1] && tension[2])) {
+        float add = 0;
+        for (int i = 0; i < 3; i++) if (tension[i]) add += r[i];
+        // powf of the reference, evaluated in double and rounded once (glibc powf is < 1 ulp)
+        float value = (float)pow((double)(1.0f + add), (double)(-vm.nu)) - 1.0f;
+        for (int i = 0; i < 3; i++) if (!tension[i]) r[i] = value;
+    }
+    return make_float4(r[0], r[1], r[2], 0.0f);
+}
+
 // CVX_Voxel::strain(true) for voxels whose cache is stale (src/VX_Voxel.cpp:300-343).
 // The reference fills this cache lazily inside the link loop; every link strain it reads is
 // still the previous step's at that point, so a pre-pass over stale voxels is equivalent.
@@ -214,21 +235,7 @@ __global__ void __launch_bounds__(128) k_pstrain(Frame f)
     for (int k = 0; k < 6; k++)
         if (mask & (1u << k)) { r[k >> 1] += f.slot_strain[(size_t)k * nv + v]; nb[k >> 1]++; }
     const DevExt* ext = (bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
-    uint32_t dof = ext ? ext->dof : 0u;
-    bool tension[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        if (nb[i] == 2) r[i] *= 0.5f;
-        tension[i] = (nb[i] == 2) || (ext && nb[i] == 1 && ((dof & (1u << i)) || ext->force[i] != 0));
-    }
-    if (!(tension[0] && tension[1] && tension[2])) {
-        float add = 0;
-        for (int i = 0; i < 3; i++) if (tension[i]) add += r[i];
-        // powf of the reference, evaluated in double and rounded once (glibc powf is < 1 ulp)
-        float value = (float)pow((double)(1.0f + add), (double)(-vm.nu)) - 1.0f;
-        for (int i = 0; i < 3; i++) if (!tension[i]) r[i] = value;
-    }
-    f.pstrain[v] = make_float4(r[0], r[1], r[2], 0.0f);
+    f.pstrain[v] = voxel_pstrain(vm, ext, r, nb);
     f.pose1[v].w = meta_pack(meta_temp(w), bits & ~VM_PSTRAIN_STALE);
 }
 

@@ -58,6 +58,9 @@ struct LatFrame {
     // CVoxelyze::setAmbientTemperature(t, true) applied by the step itself: every voxel reads temperature `amb` instead of
     // its stored one in this launch and carries it into the new generation (no separate pass over the voxels)
     int amb_set; float amb;
+    // Poisson coupling (nu != 0, k_lattice_tma<.., POISSON>): CVX_Voxel::pStrain of every voxel as of the state the step reads
+    // (= computed from the link strains of the previous step), double-buffered like the voxel state
+    const float4* c_ps; float4* n_ps;
 };
 
 __device__ __forceinline__ void lat_decode(double2 a, double2 b, double2 c, float4 s, uint32_t lflags, LinkState& st)
@@ -84,8 +87,11 @@ template <bool UNI>
 __device__ __forceinline__ void lat_eval_link_rec(const LatFrame& f, int axis, uint32_t owner_bits,
                                                   double2 ra, double2 rb, double2 rc, float4 rs,
                                                   double4 n0, double4 n1, double4 p0, double4 p1, float prev_dt,
-                                                  LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP, float damp_uni = -1.0f)
+                                                  LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP, float damp_uni = -1.0f,
+                                                  const float4* psn = nullptr, const float4* psp = nullptr, float* end_strain = nullptr)
 {
+    // psn/psp: Poisson strains of the two end voxels (nu != 0 models); end_strain[0/1]: axial strain of the half of the link
+    // inside the negative / positive end voxel (CVX_Link::axialStrain(bool), src/VX_Link.cpp:121-124), input of the next pStrain
     // damp_uni: single-material models may pass 2*sqrtMass*zeta/previousDt computed once per kernel (same float division)
     const uint32_t hn = meta_hi(n1.w), hp = meta_hi(p1.w);
     const DevVoxMat& vmn = UNI ? f.vm0 : f.vmat[hn & VM_MAT_MASK];
@@ -95,15 +101,24 @@ __device__ __forceinline__ void lat_eval_link_rec(const LatFrame& f, int axis, u
     // CVX_Link::updateRestLength (src/VX_Link.cpp:137-140)
     const float tn = f.amb_set ? f.amb : meta_temp(n1.w), tp = f.amb_set ? f.amb : meta_temp(p1.w);
     double rest = 0.5 * (vmn.size[axis] * (1 + tn * vmn.cte) + vmp.size[axis] * (1 + tp * vmp.cte));
-    float t_area = 0.5f * (vmn.nom_f * vmn.nom_f + vmp.nom_f * vmp.nom_f);
+    float t_area, t_sum = 0.0f;
+    if (psn) {                                                              // CVX_Link::updateTransverseInfo, src/VX_Link.cpp:142-147
+        t_area = 0.5f * (transverse_area(vmn, axis, *psn) + transverse_area(vmp, axis, *psp));
+        t_sum = 0.5f * (transverse_strain_sum(vmn, axis, *psn) + transverse_strain_sum(vmp, axis, *psp));
+    } else t_area = 0.5f * (vmn.nom_f * vmn.nom_f + vmp.nom_f * vmp.nom_f);
     float damp_n, damp_p;
     if (UNI && damp_uni >= 0.0f) damp_n = damp_p = damp_uni;
     else { damp_n = vmn.two_sqrtm_zeta / prev_dt; damp_p = vmp.two_sqrtm_zeta / prev_dt; }
     q4 on, op;
     on.w = n0.w; on.x = n1.x; on.y = n1.y; on.z = n1.z;
     op.w = p0.w; op.x = p1.x; op.y = p1.y; op.z = p1.z;
-    link_forces(axis, mk3(n0.x, n0.y, n0.z), on, mk3(p0.x, p0.y, p0.z), op, rest, t_area, 0.0f,
+    link_forces(axis, mk3(n0.x, n0.y, n0.z), on, mk3(p0.x, p0.y, p0.z), op, rest, t_area, t_sum,
                 damp_n, damp_p, lm, f.curve_e, f.curve_s, st, fN, mN, fP, mP);
+    if (end_strain) {
+        const float ratio = vmp.E / vmn.E;
+        end_strain[0] = 2.0f * st.strain / (1.0f + ratio);
+        end_strain[1] = 2.0f * st.strain * ratio / (1.0f + ratio);
+    }
 }
 template <bool UNI>
 __device__ __forceinline__ void lat_eval_link(const LatFrame& f, int axis, int owner, uint32_t owner_bits,
@@ -112,6 +127,11 @@ __device__ __forceinline__ void lat_eval_link(const LatFrame& f, int axis, int o
 {
     double2 ra = __ldg(f.c_rec[axis][0] + owner), rb = __ldg(f.c_rec[axis][1] + owner), rc = __ldg(f.c_rec[axis][2] + owner);
     float4 rs = __ldg(f.c_recf[axis] + owner);
+    if (f.c_ps) {                                       // Poisson models: the strains of both end voxels as the step saw them
+        const float4 psn = __ldg(f.c_ps + owner), psp = __ldg(f.c_ps + owner + (axis == 0 ? 1 : (axis == 1 ? f.nx : f.nxy)));
+        lat_eval_link_rec<UNI>(f, axis, owner_bits, ra, rb, rc, rs, n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP, -1.0f, &psn, &psp);
+        return;
+    }
     lat_eval_link_rec<UNI>(f, axis, owner_bits, ra, rb, rc, rs, n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP);
 }
 
@@ -228,12 +248,43 @@ __global__ void __launch_bounds__(256) k_lattice_max_freq(LatFrame f, unsigned i
             const DevVoxMat& vmp = f.vmat[pb & VM_MAT_MASK];
             const DevLinkMat& lm = f.lmat[f.pair_lmat[(bits & VM_MAT_MASK) * f.n_mat + (pb & VM_MAT_MASK)]];
             float m1 = vmn.mass, m2 = vmp.mass;
-            float f2 = lm.a1 / (m1 < m2 ? m1 : m2);
+            float stiff = lm.a1;
+            if (lm.nu != 0.0f && f.c_ps) {                // CVX_Link::axialStiffness with Poisson coupling, src/VX_Link.cpp:259-267
+                const double w = f.c_pose1[v].w, wp = f.c_pose1[v + stride].w;
+                const double rest = 0.5 * (vmn.size[axis] * (1 + meta_temp(w) * vmn.cte) + vmp.size[axis] * (1 + meta_temp(wp) * vmp.cte));
+                const float area = 0.5f * (transverse_area(vmn, axis, f.c_ps[v]) + transverse_area(vmp, axis, f.c_ps[v + stride]));
+                stiff = (float)(lm.e_hat * area / ((f.c_recf[axis][v].x + 1) * rest));
+            }
+            float f2 = stiff / (m1 < m2 ? m1 : m2);
             if (f2 > best) best = f2;
         }
     }
     for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
     if ((threadIdx.x & 31) == 0 && best > 0.0f) atomicMax(out, __float_as_uint(best));
+}
+
+// CVX_Voxel::pStrain of every voxel from the link strains currently in the records of generation `f.c_*` (Poisson models:
+// after a reset, after Poisson's ratio was switched on, after externals changed); written to `out`
+__global__ void __launch_bounds__(128) k_lattice_pstrain_init(LatFrame f, float4* out)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= f.n_vox) return;
+    const uint32_t bits = meta_hi(f.c_pose1[v].w);
+    const uint32_t mask = (bits >> VM_LINK_SHIFT) & 0x3Fu;
+    const DevVoxMat& vm = f.vmat[bits & VM_MAT_MASK];
+    float r[3] = {0.f, 0.f, 0.f}; int nb[3] = {0, 0, 0};
+    for (int k = 0; k < 6; k++) {
+        if (!(mask & (1u << k))) continue;
+        const int axis = k >> 1, stride = axis == 0 ? 1 : (axis == 1 ? f.nx : f.nxy);
+        const int owner = (k & 1) ? v - stride : v, other = (k & 1) ? v - stride : v + stride;      // slot odd: this voxel is the positive end
+        const float strain = f.c_recf[axis][owner].x;
+        const float e_other = f.vmat[meta_hi(f.c_pose1[other].w) & VM_MAT_MASK].E;
+        const float ratio = (k & 1) ? vm.E / e_other : e_other / vm.E;                               // E_pos / E_neg
+        r[axis] += (k & 1) ? 2.0f * strain * ratio / (1.0f + ratio) : 2.0f * strain / (1.0f + ratio);
+        nb[axis]++;
+    }
+    const DevExt* ext = (bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
+    out[v] = voxel_pstrain(vm, ext, r, nb);
 }
 
 // =================================================================================================
@@ -568,7 +619,7 @@ __device__ __forceinline__ void tma_4d(uint32_t dst, const void* map, uint32_t b
 
 // Grid: grouped (large lattices) -> 3-D, one CTA per 2x2x2 group of bricks: blockIdx = (group x, group y, member * nbz + group layer);
 //       else (ensembles of small boxes) -> 1-D, eight consecutive bricks per CTA, bricks x-fastest, no padding.
-template <bool UNI, bool PUSH>
+template <bool UNI, bool PUSH, bool POISSON = false>
 __global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
 k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book, int grouped)
 {
@@ -640,6 +691,13 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     const bool has_voxel = x < f.nx && y < f.ny && z < f.nz;
     const int v = vbase + (min(z, f.nz - 1) * f.ny + min(y, f.ny - 1)) * f.nx + min(x, f.nx - 1);
 
+    // POISSON: the Poisson strains the step reads travel outside the staged boxes (plain loads, L2-resident neighbours): this
+    // lane's voxel now, partners outside the brick when their link is evaluated; pe[k] collects the per-end axial strain of
+    // the voxel's link in slot k for the pStrain of the next step
+    float4 ps_own = make_float4(0.f, 0.f, 0.f, 0.f);
+    float pe[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (POISSON && has_voxel) ps_own = __ldg(f.c_ps + v);
+
     auto load_pose = [&](int off0, int off1, int entry, double4& a, double4& c) {        // two 32-byte records of one voxel
         const uint4* q0 = reinterpret_cast<const uint4*>(wbase + off0 + entry * 32);
         const uint4* q1 = reinterpret_cast<const uint4*>(wbase + off1 + entry * 32);
@@ -661,9 +719,18 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     const uint32_t mask = has_voxel ? ((bits >> VM_LINK_SHIFT) & 0x3Fu) : 0u;
     uint32_t new_bits = bits;
     d3 hF = mk3(0.0, 0.0, 0.0), hM = hF;
+    float h_end[2] = {0.f, 0.f};
     // zero-filled (out of range) voxels carry no link bits; the z test keeps the next ensemble member's planes out
     const bool h_active = x0 + (h_tl & 3) < f.nx && y0 + ((h_tl >> 2) & 3) < f.ny && z0 + (h_tl >> 4) < f.nz &&
                           ((meta_of(h_tl) >> (VM_LINK_SHIFT + 2 * h_axis + 1)) & 1u);
+    float4 h_psp = make_float4(0.f, 0.f, 0.f, 0.f), h_psn = h_psp;
+    if (POISSON) {                                     // positive end: the in-brick voxel h_tl (another lane's ps_own); negative end: outside
+        h_psp = make_float4(__shfl_sync(0xffffffffu, ps_own.x, h_tl), __shfl_sync(0xffffffffu, ps_own.y, h_tl), __shfl_sync(0xffffffffu, ps_own.z, h_tl), 0.f);
+        if (h_active) {
+            const int h_stride = h_axis == 0 ? 1 : (h_axis == 1 ? f.nx : f.nxy);
+            h_psn = __ldg(f.c_ps + vbase + ((z0 + (h_tl >> 4)) * f.ny + y0 + ((h_tl >> 2) & 3)) * f.nx + x0 + (h_tl & 3) - h_stride);
+        }
+    }
     if (h_active) {
         double4 n0, n1, p0, p1;
         load_pose(h_pose, h_pose + h_face, 0, n0, n1);
@@ -676,11 +743,14 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                                make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
                                make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
                                make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
-                               n0, n1, p0, p1, prev_dt, st, fN, mN, hF, hM, damp_u);
+                               n0, n1, p0, p1, prev_dt, st, fN, mN, hF, hM, damp_u,
+                               POISSON ? &h_psn : nullptr, POISSON ? &h_psp : nullptr, POISSON ? h_end : nullptr);
     }
     __syncwarp();                          // every lane has read its round-H inputs: their space is re-used now
     double (*hslot)[32] = reinterpret_cast<double (*)[32]>(wbase + 9216);                 // [comp][entering link]
     if (h_active) { hslot[0][lane] = hF.x; hslot[1][lane] = hF.y; hslot[2][lane] = hF.z; hslot[3][lane] = hM.x; hslot[4][lane] = hM.y; hslot[5][lane] = hM.z; }
+    // POISSON: the entering link's strain at its positive end stays in a register of the lane that evaluated it (h_end[1], zero
+    // where there is no such link) and is fetched by shuffle when the voxel it enters adds its X- / Y- / Z- slot
     if (elect_one()) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const unsigned char* tm = tmaps + (size_t)parity * TM_COUNT * 128;
@@ -700,14 +770,28 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         const bool inside = a == 0 ? lx < VX_WB_X - 1 : (a == 1 ? ly < VX_WB_Y - 1 : lz < VX_WB_Z - 1);
         const bool first = a == 0 ? lx == 0 : (a == 1 ? ly == 0 : lz == 0);
         const int dl = a == 0 ? 1 : (a == 1 ? 4 : 16);
+#ifdef VX_ZERO_PARTNER_FORCE
         d3 fN = mk3(0.0, 0.0, 0.0), mN = fN, fP = fN, mP = fN;
+#else
+        // a lane without this link leaves fP/mP undefined: the lane that would receive them tests its own link bit first
+        d3 fN, mN, fP, mP;
+        asm volatile("" : "=d"(fP.x), "=d"(fP.y), "=d"(fP.z), "=d"(mP.x), "=d"(mP.y), "=d"(mP.z));
+#endif
+        float4 psp = make_float4(0.f, 0.f, 0.f, 0.f);
+        float end_s[2] = {0.f, 0.f};
+        if (POISSON) {                                 // partner's Poisson strains: another lane's, or a plain load across the + face
+            const int pl = (lane + dl) & 31;
+            psp = make_float4(__shfl_sync(0xffffffffu, ps_own.x, pl), __shfl_sync(0xffffffffu, ps_own.y, pl), __shfl_sync(0xffffffffu, ps_own.z, pl), 0.f);
+            if (!inside && ((mask >> (2 * a)) & 1u)) psp = __ldg(f.c_ps + v + (a == 0 ? 1 : (a == 1 ? f.nx : f.nxy)));
+        }
         if ((mask >> (2 * a)) & 1u) {
             double4 n0, n1, p0, p1;
             load_pose(0, 1024, lane, n0, n1);
-            if (inside) load_pose(0, 1024, lane + dl, p0, p1);
-            else if (a == 0) load_pose(8192, 8448, lz * 4 + ly, p0, p1);
-            else if (a == 1) load_pose(8704, 8960, lz * 4 + lx, p0, p1);
-            else load_pose(10752, 11264, ly * 4 + lx, p0, p1);
+            {   // partner pose: one address computation, one set of loads (in the brick, or in the +X / +Y / +Z face region)
+                const int pose0_at = inside ? (lane + dl) * 32 : (a == 0 ? 8192 + (lz * 4 + ly) * 32 : (a == 1 ? 8704 + (lz * 4 + lx) * 32 : 10752 + (ly * 4 + lx) * 32));
+                const int pose1_by = inside ? 1024 : (a == 2 ? 512 : 256);
+                load_pose(pose0_at, pose0_at + pose1_by, 0, p0, p1);
+            }
             const uint4* rr = reinterpret_cast<const uint4*>(wbase + 2048 + a * 4 * 512) + lane;
             const uint4 r0 = rr[0], r1 = rr[32], r2 = rr[64], r3 = rr[96];
             LinkState st;
@@ -716,7 +800,8 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                                    make_double2(__hiloint2double(r1.y, r1.x), __hiloint2double(r1.w, r1.z)),
                                    make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
                                    make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
-                                   n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP, damp_u);
+                                   n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP, damp_u,
+                                   POISSON ? &ps_own : nullptr, POISSON ? &psp : nullptr, POISSON ? end_s : nullptr);
             double2 wa, wb, wc; float4 ws; uint32_t lf;
             lat_encode(st, wa, wb, wc, ws, lf);
             double2* nr = f.n_rec[0][0] + (size_t)(a * 4) * f.n_vox + v;
@@ -728,6 +813,13 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         const int src = (lane - dl) & 31;
         d3 inF = mk3(__shfl_sync(0xffffffffu, fP.x, src), __shfl_sync(0xffffffffu, fP.y, src), __shfl_sync(0xffffffffu, fP.z, src));
         d3 inM = mk3(__shfl_sync(0xffffffffu, mP.x, src), __shfl_sync(0xffffffffu, mP.y, src), __shfl_sync(0xffffffffu, mP.z, src));
+        float in_e = 0.f;
+        if (POISSON) {
+            const int hl_ = a == 0 ? ly + 4 * lz : (a == 1 ? 8 + lx + 4 * lz : 16 + lx + 4 * ly);
+            const float from_brick = __shfl_sync(0xffffffffu, end_s[1], src), from_h = __shfl_sync(0xffffffffu, h_end[1], hl_);
+            in_e = first ? from_h : from_brick;
+            pe[2 * a] = end_s[0];
+        }
         if ((mask >> (2 * a + 1)) & 1u) {
             if (first) {
                 const int hl = a == 0 ? ly + 4 * lz : (a == 1 ? 8 + lx + 4 * lz : 16 + lx + 4 * ly);
@@ -735,6 +827,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                 inM = mk3(hslot[3][hl], hslot[4][hl], hslot[5][hl]);
             }
             F = F + inF; M = M + inM;
+            if (POISSON) pe[2 * a + 1] = in_e;
         }
     }
 
@@ -759,6 +852,13 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
             const int cs = f.col_slot[v];
             refs = f.col_ref + f.col_start[cs];
             n_refs = f.col_start[cs + 1] - f.col_start[cs];
+        }
+        if (POISSON) {                                  // CVX_Voxel::pStrain for the NEXT step, from this step's link strains
+            float r[3] = {0.f, 0.f, 0.f}; int nb[3] = {0, 0, 0};
+            const uint32_t lm6 = (vs.bits >> VM_LINK_SHIFT) & 0x3Fu;
+#pragma unroll
+            for (int k = 0; k < 6; k++) if (lm6 & (1u << k)) { r[k >> 1] += pe[k]; nb[k >> 1]++; }
+            f.n_ps[v] = voxel_pstrain(vm, ext, r, nb);
         }
         voxel_integrate(vs, F, M, refs, n_refs, f.col_force, vm, ext, dt, floor_on != 0);
     }

@@ -25,6 +25,7 @@ static std::vector<Chunk> state_chunks(vx_sim* s)
             c.push_back({s->pose0[g].p, N * sizeof(double4)}); c.push_back({s->pose1[g].p, N * sizeof(double4)});
             c.push_back({s->mom0[g].p, N * sizeof(double4)}); c.push_back({s->mom1[g].p, N * sizeof(double2)});
             c.push_back({s->rec[g].p, N * VX_REC_PARTS * sizeof(double2)});
+            if (s->ps[g].p) c.push_back({s->ps[g].p, N * sizeof(float4)});
         }
     } else {
         c.push_back({s->pose0[0].p, N * sizeof(double4)}); c.push_back({s->pose1[0].p, N * sizeof(double4)});
@@ -166,6 +167,7 @@ int vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* s
                                                                               (const LinkStateRec*)s->staging.p, first, count);
         CK(cudaStreamSynchronize(s->stream));
         of_dev.release();
+        { int rc = refresh_lattice_ps(s); if (rc != VX_OK) return rc; }       // Poisson: pStrain follows the new link strains
         s->have_prev = false;                                    // link forces are recomputed from the previous generation, which no longer matches
     }
     s->launches++;

@@ -121,34 +121,72 @@ class EnsembleRunner(SingleRunner):
 
 
 class SlabRunner:
-    """Cantilever pattern of C5 (x=0 face fixed, -z load on the x=nx-1 face) split along z."""
+    """One rank's z-slab of a single lattice.  `SlabRunner(lib, nx, ny, nz, ...)` builds the cantilever pattern of C5 (x=0 face
+    fixed, -z load on the x=nx-1 face) without ever materialising the whole lattice on a host; `SlabRunner.from_scenario`
+    splits ANY full-box scenario -- several materials, externals (fixed / forced / prescribed voxels), gravity, floor,
+    temperature -- so that whatever runs on one GPU through the C-ABI runs on N."""
 
     def __init__(self, lib: VxLib, nx: int, ny: int, nz: int, rank: int, world: int, device: int = 0,
                  voxel_size: float = 0.005, tip_load: float = 1.0, material: Material = None, host_exchange: bool = False,
-                 path: int = 0, overlap: bool = True, peer: bool = True):
+                 path: int = 0, overlap: bool = True, peer: bool = True, scenario: "scenarios.Scenario" = None):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = rank, world
+        self.z_origin = 0
+        if scenario is not None:                        # lattice extents of the scenario; the box must be completely filled
+            lo3, hi3 = scenario.ijk.min(axis=0), scenario.ijk.max(axis=0)
+            nx, ny, nz = (int(v) for v in (hi3 - lo3 + 1))
+            if nx * ny * nz != len(scenario.ijk) or scenario.sim_id is not None:
+                raise ValueError("z-slab runs need one completely filled box")
+            self.z_origin, voxel_size = int(lo3[2]), scenario.voxel_size
         self.nx, self.ny, self.nz = nx, ny, nz
         self.z0, self.z1 = slab_range(nz, rank, world)
         self.lo = self.z0 - 1 if rank > 0 else self.z0             # first stored layer (ghost below)
         self.hi = self.z1 + 1 if rank < world - 1 else self.z1     # one past the last stored layer
         self.plane = nx * ny
-        ijk = scenarios.box_ijk(nx, ny, self.hi - self.lo, origin=(0, 0, self.lo))
-        flags = np.zeros(len(ijk), np.uint32)
-        flags[(ijk[:, 2] < self.z0) | (ijk[:, 2] >= self.z1)] = VF_GHOST
         sim = lib.create(voxel_size, device)
-        sim.set_materials([material or Material(E=1e6, rho=1e3)])
-        sim.set_path(path)
-        sim.set_voxels(ijk, np.zeros(len(ijk), np.uint16), flags=flags)
-        owned = flags == 0
-        fixed = np.nonzero((ijk[:, 0] == 0) & owned)[0]
-        load = np.nonzero((ijk[:, 0] == nx - 1) & owned)[0]
-        ev = np.concatenate([fixed, load]).astype(np.int32)
-        dof = np.concatenate([np.full(len(fixed), DOF_ALL), np.zeros(len(load))]).astype(np.uint8)
-        f = np.zeros((len(ev), 3), np.float32)
-        f[len(fixed):, 2] = np.float32(-tip_load / (ny * nz))
-        sim.set_externals(ev, dof, f)
+        if scenario is None:
+            ijk = scenarios.box_ijk(nx, ny, self.hi - self.lo, origin=(0, 0, self.lo))
+            flags = np.zeros(len(ijk), np.uint32)
+            flags[(ijk[:, 2] < self.z0) | (ijk[:, 2] >= self.z1)] = VF_GHOST
+            sim.set_materials([material or Material(E=1e6, rho=1e3)])
+            sim.set_path(path)
+            sim.set_voxels(ijk, np.zeros(len(ijk), np.uint16), flags=flags)
+            owned = flags == 0
+            fixed = np.nonzero((ijk[:, 0] == 0) & owned)[0]
+            load = np.nonzero((ijk[:, 0] == nx - 1) & owned)[0]
+            ev = np.concatenate([fixed, load]).astype(np.int32)
+            dof = np.concatenate([np.full(len(fixed), DOF_ALL), np.zeros(len(load))]).astype(np.uint8)
+            f = np.zeros((len(ev), 3), np.float32)
+            f[len(fixed):, 2] = np.float32(-tip_load / (ny * nz))
+            sim.set_externals(ev, dof, f)
+        else:
+            sc = scenario
+            z = sc.ijk[:, 2] - self.z_origin
+            keep = np.nonzero((z >= self.lo) & (z < self.hi))[0]                   # caller indices of the scenario kept here ...
+            order = np.lexsort((sc.ijk[keep, 0], sc.ijk[keep, 1], sc.ijk[keep, 2]))     # ... stored plane by plane, x fastest
+            keep = keep[order]
+            ijk = sc.ijk[keep]
+            flags = np.zeros(len(ijk), np.uint32)
+            zz = ijk[:, 2] - self.z_origin
+            flags[(zz < self.z0) | (zz >= self.z1)] = VF_GHOST
+            sim.set_materials(sc.materials)
+            sim.set_path(path)
+            sim.set_gravity(sc.gravity)
+            sim.enable_floor(sc.floor)
+            sim.set_voxels(ijk, sc.mat[keep], flags=flags)
+            if len(sc.ext_voxel):                       # externals of the voxels this rank OWNS (a ghost's pose comes from its owner)
+                local = np.full(len(sc.ijk), -1, np.int64); local[keep] = np.arange(len(keep))
+                sel = np.nonzero((local[sc.ext_voxel] >= 0) & (flags[np.maximum(local[sc.ext_voxel], 0)] == 0))[0]
+                pick = lambda a: None if a is None else np.asarray(a)[sel]
+                if len(sel):
+                    sim.set_externals(local[sc.ext_voxel][sel].astype(np.int32), sc.ext_dof[sel], pick(sc.ext_force), pick(sc.ext_moment),
+                                      pick(sc.ext_translation), pick(sc.ext_rotation))
+            if sc.collisions:
+                raise ValueError("self-collisions across z-slabs are not supported (SURVEY 8e: not required by C5b)")
+            if sc.temperature is not None:
+                sim.set_temperature_all(sc.temperature)
+            self.scenario_index = keep                  # local voxel -> caller index of the scenario
         self.sim, self.ijk = sim, ijk
         self.host_exchange = host_exchange
         self._bufs = None
@@ -160,6 +198,26 @@ class SlabRunner:
         self.peer = False
         if peer and self.overlap and dist.is_available() and dist.is_initialized():
             self.peer = self._connect_peers()
+
+    @classmethod
+    def from_scenario(cls, lib: VxLib, sc: "scenarios.Scenario", rank: int, world: int, **kw) -> "SlabRunner":
+        return cls(lib, 0, 0, 0, rank, world, scenario=sc, **kw)
+
+    def set_temperature_all(self, t: float):
+        """CVoxelyze::setAmbientTemperature on every slab (ghost temperatures travel with the halo)."""
+        self.sim.set_temperature_all(t)
+
+    def _reduce_divergence(self, div):
+        """doTimeStep returns false on every rank as soon as one slab diverged (src/Voxelyze.cpp:265-269): the step index is
+        MIN-reduced after the call.  (The other slabs may have advanced past that step; a diverged simulation is dead anyway.)"""
+        if self.world == 1 or not (self.dist.is_available() and self.dist.is_initialized()):
+            return div
+        import torch
+        dev = "cpu" if self.host_exchange else "cuda"
+        t = torch.tensor([2 ** 31 - 1 if div is None else int(div)], dtype=torch.int64, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        v = int(t.item())
+        return None if v == 2 ** 31 - 1 else v
 
     # ---- bookkeeping -------------------------------------------------------------------
     def global_counts(self):
@@ -191,17 +249,17 @@ class SlabRunner:
         dist, sim, n = self.dist, self.sim, Sim.PEER_DESC_BYTES
         mine = torch.zeros(2, n, dtype=torch.uint8)
         if self.rank > 0:
-            mine[0] = torch.frombuffer(bytearray(sim.peer_export(self.z0 - 1, False)), dtype=torch.uint8)
+            mine[0] = torch.frombuffer(bytearray(sim.peer_export(self.z_origin + self.z0 - 1, False)), dtype=torch.uint8)
         if self.rank < self.world - 1:
-            mine[1] = torch.frombuffer(bytearray(sim.peer_export(self.z1, True)), dtype=torch.uint8)
+            mine[1] = torch.frombuffer(bytearray(sim.peer_export(self.z_origin + self.z1, True)), dtype=torch.uint8)
         everyone = [torch.empty(2, n, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
         dist.all_gather(everyone, mine.cuda())
         ok = 1
         try:
             if self.rank > 0:          # my first layer is the top ghost of the slab below
-                sim.peer_attach(self.z0, bytes(everyone[self.rank - 1][1].cpu().numpy()))
+                sim.peer_attach(self.z_origin + self.z0, bytes(everyone[self.rank - 1][1].cpu().numpy()))
             if self.rank < self.world - 1:
-                sim.peer_attach(self.z1 - 1, bytes(everyone[self.rank + 1][0].cpu().numpy()))
+                sim.peer_attach(self.z_origin + self.z1 - 1, bytes(everyone[self.rank + 1][0].cpu().numpy()))
         except VxError as e:
             self.peer_error = str(e)
             ok = 0
@@ -216,8 +274,8 @@ class SlabRunner:
     def connect_local(runners):
         """Wires the slabs of ONE process to each other (tests on a single GPU)."""
         for lo, hi in zip(runners[:-1], runners[1:]):
-            hi.sim.peer_attach(hi.z0, lo.sim.peer_export(lo.z1, True))
-            lo.sim.peer_attach(lo.z1 - 1, hi.sim.peer_export(hi.z0 - 1, False))
+            hi.sim.peer_attach(hi.z_origin + hi.z0, lo.sim.peer_export(lo.z_origin + lo.z1, True))
+            lo.sim.peer_attach(lo.z_origin + lo.z1 - 1, hi.sim.peer_export(hi.z_origin + hi.z0 - 1, False))
         for r in runners:
             r.peer = True
 
@@ -242,7 +300,7 @@ class SlabRunner:
         ops, imports = [], []
         for peer, send_z, recv_z in self._neighbours():
             # the fused lattice path ping-pongs generations: the current-state arrays move every step
-            p0, p1, n, rb = self.sim.pose_plane(send_z)
+            p0, p1, n, rb = self.sim.pose_plane(self.z_origin + send_z)
             assert n == self.plane
             for ptr in (p0, p1):
                 if ptr not in views:
@@ -257,7 +315,7 @@ class SlabRunner:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         for recv_z, r0, r1 in imports:
-            self.sim.halo_import(recv_z, r0.data_ptr(), r1.data_ptr(), self.plane, import_stream)
+            self.sim.halo_import(self.z_origin + recv_z, r0.data_ptr(), r1.data_ptr(), self.plane, import_stream)
 
     def _exchange_host(self):
         import torch
@@ -289,18 +347,21 @@ class SlabRunner:
             self._exchange_device()
 
     # ---- stepping ------------------------------------------------------------------------
-    def step(self, dt: float, n: int):
+    def step(self, dt: float, n: int, check_divergence: bool = False):
+        """n steps with their halo exchanges.  check_divergence: also agree on the divergence flag across ranks (one tiny
+        all-reduce after the call; bench.py's timed region leaves it off like it leaves every other collective off)."""
         if self.peer:
-            return self.sim.slab_step(dt, n)
-        if self.overlap:
-            return self._step_overlapped(dt, n)
-        div = None
-        for _ in range(n):
-            d = self.sim.step(dt, 1)
-            if d is not None:
-                div = d
-            self.exchange()
-        return div
+            div = self.sim.slab_step(dt, n)
+        elif self.overlap:
+            div = self._step_overlapped(dt, n)
+        else:
+            div = None
+            for k in range(n):
+                d = self.sim.step(dt, 1)
+                if d is not None and div is None:
+                    div = k
+                self.exchange()
+        return self._reduce_divergence(div) if check_divergence else div
 
     def _step_overlapped(self, dt: float, n: int):
         """boundary layers first, halo push on a second stream, interior meanwhile.
