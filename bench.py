@@ -248,6 +248,7 @@ def main():
     ap.add_argument("--config", default="c5", choices=["c5", "c4"])
     ap.add_argument("--size", type=int, default=0, help="c5: override lattice edge (testing only; reported in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline + parity leg (N=1) / the whole-lattice check (N>1)")
+    ap.add_argument("--no-facade", action="store_true", help="skip the e2e leg through the C++ facade")
     ap.add_argument("--no-peer", action="store_true", help="N>1: NCCL send/recv for the halo instead of peer-memory stores")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: exchange the halo after the step instead of overlapping it with the interior")
     ap.add_argument("--path", type=int, default=0, help="kernel variant (vx_set_path): 0 auto, 1 general, 5/7 fused lattice with cp.async/TMA staging")
@@ -375,6 +376,18 @@ def main():
     e2e = {"value": units * e2e_steps / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": runner.h2d_bytes_per_step(), "d2h_bytes_per_step": 40 + 24,
            "note": "per-step blocking vx_step(dt,1) + vx_download of one voxel position through the C-ABI with host buffers; lattice state "
                    "stays in HBM like the reference keeps it in RAM (construction excluded on both arms)"}
+
+    # ---- the same per-step loop through the C++ class API of the facade (CVoxelyze::doTimeStep + CVX_Voxel::position), the
+    # binding a drop-in caller of the reference actually uses; separate process, same GPU, after the device-timed region
+    if world == 1 and not c4 and not args.no_facade:
+        exe = os.path.join(ROOT, "tests", "cpp", "_build", "facade_e2e")
+        try:
+            out = subprocess.run([exe, str(args.size or 256), "5", str(e2e_steps)], capture_output=True, text=True, timeout=600)
+            fe = json.loads(out.stdout.strip().splitlines()[-1])
+            e2e["facade"] = {"value": fe["updates_per_s"], "unit": "updates/s", "ms_per_step": fe["ms_per_step"], "build_s": fe["build_s"],
+                             "through": "libvoxelyze_facade.so: CVoxelyze::doTimeStep(dt) + CVX_Voxel::position() per step (tools/facade_e2e.cpp)"}
+        except Exception as exc:                        # missing binary (not built) or a failed run: say so, do not invent a number
+            e2e["facade"] = {"value": None, "error": f"{type(exc).__name__}: {exc}"[:200]}
 
     line = {"metric": "link+voxel updates/sec", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -363,6 +363,13 @@ int  vx_collision_forces(vx_sim* s, int32_t* pairs, float* forces, int cap, int*
  * links of the edited voxel, src/Voxelyze.cpp:485-498) or across a change of layout
  * (vx_enable_collisions mid-run).  flags: VX_LF_SMALL_ANGLE | VX_LF_LOCAL_VEL_VALID are stored,
  * yielded/failed are derived from max_strain.                                               */
+/* all six voxel fields of a range of voxels in ONE call (one kernel, one copy): what CVX_Voxel::position() / orientation() /
+ * velocity() / ... of a single voxel needs between steps (SURVEY.md section 3.5, 8b hazard 5).                            */
+typedef struct vx_voxel_state {
+    double pos[3], orient[4], linmom[3], angmom[3];     /* orient: w, x, y, z */
+    float temp; uint32_t flags;                          /* VX_VF_* */
+} vx_voxel_state;
+int  vx_download_voxel_state(vx_sim* s, int first, int count, vx_voxel_state* dst);
 typedef struct vx_link_state {
     double pos2[3], angle1v[3], angle2v[3];
     float strain, max_strain, strain_offset, stress;

@@ -1126,6 +1126,21 @@ int vx_active_path(const vx_sim*) { return 0; }
 const char* vx_kernel_name(const vx_sim*) { return "cpu (oracle port)"; }
 int vx_step_profile(vx_sim*, float, int, float*, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_prepare(vx_sim*) { return VX_OK; }
+int vx_download_voxel_state(vx_sim* s, int first, int count, vx_voxel_state* dst)
+{
+    if (!s || !dst || first < 0 || count < 0) return VX_ERR_ARG;
+    for (int k = 0; k < count; k++) {
+        vx_voxel_state& r = dst[k];
+        int rc = vx_download(s, VX_F_POS, first + k, 1, r.pos);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_ORIENT, first + k, 1, r.orient);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_LINMOM, first + k, 1, r.linmom);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_ANGMOM, first + k, 1, r.angmom);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_TEMP, first + k, 1, &r.temp);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_VOXFLAGS, first + k, 1, &r.flags);
+        if (rc != VX_OK) return rc;
+    }
+    return VX_OK;
+}
 // surface mesh: pinned directly against the reference's CVX_MeshRender (oracle/ref_shim.cpp), not restated here
 int vx_mesh_set_material_colors(vx_sim*, int, const unsigned char*) { return VX_ERR_UNSUPPORTED; }
 int vx_mesh_build(vx_sim*, int*, int*) { return VX_ERR_UNSUPPORTED; }

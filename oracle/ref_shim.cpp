@@ -427,6 +427,21 @@ int vx_active_path(const vx_sim*) { return 0; }
 const char* vx_kernel_name(const vx_sim*) { return "cpu (reference CVoxelyze::doTimeStep)"; }
 int vx_step_profile(vx_sim*, float, int, float*, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_prepare(vx_sim*) { return VX_OK; }
+int vx_download_voxel_state(vx_sim* s, int first, int count, vx_voxel_state* dst)
+{
+    if (!s || !dst || first < 0 || count < 0) return VX_ERR_ARG;
+    for (int k = 0; k < count; k++) {
+        vx_voxel_state& r = dst[k];
+        int rc = vx_download(s, VX_F_POS, first + k, 1, r.pos);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_ORIENT, first + k, 1, r.orient);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_LINMOM, first + k, 1, r.linmom);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_ANGMOM, first + k, 1, r.angmom);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_TEMP, first + k, 1, &r.temp);
+        if (rc == VX_OK) rc = vx_download(s, VX_F_VOXFLAGS, first + k, 1, &r.flags);
+        if (rc != VX_OK) return rc;
+    }
+    return VX_OK;
+}
 
 // ---- surface mesh: the reference's own CVX_MeshRender (src/VX_MeshRender.cpp), members read through the opened-up header
 static void apply_colors(vx_sim* s)

@@ -93,6 +93,12 @@ def build_cpp_tests() -> dict:
                         "-o", exe, src, "-L", LIBDIR, "-lvoxelyze_facade", "-lvoxelyze_b200",
                         "-Wl,-rpath," + LIBDIR], check=True)
     out["b200"] = exe
+    e2e = os.path.join(bdir, "facade_e2e")              # the headline workload through the C++ class API (bench.py's e2e.facade leg)
+    e2e_src = os.path.join(ROOT, "tools", "facade_e2e.cpp")
+    if not _newer(e2e, [e2e_src, FACADE_SO]):
+        subprocess.run([_host_cxx(), "-O2", "-std=c++17", "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", e2e, e2e_src,
+                        "-L", LIBDIR, "-lvoxelyze_facade", "-lvoxelyze_b200", "-Wl,-rpath," + LIBDIR], check=True)
+    out["facade_e2e"] = e2e
     ref = "/root/reference"
     exe_ref = os.path.join(bdir, "dropin_ref")
     if os.path.isdir(os.path.join(ref, "src")):

@@ -152,6 +152,7 @@ class VxLib:
             "vx_time": (f32, [vp]),
             "vx_download": (i32, [vp, i32, i32, i32, vp]),
             "vx_upload": (i32, [vp, i32, i32, i32, vp]),
+            "vx_download_voxel_state": (i32, [vp, i32, i32, vp]),
             "vx_collision_pairs": (i32, [vp, vp, i32, P(i32)]),
             "vx_collision_stats": (i32, [vp, P(i32), P(i32)]),
             "vx_state_info": (i32, [vp, i32, i32, P(f32)]),
@@ -352,6 +353,13 @@ class Sim:
         if count:
             self._chk(self.L.lib.vx_download(self.h, fid, first, count, _ptr(out)))
         return out if comps > 1 else out.reshape(-1)
+
+    VOXEL_STATE_DTYPE = np.dtype([("pos", "<f8", 3), ("orient", "<f8", 4), ("linmom", "<f8", 3), ("angmom", "<f8", 3), ("temp", "<f4"), ("flags", "<u4")])
+
+    def download_voxel_state(self, first: int = 0, count: int = 1) -> np.ndarray:
+        out = np.zeros(count, self.VOXEL_STATE_DTYPE)
+        self._chk(self.L.lib.vx_download_voxel_state(self.h, first, count, out.ctypes.data))
+        return out
 
     def upload(self, name: str, data, first: int = 0):
         fid, dt, comps, _ = FIELDS[name]

@@ -151,6 +151,7 @@ struct vx_sim {
     DevBuf<unsigned char> staging;
     DevParams* params_host = nullptr;     // pinned mirror
     unsigned int* freq_host = nullptr;    // pinned
+    VoxelStateRec* probe_host = nullptr;  // pinned + mapped: vx_download_voxel_state of a few voxels lands here without a copy
 
     // ---- collisions (tables indexed by internal voxel index: both layouts)
     std::vector<int32_t> nbr;                                      // [N][6] neighbour voxel (caller index) or -1
@@ -1081,6 +1082,7 @@ void vx_destroy(vx_sim* s)
     s->params.release(); s->freq2.release(); s->member_t.release(); s->staging.release();
     if (s->params_host) cudaFreeHost(s->params_host);
     if (s->freq_host) cudaFreeHost(s->freq_host);
+    if (s->probe_host) cudaFreeHost(s->probe_host);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -1733,6 +1735,33 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
                                                            s->staging.p, s->axis_first[1], s->axis_first[2]);
     }
     s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, s->staging.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return VX_OK;
+}
+
+int vx_download_voxel_state(vx_sim* s, int first, int count, vx_voxel_state* dst)
+{
+    static_assert(sizeof(vx_voxel_state) == sizeof(VoxelStateRec), "vx_voxel_state layout");
+    if (!s || !dst || first < 0 || count < 0 || first + (long long)count > s->N_user) return VX_ERR_ARG;
+    if (count == 0) return VX_OK;
+    { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
+    CK(cudaSetDevice(s->device));
+    if (count <= 32) {                                  // the common case (a caller polling a few voxels per step): the kernel writes
+        if (!s->probe_host) CK(cudaHostAlloc((void**)&s->probe_host, 32 * sizeof(VoxelStateRec), cudaHostAllocMapped));     // straight into mapped pinned memory
+        VoxelStateRec* dev = nullptr;
+        CK(cudaHostGetDevicePointer((void**)&dev, s->probe_host, 0));
+        k_gather_voxel_state<<<1, 32, 0, s->stream>>>(s->frame(), s->vox_e2i_dev.p, first, count, dev); s->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s->stream));
+        memcpy(dst, s->probe_host, (size_t)count * sizeof(VoxelStateRec));
+        return VX_OK;
+    }
+    const size_t bytes = (size_t)count * sizeof(VoxelStateRec);
+    CK(cudaStreamSynchronize(s->stream));
+    CK(s->staging.alloc(bytes));
+    k_gather_voxel_state<<<blocks_for(count), TPB, 0, s->stream>>>(s->frame(), s->vox_e2i_dev.p, first, count, (VoxelStateRec*)s->staging.p); s->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, s->staging.p, bytes, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));

@@ -338,6 +338,22 @@ __global__ void k_gather(Frame f, int what, const int* e2i, int first, int count
     }
 }
 
+struct VoxelStateRec { double pos[3], orient[4], linmom[3], angmom[3]; float temp; uint32_t flags; };       // = vx_voxel_state
+__global__ void k_gather_voxel_state(Frame f, const int* e2i, int first, int count, VoxelStateRec* out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int i = e2i[first + k];
+    const double4 a = f.pose0[i], b = f.pose1[i], c = f.mom0[i]; const double2 d = f.mom1[i];
+    VoxelStateRec r;
+    r.pos[0] = a.x; r.pos[1] = a.y; r.pos[2] = a.z; r.orient[0] = a.w; r.orient[1] = b.x; r.orient[2] = b.y; r.orient[3] = b.z;
+    r.linmom[0] = c.x; r.linmom[1] = c.y; r.linmom[2] = c.z; r.angmom[0] = c.w; r.angmom[1] = d.x; r.angmom[2] = d.y;
+    r.temp = meta_temp(b.w);
+    const uint32_t m = meta_hi(b.w);
+    r.flags = ((m & VM_STATIC_FRIC) ? 1u : 0u) | ((((m >> VM_LINK_SHIFT) & 0x3Fu) != 0x3Fu) ? 2u : 0u) | ((m & VM_GHOST) ? 4u : 0u);
+    out[k] = r;
+}
+
 __global__ void k_scatter(Frame f, int what, const int* e2i, int first, int count, const void* in)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;

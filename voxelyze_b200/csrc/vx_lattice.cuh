@@ -854,11 +854,16 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
             n_refs = f.col_start[cs + 1] - f.col_start[cs];
         }
         if (POISSON) {                                  // CVX_Voxel::pStrain for the NEXT step, from this step's link strains
-            float r[3] = {0.f, 0.f, 0.f}; int nb[3] = {0, 0, 0};
-            const uint32_t lm6 = (vs.bits >> VM_LINK_SHIFT) & 0x3Fu;
+            // a fully fixed voxel returns from CVX_Voxel::timeStep before its cache is invalidated (src/VX_Voxel.cpp:167-172,
+            // 231): it keeps the Poisson strain it had
+            if (ext && (ext->dof & 0x3Fu) == 0x3Fu) f.n_ps[v] = ps_own;
+            else {
+                float r[3] = {0.f, 0.f, 0.f}; int nb[3] = {0, 0, 0};
+                const uint32_t lm6 = (vs.bits >> VM_LINK_SHIFT) & 0x3Fu;
 #pragma unroll
-            for (int k = 0; k < 6; k++) if (lm6 & (1u << k)) { r[k >> 1] += pe[k]; nb[k >> 1]++; }
-            f.n_ps[v] = voxel_pstrain(vm, ext, r, nb);
+                for (int k = 0; k < 6; k++) if (lm6 & (1u << k)) { r[k >> 1] += pe[k]; nb[k >> 1]++; }
+                f.n_ps[v] = voxel_pstrain(vm, ext, r, nb);
+            }
         }
         voxel_integrate(vs, F, M, refs, n_refs, f.col_force, vm, ext, dt, floor_on != 0);
     }

@@ -712,9 +712,11 @@ void CVoxelyze::fetchVoxel(int i) const
     // a caller polling a handful of voxels per step pays a few 100-byte copies; a caller walking the
     // whole list gets one bulk download
     if (++singleFetches > 32) { fetchAll(); return; }
-    vx_download(h, VX_F_POS, i, 1, &mPos[3 * i]); vx_download(h, VX_F_ORIENT, i, 1, &mOrient[4 * i]);
-    vx_download(h, VX_F_LINMOM, i, 1, &mLin[3 * i]); vx_download(h, VX_F_ANGMOM, i, 1, &mAng[3 * i]);
-    vx_download(h, VX_F_TEMP, i, 1, &mTemp[i]); vx_download(h, VX_F_VOXFLAGS, i, 1, &mFlags[i]);
+    vx_voxel_state r;                                   // one call, one tiny kernel writing into mapped pinned memory
+    if (vx_download_voxel_state(h, i, 1, &r) != VX_OK) die("vx_download_voxel_state");
+    for (int k = 0; k < 3; k++) { mPos[3 * i + k] = r.pos[k]; mLin[3 * i + k] = r.linmom[k]; mAng[3 * i + k] = r.angmom[k]; }
+    for (int k = 0; k < 4; k++) mOrient[4 * i + k] = r.orient[k];
+    mTemp[i] = r.temp; mFlags[i] = r.flags;
     mirrorEpoch[i] = epoch;
 }
 
