@@ -1717,7 +1717,7 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
 {
     int what, comps, esize; bool is_link;
     if (!s || !dst || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
-    if (first + count > (is_link ? s->L : s->N_user)) return VX_ERR_ARG;
+    if ((long long)first + count > (is_link ? s->L : s->N_user)) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
     { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     CK(cudaSetDevice(s->device));
@@ -1774,7 +1774,7 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
     if (!s || !src || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
     if (is_link || what == G_PSTRAIN) return fail(s, VX_ERR_UNSUPPORTED, "only voxel state can be uploaded");
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_upload inside vx_step_begin .. vx_step_end");
-    if (first + count > s->N_user) return VX_ERR_ARG;
+    if ((long long)first + count > s->N_user) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
     { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     CK(cudaSetDevice(s->device));

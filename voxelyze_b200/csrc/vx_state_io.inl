@@ -4,7 +4,7 @@
 // ---- dynamic-state checkpoint (the reference has none) -----------------
 namespace {
 struct StateHeader {
-    char magic[8]; int32_t abi, lattice, N, L, nx, ny, nz, n_members, gen, have_prev, collisions, reserved;
+    char magic[8]; int32_t abi, lattice, N, L, nx, ny, nz, n_members, gen, have_prev, collisions, header_bytes;       // header_bytes: sizeof(StateHeader) of the writer (layout check)
     float last_prev_dt, prev_dt_host, time_host, ambient; uint64_t topo_hash; DevParams params;
 };
 struct Chunk { void* p; size_t bytes; };
@@ -14,6 +14,23 @@ static uint64_t topo_hash(const vx_sim* s)
     auto mix = [&](const void* d, size_t n) { const unsigned char* b = (const unsigned char*)d; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; } };
     mix(s->ijk.data(), s->ijk.size() * sizeof(int32_t)); mix(s->vmat_id.data(), s->vmat_id.size() * sizeof(uint16_t));
     mix(s->member.data(), s->member.size() * sizeof(int32_t)); mix(s->vflags.data(), s->vflags.size() * sizeof(uint32_t));
+    // ... and everything else the restored arrays are only meaningful with: voxel size, every material parameter and data
+    // curve, the externals, gravity and floor (a state resumed under other physics would be silently wrong)
+    mix(&s->vox_size, sizeof(double)); mix(&s->grav, sizeof(float));
+    const int env[2] = {s->floor_on ? 1 : 0, (int)s->descs.size()}; mix(env, sizeof(env));
+    for (size_t i = 0; i < s->descs.size(); i++) {
+        vx_material_desc d = s->descs[i]; d.strain = d.stress = nullptr;       // the curve arrays are hashed by content
+        mix(&d.model, sizeof(d.model)); mix(&d.youngs_modulus, sizeof(float)); mix(&d.plastic_modulus, sizeof(float)); mix(&d.yield_stress, sizeof(float));
+        mix(&d.fail_stress, sizeof(float)); mix(&d.n_points, sizeof(d.n_points)); mix(&d.density, sizeof(float)); mix(&d.poissons_ratio, sizeof(float));
+        mix(&d.cte, sizeof(float)); mix(&d.mu_static, sizeof(float)); mix(&d.mu_kinetic, sizeof(float)); mix(&d.zeta_internal, sizeof(float));
+        mix(&d.zeta_global, sizeof(float)); mix(&d.zeta_collision, sizeof(float)); mix(d.ext_scale, sizeof(d.ext_scale));
+        if (i < s->d_eps.size()) { mix(s->d_eps[i].data(), s->d_eps[i].size() * sizeof(float)); mix(s->d_sig[i].data(), s->d_sig[i].size() * sizeof(float)); }
+    }
+    mix(s->ext_vox.data(), s->ext_vox.size() * sizeof(int32_t));
+    for (const DevExt& e : s->ext_rows) {
+        mix(e.nominal, sizeof(e.nominal)); mix(e.translation, sizeof(e.translation)); mix(e.rot_q, sizeof(e.rot_q));
+        mix(e.force, sizeof(e.force)); mix(e.moment, sizeof(e.moment)); mix(&e.dof, sizeof(e.dof));
+    }
     return h;
 }
 static std::vector<Chunk> state_chunks(vx_sim* s)
@@ -50,7 +67,7 @@ int vx_save_state(vx_sim* s, const char* path)
     StateHeader h{};
     memcpy(h.magic, "VXB2ST02", 8);
     h.abi = VX_ABI_VERSION; h.lattice = s->lattice; h.N = s->N; h.L = s->L; h.nx = s->nx; h.ny = s->ny; h.nz = s->nz; h.n_members = s->n_members;
-    h.gen = s->gen; h.have_prev = s->have_prev; h.collisions = s->collisions;
+    h.gen = s->gen; h.have_prev = s->have_prev; h.collisions = s->collisions; h.header_bytes = (int32_t)sizeof(StateHeader);
     h.last_prev_dt = s->last_prev_dt; h.prev_dt_host = s->prev_dt_host; h.time_host = s->time_host; h.ambient = s->ambient;
     h.topo_hash = topo_hash(s);
     cudaError_t e = cudaMemcpy(&h.params, s->params.p, sizeof(DevParams), cudaMemcpyDeviceToHost);
@@ -74,11 +91,11 @@ int vx_load_state(vx_sim* s, const char* path)
     FILE* fp = fopen(path, "rb");
     if (!fp) return fail(s, VX_ERR_ARG, std::string("cannot read ") + path);
     StateHeader h{};
-    bool ok = fread(&h, sizeof(h), 1, fp) == 1 && memcmp(h.magic, "VXB2ST02", 8) == 0 && h.abi == VX_ABI_VERSION;
+    bool ok = fread(&h, sizeof(h), 1, fp) == 1 && memcmp(h.magic, "VXB2ST02", 8) == 0 && h.abi == VX_ABI_VERSION && h.header_bytes == (int32_t)sizeof(StateHeader);
     if (ok && (h.lattice != (int)s->lattice || h.N != s->N || h.L != s->L || h.nx != s->nx || h.ny != s->ny || h.nz != s->nz ||
                h.n_members != s->n_members || h.collisions != (int)s->collisions || h.topo_hash != topo_hash(s))) {
         fclose(fp);
-        return fail(s, VX_ERR_ARG, "vx_load_state: the file belongs to a different model (voxels, materials layout or options differ)");
+        return fail(s, VX_ERR_ARG, "vx_load_state: the file belongs to a different model (voxels, voxel size, materials, externals, environment or options differ)");
     }
     std::vector<unsigned char> bounce(64u << 20);
     for (const Chunk& c : state_chunks(s)) {
@@ -90,6 +107,8 @@ int vx_load_state(vx_sim* s, const char* path)
     fclose(fp);
     if (!ok) return fail(s, VX_ERR_ARG, std::string("reading ") + path + " failed (truncated or not a state file)");
     h.params.col_stale = 1;                                  // watch lists are rebuilt from the restored positions at the next step
+    h.params.div_now = h.params.div_latched = h.params.pending = 0; h.params.div_flag[0] = h.params.div_flag[1] = 0;   // step bookkeeping restarts (vx_step's k_begin does the same)
+    s->amb_pending = false; s->last_amb = false; s->n_pairs = 0;
     CK(cudaMemcpy(s->params.p, &h.params, sizeof(DevParams), cudaMemcpyHostToDevice));
     s->gen = h.gen; s->have_prev = h.have_prev != 0; s->last_prev_dt = h.last_prev_dt; s->prev_dt_host = h.prev_dt_host;
     s->time_host = h.time_host; s->ambient = h.ambient; s->col_stale_host = true;
@@ -123,7 +142,7 @@ int vx_collision_forces(vx_sim* s, int32_t* pairs, float* forces, int cap, int* 
 // ---- packed link state (topology edits and layout changes keep the state of surviving links) -------
 int vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst)
 {
-    if (!s || !dst || first < 0 || count < 0 || first + count > s->L) return VX_ERR_ARG;
+    if (!s || !dst || first < 0 || count < 0 || (long long)first + count > s->L) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
     std::vector<double> p2(3 * (size_t)count), a1(3 * (size_t)count), a2(3 * (size_t)count);
     std::vector<float> e(count), em(count), eo(count), sg(count); std::vector<uint32_t> fl(count);
@@ -147,7 +166,7 @@ int vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst)
 int vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* src)
 {
     static_assert(sizeof(vx_link_state) == sizeof(LinkStateRec), "vx_link_state layout");
-    if (!s || !src || first < 0 || count < 0 || first + count > s->L || s->call_active) return VX_ERR_ARG;
+    if (!s || !src || first < 0 || count < 0 || (long long)first + count > s->L || s->call_active) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
