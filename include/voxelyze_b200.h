@@ -152,6 +152,8 @@ enum vx_field {
 #define VX_VF_STATIC_FRICTION 0x1u  /* FLOOR_STATIC_FRICTION, VX_Voxel.h:146          */
 #define VX_VF_SURFACE         0x2u  /* fewer than 6 links, VX_Voxel.cpp:376-381       */
 #define VX_VF_GHOST           0x4u  /* z-slab halo copy: pose is imported, never integrated */
+#define VX_VF_FLOOR_OFF       0x8u  /* CVX_Voxel::enableFloor(false) on this voxel (include/VX_Voxel.h:119) while the floor is on */
+#define VX_VF_FLOOR_ON        0x10u /* CVX_Voxel::enableFloor(true) on this voxel while the simulation's floor is off            */
 /* link flag bits (download) */
 #define VX_LF_SMALL_ANGLE     0x1u  /* CVX_Link::smallAngle, VX_Link.h:103            */
 #define VX_LF_LOCAL_VEL_VALID 0x2u  /* LOCAL_VELOCITY_VALID, VX_Link.h:80             */

@@ -375,6 +375,7 @@ struct Voxel {                       // CVX_Voxel private state, VX_Voxel.h:150-
     V3 pos, linMom, angMom; Q4 orient;
     float temp = 0;
     bool floorStatic = true;
+    int floorOverride = -1;            // CVX_Voxel::enableFloor on this voxel: -1 follows the simulation
     V3f pStrain; bool pInvalid = true;
     V3f lastWatch;
     std::vector<int> colWatch, nearby;
@@ -654,6 +655,7 @@ struct vx_sim {
             return;
         }
         V3 cur = voxelForce(v, self), fric = cur;
+        const bool floorOn = v.floorOverride < 0 ? this->floorOn : v.floorOverride != 0;     // include/VX_Voxel.h:119-120
         if (floorOn) floorForce(v, cur);
         fric = sub(cur, fric);
         v.linMom = add(v.linMom, scale(dt, cur));
@@ -1003,7 +1005,8 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
             case VX_F_LINMOM: put(k, v.linMom); break;
             case VX_F_ANGMOM: put(k, v.angMom); break;
             case VX_F_TEMP: f[k] = v.temp; break;
-            case VX_F_VOXFLAGS: u[k] = (v.floorStatic ? VX_VF_STATIC_FRICTION : 0) | (s->isSurface(v) ? VX_VF_SURFACE : 0) | (v.ghost ? VX_VF_GHOST : 0); break;
+            case VX_F_VOXFLAGS: u[k] = (v.floorStatic ? VX_VF_STATIC_FRICTION : 0) | (s->isSurface(v) ? VX_VF_SURFACE : 0) | (v.ghost ? VX_VF_GHOST : 0) |
+                                       (v.floorOverride == 0 ? VX_VF_FLOOR_OFF : 0) | (v.floorOverride == 1 ? VX_VF_FLOOR_ON : 0); break;
             case VX_F_PSTRAIN: f[3 * k] = v.pStrain.x; f[3 * k + 1] = v.pStrain.y; f[3 * k + 2] = v.pStrain.z; break;
             default: return VX_ERR_ARG;
             }
@@ -1043,7 +1046,8 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
         case VX_F_LINMOM: v.linMom = V3{d[3 * k], d[3 * k + 1], d[3 * k + 2]}; break;
         case VX_F_ANGMOM: v.angMom = V3{d[3 * k], d[3 * k + 1], d[3 * k + 2]}; break;
         case VX_F_TEMP: s->setTemperature(v, f[k]); break;
-        case VX_F_VOXFLAGS: v.floorStatic = (u[k] & VX_VF_STATIC_FRICTION) != 0; break;
+        case VX_F_VOXFLAGS: v.floorStatic = (u[k] & VX_VF_STATIC_FRICTION) != 0;
+                            v.floorOverride = (u[k] & VX_VF_FLOOR_OFF) ? 0 : ((u[k] & VX_VF_FLOOR_ON) ? 1 : -1); break;
         default: return VX_ERR_ARG;
         }
     }

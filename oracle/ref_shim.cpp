@@ -333,7 +333,8 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
             case VX_F_LINMOM: put3(d + 3*k, v->linMom); break;
             case VX_F_ANGMOM: put3(d + 3*k, v->angMom); break;
             case VX_F_TEMP: f[k] = v->temp; break;
-            case VX_F_VOXFLAGS: u[k] = (v->isFloorStaticFriction() ? VX_VF_STATIC_FRICTION : 0) | (v->isSurface() ? VX_VF_SURFACE : 0); break;
+            case VX_F_VOXFLAGS: u[k] = (v->isFloorStaticFriction() ? VX_VF_STATIC_FRICTION : 0) | (v->isSurface() ? VX_VF_SURFACE : 0) |
+                                       (s->floor_on && !v->isFloorEnabled() ? VX_VF_FLOOR_OFF : 0) | (!s->floor_on && v->isFloorEnabled() ? VX_VF_FLOOR_ON : 0); break;
             case VX_F_PSTRAIN: f[3*k] = v->pStrain.x; f[3*k+1] = v->pStrain.y; f[3*k+2] = v->pStrain.z; break;
             default: return VX_ERR_ARG;
             }
@@ -374,7 +375,8 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
         case VX_F_LINMOM: v->linMom = get3(d + 3*k); break;
         case VX_F_ANGMOM: v->angMom = get3(d + 3*k); break;
         case VX_F_TEMP: v->setTemperature(f[k]); break;
-        case VX_F_VOXFLAGS: v->setFloorStaticFriction((u[k] & VX_VF_STATIC_FRICTION) != 0); break;
+        case VX_F_VOXFLAGS: v->setFloorStaticFriction((u[k] & VX_VF_STATIC_FRICTION) != 0);
+                            v->enableFloor((u[k] & VX_VF_FLOOR_OFF) ? false : ((u[k] & VX_VF_FLOOR_ON) ? true : s->floor_on)); break;
         default: return VX_ERR_ARG;
         }
     }

@@ -702,6 +702,33 @@ static void printEditScenario()
     }
 }
 
+// include/VX_Voxel.h:119-120, 130: the floor can be switched per voxel; dampingMultiplier follows the last time step
+static void perVoxelFloorAndDampingMultiplier()
+{
+    CVoxelyze Vx(0.001);
+    CVX_Material* m = Vx.addMaterial(1e6f, 1e3f);
+    m->setGlobalDamping(0.002f); m->setCollisionDamping(1.0f); m->setInternalDamping(0.7f);      // (more global damping = a terminal velocity of a few mm/s)
+    CVX_Voxel* a = Vx.setVoxel(m, 0, 0, 0);
+    CVX_Voxel* b = Vx.setVoxel(m, 4, 0, 0);
+    CVX_Voxel* c = Vx.setVoxel(m, 8, 0, 0);
+    Vx.setGravity(1.0f); Vx.enableFloor(true);
+    b->enableFloor(false);
+    CHECK(a->isFloorEnabled() && !b->isFloorEnabled() && c->isFloorEnabled());
+    float dt = Vx.recommendedTimeStep();
+    for (int i = 0; i < 8000; i++) Vx.doTimeStep(dt);
+    CHECK_FLOAT_EQ(a->dampingMultiplier(), 2 * sqrtf((float)(1e-9 * 1e3)) * 0.7f / dt);
+    CHECK(a->position().z > -1e-4 && c->position().z > -1e-4);         // held up by the floor
+    CHECK(b->position().z < -5e-4);                                     // fell through it
+    CHECK_NEAR(a->position().z, c->position().z, 1e-15);
+    const double zb = b->position().z;
+    Vx.enableFloor(true);                                               // src/Voxelyze.cpp:604-610: every voxel follows the simulation again
+    CHECK(b->isFloorEnabled());
+    c->enableFloor(false);
+    for (int i = 0; i < 8000; i++) Vx.doTimeStep(dt);
+    CHECK(b->position().z > zb);                                        // pushed back up by the floor spring
+    CHECK(c->position().z < -5e-4);
+}
+
 #ifndef DROPIN_REFERENCE
 static void copyTakesTheModel()         // Voxelyze.cpp:39-58; in the reference the copied materials come out broken (_sqrtMass negated,
 {                                       // VX_MaterialVoxel.cpp:47) and the copy diverges at once, so this can only be checked on the facade
@@ -791,7 +818,7 @@ int main(int argc, char** argv)
         {"temperatureBimorph", temperatureBimorph, true}, {"staticFriction", staticFriction, true}, {"kineticFriction", kineticFriction, true},
         {"collisionsHoldUp", collisionsHoldUp, true}, {"stateInfoBasics", stateInfoBasics, true}, {"jsonRoundTrip", jsonRoundTrip, true},
         {"largeDeformationDamping", largeDeformationDamping, true}, {"poissonsLarge", poissonsLarge, true}, {"poissonsHigh", poissonsHigh, true},
-        {"poissonsMixed", poissonsMixed, true},
+        {"poissonsMixed", poissonsMixed, true}, {"perVoxelFloorAndDampingMultiplier", perVoxelFloorAndDampingMultiplier, true},
 #ifndef DROPIN_REFERENCE
         {"stateCheckpoint", stateCheckpoint, true}, {"copyTakesTheModel", copyTakesTheModel, true},
 #endif

@@ -30,7 +30,7 @@ def test_reference_passes_the_dropin_source(binaries):
     if "ref" not in binaries:
         pytest.skip("reference sources not available at build time")
     out = _run(binaries["ref"])
-    assert "0 failures" in out and "26 tests" in out
+    assert "0 failures" in out and "27 tests" in out
 
 
 def test_facade_host_only_classes(binaries):
@@ -42,7 +42,7 @@ def test_facade_host_only_classes(binaries):
 @pytest.mark.gpu
 def test_facade_passes_the_dropin_source_on_gpu(binaries):
     out = _run(binaries["b200"])
-    assert "0 failures" in out and "28 tests" in out
+    assert "0 failures" in out and "29 tests" in out
 
 
 def test_vxl_json_files_are_interchangeable(binaries, tmp_path):

@@ -313,7 +313,8 @@ __global__ void k_gather(Frame f, int what, const int* e2i, int first, int count
     case G_TEMP: fl[k] = meta_temp(f.pose1[i].w); break;
     case G_VOXFLAGS: {
         uint32_t b = meta_hi(f.pose1[i].w);
-        u[k] = ((b & VM_STATIC_FRIC) ? 1u : 0u) | ((((b >> VM_LINK_SHIFT) & 0x3Fu) != 0x3Fu) ? 2u : 0u) | ((b & VM_GHOST) ? 4u : 0u);
+        u[k] = ((b & VM_STATIC_FRIC) ? 1u : 0u) | ((((b >> VM_LINK_SHIFT) & 0x3Fu) != 0x3Fu) ? 2u : 0u) | ((b & VM_GHOST) ? 4u : 0u) |
+               ((b & VM_FLOOR_OFF) ? 8u : 0u) | ((b & VM_FLOOR_ON) ? 16u : 0u);
         break; }
     case G_PSTRAIN: { float4 a = f.pstrain ? f.pstrain[i] : make_float4(0, 0, 0, 0); fl[3 * k] = a.x; fl[3 * k + 1] = a.y; fl[3 * k + 2] = a.z; break; }
     case G_FORCE_NEG: case G_MOMENT_NEG: case G_FORCE_POS: case G_MOMENT_POS: {
@@ -350,7 +351,8 @@ __global__ void k_gather_voxel_state(Frame f, const int* e2i, int first, int cou
     r.linmom[0] = c.x; r.linmom[1] = c.y; r.linmom[2] = c.z; r.angmom[0] = c.w; r.angmom[1] = d.x; r.angmom[2] = d.y;
     r.temp = meta_temp(b.w);
     const uint32_t m = meta_hi(b.w);
-    r.flags = ((m & VM_STATIC_FRIC) ? 1u : 0u) | ((((m >> VM_LINK_SHIFT) & 0x3Fu) != 0x3Fu) ? 2u : 0u) | ((m & VM_GHOST) ? 4u : 0u);
+    r.flags = ((m & VM_STATIC_FRIC) ? 1u : 0u) | ((((m >> VM_LINK_SHIFT) & 0x3Fu) != 0x3Fu) ? 2u : 0u) | ((m & VM_GHOST) ? 4u : 0u) |
+              ((m & VM_FLOOR_OFF) ? 8u : 0u) | ((m & VM_FLOOR_ON) ? 16u : 0u);
     out[k] = r;
 }
 
@@ -366,7 +368,7 @@ __global__ void k_scatter(Frame f, int what, const int* e2i, int first, int coun
     case G_LINMOM: { double4 a = f.mom0[i]; a.x = d[3 * k]; a.y = d[3 * k + 1]; a.z = d[3 * k + 2]; f.mom0[i] = a; break; }
     case G_ANGMOM: { double4 a = f.mom0[i]; a.w = d[3 * k]; f.mom0[i] = a; f.mom1[i] = make_double2(d[3 * k + 1], d[3 * k + 2]); break; }
     case G_TEMP: { double w = f.pose1[i].w; f.pose1[i].w = meta_pack(fl[k], meta_hi(w)); break; }
-    case G_VOXFLAGS: { double w = f.pose1[i].w; uint32_t b = meta_hi(w); b = (b & ~VM_STATIC_FRIC) | ((u[k] & 1u) ? VM_STATIC_FRIC : 0u); f.pose1[i].w = meta_pack(meta_temp(w), b); break; }
+    case G_VOXFLAGS: { double w = f.pose1[i].w; uint32_t b = meta_hi(w); b = (b & ~(VM_STATIC_FRIC | VM_FLOOR_OFF | VM_FLOOR_ON)) | ((u[k] & 1u) ? VM_STATIC_FRIC : 0u) | ((u[k] & 8u) ? VM_FLOOR_OFF : 0u) | ((u[k] & 16u) ? VM_FLOOR_ON : 0u); f.pose1[i].w = meta_pack(meta_temp(w), b); break; }
     }
 }
 

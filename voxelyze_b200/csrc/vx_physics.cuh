@@ -318,6 +318,7 @@ __device__ __forceinline__ void voxel_integrate(VoxelState& v, d3 F, d3 M, const
                                                 const DevVoxMat& m, const DevExt* __restrict__ ext,
                                                 float dt, bool floor_on)
 {
+    floor_on = (floor_on && !(v.bits & VM_FLOOR_OFF)) || (v.bits & VM_FLOOR_ON);      // per-voxel FLOOR_ENABLED, include/VX_Voxel.h:119-120
     const uint32_t dof = ext ? (ext->dof & 0x3Fu) : 0u;
     if (dof == 0x3Fu) {                                       // fully fixed: pose prescribed
         v.pos = mk3(ext->nominal[0] + ext->translation[0], ext->nominal[1] + ext->translation[1], ext->nominal[2] + ext->translation[2]);

@@ -31,6 +31,8 @@
 
 // bits of the high word of the voxel meta
 #define VM_MAT_MASK      0x3FFu          // bits 0-9   voxel material (max 1024)
+#define VM_FLOOR_OFF     (1u << 10)      // CVX_Voxel::enableFloor(false) on this voxel while the simulation's floor is on
+#define VM_FLOOR_ON      (1u << 11)      // CVX_Voxel::enableFloor(true) on this voxel while the simulation's floor is off
 #define VM_LINK_SHIFT    16              // bits 16-21 link slot present
 #define VM_STATIC_FRIC   (1u << 22)      // FLOOR_STATIC_FRICTION
 #define VM_HAS_EXT       (1u << 23)      // entry in the externals table

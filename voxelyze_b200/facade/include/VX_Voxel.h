@@ -78,7 +78,9 @@ public:
     float transverseArea(CVX_Link::linkAxis axis);
     float transverseStrainSum(CVX_Link::linkAxis axis);
     Vec3D<float> strain(bool poissonsStrain) const;            // LCS voxel strain (VX_Voxel.cpp:300-334; private in the reference)
-    bool isFloorEnabled() const;                   // the floor is a property of the whole simulation here (CVoxelyze::enableFloor)
+    void enableFloor(bool enabled);                // include/VX_Voxel.h:119: this voxel only; CVoxelyze::enableFloor sets every voxel again
+    bool isFloorEnabled() const;                   // include/VX_Voxel.h:120
+    float dampingMultiplier();                     // include/VX_Voxel.h:130: 2 sqrt(m) zeta_internal / previousDt
 
     bool isFloorStaticFriction() const;
     float floorPenetration() const { return (float)(baseSizeAverage() / 2 - mat->nominalSize() / 2 - position().z); }
@@ -93,6 +95,7 @@ private:
     float temperatureValue() const;
     CVoxelyze* sim = nullptr;       // null for a stand-alone voxel (reference test/tVX_Voxel.h)
     int index = -1;                 // voxel index of the C-ABI (creation order)
+    int floorOverride = -1;         // enableFloor() on this voxel: 0 / 1, -1 = follows the simulation
     CVX_MaterialVoxel* mat;
     short ix, iy, iz;
     CVX_External* ext = nullptr;

@@ -119,6 +119,9 @@ private:
     mutable std::list<CVX_MaterialLink*> linkMats;
     mutable std::vector<CVX_Collision*> collisionsList;
     mutable bool stepped = false;           // dynamic state exists on the device
+    mutable std::vector<CVX_Voxel*> floorEdits;  // voxels whose per-voxel floor flag still has to reach the device
+    float previousDt = 0.0f;                // CVX_Voxel::previousDt (include/VX_Voxel.h:171), the same for every voxel
+    void applyFloorEdits() const;
     mutable float envelopeSeen = 0.0f;
 
     // host mirror of the voxel state, refreshed per step on demand

@@ -298,7 +298,17 @@ float CVX_Voxel::transverseArea(CVX_Link::linkAxis axis)
     default: return size * size;
     }
 }
-bool CVX_Voxel::isFloorEnabled() const { return sim ? sim->isFloorEnabled() : false; }
+bool CVX_Voxel::isFloorEnabled() const { return floorOverride >= 0 ? floorOverride != 0 : (sim ? sim->isFloorEnabled() : false); }
+void CVX_Voxel::enableFloor(bool enabled)
+{
+    floorOverride = enabled ? 1 : 0;
+    if (sim) sim->floorEdits.push_back(this);
+}
+float CVX_Voxel::dampingMultiplier()
+{
+    vxm::MassProps p = vxm::mass_props(mat->m_, mat->nominalSize());
+    return 2 * p.sqrt_mass * mat->m_.zeta_int / (sim ? sim->previousDt : 0.0f);
+}
 Vec3D<double> CVX_Voxel::force()
 {
     Vec3D<double> total(0, 0, 0);
@@ -669,6 +679,7 @@ void CVoxelyze::rebuildTopology() const
     mTemp.resize(n); mFlags.resize(n);
     extChangesSeen = ~0ull;
     epoch++;
+    if (!keepState) for (CVX_Voxel* v : voxelsList) if (v->floorOverride >= 0) floorEdits.push_back(v);     // a fresh device model knows no per-voxel flags
 }
 
 void CVoxelyze::sync() const
@@ -691,6 +702,24 @@ void CVoxelyze::sync() const
     }
     if (extChanges != extChangesSeen) { uploadExternals(); extChangesSeen = extChanges; epoch++; }
     if (tempAllDirty) { vx_set_temperature_all(h, ambientTemp); tempAllDirty = false; epoch++; }
+    if (!floorEdits.empty()) applyFloorEdits();
+}
+
+// per-voxel CVX_Voxel::enableFloor: the voxel's VX_VF_FLOOR_OFF / VX_VF_FLOOR_ON bits, read-modify-write (its friction bit stays)
+void CVoxelyze::applyFloorEdits() const
+{
+    std::vector<CVX_Voxel*> edits;
+    edits.swap(floorEdits);
+    for (CVX_Voxel* v : edits) {
+        if (v->index < 0 || v->index >= (int)voxelsList.size() || voxelsList[v->index] != v) continue;
+        uint32_t fl = 0;
+        if (vx_download(h, VX_F_VOXFLAGS, v->index, 1, &fl) != VX_OK) die("vx_download");
+        fl &= ~(VX_VF_FLOOR_OFF | VX_VF_FLOOR_ON);
+        if (v->floorOverride == 0 && floor) fl |= VX_VF_FLOOR_OFF;
+        if (v->floorOverride == 1 && !floor) fl |= VX_VF_FLOOR_ON;
+        if (vx_upload(h, VX_F_VOXFLAGS, v->index, 1, &fl) != VX_OK) die("vx_upload");
+    }
+    epoch++;
 }
 
 void CVoxelyze::fetchAll() const
@@ -726,9 +755,11 @@ bool CVoxelyze::doTimeStep(float dt)
     if (dt == 0) return true;
     sync();
     if (voxelsList.empty()) return true;
+    const float timeBefore = vx_time(h);
     int rc = vx_step(h, dt, 1, nullptr);
     if (rc != VX_OK && rc != VX_DIVERGED) die("vx_step");
     stepped = true; epoch++; singleFetches = 0;
+    if (rc == VX_OK) previousDt = dt > 0 ? dt : vx_time(h) - timeBefore;
     return rc == VX_OK;
 }
 
@@ -744,12 +775,17 @@ void CVoxelyze::resetTime()
 {
     sync();
     if (vx_reset(h) != VX_OK) die("vx_reset");
-    stepped = false; epoch++;
+    stepped = false; epoch++; previousDt = 0.0f;
+    for (CVX_Voxel* v : voxelsList) if (v->floorOverride >= 0) floorEdits.push_back(v);      // vx_reset keeps no per-voxel flag
 }
 
 void CVoxelyze::setAmbientTemperature(float t, bool allVoxels) { ambientTemp = t; if (allVoxels) { tempAllDirty = true; } }
 void CVoxelyze::setGravity(float g) { grav = g; for (CVX_MaterialVoxel* m : voxelMats) m->gravMult_ = g; envDirty = true; }
-void CVoxelyze::enableFloor(bool e) { floor = e; envDirty = true; }
+void CVoxelyze::enableFloor(bool e)         // src/Voxelyze.cpp:604-610: every voxel follows
+{
+    floor = e; envDirty = true;
+    for (CVX_Voxel* v : voxelsList) if (v->floorOverride >= 0) { v->floorOverride = -1; floorEdits.push_back(v); }
+}
 void CVoxelyze::enableCollisions(bool e) { if (collisions == e) return; collisions = e; envDirty = true; if (!stepped) topologyDirty = true; }
 
 // ---- links / collisions -------------------------------------------------------------------------
