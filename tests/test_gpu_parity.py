@@ -91,7 +91,10 @@ def test_lattice_path_is_selected_for_full_boxes(product):
     assert scenarios.build(product, cases.BY_NAME["mixed_six"].make(), path=1).active_path() == 1
     ell = [[i, 0, 0] for i in range(5)] + [[0, j, 0] for j in range(1, 5)]
     sparse = scenarios.Scenario("ell", 0.001, [Material()], np.array(ell, np.int32), np.zeros(len(ell), np.uint16))
-    assert scenarios.build(product, sparse).active_path() == 1
+    assert scenarios.build(product, sparse).active_path() == 2           # 9 voxels in 25 cells: a single body may be as sparse as 1 in 8
+    diag = [[i, i, i] for i in range(6)]
+    very_sparse = scenarios.Scenario("diag", 0.001, [Material()], np.array(diag, np.int32), np.zeros(len(diag), np.uint16))
+    assert scenarios.build(product, very_sparse).active_path() == 1      # 6 voxels in 216 cells: general path
     assert scenarios.build(product, cases.BY_NAME["poisson_block"].make()).active_path() == 2  # nu != 0: fused too (k_lattice_tma<.., POISSON>)
     assert scenarios.build(product, cases.BY_NAME["poisson_mixed_bilinear"].make()).active_path() == 2
 
@@ -499,6 +502,36 @@ def test_ensemble_members_stay_independent_on_both_stagings(product, path):
         snaps[p] = parity.snapshot(sim)
     for f in snaps[1]:
         assert parity.bit_equal(snaps[1][f], snaps[path][f]), f
+
+
+def test_sparse_l_shaped_body_runs_fused_from_a_brick_group_list(product, oracle):
+    """A body that fills 56 % of its bounding box (two arms of an L, 24 x 8 x 8 and 8 x 24 x 8): padded to the box, but only the
+    occupied 8 x 8 x 4 brick groups are launched (LatFrame::groups; 10 of 18 here).  Same bits as the general path, parity
+    with the oracle, and the caller sees only its own voxels."""
+    ijk = np.array([[i, j, k] for k in range(8) for j in range(24) for i in range(24) if j < 8 or i < 8], np.int32)
+    assert len(ijk) == 2560
+    mats = [Material(E=1e6, rho=1e3, zeta_global=0.01), Material(E=2e6, rho=1.5e3, zeta_global=0.01)]
+    mat = ((ijk[:, 0] // 3 + ijk[:, 1] // 3) % 2).astype(np.uint16)
+    sc = scenarios.Scenario("ell_3d", 0.005, mats, ijk, mat, gravity=0.2)
+    fixed = np.nonzero(ijk[:, 0] == 23)[0]
+    load = np.nonzero(ijk[:, 1] == 23)[0]
+    sc.ext_voxel = np.concatenate([fixed, load]).astype(np.int32)
+    sc.ext_dof = np.concatenate([np.full(len(fixed), 0x3F), np.zeros(len(load))]).astype(np.uint8)
+    f = np.zeros((len(sc.ext_voxel), 3), np.float32); f[len(fixed):] = [0.001, 0.0, -0.002]
+    sc.ext_force = f
+    runs = {}
+    for path in (0, 1):
+        g = scenarios.build(product, sc, path=path); dt = g.recommended_dt()
+        assert g.active_path() == (1 if path == 1 else 2) and g.n_voxels == len(ijk)
+        assert g.step(dt, 400) is None
+        runs[path] = g
+    assert "k_lattice_tma" in runs[0].kernel_name()
+    a, c = parity.snapshot(runs[0]), parity.snapshot(runs[1])
+    for fld in a:
+        assert parity.bit_equal(a[fld], c[fld]), fld
+    o, _, _ = parity.run(oracle, sc, 400, dt=dt)
+    err = parity.rel_errors(a, parity.snapshot(o), sc)
+    assert err["pos"] <= 1e-9 and err["orient"] <= 1e-9, err
 
 
 def test_box_with_holes_runs_fused_and_matches_the_general_path_bitwise(product, oracle):

@@ -122,6 +122,7 @@ struct vx_sim {
     bool wb_opted_in = false, capturing = false;
     bool launch_failed = false;                     // a step kernel could not be launched at all (reported by the call that queued it)
     bool state_ready = false;                       // the device arrays hold a valid state (false while vx_set_voxels rebuilds them)
+    DevBuf<int> group_list; int n_groups = 0;   // sparse bodies: the occupied brick groups (LatFrame::groups), 0 = launch the whole bounding box
     DevBuf<unsigned char> tmaps;        // CUtensorMap descriptors of the lattice arrays (k_lattice_tma), rebuilt with the arrays
     bool push_in_kernel = false;        // set around the boundary launches of vx_slab_step
     DevBuf<int> peer_flags;             // [0] arrivals from the slab below, [1] from the slab above, [2] time-out marker
@@ -237,6 +238,7 @@ struct vx_sim {
         f.col_slot = (collisions && col_tables) ? c_slot.p : nullptr;
         f.col_start = c_ref_start.p; f.col_ref = c_refs.p; f.col_force = c_pair_force.p;
         f.amb_set = 0; f.amb = 0.f;
+        f.groups = n_groups > 0 ? group_list.p : nullptr;
         f.c_ps = any_poisson ? ps[g].p : nullptr; f.n_ps = any_poisson ? ps[g ^ 1].p : nullptr;
         f.push_z[0] = f.push_z[1] = -1;
         if (push_in_kernel) {
@@ -797,7 +799,8 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     const long long grid = (bricks + VX_WB_WARPS - 1) / VX_WB_WARPS;
     // staging: TMA bulk tensor copies (7, and what 0 picks on large lattices) or per-lane cp.async (5, and what 0 picks for
     // ensembles of small boxes, where whole-box copies fetch too much padding: 1.15 against 1.19 ms on 4096 robots of 10^3)
-    const bool want_tma = s->path == 7 || (s->path != 5 && grouped) || s->any_poisson;     // Poisson coupling lives in the TMA-staged kernel only
+    const bool listed = s->n_groups > 0 && ngz < 0;                 // sparse body: only its occupied brick groups
+    const bool want_tma = s->path == 7 || (s->path != 5 && grouped) || s->any_poisson || listed;     // Poisson coupling and group lists live in the TMA-staged kernel only
     // (tensor maps are built outside stream capture: ensure_lattice_graph launches nothing before they exist)
     const bool tma = want_tma && (s->tmaps.p || (!s->capturing && build_tensor_maps(s) == VX_OK));
     lattice_opt_in(s);
@@ -811,8 +814,9 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
             // grouped: one CTA per 2x2x2 group of bricks on a 3-D grid (no index divisions in the kernel); a grid too tall for
             // blockIdx.y/z falls back to the 1-D brick enumeration, which covers the same bricks
             const long long zdim = (long long)nbz * s->lat_members;
-            const bool g3 = grouped && VX_WB_WARPS == 8 && nby <= 65535 && zdim <= 65535;
-            const dim3 gr = g3 ? dim3((unsigned)nbx, (unsigned)nby, (unsigned)zdim) : dim3((unsigned)(((long long)bx * by * (ngz >= 0 ? 2 * ngz : bz) * s->lat_members + VX_WB_WARPS - 1) / VX_WB_WARPS));
+            const bool g3 = (grouped || listed) && VX_WB_WARPS == 8 && nby <= 65535 && zdim <= 65535;
+            if (!listed) f.groups = nullptr;
+            const dim3 gr = listed ? dim3((unsigned)s->n_groups) : g3 ? dim3((unsigned)nbx, (unsigned)nby, (unsigned)zdim) : dim3((unsigned)(((long long)bx * by * (ngz >= 0 ? 2 * ngz : bz) * s->lat_members + VX_WB_WARPS - 1) / VX_WB_WARPS));
             const int kx = g3 ? nbx : bx, ky = g3 ? nby : by, kz = g3 ? nbz : (ngz >= 0 ? 2 * ngz : bz), koff = g3 ? gz_off : 2 * gz_off, gr_ = g3 ? 1 : 0;
             if (s->any_poisson) k_lattice_tma<false, false, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
             else if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
@@ -1064,7 +1068,7 @@ void vx_destroy(vx_sim* s)
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->ev_boundary) cudaEventDestroy(s->ev_boundary);
     if (s->ev_comm) cudaEventDestroy(s->ev_comm);
-    s->peer_flags.release(); s->tmaps.release();
+    s->peer_flags.release(); s->tmaps.release(); s->group_list.release();
     s->drop_graph();
     for (int g = 0; g < 2; g++) { s->release_pose(g); s->mom0[g].release(); s->mom1[g].release(); s->rec[g].release(); s->ps[g].release(); }
     s->pair_lmat.release(); s->link_owner.release(); s->link_axis_dev.release();
@@ -1165,7 +1169,12 @@ int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, con
         if (sim_id) { if (sim_id[i] < 0 || sim_id[i] > 65535) return fail(s, VX_ERR_ARG, "bad member id"); members = std::max(members, sim_id[i] + 1); }
     }
     const long long ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1, cells = ex * ey * ez * members;
-    if (cells == n || cells > (long long)(1.6 * n) || cells > 2000000000LL) return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
+    // up to 60 % more cells for any model; a single body without halo voxels may be as sparse as one voxel in eight cells
+    // (only its occupied 8x8x4 brick groups are launched, LatFrame::groups), as long as the padded arrays stay below ~60 GB
+    bool user_flags = false;
+    if (flags) for (int i = 0; i < n && !user_flags; i++) user_flags = flags[i] != 0;
+    const double max_ratio = (members == 1 && !user_flags && cells <= 100000000LL) ? 8.0 : 1.6;
+    if (cells == n || cells > (long long)(max_ratio * n) || cells > 2000000000LL) return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
     std::vector<char> used((size_t)cells, 0);
     for (int i = 0; i < n; i++) {
         const long long c = ((((long long)(sim_id ? sim_id[i] : 0) * ez + (ijk[3 * i + 2] - lo[2])) * ey + (ijk[3 * i + 1] - lo[1])) * ex + (ijk[3 * i] - lo[0]));
@@ -1368,6 +1377,26 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     if (rc != VX_OK) return rc;
     if (s->collisions) { rc = build_collision_tables(s); if (rc != VX_OK) return rc; }
     find_boundary_layers(s);
+    // sparse body on the fused layout: list of the 8x8x4 brick groups that hold at least one real voxel
+    s->n_groups = 0;
+    if (s->lattice && s->N_user < s->N && s->lat_members == 1 && s->zb_layers.empty()) {
+        const int gx = (s->nx + 2 * VX_WB_X - 1) / (2 * VX_WB_X), gy = (s->ny + 2 * VX_WB_Y - 1) / (2 * VX_WB_Y), gz = (s->nz + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z);
+        if (gx <= 1024 && gy <= 1024 && gz <= 2048) {
+            std::vector<char> occupied((size_t)gx * gy * gz, 0);
+            for (int e = 0; e < s->N_user; e++) {
+                const int x = ijk[3 * e] - lo[0], y = ijk[3 * e + 1] - lo[1], z = ijk[3 * e + 2] - lo[2];
+                occupied[((size_t)(z / (2 * VX_WB_Z)) * gy + y / (2 * VX_WB_Y)) * gx + x / (2 * VX_WB_X)] = 1;
+            }
+            std::vector<int> list;
+            for (int z = 0; z < gz; z++) for (int y = 0; y < gy; y++) for (int x = 0; x < gx; x++)
+                if (occupied[((size_t)z * gy + y) * gx + x]) list.push_back(x | (y << 10) | (z << 20));
+            if (list.size() * 10 <= occupied.size() * 9) {               // worth it from 10 % empty groups on
+                CK(s->group_list.alloc(list.size()));
+                CK(cudaMemcpy(s->group_list.p, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
+                s->n_groups = (int)list.size();
+            }
+        }
+    }
     // a voxel set replaced in the middle of a run: simulation time and CVX_Voxel::previousDt go on (setVoxel does not
     // touch them, src/Voxelyze.cpp:422-498); vx_reset is what rewinds them
     const float time = s->time_host, prev_dt = s->prev_dt_host;

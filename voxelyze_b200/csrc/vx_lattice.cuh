@@ -58,6 +58,9 @@ struct LatFrame {
     // CVoxelyze::setAmbientTemperature(t, true) applied by the step itself: every voxel reads temperature `amb` instead of
     // its stored one in this launch and carries it into the new generation (no separate pass over the voxels)
     int amb_set; float amb;
+    // sparse bodies (k_lattice_tma, grouped grids): the occupied 8x8x4-voxel brick groups, gx | gy << 10 | gz << 20, one CTA each
+    // (null: every group of the bounding box is launched)
+    const int* groups;
     // Poisson coupling (nu != 0, k_lattice_tma<.., POISSON>): CVX_Voxel::pStrain of every voxel as of the state the step reads
     // (= computed from the link strains of the previous step), double-buffered like the voxel state
     const float4* c_ps; float4* n_ps;
@@ -638,7 +641,11 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     const uint32_t bar0 = sb + 13312, bar1 = sb + 13320, bar2 = sb + 13328;
 
     int x0, y0, z0, member;
-    if (grouped) {
+    if (grouped && f.groups) {                          // brick-group list of a sparse body
+        const int gid = __ldg(f.groups + blockIdx.x);
+        member = 0;
+        x0 = ((gid & 1023) * 2 + (warp & 1)) * VX_WB_X; y0 = (((gid >> 10) & 1023) * 2 + ((warp >> 1) & 1)) * VX_WB_Y; z0 = ((gid >> 20) * 2 + (warp >> 2)) * VX_WB_Z;
+    } else if (grouped) {
         const unsigned zz = blockIdx.z;
         member = gridDim.z > (unsigned)nbz ? (int)(zz / (unsigned)nbz) : 0;
         const int gz = gz_off + (int)zz - member * nbz;
