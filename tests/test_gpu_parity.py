@@ -138,6 +138,28 @@ def test_diverging_step_semantics(product, oracle):
         assert abs(g.time() - o.time()) <= 1e-9
 
 
+@pytest.mark.parametrize("path", [0, 1], ids=["fused", "general"])
+def test_diverging_step_with_collisions_enabled(product, oracle, path):
+    """with self-collisions on, the step that diverges must not touch the watch lists or the contact forces (the
+    reference returns before updateCollisions, src/Voxelyze.cpp:265-271) -- also inside a multi-step call on the fused path,
+    where the divergence flag of a step lives in the flag of its generation."""
+    sc = cases.BY_NAME["data_curve_fail"].make()
+    sc.collisions = True
+    g, dt, dg = parity.run(product, sc, 2900, path=path)
+    o, _, do = parity.run(oracle, sc, 2900)
+    assert dg == do and dg is not None
+    assert g.active_path() == (1 if path == 1 else 2)
+    sg, so = parity.snapshot(g), parity.snapshot(o)
+    err = parity.rel_errors(sg, so, sc)
+    assert err["pos"] <= 1e-7 and err["strain"] <= 1e-6, err
+    pg, po = g.collision_pairs(), o.collision_pairs()
+    assert np.array_equal(pg[np.lexsort(pg.T[::-1])] if len(pg) else pg, po[np.lexsort(po.T[::-1])] if len(po) else po)
+    # a second call after the divergence: still diverged at once, nothing moves
+    before = g.download("pos")
+    assert g.step(dt, 5) == o.step(dt, 5) == 0
+    assert np.array_equal(before, g.download("pos"))
+
+
 @pytest.mark.parametrize("path", [0, 1], ids=["auto", "general"])
 def test_determinism_two_runs_bit_equal(product, path):
     sc = scenarios.cantilever(16, 6, 5)

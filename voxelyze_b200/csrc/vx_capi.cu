@@ -221,7 +221,7 @@ struct vx_sim {
     LatFrame lat_frame(int g) const
     {
         LatFrame f{};
-        f.nx = nx; f.ny = ny; f.nz = nz; f.nxy = nx * ny; f.n_vox = N; f.n_mat = (int)mats.size();
+        f.nx = nx; f.ny = ny; f.nz = nz; f.nxy = nx * ny; f.n_vox = N; f.n_mat = (int)mats.size(); f.n_lmat = (int)lmats.size();
         f.c_pose0 = pose0[g].p; f.c_pose1 = pose1[g].p; f.c_mom0 = mom0[g].p; f.c_mom1 = mom1[g].p;
         f.n_pose0 = pose0[g ^ 1].p; f.n_pose1 = pose1[g ^ 1].p; f.n_mom0 = mom0[g ^ 1].p; f.n_mom1 = mom1[g ^ 1].p;
         for (int a = 0; a < 3; a++) {
@@ -780,10 +780,10 @@ static void lattice_opt_in(vx_sim* s)
     cudaFuncSetAttribute(k_lattice_warp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
     cudaFuncSetAttribute(k_lattice_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_WB_SMEM);
     cudaFuncSetAttribute(k_lattice_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
-    cudaFuncSetAttribute(k_lattice_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
     cudaFuncSetAttribute(k_lattice_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
-    cudaFuncSetAttribute(k_lattice_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
-    cudaFuncSetAttribute(k_lattice_tma<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
+    cudaFuncSetAttribute(k_lattice_tma<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
     s->wb_opted_in = true;
 }
 
@@ -818,13 +818,17 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
             if (!listed) f.groups = nullptr;
             const dim3 gr = listed ? dim3((unsigned)s->n_groups) : g3 ? dim3((unsigned)nbx, (unsigned)nby, (unsigned)zdim) : dim3((unsigned)(((long long)bx * by * (ngz >= 0 ? 2 * ngz : bz) * s->lat_members + VX_WB_WARPS - 1) / VX_WB_WARPS));
             const int kx = g3 ? nbx : bx, ky = g3 ? nby : by, kz = g3 ? nbz : (ngz >= 0 ? 2 * ngz : bz), koff = g3 ? gz_off : 2 * gz_off, gr_ = g3 ? 1 : 0;
-            if (s->any_poisson) k_lattice_tma<false, false, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
+            // multi-material models: tables staged in the CTA's shared memory when they fit behind the warp windows
+            const size_t tab = s->mats.size() * sizeof(DevVoxMat) + s->lmats.size() * sizeof(DevLinkMat) + s->mats.size() * 4 + s->mats.size() * s->mats.size() * 2;
+            const int stage = (!s->uni && tab <= VX_TMA_TABLE_BYTES - 16) ? 1 : 0;
+            const size_t tma_smem = VX_TMA_SMEM + (stage ? VX_TMA_TABLE_BYTES : 0);
+            if (s->any_poisson) k_lattice_tma<false, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
             else if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
-                if (s->uni) k_lattice_tma<true, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
-                else k_lattice_tma<false, true><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
+                if (s->uni) k_lattice_tma<true, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
+                else k_lattice_tma<false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
             } else {
-                if (s->uni) k_lattice_tma<true, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
-                else k_lattice_tma<false, false><<<gr, bl, VX_TMA_SMEM, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_);
+                if (s->uni) k_lattice_tma<true, false><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
+                else k_lattice_tma<false, false><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
             }
         } else if (s->any_poisson) {
             s->err = "Poisson materials on the fused layout need the TMA-staged kernel (tensor maps could not be built)"; s->launch_failed = true;

@@ -36,7 +36,7 @@ namespace vxd {
 #define VX_REC_PARTS 12       // sixteen-byte parts of the link records of one voxel: axis a -> parts 4a..4a+2 (double2) and 4a+3 (float4)
 
 struct LatFrame {
-    int nx, ny, nz, nxy, n_vox, n_mat;
+    int nx, ny, nz, nxy, n_vox, n_mat, n_lmat;
     // voxel state, current (read) and next (write) generation
     const double4* c_pose0; const double4* c_pose1; const double4* c_mom0; const double2* c_mom1;
     double4* n_pose0; double4* n_pose1; double4* n_mom0; double2* n_mom1;
@@ -66,6 +66,12 @@ struct LatFrame {
     const float4* c_ps; float4* n_ps;
 };
 
+// where a kernel reads the material tables of a multi-material model: global memory (through L1), or a copy the CTA staged
+// in its shared memory (k_lattice_tma when the tables are small, which they are for every BASELINE config) together with the
+// internal-damping factor 2 sqrt(m) zeta / previousDt of every voxel material, divided once per CTA instead of per link end
+struct MatView { const DevVoxMat* vmat; const DevLinkMat* lmat; const uint16_t* pair; const float* damp; int n_mat; };
+__device__ __forceinline__ MatView mat_view(const LatFrame& f) { MatView m; m.vmat = f.vmat; m.lmat = f.lmat; m.pair = f.pair_lmat; m.damp = nullptr; m.n_mat = f.n_mat; return m; }
+
 __device__ __forceinline__ void lat_decode(double2 a, double2 b, double2 c, float4 s, uint32_t lflags, LinkState& st)
 {
     st.small_angle = (lflags & 1u) != 0;
@@ -91,15 +97,17 @@ __device__ __forceinline__ void lat_eval_link_rec(const LatFrame& f, int axis, u
                                                   double2 ra, double2 rb, double2 rc, float4 rs,
                                                   double4 n0, double4 n1, double4 p0, double4 p1, float prev_dt,
                                                   LinkState& st, d3& fN, d3& mN, d3& fP, d3& mP, float damp_uni = -1.0f,
-                                                  const float4* psn = nullptr, const float4* psp = nullptr, float* end_strain = nullptr)
+                                                  const float4* psn = nullptr, const float4* psp = nullptr, float* end_strain = nullptr,
+                                                  const MatView* tables = nullptr)
 {
     // psn/psp: Poisson strains of the two end voxels (nu != 0 models); end_strain[0/1]: axial strain of the half of the link
     // inside the negative / positive end voxel (CVX_Link::axialStrain(bool), src/VX_Link.cpp:121-124), input of the next pStrain
     // damp_uni: single-material models may pass 2*sqrtMass*zeta/previousDt computed once per kernel (same float division)
     const uint32_t hn = meta_hi(n1.w), hp = meta_hi(p1.w);
-    const DevVoxMat& vmn = UNI ? f.vm0 : f.vmat[hn & VM_MAT_MASK];
-    const DevVoxMat& vmp = UNI ? f.vm0 : f.vmat[hp & VM_MAT_MASK];
-    const DevLinkMat& lm = UNI ? f.lm0 : f.lmat[f.pair_lmat[(hn & VM_MAT_MASK) * f.n_mat + (hp & VM_MAT_MASK)]];
+    const MatView mv = tables ? *tables : mat_view(f);
+    const DevVoxMat& vmn = UNI ? f.vm0 : mv.vmat[hn & VM_MAT_MASK];
+    const DevVoxMat& vmp = UNI ? f.vm0 : mv.vmat[hp & VM_MAT_MASK];
+    const DevLinkMat& lm = UNI ? f.lm0 : mv.lmat[mv.pair[(hn & VM_MAT_MASK) * mv.n_mat + (hp & VM_MAT_MASK)]];
     lat_decode(ra, rb, rc, rs, (owner_bits >> (VM_LFLAG_SHIFT + 2 * axis)) & 3u, st);
     // CVX_Link::updateRestLength (src/VX_Link.cpp:137-140)
     const float tn = f.amb_set ? f.amb : meta_temp(n1.w), tp = f.amb_set ? f.amb : meta_temp(p1.w);
@@ -111,6 +119,7 @@ __device__ __forceinline__ void lat_eval_link_rec(const LatFrame& f, int axis, u
     } else t_area = 0.5f * (vmn.nom_f * vmn.nom_f + vmp.nom_f * vmp.nom_f);
     float damp_n, damp_p;
     if (UNI && damp_uni >= 0.0f) damp_n = damp_p = damp_uni;
+    else if (!UNI && mv.damp) { damp_n = mv.damp[hn & VM_MAT_MASK]; damp_p = mv.damp[hp & VM_MAT_MASK]; }
     else { damp_n = vmn.two_sqrtm_zeta / prev_dt; damp_p = vmp.two_sqrtm_zeta / prev_dt; }
     q4 on, op;
     on.w = n0.w; on.x = n1.x; on.y = n1.y; on.z = n1.z;
@@ -581,6 +590,7 @@ enum { TM_P_OWN, TM_P_XF, TM_P_YF, TM_P_ZF, TM_M0, TM_M1, TM_REC_OWN, TM_REC_XF,
 // =================================================================================================
 #define VX_TMA_WARP_BYTES 13440
 #define VX_TMA_SMEM (VX_WB_WARPS * VX_TMA_WARP_BYTES)
+#define VX_TMA_TABLE_BYTES 6144                         // room for staged material tables behind the warp windows (2 CTAs/SM still fit)
 
 __device__ __forceinline__ bool elect_one()
 {
@@ -624,9 +634,10 @@ __device__ __forceinline__ void tma_4d(uint32_t dst, const void* map, uint32_t b
 //       else (ensembles of small boxes) -> 1-D, eight consecutive bricks per CTA, bricks x-fastest, no padding.
 template <bool UNI, bool PUSH, bool POISSON = false>
 __global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
-k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book, int grouped)
+k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book, int grouped, int stage_tables)
 {
     // nbx/nby/nbz, gz_off, book, grouped, PUSH: as in k_lattice_warp
+    // stage_tables (multi-material models): the CTA copies the material tables into its shared memory behind the warp windows
     extern __shared__ __align__(128) unsigned char tma_smem[];
     DevParams* p = f.params;
     // the step scalars are requested first and looked at only after the bulk copies are on their way
@@ -685,6 +696,23 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     const int frozen = div_prev | div_latched;
     const float prev_dt = first_of_call ? prev_dt_call : dt;
     const float damp_u = UNI ? f.vm0.two_sqrtm_zeta / prev_dt : -1.0f;
+    // ---- multi-material models: material tables into shared memory (all 256 threads, while the bulk copies are in flight)
+    MatView tables = mat_view(f);
+    if (!UNI && stage_tables) {
+        unsigned char* tb = tma_smem + VX_TMA_SMEM;
+        const int nv = f.n_mat, nl = f.n_lmat;
+        DevVoxMat* s_vm = reinterpret_cast<DevVoxMat*>(tb);
+        DevLinkMat* s_lm = reinterpret_cast<DevLinkMat*>(tb + nv * sizeof(DevVoxMat));
+        float* s_damp = reinterpret_cast<float*>(tb + nv * sizeof(DevVoxMat) + nl * sizeof(DevLinkMat));
+        uint16_t* s_pair = reinterpret_cast<uint16_t*>(s_damp + nv);
+        const int w_vm = nv * (int)(sizeof(DevVoxMat) / 8), w_lm = nl * (int)(sizeof(DevLinkMat) / 8);
+        for (int i = threadIdx.x; i < w_vm; i += blockDim.x) reinterpret_cast<double*>(s_vm)[i] = reinterpret_cast<const double*>(f.vmat)[i];
+        for (int i = threadIdx.x; i < w_lm; i += blockDim.x) reinterpret_cast<double*>(s_lm)[i] = reinterpret_cast<const double*>(f.lmat)[i];
+        for (int i = threadIdx.x; i < nv * nv; i += blockDim.x) s_pair[i] = f.pair_lmat[i];
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) s_damp[i] = f.vmat[i].two_sqrtm_zeta / prev_dt;
+        __syncthreads();                                // once per CTA, before any warp leaves
+        tables.vmat = s_vm; tables.lmat = s_lm; tables.pair = s_pair; tables.damp = s_damp;
+    }
     if (book && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
         if (frozen) p->div_latched = 1;
         else if (p->pending) { p->steps_done += 1; p->time += dt; }
@@ -751,7 +779,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                                make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
                                make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
                                n0, n1, p0, p1, prev_dt, st, fN, mN, hF, hM, damp_u,
-                               POISSON ? &h_psn : nullptr, POISSON ? &h_psp : nullptr, POISSON ? h_end : nullptr);
+                               POISSON ? &h_psn : nullptr, POISSON ? &h_psp : nullptr, POISSON ? h_end : nullptr, &tables);
     }
     __syncwarp();                          // every lane has read its round-H inputs: their space is re-used now
     double (*hslot)[32] = reinterpret_cast<double (*)[32]>(wbase + 9216);                 // [comp][entering link]
@@ -808,7 +836,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                                    make_double2(__hiloint2double(r2.y, r2.x), __hiloint2double(r2.w, r2.z)),
                                    make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
                                    n0, n1, p0, p1, prev_dt, st, fN, mN, fP, mP, damp_u,
-                                   POISSON ? &ps_own : nullptr, POISSON ? &psp : nullptr, POISSON ? end_s : nullptr);
+                                   POISSON ? &ps_own : nullptr, POISSON ? &psp : nullptr, POISSON ? end_s : nullptr, &tables);
             double2 wa, wb, wc; float4 ws; uint32_t lf;
             lat_encode(st, wa, wb, wc, ws, lf);
             double2* nr = f.n_rec[0][0] + (size_t)(a * 4) * f.n_vox + v;
@@ -852,7 +880,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
     vs.ang = mk3(__hiloint2double(q1.w, q1.z), __hiloint2double(q2.y, q2.x), __hiloint2double(q2.w, q2.z));
     if (vs.bits & VM_GHOST) { reinterpret_cast<uint32_t*>(&f.n_pose1[v].w)[1] = vs.bits; return; }   // see k_lattice_warp
     {
-        const DevVoxMat& vm = UNI ? f.vm0 : f.vmat[vs.bits & VM_MAT_MASK];
+        const DevVoxMat& vm = UNI ? f.vm0 : tables.vmat[vs.bits & VM_MAT_MASK];
         const DevExt* ext = (vs.bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
         const int* refs = nullptr; int n_refs = 0;
         if (f.col_slot && ((vs.bits >> VM_LINK_SHIFT) & 0x3Fu) != 0x3Fu) {        // only surface voxels are ever watched
