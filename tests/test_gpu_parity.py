@@ -526,6 +526,40 @@ def test_ensemble_members_stay_independent_on_both_stagings(product, path):
         assert parity.bit_equal(snaps[1][f], snaps[path][f]), f
 
 
+def test_single_material_grids_equal_the_general_path_bitwise(product):
+    """The single-material instantiation (k_lattice_tma<UNI>: no table look-ups) on the three grids it runs on -- a box with odd
+    edges on every axis, an ensemble stacked along z, and the brick-group list of a sparse body -- against the general
+    two-kernel path, bit for bit, with both stagings."""
+    M = Material(E=2e6, rho=1.2e3, zeta_global=0.02, zeta_internal=0.5, cte=0.004, mu_static=1.0, mu_kinetic=0.5)
+    # (a) odd box
+    sc = scenarios.cantilever(21, 14, 11, tip_load=40.0)
+    # (b) 7 members of 9 x 6 x 5 on a floor, different loads, ambient temperature program
+    base = scenarios.box_ijk(9, 6, 5)
+    ijk = np.tile(base, (7, 1)); sid = np.repeat(np.arange(7), len(base)).astype(np.int32)
+    ens = scenarios.Scenario("uni_members", 0.005, [M], ijk, np.zeros(len(ijk), np.uint16), sim_id=sid, gravity=1.0, floor=True)
+    top = np.nonzero((ijk[:, 2] == 4) & (ijk[:, 0] == 8))[0]
+    ens.ext_voxel = top.astype(np.int32); ens.ext_dof = np.zeros(len(top), np.uint8)
+    ens.ext_force = np.stack([0.002 * (sid[top] - 3), np.zeros(len(top)), -0.001 * sid[top]], 1).astype(np.float32)
+    # (c) an L of one material
+    lijk = np.array([[i, j, k] for k in range(8) for j in range(24) for i in range(24) if j < 8 or i < 8], np.int32)
+    ell = scenarios.Scenario("ell_uni", 0.005, [M], lijk, np.zeros(len(lijk), np.uint16), gravity=0.3)
+    fixed = np.nonzero(lijk[:, 0] == 23)[0]
+    ell.ext_voxel = fixed.astype(np.int32); ell.ext_dof = np.full(len(fixed), 0x3F, np.uint8); ell.ext_force = np.zeros((len(fixed), 3), np.float32)
+    for name, s, path, steps, temp in (("box", sc, 5, 300, False), ("members", ens, 5, 300, True), ("ell", ell, 0, 300, False)):
+        snaps = {}
+        for p in (1, 7, path):
+            sim = scenarios.build(product, s, path=p); dt = sim.recommended_dt()
+            assert sim.active_path() == (1 if p == 1 else 2)
+            for k in range(steps // 5):
+                if temp:
+                    sim.set_temperature_all(scenarios.robot_temperature(k * dt) * 3)
+                assert sim.step(dt, 5) is None
+            snaps[p] = parity.snapshot(sim)
+        for p in (7, path):
+            for f in snaps[1]:
+                assert parity.bit_equal(snaps[1][f], snaps[p][f]), (name, p, f)
+
+
 def test_sparse_l_shaped_body_runs_fused_from_a_brick_group_list(product, oracle):
     """A body that fills 56 % of its bounding box (two arms of an L, 24 x 8 x 8 and 8 x 24 x 8): padded to the box, but only the
     occupied 8 x 8 x 4 brick groups are launched (LatFrame::groups; 10 of 18 here).  Same bits as the general path, parity
