@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define VX_ABI_VERSION 2
+#define VX_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------- */
 #define VX_OK              0
@@ -58,6 +58,7 @@ extern "C" {
 #define VX_ERR_TOPOLOGY   -5
 #define VX_ERR_UNSUPPORTED -6
 #define VX_ERR_ALLOC      -7
+#define VX_ERR_SOLVER     -8  /* vx_linear_solve: singular system or no convergence (CVX_LinearSolver::solve returning false) */
 
 typedef struct vx_sim vx_sim;
 
@@ -266,6 +267,19 @@ int  vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds);
 /* replaces CVoxelyze::stateInfo (src/Voxelyze.cpp:752-800); info/type use the
  * reference's enum values (include/Voxelyze.h:48-67).                                */
 int  vx_state_info(vx_sim* s, int info, int type, float* out);
+
+/* ---- static solve -------------------------------------------------------
+ * replaces CVoxelyze::doLinearSolve (src/Voxelyze.cpp:243-249) = CVX_LinearSolver::solve (src/VX_LinearSolver.cpp:49-113):
+ * the model is linearised about the nominal lattice (only the beam constants a1, a2, b1, b2, b3 of the link materials
+ * enter, calculateA :116-233), degrees of freedom fixed through CVX_External keep their CURRENT displacement / rotation
+ * vector, the others carry the external force / moment (applyBX :273-328), and the solution overwrites the voxel poses:
+ * pos = originalPosition + u, orient = Quat3D(rotation vector), momenta zero; link state is left as it was
+ * (postResults :336-347).  The reference factorises with PARDISO; here the system is solved matrix-free by a
+ * preconditioned conjugate-gradient iteration in FP64 on the device, to the relative residual |r| <= rel_tol * |r0|
+ * (rel_tol <= 0: 1e-10; max_iter <= 0: 200 000).  Returns VX_OK (poses written), or VX_ERR_SOLVER with the state
+ * untouched when a part of the model is not held (singular matrix; PARDISO error -4) or max_iter was not enough.
+ * iterations / rel_residual may be NULL.  Ensembles are solved as one block-diagonal system.                        */
+int  vx_linear_solve(vx_sim* s, double rel_tol, int max_iter, int* iterations, double* rel_residual);
 
 /* ---- deformed surface mesh ---------------------------------------------
  * replaces CVX_MeshRender (include/VX_MeshRender.h:26-62, src/VX_MeshRender.cpp:49-218) and what it calls per vertex,

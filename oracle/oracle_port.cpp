@@ -1158,4 +1158,111 @@ int vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds)
     return vx_collision_pairs(s, nullptr, 0, n_pairs);
 }
 
+// ---- static solve: CVX_LinearSolver (src/VX_LinearSolver.cpp), restated with a banded Cholesky factorisation in place of
+// PARDISO.  Element matrices are written out per link (12 x 12, "voxel 1" = the end with the lower voxelsList index,
+// :173), scattered into a symmetric band, the fixed dofs eliminated as applyBX does (:302-327), results posted as
+// postResults does (:336-347).  rel_tol / max_iter do not apply to a direct solve.
+int vx_linear_solve(vx_sim* s, double, int, int* iterations, double* rel_residual)
+{
+    if (iterations) *iterations = 0;
+    if (rel_residual) *rel_residual = 0.0;
+    if (!s) return VX_ERR_ARG;
+    const int nv = (int)s->vox.size(), dof = 6 * nv;
+    if (dof == 0) return fail(s, VX_ERR_ARG, "vx_linear_solve: no voxels");                        // :60
+    int bw = 5;
+    for (const Link& l : s->links) bw = std::max(bw, 6 * std::abs(l.vn - l.vp) + 5);
+    if ((double)dof * (bw + 1) > 4e8) return fail(s, VX_ERR_ALLOC, "vx_linear_solve (oracle): band too large for the direct solve");
+    const size_t W = (size_t)bw + 1;
+    std::vector<double> U((size_t)dof * W, 0.0);                                                   // U[i*W + (j-i)], j >= i
+    auto at = [&](int i, int j) -> double& { return i <= j ? U[(size_t)i * W + (j - i)] : U[(size_t)j * W + (i - j)]; };
+    for (const Link& l : s->links) {
+        const LinkMat& m = s->lmats[l.lmat];
+        const int i1 = std::min(l.vn, l.vp), i2 = std::max(l.vn, l.vp), ax = l.axis;            // :171-173
+        double Ke[12][12] = {};
+        auto sym = [&](int r, int c, double v) { Ke[r][c] += v; if (r != c) Ke[c][r] += v; };
+        for (int j = 0; j < 3; j++) {
+            const float dt = (ax == j) ? m.a1 : m.b1;                                              // :182-187
+            sym(j, j, dt); sym(j, 6 + j, -dt); sym(6 + j, 6 + j, dt);
+            const float dr = (ax == j) ? m.a2 : 2 * m.b3, orr = (ax == j) ? -m.a2 : m.b3;          // :189-195
+            sym(3 + j, 3 + j, dr); sym(3 + j, 9 + j, orr); sym(9 + j, 9 + j, dr);
+        }
+        int R1, C1, R2, C2; float val;                                                             // :199-217
+        if (ax == 0) { R1 = 1; C1 = 5; R2 = 2; C2 = 4; val = m.b2; }
+        else if (ax == 1) { R1 = 0; C1 = 5; R2 = 2; C2 = 3; val = -m.b2; }
+        else { R1 = 0; C1 = 4; R2 = 1; C2 = 3; val = m.b2; }
+        sym(R1, C1, val); sym(R1, 6 + C1, val); sym(C1, 6 + R1, -val); sym(6 + R1, 6 + C1, -val);  // :219-222
+        sym(R2, C2, -val); sym(R2, 6 + C2, -val); sym(C2, 6 + R2, val); sym(6 + R2, 6 + C2, val);  // :224-227
+        for (int r = 0; r < 12; r++)
+            for (int c = r; c < 12; c++) {
+                if (Ke[r][c] == 0.0) continue;
+                const int gr = (r < 6 ? 6 * i1 + r : 6 * i2 + r - 6), gc = (c < 6 ? 6 * i1 + c : 6 * i2 + c - 6);
+                at(gr, gc) += Ke[r][c];
+            }
+    }
+    std::vector<double> x(dof, 0.0), b(dof, 0.0); std::vector<char> fixed(dof, 0);
+    for (int i = 0; i < nv; i++) {                                                                 // :281-300
+        const Voxel& v = s->vox[i];
+        const double sz = s->vmats[v.mat].nom;
+        const V3 disp = sub(v.pos, V3{v.ix * sz, v.iy * sz, v.iz * sz});
+        const V3 ang = v.orient.w == 1 ? V3{} : to_rotation_vector(v.orient);
+        const double u[6] = {disp.x, disp.y, disp.z, ang.x, ang.y, ang.z};
+        const Ext* e = v.ext >= 0 ? &s->exts[v.ext] : nullptr;
+        for (int j = 0; j < 6; j++) {
+            const int d = 6 * i + j;
+            x[d] = u[j];
+            fixed[d] = e ? ((e->dof >> j) & 1) : 0;
+            if (!fixed[d] && e) b[d] = j < 3 ? e->f[j] : e->m[j - 3];
+        }
+    }
+    for (int d = 0; d < dof; d++) {                                                                // :302-327
+        if (!fixed[d]) continue;
+        const int lo = std::max(0, d - bw), hi = std::min(dof - 1, d + bw);
+        for (int i = lo; i <= hi; i++) if (i != d) { b[i] -= x[d] * at(i, d); }
+    }
+    for (int d = 0; d < dof; d++) {
+        if (!fixed[d]) continue;
+        const int lo = std::max(0, d - bw), hi = std::min(dof - 1, d + bw);
+        for (int i = lo; i <= hi; i++) at(i, d) = 0.0;
+        at(d, d) = 1.0; b[d] = x[d];
+    }
+    // U^T U factorisation in the band, then two triangular solves
+    std::vector<double> diag0(dof);
+    for (int k = 0; k < dof; k++) diag0[k] = U[(size_t)k * W];
+    for (int k = 0; k < dof; k++) {
+        double* row = &U[(size_t)k * W];
+        if (!(row[0] > 1e-11 * diag0[k])) return fail(s, VX_ERR_SOLVER, "vx_linear_solve: the stiffness matrix is singular (a part of the model is not held) or not positive definite");      // pivot lost to cancellation: singular to working precision
+        const double piv = std::sqrt(row[0]);
+        const int m = std::min(bw, dof - 1 - k);
+        for (int j = 0; j <= m; j++) row[j] /= piv;
+        for (int i = 1; i <= m; i++) {
+            const double f = row[i];
+            if (f == 0.0) continue;
+            double* ri = &U[(size_t)(k + i) * W];
+            for (int j = i; j <= m; j++) ri[j - i] -= f * row[j];
+        }
+    }
+    for (int k = 0; k < dof; k++) {                                                                // U^T y = b
+        const double* row = &U[(size_t)k * W];
+        b[k] /= row[0];
+        const int m = std::min(bw, dof - 1 - k);
+        for (int j = 1; j <= m; j++) b[k + j] -= row[j] * b[k];
+    }
+    for (int k = dof - 1; k >= 0; k--) {                                                           // U x = y
+        const double* row = &U[(size_t)k * W];
+        const int m = std::min(bw, dof - 1 - k);
+        double t = b[k];
+        for (int j = 1; j <= m; j++) t -= row[j] * b[k + j];
+        b[k] = t / row[0];
+    }
+    for (int i = 0; i < nv; i++) {                                                                 // :336-347
+        Voxel& v = s->vox[i];
+        const double sz = s->vmats[v.mat].nom;
+        v.pos = add(V3{v.ix * sz, v.iy * sz, v.iz * sz}, V3{b[6 * i], b[6 * i + 1], b[6 * i + 2]});
+        v.linMom = V3{};
+        v.orient = from_rotation_vector(V3{b[6 * i + 3], b[6 * i + 4], b[6 * i + 5]});
+        v.angMom = V3{};
+    }
+    return VX_OK;
+}
+
 } // extern "C"

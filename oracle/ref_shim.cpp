@@ -34,6 +34,7 @@
 #include "VX_External.h"
 #include "VX_Collision.h"
 #include "VX_MeshRender.h"
+#include "VX_LinearSolver.h"
 #undef private
 #undef protected
 
@@ -499,6 +500,71 @@ int vx_collision_stats(vx_sim* s, int* n_pairs, int* n_rebuilds)
 {
     if (n_rebuilds) *n_rebuilds = -1;                  // not counted here
     return vx_collision_pairs(s, nullptr, 0, n_pairs);
+}
+
+// ---- static solve: the reference's own CVX_LinearSolver::solve (calculateA, applyBX, postResults run unmodified).  It is
+// compiled with PARDISO_5 defined (oracle/Makefile) and the two entry points of the closed-source PARDISO library it
+// declares (include/VX_LinearSolver.h:26-27) are provided below by a plain banded Cholesky factorisation of the
+// upper-triangular CSR matrix it passes -- enough for the model sizes the tests use.
+extern "C" void pardisoinit(void*, int*, int*, int* iparm, double*, int* error) { for (int i = 0; i < 64; i++) iparm[i] = 0; *error = 0; }
+extern "C" void pardiso(void*, int*, int*, int*, int* phase, int* n_, double* a, int* ia, int* ja, int*, int*, int*, int*, double* b, double* x, int* error, double*)
+{
+    *error = 0;
+    if (*phase != 33) return;                          // analysis / factorisation / release: all work is done in the solve phase
+    const int n = *n_;
+    int bw = 0;
+    for (int i = 0; i < n; i++) for (int k = ia[i] - 1; k < ia[i + 1] - 1; k++) bw = std::max(bw, ja[k] - 1 - i);
+    const size_t W = (size_t)bw + 1;
+    if ((double)n * W > 4e8) { *error = -2; return; }
+    std::vector<double> U((size_t)n * W, 0.0);
+    for (int i = 0; i < n; i++) for (int k = ia[i] - 1; k < ia[i + 1] - 1; k++) U[(size_t)i * W + (ja[k] - 1 - i)] += a[k];
+    std::vector<double> diag0(n);
+    for (int k = 0; k < n; k++) diag0[k] = U[(size_t)k * W];
+    for (int k = 0; k < n; k++) {
+        double* row = &U[(size_t)k * W];
+        if (!(row[0] > 1e-11 * diag0[k])) { *error = -4; return; }      // pivot lost to cancellation: singular to working precision
+        const double piv = std::sqrt(row[0]);
+        const int m = std::min(bw, n - 1 - k);
+        for (int j = 0; j <= m; j++) row[j] /= piv;
+        for (int i = 1; i <= m; i++) {
+            const double f = row[i];
+            if (f == 0.0) continue;
+            double* ri = &U[(size_t)(k + i) * W];
+            for (int j = i; j <= m; j++) ri[j - i] -= f * row[j];
+        }
+    }
+    std::vector<double> y(b, b + n);
+    for (int k = 0; k < n; k++) {
+        const double* row = &U[(size_t)k * W];
+        y[k] /= row[0];
+        const int m = std::min(bw, n - 1 - k);
+        for (int j = 1; j <= m; j++) y[k + j] -= row[j] * y[k];
+    }
+    for (int k = n - 1; k >= 0; k--) {
+        const double* row = &U[(size_t)k * W];
+        const int m = std::min(bw, n - 1 - k);
+        double t = y[k];
+        for (int j = 1; j <= m; j++) t -= row[j] * y[k + j];
+        y[k] = t / row[0];
+    }
+    std::copy(y.begin(), y.end(), x);
+}
+
+int vx_linear_solve(vx_sim* s, double, int, int* iterations, double* rel_residual)
+{
+    if (iterations) *iterations = 0;
+    if (rel_residual) *rel_residual = 0.0;
+    if (!s) return VX_ERR_ARG;
+    if (s->vox.empty()) return fail(s, VX_ERR_ARG, "vx_linear_solve: no voxels");
+    for (auto& m : s->members) {
+        std::streambuf* keep = std::cout.rdbuf(nullptr);          // solve() announces itself on stdout
+        CVX_LinearSolver solver(m.sim);
+        solver.msglvl = 0;
+        const bool ok = solver.solve();
+        std::cout.rdbuf(keep);
+        if (!ok) return fail(s, VX_ERR_SOLVER, solver.errorMsg.c_str());
+    }
+    return VX_OK;
 }
 
 } // extern "C"

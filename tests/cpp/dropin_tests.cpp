@@ -12,6 +12,9 @@
 #include "VX_Link.h"
 #include "VX_MaterialLink.h"
 #include "VX_MeshRender.h"
+#ifndef DROPIN_REFERENCE
+#include "VX_LinearSolver.h"
+#endif
 
 #include <cmath>
 #include <cstdio>
@@ -730,6 +733,46 @@ static void perVoxelFloorAndDampingMultiplier()
 }
 
 #ifndef DROPIN_REFERENCE
+// include/Voxelyze.h:80, include/VX_LinearSolver.h:42-57: static solve of a cantilever.  (The reference's needs PARDISO and is a
+// no-op without it, so this one runs on the facade only; tests/test_static_solve.py pins the algebra to the reference's.)
+static void linearSolveCantilever()
+{
+    CVoxelyze Vx(0.001);
+    CVX_Material* m = Vx.addMaterial(1e6f, 1e3f);
+    m->setGlobalDamping(0.05f);
+    const int n = 12;
+    for (int i = 0; i < n; i++) Vx.setVoxel(m, i, 0, 0);
+    Vx.voxel(0)->external()->setFixedAll();
+    const float F = 1e-6f;
+    Vx.voxel(n - 1)->external()->setForce(0, 0, -F);
+    CVX_LinearSolver solver(&Vx);
+    solver.relTolerance = 1e-13;
+    CHECK(solver.solve());
+    CHECK(solver.iterations > 0 && solver.residual <= 1e-13 && solver.progressTick == 90);
+    // a chain of Euler-Bernoulli beam elements is exact at the nodes: F L^3 / (3 E I) with I = h^4 / 12, slope F L^2 / (2 E I) -- up to
+    // the float rounding of the beam constants (b1 * 2 b3 - b2^2 cancels a third of its digits): 1e-4
+    const double L = (n - 1) * 1e-3, EI = 1e6 * 1e-12 / 12.0;
+    CHECK_NEAR(Vx.voxel(n - 1)->displacement().z, -F * L * L * L / (3 * EI), 1e-4 * F * L * L * L / (3 * EI));
+    CHECK_NEAR(Vx.voxel(n - 1)->orientation().ToRotationVector().y, F * L * L / (2 * EI), 1e-4 * F * L * L / (2 * EI));
+    CHECK(Vx.voxel(n - 1)->velocity().Length2() == 0 && Vx.voxel(3)->angularVelocity().Length2() == 0);
+    // it is a rest state of the time stepper (small deflection: 0.5 % of the length)
+    const double z0 = Vx.voxel(n - 1)->position().z;
+    float dt = Vx.recommendedTimeStep();
+    for (int i = 0; i < 300; i++) Vx.doTimeStep(dt);
+    CHECK_NEAR(Vx.voxel(n - 1)->position().z, z0, 2e-4 * fabs(Vx.voxel(n - 1)->displacement().z));
+    // doLinearSolve: same thing through CVoxelyze; a model that is not held reports through the solver object
+    Vx.resetTime();
+    CHECK(Vx.doLinearSolve());
+    CHECK_NEAR(Vx.voxel(n - 1)->position().z, z0, 1e-9 * fabs(z0));
+    Vx.voxel(0)->external()->setFixedAll(false);
+    CVX_LinearSolver loose(&Vx);
+    loose.maxIterations = 2000;
+    CHECK(!loose.solve() && !loose.errorMsg.empty());
+    CHECK_NEAR(Vx.voxel(n - 1)->position().z, z0, 1e-9 * fabs(z0));     // state untouched
+}
+#endif
+
+#ifndef DROPIN_REFERENCE
 static void copyTakesTheModel()         // Voxelyze.cpp:39-58; in the reference the copied materials come out broken (_sqrtMass negated,
 {                                       // VX_MaterialVoxel.cpp:47) and the copy diverges at once, so this can only be checked on the facade
     CVoxelyze A(0.002);
@@ -821,6 +864,7 @@ int main(int argc, char** argv)
         {"poissonsMixed", poissonsMixed, true}, {"perVoxelFloorAndDampingMultiplier", perVoxelFloorAndDampingMultiplier, true},
 #ifndef DROPIN_REFERENCE
         {"stateCheckpoint", stateCheckpoint, true}, {"copyTakesTheModel", copyTakesTheModel, true},
+        {"linearSolveCantilever", linearSolveCantilever, true},
 #endif
     };
     bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";

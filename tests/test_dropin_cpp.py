@@ -42,7 +42,7 @@ def test_facade_host_only_classes(binaries):
 @pytest.mark.gpu
 def test_facade_passes_the_dropin_source_on_gpu(binaries):
     out = _run(binaries["b200"])
-    assert "0 failures" in out and "29 tests" in out
+    assert "0 failures" in out and "30 tests" in out
 
 
 def test_vxl_json_files_are_interchangeable(binaries, tmp_path):

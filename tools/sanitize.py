@@ -25,5 +25,7 @@ for path in paths:
         sim.download("pos"); sim.download("force_neg"); sim.state_info(8, 2); sim.download_voxel_state(0, 2)
         if sc.sim_id is None:
             sim.mesh(2, 2)
+        if len(sc.ext_voxel) and (sc.ext_dof != 0).any():
+            sim.linear_solve(1e-8, 400)     # static solve kernels (vx_linsolve.cuh)
         print("path", path, sc.name, "ok", sim.kernel_name()[:32], flush=True)
         sim.close()

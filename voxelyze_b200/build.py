@@ -67,12 +67,13 @@ def build_facade(force: bool = False) -> str:
     src = os.path.join(FACADE_DIR, "src", "voxelyze_facade.cpp")
     src_json = os.path.join(FACADE_DIR, "src", "voxelyze_json.cpp")
     src_mesh = os.path.join(FACADE_DIR, "src", "voxelyze_mesh.cpp")
+    src_solver = os.path.join(FACADE_DIR, "src", "voxelyze_solver.cpp")
     inc = os.path.join(FACADE_DIR, "include")
-    deps = [src, src_json, src_mesh, PRODUCT_SO] + [os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(CSRC, "vx_material.hpp")]
+    deps = [src, src_json, src_mesh, src_solver, PRODUCT_SO] + [os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(CSRC, "vx_material.hpp")]
     if not force and _newer(FACADE_SO, deps):
         return FACADE_SO
     cmd = [_host_cxx(), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-variable", "-Wno-overloaded-virtual",
-           "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", FACADE_SO, src, src_json, src_mesh,
+           "-I", inc, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", FACADE_SO, src, src_json, src_mesh, src_solver,
            "-L", LIBDIR, "-lvoxelyze_b200", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)
     return FACADE_SO

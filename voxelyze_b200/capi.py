@@ -156,6 +156,7 @@ class VxLib:
             "vx_collision_pairs": (i32, [vp, vp, i32, P(i32)]),
             "vx_collision_stats": (i32, [vp, P(i32), P(i32)]),
             "vx_state_info": (i32, [vp, i32, i32, P(f32)]),
+            "vx_linear_solve": (i32, [vp, C.c_double, i32, P(i32), P(C.c_double)]),
             "vx_mesh_set_material_colors": (i32, [vp, i32, vp]),
             "vx_mesh_build": (i32, [vp, P(i32), P(i32)]),
             "vx_mesh_update": (i32, [vp, i32, i32]),
@@ -379,6 +380,13 @@ class Sim:
         a, b = C.c_int(0), C.c_int(0)
         self._chk(self.L.lib.vx_collision_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def linear_solve(self, rel_tol: float = 0.0, max_iter: int = 0):
+        """CVoxelyze::doLinearSolve (src/Voxelyze.cpp:243-249): static solution about the nominal lattice, written into the
+        poses.  Returns (iterations, relative residual); raises VxError(VX_ERR_SOLVER) when the model is not held."""
+        it, res = C.c_int(0), C.c_double(0.0)
+        self._chk(self.L.lib.vx_linear_solve(self.h, rel_tol, max_iter, C.byref(it), C.byref(res)))
+        return it.value, res.value
 
     # -- surface mesh (CVX_MeshRender) --------------------------------------------
     MESH_MATERIAL, MESH_FAILURE, MESH_STATE_INFO = 0, 1, 2

@@ -28,6 +28,7 @@
 #include "vx_lattice.cuh"
 #include "vx_collide.cuh"
 #include "vx_mesh.cuh"
+#include "vx_linsolve.cuh"
 
 using namespace vxd;
 
@@ -2045,5 +2046,6 @@ const char* vx_kernel_name(const vx_sim* s)
 }
 
 #include "vx_mesh.inl"
+#include "vx_linsolve.inl"
 
 } // extern "C"

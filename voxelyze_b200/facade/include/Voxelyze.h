@@ -10,11 +10,13 @@
 // caller makes through returned handles (material setters, external()->set*, setVoxel mid-run)
 // are detected by change counters at the next doTimeStep / accessor and uploaded then.
 // *.vxl.json files load and save like the reference's (facade/src/voxelyze_json.cpp; the RapidJSON-typed
-// overloads are not provided).  Not provided: doLinearSolve, mesh rendering.
+// overloads are not provided).  doLinearSolve / CVX_LinearSolver (VX_LinearSolver.h) and CVX_MeshRender (VX_MeshRender.h) run on
+// the device as well.
 #ifndef VXB200_VOXELYZE_H
 #define VXB200_VOXELYZE_H
 
 #include <vector>
+#include <string>
 #include <list>
 #include <algorithm>
 #include <map>
@@ -48,6 +50,7 @@ public:
 
     void clear();
 
+    bool doLinearSolve();                       // include/Voxelyze.h:80, src/Voxelyze.cpp:243-249 (always true, like the reference; CVX_LinearSolver::solve reports)
     bool doTimeStep(float dt = -1.0f);
     float recommendedTimeStep() const;
     void resetTime();
@@ -148,8 +151,11 @@ private:
     CVX_MaterialLink* combinedMaterial(CVX_MaterialVoxel* a, CVX_MaterialVoxel* b) const;
     [[noreturn]] void die(const char* what) const;
 
+    bool staticSolve(double relTol, int maxIter, int* iterations, double* residual, std::string* error);
+
     friend class CVX_Voxel;
     friend class CVX_Link;
+    friend class CVX_LinearSolver;
 };
 
 #endif // VXB200_VOXELYZE_H

@@ -763,6 +763,18 @@ bool CVoxelyze::doTimeStep(float dt)
     return rc == VX_OK;
 }
 
+// the static solve writes new poses and zero momenta on the device: every host mirror is stale afterwards, like after a step
+bool CVoxelyze::staticSolve(double relTol, int maxIter, int* iterations, double* residual, std::string* error)
+{
+    sync();
+    int rc = vx_linear_solve(h, relTol, maxIter, iterations, residual);
+    if (rc == VX_OK) { stepped = true; epoch++; singleFetches = 0; return true; }
+    if (error) *error = vx_last_error(h);
+    if (rc != VX_ERR_SOLVER && rc != VX_ERR_ARG) die("vx_linear_solve");
+    return false;
+}
+bool CVoxelyze::doLinearSolve() { staticSolve(0.0, 0, nullptr, nullptr, nullptr); return true; }
+
 float CVoxelyze::recommendedTimeStep() const
 {
     sync();
