@@ -402,12 +402,17 @@ int  vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* 
 int  vx_save_state(vx_sim* s, const char* path);
 int  vx_load_state(vx_sim* s, const char* path);
 /* select kernel variant (tests; the layout part takes effect at the next vx_set_voxels):
- *   0 auto: fused lattice kernel for bodies that fill at least 62.5 % of their bounding box (holes are
- *           padded with inert cells), general path otherwise
- *   1 general two-kernel path (k_link<AXIS> x3 + k_voxel), any topology
- *   fused lattice kernel (one warp per 4x4x2 brick), bit-identical to path 1, with a fixed staging flavour:
+ *   0 auto: models of at most 2048 voxels without halo flags and without self-collisions: small-model kernel (3);
+ *           otherwise the fused lattice kernel for bodies whose bounding box is at most 8x their voxel count (holes
+ *           are padded with inert cells, sparse bodies launch only their occupied brick groups), general path beyond
+ *   1 general layout, one-step kernels (k_link<AXIS> x3 + k_voxel per step), any topology
+ *   3 general layout stepped by k_small_steps: ONE thread-block cluster (<= 8 CTAs) runs all steps of a vx_step call in
+ *     a single launch, cluster barriers between the link and voxel phases (with self-collisions on, or dt < 0 on
+ *     Poisson models, the one-step kernels of path 1 run instead)
+ *   fused lattice kernel (one warp per 4x4x2 brick), with a fixed staging flavour:
  *   5 cp.async staging (k_lattice_warp; what 0 picks for ensembles of small boxes)
  *   7 TMA staging (k_lattice_tma; what 0 picks on large lattices)
+ *   all of them produce bit-identical state.
  * any other value: VX_ERR_ARG */
 int  vx_set_path(vx_sim* s, int path);
 /* which layout the handle runs: 1 general, 2 fused lattice (decided by vx_set_voxels)  */

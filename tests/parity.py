@@ -36,6 +36,18 @@ def run(lib: capi.VxLib, sc: scenarios.Scenario, steps: int, dt=None, program=No
     return sim, dt, div
 
 
+SMALL_MAX = 2048     # VX_SMALL_MAX of csrc/vx_capi.cu: below it "auto" steps the general layout with k_small_steps
+
+
+def layout(path: int, n_voxels: int, collisions: bool = False) -> int:
+    """vx_active_path() a model is expected to report: 1 general layout, 2 fused lattice layout."""
+    if path in (1, 3):
+        return 1
+    if path == 0 and n_voxels <= SMALL_MAX and not collisions:
+        return 1
+    return 2
+
+
 def bit_equal(a: np.ndarray, b: np.ndarray) -> bool:
     if a.shape != b.shape or a.dtype != b.dtype:
         return False

@@ -79,15 +79,16 @@ def test_c3_scale_model_60000_steps_pairs_and_flags_exact(product, built):
     assert abs(ke_g - ke_c) <= 1e-4 * max(ke_c, 1e-30) + 1e-18, (ke_g, ke_c)      # residual motion after 60 000 steps of contact and yielding
 
 
-def test_c4_one_robot_2000_steps_against_the_reference(product, cpu):
+@pytest.mark.parametrize("path", [7, 0], ids=["fused", "auto-small"])
+def test_c4_one_robot_2000_steps_against_the_reference(product, cpu, path):
     """One robot of the C4 population (10^3 voxels, materials by hash, CTE +/-0.01, floor, gravity, friction), ambient
     temperature 20 sin(2 pi 40 t) set before every step, 2 000 steps.  Smooth until the first floor contact; with Coulomb
     friction afterwards the stated bound is 1e-6 (SURVEY 8d parity metrics, C2/C4)."""
     sc = scenarios.robot_ensemble(1, 10, first_seed=7)
     program = lambda sim, k, t: sim.set_temperature_all(scenarios.robot_temperature(t))
-    g, dt, dg = parity.run(product, sc, 2000, program=program)
+    g, dt, dg = parity.run(product, sc, 2000, program=program, path=path)
     c, _, dc = parity.run(cpu, sc, 2000, dt=dt, program=program)
-    assert dg is None and dc is None and g.active_path() == 2
+    assert dg is None and dc is None and g.active_path() == parity.layout(path, sc.n_voxels)
     sg, so = parity.snapshot(g), parity.snapshot(c)
     err = parity.rel_errors(sg, so, sc)
     assert err["pos"] <= 1e-6 and err["orient"] <= 1e-6, err

@@ -22,11 +22,12 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NOT_BUILT = set()     # cases needing features that are not on the GPU yet
 
 
-@pytest.mark.parametrize("path", [0, 1], ids=["auto", "general"])
+@pytest.mark.parametrize("path", [0, 1, 7], ids=["auto", "general", "fused"])
 @pytest.mark.parametrize("case", cases.CASES, ids=lambda c: c.name)
 def test_cuda_matches_oracle(product, oracle, case, path):
-    """path auto = fused lattice kernel wherever the lattice is a full box, else the general
-    kernels; path general forces the two-kernel path on every case."""
+    """auto: these models are small, so the small-model cluster kernel (all steps of a call in one launch) unless
+    self-collisions are on; general: the one-step kernels of the general layout; fused: the lattice kernel wherever the
+    bounding box is at most 8x the voxel count."""
     if case.name in NOT_BUILT:
         pytest.skip("feature not on the GPU yet")
     sc = case.make()
@@ -80,33 +81,45 @@ def test_material_tables_bitwise(product, oracle):
             assert _same(pl[key][k], ol[key][k]), (key, k)
 
 
-def test_lattice_path_is_selected_for_full_boxes(product):
-    assert scenarios.build(product, scenarios.cantilever(6, 3, 3)).active_path() == 2
+def test_layout_selection(product):
+    """auto: models of at most 2048 voxels without self-collisions are stepped by the small-model cluster kernel on the general
+    layout (one launch per vx_step call); everything else runs fused wherever its bounding box is at most 8x its voxel
+    count.  vx_set_path forces either."""
+    small = scenarios.build(product, scenarios.cantilever(6, 3, 3))
+    assert small.active_path() == 1 and "k_small_steps" in small.kernel_name()
     assert scenarios.build(product, scenarios.cantilever(6, 3, 3), path=1).active_path() == 1
-    assert scenarios.build(product, scenarios.robot_ensemble(2, 3)).active_path() == 2
-    assert scenarios.build(product, cases.BY_NAME["temperature_bimorph"].make()).active_path() == 2
-    # a box with holes (6 of 2x2x2 cells) is filled up with inert cells and still runs fused; a sparse shape does not
-    six = scenarios.build(product, cases.BY_NAME["mixed_six"].make())
+    assert "k_link" in scenarios.build(product, scenarios.cantilever(6, 3, 3), path=1).kernel_name()
+    assert scenarios.build(product, scenarios.cantilever(6, 3, 3), path=7).active_path() == 2
+    big = scenarios.build(product, scenarios.cantilever(40, 8, 8))                 # 2560 voxels
+    assert big.active_path() == 2 and "k_small_steps" in scenarios.build(product, scenarios.cantilever(40, 8, 8), path=3).kernel_name()
+    assert scenarios.build(product, scenarios.robot_ensemble(2, 3), path=7).active_path() == 2
+    assert scenarios.build(product, scenarios.robot_ensemble(40, 4)).active_path() == 2           # 2560 voxels in 40 members
+    assert scenarios.build(product, cases.BY_NAME["temperature_bimorph"].make(), path=7).active_path() == 2
+    # a box with holes (6 of 2x2x2 cells) is filled up with inert cells and runs fused; a sparse shape does not
+    six = scenarios.build(product, cases.BY_NAME["mixed_six"].make(), path=7)
     assert six.active_path() == 2 and six.n_voxels == 6
     assert scenarios.build(product, cases.BY_NAME["mixed_six"].make(), path=1).active_path() == 1
     ell = [[i, 0, 0] for i in range(5)] + [[0, j, 0] for j in range(1, 5)]
     sparse = scenarios.Scenario("ell", 0.001, [Material()], np.array(ell, np.int32), np.zeros(len(ell), np.uint16))
-    assert scenarios.build(product, sparse).active_path() == 2           # 9 voxels in 25 cells: a single body may be as sparse as 1 in 8
+    assert scenarios.build(product, sparse, path=7).active_path() == 2   # 9 voxels in 25 cells: a single body may be as sparse as 1 in 8
     diag = [[i, i, i] for i in range(6)]
     very_sparse = scenarios.Scenario("diag", 0.001, [Material()], np.array(diag, np.int32), np.zeros(len(diag), np.uint16))
-    assert scenarios.build(product, very_sparse).active_path() == 1      # 6 voxels in 216 cells: general path
-    assert scenarios.build(product, cases.BY_NAME["poisson_block"].make()).active_path() == 2  # nu != 0: fused too (k_lattice_tma<.., POISSON>)
-    assert scenarios.build(product, cases.BY_NAME["poisson_mixed_bilinear"].make()).active_path() == 2
+    assert scenarios.build(product, very_sparse, path=7).active_path() == 1      # 6 voxels in 216 cells: general layout
+    assert scenarios.build(product, cases.BY_NAME["poisson_block"].make(), path=7).active_path() == 2  # nu != 0: fused too (k_lattice_tma<.., POISSON>)
+    assert scenarios.build(product, cases.BY_NAME["poisson_mixed_bilinear"].make(), path=7).active_path() == 2
+    # self-collisions switched on: a small model moves to the fused layout (its captured step graphs carry the collision kernels)
+    col = scenarios.build(product, scenarios.plate_stack(16, 4, 2, 3, 2, tip_load=0.5))
+    assert col.active_path() == 2
 
 
 def test_fused_and_general_paths_agree_bitwise(product):
     """Same physics functions, same summation order: the two device layouts give identical bits."""
     sc = scenarios.cantilever(12, 5, 4, tip_load=30.0)
     snaps = {}
-    for path in (0, 1, 5, 7):   # auto, general two-kernel, warp bricks staged by cp.async / by TMA
+    for path in (0, 1, 3, 5, 7):   # auto (= 3 at this size), general one-step kernels, small-model cluster kernel, warp bricks staged by cp.async / by TMA
         sim, dt, _ = parity.run(product, sc, 700, path=path)
         snaps[path] = parity.snapshot(sim)
-    for path in (1, 5, 7):
+    for path in (1, 3, 5, 7):
         for f in snaps[0]:
             assert parity.bit_equal(snaps[0][f], snaps[path][f]), (path, f)
 
@@ -125,10 +138,10 @@ def test_fused_kernels_odd_sizes(product, oracle, path):
 
 def test_diverging_step_semantics(product, oracle):
     """A step whose links exceed strain 100 returns VX_DIVERGED, advances links but not voxels
-    (src/Voxelyze.cpp:263-269), on both device layouts."""
+    (src/Voxelyze.cpp:263-269), on both device layouts and inside the one-launch call of the small-model kernel."""
     c = cases.BY_NAME["data_curve_fail"]
     sc = c.make()
-    for path in (0, 1):
+    for path in (0, 1, 7):
         g, dt, dg = parity.run(product, sc, 2900, path=path)
         o, _, do = parity.run(oracle, sc, 2900)
         assert dg == do and dg is not None
@@ -160,7 +173,7 @@ def test_diverging_step_with_collisions_enabled(product, oracle, path):
     assert np.array_equal(before, g.download("pos"))
 
 
-@pytest.mark.parametrize("path", [0, 1], ids=["auto", "general"])
+@pytest.mark.parametrize("path", [0, 1, 7], ids=["auto", "general", "fused"])
 def test_determinism_two_runs_bit_equal(product, path):
     sc = scenarios.cantilever(16, 6, 5)
     a, _, _ = parity.run(product, sc, 500, path=path)
@@ -170,12 +183,14 @@ def test_determinism_two_runs_bit_equal(product, path):
         assert np.array_equal(sa[f], sb[f]), f
 
 
-def test_graph_and_single_steps_agree(product):
-    """vx_step(n) uses captured CUDA graphs; one-step calls do not.  Same bits either way."""
+@pytest.mark.parametrize("path", [7, 1, 0], ids=["fused", "general", "auto-small"])
+def test_graph_and_single_steps_agree(product, path):
+    """vx_step(n) uses captured CUDA graphs (fused, general) or one launch for the whole call (small-model kernel); one-step
+    calls do not.  Same bits either way."""
     sc = scenarios.cantilever(10, 3, 3)
-    a = scenarios.build(product, sc); dt = a.recommended_dt()
+    a = scenarios.build(product, sc, path=path); dt = a.recommended_dt()
     a.step(dt, 100)
-    b = scenarios.build(product, sc)
+    b = scenarios.build(product, sc, path=path)
     for _ in range(100):
         b.step(dt, 1)
     sa, sb = parity.snapshot(a), parity.snapshot(b)
@@ -280,7 +295,7 @@ def test_full_size_properties_256(product):
     assert abs(lm[:, 1].sum()) <= 1e-9 * np.abs(lm).sum()
 
 
-@pytest.mark.parametrize("path", [0, 1], ids=["lattice", "general"])
+@pytest.mark.parametrize("path", [7, 1, 0], ids=["lattice", "general", "auto-small"])
 def test_state_info_reductions(product, oracle, path):
     """vx_state_info (device reductions) against the oracle's sequential float loops
     (CVoxelyze::stateInfo, src/Voxelyze.cpp:752-800); summation order differs, tolerance 1e-6 relative."""
@@ -420,7 +435,7 @@ def test_any_scenario_runs_as_peer_memory_slabs_bitwise(product):
     from voxelyze_b200 import slab
     from test_slab_gloo import _general_scenario
     sc = _general_scenario()
-    whole = scenarios.build(product, sc); dt = whole.recommended_dt()
+    whole = scenarios.build(product, sc, path=7); dt = whole.recommended_dt()
     runs = [slab.SlabRunner.from_scenario(product, sc, r, 3) for r in range(3)]
     assert all(r.sim.active_path() == 2 for r in runs) and whole.active_path() == 2
     slab.SlabRunner.connect_local(runs)
@@ -439,21 +454,22 @@ def test_any_scenario_runs_as_peer_memory_slabs_bitwise(product):
         assert parity.bit_equal(got, whole.download(f)[index]), f
 
 
+@pytest.mark.parametrize("layout", [7, 0], ids=["fused", "auto"])
 @pytest.mark.parametrize("case", ["cantilever", "plates", "robots"])
-def test_checkpoint_resume_is_bit_identical(product, tmp_path, case):
+def test_checkpoint_resume_is_bit_identical(product, tmp_path, case, layout):
     """vx_save_state / vx_load_state: stop, restore into a freshly built handle, continue == never stopped.
     Lattice path (cantilever, ensemble with temperature) and general path with collisions and plastic links."""
     sc = {"cantilever": lambda: scenarios.cantilever(14, 5, 6, tip_load=40.0),
           "plates": lambda: scenarios.plate_stack(16, 8, 2, thick=3, gap=2, tip_load=1.0),
           "robots": lambda: scenarios.robot_ensemble(5, 4)}[case]()
-    a = scenarios.build(product, sc); dt = a.recommended_dt()
+    a = scenarios.build(product, sc, path=layout); dt = a.recommended_dt()
     if case == "robots":
         a.set_temperature_all(7.5)
     a.step(dt, 333)
     path = str(tmp_path / "state.bin")
     a.save_state(path)
     a.step(dt, 200)
-    b = scenarios.build(product, sc)
+    b = scenarios.build(product, sc, path=layout)
     b.load_state(path)
     assert b.time() == pytest.approx(333 * dt, rel=1e-4)
     b.step(dt, 200)
@@ -467,7 +483,7 @@ def test_checkpoint_resume_is_bit_identical(product, tmp_path, case):
         other.load_state(path)
 
 
-@pytest.mark.parametrize("path", [0, 1], ids=["lattice", "general"])
+@pytest.mark.parametrize("path", [7, 1, 0], ids=["lattice", "general", "auto-small"])
 def test_link_state_upload_round_trip(product, path):
     """vx_download_link_state / vx_upload_link_state: a fresh handle that receives the voxel and link state of a
     running one continues bit-identically (what the facade does across setVoxel edits)."""
@@ -496,7 +512,7 @@ def test_enabling_collisions_mid_run_matches_the_oracle(product, oracle):
     out again (collision tables) while every voxel and link keeps its state."""
     sc = scenarios.drop_block(6)
     g = scenarios.build(product, sc); o = scenarios.build(oracle, sc)
-    assert g.active_path() == 2
+    assert g.active_path() == 1                       # 216 voxels, no collisions yet: small-model kernel on the general layout
     dt = g.recommended_dt()
     g.step(dt, 300); o.step(dt, 300)
     g.enable_collisions(True); o.enable_collisions(True)
@@ -606,7 +622,7 @@ def test_box_with_holes_runs_fused_and_matches_the_general_path_bitwise(product,
     runs = {}
     for path in (0, 5, 7, 1):
         g = scenarios.build(product, sc, path=path); dt = g.recommended_dt()
-        assert g.active_path() == (1 if path == 1 else 2) and g.n_voxels == len(ijk)
+        assert g.active_path() == parity.layout(path, len(ijk)) and g.n_voxels == len(ijk)
         g.step(dt, 1200)
         runs[path] = g
     o = scenarios.build(oracle, sc); o.step(dt, 1200)
@@ -643,7 +659,8 @@ def test_collisions_on_the_fused_path_match_the_general_path_bitwise(product):
         assert np.array_equal(runs[path].collision_pairs(), runs[1].collision_pairs())
 
 
-def test_poissons_ratio_switched_on_mid_run_keeps_the_state(product, oracle):
+@pytest.mark.parametrize("path", [7, 0], ids=["fused", "auto-small"])
+def test_poissons_ratio_switched_on_mid_run_keeps_the_state(product, oracle, path):
     """The reference lets a caller change Poisson's ratio at any time (src/VX_Link.cpp:160-166 'catches when we disable
     poissons mid-simulation').  A model on the fused layout stays there: its per-voxel Poisson strains are created from the
     current link strains when nu becomes non-zero; voxel and link state, time and previousDt go on, and later calls (gravity,
@@ -652,7 +669,7 @@ def test_poissons_ratio_switched_on_mid_run_keeps_the_state(product, oracle):
 
     def run(lib):
         sc = scenarios.cantilever(8, 3, 3, tip_load=20.0)
-        s = scenarios.build(lib, sc); dt = s.recommended_dt()
+        s = scenarios.build(lib, sc, path=path); dt = s.recommended_dt()
         s.step(dt, 150)
         m = copy.copy(sc.materials[0]); m.nu = 0.3
         s.set_materials([m])
@@ -663,7 +680,7 @@ def test_poissons_ratio_switched_on_mid_run_keeps_the_state(product, oracle):
         return s, sc, dt, dt2
 
     (g, sc, dtg, dtg2), (o, _, dto, dto2) = run(product), run(oracle)
-    assert g.active_path() == 2 and dtg == dto
+    assert g.active_path() == parity.layout(path, sc.n_voxels) and dtg == dto
     assert abs(dtg2 - dto2) <= 1e-6 * dto2
     err = parity.rel_errors(parity.snapshot(g), parity.snapshot(o), sc)
     assert err["pos"] <= 1e-6 and err["orient"] <= 1e-6, err

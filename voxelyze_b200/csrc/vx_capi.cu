@@ -96,7 +96,8 @@ struct vx_sim {
     bool amb_pending = false, last_amb = false; float amb_value = 0.f, last_amb_value = 0.f;
     bool floor_on = false, collisions = false;
     float time_host = 0.f;
-    int path = 0;                       // vx_set_path: 0 auto, 1 general, 5 / 7 fused lattice with cp.async / TMA staging
+    int path = 0;                       // vx_set_path: 0 auto, 1 general, 3 small-model cluster kernel, 5 / 7 fused lattice with cp.async / TMA staging
+    bool small = false;                 // general layout stepped by k_small_steps (one launch per vx_step call)
     bool relayout = false;
 
     // ---- lattice mode
@@ -696,6 +697,27 @@ static int launch_step(vx_sim* s, const Frame& f, bool per_step_dt, bool capturi
     return VX_OK;
 }
 
+// k_small_steps: one cluster of up to 8 CTAs x 256 threads (portable cluster size), all n steps
+static int launch_small_steps(vx_sim* s, const Frame& f, int n_steps)
+{
+    const int work = std::max(s->N, s->L);
+    int ctas = std::max(1, std::min(8, (work + 255) / 256));
+    while (ctas & (ctas - 1)) ctas++;                               // 1, 2, 4 or 8
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const int af1 = s->axis_first[1], af2 = s->axis_first[2], fl = s->floor_on ? 1 : 0;
+    cudaError_t e;
+    if (s->any_poisson) e = cudaLaunchKernelEx(&cfg, k_small_steps<true, false>, f, af1, af2, n_steps, fl);
+    else if (s->uni) e = cudaLaunchKernelEx(&cfg, k_small_steps<false, true>, f, af1, af2, n_steps, fl);
+    else e = cudaLaunchKernelEx(&cfg, k_small_steps<false, false>, f, af1, af2, n_steps, fl);
+    s->launches++;
+    if (e != cudaSuccess) return cuda_fail(s, e, "k_small_steps");
+    return VX_OK;
+}
+
 __global__ void k_begin(DevParams* p, float dt, int set_dt)
 {
     p->div_now = 0; p->div_latched = 0; p->steps_done = 0;
@@ -1129,6 +1151,10 @@ int vx_set_materials(vx_sim* s, int n, const vx_material_desc* d)
         for (uint32_t f : s->vflags) if ((f & VX_VF_GHOST) && !(f & VF_FILL)) ghosts = true;
         if (ghosts) return fail(s, VX_ERR_UNSUPPORTED, "Poisson materials on a z-slab (halo voxels carry no Poisson strains)");
     }
+    if (!s->lattice && s->any_poisson && s->state_ready && s->L > 0) {
+        k_refresh_slot_strain<<<blocks_for(s->L), TPB, 0, s->stream>>>(s->frame(), s->axis_first[1], s->axis_first[2]); s->launches++;
+        CK(cudaGetLastError());
+    }
     return refresh_lattice_ps(s);
 }
 
@@ -1156,13 +1182,24 @@ int vx_get_linkmat_curve(vx_sim* s, int a, int b, float* eps, float* sig, int ca
 
 static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags, int n_user);
 
+// Small models are stepped by one thread-block cluster that runs a whole vx_step call in a single launch
+// (k_small_steps, general layout): chosen by vx_set_path(3), or by default below VX_SMALL_MAX voxels when the model has no
+// halo / per-voxel flags and self-collisions are off at this point (with collisions the fused path's captured graphs win).
+constexpr int VX_SMALL_MAX = 2048;
+static bool small_model(const vx_sim* s, int n, const uint32_t* flags)
+{
+    if (s->path != 3 && !(s->path == 0 && n <= VX_SMALL_MAX && !s->collisions && !getenv("VX_NO_SMALL"))) return false;
+    if (flags) for (int i = 0; i < n; i++) if (flags[i] & VX_VF_GHOST) return false;
+    return n > 0;
+}
+
 // A box with holes still runs on the fused lattice path: the missing cells are appended as inert voxels (never
 // integrated, no links, invisible to the caller) when that costs at most 60 % more cells.
 int vx_set_voxels(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags)
 {
     if (!s || n < 0 || (n && (!ijk || !mat))) return VX_ERR_ARG;
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_voxels inside vx_step_begin .. vx_step_end");
-    if (n == 0 || s->path == 1)
+    if (n == 0 || s->path == 1 || small_model(s, n, flags))
         return set_voxels_impl(s, n, ijk, mat, sim_id, flags, n);
     int lo[3] = {32767, 32767, 32767}, hi[3] = {-32768, -32768, -32768}, members = 1;
     for (int i = 0; i < n; i++) {
@@ -1284,7 +1321,8 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     if (flags) for (int i = 0; i < n && !halo; i++) halo = (flags[i] & VX_VF_GHOST) && !(flags[i] & VF_FILL);
     // fused layout: a completely filled box; Poisson materials too (k_lattice_tma<.., POISSON>) unless the box is a z-slab
     // with halo voxels, whose Poisson strains nobody exchanges
-    s->lattice = n > 0 && cells == (long long)n && !(poisson && halo) && s->path != 1;
+    s->small = n == n_user && small_model(s, n, flags);
+    s->lattice = n > 0 && cells == (long long)n && !(poisson && halo) && s->path != 1 && !s->small;
     s->state_ready = false;
     s->pack[0] = s->pack[1] = 1; s->pack[2] = s->n_members; s->lat_members = s->n_members;
     if (s->lattice && s->n_members > 1 && !getenv("VX_NO_PACK")) {
@@ -1580,6 +1618,11 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     }
     int left = n_steps;
     collision_call_begin(s);
+    if (s->small && !s->collisions && !per_step_dt) {              // the whole call in one launch of one thread-block cluster
+        int rc = launch_small_steps(s, f, left);
+        if (rc != VX_OK) return rc;
+        left = 0;
+    }
     if (!per_step_dt && left >= GRAPH_STEPS) {
         int rc = ensure_graph(s);
         if (rc != VX_OK) return rc;
@@ -2026,7 +2069,7 @@ int vx_sync(vx_sim* s) { if (!s) return VX_ERR_ARG; CK(cudaSetDevice(s->device))
 int vx_set_path(vx_sim* s, int path)
 {
     if (!s) return VX_ERR_ARG;
-    if (path != 0 && path != 1 && path != 5 && path != 7) return fail(s, VX_ERR_ARG, "vx_set_path: 0 (auto), 1 (general), 5 (fused, cp.async) or 7 (fused, TMA)");
+    if (path != 0 && path != 1 && path != 3 && path != 5 && path != 7) return fail(s, VX_ERR_ARG, "vx_set_path: 0 (auto), 1 (general), 3 (small-model cluster kernel), 5 (fused, cp.async) or 7 (fused, TMA)");
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_path inside vx_step_begin .. vx_step_end");
     if (path != s->path) s->drop_graph();            // captured graphs hold the kernel variant
     s->path = path;
@@ -2035,6 +2078,7 @@ int vx_set_path(vx_sim* s, int path)
 int vx_active_path(const vx_sim* s) { return s && s->lattice ? 2 : 1; }
 const char* vx_kernel_name(const vx_sim* s)
 {
+    if (s && !s->lattice && s->small && !s->collisions) return "k_small_steps (general layout, one thread-block cluster runs all steps of a call in one launch)";
     if (!s || !s->lattice) return "k_link<AXIS> (3 launches per step, one per link axis)";
     bool tma = s->path == 7;
     if (s->path == 0) {

@@ -11,6 +11,7 @@
 // exists between threads, so the design rules are coalesced 128-bit accesses, enough
 // resident warps to cover DRAM latency and grids of many waves over the 148 SMs.
 #pragma once
+#include <cooperative_groups.h>
 #include "vx_physics.cuh"
 
 namespace vxd {
@@ -50,6 +51,24 @@ __device__ __forceinline__ double4 ld4(const double4* p)
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// Loads of state that another CTA of the same (persistent, multi-step) kernel may have written since this SM last read it
+// (k_small_steps): COH = true bypasses L1 (ld.global.cg); COH = false is the plain / read-only path of the one-step kernels.
+template <bool COH> __device__ __forceinline__ double4 ldv4(const double4* p)
+{
+    if (!COH) return ld4(p);
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldcg(q), b = __ldcg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+template <bool COH> __device__ __forceinline__ double4 ldw4(const double4* p)       // arrays the one-step kernels read with plain loads
+{
+    if (!COH) return *p;
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldcg(q), b = __ldcg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+template <bool COH, typename T> __device__ __forceinline__ T ldv(const T* p) { return COH ? __ldcg(p) : *p; }
+
 // transverse area of a voxel cross-section seen along `axis` (src/VX_Voxel.cpp:361-374)
 __device__ __forceinline__ float transverse_area(const DevVoxMat& m, int axis, float4 ps)
 {
@@ -69,22 +88,20 @@ __device__ __forceinline__ float transverse_strain_sum(const DevVoxMat& m, int a
     return ps.x + ps.y;
 }
 
-template <int AXIS, bool POISSON, bool UNI>
-__global__ void __launch_bounds__(128) k_link(int first, int count, Frame f)
+// CVX_Link::updateForces of link l (src/VX_Link.cpp:149-217) on the general layout
+template <int AXIS, bool POISSON, bool UNI, bool COH>
+__device__ __forceinline__ void link_body(const int l, const Frame& f)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    if (f.params->div_latched) return;
-    const int l = first + t;
-    const float prev_dt = f.params->prev_dt;
+    if (ldv<COH>(&f.params->div_latched)) return;
+    const float prev_dt = ldv<COH>(&f.params->prev_dt);
 
     int2 e = f.lends[l];
-    double4 n0 = ld4(f.pose0 + e.x), n1 = ld4(f.pose1 + e.x);
-    double4 p0 = ld4(f.pose0 + e.y), p1 = ld4(f.pose1 + e.y);
-    double4 sa = f.lstA[l], sb = f.lstB[l];
-    double sc = f.lstC[l];
-    float4 sm = f.lstrain[l];
-    uint32_t lm_bits = f.lmeta[l];
+    double4 n0 = ldv4<COH>(f.pose0 + e.x), n1 = ldv4<COH>(f.pose1 + e.x);
+    double4 p0 = ldv4<COH>(f.pose0 + e.y), p1 = ldv4<COH>(f.pose1 + e.y);
+    double4 sa = ldw4<COH>(f.lstA + l), sb = ldw4<COH>(f.lstB + l);
+    double sc = ldv<COH>(f.lstC + l);
+    float4 sm = ldv<COH>(f.lstrain + l);
+    uint32_t lm_bits = ldv<COH>(f.lmeta + l);
 
     const uint32_t hn = meta_hi(n1.w), hp = meta_hi(p1.w);
     const float tn = meta_temp(n1.w), tp = meta_temp(p1.w);
@@ -97,7 +114,7 @@ __global__ void __launch_bounds__(128) k_link(int first, int count, Frame f)
 
     float t_area, t_sum = 0.0f;
     if (POISSON) {
-        float4 psn = f.pstrain[e.x], psp = f.pstrain[e.y];
+        float4 psn = ldv<COH>(f.pstrain + e.x), psp = ldv<COH>(f.pstrain + e.y);
         t_area = 0.5f * (transverse_area(vmn, AXIS, psn) + transverse_area(vmp, AXIS, psp));
         t_sum = 0.5f * (transverse_strain_sum(vmn, AXIS, psn) + transverse_strain_sum(vmp, AXIS, psp));
     } else {
@@ -142,23 +159,30 @@ __global__ void __launch_bounds__(128) k_link(int first, int count, Frame f)
     }
 }
 
-template <bool UNI>
-__global__ void __launch_bounds__(128) k_voxel(Frame f, int floor_on, int collisions)
+template <int AXIS, bool POISSON, bool UNI>
+__global__ void __launch_bounds__(128) k_link(int first, int count, Frame f)
 {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= f.n_vox) return;
-    DevParams* p = f.params;
-    if (p->div_now | p->div_latched) { if (v == 0) p->div_latched = 1; return; }
-    const float dt = p->dt;
-    if (v == 0) { p->prev_dt = dt; p->time += dt; p->steps_done += 1; }
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    link_body<AXIS, POISSON, UNI, false>(first + t, f);
+}
 
-    double4 q1 = f.pose1[v];
+// CVX_Voxel::timeStep of voxel v (src/VX_Voxel.cpp:162-232) on the general layout
+template <bool UNI, bool COH>
+__device__ __forceinline__ void voxel_body(const int v, const Frame& f, int floor_on, int collisions)
+{
+    DevParams* p = f.params;
+    if (ldv<COH>(&p->div_now) | ldv<COH>(&p->div_latched)) { if (v == 0) p->div_latched = 1; return; }
+    const float dt = p->dt;
+    if (v == 0) { p->prev_dt = dt; p->time = ldv<COH>(&p->time) + dt; p->steps_done = ldv<COH>(&p->steps_done) + 1; }
+
+    double4 q1 = ldw4<COH>(f.pose1 + v);
     VoxelState s;
     s.bits = meta_hi(q1.w);
     if (s.bits & VM_GHOST) return;
     s.temp = meta_temp(q1.w);
-    double4 q0 = f.pose0[v], m0 = f.mom0[v];
-    double2 m1 = f.mom1[v];
+    double4 q0 = ldw4<COH>(f.pose0 + v), m0 = ldw4<COH>(f.mom0 + v);
+    double2 m1 = ldv<COH>(f.mom1 + v);
     s.pos = mk3(q0.x, q0.y, q0.z);
     s.orient.w = q0.w; s.orient.x = q1.x; s.orient.y = q1.y; s.orient.z = q1.z;
     s.lin = mk3(m0.x, m0.y, m0.z);
@@ -172,7 +196,7 @@ __global__ void __launch_bounds__(128) k_voxel(Frame f, int floor_on, int collis
     for (int k = 0; k < 6; k++) {
         if (mask & (1u << k)) {
             const double2* sl = reinterpret_cast<const double2*>(f.slots + ((size_t)k * nv + v) * 6);
-            double2 a = sl[0], b = sl[1], c = sl[2];
+            double2 a = ldv<COH>(sl), b = ldv<COH>(sl + 1), c = ldv<COH>(sl + 2);
             F = F + mk3(a.x, a.y, b.x);
             M = M + mk3(b.y, c.x, c.y);
         }
@@ -192,6 +216,14 @@ __global__ void __launch_bounds__(128) k_voxel(Frame f, int floor_on, int collis
     f.pose1[v] = make_double4(s.orient.x, s.orient.y, s.orient.z, meta_pack(s.temp, s.bits));
     f.mom0[v] = make_double4(s.lin.x, s.lin.y, s.lin.z, s.ang.x);
     f.mom1[v] = make_double2(s.ang.y, s.ang.z);
+}
+
+template <bool UNI>
+__global__ void __launch_bounds__(128) k_voxel(Frame f, int floor_on, int collisions)
+{
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= f.n_vox) return;
+    voxel_body<UNI, false>(v, f, floor_on, collisions);
 }
 
 // CVX_Voxel::strain(true) (src/VX_Voxel.cpp:300-343) from the sums r[] and counts nb[] of the per-end axial strains of the
@@ -218,12 +250,11 @@ __device__ __forceinline__ float4 voxel_pstrain(const DevVoxMat& vm, const DevEx
 // CVX_Voxel::strain(true) for voxels whose cache is stale (src/VX_Voxel.cpp:300-343).
 // The reference fills this cache lazily inside the link loop; every link strain it reads is
 // still the previous step's at that point, so a pre-pass over stale voxels is equivalent.
-__global__ void __launch_bounds__(128) k_pstrain(Frame f)
+template <bool COH>
+__device__ __forceinline__ void pstrain_body(const int v, const Frame& f)
 {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= f.n_vox) return;
-    if (f.params->div_latched) return;
-    double w = f.pose1[v].w;
+    if (ldv<COH>(&f.params->div_latched)) return;
+    double w = ldv<COH>(&f.pose1[v].w);
     uint32_t bits = meta_hi(w);
     if (!(bits & VM_PSTRAIN_STALE)) return;
     const DevVoxMat& vm = f.vmat[bits & VM_MAT_MASK];
@@ -233,10 +264,45 @@ __global__ void __launch_bounds__(128) k_pstrain(Frame f)
     int nb[3] = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 6; k++)
-        if (mask & (1u << k)) { r[k >> 1] += f.slot_strain[(size_t)k * nv + v]; nb[k >> 1]++; }
+        if (mask & (1u << k)) { r[k >> 1] += ldv<COH>(f.slot_strain + (size_t)k * nv + v); nb[k >> 1]++; }
     const DevExt* ext = (bits & VM_HAS_EXT) ? f.ext + f.ext_idx[v] : nullptr;
     f.pstrain[v] = voxel_pstrain(vm, ext, r, nb);
     f.pose1[v].w = meta_pack(meta_temp(w), bits & ~VM_PSTRAIN_STALE);
+}
+__global__ void __launch_bounds__(128) k_pstrain(Frame f)
+{
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= f.n_vox) return;
+    pstrain_body<false>(v, f);
+}
+
+// ---- small models: ALL steps of a vx_step call in ONE launch -------------------------------------------------------
+// A model of a few hundred voxels (320 voxels, 784 links) cannot fill the GPU; what it pays per step is launch
+// latency and the dependent FP64 chain of one link and one voxel update.  k_small_steps runs the whole call as one
+// thread-block cluster (<= 8 CTAs on 8 SMs: one SM's 64 FP64 lanes would need ~5 us for C1's 784 link updates): per step a
+// link phase (thread per link, axis by range), a cluster barrier, a voxel phase, a cluster barrier -- the barrier
+// (barrier.cluster, release/acquire) replaces the kernel boundary of the general path, the state stays in L2 (state loads
+// bypass L1, ld.global.cg, because another SM wrote them one phase earlier).  Same device functions, same per-voxel
+// summation order: bit-identical to k_link / k_voxel.
+template <bool POISSON, bool UNI>
+__global__ void __launch_bounds__(256) k_small_steps(Frame f, int af1, int af2, int n_steps, int floor_on)
+{
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int step = 0; step < n_steps; step++) {
+        if (POISSON) {
+            for (int v = tid; v < f.n_vox; v += nthr) pstrain_body<true>(v, f);
+            cluster.sync();
+        }
+        for (int l = tid; l < f.n_link; l += nthr) {
+            if (l < af1) link_body<0, POISSON, UNI, true>(l, f);
+            else if (l < af2) link_body<1, POISSON, UNI, true>(l, f);
+            else link_body<2, POISSON, UNI, true>(l, f);
+        }
+        cluster.sync();
+        for (int v = tid; v < f.n_vox; v += nthr) voxel_body<UNI, true>(v, f, floor_on, 0);
+        cluster.sync();
+    }
 }
 
 // max over links of axialStiffness/min(m1,m2) (src/Voxelyze.cpp:291-299, src/VX_Link.cpp:259-267)
@@ -393,6 +459,21 @@ __global__ void k_scatter_link_state(Frame f, const int* e2i, int first, int cou
     f.lstC[l] = r.a2v[2];
     f.lstrain[l] = make_float4(r.strain, r.max_strain, r.strain_offset, r.stress);
     f.lmeta[l] = (f.lmeta[l] & LM_MAT_MASK) | ((r.flags & 1u) ? LM_SMALL_ANGLE : 0u) | ((r.flags & 2u) ? LM_VEL_VALID : 0u);
+}
+
+// Poisson's ratio switched on mid-run on the general layout: the per-end axial strains the Poisson pre-pass reads are only kept
+// up to date by the POISSON link kernels, so they are rebuilt here from the current link strains (src/VX_Link.cpp:121-124)
+__global__ void k_refresh_slot_strain(Frame f, int axis_first1, int axis_first2)
+{
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= f.n_link) return;
+    const int2 e = f.lends[l];
+    const int axis = l >= axis_first2 ? 2 : (l >= axis_first1 ? 1 : 0);
+    const float strain = f.lstrain[l].x;
+    const float ratio = f.vmat[meta_hi(f.pose1[e.y].w) & VM_MAT_MASK].E / f.vmat[meta_hi(f.pose1[e.x].w) & VM_MAT_MASK].E;
+    const size_t nv = (size_t)f.n_vox;
+    f.slot_strain[(size_t)(2 * axis) * nv + e.x] = 2.0f * strain / (1.0f + ratio);
+    f.slot_strain[(size_t)(2 * axis + 1) * nv + e.y] = 2.0f * strain * ratio / (1.0f + ratio);
 }
 
 __global__ void k_fill_temp(Frame f, float t, const float* member_t, const int* member_of)
