@@ -402,11 +402,11 @@ int  vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* 
 int  vx_save_state(vx_sim* s, const char* path);
 int  vx_load_state(vx_sim* s, const char* path);
 /* select kernel variant (tests; the layout part takes effect at the next vx_set_voxels):
- *   0 auto: models of at most 2048 voxels without halo flags and without self-collisions: small-model kernel (3);
+ *   0 auto: models of at most 700 voxels without halo flags and without self-collisions: small-model kernel (3);
  *           otherwise the fused lattice kernel for bodies whose bounding box is at most 8x their voxel count (holes
  *           are padded with inert cells, sparse bodies launch only their occupied brick groups), general path beyond
  *   1 general layout, one-step kernels (k_link<AXIS> x3 + k_voxel per step), any topology
- *   3 general layout stepped by k_small_steps: ONE thread-block cluster (<= 8 CTAs) runs all steps of a vx_step call in
+ *   3 general layout stepped by k_small_steps: ONE thread-block cluster (<= 16 CTAs) runs all steps of a vx_step call in
  *     a single launch, cluster barriers between the link and voxel phases (with self-collisions on, or dt < 0 on
  *     Poisson models, the one-step kernels of path 1 run instead)
  *   fused lattice kernel (one warp per 4x4x2 brick), with a fixed staging flavour:

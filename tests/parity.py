@@ -36,7 +36,7 @@ def run(lib: capi.VxLib, sc: scenarios.Scenario, steps: int, dt=None, program=No
     return sim, dt, div
 
 
-SMALL_MAX = 2048     # VX_SMALL_MAX of csrc/vx_capi.cu: below it "auto" steps the general layout with k_small_steps
+SMALL_MAX = 700     # VX_SMALL_MAX of csrc/vx_capi.cu: below it "auto" steps the general layout with k_small_steps
 
 
 def layout(path: int, n_voxels: int, collisions: bool = False) -> int:

@@ -82,7 +82,7 @@ def test_material_tables_bitwise(product, oracle):
 
 
 def test_layout_selection(product):
-    """auto: models of at most 2048 voxels without self-collisions are stepped by the small-model cluster kernel on the general
+    """auto: models of at most 700 voxels without self-collisions are stepped by the small-model cluster kernel on the general
     layout (one launch per vx_step call); everything else runs fused wherever its bounding box is at most 8x its voxel
     count.  vx_set_path forces either."""
     small = scenarios.build(product, scenarios.cantilever(6, 3, 3))

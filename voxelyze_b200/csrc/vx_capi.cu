@@ -697,14 +697,33 @@ static int launch_step(vx_sim* s, const Frame& f, bool per_step_dt, bool capturi
     return VX_OK;
 }
 
-// k_small_steps: one cluster of up to 8 CTAs x 256 threads (portable cluster size), all n steps
+// k_small_steps: one cluster of up to 16 CTAs, all n steps
 static int launch_small_steps(vx_sim* s, const Frame& f, int n_steps)
 {
+    // launch shape (profiles/r2_small_model.md): few warps per SM -- a step is the dependent FP64 chain of one link plus one voxel
+    // update, so spreading the threads over up to 16 SMs (non-portable cluster size, checked once) beats filling 4 of them
     const int work = std::max(s->N, s->L);
-    int ctas = std::max(1, std::min(8, (work + 255) / 256));
-    while (ctas & (ctas - 1)) ctas++;                               // 1, 2, 4 or 8
+    const int tpb = work <= 1024 ? 64 : 128;
+    static int max_ctas = 0;
+    if (!max_ctas) {
+        max_ctas = 8;
+        bool ok = true;
+        ok &= cudaFuncSetAttribute(k_small_steps<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(k_small_steps<false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(k_small_steps<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        cudaLaunchConfig_t probe = {};
+        probe.gridDim = dim3(16); probe.blockDim = dim3(128);
+        cudaLaunchAttribute pa[1];
+        pa[0].id = cudaLaunchAttributeClusterDimension; pa[0].val.clusterDim.x = 16; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+        probe.attrs = pa; probe.numAttrs = 1;
+        int clusters = 0;
+        if (ok && cudaOccupancyMaxActiveClusters(&clusters, k_small_steps<false, false>, &probe) == cudaSuccess && clusters > 0) max_ctas = 16;
+        cudaGetLastError();
+    }
+    int ctas = std::max(1, std::min(max_ctas, (work + tpb - 1) / tpb));
+    while (ctas & (ctas - 1)) ctas++;                               // 1, 2, 4, 8 or 16
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s->stream;
+    cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3((unsigned)tpb); cfg.dynamicSmemBytes = 0; cfg.stream = s->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
@@ -1183,9 +1202,9 @@ int vx_get_linkmat_curve(vx_sim* s, int a, int b, float* eps, float* sig, int ca
 static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t* mat, const int32_t* sim_id, const uint32_t* flags, int n_user);
 
 // Small models are stepped by one thread-block cluster that runs a whole vx_step call in a single launch
-// (k_small_steps, general layout): chosen by vx_set_path(3), or by default below VX_SMALL_MAX voxels when the model has no
+// (k_small_steps, general layout): chosen by vx_set_path(3), or by default up to VX_SMALL_MAX voxels when the model has no
 // halo / per-voxel flags and self-collisions are off at this point (with collisions the fused path's captured graphs win).
-constexpr int VX_SMALL_MAX = 2048;
+constexpr int VX_SMALL_MAX = 700;       // ~2 000 links: one pass of a 16 x 128-thread cluster; beyond, the fused kernel's graphs are as fast or faster
 static bool small_model(const vx_sim* s, int n, const uint32_t* flags)
 {
     if (s->path != 3 && !(s->path == 0 && n <= VX_SMALL_MAX && !s->collisions && !getenv("VX_NO_SMALL"))) return false;

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128) k_pstrain(Frame f)
 // ---- small models: ALL steps of a vx_step call in ONE launch -------------------------------------------------------
 // A model of a few hundred voxels (320 voxels, 784 links) cannot fill the GPU; what it pays per step is launch
 // latency and the dependent FP64 chain of one link and one voxel update.  k_small_steps runs the whole call as one
-// thread-block cluster (<= 8 CTAs on 8 SMs: one SM's 64 FP64 lanes would need ~5 us for C1's 784 link updates): per step a
+// thread-block cluster (<= 16 CTAs of 64 or 128 threads on as many SMs: one or two warps per SM sub-partition): per step a
 // link phase (thread per link, axis by range), a cluster barrier, a voxel phase, a cluster barrier -- the barrier
 // (barrier.cluster, release/acquire) replaces the kernel boundary of the general path, the state stays in L2 (state loads
 // bypass L1, ld.global.cg, because another SM wrote them one phase earlier).  Same device functions, same per-voxel
@@ -294,14 +294,19 @@ __global__ void __launch_bounds__(256) k_small_steps(Frame f, int af1, int af2, 
             for (int v = tid; v < f.n_vox; v += nthr) pstrain_body<true>(v, f);
             cluster.sync();
         }
+#ifndef VX_SMALL_PHASES
+#define VX_SMALL_PHASES 7      // ablation only (profiles/r2_small_model.md): 1 link phase, 2 voxel phase, 4 cluster barriers
+#endif
+        if (VX_SMALL_PHASES & 1)
         for (int l = tid; l < f.n_link; l += nthr) {
             if (l < af1) link_body<0, POISSON, UNI, true>(l, f);
             else if (l < af2) link_body<1, POISSON, UNI, true>(l, f);
             else link_body<2, POISSON, UNI, true>(l, f);
         }
-        cluster.sync();
+        if (VX_SMALL_PHASES & 4) cluster.sync();
+        if (VX_SMALL_PHASES & 2)
         for (int v = tid; v < f.n_vox; v += nthr) voxel_body<UNI, true>(v, f, floor_on, 0);
-        cluster.sync();
+        if (VX_SMALL_PHASES & 4) cluster.sync();
     }
 }
 
