@@ -404,6 +404,7 @@ def test_peer_memory_halo_steps_match_whole_steps_bitwise(product):
     sc = scenarios.cantilever(nx, ny, nz, tip_load=25.0)
     whole, dt, _ = parity.run(product, sc, steps)
     runs = [slab.SlabRunner(product, nx, ny, nz, r, 3, tip_load=25.0) for r in range(3)]
+    assert all("GSKIP" in r.sim.kernel_name() for r in runs)     # the ghost planes at the slab ends carry no bricks
     slab.SlabRunner.connect_local(runs)
     for _ in range(steps):
         for r in runs:
@@ -437,7 +438,7 @@ def test_any_scenario_runs_as_peer_memory_slabs_bitwise(product):
     sc = _general_scenario()
     whole = scenarios.build(product, sc, path=7); dt = whole.recommended_dt()
     runs = [slab.SlabRunner.from_scenario(product, sc, r, 3) for r in range(3)]
-    assert all(r.sim.active_path() == 2 for r in runs) and whole.active_path() == 2
+    assert all(r.sim.active_path() == 2 and "GSKIP" in r.sim.kernel_name() for r in runs) and whole.active_path() == 2
     slab.SlabRunner.connect_local(runs)
     for r in runs:
         r.exchange()                                     # initial temperature of the ghosts

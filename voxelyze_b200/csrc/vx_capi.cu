@@ -112,6 +112,9 @@ struct vx_sim {
     bool call_active = false, call_half = false;
     int call_g0 = 0, call_done = 0;     // starting generation, steps whose boundary part has been enqueued
     std::vector<int> zb_layers;         // brick-group layers (4 planes each) that hold ghost planes or their neighbours
+    // z-slabs on the TMA-staged kernel: the all-ghost planes at the ends are not covered by bricks (k_lattice_tma<.., GSKIP>);
+    // bricks, brick-group layers and zb_layers then count from plane z_lo
+    bool ghost_skip = false; int z_lo = 0, z_hi = 0;
     // peer-memory halo (vx_peer_*): my boundary layer -> the ghost layer of the neighbouring slab, over NVLink
     struct PeerLink {
         size_t src_first = 0, count = 0;                  // my layer (internal voxel range)
@@ -242,6 +245,7 @@ struct vx_sim {
         f.amb_set = 0; f.amb = 0.f;
         f.groups = n_groups > 0 ? group_list.p : nullptr;
         f.c_ps = any_poisson ? ps[g].p : nullptr; f.n_ps = any_poisson ? ps[g ^ 1].p : nullptr;
+        f.z_lo = ghost_skip ? z_lo : 0; f.z_hi = ghost_skip ? z_hi : nz;
         f.push_z[0] = f.push_z[1] = -1;
         if (push_in_kernel) {
             for (size_t k = 0; k < peers.size() && k < 2; k++) {
@@ -826,13 +830,18 @@ static void lattice_opt_in(vx_sim* s)
     cudaFuncSetAttribute(k_lattice_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
     cudaFuncSetAttribute(k_lattice_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
     cudaFuncSetAttribute(k_lattice_tma<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
+    cudaFuncSetAttribute(k_lattice_tma<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
+    cudaFuncSetAttribute(k_lattice_tma<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
+    cudaFuncSetAttribute(k_lattice_tma<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
     s->wb_opted_in = true;
 }
 
 // default fused kernel over the brick-group layers [gz_off, gz_off + ngz) (ngz < 0: all)
 static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off, int ngz, int book)
 {
-    const int bx = (s->nx + VX_WB_X - 1) / VX_WB_X, by = (s->ny + VX_WB_Y - 1) / VX_WB_Y, bz = (s->nz + VX_WB_Z - 1) / VX_WB_Z;
+    const int planes = s->ghost_skip ? s->z_hi - s->z_lo : s->nz;    // z-slabs: the ghost planes at the ends are data, not bricks
+    const int bx = (s->nx + VX_WB_X - 1) / VX_WB_X, by = (s->ny + VX_WB_Y - 1) / VX_WB_Y, bz = (planes + VX_WB_Z - 1) / VX_WB_Z;
     const int gx = (bx + 1) / 2, gy = (by + 1) / 2, gz = (bz + 1) / 2;
     // 2x2x2 groups of bricks unless their padding would waste more than a tenth of the warps (small boxes)
     const bool grouped = ngz >= 0 || (double)gx * gy * gz * 8 <= 1.1 * (double)bx * by * bz;
@@ -842,7 +851,7 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     // staging: TMA bulk tensor copies (7, and what 0 picks on large lattices) or per-lane cp.async (5, and what 0 picks for
     // ensembles of small boxes, where whole-box copies fetch too much padding: 1.15 against 1.19 ms on 4096 robots of 10^3)
     const bool listed = s->n_groups > 0 && ngz < 0;                 // sparse body: only its occupied brick groups
-    const bool want_tma = s->path == 7 || (s->path != 5 && grouped) || s->any_poisson || listed;     // Poisson coupling and group lists live in the TMA-staged kernel only
+    const bool want_tma = s->path == 7 || (s->path != 5 && grouped) || s->any_poisson || listed || s->ghost_skip;     // Poisson coupling and group lists live in the TMA-staged kernel only
     // (tensor maps are built outside stream capture: ensure_lattice_graph launches nothing before they exist)
     const bool tma = want_tma && (s->tmaps.p || (!s->capturing && build_tensor_maps(s) == VX_OK));
     lattice_opt_in(s);
@@ -864,7 +873,16 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
             const size_t tab = s->mats.size() * sizeof(DevVoxMat) + s->lmats.size() * sizeof(DevLinkMat) + s->mats.size() * 4 + s->mats.size() * s->mats.size() * 2;
             const int stage = (!s->uni && tab <= VX_TMA_TABLE_BYTES - 16) ? 1 : 0;
             const size_t tma_smem = VX_TMA_SMEM + (stage ? VX_TMA_TABLE_BYTES : 0);
-            if (s->any_poisson) k_lattice_tma<false, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
+            if (s->ghost_skip) {                                  // z-slab: bricks over the owned planes only
+                if (s->push_in_kernel) {
+                    if (s->uni) k_lattice_tma<true, true, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
+                    else k_lattice_tma<false, true, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
+                } else {
+                    if (s->uni) k_lattice_tma<true, false, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
+                    else k_lattice_tma<false, false, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
+                }
+            }
+            else if (s->any_poisson) k_lattice_tma<false, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
             else if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
                 if (s->uni) k_lattice_tma<true, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
                 else k_lattice_tma<false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
@@ -872,8 +890,8 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
                 if (s->uni) k_lattice_tma<true, false><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
                 else k_lattice_tma<false, false><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
             }
-        } else if (s->any_poisson) {
-            s->err = "Poisson materials on the fused layout need the TMA-staged kernel (tensor maps could not be built)"; s->launch_failed = true;
+        } else if (s->any_poisson || s->ghost_skip) {
+            s->err = "this model needs the TMA-staged kernel (tensor maps could not be built)"; s->launch_failed = true;
         } else {
             const dim3 gr((unsigned)grid);
             const int gr_ = grouped ? 1 : 0;
@@ -970,6 +988,16 @@ static int finish_lattice_call(vx_sim* s, int g_start, int launched, int* diverg
     return VX_DIVERGED;
 }
 
+// z-slabs with skipped ghost planes: their flag words into the generation the call writes first
+static void ghost_words_begin(vx_sim* s)
+{
+    if (!s->ghost_skip) return;
+    const int plane = s->nx * s->ny, n_lo = s->z_lo * plane, n_hi = (s->nz - s->z_hi) * plane;
+    if (n_lo + n_hi == 0) return;
+    k_lattice_ghost_words<<<blocks_for(n_lo + n_hi), TPB, 0, s->stream>>>(s->pose1[s->gen].p, s->pose1[s->gen ^ 1].p, n_lo, s->z_hi * plane, n_hi);
+    s->launches++;
+}
+
 static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
 {
     const bool per_step_dt = dt < 0 && s->any_poisson;      // with Poisson coupling the stable step depends on the state (src/VX_Link.cpp:259-267)
@@ -980,6 +1008,7 @@ static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     }
     k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, per_step_dt ? 0 : 1); s->launches++;
     collision_call_begin(s);
+    ghost_words_begin(s);
     const int g0 = s->gen;
     int done = 0;
     if (per_step_dt) {
@@ -1009,7 +1038,7 @@ static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
 // brick-group layers that a halo exchange touches: those holding an all-ghost plane or a plane next to one
 static void find_boundary_layers(vx_sim* s)
 {
-    s->zb_layers.clear();
+    s->zb_layers.clear(); s->ghost_skip = false; s->z_lo = 0; s->z_hi = s->nz;
     if (!s->lattice || s->n_members != 1 || s->vflags.empty()) return;
     const size_t plane = (size_t)s->nx * s->ny;
     std::vector<char> ghost(s->nz, 0);
@@ -1019,6 +1048,17 @@ static void find_boundary_layers(vx_sim* s)
         ghost[z] = all;
     }
     const int per = 2 * VX_WB_Z;
+    // ghost planes only at the two ends, single-material-or-not but no Poisson coupling, TMA staging allowed: skip them
+    s->z_lo = ghost[0] ? 1 : 0; s->z_hi = s->nz - (s->nz > 1 && ghost[s->nz - 1] ? 1 : 0);
+    bool inner = false;
+    for (int z = s->z_lo; z < s->z_hi; z++) inner = inner || ghost[z];
+    s->ghost_skip = (s->z_lo > 0 || s->z_hi < s->nz) && !inner && s->z_hi > s->z_lo && !s->any_poisson && !s->collisions && s->path != 5 && !getenv("VX_NO_GSKIP");
+    if (s->ghost_skip) {
+        const int last = (s->z_hi - 1 - s->z_lo) / per;
+        if (s->z_lo > 0) s->zb_layers.push_back(0);
+        if (s->z_hi < s->nz && (s->zb_layers.empty() || s->zb_layers.back() != last)) s->zb_layers.push_back(last);
+        return;
+    }
     for (int z = 0; z < s->nz; z++) {
         bool b = ghost[z] || (z > 0 && ghost[z - 1]) || (z + 1 < s->nz && ghost[z + 1]);
         if (b && (s->zb_layers.empty() || s->zb_layers.back() != z / per)) s->zb_layers.push_back(z / per);
@@ -1035,6 +1075,7 @@ int vx_step_begin(vx_sim* s, float dt)
     if (dt <= 0) return fail(s, VX_ERR_ARG, "vx_step_begin needs an explicit dt");
     CK(cudaSetDevice(s->device));
     k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
+    ghost_words_begin(s);
     s->call_active = true; s->call_half = false; s->call_g0 = s->gen; s->call_done = 0;
     return VX_OK;
 }
@@ -1042,7 +1083,7 @@ int vx_step_begin(vx_sim* s, float dt)
 int vx_step_enqueue(vx_sim* s, int part)
 {
     if (!s || !s->call_active || part < 0 || part > 2) return VX_ERR_ARG;
-    const int ngz = (s->nz + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z);
+    const int ngz = ((s->ghost_skip ? s->z_hi - s->z_lo : s->nz) + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z);
     const bool split = !s->zb_layers.empty() && (int)s->zb_layers.size() < ngz;
     if (part == VX_PART_Z_INTERIOR) {
         if (!s->call_half) return fail(s, VX_ERR_ARG, "vx_step_enqueue: interior part without its boundary part");
@@ -1684,6 +1725,7 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
         if (dt < 0) { rc = vx_recommended_dt(s, &dt); if (rc != VX_OK || dt <= 0) return rc; }
         k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
         collision_call_begin(s);
+        ghost_words_begin(s);
         const int g0 = s->gen;
         for (int k = 0; k < n_steps; k++) {
             CK(cudaEventRecord(ev[4 * k + 0], s->stream));
@@ -2104,6 +2146,7 @@ const char* vx_kernel_name(const vx_sim* s)
         const int bx = (s->nx + VX_WB_X - 1) / VX_WB_X, by = (s->ny + VX_WB_Y - 1) / VX_WB_Y, bz = (s->nz + VX_WB_Z - 1) / VX_WB_Z;
         tma = (double)((bx + 1) / 2) * ((by + 1) / 2) * ((bz + 1) / 2) * 8 <= 1.1 * (double)bx * by * bz;
     }
+    if (s->ghost_skip) return "k_lattice_tma<GSKIP> (fused link+voxel, 4x4x2 brick per warp, TMA staging, z-slab: no bricks on the ghost planes, 1 launch per step part)";
     return tma ? "k_lattice_tma (fused link+voxel, 4x4x2 brick per warp, TMA staging, 1 launch per step)"
                : "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, cp.async staging, 1 launch per step)";
 }

@@ -64,6 +64,9 @@ struct LatFrame {
     // Poisson coupling (nu != 0, k_lattice_tma<.., POISSON>): CVX_Voxel::pStrain of every voxel as of the state the step reads
     // (= computed from the link strains of the previous step), double-buffered like the voxel state
     const float4* c_ps; float4* n_ps;
+    // z-slab runs on k_lattice_tma<.., GSKIP>: bricks cover the planes [z_lo, z_hi) only -- the all-ghost planes below and above
+    // are data, not work (brick origins are shifted by z_lo; 0 / nz everywhere else)
+    int z_lo, z_hi;
 };
 
 // where a kernel reads the material tables of a multi-material model: global memory (through L1), or a copy the CTA staged
@@ -563,6 +566,16 @@ k_lattice_warp(LatFrame f, int parity, int first_of_call, int floor_on, int nbx,
 }
 
 
+// GSKIP (see k_lattice_tma): no brick rewrites the flag words (upper half of pose1.w) of the ghost planes any more, so the
+// generation a stepping call writes first gets them copied once, from the generation it starts on
+__global__ void k_lattice_ghost_words(const double4* __restrict__ c_pose1, double4* __restrict__ n_pose1, int n_lo, int hi_first, int n_hi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lo + n_hi) return;
+    const int v = i < n_lo ? i : hi_first + (i - n_lo);
+    reinterpret_cast<uint32_t*>(&n_pose1[v].w)[1] = reinterpret_cast<const uint32_t*>(&c_pose1[v].w)[1];
+}
+
 // =================================================================================================
 // k_lattice_tma -- the warp-brick step with its staging done by the Tensor Memory Accelerator.
 //
@@ -632,7 +645,11 @@ __device__ __forceinline__ void tma_4d(uint32_t dst, const void* map, uint32_t b
 
 // Grid: grouped (large lattices) -> 3-D, one CTA per 2x2x2 group of bricks: blockIdx = (group x, group y, member * nbz + group layer);
 //       else (ensembles of small boxes) -> 1-D, eight consecutive bricks per CTA, bricks x-fastest, no padding.
-template <bool UNI, bool PUSH, bool POISSON = false>
+// GSKIP (z-slabs): the ghost planes at the two ends of the slab are not covered by bricks.  The top one never needed any: its
+// voxels are not integrated and the links that reach it are owned from below.  The bottom one owns the +Z links into the first
+// owned plane; those are evaluated in round H of the bricks above it anyway (as entering links), so with GSKIP that lane also
+// stores the link's new record and mode bits on the ghost's behalf -- the same values the ghost's own brick would have stored.
+template <bool UNI, bool PUSH, bool POISSON = false, bool GSKIP = false>
 __global__ void __launch_bounds__(32 * VX_WB_WARPS, VX_WB_MINBLOCKS)
 k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_call, int floor_on, int nbx, int nby, int nbz, int gz_off, int book, int grouped, int stage_tables)
 {
@@ -660,15 +677,15 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         const unsigned zz = blockIdx.z;
         member = gridDim.z > (unsigned)nbz ? (int)(zz / (unsigned)nbz) : 0;
         const int gz = gz_off + (int)zz - member * nbz;
-        x0 = ((int)blockIdx.x * 2 + (warp & 1)) * VX_WB_X; y0 = ((int)blockIdx.y * 2 + ((warp >> 1) & 1)) * VX_WB_Y; z0 = (gz * 2 + (warp >> 2)) * VX_WB_Z;
+        x0 = ((int)blockIdx.x * 2 + (warp & 1)) * VX_WB_X; y0 = ((int)blockIdx.y * 2 + ((warp >> 1) & 1)) * VX_WB_Y; z0 = (gz * 2 + (warp >> 2)) * VX_WB_Z + (GSKIP ? f.z_lo : 0);
     } else {
         unsigned b = blockIdx.x * VX_WB_WARPS + warp;
         const unsigned gx = b % (unsigned)nbx; b /= (unsigned)nbx;
         const unsigned gy = b % (unsigned)nby; b /= (unsigned)nby;
         const unsigned gz = b % (unsigned)nbz; member = (int)(b / (unsigned)nbz);
-        x0 = (int)gx * VX_WB_X; y0 = (int)gy * VX_WB_Y; z0 = (gz_off + (int)gz) * VX_WB_Z;
+        x0 = (int)gx * VX_WB_X; y0 = (int)gy * VX_WB_Y; z0 = (gz_off + (int)gz) * VX_WB_Z + (GSKIP ? f.z_lo : 0);
     }
-    const bool no_brick = member * f.nz * f.nxy >= f.n_vox || x0 >= f.nx || y0 >= f.ny || z0 >= f.nz;            // whole warp
+    const bool no_brick = member * f.nz * f.nxy >= f.n_vox || x0 >= f.nx || y0 >= f.ny || z0 >= (GSKIP ? f.z_hi : f.nz);            // whole warp
     const int vbase = member * f.nz * f.nxy;
     const int Z0 = member * f.nz + z0;             // the tensors see the members stacked along z
 
@@ -780,6 +797,15 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
                                make_float4(__uint_as_float(r3.x), __uint_as_float(r3.y), __uint_as_float(r3.z), __uint_as_float(r3.w)),
                                n0, n1, p0, p1, prev_dt, st, fN, mN, hF, hM, damp_u,
                                POISSON ? &h_psn : nullptr, POISSON ? &h_psp : nullptr, POISSON ? h_end : nullptr, &tables);
+        if (GSKIP && h_axis == 2 && (meta_hi(n1.w) & VM_GHOST)) {     // the link's owner is a ghost below the bricks: keep its record
+            const int vg = vbase + ((z0 - 1) * f.ny + y0 + ((h_tl >> 2) & 3)) * f.nx + x0 + (h_tl & 3);
+            double2 wa, wb, wc; float4 ws; uint32_t lf;
+            lat_encode(st, wa, wb, wc, ws, lf);
+            double2* nr = f.n_rec[0][0] + (size_t)8 * f.n_vox + vg;
+            nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; *reinterpret_cast<float4*>(nr + 3 * (size_t)f.n_vox) = ws;
+            reinterpret_cast<uint32_t*>(&f.n_pose1[vg].w)[1] = (meta_hi(n1.w) & ~(3u << (VM_LFLAG_SHIFT + 4))) | (lf << (VM_LFLAG_SHIFT + 4));
+            if (st.strain > 100) p->div_flag[parity] = 1;
+        }
     }
     __syncwarp();                          // every lane has read its round-H inputs: their space is re-used now
     double (*hslot)[32] = reinterpret_cast<double (*)[32]>(wbase + 9216);                 // [comp][entering link]
