@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define VX_ABI_VERSION 3
+#define VX_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------- */
 #define VX_OK              0
@@ -359,6 +359,11 @@ int  vx_peer_attach(vx_sim* s, int send_iz, const vx_peer_desc* peer_ghost);
 int  vx_peer_detach(vx_sim* s);
 int  vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step);
 int  vx_slab_exchange(vx_sim* s);
+/* vx_slab_step in two halves for a caller that drives several slabs from ONE thread: vx_slab_step_begin queues all n steps
+ * (with their waits, pushes and signals) and returns without blocking, vx_slab_step_finish blocks and reports like
+ * vx_slab_step.  Begin every slab before finishing any; each slab must be on a device of its own.                      */
+int  vx_slab_step_begin(vx_sim* s, float dt, int n_steps);
+int  vx_slab_step_finish(vx_sim* s, int* diverged_step);
 /* number of kernels this handle has launched so far (bench.py "gpu_launches").       */
 int64_t vx_launch_count(const vx_sim* s);
 /* block until all queued work of this handle is done.                                */
@@ -419,6 +424,48 @@ int  vx_set_path(vx_sim* s, int path);
 int  vx_active_path(const vx_sim* s);
 /* name of the kernel that dominates a step of this handle (static string, for reports)  */
 const char* vx_kernel_name(const vx_sim* s);
+
+/* ---- one lattice on several GPUs of ONE process ---------------------------------
+ * What a caller of the C++ class API needs to reach more than one GPU: a vx_slabbed handle takes the WHOLE model in the
+ * caller's numbering, cuts it into z-slabs (one vx_sim per listed device, one ghost plane per cut), and fans the calls of
+ * the hot path out / gathers state back, in the voxel and link numbering of the whole model.  The functions mirror their
+ * vx_* namesakes (same argument meaning, same status codes); bits are those of the unsplit run.  Halo transport:
+ * vx_slabbed_halo_mode = 2: the step kernels store boundary poses into the neighbours' ghost planes themselves (peer
+ * memory over NVLink, all devices queued before any is waited for); 1: host copies after every step (implementations
+ * without peer memory); 0: the model runs on one slab (fewer than four z planes, or one device listed).
+ * Restrictions: one body (no ensemble ids), no self-collisions, no Poisson materials (a ghost copy lacks the links its
+ * Poisson strain needs, src/VX_Voxel.cpp:300-374): VX_ERR_UNSUPPORTED.  devices == NULL: devices 0 .. n_slabs-1; the
+ * same device may be listed more than once (tests on one GPU).  vx_slabbed_slab exposes slab k for reports
+ * (vx_kernel_name, vx_launch_count, vx_active_path); do not step it directly.                                        */
+typedef struct vx_slabbed vx_slabbed;
+int  vx_slabbed_create(double voxel_size, int n_slabs, const int* devices, vx_slabbed** out);
+void vx_slabbed_destroy(vx_slabbed* m);
+const char* vx_slabbed_last_error(const vx_slabbed* m);
+int  vx_slabbed_slab_count(const vx_slabbed* m);                 /* slabs the current model uses */
+vx_sim* vx_slabbed_slab(vx_slabbed* m, int k);
+int  vx_slabbed_halo_mode(const vx_slabbed* m);
+int  vx_slabbed_set_materials(vx_slabbed* m, int n, const vx_material_desc* descs);
+int  vx_slabbed_set_gravity(vx_slabbed* m, float g);
+int  vx_slabbed_enable_floor(vx_slabbed* m, int enabled);
+int  vx_slabbed_set_voxels(vx_slabbed* m, int n, const int32_t* ijk, const uint16_t* mat);
+int  vx_slabbed_voxel_count(const vx_slabbed* m);
+int  vx_slabbed_link_count(const vx_slabbed* m);
+int  vx_slabbed_get_links(const vx_slabbed* m, int32_t* v_neg, int32_t* v_pos, uint8_t* axis);
+int  vx_slabbed_set_externals(vx_slabbed* m, int n, const int32_t* voxel, const uint8_t* dof,
+                              const float* force, const float* moment,
+                              const double* translation, const double* rotation);
+int  vx_slabbed_set_temperature_all(vx_slabbed* m, float t);
+int  vx_slabbed_set_temperature(vx_slabbed* m, int n, const float* t);
+int  vx_slabbed_step(vx_slabbed* m, float dt, int n_steps, int* diverged_step);
+int  vx_slabbed_recommended_dt(vx_slabbed* m, float* dt);
+int  vx_slabbed_reset(vx_slabbed* m);
+float vx_slabbed_time(const vx_slabbed* m);
+int  vx_slabbed_download(vx_slabbed* m, int field, int first, int count, void* dst);
+int  vx_slabbed_upload(vx_slabbed* m, int field, int first, int count, const void* src);      /* voxel fields */
+int  vx_slabbed_download_voxel_state(vx_slabbed* m, int first, int count, vx_voxel_state* dst);
+int  vx_slabbed_download_link_state(vx_slabbed* m, int first, int count, vx_link_state* dst);
+int  vx_slabbed_upload_link_state(vx_slabbed* m, int first, int count, const vx_link_state* src);
+int64_t vx_slabbed_launch_count(const vx_slabbed* m);
 
 #ifdef __cplusplus
 }

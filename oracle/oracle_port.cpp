@@ -1117,6 +1117,8 @@ int vx_peer_export(vx_sim*, int, int, vx_peer_desc*) { return VX_ERR_UNSUPPORTED
 int vx_peer_attach(vx_sim*, int, const vx_peer_desc*) { return VX_ERR_UNSUPPORTED; }
 int vx_peer_detach(vx_sim*) { return VX_ERR_UNSUPPORTED; }
 int vx_slab_step(vx_sim*, float, int, int*) { return VX_ERR_UNSUPPORTED; }
+int vx_slab_step_begin(vx_sim*, float, int) { return VX_ERR_UNSUPPORTED; }
+int vx_slab_step_finish(vx_sim*, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_slab_exchange(vx_sim*) { return VX_ERR_UNSUPPORTED; }
 int vx_save_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
 int vx_load_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
@@ -1266,3 +1268,6 @@ int vx_linear_solve(vx_sim* s, double, int, int* iterations, double* rel_residua
 }
 
 } // extern "C"
+
+// vx_slabbed_*: host-side composition over the entry points above (shared with the product library: the partition logic under test)
+#include "../voxelyze_b200/csrc/vx_slabbed.hpp"

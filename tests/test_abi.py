@@ -43,7 +43,7 @@ def test_oracles_export_every_symbol(built):
 def test_ctypes_binding_matches_header(built):
     lib = capi.load_oracle()
     assert sorted(lib.symbols) == declared_symbols()
-    assert lib.lib.vx_abi_version() == 3
+    assert lib.lib.vx_abi_version() == 4
     assert lib.backend == "oracle-port"
 
 

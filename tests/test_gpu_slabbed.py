@@ -1,0 +1,58 @@
+"""vx_slabbed_* on the CUDA library: the whole model in the caller's numbering, z-slabs on the devices of ONE process, halo by
+the step kernels' own peer stores.  Bit for bit against the unsplit run.  With one GPU all slabs share it (lock-step stepping);
+with two or more (gpurun --gpus 2) every slab has its own device and all of them are queued before any is waited for."""
+import numpy as np
+import pytest
+
+import parity
+from test_slab_gloo import _general_scenario
+from test_slabbed import check_slabbed_against_whole, check_state_edits, holes_scenario, VOXEL_FIELDS
+from voxelyze_b200 import scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_slabbed_handle_runs_on_peer_stores_bitwise(product):
+    whole, multi, dt = check_slabbed_against_whole(product, _general_scenario(), [0, 0, 0], 120, expect_halo=2)
+    assert all(multi.slab(k).active_path() == 2 and "GSKIP" in multi.slab(k).kernel_name() for k in range(3))
+    assert multi.launch_count() > 0
+
+
+def test_slabbed_body_with_holes(product):
+    whole, multi, dt = check_slabbed_against_whole(product, holes_scenario(), [0] * 4, 150, temperature_program=False, chunk=10)
+    assert multi.halo_mode in (1, 2)
+
+
+def test_slabbed_state_edits_reach_every_copy(product):
+    check_state_edits(product, [0, 0, 0])
+
+
+def test_slabbed_larger_lattice_many_steps_per_call(product):
+    sc = scenarios.cantilever(40, 24, 48, tip_load=60.0)
+    check_slabbed_against_whole(product, sc, [0, 0], 200, temperature_program=False, expect_halo=2, chunk=50)
+
+
+def test_slabbed_divergence(product):
+    sc = scenarios.cantilever(12, 6, 16, tip_load=1.0)
+    whole, multi = scenarios.build(product, sc, path=7), scenarios.build_slabbed(product, sc, [0, 0])
+    dt = 40.0 * whole.recommended_dt()
+    a, b = whole.step(dt, 400), multi.step(dt, 400)
+    assert a is not None and a == b
+
+
+@pytest.mark.parametrize("n_dev", [2, 4])
+def test_slabbed_one_slab_per_device(product, n_dev):
+    """Distinct devices: vx_slab_step_begin on every slab, then vx_slab_step_finish -- no host work per step."""
+    if _gpus() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs (gpurun --gpus {n_dev})")
+    sc = scenarios.cantilever(64, 32, 64, tip_load=200.0)
+    whole, multi, dt = check_slabbed_against_whole(product, sc, list(range(n_dev)), 300, temperature_program=False, expect_halo=2, chunk=100)
+    multi.reset(); whole.reset()
+    assert multi.step(dt, 37) is None and whole.step(dt, 37) is None
+    for f in VOXEL_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f

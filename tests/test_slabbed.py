@@ -1,0 +1,130 @@
+"""vx_slabbed_*: one model, several slabs, ONE process (include/voxelyze_b200.h).  The composition is host code shared by every
+library that implements the header, so its partition logic -- slab ranges, ghost planes, externals, link numbering, gather
+and scatter in the caller's numbering -- is checked here on the CPU with the restatement library and host halo copies,
+bit for bit against the unsplit run of the same calls; tests/test_gpu_slabbed.py runs the same checks on the CUDA library
+with the in-kernel peer stores."""
+import numpy as np
+import pytest
+
+import parity
+from test_slab_gloo import _general_scenario
+from voxelyze_b200 import capi, scenarios
+
+VOXEL_FIELDS = ("pos", "orient", "linmom", "angmom", "temp", "voxflags")
+LINK_FIELDS = ("force_neg", "force_pos", "moment_neg", "moment_pos", "pos2", "angle1v", "angle2v", "strain", "maxstrain", "strainoffset", "stress", "linkflags")
+
+
+def holes_scenario():
+    """A 6 x 5 x 12 block with a window through it and a notch, created in shuffled order, hanging from its x = 0 face."""
+    ijk = scenarios.box_ijk(6, 5, 12, origin=(-3, 2, -4))
+    keep = ~((ijk[:, 0] >= -1) & (ijk[:, 0] <= 0) & (ijk[:, 2] >= 0) & (ijk[:, 2] <= 3)) & ~((ijk[:, 0] == 2) & (ijk[:, 1] == 6) & (ijk[:, 2] > 5))
+    ijk = ijk[keep]
+    ijk = ijk[np.random.default_rng(11).permutation(len(ijk))]
+    mats = [capi.Material(E=1e6, rho=1e3, zeta_global=0.01), capi.Material(E=2e6, rho=1.5e3, model=capi.MODEL_BILINEAR, plastic_modulus=2e5, yield_stress=2e3, fail_stress=-1.0)]
+    mat = (ijk[:, 1] & 1).astype(np.uint16)
+    sc = scenarios.Scenario("slabbed_holes", 0.005, mats, ijk, mat, gravity=1.0)
+    fixed = np.nonzero(ijk[:, 0] == -3)[0]
+    load = np.nonzero(ijk[:, 0] == 2)[0]
+    sc.ext_voxel = np.concatenate([fixed, load]).astype(np.int32)
+    sc.ext_dof = np.concatenate([np.full(len(fixed), capi.DOF_ALL), np.zeros(len(load))]).astype(np.uint8)
+    f = np.zeros((len(sc.ext_voxel), 3), np.float32); f[len(fixed):] = [0.0, 0.01, -0.05]
+    sc.ext_force = f
+    return sc
+
+
+def check_slabbed_against_whole(lib, sc, devices, steps, temperature_program=True, expect_halo=None, chunk=1):
+    whole = scenarios.build(lib, sc)
+    multi = scenarios.build_slabbed(lib, sc, devices)
+    assert multi.n_slabs == min(len(devices), (int(sc.ijk[:, 2].max()) - int(sc.ijk[:, 2].min()) + 1) // 2)
+    if expect_halo is not None:
+        assert multi.halo_mode == expect_halo, multi.halo_mode
+    assert multi.n_voxels == whole.n_voxels and multi.n_links == whole.n_links
+    for a, b in zip(multi.links(), whole.links()):          # the reference's link creation order, restated on the host
+        assert np.array_equal(a, b)
+    dt = whole.recommended_dt()
+    assert np.float32(dt) == np.float32(multi.recommended_dt())
+    k = 0
+    while k < steps:
+        if temperature_program:
+            t = 3.0 * np.sin(k / 10.0)
+            whole.set_temperature_all(t); multi.set_temperature_all(t)
+        assert whole.step(dt, chunk) is None and multi.step(dt, chunk) is None
+        k += chunk
+    assert whole.time() == multi.time()
+    for f in VOXEL_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
+    for f in LINK_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
+    n, nl = whole.n_voxels, whole.n_links
+    for i in (0, n // 3, n - 1):                             # single elements come from the owning slab
+        assert parity.bit_equal(multi.download("pos", i, 1), whole.download("pos", i, 1))
+        a, b = multi.download_voxel_state(i, 1), whole.download_voxel_state(i, 1)
+        assert a.tobytes() == b.tobytes()
+    assert multi.download_voxel_state(0, n).tobytes() == whole.download_voxel_state(0, n).tobytes()
+    if lib.backend.startswith("cuda"):                     # packed link records: the restatement library has none
+        assert multi.download_link_state().tobytes() == whole.download_link_state().tobytes()
+        for i in (0, nl // 2, nl - 1):
+            assert multi.download_link_state(i, 1).tobytes() == whole.download_link_state(i, 1).tobytes()
+    return whole, multi, dt
+
+
+def test_slabbed_handle_equals_the_unsplit_run_bitwise(built):
+    lib = capi.load_oracle()
+    check_slabbed_against_whole(lib, _general_scenario(), [0, 0, 0], 90, expect_halo=1)
+
+
+def test_slabbed_body_with_holes_and_plastic_links(built):
+    lib = capi.load_oracle()
+    whole, multi, dt = check_slabbed_against_whole(lib, holes_scenario(), [0] * 4, 150, temperature_program=False, expect_halo=1, chunk=10)
+    assert (whole.download("linkflags") & capi.LF_YIELDED).any()
+
+
+def check_state_edits(lib, devices):
+    sc = _general_scenario()
+    whole, multi, dt = check_slabbed_against_whole(lib, sc, devices, 40)
+    n = whole.n_voxels
+    rng = np.random.default_rng(3)
+    pos = whole.download("pos") + 1e-6 * rng.standard_normal((n, 3))
+    temp = rng.uniform(-2, 2, n).astype(np.float32)
+    records = lib.backend.startswith("cuda")
+    if records:
+        link = whole.download_link_state(); link["strain_offset"] += np.float32(1e-5)
+    for s in (whole, multi):
+        s.upload("pos", pos)                                  # everything at once ...
+        s.upload("linmom", np.zeros((5, 3)), first=n // 2)   # ... a short range (per element: owner + ghost copies) ...
+        s.set_temperature(temp)
+        if records:
+            s.upload_link_state(link)
+            s.upload_link_state(link[7:9], first=7)
+        assert s.step(dt, 25) is None
+    for f in VOXEL_FIELDS + LINK_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
+    for s in (whole, multi):
+        s.reset()
+        assert s.time() == 0.0
+        assert s.step(dt, 10) is None
+    for f in VOXEL_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
+
+
+def test_slabbed_state_edits_reach_every_copy(built):
+    """vx_slabbed_upload / upload_link_state / set_temperature / reset: the ghost copies across the cuts follow, so the run that
+    continues from edited state stays bit-identical to the unsplit run given the same edits."""
+    check_state_edits(capi.load_oracle(), [0, 0, 0])
+
+
+def test_slabbed_divergence_and_refusals(built):
+    lib = capi.load_oracle()
+    sc = scenarios.cantilever(6, 3, 8, tip_load=1.0)
+    whole, multi = scenarios.build(lib, sc), scenarios.build_slabbed(lib, sc, [0, 0])
+    dt = 40.0 * whole.recommended_dt()                        # far beyond the stable step: the run blows up
+    a, b = whole.step(dt, 400), multi.step(dt, 400)
+    assert a is not None and a == b
+    # thin bodies run on one slab, Poisson materials are refused when cut
+    thin = scenarios.cantilever(6, 3, 3)
+    assert scenarios.build_slabbed(lib, thin, [0, 0, 0]).n_slabs == 1
+    m = lib.create_slabbed(0.005, [0, 0])
+    m.set_materials([capi.Material(E=1e6, rho=1e3, nu=0.3)])
+    with pytest.raises(capi.VxError) as e:
+        m.set_voxels(sc.ijk, sc.mat)
+    assert e.value.code == -6

@@ -186,6 +186,35 @@ class VxLib:
             "vx_active_path": (i32, [vp]),
             "vx_kernel_name": (C.c_char_p, [vp]),
             "vx_step_profile": (i32, [vp, f32, i32, P(f32), P(i32)]),
+            "vx_slab_step_begin": (i32, [vp, f32, i32]),
+            "vx_slab_step_finish": (i32, [vp, P(i32)]),
+            # one lattice on several devices of one process
+            "vx_slabbed_create": (i32, [C.c_double, i32, vp, P(vp)]),
+            "vx_slabbed_destroy": (None, [vp]),
+            "vx_slabbed_last_error": (C.c_char_p, [vp]),
+            "vx_slabbed_slab_count": (i32, [vp]),
+            "vx_slabbed_slab": (vp, [vp, i32]),
+            "vx_slabbed_halo_mode": (i32, [vp]),
+            "vx_slabbed_set_materials": (i32, [vp, i32, P(MaterialDesc)]),
+            "vx_slabbed_set_gravity": (i32, [vp, f32]),
+            "vx_slabbed_enable_floor": (i32, [vp, i32]),
+            "vx_slabbed_set_voxels": (i32, [vp, i32, vp, vp]),
+            "vx_slabbed_voxel_count": (i32, [vp]),
+            "vx_slabbed_link_count": (i32, [vp]),
+            "vx_slabbed_get_links": (i32, [vp, vp, vp, vp]),
+            "vx_slabbed_set_externals": (i32, [vp, i32, vp, vp, vp, vp, vp, vp]),
+            "vx_slabbed_set_temperature_all": (i32, [vp, f32]),
+            "vx_slabbed_set_temperature": (i32, [vp, i32, vp]),
+            "vx_slabbed_step": (i32, [vp, f32, i32, P(i32)]),
+            "vx_slabbed_recommended_dt": (i32, [vp, P(f32)]),
+            "vx_slabbed_reset": (i32, [vp]),
+            "vx_slabbed_time": (f32, [vp]),
+            "vx_slabbed_download": (i32, [vp, i32, i32, i32, vp]),
+            "vx_slabbed_upload": (i32, [vp, i32, i32, i32, vp]),
+            "vx_slabbed_download_voxel_state": (i32, [vp, i32, i32, vp]),
+            "vx_slabbed_download_link_state": (i32, [vp, i32, i32, vp]),
+            "vx_slabbed_upload_link_state": (i32, [vp, i32, i32, vp]),
+            "vx_slabbed_launch_count": (C.c_int64, [vp]),
         }
         self.symbols = list(sig)
         for name, (res, args) in sig.items():
@@ -198,6 +227,9 @@ class VxLib:
 
     def create(self, voxel_size: float, device: int = 0) -> "Sim":
         return Sim(self, voxel_size, device)
+
+    def create_slabbed(self, voxel_size: float, devices: Sequence[int]) -> "SlabbedSim":
+        return SlabbedSim(self, voxel_size, devices)
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -234,23 +266,7 @@ class Sim:
 
     # -- model -----------------------------------------------------------------
     def set_materials(self, mats: Sequence[Material]):
-        arr = (MaterialDesc * len(mats))()
-        keep = []
-        for d, m in zip(arr, mats):
-            d.model = m.model
-            d.youngs_modulus, d.plastic_modulus = m.E, m.plastic_modulus
-            d.yield_stress, d.fail_stress = m.yield_stress, m.fail_stress
-            if m.model == MODEL_DATA:
-                s = np.ascontiguousarray(m.strain, dtype=np.float32)
-                t = np.ascontiguousarray(m.stress, dtype=np.float32)
-                keep += [s, t]
-                d.n_points = len(s)
-                d.strain = s.ctypes.data_as(C.POINTER(C.c_float))
-                d.stress = t.ctypes.data_as(C.POINTER(C.c_float))
-            d.density, d.poissons_ratio, d.cte = m.rho, m.nu, m.cte
-            d.mu_static, d.mu_kinetic = m.mu_static, m.mu_kinetic
-            d.zeta_internal, d.zeta_global, d.zeta_collision = m.zeta_internal, m.zeta_global, m.zeta_collision
-            d.ext_scale[0], d.ext_scale[1], d.ext_scale[2] = m.ext_scale
+        arr, keep = _material_descs(mats)
         self._chk(self.L.lib.vx_set_materials(self.h, len(mats), arr))
 
     def voxmat(self, i: int) -> dict:
@@ -503,6 +519,173 @@ class Sim:
 
     def set_path(self, path: int):
         self._chk(self.L.lib.vx_set_path(self.h, path))
+
+
+def _material_descs(mats: Sequence[Material]):
+    arr = (MaterialDesc * len(mats))()
+    keep = []
+    for d, m in zip(arr, mats):
+        d.model = m.model
+        d.youngs_modulus, d.plastic_modulus = m.E, m.plastic_modulus
+        d.yield_stress, d.fail_stress = m.yield_stress, m.fail_stress
+        if m.model == MODEL_DATA:
+            s = np.ascontiguousarray(m.strain, dtype=np.float32)
+            t = np.ascontiguousarray(m.stress, dtype=np.float32)
+            keep += [s, t]
+            d.n_points = len(s)
+            d.strain = s.ctypes.data_as(C.POINTER(C.c_float))
+            d.stress = t.ctypes.data_as(C.POINTER(C.c_float))
+        d.density, d.poissons_ratio, d.cte = m.rho, m.nu, m.cte
+        d.mu_static, d.mu_kinetic = m.mu_static, m.mu_kinetic
+        d.zeta_internal, d.zeta_global, d.zeta_collision = m.zeta_internal, m.zeta_global, m.zeta_collision
+        d.ext_scale[0], d.ext_scale[1], d.ext_scale[2] = m.ext_scale
+    return arr, keep
+
+
+class _SlabView(Sim):
+    """One slab of a SlabbedSim, for reports (kernel_name, launch_count, active_path); owned by the slabbed handle."""
+
+    def __init__(self, lib: VxLib, handle):
+        self.L, self.h, self._keep = lib, C.c_void_p(handle), []
+
+    def close(self):
+        self.h = C.c_void_p()
+
+
+class SlabbedSim:
+    """vx_slabbed_*: the WHOLE model in the caller's numbering, run as z-slabs on the listed devices of this process
+    (include/voxelyze_b200.h).  Same method names and meaning as Sim where they exist."""
+
+    def __init__(self, lib: VxLib, voxel_size: float, devices: Sequence[int]):
+        self.L = lib
+        self.h = C.c_void_p()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = lib.lib.vx_slabbed_create(float(voxel_size), len(dev), _ptr(dev), C.byref(self.h))
+        if rc != VX_OK:
+            raise VxError(rc, f"vx_slabbed_create failed on {lib.path}")
+        self.voxel_size = voxel_size
+
+    def close(self):
+        if self.h:
+            self.L.lib.vx_slabbed_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int, ok=(VX_OK,)):
+        if rc not in ok:
+            raise VxError(rc, self.L.lib.vx_slabbed_last_error(self.h).decode())
+        return rc
+
+    @property
+    def n_slabs(self) -> int:
+        return self.L.lib.vx_slabbed_slab_count(self.h)
+
+    @property
+    def halo_mode(self) -> int:
+        return self.L.lib.vx_slabbed_halo_mode(self.h)
+
+    def slab(self, k: int) -> Sim:
+        return _SlabView(self.L, self.L.lib.vx_slabbed_slab(self.h, k))
+
+    def set_materials(self, mats: Sequence[Material]):
+        arr, keep = _material_descs(mats)
+        self._chk(self.L.lib.vx_slabbed_set_materials(self.h, len(mats), arr))
+
+    def set_gravity(self, g: float):
+        self._chk(self.L.lib.vx_slabbed_set_gravity(self.h, g))
+
+    def enable_floor(self, on: bool = True):
+        self._chk(self.L.lib.vx_slabbed_enable_floor(self.h, int(on)))
+
+    def set_voxels(self, ijk, mat):
+        ijk = np.ascontiguousarray(ijk, dtype=np.int32).reshape(-1, 3)
+        mat = np.ascontiguousarray(mat, dtype=np.uint16)
+        self._chk(self.L.lib.vx_slabbed_set_voxels(self.h, len(ijk), _ptr(ijk), _ptr(mat)))
+
+    @property
+    def n_voxels(self) -> int:
+        return self.L.lib.vx_slabbed_voxel_count(self.h)
+
+    @property
+    def n_links(self) -> int:
+        return self.L.lib.vx_slabbed_link_count(self.h)
+
+    def links(self):
+        n = self.n_links
+        vn, vp, ax = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        self._chk(self.L.lib.vx_slabbed_get_links(self.h, _ptr(vn), _ptr(vp), _ptr(ax)))
+        return vn, vp, ax
+
+    def set_externals(self, voxel, dof, force=None, moment=None, translation=None, rotation=None):
+        voxel = np.ascontiguousarray(voxel, dtype=np.int32)
+        n = len(voxel)
+        dof = np.ascontiguousarray(dof, dtype=np.uint8)
+        f = None if force is None else np.ascontiguousarray(force, dtype=np.float32).reshape(n, 3)
+        m = None if moment is None else np.ascontiguousarray(moment, dtype=np.float32).reshape(n, 3)
+        t = None if translation is None else np.ascontiguousarray(translation, dtype=np.float64).reshape(n, 3)
+        r = None if rotation is None else np.ascontiguousarray(rotation, dtype=np.float64).reshape(n, 3)
+        self._chk(self.L.lib.vx_slabbed_set_externals(self.h, n, _ptr(voxel), _ptr(dof), _ptr(f), _ptr(m), _ptr(t), _ptr(r)))
+
+    def set_temperature_all(self, t: float):
+        self._chk(self.L.lib.vx_slabbed_set_temperature_all(self.h, t))
+
+    def set_temperature(self, t):
+        t = np.ascontiguousarray(t, dtype=np.float32)
+        self._chk(self.L.lib.vx_slabbed_set_temperature(self.h, len(t), _ptr(t)))
+
+    def step(self, dt: float, n: int = 1) -> Optional[int]:
+        div = C.c_int(-1)
+        rc = self._chk(self.L.lib.vx_slabbed_step(self.h, dt, n, C.byref(div)), ok=(VX_OK, VX_DIVERGED))
+        return div.value if rc == VX_DIVERGED else None
+
+    def recommended_dt(self) -> float:
+        dt = C.c_float()
+        self._chk(self.L.lib.vx_slabbed_recommended_dt(self.h, C.byref(dt)))
+        return dt.value
+
+    def reset(self):
+        self._chk(self.L.lib.vx_slabbed_reset(self.h))
+
+    def time(self) -> float:
+        return self.L.lib.vx_slabbed_time(self.h)
+
+    def download(self, name: str, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        fid, dt, comps, is_link = FIELDS[name]
+        total = self.n_links if is_link else self.n_voxels
+        if count is None:
+            count = total - first
+        out = np.zeros((count, comps), dtype=dt)
+        if count:
+            self._chk(self.L.lib.vx_slabbed_download(self.h, fid, first, count, _ptr(out)))
+        return out if comps > 1 else out.reshape(-1)
+
+    def upload(self, name: str, data, first: int = 0):
+        fid, dt, comps, _ = FIELDS[name]
+        a = np.ascontiguousarray(data, dtype=dt).reshape(-1, comps)
+        self._chk(self.L.lib.vx_slabbed_upload(self.h, fid, first, len(a), _ptr(a)))
+
+    def download_voxel_state(self, first: int = 0, count: int = 1) -> np.ndarray:
+        out = np.zeros(count, Sim.VOXEL_STATE_DTYPE)
+        self._chk(self.L.lib.vx_slabbed_download_voxel_state(self.h, first, count, out.ctypes.data))
+        return out
+
+    def download_link_state(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self.n_links - first if count is None else count
+        out = np.zeros(count, Sim.LINK_STATE_DTYPE)
+        self._chk(self.L.lib.vx_slabbed_download_link_state(self.h, first, count, out.ctypes.data))
+        return out
+
+    def upload_link_state(self, rec: np.ndarray, first: int = 0):
+        rec = np.ascontiguousarray(rec, dtype=Sim.LINK_STATE_DTYPE)
+        self._chk(self.L.lib.vx_slabbed_upload_link_state(self.h, first, len(rec), rec.ctypes.data))
+
+    def launch_count(self) -> int:
+        return self.L.lib.vx_slabbed_launch_count(self.h)
 
 
 _cache: dict = {}

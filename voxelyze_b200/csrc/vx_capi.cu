@@ -1083,6 +1083,7 @@ int vx_step_begin(vx_sim* s, float dt)
 int vx_step_enqueue(vx_sim* s, int part)
 {
     if (!s || !s->call_active || part < 0 || part > 2) return VX_ERR_ARG;
+    CK(cudaSetDevice(s->device));
     const int ngz = ((s->ghost_skip ? s->z_hi - s->z_lo : s->nz) + 2 * VX_WB_Z - 1) / (2 * VX_WB_Z);
     const bool split = !s->zb_layers.empty() && (int)s->zb_layers.size() < ngz;
     if (part == VX_PART_Z_INTERIOR) {
@@ -1113,6 +1114,7 @@ int vx_step_end(vx_sim* s, int* diverged_step)
 {
     if (!s || !s->call_active) return VX_ERR_ARG;
     if (s->call_half) return fail(s, VX_ERR_ARG, "vx_step_end: the last step lacks its interior part");
+    CK(cudaSetDevice(s->device));
     s->call_active = false;
     if (diverged_step) *diverged_step = -1;
     if (s->call_done == 0) return VX_OK;
@@ -1527,6 +1529,7 @@ int vx_set_externals(vx_sim* s, int n, const int32_t* voxel, const uint8_t* dof,
 {
     if (!s || n < 0 || (n && (!voxel || !dof))) return VX_ERR_ARG;
     for (int k = 0; k < n; k++) if (voxel[k] < 0 || voxel[k] >= s->N_user) return fail(s, VX_ERR_ARG, "external voxel index out of range");
+    CK(cudaSetDevice(s->device));
     if (voxel != s->ext_raw_vox.data()) {
         s->ext_raw_vox.assign(voxel, voxel + n); s->ext_raw_dof.assign(dof, dof + n);
         s->ext_raw_f.clear(); s->ext_raw_m.clear(); s->ext_raw_t.clear(); s->ext_raw_r.clear();
@@ -2155,3 +2158,6 @@ const char* vx_kernel_name(const vx_sim* s)
 #include "vx_linsolve.inl"
 
 } // extern "C"
+
+#include "vx_slabbed.hpp"      // vx_slabbed_*: one lattice on several devices of one process, composed from the entry points above
+

@@ -135,12 +135,11 @@ int vx_slab_exchange(vx_sim* s)
     return VX_OK;
 }
 
-int vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
+int vx_slab_step_begin(vx_sim* s, float dt, int n_steps)
 {
-    if (!s || n_steps < 0) return VX_ERR_ARG;
-    if (n_steps == 0) return VX_OK;
+    if (!s || n_steps < 1) return VX_ERR_ARG;
     int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
-    NvtxRange nvtx("vx_slab_step");
+    NvtxRange nvtx("vx_slab_step_begin");
     rc = vx_step_begin(s, dt); if (rc != VX_OK) return rc;
     auto abandon = [&](int code) { s->call_active = false; s->call_half = false; s->push_in_kernel = false; return code; };   // leave no call open behind an error
     for (int k = 0; k < n_steps; k++) {
@@ -155,11 +154,27 @@ int vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
         if (cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0) != cudaSuccess) return abandon(cuda_fail(s, cudaGetLastError(), "cudaStreamWaitEvent"));
         peer_push(s, s->newest_gen(), fused);
     }
-    CK(cudaEventRecord(s->ev_comm, s->comm_stream));
-    CK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
-    rc = vx_step_end(s, diverged_step);
+    if (cudaEventRecord(s->ev_comm, s->comm_stream) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->ev_comm, 0) != cudaSuccess)
+        return abandon(cuda_fail(s, cudaGetLastError(), "cudaEventRecord"));
+    return VX_OK;
+}
+
+int vx_slab_step_finish(vx_sim* s, int* diverged_step)
+{
+    if (!s || !s->call_active) return VX_ERR_ARG;
+    NvtxRange nvtx("vx_slab_step_finish");
+    CK(cudaSetDevice(s->device));
+    int rc = vx_step_end(s, diverged_step);
     if (rc != VX_OK && rc != VX_DIVERGED) return rc;
     int rc2 = peer_check(s);
     return rc2 != VX_OK ? rc2 : rc;
 }
 
+int vx_slab_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
+{
+    if (!s || n_steps < 0) return VX_ERR_ARG;
+    if (n_steps == 0) return VX_OK;
+    NvtxRange nvtx("vx_slab_step");
+    int rc = vx_slab_step_begin(s, dt, n_steps); if (rc != VX_OK) return rc;
+    return vx_slab_step_finish(s, diverged_step);
+}

@@ -144,6 +144,7 @@ int vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst)
 {
     if (!s || !dst || first < 0 || count < 0 || (long long)first + count > s->L) return VX_ERR_ARG;
     if (count == 0) return VX_OK;
+    CK(cudaSetDevice(s->device));
     std::vector<double> p2(3 * (size_t)count), a1(3 * (size_t)count), a2(3 * (size_t)count);
     std::vector<float> e(count), em(count), eo(count), sg(count); std::vector<uint32_t> fl(count);
     int rc = vx_download(s, VX_F_POS2, first, count, p2.data());

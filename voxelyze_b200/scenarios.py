@@ -57,6 +57,23 @@ def build(lib: VxLib, sc: Scenario, device: int = 0, path: int = 0) -> Sim:
     return s
 
 
+def build_slabbed(lib: VxLib, sc: Scenario, devices) -> "SlabbedSim":
+    """The same calls as build() on a vx_slabbed handle: the whole model in the caller's numbering, cut into z-slabs over
+    `devices` of this process (include/voxelyze_b200.h)."""
+    if sc.sim_id is not None or sc.collisions:
+        raise ValueError("vx_slabbed: one body, no self-collisions")
+    s = lib.create_slabbed(sc.voxel_size, devices)
+    s.set_materials(sc.materials)
+    s.set_gravity(sc.gravity)
+    s.enable_floor(sc.floor)
+    s.set_voxels(sc.ijk, sc.mat)
+    if len(sc.ext_voxel):
+        s.set_externals(sc.ext_voxel, sc.ext_dof, sc.ext_force, sc.ext_moment, sc.ext_translation, sc.ext_rotation)
+    if sc.temperature is not None:
+        s.set_temperature_all(sc.temperature)
+    return s
+
+
 def box_ijk(nx: int, ny: int, nz: int, origin=(0, 0, 0)) -> np.ndarray:
     """Lattice indices of a solid box in the insertion order k -> j -> i (x fastest)."""
     k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
