@@ -248,6 +248,10 @@ int  vx_recommended_dt(vx_sim* s, float* dt);
 int  vx_reset(vx_sim* s);
 /* simulated time (float accumulation like currentTime, Voxelyze.cpp:282)            */
 float vx_time(const vx_sim* s);
+/* sets CVoxelyze::currentTime and CVX_Voxel::previousDt (include/VX_Voxel.h:171; the same for every voxel): what a model
+ * that moves to another handle mid-run (other devices, other voxel size) takes along besides its voxel and link state,
+ * so that the next step damps with the dt of the step before it, as if nothing had happened.                          */
+int  vx_set_clock(vx_sim* s, float time, float previous_dt);
 
 /* ---- state access ---------------------------------------------------------- */
 /* Copies elements [first, first+count) of a field to/from host memory.  Element
@@ -460,6 +464,7 @@ int  vx_slabbed_step(vx_slabbed* m, float dt, int n_steps, int* diverged_step);
 int  vx_slabbed_recommended_dt(vx_slabbed* m, float* dt);
 int  vx_slabbed_reset(vx_slabbed* m);
 float vx_slabbed_time(const vx_slabbed* m);
+int  vx_slabbed_set_clock(vx_slabbed* m, float time, float previous_dt);
 int  vx_slabbed_download(vx_slabbed* m, int field, int first, int count, void* dst);
 int  vx_slabbed_upload(vx_slabbed* m, int field, int first, int count, const void* src);      /* voxel fields */
 int  vx_slabbed_download_voxel_state(vx_slabbed* m, int first, int count, vx_voxel_state* dst);

@@ -988,6 +988,7 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
 int vx_recommended_dt(vx_sim* s, float* dt) { if (!s || !dt) return VX_ERR_ARG; *dt = s->recommendedTimeStep(); return VX_OK; }
 int vx_reset(vx_sim* s) { if (!s) return VX_ERR_ARG; s->resetTime(); return VX_OK; }
 float vx_time(const vx_sim* s) { return s ? s->curTime : 0.f; }
+int vx_set_clock(vx_sim* s, float time, float previous_dt) { if (!s || !(time >= 0.f) || !(previous_dt >= 0.f)) return VX_ERR_ARG; s->curTime = time; s->prevDt = previous_dt; return VX_OK; }
 
 int vx_download(vx_sim* s, int field, int first, int count, void* dst)
 {

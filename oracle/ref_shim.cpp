@@ -314,6 +314,12 @@ int vx_recommended_dt(vx_sim* s, float* dt)
 }
 int vx_reset(vx_sim* s) { if (!s) return VX_ERR_ARG; for (auto& m : s->members) m.sim->resetTime(); return VX_OK; }
 float vx_time(const vx_sim* s) { return (s && !s->members.empty()) ? s->members[0].sim->currentTime : 0.f; }
+int vx_set_clock(vx_sim* s, float time, float previous_dt)
+{
+    if (!s || !(time >= 0.f) || !(previous_dt >= 0.f)) return VX_ERR_ARG;
+    for (auto& m : s->members) { m.sim->currentTime = time; for (int i = 0; i < m.sim->voxelCount(); i++) m.sim->voxel(i)->previousDt = previous_dt; }
+    return VX_OK;
+}
 
 static void put3(double* d, const Vec3D<double>& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
 static Vec3D<double> get3(const double* d) { return Vec3D<double>(d[0], d[1], d[2]); }

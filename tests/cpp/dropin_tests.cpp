@@ -807,6 +807,64 @@ static void stateCheckpoint()           // facade extra: saveState / loadState (
     C.setVoxel(C.addMaterial(), 0, 0, 0);
     CHECK(!C.loadState(path.c_str()));                      // another model: refused
 }
+static void slabbedModel(CVoxelyze& Vx)
+{
+    CVX_Material* soft = Vx.addMaterial(1e6f, 1e3f); soft->setGlobalDamping(0.01f); soft->setCte(0.01f); soft->setStaticFriction(1.0f); soft->setKineticFriction(0.5f);
+    CVX_Material* hard = Vx.addMaterial(4e6f, 2e3f); hard->setGlobalDamping(0.01f);
+    Vx.setGravity(1.0f); Vx.enableFloor(true);
+    for (int z = 0; z < 12; z++) for (int y = 0; y < 4; y++) for (int x = 0; x < 6; x++) Vx.setVoxel(((x + z) & 1) ? hard : soft, x, y, z);
+    for (int z = 4; z < 12; z++) for (int y = 0; y < 4; y++) Vx.voxel(0, y, z)->external()->setFixedAll();
+    for (int y = 0; y < 4; y++) Vx.voxel(5, y, 11)->external()->setForce(0.0f, 0.002f, -0.01f);
+}
+static void slabbedDevices()            // facade extra: setDevices -- the class API on several devices of one process (vx_slabbed_*), bits as on one
+{
+    CVoxelyze A(0.005), B(0.005);
+    slabbedModel(A); slabbedModel(B);
+    A.setDevice(0);                                                 // whatever VX_DEVICES says
+    B.setDevices(std::vector<int>(3, 0));                           // three slabs (on one GPU here; gpurun --gpus N: one each)
+    CHECK(B.isSlabbed() && !A.isSlabbed() && B.linkCount() == A.linkCount());
+    float dt = A.recommendedTimeStep();
+    CHECK(dt == B.recommendedTimeStep());
+    auto same = [&]() {
+        bool ok = true;
+        for (int i = 0; i < A.voxelCount(); i++) {
+            CVX_Voxel *a = A.voxel(i), *b = B.voxel(i);
+            ok = ok && a->position() == b->position() && a->orientation() == b->orientation() && a->velocity() == b->velocity() && a->angularVelocity() == b->angularVelocity()
+                    && a->temperature() == b->temperature() && a->isFloorStaticFriction() == b->isFloorStaticFriction();
+        }
+        for (int i = 0; i < A.linkCount(); i += 7) {
+            CVX_Link *a = A.link(i), *b = B.link(i);
+            ok = ok && a->axialStrain() == b->axialStrain() && a->force(true) == b->force(true) && a->moment(false) == b->moment(false) && a->isSmallAngle() == b->isSmallAngle();
+        }
+        return ok;
+    };
+    for (int i = 0; i < 150; i++) {
+        float t = 3.0f * sinf(i / 10.0f);
+        A.setAmbientTemperature(t); B.setAmbientTemperature(t);
+        CHECK(A.doTimeStep(dt) && B.doTimeStep(dt));
+    }
+    CHECK(same());
+    // per-voxel edits reach the owner and the ghost copies across the cuts (voxels of the planes next to a cut: z = 3, 4, 7, 8)
+    CVoxelyze* both[2] = {&A, &B};
+    for (CVoxelyze* V : both) {
+        V->voxel(3, 1, 3)->setTemperature(9.0f); V->voxel(2, 2, 4)->setTemperature(-4.0f); V->voxel(4, 0, 8)->haltMotion();
+        V->voxel(1, 1, 0)->enableFloor(false);
+        for (int i = 0; i < 60; i++) V->doTimeStep(dt);
+    }
+    CHECK(same());
+    // back to one device with the dynamic state; what a slabbed run cannot answer is available again
+    B.setDevices(std::vector<int>(1, 0));
+    CHECK(!B.isSlabbed());
+    CHECK(float_eq(A.stateInfo(CVoxelyze::DISPLACEMENT, CVoxelyze::MAX), B.stateInfo(CVoxelyze::DISPLACEMENT, CVoxelyze::MAX)));
+    for (int i = 0; i < 60; i++) { A.doTimeStep(dt); B.doTimeStep(dt); }
+    CHECK(same());
+    B.setDevices(std::vector<int>(2, 0));                           // and out again, mid-run
+    for (int i = 0; i < 60; i++) { A.doTimeStep(dt); B.doTimeStep(dt); }
+    CHECK(B.isSlabbed() && same());
+    B.resetTime(); A.resetTime();
+    for (int i = 0; i < 30; i++) { A.doTimeStep(dt); B.doTimeStep(dt); }
+    CHECK(same());
+}
 #endif
 
 // the deformed surface mesh of a stepped model written by CVX_MeshRender::saveObj (src/VX_MeshRender.cpp:238-251): the file of
@@ -864,7 +922,7 @@ int main(int argc, char** argv)
         {"poissonsMixed", poissonsMixed, true}, {"perVoxelFloorAndDampingMultiplier", perVoxelFloorAndDampingMultiplier, true},
 #ifndef DROPIN_REFERENCE
         {"stateCheckpoint", stateCheckpoint, true}, {"copyTakesTheModel", copyTakesTheModel, true},
-        {"linearSolveCantilever", linearSolveCantilever, true},
+        {"linearSolveCantilever", linearSolveCantilever, true}, {"slabbedDevices", slabbedDevices, true},
 #endif
     };
     bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";

@@ -42,7 +42,7 @@ def test_facade_host_only_classes(binaries):
 @pytest.mark.gpu
 def test_facade_passes_the_dropin_source_on_gpu(binaries):
     out = _run(binaries["b200"])
-    assert "0 failures" in out and "30 tests" in out
+    assert "0 failures" in out and "31 tests" in out
 
 
 def test_vxl_json_files_are_interchangeable(binaries, tmp_path):
@@ -187,3 +187,13 @@ def test_poissons_ratio_toggled_through_the_material_handle_mid_run(binaries):
     assert len(ref) == len(got) == 24
     scale = max(abs(c) for r in ref for c in r)
     assert max(abs(a - b) for r, g in zip(ref, got) for a, b in zip(r, g)) <= 1e-6 * scale
+
+
+@pytest.mark.gpu
+def test_unmodified_callers_reach_several_devices_through_vx_devices(binaries):
+    """VX_DEVICES makes every CVoxelyze of an unmodified caller run slabbed (three slabs on device 0 here) where the model can be
+    cut, and moves it to one device where a call needs that (collisions, Poisson materials, stateInfo, the mesh, the solve):
+    the whole drop-in source and the reference's own gtests pass unchanged."""
+    env = dict(os.environ, VX_DEVICES="0,0,0")
+    r = subprocess.run([binaries["b200"]], capture_output=True, text=True, timeout=1200, env=env)
+    assert r.returncode == 0 and "0 failures" in r.stdout and "31 tests" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]

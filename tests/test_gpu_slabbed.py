@@ -56,3 +56,24 @@ def test_slabbed_one_slab_per_device(product, n_dev):
     assert multi.step(dt, 37) is None and whole.step(dt, 37) is None
     for f in VOXEL_FIELDS:
         assert parity.bit_equal(multi.download(f), whole.download(f)), f
+
+
+def test_state_moves_between_handles_with_its_clock(product):
+    """What CVoxelyze::setDevices does mid-run: voxel fields, link records and vx_set_clock (time, CVX_Voxel::previousDt) into a
+    fresh handle -- one device to three slabs and back -- and the run goes on with the bits of the run that never moved."""
+    sc = _general_scenario()
+    a = scenarios.build(product, sc, path=7); dt = a.recommended_dt()
+    assert a.step(dt, 80) is None
+    b = scenarios.build_slabbed(product, sc, [0, 0, 0])
+    c = scenarios.build(product, sc, path=7)
+    src = a
+    for dst in (b, c):
+        for f in ("pos", "orient", "linmom", "angmom", "temp", "voxflags"):
+            dst.upload(f, src.download(f))
+        dst.upload_link_state(src.download_link_state())
+        dst.set_clock(src.time(), dt)
+        assert dst.time() == src.time()
+        assert a.step(dt, 40) is None and dst.step(dt, 40) is None
+        for f in VOXEL_FIELDS:
+            assert parity.bit_equal(dst.download(f), a.download(f)), (f, type(dst).__name__)
+        src = dst

@@ -100,6 +100,8 @@ def check_state_edits(lib, devices):
     for f in VOXEL_FIELDS + LINK_FIELDS:
         assert parity.bit_equal(multi.download(f), whole.download(f)), f
     for s in (whole, multi):
+        s.set_clock(0.25, dt)                                 # what a model that moves between handles takes along
+        assert s.time() == 0.25 and s.step(dt, 3) is None
         s.reset()
         assert s.time() == 0.0
         assert s.step(dt, 10) is None

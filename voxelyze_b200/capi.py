@@ -150,6 +150,7 @@ class VxLib:
             "vx_recommended_dt": (i32, [vp, P(f32)]),
             "vx_reset": (i32, [vp]),
             "vx_time": (f32, [vp]),
+            "vx_set_clock": (i32, [vp, f32, f32]),
             "vx_download": (i32, [vp, i32, i32, i32, vp]),
             "vx_upload": (i32, [vp, i32, i32, i32, vp]),
             "vx_download_voxel_state": (i32, [vp, i32, i32, vp]),
@@ -209,6 +210,7 @@ class VxLib:
             "vx_slabbed_recommended_dt": (i32, [vp, P(f32)]),
             "vx_slabbed_reset": (i32, [vp]),
             "vx_slabbed_time": (f32, [vp]),
+            "vx_slabbed_set_clock": (i32, [vp, f32, f32]),
             "vx_slabbed_download": (i32, [vp, i32, i32, i32, vp]),
             "vx_slabbed_upload": (i32, [vp, i32, i32, i32, vp]),
             "vx_slabbed_download_voxel_state": (i32, [vp, i32, i32, vp]),
@@ -359,6 +361,9 @@ class Sim:
 
     def time(self) -> float:
         return self.L.lib.vx_time(self.h)
+
+    def set_clock(self, time: float, previous_dt: float):
+        self._chk(self.L.lib.vx_set_clock(self.h, time, previous_dt))
 
     # -- state -----------------------------------------------------------------
     def download(self, name: str, first: int = 0, count: Optional[int] = None) -> np.ndarray:
@@ -653,6 +658,9 @@ class SlabbedSim:
 
     def time(self) -> float:
         return self.L.lib.vx_slabbed_time(self.h)
+
+    def set_clock(self, time: float, previous_dt: float):
+        self._chk(self.L.lib.vx_slabbed_set_clock(self.h, time, previous_dt))
 
     def download(self, name: str, first: int = 0, count: Optional[int] = None) -> np.ndarray:
         fid, dt, comps, is_link = FIELDS[name]

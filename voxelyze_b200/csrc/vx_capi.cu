@@ -1815,6 +1815,17 @@ int vx_reset(vx_sim* s)
     return upload_initial_state(s, 0.0f);          // CVX_Voxel::reset zeroes the temperature, src/VX_Voxel.cpp:53
 }
 float vx_time(const vx_sim* s) { return s ? s->time_host : 0.f; }
+int vx_set_clock(vx_sim* s, float time, float previous_dt)
+{
+    if (!s || !(time >= 0.f) || !(previous_dt >= 0.f)) return VX_ERR_ARG;
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_clock inside vx_step_begin .. vx_step_end");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy(&s->params.p->time, &time, sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&s->params.p->prev_dt, &previous_dt, sizeof(float), cudaMemcpyHostToDevice));
+    s->time_host = time; s->prev_dt_host = previous_dt; s->last_prev_dt = previous_dt;
+    return VX_OK;
+}
 
 static bool field_info(int field, int& what, int& comps, int& esize, bool& is_link)
 {

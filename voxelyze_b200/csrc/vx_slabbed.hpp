@@ -415,6 +415,13 @@ int vx_slabbed_reset(vx_slabbed* m)
 
 float vx_slabbed_time(const vx_slabbed* m) { return m && m->active ? vx_time(m->slab[0]) : 0.f; }
 
+int vx_slabbed_set_clock(vx_slabbed* m, float time, float previous_dt)
+{
+    if (!m) return VX_ERR_ARG;
+    for (int k = 0; k < m->active; k++) { int rc = vx_set_clock(m->slab[k], time, previous_dt); if (rc != VX_OK) return vxs::fail_from(m, k, rc, "vx_set_clock"); }
+    return VX_OK;
+}
+
 int vx_slabbed_download(vx_slabbed* m, int field, int first, int count, void* dst)
 {
     const size_t eb = vxs::field_bytes(field);

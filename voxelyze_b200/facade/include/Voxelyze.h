@@ -33,6 +33,7 @@
 #define DEFAULT_VOXEL_SIZE 0.001
 
 struct vx_sim;
+struct vx_slabbed;
 
 class CVoxelyze {
 public:
@@ -100,14 +101,25 @@ public:
     bool saveState(const char* path);
     bool loadState(const char* path);
     // device ordinal before the first step; the raw C-ABI handle
-    void setDevice(int cudaDevice) { device = cudaDevice; }
-    vx_sim* handle() const { sync(); return h; }
+    void setDevice(int cudaDevice) { setDevices(std::vector<int>(1, cudaDevice)); }
+    // several GPUs of this process: the lattice is cut into z-slabs, one per listed device (vx_slabbed_*, include/voxelyze_b200.h),
+    // doTimeStep and the voxel / link accessors work in the numbering of the whole model, bits as on one device.  May be called
+    // at any time: dynamic state moves with the model.  Not available while slabbed (the call aborts with a message; setDevices
+    // with one device first): self-collisions, Poisson materials, stateInfo, the mesh, the static solve, state files, handle().
+    // The environment variable VX_DEVICES ("0,1,2,3") sets the initial list, so that an unmodified caller of the class API
+    // reaches every GPU; a list that came from there is a wish: a model or a call that cannot run slabbed moves the model to
+    // the first listed device instead of aborting.
+    void setDevices(const std::vector<int>& cudaDevices);
+    int deviceCount() const { return (int)devices.size(); }
+    bool isSlabbed() const { sync(); return hm != nullptr; }
+    vx_sim* handle() const { sync(); if (hm) notSlabbed("handle()"); return h; }
 
 private:
     double voxSize;
     float ambientTemp = 0.0f, grav = 0.0f;
     bool floor = false, collisions = false;
     int device = 0;
+    mutable std::vector<int> devices;       // more than one entry: slabbed over these devices
 
     std::vector<CVX_MaterialVoxel*> voxelMats;
     std::vector<CVX_Voxel*> voxelsList;
@@ -115,6 +127,11 @@ private:
 
     // ---- device side, maintained lazily (logically const: accessors may have to upload first)
     mutable vx_sim* h = nullptr;
+    mutable vx_slabbed* hm = nullptr;       // instead of h when the model runs on several devices
+    void destroyHandle() const;
+    mutable bool devicesFromEnv = false, syncing = false, clockPending = false;
+    mutable float clockTime = 0.0f;
+    void notSlabbed(const char* what) const;
     mutable bool topologyDirty = true, envDirty = true, tempAllDirty = false;
     mutable uint64_t matChangesSeen = ~0ull, extChanges = 0, extChangesSeen = ~0ull;
     mutable std::vector<CVX_Link*> linksList;
@@ -156,6 +173,7 @@ private:
     friend class CVX_Voxel;
     friend class CVX_Link;
     friend class CVX_LinearSolver;
+    friend struct LinkRead;
 };
 
 #endif // VXB200_VOXELYZE_H

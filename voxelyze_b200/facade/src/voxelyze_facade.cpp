@@ -14,6 +14,10 @@
 #include <cstdlib>
 #include <cstring>
 
+// the same call on the single-device handle or on the slabbed one (include/voxelyze_b200.h: vx_slabbed_* mirror their namesakes)
+#define VXH(sim, fn, ...) ((sim)->hm ? vx_slabbed_##fn((sim)->hm, __VA_ARGS__) : vx_##fn((sim)->h, __VA_ARGS__))
+#define VXH0(sim, fn) ((sim)->hm ? vx_slabbed_##fn((sim)->hm) : vx_##fn((sim)->h))
+
 float CVX_Collision::envelopeRadius = 0.625f;
 
 // ================================================================================================ CVX_Material
@@ -224,7 +228,7 @@ void CVX_Voxel::setTemperature(float t)
 {
     if (!sim) { temp0 = t; return; }
     sim->sync();
-    vx_upload(sim->h, VX_F_TEMP, index, 1, &t);
+    VXH(sim, upload, VX_F_TEMP, index, 1, &t);
     sim->epoch++;
 }
 void CVX_Voxel::haltMotion()
@@ -232,8 +236,8 @@ void CVX_Voxel::haltMotion()
     if (!sim) return;
     sim->sync();
     const double zero[3] = {0, 0, 0};
-    vx_upload(sim->h, VX_F_LINMOM, index, 1, zero);
-    vx_upload(sim->h, VX_F_ANGMOM, index, 1, zero);
+    VXH(sim, upload, VX_F_LINMOM, index, 1, zero);
+    VXH(sim, upload, VX_F_ANGMOM, index, 1, zero);
     sim->epoch++;
 }
 // ---- derived quantities, computed on the host from the mirrored state exactly as the reference does
@@ -357,29 +361,25 @@ bool CVX_Voxel::isYielded() const { for (int i = 0; i < 6; i++) if (links[i] && 
 bool CVX_Voxel::isFailed() const { for (int i = 0; i < 6; i++) if (links[i] && links[i]->isFailed()) return true; return false; }
 
 // ================================================================================================ CVX_Link
-static Vec3D<> link_vec(const CVoxelyze* sim, vx_sim* h, int field, int index)
-{
-    (void)sim;
-    double v[3] = {0, 0, 0};
-    vx_download(h, field, index, 1, v);
-    return Vec3D<>(v[0], v[1], v[2]);
-}
-static float link_f32(vx_sim* h, int field, int index) { float v = 0; vx_download(h, field, index, 1, &v); return v; }
-static uint32_t link_flags(vx_sim* h, int index) { uint32_t v = 0; vx_download(h, VX_F_LINKFLAGS, index, 1, &v); return v; }
+struct LinkRead {         // single link fields, from the device that owns the link
+    static Vec3D<> vec(const CVoxelyze* sim, int field, int index) { double v[3] = {0, 0, 0}; VXH(sim, download, field, index, 1, v); return Vec3D<>(v[0], v[1], v[2]); }
+    static float f32(const CVoxelyze* sim, int field, int index) { float v = 0; VXH(sim, download, field, index, 1, &v); return v; }
+    static uint32_t flags(const CVoxelyze* sim, int index) { uint32_t v = 0; VXH(sim, download, VX_F_LINKFLAGS, index, 1, &v); return v; }
+};
 
-Vec3D<> CVX_Link::force(bool positiveEnd) const { sim->sync(); return link_vec(sim, sim->h, positiveEnd ? VX_F_FORCE_POS : VX_F_FORCE_NEG, index); }
-Vec3D<> CVX_Link::moment(bool positiveEnd) const { sim->sync(); return link_vec(sim, sim->h, positiveEnd ? VX_F_MOMENT_POS : VX_F_MOMENT_NEG, index); }
-float CVX_Link::axialStrain() const { sim->sync(); return link_f32(sim->h, VX_F_STRAIN, index); }
+Vec3D<> CVX_Link::force(bool positiveEnd) const { sim->sync(); return LinkRead::vec(sim, positiveEnd ? VX_F_FORCE_POS : VX_F_FORCE_NEG, index); }
+Vec3D<> CVX_Link::moment(bool positiveEnd) const { sim->sync(); return LinkRead::vec(sim, positiveEnd ? VX_F_MOMENT_POS : VX_F_MOMENT_NEG, index); }
+float CVX_Link::axialStrain() const { sim->sync(); return LinkRead::f32(sim, VX_F_STRAIN, index); }
 float CVX_Link::axialStrain(bool positiveEnd) const
 {
     float strain = axialStrain();
     float ratio = pVPos->material()->youngsModulus() / pVNeg->material()->youngsModulus();      // strainRatio, src/VX_Link.cpp:67
     return positiveEnd ? 2.0f * strain * ratio / (1.0f + ratio) : 2.0f * strain / (1.0f + ratio);
 }
-float CVX_Link::axialStress() const { sim->sync(); return link_f32(sim->h, VX_F_STRESS, index); }
-bool CVX_Link::isSmallAngle() const { sim->sync(); return (link_flags(sim->h, index) & VX_LF_SMALL_ANGLE) != 0; }
-bool CVX_Link::isYielded() const { sim->sync(); return (link_flags(sim->h, index) & VX_LF_YIELDED) != 0; }
-bool CVX_Link::isFailed() const { sim->sync(); return (link_flags(sim->h, index) & VX_LF_FAILED) != 0; }
+float CVX_Link::axialStress() const { sim->sync(); return LinkRead::f32(sim, VX_F_STRESS, index); }
+bool CVX_Link::isSmallAngle() const { sim->sync(); return (LinkRead::flags(sim, index) & VX_LF_SMALL_ANGLE) != 0; }
+bool CVX_Link::isYielded() const { sim->sync(); return (LinkRead::flags(sim, index) & VX_LF_YIELDED) != 0; }
+bool CVX_Link::isFailed() const { sim->sync(); return (LinkRead::flags(sim, index) & VX_LF_FAILED) != 0; }
 float CVX_Link::strainEnergy() const                                                              // src/VX_Link.cpp:251-257
 {
     Vec3D<> fN = force(false), mN = moment(false), mP = moment(true);
@@ -390,8 +390,15 @@ float CVX_Link::strainEnergy() const                                            
 float CVX_Link::axialStiffness() { return mat->a1(); }      // nu = 0 value (src/VX_Link.cpp:260)
 
 // ================================================================================================ CVoxelyze
-CVoxelyze::CVoxelyze(double voxelSize) : voxSize(voxelSize) {}
-CVoxelyze::~CVoxelyze() { clear(); if (h) vx_destroy(h); }
+CVoxelyze::CVoxelyze(double voxelSize) : voxSize(voxelSize)
+{
+    if (const char* e = getenv("VX_DEVICES")) {               // "0,1,2,3": an unmodified caller of the class API runs slabbed over these
+        std::vector<int> d;
+        for (const char* q = e; *q;) { char* end = nullptr; long v = strtol(q, &end, 10); if (end == q) break; d.push_back((int)v); q = *end == ',' ? end + 1 : end; }
+        if (!d.empty()) { devices = d; device = d[0]; devicesFromEnv = d.size() > 1; }
+    }
+}
+CVoxelyze::~CVoxelyze() { clear(); destroyHandle(); }
 
 CVoxelyze& CVoxelyze::operator=(CVoxelyze& VIn)             // src/Voxelyze.cpp:39-58
 {
@@ -413,13 +420,13 @@ CVoxelyze& CVoxelyze::operator=(CVoxelyze& VIn)             // src/Voxelyze.cpp:
 void CVoxelyze::setVoxelSize(double voxelSize)
 {
     const double scale = voxelSize / voxSize;
-    const bool had = stepped && h && !voxelsList.empty();
-    if (had) fetchAll();
+    const bool had = stepped && (h || hm) && !voxelsList.empty();
+    if (had) { fetchAll(); clockTime = VXH0(this, time); clockPending = true; }
     voxSize = voxelSize;
     for (CVX_MaterialVoxel* m : voxelMats) m->setNominalSize(voxelSize);
     for (CVX_MaterialLink* m : linkMats) delete m;            // combined materials depend on the size: rebuilt on demand
     linkMats.clear();
-    if (h) { vx_destroy(h); h = nullptr; }                    // the voxel size is a property of the device handle
+    destroyHandle();                                          // the voxel size is a property of the device handle
     topologyDirty = envDirty = true; matChangesSeen = ~0ull; extChangesSeen = ~0ull;
     linkStateFetched = false; linkStateMirror.clear(); editedVoxels.clear();        // links restart (CVX_Link::reset)
     if (had) {
@@ -432,7 +439,7 @@ void CVoxelyze::setVoxelSize(double voxelSize)
 
 void CVoxelyze::die(const char* what) const
 {
-    fprintf(stderr, "voxelyze_b200: %s: %s\n", what, h ? vx_last_error(h) : "no CUDA device handle (this build has no CPU fallback)");
+    fprintf(stderr, "voxelyze_b200: %s: %s\n", what, hm ? vx_slabbed_last_error(hm) : h ? vx_last_error(h) : "no CUDA device handle (this build has no CPU fallback)");
     abort();
 }
 
@@ -449,8 +456,8 @@ void CVoxelyze::clear()
     for (CVX_Collision* c : collisionsList) delete c;
     collisionsList.clear();
     ambientTemp = 0.0f; grav = 0.0f; floor = false; collisions = false;
-    topologyDirty = envDirty = true; stepped = false; epoch++;
-    if (h) { vx_destroy(h); h = nullptr; }
+    topologyDirty = envDirty = true; stepped = false; clockPending = false; epoch++;
+    destroyHandle();
 }
 
 CVX_Material* CVoxelyze::addMaterial(float E, float rho)
@@ -560,6 +567,36 @@ CVX_MaterialLink* CVoxelyze::combinedMaterial(CVX_MaterialVoxel* a, CVX_Material
     return m;
 }
 
+// ---- devices ---------------------------------------------------------------------------------------
+void CVoxelyze::destroyHandle() const
+{
+    if (h) { vx_destroy(h); h = nullptr; }
+    if (hm) { vx_slabbed_destroy(hm); hm = nullptr; }
+}
+void CVoxelyze::notSlabbed(const char* what) const
+{
+    if (devicesFromEnv && !syncing) {                 // the device list came from VX_DEVICES, not from the caller: move the model to one device and carry on
+        const_cast<CVoxelyze*>(this)->setDevices(std::vector<int>(1, devices[0]));
+        sync();
+        return;
+    }
+    fprintf(stderr, "voxelyze_b200: %s is not available while the model is cut into slabs over %d devices; call setDevices() with one device first\n", what, (int)devices.size());
+    abort();
+}
+// the model moves to another set of devices with its dynamic state: voxel mirrors and link records are fetched from the old
+// handle(s) and uploaded by the rebuild, like after a topology edit
+void CVoxelyze::setDevices(const std::vector<int>& cudaDevices)
+{
+    if (cudaDevices.empty() || cudaDevices == devices) return;
+    const bool had = stepped && (h || hm) && !voxelsList.empty() && !topologyDirty;
+    if (had) { sync(); fetchAll(); fetchLinkState(); clockTime = VXH0(this, time); clockPending = true; }
+    destroyHandle();
+    devices = cudaDevices; device = devices[0]; devicesFromEnv = false;
+    topologyDirty = envDirty = true; matChangesSeen = ~0ull; extChangesSeen = ~0ull; envelopeSeen = 0.0f;
+    if (ambientTemp != 0.0f && !had) tempAllDirty = true;
+    epoch++;
+}
+
 // ---- device synchronisation -------------------------------------------------------------------
 void CVoxelyze::uploadMaterials() const
 {
@@ -576,7 +613,7 @@ void CVoxelyze::uploadMaterials() const
         o.zeta_internal = m.zeta_int; o.zeta_global = m.zeta_glob; o.zeta_collision = m.zeta_coll;
         for (int a = 0; a < 3; a++) o.ext_scale[a] = m.ext_scale[a];
     }
-    if (vx_set_materials(h, (int)d.size(), d.data()) != VX_OK) die("vx_set_materials");
+    if (VXH(this, set_materials, (int)d.size(), d.data()) != VX_OK) die("vx_set_materials");
     for (CVX_MaterialLink* lm : linkMats) lm->updateAll();
 }
 
@@ -591,16 +628,16 @@ void CVoxelyze::uploadExternals() const
         f.insert(f.end(), {ef.x, ef.y, ef.z}); m.insert(m.end(), {em.x, em.y, em.z});
         t.insert(t.end(), {et.x, et.y, et.z}); r.insert(r.end(), {er.x, er.y, er.z});
     }
-    if (vx_set_externals(h, (int)vox.size(), vox.data(), dof.data(), f.data(), m.data(), t.data(), r.data()) != VX_OK) die("vx_set_externals");
+    if (VXH(this, set_externals, (int)vox.size(), vox.data(), dof.data(), f.data(), m.data(), t.data(), r.data()) != VX_OK) die("vx_set_externals");
 }
 
 // state of every link of the model the device currently holds, fetched once before the first edit of a batch
 void CVoxelyze::fetchLinkState() const
 {
-    if (!stepped || linkStateFetched || !h || topologyDirty) return;
-    const int L = vx_link_count(h);
+    if (!stepped || linkStateFetched || (!h && !hm) || topologyDirty) return;
+    const int L = VXH0(this, link_count);
     linkStateMirror.resize((size_t)L * sizeof(vx_link_state));
-    if (L && vx_download_link_state(h, 0, L, (vx_link_state*)linkStateMirror.data()) != VX_OK) die("vx_download_link_state");
+    if (L && VXH(this, download_link_state, 0, L, (vx_link_state*)linkStateMirror.data()) != VX_OK) die("vx_download_link_state");
     linkStateFetched = true;
 }
 
@@ -614,14 +651,27 @@ void CVoxelyze::rebuildTopology() const
         mat[i] = (uint16_t)(std::find(voxelMats.begin(), voxelMats.end(), v->mat) - voxelMats.begin());
     }
     const bool keepState = stepped;                 // mirrors were made current by setVoxel/removeVoxel before the edit
-    if (vx_enable_collisions(h, 0) != VX_OK) die("vx_enable_collisions");
-    if (collisions && vx_enable_collisions(h, 1) != VX_OK) die("vx_enable_collisions");
-    if (vx_set_voxels(h, n, ijk.data(), mat.data(), nullptr, nullptr) != VX_OK) die("vx_set_voxels");
+    if (hm) {
+        if (collisions) notSlabbed("enableCollisions");
+        const int rc = vx_slabbed_set_voxels(hm, n, ijk.data(), mat.data());
+        if (rc == VX_ERR_UNSUPPORTED && devicesFromEnv) {             // a model that cannot be cut (Poisson materials, too sparse): one device after all
+            destroyHandle();
+            devices.resize(1);
+            if (vx_create(voxSize, devices[0], &h) != VX_OK) die("vx_create");
+            if (vx_set_gravity(h, grav) != VX_OK || vx_enable_floor(h, floor) != VX_OK) die("environment");
+            uploadMaterials();
+        } else if (rc != VX_OK) die("vx_slabbed_set_voxels");
+    }
+    if (h) {
+        if (vx_enable_collisions(h, 0) != VX_OK) die("vx_enable_collisions");
+        if (collisions && vx_enable_collisions(h, 1) != VX_OK) die("vx_enable_collisions");
+        if (vx_set_voxels(h, n, ijk.data(), mat.data(), nullptr, nullptr) != VX_OK) die("vx_set_voxels");
+    }
 
     // link handles in C-ABI link order; surviving links keep their handle
-    const int L = vx_link_count(h);
+    const int L = VXH0(this, link_count);
     std::vector<int32_t> vn(L), vp(L); std::vector<uint8_t> ax(L);
-    vx_get_links(h, vn.data(), vp.data(), ax.data());
+    VXH(this, get_links, vn.data(), vp.data(), ax.data());
     std::map<std::pair<CVX_Voxel*, int>, CVX_Link*> pool;
     // links that survive the edit keep their state; the links of a voxel whose material was swapped restart, like
     // every new link (the reference destroys and recreates exactly those, src/Voxelyze.cpp:485-498)
@@ -666,12 +716,12 @@ void CVoxelyze::rebuildTopology() const
         int old = (int)mTemp.size();                 // voxels [0, old) existed before; the rest are new and start fresh
         if (old > n) old = n;
         if (old) {
-            vx_upload(h, VX_F_POS, 0, old, mPos.data()); vx_upload(h, VX_F_ORIENT, 0, old, mOrient.data());
-            vx_upload(h, VX_F_LINMOM, 0, old, mLin.data()); vx_upload(h, VX_F_ANGMOM, 0, old, mAng.data());
-            vx_upload(h, VX_F_TEMP, 0, old, mTemp.data()); vx_upload(h, VX_F_VOXFLAGS, 0, old, mFlags.data());
+            VXH(this, upload, VX_F_POS, 0, old, mPos.data()); VXH(this, upload, VX_F_ORIENT, 0, old, mOrient.data());
+            VXH(this, upload, VX_F_LINMOM, 0, old, mLin.data()); VXH(this, upload, VX_F_ANGMOM, 0, old, mAng.data());
+            VXH(this, upload, VX_F_TEMP, 0, old, mTemp.data()); VXH(this, upload, VX_F_VOXFLAGS, 0, old, mFlags.data());
         }
     }
-    if (!carried.empty() && vx_upload_link_state(h, 0, L, carried.data()) != VX_OK) die("vx_upload_link_state");
+    if (!carried.empty() && VXH(this, upload_link_state, 0, L, carried.data()) != VX_OK) die("vx_upload_link_state");
     removedIndices.clear(); pendingStateEdit.clear(); editedVoxels.clear();
     linkStateMirror.clear(); linkStateFetched = false;
     mirrorEpoch.assign(n, 0);
@@ -684,24 +734,36 @@ void CVoxelyze::rebuildTopology() const
 
 void CVoxelyze::sync() const
 {
-    if (!h) {
-        if (vx_create(voxSize, device, &h) != VX_OK) die("vx_create");
+    struct Busy { bool& b; bool was; Busy(bool& x) : b(x), was(x) { b = true; } ~Busy() { b = was; } } busy(syncing);
+    if (!h && !hm) {
+        if (devices.size() > 1 && devicesFromEnv) {                                          // VX_DEVICES is a wish, setDevices an order
+            bool cut = !collisions && !voxelsList.empty() && bound(2, true) - bound(2, false) + 1 >= 4;      // at least two planes per slab
+            for (CVX_MaterialVoxel* m : voxelMats) cut = cut && m->poissonsRatio() == 0.0f;
+            if (!cut) devices.resize(1);
+        }
+        if (devices.size() > 1) { if (vx_slabbed_create(voxSize, (int)devices.size(), devices.data(), &hm) != VX_OK) die("vx_slabbed_create"); }
+        else if (vx_create(voxSize, devices.empty() ? device : devices[0], &h) != VX_OK) die("vx_create");
         topologyDirty = envDirty = true; matChangesSeen = ~0ull;
     }
     uint64_t matChanges = voxelMats.size();
     for (CVX_MaterialVoxel* m : voxelMats) matChanges += m->changeCount() * 1315423911ull;
-    if (CVX_Collision::envelopeRadius != envelopeSeen) { vx_set_collision_envelope(h, CVX_Collision::envelopeRadius); envelopeSeen = CVX_Collision::envelopeRadius; }
+    if (h && CVX_Collision::envelopeRadius != envelopeSeen) { vx_set_collision_envelope(h, CVX_Collision::envelopeRadius); envelopeSeen = CVX_Collision::envelopeRadius; }
     if (envDirty) {
-        if (vx_set_gravity(h, grav) != VX_OK || vx_enable_floor(h, floor) != VX_OK) die("environment");
+        if (VXH(this, set_gravity, grav) != VX_OK || VXH(this, enable_floor, floor) != VX_OK) die("environment");
     }
     if (matChanges != matChangesSeen || topologyDirty) { uploadMaterials(); matChangesSeen = matChanges; epoch++; }
     if (topologyDirty) { rebuildTopology(); topologyDirty = false; }
+    if (clockPending) {                               // the model came from another handle mid-run: time and CVX_Voxel::previousDt go on
+        if (stepped && VXH(this, set_clock, clockTime, previousDt) != VX_OK) die("vx_set_clock");
+        clockPending = false;
+    }
     if (envDirty) {
-        if (vx_enable_collisions(h, collisions) != VX_OK) die("vx_enable_collisions");
+        if (hm && collisions) notSlabbed("enableCollisions");
+        if (h && vx_enable_collisions(h, collisions) != VX_OK) die("vx_enable_collisions");
         envDirty = false;
     }
     if (extChanges != extChangesSeen) { uploadExternals(); extChangesSeen = extChanges; epoch++; }
-    if (tempAllDirty) { vx_set_temperature_all(h, ambientTemp); tempAllDirty = false; epoch++; }
+    if (tempAllDirty) { VXH(this, set_temperature_all, ambientTemp); tempAllDirty = false; epoch++; }
     if (!floorEdits.empty()) applyFloorEdits();
 }
 
@@ -713,23 +775,23 @@ void CVoxelyze::applyFloorEdits() const
     for (CVX_Voxel* v : edits) {
         if (v->index < 0 || v->index >= (int)voxelsList.size() || voxelsList[v->index] != v) continue;
         uint32_t fl = 0;
-        if (vx_download(h, VX_F_VOXFLAGS, v->index, 1, &fl) != VX_OK) die("vx_download");
+        if (VXH(this, download, VX_F_VOXFLAGS, v->index, 1, &fl) != VX_OK) die("vx_download");
         fl &= ~(VX_VF_FLOOR_OFF | VX_VF_FLOOR_ON);
         if (v->floorOverride == 0 && floor) fl |= VX_VF_FLOOR_OFF;
         if (v->floorOverride == 1 && !floor) fl |= VX_VF_FLOOR_ON;
-        if (vx_upload(h, VX_F_VOXFLAGS, v->index, 1, &fl) != VX_OK) die("vx_upload");
+        if (VXH(this, upload, VX_F_VOXFLAGS, v->index, 1, &fl) != VX_OK) die("vx_upload");
     }
     epoch++;
 }
 
 void CVoxelyze::fetchAll() const
 {
-    if (!h || voxelsList.empty() || topologyDirty) return;
+    if ((!h && !hm) || voxelsList.empty() || topologyDirty) return;
     const int n = (int)mTemp.size();
     if (n == 0) return;
-    vx_download(h, VX_F_POS, 0, n, mPos.data()); vx_download(h, VX_F_ORIENT, 0, n, mOrient.data());
-    vx_download(h, VX_F_LINMOM, 0, n, mLin.data()); vx_download(h, VX_F_ANGMOM, 0, n, mAng.data());
-    vx_download(h, VX_F_TEMP, 0, n, mTemp.data()); vx_download(h, VX_F_VOXFLAGS, 0, n, mFlags.data());
+    VXH(this, download, VX_F_POS, 0, n, mPos.data()); VXH(this, download, VX_F_ORIENT, 0, n, mOrient.data());
+    VXH(this, download, VX_F_LINMOM, 0, n, mLin.data()); VXH(this, download, VX_F_ANGMOM, 0, n, mAng.data());
+    VXH(this, download, VX_F_TEMP, 0, n, mTemp.data()); VXH(this, download, VX_F_VOXFLAGS, 0, n, mFlags.data());
     std::fill(mirrorEpoch.begin(), mirrorEpoch.end(), epoch);
     singleFetches = 0;
 }
@@ -742,7 +804,7 @@ void CVoxelyze::fetchVoxel(int i) const
     // whole list gets one bulk download
     if (++singleFetches > 32) { fetchAll(); return; }
     vx_voxel_state r;                                   // one call, one tiny kernel writing into mapped pinned memory
-    if (vx_download_voxel_state(h, i, 1, &r) != VX_OK) die("vx_download_voxel_state");
+    if (VXH(this, download_voxel_state, i, 1, &r) != VX_OK) die("vx_download_voxel_state");
     for (int k = 0; k < 3; k++) { mPos[3 * i + k] = r.pos[k]; mLin[3 * i + k] = r.linmom[k]; mAng[3 * i + k] = r.angmom[k]; }
     for (int k = 0; k < 4; k++) mOrient[4 * i + k] = r.orient[k];
     mTemp[i] = r.temp; mFlags[i] = r.flags;
@@ -755,11 +817,11 @@ bool CVoxelyze::doTimeStep(float dt)
     if (dt == 0) return true;
     sync();
     if (voxelsList.empty()) return true;
-    const float timeBefore = vx_time(h);
-    int rc = vx_step(h, dt, 1, nullptr);
+    const float timeBefore = VXH0(this, time);
+    int rc = VXH(this, step, dt, 1, nullptr);
     if (rc != VX_OK && rc != VX_DIVERGED) die("vx_step");
     stepped = true; epoch++; singleFetches = 0;
-    if (rc == VX_OK) previousDt = dt > 0 ? dt : vx_time(h) - timeBefore;
+    if (rc == VX_OK) previousDt = dt > 0 ? dt : VXH0(this, time) - timeBefore;
     return rc == VX_OK;
 }
 
@@ -767,6 +829,7 @@ bool CVoxelyze::doTimeStep(float dt)
 bool CVoxelyze::staticSolve(double relTol, int maxIter, int* iterations, double* residual, std::string* error)
 {
     sync();
+    if (hm) notSlabbed("doLinearSolve");
     int rc = vx_linear_solve(h, relTol, maxIter, iterations, residual);
     if (rc == VX_OK) { stepped = true; epoch++; singleFetches = 0; return true; }
     if (error) *error = vx_last_error(h);
@@ -779,14 +842,14 @@ float CVoxelyze::recommendedTimeStep() const
 {
     sync();
     float dt = 0.0f;
-    if (vx_recommended_dt(h, &dt) != VX_OK) die("vx_recommended_dt");
+    if (VXH(this, recommended_dt, &dt) != VX_OK) die("vx_recommended_dt");
     return dt;
 }
 
 void CVoxelyze::resetTime()
 {
     sync();
-    if (vx_reset(h) != VX_OK) die("vx_reset");
+    if (VXH0(this, reset) != VX_OK) die("vx_reset");
     stepped = false; epoch++; previousDt = 0.0f;
     for (CVX_Voxel* v : voxelsList) if (v->floorOverride >= 0) floorEdits.push_back(v);      // vx_reset keeps no per-voxel flag
 }
@@ -798,7 +861,7 @@ void CVoxelyze::enableFloor(bool e)         // src/Voxelyze.cpp:604-610: every v
     floor = e; envDirty = true;
     for (CVX_Voxel* v : voxelsList) if (v->floorOverride >= 0) { v->floorOverride = -1; floorEdits.push_back(v); }
 }
-void CVoxelyze::enableCollisions(bool e) { if (collisions == e) return; collisions = e; envDirty = true; if (!stepped) topologyDirty = true; }
+void CVoxelyze::enableCollisions(bool e) { if (collisions == e) return; if (e && hm && devicesFromEnv) notSlabbed("enableCollisions"); collisions = e; envDirty = true; if (!stepped) topologyDirty = true; }
 
 // ---- links / collisions -------------------------------------------------------------------------
 int CVoxelyze::linkCount() const { sync(); return (int)linksList.size(); }
@@ -816,6 +879,7 @@ const std::vector<CVX_Collision*>* CVoxelyze::collisionList() const
     for (CVX_Collision* c : collisionsList) delete c;
     collisionsList.clear();
     int n = 0;
+    if (hm) return &collisionsList;                   // no self-collisions on a slabbed run
     vx_collision_forces(h, nullptr, nullptr, 0, &n);
     std::vector<int32_t> p(2 * (size_t)n); std::vector<float> fr(3 * (size_t)n);
     if (n) vx_collision_forces(h, p.data(), fr.data(), n, &n);
@@ -832,6 +896,7 @@ float CVoxelyze::stateInfo(stateInfoType info, valueType type)
 {
     sync();
     float v = 0.0f;
+    if (hm) notSlabbed("stateInfo");
     int rc = vx_state_info(h, (int)info, (int)type, &v);
     if (rc != VX_OK && rc != VX_ERR_UNSUPPORTED) die("vx_state_info");
     return v;
