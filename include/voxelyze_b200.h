@@ -437,8 +437,8 @@ const char* vx_kernel_name(const vx_sim* s);
  * vx_slabbed_halo_mode = 2: the step kernels store boundary poses into the neighbours' ghost planes themselves (peer
  * memory over NVLink, all devices queued before any is waited for); 1: host copies after every step (implementations
  * without peer memory); 0: the model runs on one slab (fewer than four z planes, or one device listed).
- * Restrictions: one body (no ensemble ids), no self-collisions, no Poisson materials (a ghost copy lacks the links its
- * Poisson strain needs, src/VX_Voxel.cpp:300-374): VX_ERR_UNSUPPORTED.  devices == NULL: devices 0 .. n_slabs-1; the
+ * Poisson materials: a ghost copy lacks the links its Poisson strain needs (src/VX_Voxel.cpp:300-374), so the owners' values
+ * travel with the halo.  Restrictions: one body (no ensemble ids), no self-collisions.  devices == NULL: devices 0 .. n_slabs-1; the
  * same device may be listed more than once (tests on one GPU).  vx_slabbed_slab exposes slab k for reports
  * (vx_kernel_name, vx_launch_count, vx_active_path); do not step it directly.                                        */
 typedef struct vx_slabbed vx_slabbed;

@@ -1008,7 +1008,8 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
             case VX_F_TEMP: f[k] = v.temp; break;
             case VX_F_VOXFLAGS: u[k] = (v.floorStatic ? VX_VF_STATIC_FRICTION : 0) | (s->isSurface(v) ? VX_VF_SURFACE : 0) | (v.ghost ? VX_VF_GHOST : 0) |
                                        (v.floorOverride == 0 ? VX_VF_FLOOR_OFF : 0) | (v.floorOverride == 1 ? VX_VF_FLOOR_ON : 0); break;
-            case VX_F_PSTRAIN: f[3 * k] = v.pStrain.x; f[3 * k + 1] = v.pStrain.y; f[3 * k + 2] = v.pStrain.z; break;
+            case VX_F_PSTRAIN: { if (!v.ghost) s->poissonsStrain(const_cast<Voxel&>(v));        // what the links of the next step will read (cached until the voxel moves, VX_Voxel.cpp:336-343)
+                                 f[3 * k] = v.pStrain.x; f[3 * k + 1] = v.pStrain.y; f[3 * k + 2] = v.pStrain.z; break; }
             default: return VX_ERR_ARG;
             }
         } else {
@@ -1047,6 +1048,7 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
         case VX_F_LINMOM: v.linMom = V3{d[3 * k], d[3 * k + 1], d[3 * k + 2]}; break;
         case VX_F_ANGMOM: v.angMom = V3{d[3 * k], d[3 * k + 1], d[3 * k + 2]}; break;
         case VX_F_TEMP: s->setTemperature(v, f[k]); break;
+        case VX_F_PSTRAIN: v.pStrain = V3f{f[3 * k], f[3 * k + 1], f[3 * k + 2]}; v.pInvalid = false; break;      // a halo voxel's Poisson strain comes from its owner
         case VX_F_VOXFLAGS: v.floorStatic = (u[k] & VX_VF_STATIC_FRICTION) != 0;
                             v.floorOverride = (u[k] & VX_VF_FLOOR_OFF) ? 0 : ((u[k] & VX_VF_FLOOR_ON) ? 1 : -1); break;
         default: return VX_ERR_ARG;

@@ -6,7 +6,7 @@ import pytest
 
 import parity
 from test_slab_gloo import _general_scenario
-from test_slabbed import check_slabbed_against_whole, check_state_edits, holes_scenario, VOXEL_FIELDS
+from test_slabbed import check_slabbed_against_whole, check_state_edits, holes_scenario, poisson_scenario, VOXEL_FIELDS, LINK_FIELDS
 from voxelyze_b200 import scenarios
 
 pytestmark = pytest.mark.gpu
@@ -26,6 +26,27 @@ def test_slabbed_handle_runs_on_peer_stores_bitwise(product):
 def test_slabbed_body_with_holes(product):
     whole, multi, dt = check_slabbed_against_whole(product, holes_scenario(), [0] * 4, 150, temperature_program=False, chunk=10)
     assert multi.halo_mode in (1, 2)
+
+
+def test_slabbed_poisson_materials_on_peer_stores(product):
+    """Poisson coupling across the cuts on the fused kernel: k_lattice_tma<.., PUSH, POISSON> stores a boundary voxel's new Poisson
+    strain into the neighbour's ghost plane next to its pose."""
+    sc = poisson_scenario()
+    whole, multi, dt = check_slabbed_against_whole(product, sc, [0, 0, 0], 150, temperature_program=False, expect_halo=2, chunk=5, path=7)
+    assert all(multi.slab(k).active_path() == 2 for k in range(3)) and whole.active_path() == 2
+    assert np.abs(whole.download("pstrain")).max() > 1e-4
+    assert parity.bit_equal(multi.download("pstrain"), whole.download("pstrain"))
+    assert whole.step(-1.0, 7) is None and multi.step(-1.0, 7) is None       # the stable step re-evaluated before every step
+    assert whole.time() == multi.time()
+    for f in VOXEL_FIELDS + LINK_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
+    sc0 = poisson_scenario(); sc0.materials[0].nu = 0.0           # switched on mid-run
+    whole, multi, dt = check_slabbed_against_whole(product, sc0, [0, 0, 0], 60, temperature_program=False, chunk=5, path=7)
+    for s in (whole, multi):
+        s.set_materials(sc.materials)
+        assert s.step(dt, 60) is None
+    for f in VOXEL_FIELDS + LINK_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
 
 
 def test_slabbed_state_edits_reach_every_copy(product):

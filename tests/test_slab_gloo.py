@@ -118,3 +118,34 @@ def test_any_scenario_splits_into_slabs_bitwise(built, tmp_path):
     for f in ("pos", "orient", "temp"):
         stitched = np.concatenate([p[f] for p in parts])
         assert np.array_equal(stitched, whole.download(f)[index]), f
+
+
+def _worker_poisson(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from test_slabbed import poisson_scenario
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r = slab.SlabRunner.from_scenario(capi.load_oracle(), poisson_scenario(), rank, world, host_exchange=True)
+    dt = r.recommended_dt()
+    assert r.poisson and r.step(dt, 80) is None
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), pos=r.owned_state("pos"), orient=r.owned_state("orient"), pstrain=r.owned_state("pstrain"),
+             index=r.scenario_index[(r.z0 - r.lo) * r.plane:(r.z1 - r.lo) * r.plane], dt=dt)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_poisson_materials_split_into_slabs_bitwise(built, tmp_path):
+    """Poisson coupling across the cuts: the ghosts' Poisson strains travel with the halo (third field of the host exchange)."""
+    import torch.multiprocessing as mp
+    from test_slabbed import poisson_scenario
+    world = 2
+    mp.spawn(_worker_poisson, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
+    whole = scenarios.build(capi.load_oracle(), poisson_scenario())
+    dt = whole.recommended_dt()
+    assert np.float32(dt) == np.float32(parts[0]["dt"]) and whole.step(dt, 80) is None
+    index = np.concatenate([p["index"] for p in parts])
+    for f in ("pos", "orient", "pstrain"):
+        stitched = np.concatenate([p[f] for p in parts])
+        assert np.array_equal(stitched, whole.download(f)[index]), f

@@ -32,8 +32,25 @@ def holes_scenario():
     return sc
 
 
-def check_slabbed_against_whole(lib, sc, devices, steps, temperature_program=True, expect_halo=None, chunk=1):
-    whole = scenarios.build(lib, sc)
+def poisson_scenario():
+    """A 5 x 4 x 10 bar along z, nu = 0.3 bilinear skin around a nu = 0 core (tVoxelyze.h:806-842 turned upright), clamped at the
+    bottom, its top plane pulled up by a prescribed displacement: the lateral contraction crosses every cut."""
+    ijk = scenarios.box_ijk(5, 4, 10, origin=(0, 0, -2))
+    ijk = ijk[np.random.default_rng(2).permutation(len(ijk))]
+    core = (ijk[:, 0] >= 1) & (ijk[:, 0] <= 3) & (ijk[:, 1] >= 1) & (ijk[:, 1] <= 2)
+    mats = [capi.Material(E=1e6, rho=1e3, nu=0.3, zeta_internal=1.0, zeta_global=0.2, model=capi.MODEL_BILINEAR, plastic_modulus=2e5, yield_stress=4e4),
+            capi.Material(E=2e6, rho=1e3, nu=0.0, zeta_internal=1.0, zeta_global=0.2)]
+    sc = scenarios.Scenario("slabbed_poisson", 0.005, mats, ijk, core.astype(np.uint16))
+    bottom, top = np.nonzero(ijk[:, 2] == -2)[0], np.nonzero(ijk[:, 2] == 7)[0]
+    sc.ext_voxel = np.concatenate([bottom, top]).astype(np.int32)
+    sc.ext_dof = np.concatenate([np.full(len(bottom), capi.DOF_ALL), np.full(len(top), 0x04)]).astype(np.uint8)
+    t = np.zeros((len(sc.ext_voxel), 3)); t[len(bottom):, 2] = 0.002
+    sc.ext_translation = t
+    return sc
+
+
+def check_slabbed_against_whole(lib, sc, devices, steps, temperature_program=True, expect_halo=None, chunk=1, path=0):
+    whole = scenarios.build(lib, sc, path=path)
     multi = scenarios.build_slabbed(lib, sc, devices)
     assert multi.n_slabs == min(len(devices), (int(sc.ijk[:, 2].max()) - int(sc.ijk[:, 2].min()) + 1) // 2)
     if expect_halo is not None:
@@ -109,6 +126,28 @@ def check_state_edits(lib, devices):
         assert parity.bit_equal(multi.download(f), whole.download(f)), f
 
 
+def test_slabbed_poisson_materials(built):
+    """Poisson coupling across the cuts: a ghost copy cannot compute its Poisson strain (it lacks links), the halo brings its
+    owner's.  Also with the stable time step re-evaluated every step (dt < 0), and with Poisson's ratio switched on mid-run."""
+    lib = capi.load_oracle()
+    sc = poisson_scenario()
+    whole, multi, dt = check_slabbed_against_whole(lib, sc, [0, 0, 0], 150, temperature_program=False, expect_halo=1, chunk=5)
+    assert np.abs(whole.download("pstrain")).max() > 1e-4
+    assert parity.bit_equal(multi.download("pstrain"), whole.download("pstrain"))
+    assert whole.step(-1.0, 7) is None and multi.step(-1.0, 7) is None
+    assert whole.time() == multi.time()
+    for f in VOXEL_FIELDS + LINK_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
+    # switched on mid-run (src/VX_Link.cpp:160-166)
+    sc0 = poisson_scenario(); sc0.materials[0].nu = 0.0
+    whole, multi, dt = check_slabbed_against_whole(lib, sc0, [0, 0, 0], 60, temperature_program=False, chunk=5)
+    for s in (whole, multi):
+        s.set_materials(sc.materials)
+        assert s.step(dt, 60) is None
+    for f in VOXEL_FIELDS + LINK_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
+
+
 def test_slabbed_state_edits_reach_every_copy(built):
     """vx_slabbed_upload / upload_link_state / set_temperature / reset: the ghost copies across the cuts follow, so the run that
     continues from edited state stays bit-identical to the unsplit run given the same edits."""
@@ -122,11 +161,8 @@ def test_slabbed_divergence_and_refusals(built):
     dt = 40.0 * whole.recommended_dt()                        # far beyond the stable step: the run blows up
     a, b = whole.step(dt, 400), multi.step(dt, 400)
     assert a is not None and a == b
-    # thin bodies run on one slab, Poisson materials are refused when cut
+    # thin bodies run on one slab
     thin = scenarios.cantilever(6, 3, 3)
     assert scenarios.build_slabbed(lib, thin, [0, 0, 0]).n_slabs == 1
-    m = lib.create_slabbed(0.005, [0, 0])
-    m.set_materials([capi.Material(E=1e6, rho=1e3, nu=0.3)])
-    with pytest.raises(capi.VxError) as e:
-        m.set_voxels(sc.ijk, sc.mat)
-    assert e.value.code == -6
+    with pytest.raises(ValueError):
+        scenarios.build_slabbed(lib, scenarios.plate_stack(8, 8, 2, thick=2, gap=1), [0, 0])       # self-collisions

@@ -107,6 +107,7 @@ struct vx_sim {
     int gen_view = -1;                  // inside a multi-step lattice call: the generation frame() shows (collision kernels)
     bool have_prev = false;             // gen^1 holds the inputs of the last executed step
     float last_prev_dt = 0.f;           // previousDt that step used
+    bool call_per_step_dt = false;      // the running / last stepping call re-evaluated dt before every step (Poisson models, dt < 0)
     float prev_dt_host = 0.f;           // mirror of DevParams::prev_dt
     // asynchronous call (vx_step_begin .. vx_step_end), used by z-slab runs to overlap the halo exchange
     bool call_active = false, call_half = false;
@@ -120,8 +121,9 @@ struct vx_sim {
         size_t src_first = 0, count = 0;                  // my layer (internal voxel range)
         double4* dst0[2] = {nullptr, nullptr};            // the peer's ghost layer in its pose0/pose1 arrays, per generation
         double4* dst1[2] = {nullptr, nullptr};
+        float4* dst_ps[2] = {nullptr, nullptr};           // Poisson models: the peer's ghost layer in its pStrain arrays, per generation
         int* dst_flag = nullptr;                          // the peer's arrival counter for messages from me
-        void* opened[3] = {nullptr, nullptr, nullptr};     // cudaIpcOpenMemHandle results (other-process peers)
+        void* opened[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // cudaIpcOpenMemHandle results (other-process peers)
     };
     std::vector<PeerLink> peers;
     bool wb_opted_in = false, capturing = false;
@@ -246,11 +248,11 @@ struct vx_sim {
         f.groups = n_groups > 0 ? group_list.p : nullptr;
         f.c_ps = any_poisson ? ps[g].p : nullptr; f.n_ps = any_poisson ? ps[g ^ 1].p : nullptr;
         f.z_lo = ghost_skip ? z_lo : 0; f.z_hi = ghost_skip ? z_hi : nz;
-        f.push_z[0] = f.push_z[1] = -1;
+        f.push_z[0] = f.push_z[1] = -1; f.push_ps[0] = f.push_ps[1] = nullptr;
         if (push_in_kernel) {
             for (size_t k = 0; k < peers.size() && k < 2; k++) {
                 f.push_z[k] = (int)(peers[k].src_first / ((size_t)nx * ny));
-                f.push0[k] = peers[k].dst0[g ^ 1]; f.push1[k] = peers[k].dst1[g ^ 1];
+                f.push0[k] = peers[k].dst0[g ^ 1]; f.push1[k] = peers[k].dst1[g ^ 1]; f.push_ps[k] = peers[k].dst_ps[g ^ 1];
             }
         }
         return f;
@@ -694,7 +696,7 @@ static void launch_voxel(vx_sim* s, const Frame& f)
 static int launch_step(vx_sim* s, const Frame& f, bool per_step_dt, bool capturing = false)
 {
     if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
-    if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+    if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p, 0); s->launches++; }
     launch_links(s, f);
     if (s->collisions) { int rc = enqueue_collision_step(s, capturing); if (rc != VX_OK) return rc; }
     launch_voxel(s, f);
@@ -830,6 +832,7 @@ static void lattice_opt_in(vx_sim* s)
     cudaFuncSetAttribute(k_lattice_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
     cudaFuncSetAttribute(k_lattice_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
     cudaFuncSetAttribute(k_lattice_tma<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
+    cudaFuncSetAttribute(k_lattice_tma<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
     cudaFuncSetAttribute(k_lattice_tma<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
     cudaFuncSetAttribute(k_lattice_tma<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM + VX_TMA_TABLE_BYTES);
     cudaFuncSetAttribute(k_lattice_tma<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VX_TMA_SMEM);
@@ -882,6 +885,7 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
                     else k_lattice_tma<false, false, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
                 }
             }
+            else if (s->any_poisson && s->push_in_kernel) k_lattice_tma<false, true, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
             else if (s->any_poisson) k_lattice_tma<false, false, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
             else if (s->push_in_kernel) {     // boundary part of vx_slab_step: new poses also go to the neighbours' ghost layers
                 if (s->uni) k_lattice_tma<true, true><<<gr, bl, tma_smem, s->stream>>>(f, tm, g, first_of_call, fl, kx, ky, kz, koff, book, gr_, stage);
@@ -965,7 +969,7 @@ static int finish_lattice_call(vx_sim* s, int g_start, int launched, int* diverg
         s->gen = (g_start + launched) & 1;
         s->have_prev = true;
         s->last_amb = amb_used && launched == 1; s->last_amb_value = s->amb_value;
-        s->last_prev_dt = launched > 1 ? p.dt : s->prev_dt_host;
+        s->last_prev_dt = launched > 1 ? (s->call_per_step_dt ? p.last_prev : p.dt) : s->prev_dt_host;
         s->prev_dt_host = p.prev_dt;
         return VX_OK;
     }
@@ -982,7 +986,7 @@ static int finish_lattice_call(vx_sim* s, int g_start, int launched, int* diverg
     CK(cudaStreamSynchronize(s->stream));
     s->last_amb = amb_used && p.steps_done == 0; s->last_amb_value = s->amb_value;
     s->have_prev = true;
-    s->last_prev_dt = p.steps_done > 0 ? p.dt : s->prev_dt_host;
+    s->last_prev_dt = p.steps_done > 0 ? (s->call_per_step_dt ? p.last_prev : p.dt) : s->prev_dt_host;
     s->prev_dt_host = p.prev_dt;
     if (diverged_step) *diverged_step = p.steps_done;
     return VX_DIVERGED;
@@ -1011,11 +1015,12 @@ static int lattice_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     ghost_words_begin(s);
     const int g0 = s->gen;
     int done = 0;
+    s->call_per_step_dt = per_step_dt;
     if (per_step_dt) {
         for (; done < n_steps; done++) {
             launch_recommended_dt(s, (g0 + done) & 1);
-            k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++;
-            int rc = launch_lattice(s, (g0 + done) & 1, done == 0 ? 1 : 0); if (rc != VX_OK) return rc;
+            k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p, done > 0 ? 1 : 0, ((g0 + done) & 1) ^ 1); s->launches++;
+            int rc = launch_lattice(s, (g0 + done) & 1, 1); if (rc != VX_OK) return rc;       // every step damps with the dt of the step before it (DevParams::prev_dt)
         }
         return finish_lattice_call(s, g0, n_steps, diverged_step);
     }
@@ -1076,7 +1081,7 @@ int vx_step_begin(vx_sim* s, float dt)
     CK(cudaSetDevice(s->device));
     k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
     ghost_words_begin(s);
-    s->call_active = true; s->call_half = false; s->call_g0 = s->gen; s->call_done = 0;
+    s->call_active = true; s->call_half = false; s->call_g0 = s->gen; s->call_done = 0; s->call_per_step_dt = false;
     return VX_OK;
 }
 
@@ -1206,13 +1211,10 @@ int vx_set_materials(vx_sim* s, int n, const vx_material_desc* d)
     // Poisson's ratio may be switched on or off at any time (the reference allows it, src/VX_Link.cpp:160-166): on the fused
     // layout the per-voxel pStrain arrays are created from the current link strains the first time it becomes non-zero
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_set_materials inside vx_step_begin .. vx_step_end");
+    const bool had_poisson = s->any_poisson;
     int rc = upload_tables(s);
     if (rc != VX_OK) return rc;
-    if (s->lattice && s->any_poisson && !s->vflags.empty()) {
-        bool ghosts = false;
-        for (uint32_t f : s->vflags) if ((f & VX_VF_GHOST) && !(f & VF_FILL)) ghosts = true;
-        if (ghosts) return fail(s, VX_ERR_UNSUPPORTED, "Poisson materials on a z-slab (halo voxels carry no Poisson strains)");
-    }
+    if (s->lattice && had_poisson != s->any_poisson) { find_boundary_layers(s); s->drop_graph(); }      // z-slabs: the ghost-skipping kernel has no Poisson variant
     if (!s->lattice && s->any_poisson && s->state_ready && s->L > 0) {
         k_refresh_slot_strain<<<blocks_for(s->L), TPB, 0, s->stream>>>(s->frame(), s->axis_first[1], s->axis_first[2]); s->launches++;
         CK(cudaGetLastError());
@@ -1381,10 +1383,10 @@ static int set_voxels_impl(vx_sim* s, int n, const int32_t* ijk, const uint16_t*
     bool poisson = false, halo = false;
     for (auto& m : s->mats) if (m.nu != 0.0f) poisson = true;
     if (flags) for (int i = 0; i < n && !halo; i++) halo = (flags[i] & VX_VF_GHOST) && !(flags[i] & VF_FILL);
-    // fused layout: a completely filled box; Poisson materials too (k_lattice_tma<.., POISSON>) unless the box is a z-slab
-    // with halo voxels, whose Poisson strains nobody exchanges
+    // fused layout: a completely filled box; Poisson materials too (k_lattice_tma<.., POISSON>; on a z-slab the halo carries
+    // the ghosts' Poisson strains along with their poses)
     s->small = n == n_user && small_model(s, n, flags);
-    s->lattice = n > 0 && cells == (long long)n && !(poisson && halo) && s->path != 1 && !s->small;
+    s->lattice = n > 0 && cells == (long long)n && s->path != 1 && !s->small;
     s->state_ready = false;
     s->pack[0] = s->pack[1] = 1; s->pack[2] = s->n_members; s->lat_members = s->n_members;
     if (s->lattice && s->n_members > 1 && !getenv("VX_NO_PACK")) {
@@ -1677,7 +1679,7 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
     k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, dt > 0 ? 1 : 0); s->launches++;
     if (dt < 0 && !per_step_dt) {                                  // constant recommended dt
         launch_recommended_dt(s);
-        k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++;
+        k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p, 0); s->launches++;
     }
     int left = n_steps;
     collision_call_begin(s);
@@ -1726,6 +1728,7 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
     if (s->lattice) {
         // one fused kernel per step: reported as the "link" group (it is the dominant kernel)
         if (dt < 0) { rc = vx_recommended_dt(s, &dt); if (rc != VX_OK || dt <= 0) return rc; }
+        s->call_per_step_dt = false;
         k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
         collision_call_begin(s);
         ghost_words_begin(s);
@@ -1742,13 +1745,13 @@ int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)
         Frame f = s->frame();
         const bool per_step_dt = dt < 0 && s->any_poisson;
         k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, dt > 0 ? 1 : 0); s->launches++;
-        if (dt < 0 && !per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+        if (dt < 0 && !per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p, 0); s->launches++; }
         collision_call_begin(s);
         for (int k = 0; k < n_steps; k++) {
             int64_t l0 = s->launches;
             CK(cudaEventRecord(ev[4 * k + 0], s->stream));
             if (s->any_poisson) { k_pstrain<<<blocks_for(s->N), TPB, 0, s->stream>>>(f); s->launches++; }
-            if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p); s->launches++; }
+            if (per_step_dt) { launch_recommended_dt(s); k_dt_from_freq<<<1, 1, 0, s->stream>>>(s->freq2.p, s->params.p, 0); s->launches++; }
             int64_t l1 = s->launches;
             CK(cudaEventRecord(ev[4 * k + 1], s->stream));
             launch_links(s, f);
@@ -1924,7 +1927,8 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
 {
     int what, comps, esize; bool is_link;
     if (!s || !src || first < 0 || count < 0 || !field_info(field, what, comps, esize, is_link)) return VX_ERR_ARG;
-    if (is_link || what == G_PSTRAIN) return fail(s, VX_ERR_UNSUPPORTED, "only voxel state can be uploaded");
+    if (is_link) return fail(s, VX_ERR_UNSUPPORTED, "only voxel state can be uploaded");
+    if (what == G_PSTRAIN && !(s->lattice && s->any_poisson)) return fail(s, VX_ERR_UNSUPPORTED, "Poisson strains are uploaded into the ghost voxels of a z-slab on the fused layout only");
     if (s->call_active) return fail(s, VX_ERR_ARG, "vx_upload inside vx_step_begin .. vx_step_end");
     if ((long long)first + count > s->N_user) return VX_ERR_ARG;
     if (count == 0) return VX_OK;

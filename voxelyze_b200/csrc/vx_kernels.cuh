@@ -357,9 +357,17 @@ __global__ void __launch_bounds__(256) k_max_freq_voxels(Frame f, unsigned int* 
 }
 
 // dt = 1/(2*pi*sqrt(maxFreq2)) written to the device-resident step parameters
-__global__ void k_dt_from_freq(const unsigned int* freq2, DevParams* p)
+// roll (fused path, calls that re-evaluate dt every step): the step before this one ran in the same call with another dt --
+// it is counted here, with ITS dt, before that is replaced (the fused kernels otherwise count a step when the next one
+// starts), and its dt becomes CVX_Voxel::previousDt; parity_prev: generation parity whose divergence flag that step wrote
+__global__ void k_dt_from_freq(const unsigned int* freq2, DevParams* p, int roll, int parity_prev = 0)
 {
     float m = __uint_as_float(*freq2);
+    if (roll) {
+        if (p->div_flag[parity_prev] | p->div_latched) p->div_latched = 1;
+        else if (p->pending) { p->steps_done += 1; p->time += p->dt; p->pending = 0; }
+        p->prev_dt = p->dt;
+    }
     p->dt = (m <= 0.0f) ? 0.0f : 1.0f / (6.283185f * sqrtf(m));
 }
 
@@ -439,6 +447,7 @@ __global__ void k_scatter(Frame f, int what, const int* e2i, int first, int coun
     case G_LINMOM: { double4 a = f.mom0[i]; a.x = d[3 * k]; a.y = d[3 * k + 1]; a.z = d[3 * k + 2]; f.mom0[i] = a; break; }
     case G_ANGMOM: { double4 a = f.mom0[i]; a.w = d[3 * k]; f.mom0[i] = a; f.mom1[i] = make_double2(d[3 * k + 1], d[3 * k + 2]); break; }
     case G_TEMP: { double w = f.pose1[i].w; f.pose1[i].w = meta_pack(fl[k], meta_hi(w)); break; }
+    case G_PSTRAIN: if (f.pstrain) f.pstrain[i] = make_float4(fl[3 * k], fl[3 * k + 1], fl[3 * k + 2], 0.f); break;     // a ghost's Poisson strain comes from its owner
     case G_VOXFLAGS: { double w = f.pose1[i].w; uint32_t b = meta_hi(w); b = (b & ~(VM_STATIC_FRIC | VM_FLOOR_OFF | VM_FLOOR_ON)) | ((u[k] & 1u) ? VM_STATIC_FRIC : 0u) | ((u[k] & 8u) ? VM_FLOOR_OFF : 0u) | ((u[k] & 16u) ? VM_FLOOR_ON : 0u); f.pose1[i].w = meta_pack(meta_temp(w), b); break; }
     }
 }

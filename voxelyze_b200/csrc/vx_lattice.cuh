@@ -64,6 +64,7 @@ struct LatFrame {
     // Poisson coupling (nu != 0, k_lattice_tma<.., POISSON>): CVX_Voxel::pStrain of every voxel as of the state the step reads
     // (= computed from the link strains of the previous step), double-buffered like the voxel state
     const float4* c_ps; float4* n_ps;
+    float4* push_ps[2];                 // with PUSH: the neighbours' ghost planes in their pStrain arrays of the generation being written
     // z-slab runs on k_lattice_tma<.., GSKIP>: bricks cover the planes [z_lo, z_hi) only -- the all-ghost planes below and above
     // are data, not work (brick origins are shifted by z_lo; 0 / nz everywhere else)
     int z_lo, z_hi;
@@ -155,6 +156,7 @@ __global__ void k_lattice_finish(DevParams* p, int parity_of_last)
 {
     if (p->div_flag[parity_of_last] | p->div_latched) p->div_latched = 1;
     else if (p->pending) { p->steps_done += 1; p->time += p->dt; }
+    p->last_prev = p->prev_dt;
     if (p->steps_done > 0) p->prev_dt = p->dt;
     p->pending = 0;
 }
@@ -917,14 +919,14 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         if (POISSON) {                                  // CVX_Voxel::pStrain for the NEXT step, from this step's link strains
             // a fully fixed voxel returns from CVX_Voxel::timeStep before its cache is invalidated (src/VX_Voxel.cpp:167-172,
             // 231): it keeps the Poisson strain it had
-            if (ext && (ext->dof & 0x3Fu) == 0x3Fu) f.n_ps[v] = ps_own;
-            else {
+            if (!(ext && (ext->dof & 0x3Fu) == 0x3Fu)) {
                 float r[3] = {0.f, 0.f, 0.f}; int nb[3] = {0, 0, 0};
                 const uint32_t lm6 = (vs.bits >> VM_LINK_SHIFT) & 0x3Fu;
 #pragma unroll
                 for (int k = 0; k < 6; k++) if (lm6 & (1u << k)) { r[k >> 1] += pe[k]; nb[k >> 1]++; }
-                f.n_ps[v] = voxel_pstrain(vm, ext, r, nb);
+                ps_own = voxel_pstrain(vm, ext, r, nb);
             }
+            f.n_ps[v] = ps_own;
         }
         voxel_integrate(vs, F, M, refs, n_refs, f.col_force, vm, ext, dt, floor_on != 0);
     }
@@ -941,6 +943,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
             double* d = reinterpret_cast<double*>(f.push1[k] + q);
             d[0] = vs.orient.x; d[1] = vs.orient.y; d[2] = vs.orient.z;
             reinterpret_cast<float*>(d + 3)[0] = vs.temp;
+            if (POISSON) f.push_ps[k][q] = ps_own;       // the ghost copy's Poisson strain for the next step
         }
     }
 }

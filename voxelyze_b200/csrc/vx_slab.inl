@@ -8,6 +8,8 @@ struct PeerDescWire {                       // what vx_peer_export writes into v
     cudaIpcMemHandle_t mem[2]; cudaIpcMemHandle_t flag;      // the pose allocation of generation 0 and 1 (pose0, then pose1 at +pose1_off); flag array
     uint64_t raw[2]; uint64_t raw_flag;                      // same-process peers use the addresses directly
     uint64_t pose1_off;                                      // in double4 elements
+    int32_t has_ps, pad;                                     // Poisson models: the two pStrain generations travel too
+    cudaIpcMemHandle_t mem_ps[2]; uint64_t raw_ps[2];
 };
 static_assert(sizeof(PeerDescWire) <= VX_PEER_DESC_BYTES, "vx_peer_desc too small");
 
@@ -47,6 +49,8 @@ int vx_peer_export(vx_sim* s, int ghost_iz, int from_above, vx_peer_desc* out)
     w.pose1_off = (uint64_t)(s->pose1[0].p - s->pose0[0].p);
     if ((uint64_t)(s->pose1[1].p - s->pose0[1].p) != w.pose1_off) return fail(s, VX_ERR_CUDA, "vx_peer_export: generations laid out differently");
     CK(cudaIpcGetMemHandle(&w.flag, s->peer_flags.p)); w.raw_flag = (uint64_t)(uintptr_t)s->peer_flags.p;
+    w.has_ps = s->any_poisson && s->ps[0].p && s->ps[1].p ? 1 : 0;
+    for (int k = 0; k < 2 && w.has_ps; k++) { CK(cudaIpcGetMemHandle(&w.mem_ps[k], s->ps[k].p)); w.raw_ps[k] = (uint64_t)(uintptr_t)s->ps[k].p; }
     memset(out->bytes, 0, VX_PEER_DESC_BYTES); memcpy(out->bytes, &w, sizeof(w));
     s->expect_side[w.side] = true;                                   // a neighbour will write here
     return VX_OK;
@@ -60,10 +64,12 @@ int vx_peer_attach(vx_sim* s, int send_iz, const vx_peer_desc* peer_ghost)
     if (w.magic != 0x56585045455231ULL) return fail(s, VX_ERR_ARG, "vx_peer_attach: not a peer descriptor");
     vx_sim::PeerLink pl;
     if (plane_range(s, send_iz, pl.src_first, pl.count) != VX_OK || pl.count != w.count) return fail(s, VX_ERR_ARG, "vx_peer_attach: layer size mismatch");
-    void* base[3];
-    if (w.pid == (int64_t)getpid()) {                                 // same process (tests): plain addresses
+    if ((w.has_ps != 0) != (s->any_poisson && s->ps[0].p)) return fail(s, VX_ERR_ARG, "vx_peer_attach: only one side carries Poisson strains");
+    void* base[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (w.pid == (int64_t)getpid()) {                                 // same process (tests, vx_slabbed): plain addresses
         for (int k = 0; k < 2; k++) base[k] = (void*)(uintptr_t)w.raw[k];
         base[2] = (void*)(uintptr_t)w.raw_flag;
+        for (int k = 0; k < 2 && w.has_ps; k++) base[3 + k] = (void*)(uintptr_t)w.raw_ps[k];
         if (w.device != s->device) { int can = 0; cudaDeviceCanAccessPeer(&can, s->device, w.device); if (!can) return fail(s, VX_ERR_UNSUPPORTED, "no peer access"); cudaError_t e = cudaDeviceEnablePeerAccess(w.device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(s, e, "cudaDeviceEnablePeerAccess"); cudaGetLastError(); }
     } else {
         for (int k = 0; k < 2; k++) {
@@ -74,7 +80,13 @@ int vx_peer_attach(vx_sim* s, int send_iz, const vx_peer_desc* peer_ghost)
         cudaError_t e = cudaIpcOpenMemHandle(&base[2], w.flag, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) { cudaGetLastError(); return fail(s, VX_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
         pl.opened[2] = base[2];
+        for (int k = 0; k < 2 && w.has_ps; k++) {
+            e = cudaIpcOpenMemHandle(&base[3 + k], w.mem_ps[k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(s, VX_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+            pl.opened[3 + k] = base[3 + k];
+        }
     }
+    if (w.has_ps) { pl.dst_ps[0] = (float4*)base[3] + w.first; pl.dst_ps[1] = (float4*)base[4] + w.first; }
     pl.dst0[0] = (double4*)base[0] + w.first; pl.dst0[1] = (double4*)base[1] + w.first;
     pl.dst1[0] = (double4*)base[0] + w.pose1_off + w.first; pl.dst1[1] = (double4*)base[1] + w.pose1_off + w.first;
     pl.dst_flag = (int*)base[2] + w.side;
@@ -111,6 +123,7 @@ static void peer_push(vx_sim* s, int g, bool already_stored)
             k_halo_push<<<blocks_for((long long)pl.count), TPB, 0, s->comm_stream>>>(s->pose0[g].p + pl.src_first, s->pose1[g].p + pl.src_first,
                                                                                      pl.dst0[g], pl.dst1[g], (int)pl.count);
             s->launches++;
+            if (pl.dst_ps[g]) cudaMemcpyAsync(pl.dst_ps[g], s->ps[g].p + pl.src_first, pl.count * sizeof(float4), cudaMemcpyDefault, s->comm_stream);
         }
         k_peer_signal<<<1, 1, 0, s->comm_stream>>>(pl.dst_flag, s->xseq);
         s->launches++;
@@ -123,10 +136,19 @@ static int peer_check(vx_sim* s)
     return t ? fail(s, VX_ERR_CUDA, "peer halo: a neighbouring slab did not deliver in time") : VX_OK;
 }
 
+// Poisson strains travel with the poses: peers attached while the model had no Poisson material do not know where to put them
+static int peers_carry_ps(vx_sim* s)
+{
+    if (s->any_poisson) for (auto& pl : s->peers) if (!pl.dst_ps[0] || !pl.dst_ps[1])
+        return fail(s, VX_ERR_ARG, "Poisson's ratio was switched on after vx_peer_attach: detach, export and attach again");
+    return VX_OK;
+}
+
 int vx_slab_exchange(vx_sim* s)
 {
     if (!s || !s->lattice || s->call_active) return VX_ERR_ARG;
     int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
+    rc = peers_carry_ps(s); if (rc != VX_OK) return rc;
     rc = flush_ambient(s); if (rc != VX_OK) return rc;
     CK(cudaEventRecord(s->ev_boundary, s->stream));
     CK(cudaStreamWaitEvent(s->comm_stream, s->ev_boundary, 0));
@@ -139,6 +161,7 @@ int vx_slab_step_begin(vx_sim* s, float dt, int n_steps)
 {
     if (!s || n_steps < 1) return VX_ERR_ARG;
     int rc = ensure_peer_state(s); if (rc != VX_OK) return rc;
+    rc = peers_carry_ps(s); if (rc != VX_OK) return rc;
     NvtxRange nvtx("vx_slab_step_begin");
     rc = vx_step_begin(s, dt); if (rc != VX_OK) return rc;
     auto abandon = [&](int code) { s->call_active = false; s->call_half = false; s->push_in_kernel = false; return code; };   // leave no call open behind an error

@@ -81,7 +81,8 @@ static int host_exchange(vx_slabbed* m)
     std::vector<double> buf;
     for (int k = 0; k + 1 < m->active; k++) {
         const vx_slabbed::Part &a = m->part[k], &b = m->part[k + 1];
-        const int fields[2] = {VX_F_POS, VX_F_ORIENT};
+        const int fields[3] = {VX_F_POS, VX_F_ORIENT, VX_F_PSTRAIN};
+        const int n_fields = m->poisson ? 3 : 2;
         for (int dir = 0; dir < 2; dir++) {
             const int z = dir == 0 ? a.z1 - 1 : b.z0;                          // plane that travels: up out of a, down out of b
             const vx_slabbed::Part &src = dir == 0 ? a : b, &dst = dir == 0 ? b : a;
@@ -89,7 +90,7 @@ static int host_exchange(vx_slabbed* m)
             const int sf = src.plane_first[z - src.lo], sn = src.plane_first[z - src.lo + 1] - sf;
             const int df = dst.plane_first[z - dst.lo], dn = dst.plane_first[z - dst.lo + 1] - df;
             if (sn != dn) return fail(m, VX_ERR_TOPOLOGY, "slab planes of different size");
-            for (int f = 0; f < 2; f++) {
+            for (int f = 0; f < n_fields; f++) {
                 buf.resize((size_t)sn * 4);
                 int rc = vx_download(m->slab[ks], fields[f], sf, sn, buf.data()); if (rc != VX_OK) return fail_from(m, ks, rc, "vx_download");
                 rc = vx_upload(m->slab[kd], fields[f], df, dn, buf.data()); if (rc != VX_OK) return fail_from(m, kd, rc, "vx_upload");
@@ -183,11 +184,14 @@ int vx_slabbed_set_materials(vx_slabbed* m, int n, const vx_material_desc* descs
     if (!m || n < 0 || (n && !descs)) return VX_ERR_ARG;
     bool poisson = false;
     for (int i = 0; i < n; i++) poisson = poisson || descs[i].poissons_ratio != 0.0f;
-    // a voxel's Poisson strain needs all of its links (src/VX_Voxel.cpp:300-374); a ghost copy does not have them
-    if (poisson && m->active > 1) return vxs::fail(m, VX_ERR_UNSUPPORTED, "materials with a Poisson's ratio cannot be cut into slabs");
     for (size_t k = 0; k < m->slab.size(); k++) { int rc = vx_set_materials(m->slab[k], n, descs); if (rc != VX_OK) return vxs::fail_from(m, (int)k, rc, "vx_set_materials"); }
+    const bool changed = poisson != m->poisson;
     m->poisson = poisson;
-    return VX_OK;
+    // a voxel's Poisson strain needs all of its links (src/VX_Voxel.cpp:300-374); a ghost copy does not have them and takes
+    // its owner's value through the halo -- also right after Poisson's ratio was switched on mid-run
+    if (!changed || m->active < 2) return VX_OK;
+    if (m->halo == 2) { vxs::detach_all(m); m->halo = vxs::connect_peers(m) ? 2 : 1; }      // the peer mappings cover the Poisson strain arrays only when they exist
+    return poisson ? vxs::exchange_all(m) : VX_OK;
 }
 
 int vx_slabbed_set_gravity(vx_slabbed* m, float g)
@@ -225,7 +229,6 @@ int vx_slabbed_set_voxels(vx_slabbed* m, int n, const int32_t* ijk, const uint16
     const long long ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1;
     if (ex * ey * ez > std::max(16LL * n, 1LL << 22)) return vxs::fail(m, VX_ERR_UNSUPPORTED, "body too sparse for its bounding box to be cut into slabs");
     const int act = (int)std::max(1LL, std::min((long long)G, ez / 2));       // at least two owned planes per slab
-    if (m->poisson && act > 1) return vxs::fail(m, VX_ERR_UNSUPPORTED, "materials with a Poisson's ratio cannot be cut into slabs");
     // occupancy grid over the bounding box: cell -> voxel
     std::vector<int32_t> grid((size_t)(ex * ey * ez), -1);
     auto cell = [&](int x, int y, int z) -> size_t { return ((size_t)(z - lo[2]) * ey + (y - lo[1])) * ex + (x - lo[0]); };
@@ -330,7 +333,7 @@ int vx_slabbed_set_externals(vx_slabbed* m, int n, const int32_t* voxel, const u
         int rc = vx_set_externals(m->slab[k], (int)v.size(), v.data(), d.data(), f.data(), mo.data(), t.data(), r.data());
         if (rc != VX_OK) return vxs::fail_from(m, k, rc, "vx_set_externals");
     }
-    return VX_OK;
+    return m->poisson ? vxs::exchange_all(m) : VX_OK;         // fixed degrees of freedom enter a voxel's Poisson strain
 }
 
 int vx_slabbed_set_temperature_all(vx_slabbed* m, float t)
@@ -372,6 +375,15 @@ int vx_slabbed_step(vx_slabbed* m, float dt, int n_steps, int* diverged_step)
     if (m->active == 1) {
         int rc = vx_step(m->slab[0], dt, n_steps, diverged_step);
         return rc == VX_OK || rc == VX_DIVERGED ? rc : vxs::fail_from(m, 0, rc, "vx_step");
+    }
+    if (dt < 0 && m->poisson && n_steps > 1) {            // with Poisson coupling the stable step follows the state (src/VX_Link.cpp:259-267): step by step
+        for (int s = 0; s < n_steps; s++) {
+            int d = -1;
+            int rc = vx_slabbed_step(m, -1.0f, 1, &d);
+            if (rc == VX_DIVERGED) { if (diverged_step) *diverged_step = s; return rc; }
+            if (rc != VX_OK) return rc;
+        }
+        return VX_OK;
     }
     if (dt < 0) { int rc = vx_slabbed_recommended_dt(m, &dt); if (rc != VX_OK) return rc; if (dt <= 0) return VX_OK; }      // state independent without Poisson coupling
     int first_div = -1, err = VX_OK;
@@ -548,13 +560,13 @@ int vx_slabbed_upload_link_state(vx_slabbed* m, int first, int count, const vx_l
             for (int j = 0; j < ln; j++) buf[j] = src[p.link_l2g[j]];
             int rc = vx_upload_link_state(m->slab[k], 0, ln, buf.data()); if (rc != VX_OK) return vxs::fail_from(m, k, rc, "vx_upload_link_state");
         }
-        return VX_OK;
+        return m->poisson ? vxs::exchange_all(m) : VX_OK;      // the slabs rebuilt their Poisson strains from their own links: ghosts take their owners'
     }
     for (int i = first; i < first + count; i++) {         // the owner's copy and the copy above the cut the link crosses
         int rc = vx_upload_link_state(m->slab[m->link_owner[i]], m->link_local[i], 1, src + (i - first)); if (rc != VX_OK) return vxs::fail_from(m, m->link_owner[i], rc, "vx_upload_link_state");
         if (m->link_slab2[i] >= 0) { rc = vx_upload_link_state(m->slab[m->link_slab2[i]], m->link_local2[i], 1, src + (i - first)); if (rc != VX_OK) return vxs::fail_from(m, m->link_slab2[i], rc, "vx_upload_link_state"); }
     }
-    return VX_OK;
+    return m->poisson ? vxs::exchange_all(m) : VX_OK;
 }
 
 int64_t vx_slabbed_launch_count(const vx_slabbed* m)

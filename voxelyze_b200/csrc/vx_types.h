@@ -102,4 +102,5 @@ struct DevParams {
     int   col_stale;       // collision watch list must be rebuilt
     int   pending;         // fused path: the previous step still has to be counted
     int   div_flag[2];     // fused path: divergence flag of the step with that generation parity
+    float last_prev;       // fused path: DevParams::prev_dt as the last step of the finished call saw it (calls that change dt every step)
 };

@@ -654,7 +654,7 @@ void CVoxelyze::rebuildTopology() const
     if (hm) {
         if (collisions) notSlabbed("enableCollisions");
         const int rc = vx_slabbed_set_voxels(hm, n, ijk.data(), mat.data());
-        if (rc == VX_ERR_UNSUPPORTED && devicesFromEnv) {             // a model that cannot be cut (Poisson materials, too sparse): one device after all
+        if (rc == VX_ERR_UNSUPPORTED && devicesFromEnv) {             // a model that cannot be cut (too sparse for its bounding box): one device after all
             destroyHandle();
             devices.resize(1);
             if (vx_create(voxSize, devices[0], &h) != VX_OK) die("vx_create");
@@ -737,8 +737,7 @@ void CVoxelyze::sync() const
     struct Busy { bool& b; bool was; Busy(bool& x) : b(x), was(x) { b = true; } ~Busy() { b = was; } } busy(syncing);
     if (!h && !hm) {
         if (devices.size() > 1 && devicesFromEnv) {                                          // VX_DEVICES is a wish, setDevices an order
-            bool cut = !collisions && !voxelsList.empty() && bound(2, true) - bound(2, false) + 1 >= 4;      // at least two planes per slab
-            for (CVX_MaterialVoxel* m : voxelMats) cut = cut && m->poissonsRatio() == 0.0f;
+            const bool cut = !collisions && !voxelsList.empty() && bound(2, true) - bound(2, false) + 1 >= 4;      // at least two planes per slab
             if (!cut) devices.resize(1);
         }
         if (devices.size() > 1) { if (vx_slabbed_create(voxSize, (int)devices.size(), devices.data(), &hm) != VX_OK) die("vx_slabbed_create"); }

@@ -188,6 +188,9 @@ class SlabRunner:
                 sim.set_temperature_all(sc.temperature)
             self.scenario_index = keep                  # local voxel -> caller index of the scenario
         self.sim, self.ijk = sim, ijk
+        # Poisson materials: a ghost's Poisson strain (it lacks the links to compute it) travels with the halo -- in the peer
+        # stores of the step kernel, or as a third field of the host exchange; the NCCL pose messages do not carry it
+        self.poisson = any(m.nu != 0.0 for m in (scenario.materials if scenario is not None else [material or Material()]))
         self.host_exchange = host_exchange
         self._bufs = None
         # overlap the exchange with the interior of the step (device exchange on the fused lattice path only)
@@ -294,6 +297,8 @@ class SlabRunner:
         torch's current stream; import_stream: cudaStream_t the import kernels go to (None: the handle's)."""
         import torch
         dist = self.dist
+        if self.poisson:
+            raise RuntimeError("Poisson materials on z-slabs need the peer-memory halo or the host exchange (the NCCL pose messages carry no Poisson strains)")
         if self._bufs is None:
             self._bufs = {"views": {}, "recv": {}}
         views, recv = self._bufs["views"], self._bufs["recv"]
@@ -323,9 +328,12 @@ class SlabRunner:
         reqs, recvs = [], []
         for peer, send_z, recv_z in self._neighbours():
             first, n = self.layer_index_range(send_z)
-            payload = np.concatenate([self.sim.download("pos", first, n).ravel(), self.sim.download("orient", first, n).ravel()])
+            parts = [self.sim.download("pos", first, n).ravel(), self.sim.download("orient", first, n).ravel()]
+            if self.poisson:
+                parts.append(self.sim.download("pstrain", first, n).ravel().astype(np.float64))      # float32 values, exact in float64
+            payload = np.concatenate(parts)
             reqs.append(dist.isend(torch.from_numpy(payload), peer))
-            buf = torch.empty(7 * self.plane, dtype=torch.float64)
+            buf = torch.empty((10 if self.poisson else 7) * self.plane, dtype=torch.float64)
             reqs.append(dist.irecv(buf, peer))
             recvs.append((buf, recv_z))
         for r in reqs:
@@ -334,7 +342,9 @@ class SlabRunner:
             first, n = self.layer_index_range(recv_z)
             a = buf.numpy()
             self.sim.upload("pos", a[:3 * n].reshape(n, 3), first)
-            self.sim.upload("orient", a[3 * n:].reshape(n, 4), first)
+            self.sim.upload("orient", a[3 * n:7 * n].reshape(n, 4), first)
+            if self.poisson:
+                self.sim.upload("pstrain", a[7 * n:].astype(np.float32).reshape(n, 3), first)
 
     def exchange(self):
         if self.world == 1:
