@@ -238,6 +238,12 @@ int  vx_set_temperature(vx_sim* s, int n, const float* t);
  * completed before the diverging one; like the reference, on the diverging step the
  * links are updated but the voxels are not advanced, and no later step is run.       */
 int  vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step);
+/* vx_step with an ambient temperature program: before step k every voxel takes temperature ambient[k] -- what a caller does
+ * who calls CVoxelyze::setAmbientTemperature(t_k, true) and doTimeStep(dt) in turn (src/Voxelyze.cpp:585-594, 251-284; the
+ * thermally actuated robots of BASELINE config C4), n_steps of it without a host round trip per step.  Same bits as the
+ * n_steps pairs of vx_set_temperature_all + vx_step(s, dt, 1).  On divergence the voxels keep the temperature of the
+ * diverging step, like there.                                                                                          */
+int  vx_step_ambient(vx_sim* s, float dt, int n_steps, const float* ambient, int* diverged_step);
 /* optional: builds everything vx_step would otherwise build lazily on its first long call (the captured
  * CUDA graphs of 16 steps, tensor maps) without touching the state, so that a caller who times
  * steps does not time the set-up.  No reference counterpart.                          */

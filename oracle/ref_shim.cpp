@@ -423,6 +423,19 @@ int vx_peer_export(vx_sim*, int, int, vx_peer_desc*) { return VX_ERR_UNSUPPORTED
 int vx_peer_attach(vx_sim*, int, const vx_peer_desc*) { return VX_ERR_UNSUPPORTED; }
 int vx_peer_detach(vx_sim*) { return VX_ERR_UNSUPPORTED; }
 int vx_slab_step(vx_sim*, float, int, int*) { return VX_ERR_UNSUPPORTED; }
+int vx_step_ambient(vx_sim* s, float dt, int n_steps, const float* ambient, int* diverged_step)
+{
+    if (!s || n_steps < 0 || (n_steps && !ambient)) return VX_ERR_ARG;
+    if (diverged_step) *diverged_step = -1;
+    for (int k = 0; k < n_steps; k++) {                 // the calls it stands for, one by one
+        int rc = vx_set_temperature_all(s, ambient[k]); if (rc != VX_OK) return rc;
+        int d = -1;
+        rc = vx_step(s, dt, 1, &d);
+        if (rc == VX_DIVERGED && diverged_step) *diverged_step = k;
+        if (rc != VX_OK) return rc;
+    }
+    return VX_OK;
+}
 int vx_slab_step_begin(vx_sim*, float, int) { return VX_ERR_UNSUPPORTED; }
 int vx_slab_step_finish(vx_sim*, int*) { return VX_ERR_UNSUPPORTED; }
 int vx_slab_exchange(vx_sim*) { return VX_ERR_UNSUPPORTED; }

@@ -146,6 +146,7 @@ class VxLib:
             "vx_set_temperature_members": (i32, [vp, i32, vp]),
             "vx_set_temperature": (i32, [vp, i32, vp]),
             "vx_step": (i32, [vp, f32, i32, P(i32)]),
+            "vx_step_ambient": (i32, [vp, f32, i32, vp, P(i32)]),
             "vx_prepare": (i32, [vp]),
             "vx_recommended_dt": (i32, [vp, P(f32)]),
             "vx_reset": (i32, [vp]),
@@ -345,6 +346,13 @@ class Sim:
         """Runs n steps; returns None, or the number of completed steps if diverged."""
         div = C.c_int(-1)
         rc = self._chk(self.L.lib.vx_step(self.h, dt, n, C.byref(div)), ok=(VX_OK, VX_DIVERGED))
+        return div.value if rc == VX_DIVERGED else None
+
+    def step_ambient(self, dt: float, ambient) -> Optional[int]:
+        """len(ambient) steps; before step k every voxel takes temperature ambient[k] (setAmbientTemperature + doTimeStep in turn)."""
+        a = np.ascontiguousarray(ambient, dtype=np.float32)
+        div = C.c_int(-1)
+        rc = self._chk(self.L.lib.vx_step_ambient(self.h, dt, len(a), _ptr(a), C.byref(div)), ok=(VX_OK, VX_DIVERGED))
         return div.value if rc == VX_DIVERGED else None
 
     def prepare(self):

@@ -94,6 +94,7 @@ struct vx_sim {
     // of by a pass of its own; flush_ambient() materialises it for every other reader.  last_amb: the last executed
     // step was such a step (its inputs, generation gen^1, still hold the old temperatures)
     bool amb_pending = false, last_amb = false; float amb_value = 0.f, last_amb_value = 0.f;
+    bool amb_each_step = false;         // vx_step_ambient is queueing: every step applies the ambient temperature it is launched with
     bool floor_on = false, collisions = false;
     float time_host = 0.f;
     int path = 0;                       // vx_set_path: 0 auto, 1 general, 3 small-model cluster kernel, 5 / 7 fused lattice with cp.async / TMA staging
@@ -694,7 +695,7 @@ static void launch_lattice_warp(vx_sim* s, int g, int first_of_call, int gz_off,
     lattice_opt_in(s);
     if (grid > 0) {
         LatFrame f = s->lat_frame(g);
-        if (first_of_call && s->amb_pending) { f.amb_set = 1; f.amb = s->amb_value; }
+        if ((first_of_call || s->amb_each_step) && s->amb_pending) { f.amb_set = 1; f.amb = s->amb_value; }
         const int fl = s->floor_on ? 1 : 0;
         const dim3 bl(32 * VX_WB_WARPS);
         const unsigned char* tm = s->tmaps.p;
@@ -1164,6 +1165,53 @@ int vx_step(vx_sim* s, float dt, int n_steps, int* diverged_step)
         return VX_DIVERGED;
     }
     return VX_OK;
+}
+
+int vx_step_ambient(vx_sim* s, float dt, int n_steps, const float* ambient, int* diverged_step)
+{
+    if (!s || n_steps < 0 || (n_steps && !ambient)) return VX_ERR_ARG;
+    if (s->call_active) return fail(s, VX_ERR_ARG, "vx_step_ambient inside vx_step_begin .. vx_step_end");
+    if (diverged_step) *diverged_step = -1;
+    if (n_steps == 0 || dt == 0 || s->N == 0) return VX_OK;
+    if (!s->lattice || s->collisions || (dt < 0 && s->any_poisson)) {         // other layouts: the calls it stands for, one by one
+        for (int k = 0; k < n_steps; k++) {
+            int rc = vx_set_temperature_all(s, ambient[k]); if (rc != VX_OK) return rc;
+            int d = -1;
+            rc = vx_step(s, dt, 1, &d);
+            if (rc == VX_DIVERGED && diverged_step) *diverged_step = k;
+            if (rc != VX_OK) return rc;
+        }
+        return VX_OK;
+    }
+    NvtxRange nvtx("vx_step_ambient");
+    CK(cudaSetDevice(s->device));
+    // fused lattice path: the temperature is a launch parameter of the step kernel (LatFrame::amb), so a program of n
+    // temperatures is n launches queued back to back -- no pass over the voxels, no host synchronisation until the end
+    if (dt < 0) { int rc = vx_recommended_dt(s, &dt); if (rc != VX_OK) return rc; if (dt <= 0) return VX_OK; }
+    k_begin<<<1, 1, 0, s->stream>>>(s->params.p, dt, 1); s->launches++;
+    collision_call_begin(s);
+    ghost_words_begin(s);
+    const int g0 = s->gen;
+    s->call_per_step_dt = false; s->amb_each_step = true;
+    int rc = VX_OK;
+    for (int k = 0; k < n_steps && rc == VX_OK; k++) {
+        s->amb_pending = true; s->amb_value = ambient[k];
+        rc = launch_lattice(s, (g0 + k) & 1, k == 0 ? 1 : 0);
+    }
+    s->amb_each_step = false; s->amb_pending = false;      // (finish_lattice_call's own ambient bookkeeping is for single pending values)
+    if (rc != VX_OK) { cudaStreamSynchronize(s->stream); return rc; }
+    int d = -1;
+    rc = finish_lattice_call(s, g0, n_steps, &d);
+    if (rc != VX_OK && rc != VX_DIVERGED) return rc;
+    const int last = rc == VX_DIVERGED ? d : n_steps - 1;         // the last step that ran (a diverging step updates its links)
+    s->ambient = ambient[last]; s->amb_value = ambient[last];
+    if (rc == VX_DIVERGED) {               // its voxels were not advanced, but they had been given their new temperature (src/Voxelyze.cpp:585-594 precedes doTimeStep)
+        k_fill_temp<<<blocks_for(s->N), TPB, 0, s->stream>>>(s->frame(), ambient[last], nullptr, nullptr); s->launches++;
+        CK(cudaStreamSynchronize(s->stream));
+        if (diverged_step) *diverged_step = d;
+    }
+    s->last_amb = true; s->last_amb_value = ambient[last];       // the inputs of that step (generation gen^1) still hold the temperatures before it
+    return rc;
 }
 
 int vx_step_profile(vx_sim* s, float dt, int n_steps, float* ms, int* launches)

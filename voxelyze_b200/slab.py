@@ -94,12 +94,18 @@ class EnsembleRunner(SingleRunner):
         self.sim.set_temperature_all(scenarios.robot_temperature(self.sim.time()))
 
     def step(self, dt: float, n: int):
-        div = None
-        for _ in range(n):
+        """n == 1: the two calls a user of the class API makes per step (setAmbientTemperature, doTimeStep -- bench.py's e2e leg);
+        n > 1: the same program handed over in one call (vx_step_ambient: one launch per step, no host round trip in between).
+        The device accumulates the simulated time in float (src/Voxelyze.cpp:282); so does the program here, so both ways
+        set the same temperatures."""
+        if n == 1:
             self._advance(dt)
-            d = self.sim.step(dt, 1)
-            div = d if d is not None else div
-        return div
+            return self.sim.step(dt, 1)
+        t, temps = np.float32(self.sim.time()), []
+        for _ in range(n):
+            temps.append(scenarios.robot_temperature(float(t)))
+            t = np.float32(t + np.float32(dt))
+        return self.sim.step_ambient(dt, temps)
 
     def step_profile(self, dt: float, n: int):
         tot, launches = None, None
