@@ -98,3 +98,13 @@ def test_state_moves_between_handles_with_its_clock(product):
         for f in VOXEL_FIELDS:
             assert parity.bit_equal(dst.download(f), a.download(f)), (f, type(dst).__name__)
         src = dst
+
+
+def test_slabbed_poisson_one_slab_per_device(product):
+    """Poisson strains through the peer stores between DEVICES: all slabs queued (n steps each) before any is waited for."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    n_dev = min(_gpus(), 4)
+    sc = poisson_scenario()
+    whole, multi, dt = check_slabbed_against_whole(product, sc, list(range(n_dev)), 200, temperature_program=False, expect_halo=2, chunk=50, path=7)
+    assert parity.bit_equal(multi.download("pstrain"), whole.download("pstrain"))
