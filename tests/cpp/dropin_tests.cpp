@@ -864,6 +864,17 @@ static void slabbedDevices()            // facade extra: setDevices -- the class
     B.resetTime(); A.resetTime();
     for (int i = 0; i < 30; i++) { A.doTimeStep(dt); B.doTimeStep(dt); }
     CHECK(same());
+    // checkpoint of the slabbed object (one file per slab) into a freshly built one with the same cut
+    std::string path = g_tmpdir + "/dropin_slabbed_state";
+    CHECK(B.saveState(path.c_str()));
+    CVoxelyze C(0.005);
+    slabbedModel(C);
+    C.setDevices(std::vector<int>(2, 0));
+    CHECK(C.loadState(path.c_str()) && C.isSlabbed());
+    for (int i = 0; i < 25; i++) { B.doTimeStep(dt); C.doTimeStep(dt); }
+    bool resumed = true;
+    for (int i = 0; i < B.voxelCount(); i++) resumed = resumed && B.voxel(i)->position() == C.voxel(i)->position() && B.voxel(i)->velocity() == C.voxel(i)->velocity();
+    CHECK(resumed);
 }
 #endif
 

@@ -7,7 +7,7 @@ import pytest
 import parity
 from test_slab_gloo import _general_scenario
 from test_slabbed import check_slabbed_against_whole, check_state_edits, holes_scenario, poisson_scenario, VOXEL_FIELDS, LINK_FIELDS
-from voxelyze_b200 import scenarios
+from voxelyze_b200 import capi, scenarios
 
 pytestmark = pytest.mark.gpu
 
@@ -108,3 +108,23 @@ def test_slabbed_poisson_one_slab_per_device(product):
     sc = poisson_scenario()
     whole, multi, dt = check_slabbed_against_whole(product, sc, list(range(n_dev)), 200, temperature_program=False, expect_halo=2, chunk=50, path=7)
     assert parity.bit_equal(multi.download("pstrain"), whole.download("pstrain"))
+
+
+def test_slabbed_checkpoint_resume_is_bit_identical(product, tmp_path):
+    """vx_slabbed_save_state / load_state: one file per slab; a freshly built slabbed handle continues with the bits of the run
+    that never stopped (ghost planes and both generations are in the files: no exchange needed)."""
+    sc = _general_scenario()
+    a = scenarios.build_slabbed(product, sc, [0, 0, 0]); dt = a.recommended_dt()
+    assert a.step(dt, 77) is None
+    path = str(tmp_path / "slabbed_state")
+    a.save_state(path)
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["slabbed_state.0of3", "slabbed_state.1of3", "slabbed_state.2of3"]
+    assert a.step(dt, 50) is None
+    b = scenarios.build_slabbed(product, sc, [0, 0, 0])
+    b.load_state(path)
+    assert b.time() == pytest.approx(77 * dt, rel=1e-4) and b.step(dt, 50) is None
+    for f in VOXEL_FIELDS + LINK_FIELDS:
+        assert parity.bit_equal(a.download(f), b.download(f)), f
+    c = scenarios.build_slabbed(product, sc, [0, 0])             # another cut: refused (no such files)
+    with pytest.raises(capi.VxError):
+        c.load_state(path)

@@ -217,6 +217,8 @@ class VxLib:
             "vx_slabbed_download_voxel_state": (i32, [vp, i32, i32, vp]),
             "vx_slabbed_download_link_state": (i32, [vp, i32, i32, vp]),
             "vx_slabbed_upload_link_state": (i32, [vp, i32, i32, vp]),
+            "vx_slabbed_save_state": (i32, [vp, C.c_char_p]),
+            "vx_slabbed_load_state": (i32, [vp, C.c_char_p]),
             "vx_slabbed_launch_count": (C.c_int64, [vp]),
         }
         self.symbols = list(sig)
@@ -699,6 +701,12 @@ class SlabbedSim:
     def upload_link_state(self, rec: np.ndarray, first: int = 0):
         rec = np.ascontiguousarray(rec, dtype=Sim.LINK_STATE_DTYPE)
         self._chk(self.L.lib.vx_slabbed_upload_link_state(self.h, first, len(rec), rec.ctypes.data))
+
+    def save_state(self, path: str):
+        self._chk(self.L.lib.vx_slabbed_save_state(self.h, os.fsencode(path)))
+
+    def load_state(self, path: str):
+        self._chk(self.L.lib.vx_slabbed_load_state(self.h, os.fsencode(path)))
 
     def launch_count(self) -> int:
         return self.L.lib.vx_slabbed_launch_count(self.h)

@@ -569,6 +569,30 @@ int vx_slabbed_upload_link_state(vx_slabbed* m, int first, int count, const vx_l
     return m->poisson ? vxs::exchange_all(m) : VX_OK;
 }
 
+// dynamic-state checkpoint of a slabbed run: one vx_save_state file per slab, "<path>.<k>of<n>" (ghost planes and both
+// generations included, so a restored run continues without an exchange).  Restores into a handle built from the same model
+// with the same number of slabs.
+int vx_slabbed_save_state(vx_slabbed* m, const char* path)
+{
+    if (!m || !path) return VX_ERR_ARG;
+    for (int k = 0; k < m->active; k++) {
+        const std::string file = std::string(path) + "." + std::to_string(k) + "of" + std::to_string(m->active);
+        int rc = vx_save_state(m->slab[k], file.c_str()); if (rc != VX_OK) return vxs::fail_from(m, k, rc, "vx_save_state");
+    }
+    return VX_OK;
+}
+
+int vx_slabbed_load_state(vx_slabbed* m, const char* path)
+{
+    if (!m || !path) return VX_ERR_ARG;
+    for (int k = 0; k < m->active; k++) {
+        const std::string file = std::string(path) + "." + std::to_string(k) + "of" + std::to_string(m->active);
+        int rc = vx_load_state(m->slab[k], file.c_str());
+        if (rc != VX_OK) return vxs::fail_from(m, k, rc, "vx_load_state");      // (slabs before k are restored already: reload or reset)
+    }
+    return VX_OK;
+}
+
 int64_t vx_slabbed_launch_count(const vx_slabbed* m)
 {
     int64_t n = 0;

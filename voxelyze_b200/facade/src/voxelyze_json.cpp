@@ -348,12 +348,11 @@ bool CVoxelyze::saveJSON(const char* jsonFilePath)
 }
 
 // ---- dynamic state (additive; the reference cannot checkpoint)
-bool CVoxelyze::saveState(const char* path) { sync(); if (hm) notSlabbed("saveState"); return h && vx_save_state(h, path) == VX_OK; }
+bool CVoxelyze::saveState(const char* path) { sync(); return hm ? vx_slabbed_save_state(hm, path) == VX_OK : (h && vx_save_state(h, path) == VX_OK); }
 bool CVoxelyze::loadState(const char* path)
 {
     sync();
-    if (hm) notSlabbed("loadState");
-    if (!h || vx_load_state(h, path) != VX_OK) return false;
+    if (hm ? vx_slabbed_load_state(hm, path) != VX_OK : (!h || vx_load_state(h, path) != VX_OK)) return false;       // slabbed: one file per slab, same slab count
     stepped = true; epoch++;
     return true;
 }
