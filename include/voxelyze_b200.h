@@ -476,6 +476,9 @@ int  vx_slabbed_upload(vx_slabbed* m, int field, int first, int count, const voi
 int  vx_slabbed_download_voxel_state(vx_slabbed* m, int first, int count, vx_voxel_state* dst);
 int  vx_slabbed_download_link_state(vx_slabbed* m, int first, int count, vx_link_state* dst);
 int  vx_slabbed_upload_link_state(vx_slabbed* m, int first, int count, const vx_link_state* src);
+/* CVoxelyze::stateInfo of the whole model: voxel quantities reduced per slab on its device and combined, link quantities
+ * gathered in the whole model's numbering (a cut-crossing link lives in two slabs) and reduced on the host.            */
+int  vx_slabbed_state_info(vx_slabbed* m, int info, int type, float* out);
 /* checkpoint of a slabbed run: one vx_save_state file per slab, "<path>.<k>of<n>"; restores into a handle built from the
  * same model with the same number of slabs, and the run continues bit-identically.                                    */
 int  vx_slabbed_save_state(vx_slabbed* m, const char* path);

@@ -1088,7 +1088,10 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
         if (type == AVERAGE) ret /= (int)s->links.size();
     } else {
         if (s->vox.empty()) { *out = 0; return VX_OK; }
+        int counted = 0;
         for (auto& v : s->vox) {
+            if (v.ghost) continue;                       // halo copies are not voxels of this model (their owner counts them)
+            counted++;
             const VoxMat& m = s->vmats[v.mat];
             double sz = m.nom; V3 disp = sub(v.pos, V3{v.ix * sz, v.iy * sz, v.iz * sz});
             float val = 0;
@@ -1104,7 +1107,7 @@ int vx_state_info(vx_sim* s, int info, int type, float* out)
             }
             acc(val);
         }
-        if (type == AVERAGE) ret /= (int)s->vox.size();
+        if (type == AVERAGE && counted) ret /= counted;
     }
     *out = ret; return VX_OK;
 }

@@ -844,6 +844,17 @@ static void slabbedDevices()            // facade extra: setDevices -- the class
         CHECK(A.doTimeStep(dt) && B.doTimeStep(dt));
     }
     CHECK(same());
+    // stateInfo of the whole model while slabbed: voxel quantities reduced per slab and combined, link quantities gathered
+    CHECK(A.stateInfo(CVoxelyze::DISPLACEMENT, CVoxelyze::MAX) == B.stateInfo(CVoxelyze::DISPLACEMENT, CVoxelyze::MAX));
+    CHECK(A.stateInfo(CVoxelyze::ENG_STRAIN, CVoxelyze::MIN) == B.stateInfo(CVoxelyze::ENG_STRAIN, CVoxelyze::MIN));
+    const CVoxelyze::stateInfoType sums[4] = {CVoxelyze::STRAIN_ENERGY, CVoxelyze::KINETIC_ENERGY, CVoxelyze::MASS, CVoxelyze::ENG_STRESS};
+    for (int k = 0; k < 4; k++) {
+        float a = A.stateInfo(sums[k], CVoxelyze::TOTAL), b = B.stateInfo(sums[k], CVoxelyze::TOTAL);
+        CHECK(a != 0 && fabsf(a - b) <= 2e-5f * fabsf(a));
+        a = A.stateInfo(sums[k], CVoxelyze::AVERAGE); b = B.stateInfo(sums[k], CVoxelyze::AVERAGE);
+        CHECK(fabsf(a - b) <= 2e-5f * fabsf(a));
+    }
+    CHECK(B.isSlabbed());
     // per-voxel edits reach the owner and the ghost copies across the cuts (voxels of the planes next to a cut: z = 3, 4, 7, 8)
     CVoxelyze* both[2] = {&A, &B};
     for (CVoxelyze* V : both) {

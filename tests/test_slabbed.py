@@ -72,6 +72,10 @@ def check_slabbed_against_whole(lib, sc, devices, steps, temperature_program=Tru
         assert parity.bit_equal(multi.download(f), whole.download(f)), f
     for f in LINK_FIELDS:
         assert parity.bit_equal(multi.download(f), whole.download(f)), f
+    for info in range(10):                                   # CVoxelyze::stateInfo of the whole model (enum values of include/Voxelyze.h:48-67)
+        for typ in range(4):
+            a, b = multi.state_info(info, typ), whole.state_info(info, typ)
+            assert a == pytest.approx(b, rel=2e-5, abs=1e-30), (info, typ, a, b)
     n, nl = whole.n_voxels, whole.n_links
     for i in (0, n // 3, n - 1):                             # single elements come from the owning slab
         assert parity.bit_equal(multi.download("pos", i, 1), whole.download("pos", i, 1))

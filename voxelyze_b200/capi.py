@@ -217,6 +217,7 @@ class VxLib:
             "vx_slabbed_download_voxel_state": (i32, [vp, i32, i32, vp]),
             "vx_slabbed_download_link_state": (i32, [vp, i32, i32, vp]),
             "vx_slabbed_upload_link_state": (i32, [vp, i32, i32, vp]),
+            "vx_slabbed_state_info": (i32, [vp, i32, i32, P(f32)]),
             "vx_slabbed_save_state": (i32, [vp, C.c_char_p]),
             "vx_slabbed_load_state": (i32, [vp, C.c_char_p]),
             "vx_slabbed_launch_count": (C.c_int64, [vp]),
@@ -701,6 +702,11 @@ class SlabbedSim:
     def upload_link_state(self, rec: np.ndarray, first: int = 0):
         rec = np.ascontiguousarray(rec, dtype=Sim.LINK_STATE_DTYPE)
         self._chk(self.L.lib.vx_slabbed_upload_link_state(self.h, first, len(rec), rec.ctypes.data))
+
+    def state_info(self, info: int, typ: int) -> float:
+        v = C.c_float()
+        self._chk(self.L.lib.vx_slabbed_state_info(self.h, info, typ, C.byref(v)))
+        return v.value
 
     def save_state(self, path: str):
         self._chk(self.L.lib.vx_slabbed_save_state(self.h, os.fsencode(path)))

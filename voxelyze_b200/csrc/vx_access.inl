@@ -158,6 +158,14 @@ static int gather_link_field(vx_sim* s, int what, void* dst)
     return VX_OK;
 }
 
+// halo copies among the caller's voxels (z-slab handles): how many
+static int user_ghosts(const vx_sim* s)
+{
+    int n = 0;
+    if (!s->vflags.empty()) for (int v = 0; v < s->N_user; v++) n += (s->vflags[v] & VX_VF_GHOST) ? 1 : 0;
+    return n;
+}
+
 // per voxel (caller order) the caller index of its link in each of the six directions, the strain ratio of every link and
 // {E, nu} of every voxel: shared by the pressure reduction and the surface mesh
 static int ensure_vlinks(vx_sim* s)
@@ -175,6 +183,13 @@ static int ensure_vlinks(vx_sim* s)
     CK(cudaMemcpy(s->si_vlinks.p, vl.data(), vl.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->si_ratio.p, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->si_en.p, en.data(), en.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    s->si_skip.release();
+    if (user_ghosts(s)) {                                    // z-slab: halo copies are left out of the reductions
+        std::vector<unsigned char> sk(nu, 0);
+        for (size_t v = 0; v < nu; v++) sk[v] = (s->vflags[v] & VX_VF_GHOST) ? 1 : 0;
+        CK(s->si_skip.alloc(nu));
+        CK(cudaMemcpy(s->si_skip.p, sk.data(), nu, cudaMemcpyHostToDevice));
+    }
     s->si_pressure_ok = true;
     return VX_OK;
 }
@@ -188,7 +203,7 @@ static int state_info_impl(vx_sim* s, int info, int type, float* out, float* val
     if (!s || !out || info < 0 || info > SI_MASS || type < 0 || type > SI_AVERAGE) return VX_ERR_ARG;
     *out = 0.0f;
     const bool link_info = info == SI_STRAIN_ENERGY || info == SI_ENG_STRESS || info == SI_ENG_STRAIN;
-    const int count = link_info ? s->L : s->N_user;                 // fill cells of a box with holes are not voxels
+    const int count = link_info ? s->L : s->N_user - user_ghosts(s);       // fill cells of a box with holes and halo copies are not voxels
     if (count == 0) return VX_OK;                                  // src/Voxelyze.cpp:759,777
     { int rc = flush_ambient(s); if (rc != VX_OK) return rc; }
     CK(cudaSetDevice(s->device));
@@ -202,7 +217,7 @@ static int state_info_impl(vx_sim* s, int info, int type, float* out, float* val
         CK(s->si_buf.alloc((size_t)std::max(s->L, 1) * sizeof(float)));
         if (s->L) { int rc = gather_link_field(s, G_STRAIN, s->si_buf.p); if (rc != VX_OK) return rc; }
         k_state_pressure<<<grid, 256, 0, s->stream>>>(s->N_user, s->si_vlinks.p, (const float*)s->si_buf.p, s->si_ratio.p, s->si_en.p,
-                                                      s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p, vals);
+                                                      s->si_minmax.p, s->si_minmax.p + 1, s->si_sum.p, vals, s->si_skip.p);
         s->launches++;
     } else if (!link_info) {
         if (info == SI_DISPLACEMENT && !s->si_nominal_ok) {

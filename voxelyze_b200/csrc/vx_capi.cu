@@ -178,7 +178,7 @@ struct vx_sim {
     // stateInfo reductions
     DevBuf<float> si_minmax; DevBuf<double> si_sum; DevBuf<double4> si_nominal; DevBuf<float> si_consts; DevBuf<unsigned char> si_buf;
     bool si_nominal_ok = false, si_consts_ok = false, si_pressure_ok = false;
-    DevBuf<int> si_vlinks; DevBuf<float> si_ratio; DevBuf<float2> si_en;
+    DevBuf<int> si_vlinks; DevBuf<float> si_ratio; DevBuf<float2> si_en; DevBuf<unsigned char> si_skip;
     // surface mesh (vx_mesh.inl): topology tables built by vx_mesh_build, float buffers refreshed by vx_mesh_update
     struct Mesh {
         bool built = false; int n_vert = 0, n_quad = 0;
@@ -1007,7 +1007,7 @@ void vx_destroy(vx_sim* s)
     s->c_pair_force.release(); s->c_counters.release(); s->c_deg.release(); s->c_ref_start.release(); s->c_ref_fill.release(); s->c_refs.release();
     if (s->counters_host) cudaFreeHost(s->counters_host);
     s->si_minmax.release(); s->si_sum.release(); s->si_nominal.release(); s->si_consts.release(); s->si_buf.release();
-    s->si_vlinks.release(); s->si_ratio.release(); s->si_en.release(); s->mesh.release();
+    s->si_vlinks.release(); s->si_ratio.release(); s->si_en.release(); s->si_skip.release(); s->mesh.release();
     s->ext_idx.release(); s->ext_vox_dev.release(); s->vox_e2i_dev.release(); s->link_e2i_dev.release(); s->member_dev.release();
     s->pstrain.release(); s->slots.release(); s->slot_strain.release();
     s->lends.release(); s->lmeta.release(); s->lstA.release(); s->lstB.release(); s->lstC.release(); s->lstrain.release();

@@ -319,11 +319,13 @@ __global__ void __launch_bounds__(256) k_state_voxels(Frame f, int info, const d
 // axes of the voxel's strain (src/VX_Voxel.cpp:300-317: half-link strains, averaged when links exist on both sides), float.
 // vlinks[d * n + v]: caller index of the link of voxel v (caller order) in direction d or -1; strain: per-link axial strain;
 // ratio: CVX_Link::strainRatio (src/VX_Link.cpp:67); en: per voxel {E, nu}
+// skip (optional): 1 for the halo copies of a z-slab -- they are not voxels of this model (their owner counts them)
 __global__ void __launch_bounds__(256) k_state_pressure(int n, const int* vlinks, const float* strain, const float* ratio, const float2* en,
-                                                        float* out_min, float* out_max, double* out_sum, float* vals = nullptr)
+                                                        float* out_min, float* out_max, double* out_sum, float* vals = nullptr, const unsigned char* skip = nullptr)
 {
     StateAcc a; a.mn = 3.402823466e38f; a.mx = -3.402823466e38f; a.sum = 0.0;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        if (skip && skip[v]) { if (vals) vals[v] = 0.f; continue; }
         float s3[3] = {0.0f, 0.0f, 0.0f}; int cnt[3] = {0, 0, 0};
         for (int d = 0; d < 6; d++) {
             const int l = vlinks[(size_t)d * n + v];

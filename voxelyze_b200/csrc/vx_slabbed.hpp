@@ -39,6 +39,7 @@ struct vx_slabbed {
     std::string err;
     bool poisson = false;
     int N = 0, L = 0, z_origin = 0;
+    std::vector<uint16_t> mat;                            // material of every voxel (link quantities of vx_slabbed_state_info)
     std::vector<Part> part;
     std::vector<int32_t> owner, local;                    // per voxel of the model: owning slab, index there
     std::vector<int32_t> lneg, lpos; std::vector<uint8_t> laxis;
@@ -254,6 +255,7 @@ int vx_slabbed_set_voxels(vx_slabbed* m, int n, const int32_t* ijk, const uint16
         }
     }
     m->N = n; m->L = (int)m->lneg.size(); m->z_origin = lo[2]; m->active = act;
+    m->mat.assign(mat, mat + n);
     // voxels plane by plane, x fastest: every stored plane of a slab is one contiguous index range on both sides of a cut
     std::vector<int32_t> order; order.reserve(n);
     std::vector<int> plane_start((size_t)ez + 1, 0);
@@ -567,6 +569,59 @@ int vx_slabbed_upload_link_state(vx_slabbed* m, int first, int count, const vx_l
         if (m->link_slab2[i] >= 0) { rc = vx_upload_link_state(m->slab[m->link_slab2[i]], m->link_local2[i], 1, src + (i - first)); if (rc != VX_OK) return vxs::fail_from(m, m->link_slab2[i], rc, "vx_upload_link_state"); }
     }
     return m->poisson ? vxs::exchange_all(m) : VX_OK;
+}
+
+// CVoxelyze::stateInfo (src/Voxelyze.cpp:752-800) of the whole model.  Voxel quantities: every slab reduces its own voxels on
+// its device (ghost copies are skipped there) and the results are combined.  Link quantities: a link that crosses a cut lives
+// in two slabs, so the per-link values are gathered in the numbering of the whole model (the owner's copy) and reduced here.
+int vx_slabbed_state_info(vx_slabbed* m, int info, int type, float* out)
+{
+    enum { DISPLACEMENT, VELOCITY, KINETIC_ENERGY, ANGULAR_DISPLACEMENT, ANGULAR_VELOCITY, ENG_STRESS, ENG_STRAIN, STRAIN_ENERGY, PRESSURE, MASS };
+    enum { MIN, MAX, TOTAL, AVERAGE };
+    if (!m || !out || info < 0 || info > MASS || type < 0 || type > AVERAGE) return VX_ERR_ARG;
+    *out = 0.f;
+    if (m->active == 0) return VX_OK;
+    if (m->active == 1) { int rc = vx_state_info(m->slab[0], info, type, out); return rc == VX_OK ? rc : vxs::fail_from(m, 0, rc, "vx_state_info"); }
+    float ret = type == MAX ? -3.402823466e38f : (type == MIN ? 3.402823466e38f : 0.f);
+    if (info == STRAIN_ENERGY || info == ENG_STRESS || info == ENG_STRAIN) {
+        if (m->L == 0) return VX_OK;
+        std::vector<float> val(m->L);
+        if (info != STRAIN_ENERGY) {
+            int rc = vx_slabbed_download(m, info == ENG_STRESS ? VX_F_STRESS : VX_F_STRAIN, 0, m->L, val.data()); if (rc != VX_OK) return rc;
+        } else {
+            std::vector<double> fn((size_t)3 * m->L), mn((size_t)3 * m->L), mp((size_t)3 * m->L);
+            int rc = vx_slabbed_download(m, VX_F_FORCE_NEG, 0, m->L, fn.data());
+            if (rc == VX_OK) rc = vx_slabbed_download(m, VX_F_MOMENT_NEG, 0, m->L, mn.data());
+            if (rc == VX_OK) rc = vx_slabbed_download(m, VX_F_MOMENT_POS, 0, m->L, mp.data());
+            if (rc != VX_OK) return rc;
+            int n_mat = 0;
+            for (int i = 0; i < m->N; i++) n_mat = std::max(n_mat, (int)m->mat[i] + 1);
+            std::vector<vx_linkmat_row> rows((size_t)n_mat * n_mat);
+            std::vector<char> have((size_t)n_mat * n_mat, 0);
+            for (int l = 0; l < m->L; l++) {                      // CVX_Link::strainEnergy, src/VX_Link.cpp:251-257
+                const int a = m->mat[m->lneg[l]], b = m->mat[m->lpos[l]];
+                const size_t k = (size_t)std::min(a, b) * n_mat + std::max(a, b);
+                if (!have[k]) { rc = vx_get_linkmat(m->slab[0], a, b, &rows[k]); if (rc != VX_OK) return vxs::fail_from(m, 0, rc, "vx_get_linkmat"); have[k] = 1; }
+                const vx_linkmat_row& r = rows[k];
+                const double fx = fn[3 * (size_t)l], mnx = mn[3 * (size_t)l], mny = mn[3 * (size_t)l + 1], mnz = mn[3 * (size_t)l + 2], mpy = mp[3 * (size_t)l + 1], mpz = mp[3 * (size_t)l + 2];
+                val[l] = (float)(fx * fx / (2.0f * r.a1) + mnx * mnx / (2.0 * r.a2) + (mnz * mnz - mnz * mpz + mpz * mpz) / (3.0 * r.b3) + (mny * mny - mny * mpy + mpy * mpy) / (3.0 * r.b3));
+            }
+        }
+        double sum = 0.0;                                         // totals in double, like the one-device library (vx_collide.cuh)
+        for (int l = 0; l < m->L; l++) {
+            if (type == MIN) { if (val[l] < ret) ret = val[l]; } else if (type == MAX) { if (val[l] > ret) ret = val[l]; } else sum += (double)val[l];
+        }
+        *out = type == TOTAL ? (float)sum : (type == AVERAGE ? (float)sum / m->L : ret);
+        return VX_OK;
+    }
+    double total = 0.0;
+    for (int k = 0; k < m->active; k++) {
+        float v = 0.f;
+        int rc = vx_state_info(m->slab[k], info, type == AVERAGE ? TOTAL : type, &v); if (rc != VX_OK) return vxs::fail_from(m, k, rc, "vx_state_info");
+        if (type == MIN) ret = std::min(ret, v); else if (type == MAX) ret = std::max(ret, v); else total += v;
+    }
+    *out = type == TOTAL ? (float)total : (type == AVERAGE ? (float)total / m->N : ret);
+    return VX_OK;
 }
 
 // dynamic-state checkpoint of a slabbed run: one vx_save_state file per slab, "<path>.<k>of<n>" (ghost planes and both

@@ -105,7 +105,7 @@ public:
     // several GPUs of this process: the lattice is cut into z-slabs, one per listed device (vx_slabbed_*, include/voxelyze_b200.h),
     // doTimeStep and the voxel / link accessors work in the numbering of the whole model, bits as on one device.  May be called
     // at any time: dynamic state moves with the model.  Not available while slabbed (the call aborts with a message; setDevices
-    // with one device first): self-collisions, stateInfo, the mesh, the static solve, handle().  saveState / loadState of a
+    // with one device first): self-collisions, the mesh, the static solve, handle().  saveState / loadState of a
     // slabbed object write / read one file per slab ("<path>.<k>of<n>").
     // The environment variable VX_DEVICES ("0,1,2,3") sets the initial list, so that an unmodified caller of the class API
     // reaches every GPU; a list that came from there is a wish: a model or a call that cannot run slabbed moves the model to

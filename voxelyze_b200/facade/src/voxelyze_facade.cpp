@@ -895,8 +895,7 @@ float CVoxelyze::stateInfo(stateInfoType info, valueType type)
 {
     sync();
     float v = 0.0f;
-    if (hm) notSlabbed("stateInfo");
-    int rc = vx_state_info(h, (int)info, (int)type, &v);
+    int rc = VXH(this, state_info, (int)info, (int)type, &v);
     if (rc != VX_OK && rc != VX_ERR_UNSUPPORTED) die("vx_state_info");
     return v;
 }
