@@ -178,6 +178,27 @@ def robots_program(sim, k, t):
     sim.set_temperature_all(scenarios.robot_temperature(t))
 
 
+# the scenarios of the z-slab tests (tests/test_slab_gloo.py, tests/test_slabbed.py), as whole models: what the slabbed runs are
+# compared with is itself pinned to the reference
+def _slab_general():
+    from test_slab_gloo import _general_scenario
+    return _general_scenario()
+
+
+def _slab_holes():
+    from test_slabbed import holes_scenario
+    return holes_scenario()
+
+
+def _slab_poisson():
+    from test_slabbed import poisson_scenario
+    return poisson_scenario()
+
+
+def _slab_program(sim, k, t):
+    sim.set_temperature_all(3.0 * np.sin(k / 10.0))
+
+
 CASES = [
     Case("c1_cantilever", scenarios.cantilever, 10000),
     Case("single_bond_axial", single_bond(), 300),
@@ -197,5 +218,8 @@ CASES = [
     Case("poisson_mixed_bilinear", poisson_mixed_bilinear, 500, smooth=False, tol=1e-6),
     Case("collide_two", collide_two, 300, smooth=False, tol=1e-6),
     Case("plates_16x4x2", lambda: scenarios.plate_stack(16, 4, 2, 3, 2, tip_load=0.5), 3000, smooth=False, tol=1e-6),
+    Case("slab_general", _slab_general, 120, program=_slab_program, smooth=False, tol=1e-7),
+    Case("slab_holes", _slab_holes, 150, smooth=False, tol=1e-7),
+    Case("slab_poisson", _slab_poisson, 150, smooth=False, tol=1e-6),
 ]
 BY_NAME = {c.name: c for c in CASES}
