@@ -1417,6 +1417,7 @@ const char* vx_kernel_name(const vx_sim* s)
         const int bx = (s->nx + VX_WB_X - 1) / VX_WB_X, by = (s->ny + VX_WB_Y - 1) / VX_WB_Y, bz = (s->nz + VX_WB_Z - 1) / VX_WB_Z;
         tma = (double)((bx + 1) / 2) * ((by + 1) / 2) * ((bz + 1) / 2) * 8 <= 1.1 * (double)bx * by * bz;
     }
+    if (s->any_poisson || s->n_groups > 0) tma = true;            // Poisson coupling and brick-group lists live in the TMA-staged kernel only
     if (s->ghost_skip) return "k_lattice_tma<GSKIP> (fused link+voxel, 4x4x2 brick per warp, TMA staging, z-slab: no bricks on the ghost planes, 1 launch per step part)";
     return tma ? "k_lattice_tma (fused link+voxel, 4x4x2 brick per warp, TMA staging, 1 launch per step)"
                : "k_lattice_warp (fused link+voxel, 4x4x2 brick per warp, cp.async staging, 1 launch per step)";
