@@ -1008,8 +1008,9 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
             case VX_F_TEMP: f[k] = v.temp; break;
             case VX_F_VOXFLAGS: u[k] = (v.floorStatic ? VX_VF_STATIC_FRICTION : 0) | (s->isSurface(v) ? VX_VF_SURFACE : 0) | (v.ghost ? VX_VF_GHOST : 0) |
                                        (v.floorOverride == 0 ? VX_VF_FLOOR_OFF : 0) | (v.floorOverride == 1 ? VX_VF_FLOOR_ON : 0); break;
-            case VX_F_PSTRAIN: { if (!v.ghost) s->poissonsStrain(const_cast<Voxel&>(v));        // what the links of the next step will read (cached until the voxel moves, VX_Voxel.cpp:336-343)
-                                 f[3 * k] = v.pStrain.x; f[3 * k + 1] = v.pStrain.y; f[3 * k + 2] = v.pStrain.z; break; }
+            case VX_F_PSTRAIN: {       // what the links of the next step will read (VX_Voxel.cpp:336-343), without touching the cache: reading must not change when it is filled
+                                 const V3f p = (v.pInvalid && !v.ghost) ? s->voxelStrain(const_cast<Voxel&>(v), true) : v.pStrain;
+                                 f[3 * k] = p.x; f[3 * k + 1] = p.y; f[3 * k + 2] = p.z; break; }
             default: return VX_ERR_ARG;
             }
         } else {

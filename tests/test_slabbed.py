@@ -150,6 +150,12 @@ def test_slabbed_poisson_materials(built):
         assert s.step(dt, 60) is None
     for f in VOXEL_FIELDS + LINK_FIELDS:
         assert parity.bit_equal(multi.download(f), whole.download(f)), f
+    stiffer = poisson_scenario().materials; stiffer[0].nu = 0.4; stiffer[1].E = 3e6      # and changed again, still non-zero
+    for s in (whole, multi):
+        s.set_materials(stiffer)
+        assert s.step(dt, 40) is None
+    for f in VOXEL_FIELDS + LINK_FIELDS:
+        assert parity.bit_equal(multi.download(f), whole.download(f)), f
 
 
 def test_slabbed_state_edits_reach_every_copy(built):

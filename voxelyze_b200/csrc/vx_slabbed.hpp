@@ -200,9 +200,9 @@ int vx_slabbed_set_materials(vx_slabbed* m, int n, const vx_material_desc* descs
     m->poisson = poisson;
     // a voxel's Poisson strain needs all of its links (src/VX_Voxel.cpp:300-374); a ghost copy does not have them and takes
     // its owner's value through the halo -- also right after Poisson's ratio was switched on mid-run
-    if (!changed || m->active < 2) return VX_OK;
-    if (m->halo == 2) { vxs::detach_all(m); m->halo = vxs::connect_peers(m) ? 2 : 1; }      // the peer mappings cover the Poisson strain arrays only when they exist
-    return poisson ? vxs::exchange_all(m) : VX_OK;
+    if (m->active < 2) return VX_OK;
+    if (changed && m->halo == 2) { vxs::detach_all(m); m->halo = vxs::connect_peers(m) ? 2 : 1; }      // the peer mappings cover the Poisson strain arrays only when they exist
+    return poisson ? vxs::exchange_all(m) : VX_OK;           // every slab has just rebuilt its Poisson strains from its own links
 }
 
 int vx_slabbed_set_gravity(vx_slabbed* m, float g)
