@@ -134,3 +134,18 @@ def test_slabbed_checkpoint_resume_is_bit_identical(product, tmp_path):
     c = scenarios.build_slabbed(product, sc, [0, 0])             # another cut: refused (no such files)
     with pytest.raises(capi.VxError):
         c.load_state(path)
+
+
+def test_slabbed_model_cut_again_with_another_slab_count(product):
+    """vx_slabbed_set_voxels on a handle that has been stepping: a thin model on two of three slabs, then a tall one on all three --
+    the slab that sat idle joins with a fresh exchange count."""
+    thin, tall = scenarios.cantilever(8, 4, 5, tip_load=5.0), scenarios.cantilever(8, 4, 14, tip_load=5.0)
+    m = scenarios.build_slabbed(product, thin, [0, 0, 0])
+    assert m.n_slabs == 2 and m.step(m.recommended_dt(), 25) is None
+    m.set_voxels(tall.ijk, tall.mat)
+    m.set_externals(tall.ext_voxel, tall.ext_dof, tall.ext_force)
+    assert m.n_slabs == 3 and m.halo_mode == 2
+    whole = scenarios.build(product, tall, path=7); dt = whole.recommended_dt()
+    assert m.step(dt, 60) is None and whole.step(dt, 60) is None
+    for f in VOXEL_FIELDS:
+        assert parity.bit_equal(m.download(f), whole.download(f)), f

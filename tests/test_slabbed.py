@@ -176,3 +176,17 @@ def test_slabbed_divergence_and_refusals(built):
     assert scenarios.build_slabbed(lib, thin, [0, 0, 0]).n_slabs == 1
     with pytest.raises(ValueError):
         scenarios.build_slabbed(lib, scenarios.plate_stack(8, 8, 2, thick=2, gap=1), [0, 0])       # self-collisions
+
+
+def test_slabbed_model_cut_again_with_another_slab_count(built):
+    lib = capi.load_oracle()
+    thin, tall = scenarios.cantilever(8, 4, 5, tip_load=5.0), scenarios.cantilever(8, 4, 14, tip_load=5.0)
+    m = scenarios.build_slabbed(lib, thin, [0, 0, 0])
+    assert m.n_slabs == 2 and m.step(m.recommended_dt(), 25) is None
+    m.set_voxels(tall.ijk, tall.mat)
+    m.set_externals(tall.ext_voxel, tall.ext_dof, tall.ext_force)
+    assert m.n_slabs == 3
+    whole = scenarios.build(lib, tall); dt = whole.recommended_dt()
+    assert m.step(dt, 60) is None and whole.step(dt, 60) is None
+    for f in VOXEL_FIELDS:
+        assert parity.bit_equal(m.download(f), whole.download(f)), f

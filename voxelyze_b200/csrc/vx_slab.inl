@@ -101,6 +101,10 @@ int vx_peer_detach(vx_sim* s)
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
     for (auto& pl : s->peers) for (void* q : pl.opened) if (q) cudaIpcCloseMemHandle(q);
     s->peers.clear(); s->expect_side[0] = s->expect_side[1] = false;
+    // exchange counting restarts with the next attachment: the slabs that meet then need not have the same history (a model
+    // that is cut again may use a slab that sat idle before)
+    s->xseq = 0;
+    if (s->peer_flags.p) cudaMemset(s->peer_flags.p, 0, 4 * sizeof(int));
     return VX_OK;
 }
 
