@@ -249,6 +249,7 @@ struct vx_sim {
         f.groups = n_groups > 0 ? group_list.p : nullptr;
         f.c_ps = any_poisson ? ps[g].p : nullptr; f.n_ps = any_poisson ? ps[g ^ 1].p : nullptr;
         f.z_lo = ghost_skip ? z_lo : 0; f.z_hi = ghost_skip ? z_hi : nz;
+        f.stream_out = (size_t)N * 608 > ((size_t)96 << 20) && !getenv("VX_NO_STREAM_STORES");      // 608 B of state per voxel against the 126 MB L2
         f.push_z[0] = f.push_z[1] = -1; f.push_ps[0] = f.push_ps[1] = nullptr;
         if (push_in_kernel) {
             for (size_t k = 0; k < peers.size() && k < 2; k++) {
@@ -613,7 +614,7 @@ static int ensure_graph(vx_sim* s)
 // ------------------------------------------------------------------------------------------------
 // stepping, lattice mode
 #ifndef VX_TMA_L2PROMO
-#define VX_TMA_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#define VX_TMA_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_256B      // 256 B against 128 B: 2.618 -> 2.615 ms/step at 256^3 (profiles/r2_ablation_cache_hints.log)
 #endif
 // ---- tensor maps of the lattice arrays for k_lattice_tma (u64 elements; members stacked along z) --------------
 static int build_tensor_maps(vx_sim* s)

@@ -64,6 +64,7 @@ struct LatFrame {
     // Poisson coupling (nu != 0, k_lattice_tma<.., POISSON>): CVX_Voxel::pStrain of every voxel as of the state the step reads
     // (= computed from the link strains of the previous step), double-buffered like the voxel state
     const float4* c_ps; float4* n_ps;
+    bool stream_out;                    // k_lattice_tma: the state does not fit the L2, results are stored with st.global.cs (st_out)
     float4* push_ps[2];                 // with PUSH: the neighbours' ghost planes in their pStrain arrays of the generation being written
     // z-slab runs on k_lattice_tma<.., GSKIP>: bricks cover the planes [z_lo, z_hi) only -- the all-ghost planes below and above
     // are data, not work (brick origins are shifted by z_lo; 0 / nz everywhere else)
@@ -607,6 +608,18 @@ enum { TM_P_OWN, TM_P_XF, TM_P_YF, TM_P_ZF, TM_M0, TM_M1, TM_REC_OWN, TM_REC_XF,
 #define VX_TMA_SMEM (VX_WB_WARPS * VX_TMA_WARP_BYTES)
 #define VX_TMA_TABLE_BYTES 6144                         // room for staged material tables behind the warp windows (2 CTAs/SM still fit)
 
+// stores of a step's results: nothing reads them before the next step.  On lattices whose state does not fit the L2 (stream:
+// LatFrame::stream_out) that is ~10 GB of other traffic later, and st.global.cs keeps them from pushing the face data that
+// neighbouring bricks are about to read out of L2 (256^3: 2.644 -> 2.618 ms/step, profiles/r2_ablation_cache_hints.log);
+// smaller lattices keep plain stores, their next step finds the results in L2
+__device__ __forceinline__ void st_out(double2* p, const double2& v, bool stream) { if (stream) __stcs(p, v); else *p = v; }
+__device__ __forceinline__ void st_out(float4* p, const float4& v, bool stream) { if (stream) __stcs(p, v); else *p = v; }
+__device__ __forceinline__ void st_out(double4* p, const double4& v, bool stream)
+{
+    if (stream) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(v.z, v.w)); }
+    else *p = v;
+}
+
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred;
@@ -643,6 +656,25 @@ __device__ __forceinline__ void tma_4d(uint32_t dst, const void* map, uint32_t b
 {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// the same copies with an L2 eviction hint: a brick's own link records and momenta are read exactly once per step, so they
+// need not stay in L2 behind the poses, which neighbouring bricks read again as faces (VX_REC_EVICT_FIRST)
+__device__ __forceinline__ uint64_t l2_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_3d_hint(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_4d_hint(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol) : "memory");
 }
 
 // Grid: grouped (large lattices) -> 3-D, one CTA per 2x2x2 group of bricks: blockIdx = (group x, group y, member * nbz + group layer);
@@ -707,7 +739,11 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         tma_4d(sb + 11776, map(TM_REC_YF), bar0, 2 * x0, y0 - 1, Z0, 4);
         tma_4d(sb + 12288, map(TM_REC_ZF), bar0, 2 * x0, y0, Z0 - 1, 8);
         mbar_expect(bar1, 6144 + 1024);
+#ifdef VX_REC_EVICT_FIRST
+        tma_4d_hint(sb + 2048, map(TM_REC_OWN), bar1, 2 * x0, y0, Z0, 0, l2_evict_first());
+#else
         tma_4d(sb + 2048, map(TM_REC_OWN), bar1, 2 * x0, y0, Z0, 0);
+#endif
         tma_4d(sb + 8192, map(TM_P_XF), bar1, 4 * (x0 + VX_WB_X), y0, Z0, 0);
         tma_4d(sb + 8704, map(TM_P_YF), bar1, 4 * x0, y0 + VX_WB_Y, Z0, 0);
     }
@@ -819,8 +855,14 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         const unsigned char* tm = tmaps + (size_t)parity * TM_COUNT * 128;
         mbar_expect(bar2, 1024 + 1024 + 512);
         tma_4d(sb + 10752, tm + TM_P_ZF * 128, bar2, 4 * x0, y0, Z0 + VX_WB_Z, 0);
+#ifdef VX_REC_EVICT_FIRST
+        const uint64_t once = l2_evict_first();
+        tma_3d_hint(sb + 11776, tm + TM_M0 * 128, bar2, 4 * x0, y0, Z0, once);
+        tma_3d_hint(sb + 12800, tm + TM_M1 * 128, bar2, 2 * x0, y0, Z0, once);
+#else
         tma_3d(sb + 11776, tm + TM_M0 * 128, bar2, 4 * x0, y0, Z0);
         tma_3d(sb + 12800, tm + TM_M1 * 128, bar2, 2 * x0, y0, Z0);
+#endif
     }
     __syncwarp();
     mbar_wait(bar1);
@@ -868,7 +910,7 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
             double2 wa, wb, wc; float4 ws; uint32_t lf;
             lat_encode(st, wa, wb, wc, ws, lf);
             double2* nr = f.n_rec[0][0] + (size_t)(a * 4) * f.n_vox + v;
-            nr[0] = wa; nr[f.n_vox] = wb; nr[2 * (size_t)f.n_vox] = wc; *reinterpret_cast<float4*>(nr + 3 * (size_t)f.n_vox) = ws;
+            st_out(nr, wa, f.stream_out); st_out(nr + f.n_vox, wb, f.stream_out); st_out(nr + 2 * (size_t)f.n_vox, wc, f.stream_out); st_out(reinterpret_cast<float4*>(nr + 3 * (size_t)f.n_vox), ws, f.stream_out);
             new_bits = (new_bits & ~(3u << (VM_LFLAG_SHIFT + 2 * a))) | (lf << (VM_LFLAG_SHIFT + 2 * a));
             if (st.strain > 100) p->div_flag[parity] = 1;          // src/Voxelyze.cpp:265
             F = F + fN; M = M + mN;
@@ -930,10 +972,10 @@ k_lattice_tma(LatFrame f, const unsigned char* tmaps, int parity, int first_of_c
         }
         voxel_integrate(vs, F, M, refs, n_refs, f.col_force, vm, ext, dt, floor_on != 0);
     }
-    f.n_pose0[v] = make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w);
-    f.n_pose1[v] = make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits));
-    f.n_mom0[v] = make_double4(vs.lin.x, vs.lin.y, vs.lin.z, vs.ang.x);
-    f.n_mom1[v] = make_double2(vs.ang.y, vs.ang.z);
+    st_out(f.n_pose0 + v, make_double4(vs.pos.x, vs.pos.y, vs.pos.z, vs.orient.w), f.stream_out);
+    st_out(f.n_pose1 + v, make_double4(vs.orient.x, vs.orient.y, vs.orient.z, meta_pack(vs.temp, vs.bits)), f.stream_out);
+    st_out(f.n_mom0 + v, make_double4(vs.lin.x, vs.lin.y, vs.lin.z, vs.ang.x), f.stream_out);
+    st_out(f.n_mom1 + v, make_double2(vs.ang.y, vs.ang.z), f.stream_out);
     // halo push fused into the step (z-slab runs): posted stores over NVLink; the receiver owns the upper half of pose1.w
 #pragma unroll
     for (int k = 0; k < 2; k++) {
