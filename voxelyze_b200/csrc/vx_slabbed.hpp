@@ -93,6 +93,7 @@ static int host_exchange(vx_slabbed* m)
             const int sf = src.plane_first[z - src.lo], sn = src.plane_first[z - src.lo + 1] - sf;
             const int df = dst.plane_first[z - dst.lo], dn = dst.plane_first[z - dst.lo + 1] - df;
             if (sn != dn) return fail(m, VX_ERR_TOPOLOGY, "slab planes of different size");
+            if (sn == 0) continue;                                             // the body has no voxels in this plane
             for (int f = 0; f < n_fields; f++) {
                 buf.resize((size_t)sn * 4);
                 int rc = vx_download(m->slab[ks], fields[f], sf, sn, buf.data()); if (rc != VX_OK) return fail_from(m, ks, rc, "vx_download");
