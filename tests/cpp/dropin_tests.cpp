@@ -869,6 +869,8 @@ static void slabbedDevices()            // facade extra: setDevices -- the class
     CHECK(float_eq(A.stateInfo(CVoxelyze::DISPLACEMENT, CVoxelyze::MAX), B.stateInfo(CVoxelyze::DISPLACEMENT, CVoxelyze::MAX)));
     for (int i = 0; i < 60; i++) { A.doTimeStep(dt); B.doTimeStep(dt); }
     CHECK(same());
+    A.voxel(2, 2, 6)->external()->setForce(0.0f, 0.0f, 0.004f);    // an edit that is still pending when the model moves
+    B.voxel(2, 2, 6)->external()->setForce(0.0f, 0.0f, 0.004f);
     B.setDevices(std::vector<int>(2, 0));                           // and out again, mid-run
     for (int i = 0; i < 60; i++) { A.doTimeStep(dt); B.doTimeStep(dt); }
     CHECK(B.isSlabbed() && same());
@@ -880,6 +882,7 @@ static void slabbedDevices()            // facade extra: setDevices -- the class
     CHECK(B.saveState(path.c_str()));
     CVoxelyze C(0.005);
     slabbedModel(C);
+    C.voxel(2, 2, 6)->external()->setForce(0.0f, 0.0f, 0.004f);    // the same model, edit included: a state file of another model is refused
     C.setDevices(std::vector<int>(2, 0));
     CHECK(C.loadState(path.c_str()) && C.isSlabbed());
     for (int i = 0; i < 25; i++) { B.doTimeStep(dt); C.doTimeStep(dt); }

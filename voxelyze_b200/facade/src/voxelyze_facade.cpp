@@ -588,8 +588,8 @@ void CVoxelyze::notSlabbed(const char* what) const
 void CVoxelyze::setDevices(const std::vector<int>& cudaDevices)
 {
     if (cudaDevices.empty() || cudaDevices == devices) return;
-    const bool had = stepped && (h || hm) && !voxelsList.empty() && !topologyDirty;
-    if (had) { sync(); fetchAll(); fetchLinkState(); clockTime = VXH0(this, time); clockPending = true; }
+    const bool had = stepped && (h || hm) && !voxelsList.empty();
+    if (had) { sync(); fetchAll(); fetchLinkState(); clockTime = VXH0(this, time); clockPending = true; }      // (sync: pending edits are applied where the state is)
     destroyHandle();
     devices = cudaDevices; device = devices[0]; devicesFromEnv = false;
     topologyDirty = envDirty = true; matChangesSeen = ~0ull; extChangesSeen = ~0ull; envelopeSeen = 0.0f;
