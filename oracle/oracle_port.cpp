@@ -1143,8 +1143,39 @@ int vx_slab_exchange(vx_sim*) { return VX_ERR_UNSUPPORTED; }
 int vx_save_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
 int vx_load_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
 int vx_collision_forces(vx_sim*, int32_t*, float*, int, int*) { return VX_ERR_UNSUPPORTED; }
-int vx_download_link_state(vx_sim*, int, int, vx_link_state*) { return VX_ERR_UNSUPPORTED; }
-int vx_upload_link_state(vx_sim*, int, int, const vx_link_state*) { return VX_ERR_UNSUPPORTED; }
+// what CVX_Link keeps between steps (VX_Link.h:74-107): everything else a link holds (forces, the two quaternions, rest length,
+// transverse strain sums) is recomputed by the next updateForces before it is read
+int vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst)
+{
+    if (!s || !dst || first < 0 || count < 0 || first + count > (int)s->links.size()) return VX_ERR_ARG;
+    for (int k = 0; k < count; k++) {
+        const Link& l = s->links[first + k]; const LinkMat& m = s->lmats[l.lmat];
+        vx_link_state& r = dst[k];
+        memset(&r, 0, sizeof(r));
+        r.pos2[0] = l.pos2.x; r.pos2[1] = l.pos2.y; r.pos2[2] = l.pos2.z;
+        r.angle1v[0] = l.a1v.x; r.angle1v[1] = l.a1v.y; r.angle1v[2] = l.a1v.z;
+        r.angle2v[0] = l.a2v.x; r.angle2v[1] = l.a2v.y; r.angle2v[2] = l.a2v.z;
+        r.strain = l.strain; r.max_strain = l.maxStrain; r.strain_offset = l.strainOffset; r.stress = l.stress;
+        uint32_t fl = 0;
+        vx_download(s, VX_F_LINKFLAGS, first + k, 1, &fl);
+        r.flags = fl; (void)m;
+    }
+    return VX_OK;
+}
+int vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* src)
+{
+    if (!s || !src || first < 0 || count < 0 || first + count > (int)s->links.size()) return VX_ERR_ARG;
+    for (int k = 0; k < count; k++) {
+        Link& l = s->links[first + k]; const vx_link_state& r = src[k];
+        l.pos2 = V3{r.pos2[0], r.pos2[1], r.pos2[2]};
+        l.a1v = V3{r.angle1v[0], r.angle1v[1], r.angle1v[2]};
+        l.a2v = V3{r.angle2v[0], r.angle2v[1], r.angle2v[2]};
+        l.strain = r.strain; l.maxStrain = r.max_strain; l.strainOffset = r.strain_offset; l.stress = r.stress;
+        l.smallAngle = (r.flags & VX_LF_SMALL_ANGLE) != 0; l.velValid = (r.flags & VX_LF_LOCAL_VEL_VALID) != 0;
+    }
+    for (auto& v : s->vox) if (!v.ghost) v.pInvalid = true;          // Poisson strains follow the link strains (halo copies keep what their owner sent)
+    return VX_OK;
+}
 int64_t vx_launch_count(const vx_sim*) { return 0; }
 int vx_sync(vx_sim*) { return VX_OK; }
 int vx_set_path(vx_sim*, int) { return VX_OK; }
