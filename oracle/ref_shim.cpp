@@ -342,7 +342,8 @@ int vx_download(vx_sim* s, int field, int first, int count, void* dst)
             case VX_F_TEMP: f[k] = v->temp; break;
             case VX_F_VOXFLAGS: u[k] = (v->isFloorStaticFriction() ? VX_VF_STATIC_FRICTION : 0) | (v->isSurface() ? VX_VF_SURFACE : 0) |
                                        (s->floor_on && !v->isFloorEnabled() ? VX_VF_FLOOR_OFF : 0) | (!s->floor_on && v->isFloorEnabled() ? VX_VF_FLOOR_ON : 0); break;
-            case VX_F_PSTRAIN: f[3*k] = v->pStrain.x; f[3*k+1] = v->pStrain.y; f[3*k+2] = v->pStrain.z; break;
+            case VX_F_PSTRAIN: { const Vec3D<float> p = v->poissonsStrainInvalid ? v->strain(true) : v->pStrain;      // what the links of the next step will read, cache untouched
+                                 f[3*k] = p.x; f[3*k+1] = p.y; f[3*k+2] = p.z; break; }
             default: return VX_ERR_ARG;
             }
         } else {
@@ -382,6 +383,7 @@ int vx_upload(vx_sim* s, int field, int first, int count, const void* src)
         case VX_F_LINMOM: v->linMom = get3(d + 3*k); break;
         case VX_F_ANGMOM: v->angMom = get3(d + 3*k); break;
         case VX_F_TEMP: v->setTemperature(f[k]); break;
+        case VX_F_PSTRAIN: v->pStrain = Vec3D<float>(f[3*k], f[3*k+1], f[3*k+2]); v->poissonsStrainInvalid = false; break;
         case VX_F_VOXFLAGS: v->setFloorStaticFriction((u[k] & VX_VF_STATIC_FRICTION) != 0);
                             v->enableFloor((u[k] & VX_VF_FLOOR_OFF) ? false : ((u[k] & VX_VF_FLOOR_ON) ? true : s->floor_on)); break;
         default: return VX_ERR_ARG;
@@ -442,8 +444,36 @@ int vx_slab_exchange(vx_sim*) { return VX_ERR_UNSUPPORTED; }
 int vx_save_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
 int vx_load_state(vx_sim*, const char*) { return VX_ERR_UNSUPPORTED; }
 int vx_collision_forces(vx_sim*, int32_t*, float*, int, int*) { return VX_ERR_UNSUPPORTED; }
-int vx_download_link_state(vx_sim*, int, int, vx_link_state*) { return VX_ERR_UNSUPPORTED; }
-int vx_upload_link_state(vx_sim*, int, int, const vx_link_state*) { return VX_ERR_UNSUPPORTED; }
+// what CVX_Link keeps between steps (include/VX_Link.h:74-107), read from and written into the reference's own objects: with these
+// records (plus the voxel fields, the cached Poisson strains and the clock) a run of the UNMODIFIED reference can be moved into a
+// freshly built CVoxelyze and goes on bit for bit (tests/test_oracle.py) -- which is what the C-ABI's state-carrying calls rest on
+int vx_download_link_state(vx_sim* s, int first, int count, vx_link_state* dst)
+{
+    if (!s || !dst || first < 0 || count < 0 || first + count > (int)s->links.size()) return VX_ERR_ARG;
+    for (int k = 0; k < count; k++) {
+        const CVX_Link* l = s->links[first + k];
+        vx_link_state& r = dst[k];
+        memset(&r, 0, sizeof(r));
+        put3(r.pos2, l->pos2); put3(r.angle1v, l->angle1v); put3(r.angle2v, l->angle2v);
+        r.strain = l->strain; r.max_strain = l->maxStrain; r.strain_offset = l->strainOffset; r.stress = l->_stress;
+        r.flags = (l->smallAngle ? VX_LF_SMALL_ANGLE : 0) | (l->isLocalVelocityValid() ? VX_LF_LOCAL_VEL_VALID : 0)
+                | (l->isYielded() ? VX_LF_YIELDED : 0) | (l->isFailed() ? VX_LF_FAILED : 0);
+    }
+    return VX_OK;
+}
+int vx_upload_link_state(vx_sim* s, int first, int count, const vx_link_state* src)
+{
+    if (!s || !src || first < 0 || count < 0 || first + count > (int)s->links.size()) return VX_ERR_ARG;
+    for (int k = 0; k < count; k++) {
+        CVX_Link* l = s->links[first + k]; const vx_link_state& r = src[k];
+        l->pos2 = get3(r.pos2); l->angle1v = get3(r.angle1v); l->angle2v = get3(r.angle2v);
+        l->strain = r.strain; l->maxStrain = r.max_strain; l->strainOffset = r.strain_offset; l->_stress = r.stress;
+        l->smallAngle = (r.flags & VX_LF_SMALL_ANGLE) != 0;
+        l->setBoolState(CVX_Link::LOCAL_VELOCITY_VALID, (r.flags & VX_LF_LOCAL_VEL_VALID) != 0);
+    }
+    for (CVX_Voxel* v : s->vox) v->poissonsStrainInvalid = true;
+    return VX_OK;
+}
 int64_t vx_launch_count(const vx_sim*) { return 0; }
 int vx_sync(vx_sim*) { return VX_OK; }
 int vx_set_path(vx_sim*, int) { return VX_OK; }

@@ -178,3 +178,32 @@ def test_oracle_follows_the_reference_when_poissons_ratio_is_switched_on_mid_run
     assert dta == dtb
     for f in a:
         assert parity.bit_equal(a[f], b[f]), f
+
+
+@pytest.mark.parametrize("which", ["slab_general", "slab_poisson", "bilinear_yield", "large_deformation"])
+def test_a_run_of_the_unmodified_reference_moves_between_objects(reference, oracle, which):
+    """What the C-ABI's state-carrying calls (vx_upload, vx_upload_link_state, vx_set_clock; VX_F_PSTRAIN with Poisson materials)
+    rest on: these records ARE the persistent state of the reference's objects.  A run of the unmodified reference is read out
+    through them, written into a freshly built CVoxelyze, and both go on bit for bit -- and so does the restatement, fed with
+    the reference's records."""
+    case = cases.BY_NAME[which]
+    sc = case.make()
+    a = scenarios.build(reference, sc); dt = a.recommended_dt()
+    first = case.steps // 2
+    assert a.step(dt, first) is None
+    state = {f: a.download(f) for f in parity.VOXEL_FIELDS}
+    links, pstrain, clock = a.download_link_state(), a.download("pstrain"), a.time()
+    movers = [scenarios.build(reference, sc), scenarios.build(oracle, sc)]
+    for b in movers:
+        for f, v in state.items():
+            b.upload(f, v)
+        b.upload_link_state(links)
+        b.upload("pstrain", pstrain)
+        b.set_clock(clock, dt)
+    assert a.step(dt, case.steps - first) is None
+    sa = parity.snapshot(a)
+    for b in movers:
+        assert b.step(dt, case.steps - first) is None and b.time() == a.time()
+        sb = parity.snapshot(b)
+        for f in sa:
+            assert parity.bit_equal(sa[f], sb[f]), (f, b.L.backend)
