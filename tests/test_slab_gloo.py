@@ -149,3 +149,38 @@ def test_poisson_materials_split_into_slabs_bitwise(built, tmp_path):
     for f in ("pos", "orient", "pstrain"):
         stitched = np.concatenate([p[f] for p in parts])
         assert np.array_equal(stitched, whole.download(f)[index]), f
+
+
+def _worker_ensemble(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    robots = 6 // world                                   # bench.py --config c4: rank r holds robots [r * robots, (r + 1) * robots)
+    sc = scenarios.robot_ensemble(robots, 4, first_seed=rank * robots)
+    r = slab.EnsembleRunner(scenarios.build(capi.load_oracle(), sc), world)
+    dt = r.recommended_dt()
+    assert r.step(dt, 1) is None and r.step(dt, 59) is None          # the per-step calls of the e2e leg, then the program in one call
+    nv, nl = r.global_counts()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), pos=r.sim.download("pos"), orient=r.sim.download("orient"), temp=r.sim.download("temp"), dt=dt, nv=nv, nl=nl)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ensemble_shards_equal_the_whole_population_bitwise(built, tmp_path, world):
+    """BASELINE config C4 sharded like bench.py --config c4 does (no data-path communication, "replicas only"): the shards'
+    robots, stepped with the temperature program handed over in one call (vx_step_ambient), equal the same robots in one handle
+    stepped with setAmbientTemperature + doTimeStep in turn."""
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_ensemble, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
+    sc = scenarios.robot_ensemble(6, 4)
+    whole = scenarios.build(capi.load_oracle(), sc); dt = whole.recommended_dt()
+    assert np.float32(dt) == np.float32(parts[0]["dt"])
+    assert int(parts[0]["nv"]) == whole.n_voxels and int(parts[0]["nl"]) == whole.n_links
+    for _ in range(60):
+        whole.set_temperature_all(scenarios.robot_temperature(whole.time()))
+        assert whole.step(dt, 1) is None
+    for f in ("pos", "orient", "temp"):
+        assert np.array_equal(np.concatenate([p[f] for p in parts]), whole.download(f)), f
